@@ -1,0 +1,132 @@
+/*
+ * m3d_b200.h -- C ABI of the B200-native PixelDecoder hot path (libm3d_b200.so).
+ *
+ * The reference (QI2lab/merfish3d-analysis 0.13.0) has no FFI layer: its hot path is the
+ * Python class `PixelDecoder` calling CuPy / cuVS / cuCIM / scikit-image.  Each entry
+ * point below replaces the private method(s) cited beside it ("PD" =
+ * src/merfish3danalysis/PixelDecoder.py).  The host mirror of the class
+ * (merfish3d-analysis_b200/PixelDecoder.py) binds these with ctypes; INTEGRATION.md shows
+ * the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer named *_dev is DEVICE memory owned by the caller (torch tensors in the
+ *     Python host); the library never frees or retains it past the call's stream work.
+ *     Pointers named *_host are plain host memory read before the call returns.
+ *   - `stream` is a cudaStream_t passed as void*; calls enqueue on it and only synchronise
+ *     where a host-visible count is returned (documented per call).
+ *   - dims = {z, y, x}; image layout is C-order (bits, z, y, x) exactly like the
+ *     reference's `_image_data` (PD:1894).
+ *   - return value 0 = ok, negative = error; m3d_last_error() gives the text
+ *     (thread-local).  There is NO CPU fallback: every call fails if no CUDA device.
+ */
+#ifndef M3D_B200_H
+#define M3D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M3D_ABI_VERSION 1
+
+#define M3D_DTYPE_U16 0
+#define M3D_DTYPE_F32 1
+
+#define M3D_OK 0
+#define M3D_ERR_ARG -1
+#define M3D_ERR_CUDA -2
+#define M3D_ERR_CAPACITY -3
+#define M3D_ERR_STATE -4
+
+#define M3D_MAX_BITS 32
+/* feature-table columns before the per-bit means (see m3d_features) */
+#define M3D_TABLE_FIXED_COLS 14
+
+typedef struct m3d_ctx m3d_ctx;
+
+int m3d_abi_version(void);
+const char* m3d_last_error(void);
+
+/* PixelDecoder.__init__ / _normalize_codebook (PD:449-557, PD:879-906): one context per
+ * process/GPU.  codebook_unit_host = (K, n_bits) float32 unit codewords (the reference's
+ * `_decoding_matrix` cast to float32, PD:2497-2498); excluded_host = codeword row indices
+ * whose winning assignments are suppressed (PD:863-877). */
+int m3d_create(int device, int n_bits, int n_codewords, const float* codebook_unit_host,
+               const int32_t* excluded_host, int n_excluded, m3d_ctx** out);
+int m3d_destroy(m3d_ctx* ctx);
+
+/* _scale_pixel_traces vectors (PD:2577-2592).  NULL, NULL = decode unnormalised. */
+int m3d_set_normalization(m3d_ctx* ctx, const float* background_host,
+                          const float* normalization_host);
+/* pixel_assignment_threshold (PD:778-785) and magnitude_threshold (PD:2613-2614); compared
+ * in float32 like the reference (NEP-50 weak Python scalars). */
+int m3d_set_thresholds(m3d_ctx* ctx, float pixel_threshold, float magnitude_lo,
+                       float magnitude_hi);
+
+/* _load_bit_data weighting (PD:1879-1881): out = float32(readout) * float32(predictor). */
+int m3d_weight(m3d_ctx* ctx, const uint16_t* readout_dev, const float* predictor_dev,
+               int64_t n, float* out_dev, void* stream);
+
+/* _lp_filter / _lowpass_image (PD:1948-2024): per-volume Gaussian, reflect boundary,
+ * radius int(4*sigma+0.5), axis order z,y,x, fp64 accumulation, fp32 result per pass
+ * (scipy.ndimage.gaussian_filter semantics).  mode2d!=0 filters y,x only (per plane).
+ * in_dev = n_vols volumes of `in_dtype`; predictor_dev (nullable, float32, same shape) is
+ * multiplied in first (PD:1879-1881).  out_dev may not alias in_dev. */
+int m3d_lowpass(m3d_ctx* ctx, const void* in_dev, int in_dtype, const float* predictor_dev,
+                int n_vols, const int64_t dims[3], const double sigma[3], int mode2d,
+                float* out_dev, void* stream);
+
+/* _decode_pixels (PD:2523-2643) fused: scale -> clip -> L2 norm -> nearest codeword ->
+ * pixel gate -> magnitude gates -> exclusion.  decoded_dev int16 (z,y,x) is always
+ * written.  magnitude/distance (float16 (z,y,x)) and scaled (float16 (bits,z,y,x)) are
+ * the reference's result images after round(.,5); pass all three NULL for the
+ * production fast path (search only where the magnitude gate passes; features recompute
+ * what they need). */
+int m3d_decode(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t dims[3],
+               int16_t* decoded_dev, uint16_t* magnitude_f16_dev, uint16_t* distance_f16_dev,
+               uint16_t* scaled_f16_dev, void* stream);
+
+/* _extract_barcodes labelling + size filters (PD:2946-2989): equal-value connected
+ * components (26-conn 3D / 8-conn per plane when mode2d), drop area > maximum_pixels and
+ * area <= max(int(minimum_pixels)-1, 0).  Surviving components get canonical ids 0..n-1 in
+ * raster order of their first voxel.  labels_dev (nullable, int32 (z,y,x)) receives id+1
+ * (0 = background).  Synchronises the stream to return *n_features_out. */
+int m3d_label(m3d_ctx* ctx, const int16_t* decoded_dev, const int64_t dims[3], int mode2d,
+              double minimum_pixels, int maximum_pixels, int32_t* labels_dev,
+              int64_t* n_features_out, void* stream);
+
+/* _extract_barcodes regionprops (PD:2991-3062) for the components of the last m3d_label
+ * call, one row per component in canonical order.  table_dev = (n_rows, 14 + n_bits)
+ * float64, columns:
+ *   0 first_voxel (linear index)  1 area  2 decoded_id
+ *   3..5 centroid z,y,x           6..11 central 2nd moments zz,yy,xx,zy,zx,yx (sums)
+ *   12 distance_min               13 magnitude_mean      14.. per-bit intensity_mean
+ * optimize_mode=0: bit means over the float16 scaled image (result float16-rounded);
+ * optimize_mode=1: over the raw float32 input stack (PD:2935-2941). */
+int m3d_features(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t dims[3],
+                 const int16_t* decoded_dev, int optimize_mode, double* table_dev,
+                 int64_t n_rows, void* stream);
+
+/* _global_normalization_vectors order statistics (PD:1113-1177).  One radix-select pass:
+ * histogram of bits [shift, shift+11) of the order-preserving uint32 key of
+ * v = clip0 ? max(x - sub, 0) : x - sub, over elements whose key matches
+ * (key & prefix_mask) == prefix_value and that satisfy the predicate
+ * (pred 0: all, 1: v < cutoff, 2: v > cutoff).  hist_dev = 2048 uint64 counters,
+ * accumulated (caller zeroes).  */
+int m3d_select_hist(m3d_ctx* ctx, const float* data_dev, int64_t n, float sub, int clip0,
+                    int pred, float cutoff, uint32_t prefix_mask, uint32_t prefix_value,
+                    int shift, unsigned long long* hist_dev, void* stream);
+/* hot-pixel replacement (PD:1072-1074): data[data > threshold] = value, in place. */
+int m3d_replace_above(m3d_ctx* ctx, float* data_dev, int64_t n, float threshold, float value,
+                      void* stream);
+
+/* number of kernels this context has launched since creation (bench.py gpu_launches). */
+int64_t m3d_launch_count(m3d_ctx* ctx);
+/* name and cumulative launches of the i-th kernel family; NULL when i is out of range. */
+const char* m3d_kernel_name(int i);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M3D_B200_H */

@@ -1,0 +1,275 @@
+// api.cu -- context lifetime, normalisation state, order-statistic helpers (C ABI).
+#include <math.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+thread_local std::string g_m3d_error;
+
+int m3d_fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_m3d_error = buf;
+    return code;
+}
+
+static const char* const kKernelNames[KF_COUNT] = {
+    "weight_kernel",       "lowpass_z_kernel",    "lowpass_yx_kernel",   "lowpass_axis_generic_kernel",
+    "decode_gate_kernel",  "decode_search_kernel", "decode_dense_kernel", "ccl_collect_kernel",
+    "ccl_init_kernel",     "ccl_merge_kernel",    "ccl_compress_kernel", "ccl_select_kernel",
+    "cub_radix_sort",      "ccl_assign_kernel",   "cub_exclusive_sum",   "ccl_scatter_kernel",
+    "ccl_labels_kernel",   "features_kernel",     "select_hist_kernel",  "replace_above_kernel"};
+
+DecodeParams m3d_ctx::params() const {
+    DecodeParams P;
+    memset(&P, 0, sizeof(P));
+    for (int b = 0; b < M3D_MAX_BITS; ++b) {
+        P.bkg[b] = bkg[b];
+        P.nrm[b] = nrm[b];
+        P.rcp[b] = rcp[b];
+    }
+    P.pix_thr = pix_thr;
+    P.mag_lo = mag_lo;
+    P.mag_hi = mag_hi;
+    P.use_norm = use_norm;
+    P.n_bits = n_bits;
+    P.K = K;
+    P.max_on = max_on;
+    P.binary = binary;
+    P.codebook = d_codebook;
+    P.onbits = d_onbits;
+    P.cw_a = d_cw_a;
+    P.cw_g = d_cw_g;
+    P.cw_c = d_cw_c;
+    P.cw_mask = d_cw_mask;
+    P.excluded = d_excluded;
+    return P;
+}
+
+extern "C" int m3d_abi_version(void) { return M3D_ABI_VERSION; }
+extern "C" const char* m3d_last_error(void) { return g_m3d_error.c_str(); }
+
+extern "C" int m3d_create(int device, int n_bits, int n_codewords, const float* codebook_unit_host,
+                          const int32_t* excluded_host, int n_excluded, m3d_ctx** out) {
+    if (!out || !codebook_unit_host) return m3d_fail(M3D_ERR_ARG, "m3d_create: null argument");
+    if (n_bits < 1 || n_bits > M3D_MAX_BITS) return m3d_fail(M3D_ERR_ARG, "m3d_create: n_bits must be in [1, %d]", M3D_MAX_BITS);
+    if (n_codewords < 1 || n_codewords > 32767) return m3d_fail(M3D_ERR_ARG, "m3d_create: n_codewords must be in [1, 32767] (int16 decoded image)");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev < 1)
+        return m3d_fail(M3D_ERR_CUDA, "m3d_create: no CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= n_dev) return m3d_fail(M3D_ERR_ARG, "m3d_create: device %d of %d", device, n_dev);
+    M3D_CUDA(cudaSetDevice(device));
+    m3d_ctx* ctx = new m3d_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    M3D_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->n_bits = n_bits;
+    ctx->nb_pad = n_bits <= 16 ? 16 : (n_bits <= 24 ? 24 : 32);
+    ctx->K = n_codewords;
+    memset(ctx->launches, 0, sizeof(ctx->launches));
+    for (int b = 0; b < M3D_MAX_BITS; ++b) {
+        ctx->bkg[b] = 0.f;
+        ctx->nrm[b] = 1.f;
+        ctx->rcp[b] = 1.f;
+    }
+    const int K = n_codewords;
+    // padded codebook + structure analysis
+    std::vector<float> cb((size_t)K * M3D_MAX_BITS, 0.f);
+    std::vector<float> cw_a(K), cw_g(K), cw_c(K);
+    std::vector<uint32_t> mask(K, 0u);
+    int binary = 1, max_on = 1;
+    for (int k = 0; k < K; ++k) {
+        float cval = 0.f;
+        int n_on = 0;
+        double nn = 0.0;
+        for (int b = 0; b < n_bits; ++b) {
+            float v = codebook_unit_host[(size_t)k * n_bits + b];
+            cb[(size_t)k * M3D_MAX_BITS + b] = v;
+            nn += (double)v * (double)v;
+            if (v != 0.f) {
+                if (n_on == 0) cval = v;
+                else if (v != cval) binary = 0;
+                mask[k] |= (1u << b);
+                ++n_on;
+            }
+            if (!(v == v)) binary = 0;
+        }
+        if (n_on > max_on) max_on = n_on;
+        cw_a[k] = (float)nn;
+        cw_g[k] = 2.f * cval;
+        cw_c[k] = cval;
+    }
+    if (max_on > 16) binary = 0;  // proxy path keeps short on-bit lists only
+    ctx->binary = binary;
+    ctx->max_on = max_on;
+    std::vector<uint8_t> on((size_t)K * max_on, (uint8_t)ctx->nb_pad);  // pad -> zero slot
+    for (int k = 0; k < K; ++k) {
+        int j = 0;
+        for (int b = 0; b < n_bits && j < max_on; ++b)
+            if (mask[k] & (1u << b)) on[(size_t)k * max_on + j++] = (uint8_t)b;
+    }
+    std::vector<uint8_t> excl(K, 0);
+    for (int i = 0; i < n_excluded; ++i) {
+        if (!excluded_host) break;
+        int idx = excluded_host[i];
+        if (idx < 0 || idx >= K) {
+            delete ctx;
+            return m3d_fail(M3D_ERR_ARG, "m3d_create: excluded index %d out of range", idx);
+        }
+        excl[idx] = 1;
+    }
+#define UP(dst, vec, T)                                                                          \
+    M3D_CUDA(cudaMalloc((void**)&ctx->dst, vec.size() * sizeof(T)));                            \
+    M3D_CUDA(cudaMemcpy(ctx->dst, vec.data(), vec.size() * sizeof(T), cudaMemcpyHostToDevice));
+    UP(d_codebook, cb, float)
+    UP(d_onbits, on, uint8_t)
+    UP(d_cw_a, cw_a, float)
+    UP(d_cw_g, cw_g, float)
+    UP(d_cw_c, cw_c, float)
+    UP(d_cw_mask, mask, uint32_t)
+    UP(d_excluded, excl, uint8_t)
+#undef UP
+    *out = ctx;
+    return M3D_OK;
+}
+
+extern "C" int m3d_destroy(m3d_ctx* ctx) {
+    if (!ctx) return M3D_OK;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_codebook);
+    cudaFree(ctx->d_onbits);
+    cudaFree(ctx->d_cw_a);
+    cudaFree(ctx->d_cw_g);
+    cudaFree(ctx->d_cw_c);
+    cudaFree(ctx->d_cw_mask);
+    cudaFree(ctx->d_excluded);
+    ctx->s_cand.release();
+    ctx->s_counters.release();
+    ctx->s_lp_tmp.release();
+    ctx->s_fg.release();
+    ctx->s_parent.release();
+    ctx->s_aux.release();
+    ctx->s_roots.release();
+    ctx->s_area.release();
+    ctx->s_vox.release();
+    ctx->s_sort.release();
+    delete ctx;
+    return M3D_OK;
+}
+
+extern "C" int m3d_set_normalization(m3d_ctx* ctx, const float* background_host, const float* normalization_host) {
+    if (!ctx) return m3d_fail(M3D_ERR_ARG, "m3d_set_normalization: null ctx");
+    if (!background_host || !normalization_host) {
+        ctx->use_norm = 0;
+        ctx->safe_div = 0;
+        return M3D_OK;
+    }
+    ctx->use_norm = 1;
+    int safe = 0;
+    for (int b = 0; b < ctx->n_bits; ++b) {
+        const float bg = background_host[b], nm = normalization_host[b];
+        ctx->bkg[b] = bg;
+        ctx->nrm[b] = nm;
+        // correctly rounded reciprocal: double division rounded once more is innocuous for p=24
+        ctx->rcp[b] = (float)(1.0 / (double)nm);
+        const float an = fabsf(nm), ab = fabsf(bg);
+        // reciprocal-division preconditions (voxel_math.cuh): finite, mid-range divisor and a
+        // background large enough that (s - bkg) is either 0 or far from the subnormal range
+        if (!(an >= 9.3132257e-10f && an <= 1.0737418e9f)) safe = 1;
+        if (!(ab >= 9.5367432e-7f && ab <= 1.0e30f)) safe = 1;
+    }
+    ctx->safe_div = safe;
+    return M3D_OK;
+}
+
+extern "C" int m3d_set_thresholds(m3d_ctx* ctx, float pixel_threshold, float magnitude_lo, float magnitude_hi) {
+    if (!ctx) return m3d_fail(M3D_ERR_ARG, "m3d_set_thresholds: null ctx");
+    ctx->pix_thr = pixel_threshold;
+    ctx->mag_lo = magnitude_lo;
+    ctx->mag_hi = magnitude_hi;
+    return M3D_OK;
+}
+
+extern "C" int64_t m3d_launch_count(m3d_ctx* ctx) {
+    if (!ctx) return 0;
+    int64_t n = 0;
+    for (int i = 0; i < KF_COUNT; ++i) n += ctx->launches[i];
+    return n;
+}
+
+extern "C" const char* m3d_kernel_name(int i) { return (i >= 0 && i < KF_COUNT) ? kKernelNames[i] : nullptr; }
+
+// ------------------------------------------------------------------ order statistics (PD:1113-1177)
+namespace {
+
+__device__ __forceinline__ uint32_t ordered_key(float v) {
+    uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(256)
+select_hist_kernel(const float* __restrict__ data, size_t n, float sub, int clip0, int pred, float cutoff,
+                   uint32_t prefix_mask, uint32_t prefix_value, int shift, unsigned long long* __restrict__ hist) {
+    __shared__ unsigned int s_hist[2048];
+    for (int i = threadIdx.x; i < 2048; i += 256) s_hist[i] = 0u;
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        float v = __fsub_rn(__ldcs(data + i), sub);
+        if (clip0 && v < 0.f) v = 0.f;
+        bool ok = true;
+        if (pred == 1) ok = v < cutoff;
+        else if (pred == 2) ok = v > cutoff;
+        if (ok) {
+            const uint32_t key = ordered_key(v);
+            if ((key & prefix_mask) == prefix_value) atomicAdd(&s_hist[(key >> shift) & 2047u], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2048; i += 256)
+        if (s_hist[i]) atomicAdd(hist + i, (unsigned long long)s_hist[i]);
+}
+
+__global__ void __launch_bounds__(256)
+replace_above_kernel(float* __restrict__ data, size_t n, float thr, float value) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+        if (data[i] > thr) data[i] = value;
+}
+
+}  // namespace
+
+extern "C" int m3d_select_hist(m3d_ctx* ctx, const float* data_dev, int64_t n, float sub, int clip0, int pred,
+                               float cutoff, uint32_t prefix_mask, uint32_t prefix_value, int shift,
+                               unsigned long long* hist_dev, void* stream) {
+    if (!ctx || !data_dev || !hist_dev || n < 0) return m3d_fail(M3D_ERR_ARG, "m3d_select_hist: bad argument");
+    if (shift < 0 || shift > 31) return m3d_fail(M3D_ERR_ARG, "m3d_select_hist: shift %d", shift);
+    if (n == 0) return M3D_OK;
+    M3D_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    size_t want = ((size_t)n + 255) / 256;
+    size_t cap = (size_t)ctx->num_sms * 8;
+    int blocks = (int)(want < cap ? want : cap);
+    select_hist_kernel<<<blocks, 256, 0, st>>>(data_dev, (size_t)n, sub, clip0, pred, cutoff, prefix_mask,
+                                                prefix_value, shift, hist_dev);
+    M3D_CHECK_LAUNCH();
+    count_launch(ctx, KF_SELECT_HIST);
+    return M3D_OK;
+}
+
+extern "C" int m3d_replace_above(m3d_ctx* ctx, float* data_dev, int64_t n, float threshold, float value, void* stream) {
+    if (!ctx || !data_dev || n < 0) return m3d_fail(M3D_ERR_ARG, "m3d_replace_above: bad argument");
+    if (n == 0) return M3D_OK;
+    M3D_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    size_t want = ((size_t)n + 255) / 256;
+    size_t cap = (size_t)ctx->num_sms * 8;
+    int blocks = (int)(want < cap ? want : cap);
+    replace_above_kernel<<<blocks, 256, 0, st>>>(data_dev, (size_t)n, threshold, value);
+    M3D_CHECK_LAUNCH();
+    count_launch(ctx, KF_REPLACE_ABOVE);
+    return M3D_OK;
+}

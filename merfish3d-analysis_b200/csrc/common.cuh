@@ -1,0 +1,147 @@
+// common.cuh -- context, error handling and launch accounting for libm3d_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/m3d_b200.h"
+
+#define M3D_NUM_SMS_DEFAULT 148
+
+// ---------------------------------------------------------------- errors
+extern thread_local std::string g_m3d_error;
+int m3d_fail(int code, const char* fmt, ...);
+
+#define M3D_CUDA(call)                                                                     \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            return m3d_fail(M3D_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,     \
+                            cudaGetErrorString(e__));                                      \
+    } while (0)
+
+#define M3D_CHECK_LAUNCH() M3D_CUDA(cudaGetLastError())
+
+// ---------------------------------------------------------------- kernel families (launch accounting)
+enum M3dKernel {
+    KF_WEIGHT = 0,
+    KF_LOWPASS_Z,
+    KF_LOWPASS_YX,
+    KF_LOWPASS_GENERIC,
+    KF_DECODE_GATE,
+    KF_DECODE_SEARCH,
+    KF_DECODE_DENSE,
+    KF_CCL_COLLECT,
+    KF_CCL_INIT,
+    KF_CCL_MERGE,
+    KF_CCL_COMPRESS,
+    KF_CCL_SELECT,
+    KF_CCL_SORT,
+    KF_CCL_ASSIGN,
+    KF_CCL_SCAN,
+    KF_CCL_SCATTER,
+    KF_CCL_LABELS,
+    KF_FEATURES,
+    KF_SELECT_HIST,
+    KF_REPLACE_ABOVE,
+    KF_COUNT
+};
+
+// ---------------------------------------------------------------- scratch buffer
+struct Scratch {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        // grow with headroom so tile-to-tile size jitter does not reallocate
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e != cudaSuccess) {
+            ptr = nullptr;
+            return m3d_fail(M3D_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+// ---------------------------------------------------------------- per-call decode parameters (by value)
+struct DecodeParams {
+    float bkg[M3D_MAX_BITS];
+    float nrm[M3D_MAX_BITS];
+    float rcp[M3D_MAX_BITS];  // correctly rounded 1/nrm (fast exact division)
+    float pix_thr, mag_lo, mag_hi;
+    int use_norm;
+    int n_bits;
+    int K;
+    int max_on;        // padded on-bit list length (binary codebooks)
+    int binary;        // 1: every row's non-zeros share one value
+    const float* codebook;       // K x NBPAD fp32 (zero padded)
+    const uint8_t* onbits;       // K x max_on bit indices (pad = NBPAD -> zero slot)
+    const float* cw_a;           // K: ||c_k||^2
+    const float* cw_g;           // K: 2*c_k
+    const float* cw_c;           // K: c_k (value of the non-zero entries)
+    const uint32_t* cw_mask;     // K: on-bit mask
+    const uint8_t* excluded;     // K flags
+};
+
+struct m3d_ctx {
+    int device = 0;
+    int num_sms = M3D_NUM_SMS_DEFAULT;
+    int n_bits = 0;
+    int nb_pad = 0;  // 16 / 24 / 32
+    int K = 0;
+    int max_on = 0;
+    int binary = 0;
+    // device-side codebook artefacts
+    float* d_codebook = nullptr;
+    uint8_t* d_onbits = nullptr;
+    float* d_cw_a = nullptr;
+    float* d_cw_g = nullptr;
+    float* d_cw_c = nullptr;
+    uint32_t* d_cw_mask = nullptr;
+    uint8_t* d_excluded = nullptr;
+    // normalisation state
+    float bkg[M3D_MAX_BITS];
+    float nrm[M3D_MAX_BITS];
+    float rcp[M3D_MAX_BITS];
+    int use_norm = 0;
+    int safe_div = 1;
+    float pix_thr = 0.f, mag_lo = 0.f, mag_hi = 0.f;
+    // scratch
+    Scratch s_cand;      // decode candidates
+    Scratch s_counters;  // small device counters
+    Scratch s_lp_tmp;    // low-pass intermediate volume
+    Scratch s_fg;        // CCL foreground list
+    Scratch s_parent;    // dense union-find parents
+    Scratch s_aux;       // dense per-root aux (area / id)
+    Scratch s_roots;     // surviving roots (unsorted, sorted)
+    Scratch s_area;      // area by id, offsets, cursors
+    Scratch s_vox;       // voxel lists grouped by component
+    Scratch s_sort;      // cub temp storage
+    unsigned long long* h_pinned = nullptr;  // pinned host mailbox for counts
+    // label state (valid between m3d_label and m3d_features)
+    int64_t lab_dims[3] = {0, 0, 0};
+    int64_t lab_n_fg = 0;
+    int64_t lab_n_features = -1;
+    int lab_max_px = 0;
+    // accounting
+    int64_t launches[KF_COUNT];
+    DecodeParams params() const;
+};
+
+static inline void count_launch(m3d_ctx* ctx, M3dKernel k, int64_t n = 1) { ctx->launches[k] += n; }
+
+static inline int ceil_div_i64(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

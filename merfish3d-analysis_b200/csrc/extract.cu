@@ -1,0 +1,491 @@
+// extract.cu -- connected components, size filters and regionprops (replaces PD:2908-3062).
+//
+// Labelling (m3d_label).  The decoded image is sparse (a few % foreground), so everything
+// after one streaming pass over it works on the compacted foreground list:
+//   ccl_collect_kernel : stream decoded (int16, 128-bit loads), append foreground voxels to a
+//                        list and initialise their union-find parent / aux slots.  Parent and
+//                        aux are dense uint32 arrays indexed by voxel but only foreground
+//                        entries are ever touched.
+//   ccl_merge_kernel   : per foreground voxel, union with each equal-valued backward
+//                        neighbour (13 of 26 in 3-D, 4 of 8 per plane in 2-D); lock-free
+//                        atomicMin union-find, so every root is the component's smallest
+//                        linear index = the raster-first voxel = the canonical identity.
+//   ccl_compress_kernel: flatten to roots, count areas.
+//   ccl_select_kernel  : roots whose area passes both size filters are appended to a list,
+//                        which is radix-sorted (CUB) -> canonical ids in raster order.
+//   ccl_assign / scan / scatter : area by id, exclusive offsets, voxels grouped by component.
+// Regionprops (m3d_features): one warp per component sorts its voxel list (bitonic, shared
+// memory) so that every float32 accumulation runs in raster order exactly like NumPy's
+// reductions in scikit-image; per-voxel values are recomputed from the input stack with the
+// same device functions the decode kernels use (voxel_math.cuh).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "voxel_math.cuh"
+
+namespace {
+
+constexpr uint32_t DROPPED = 0xFFFFFFFFu;
+constexpr int FEAT_MAX_PX = 1024;  // upper bound on maximum_pixels supported by the warp-sort path
+
+// counters layout inside ctx->s_counters (uint32 each)
+enum { CNT_CAND = 0, CNT_FG = 1, CNT_ROOTS = 2 };
+
+__device__ __forceinline__ void warp_append(bool pass, uint32_t value, uint32_t* list, unsigned int* counter) {
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (m) {
+        unsigned base = 0;
+        const int leader = __ffs(m) - 1;
+        if ((int)lane == leader) base = atomicAdd(counter, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (pass) list[base + __popc(m & ((1u << lane) - 1u))] = value;
+    }
+}
+
+// ------------------------------------------------------------------ collect + init
+__global__ void __launch_bounds__(256)
+ccl_collect_kernel(const int16_t* __restrict__ decoded, size_t n_vox, int vec, uint32_t* __restrict__ fg,
+                   unsigned int* __restrict__ fg_count, uint32_t* __restrict__ parent,
+                   uint32_t* __restrict__ aux) {
+    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+    int16_t vals[8];
+    const size_t v0 = t * 8;
+    if (vec && v0 + 8 <= n_vox) {
+        uint4 q = __ldcs(reinterpret_cast<const uint4*>(decoded + v0));
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            vals[2 * j] = (int16_t)(w[j] & 0xFFFFu);
+            vals[2 * j + 1] = (int16_t)(w[j] >> 16);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) vals[j] = (v0 + j < n_vox) ? decoded[v0 + j] : (int16_t)-1;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const bool is_fg = vals[j] != -1;
+        if (is_fg) {
+            parent[v0 + j] = (uint32_t)(v0 + j);
+            aux[v0 + j] = 0u;
+        }
+        warp_append(is_fg, (uint32_t)(v0 + j), fg, fg_count);
+    }
+}
+
+// ------------------------------------------------------------------ union-find
+__device__ __forceinline__ uint32_t uf_find(const uint32_t* L, uint32_t a) {
+    uint32_t p = __ldcg(L + a);
+    while (p != a) {
+        a = p;
+        p = __ldcg(L + a);
+    }
+    return a;
+}
+
+// Playne-Hawick style lock-free union; roots always move towards smaller indices.
+__device__ __forceinline__ void uf_union(uint32_t* L, uint32_t a, uint32_t b) {
+    a = uf_find(L, a);
+    b = uf_find(L, b);
+    while (a != b) {
+        if (a < b) {
+            uint32_t t = a;
+            a = b;
+            b = t;
+        }  // a > b
+        uint32_t old = atomicMin(L + a, b);
+        a = (old == a) ? b : old;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ccl_merge_kernel(const int16_t* __restrict__ decoded, const uint32_t* __restrict__ fg,
+                 const unsigned int* __restrict__ fg_count, uint32_t* __restrict__ parent, int Z, int Y, int X,
+                 int mode2d) {
+    const unsigned n = *fg_count;
+    const uint32_t plane = (uint32_t)Y * (uint32_t)X;
+    for (unsigned i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const uint32_t v = fg[i];
+        const int16_t val = decoded[v];
+        const int z = (int)(v / plane);
+        const uint32_t rem = v - (uint32_t)z * plane;
+        const int y = (int)(rem / (uint32_t)X);
+        const int x = (int)(rem - (uint32_t)y * (uint32_t)X);
+        // backward half of the neighbourhood, lexicographic (dz,dy,dx) < (0,0,0)
+        for (int dz = mode2d ? 0 : -1; dz <= 0; ++dz) {
+            const int zz = z + dz;
+            if (zz < 0) continue;
+            const int dy_hi = (dz < 0) ? 1 : 0;
+            for (int dy = -1; dy <= dy_hi; ++dy) {
+                const int yy = y + dy;
+                if (yy < 0 || yy >= Y) continue;
+                const int dx_hi = (dz < 0 || dy < 0) ? 1 : -1;
+                for (int dx = -1; dx <= dx_hi; ++dx) {
+                    const int xx = x + dx;
+                    if (xx < 0 || xx >= X) continue;
+                    const uint32_t nb = (uint32_t)zz * plane + (uint32_t)yy * (uint32_t)X + (uint32_t)xx;
+                    if (decoded[nb] == val) uf_union(parent, v, nb);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ccl_compress_kernel(const uint32_t* __restrict__ fg, const unsigned int* __restrict__ fg_count,
+                    uint32_t* __restrict__ parent, uint32_t* __restrict__ aux, uint32_t* __restrict__ root_of) {
+    const unsigned n = *fg_count;
+    for (unsigned i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const uint32_t v = fg[i];
+        const uint32_t r = uf_find(parent, v);
+        root_of[i] = r;
+        atomicAdd(aux + r, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ccl_select_kernel(const uint32_t* __restrict__ fg, const unsigned int* __restrict__ fg_count,
+                  const uint32_t* __restrict__ root_of, uint32_t* __restrict__ aux, uint32_t min_keep,
+                  uint32_t max_keep, uint32_t* __restrict__ roots, unsigned int* __restrict__ root_count) {
+    const unsigned n = *fg_count;
+    const unsigned stride = gridDim.x * 256;
+    const unsigned n_round = ((n + 31u) / 32u) * 32u;
+    for (unsigned i = blockIdx.x * 256 + threadIdx.x; i < n_round; i += stride) {
+        bool keep = false;
+        uint32_t v = 0;
+        if (i < n) {
+            v = fg[i];
+            if (root_of[i] == v) {
+                const uint32_t a = aux[v];
+                keep = (a >= min_keep) && (a <= max_keep);
+                if (!keep) aux[v] = DROPPED;
+            }
+        }
+        warp_append(keep, v, roots, root_count);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ccl_assign_kernel(const uint32_t* __restrict__ roots_sorted, unsigned n_roots, uint32_t* __restrict__ aux,
+                  uint32_t* __restrict__ area_by_id) {
+    const unsigned id = blockIdx.x * 256 + threadIdx.x;
+    if (id < n_roots) {
+        const uint32_t r = roots_sorted[id];
+        area_by_id[id] = aux[r];
+        aux[r] = id;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ccl_scatter_kernel(const uint32_t* __restrict__ fg, const unsigned int* __restrict__ fg_count,
+                   const uint32_t* __restrict__ root_of, const uint32_t* __restrict__ aux,
+                   const uint32_t* __restrict__ offs, uint32_t* __restrict__ cursor, uint32_t* __restrict__ vox,
+                   int32_t* __restrict__ labels) {
+    const unsigned n = *fg_count;
+    for (unsigned i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const uint32_t id = aux[root_of[i]];
+        if (id != DROPPED) {
+            const uint32_t v = fg[i];
+            const uint32_t slot = atomicAdd(cursor + id, 1u);
+            vox[offs[id] + slot] = v;
+            if (labels) labels[v] = (int32_t)(id + 1u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ regionprops
+// NumPy's float32 pairwise sum (numpy/_core/src/umath/loops_utils.h.src), n <= 1024.
+__device__ float np_pairwise_sum(const float* a, int n) {
+    if (n < 8) {
+        float res = 0.f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, a[i]);
+        return res;
+    } else if (n <= 128) {
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
+        }
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __fadd_rn(res, a[i]);
+        return res;
+    } else {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        return __fadd_rn(np_pairwise_sum(a, n2), np_pairwise_sum(a + n2, n - n2));
+    }
+}
+
+constexpr int FEAT_WARPS = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(FEAT_WARPS * 32)
+features_kernel(const T* __restrict__ stack, size_t n_vox, int Y, int X, DecodeParams P,
+                const int16_t* __restrict__ decoded, const uint32_t* __restrict__ vox,
+                const uint32_t* __restrict__ offs, const uint32_t* __restrict__ area_by_id, unsigned n_feat,
+                int optimize_mode, double* __restrict__ table, int n_cols) {
+    __shared__ uint32_t s_vox[FEAT_WARPS][FEAT_MAX_PX];
+    __shared__ float s_mag[FEAT_WARPS][FEAT_MAX_PX];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t plane = (uint32_t)Y * (uint32_t)X;
+    uint32_t* sv = s_vox[warp];
+    float* sm = s_mag[warp];
+    for (unsigned id = blockIdx.x * FEAT_WARPS + warp; id < n_feat; id += gridDim.x * FEAT_WARPS) {
+        const int n = (int)area_by_id[id];
+        const uint32_t* seg = vox + offs[id];
+        int Pn = 32;
+        while (Pn < n) Pn <<= 1;
+        for (int i = lane; i < Pn; i += 32) sv[i] = (i < n) ? seg[i] : 0xFFFFFFFFu;
+        __syncwarp();
+        // bitonic sort, ascending
+        for (int k = 2; k <= Pn; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = lane; i < Pn; i += 32) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const uint32_t a = sv[i], b = sv[ixj];
+                        const bool up = ((i & k) == 0);
+                        if ((a > b) == up) {
+                            sv[i] = b;
+                            sv[ixj] = a;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        const uint32_t v_first = sv[0];
+        const int z0 = (int)(v_first / plane);
+        const uint32_t rem0 = v_first - (uint32_t)z0 * plane;
+        const int y0 = (int)(rem0 / (uint32_t)X);
+        const int x0 = (int)(rem0 - (uint32_t)y0 * (uint32_t)X);
+        const int dec_id = decoded[v_first];
+        const float* crow = P.codebook + (size_t)(dec_id < 0 ? 0 : dec_id) * M3D_MAX_BITS;
+        const bool bit_lane = lane < P.n_bits;
+        const float c_b = bit_lane ? __ldg(crow + lane) : 0.f;
+        float bit_acc = 0.f;
+        float dist_min = __int_as_float(0x7f800000);
+        long long sz = 0, sy = 0, sx = 0;
+        long long szz = 0, syy = 0, sxx = 0, szy = 0, szx = 0, syx = 0;
+        for (int j = 0; j < n; ++j) {
+            const uint32_t v = sv[j];
+            float raw = 0.f, x = 0.f;
+            if (bit_lane) {
+                raw = load_elem(stack, (size_t)lane * n_vox + v);
+                x = raw;
+                if (P.use_norm) x = __fdiv_rn(__fsub_rn(raw, P.bkg[lane]), P.nrm[lane]);
+                x = clip01_nan(x);
+            }
+            const float sq = __fmul_rn(x, x);
+            float acc = __shfl_sync(0xffffffffu, sq, 0);
+            for (int b = 1; b < P.n_bits; ++b) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, sq, b));
+            const float nrm2 = __fsqrt_rn(acc);
+            float mag = nrm2, xh;
+            if (nrm2 == 0.f) {
+                mag = -1.f;
+                xh = __fdiv_rn(x, __int_as_float(0x7f800000));
+            } else {
+                xh = __fdiv_rn(x, nrm2);
+            }
+            const float t = __fsub_rn(xh, c_b);
+            const float tsq = __fmul_rn(t, t);
+            float dacc = __shfl_sync(0xffffffffu, tsq, 0);
+            for (int b = 1; b < P.n_bits; ++b) dacc = __fadd_rn(dacc, __shfl_sync(0xffffffffu, tsq, b));
+            const float d = __fsqrt_rn(dacc);
+            const float d16 = __half2float(round5_f16(d));
+            dist_min = fminf(dist_min, d16);
+            if (lane == 0) sm[j] = __half2float(round5_f16(mag));
+            if (bit_lane) {
+                const float val = optimize_mode ? raw : __half2float(round5_f16(x));
+                bit_acc = (j == 0) ? val : __fadd_rn(bit_acc, val);
+            }
+            if (lane == 0) {
+                const int z = (int)(v / plane);
+                const uint32_t rem = v - (uint32_t)z * plane;
+                const int y = (int)(rem / (uint32_t)X);
+                const int xx = (int)(rem - (uint32_t)y * (uint32_t)X);
+                sz += z; sy += y; sx += xx;
+                const long long dz = z - z0, dy = y - y0, dx = xx - x0;
+                szz += dz * dz; syy += dy * dy; sxx += dx * dx;
+                szy += dz * dy; szx += dz * dx; syx += dy * dx;
+            }
+        }
+        __syncwarp();
+        double* row = table + (size_t)id * n_cols;
+        if (bit_lane) {
+            float mean = __fdiv_rn(bit_acc, (float)n);
+            if (!optimize_mode) mean = __half2float(__float2half_rn(mean));
+            row[M3D_TABLE_FIXED_COLS + lane] = (double)mean;
+        }
+        if (lane == 0) {
+            const double dn = (double)n;
+            float msum = np_pairwise_sum(sm, n);
+            float mmean = __half2float(__float2half_rn(__fdiv_rn(msum, (float)n)));
+            row[0] = (double)v_first;
+            row[1] = dn;
+            row[2] = (double)dec_id;
+            row[3] = (double)sz / dn;
+            row[4] = (double)sy / dn;
+            row[5] = (double)sx / dn;
+            // central second moments from first-voxel-relative integer sums (exact in int64)
+            const double mz = (double)(sz - (long long)z0 * n), my = (double)(sy - (long long)y0 * n),
+                         mx = (double)(sx - (long long)x0 * n);
+            row[6] = (double)szz - mz * mz / dn;
+            row[7] = (double)syy - my * my / dn;
+            row[8] = (double)sxx - mx * mx / dn;
+            row[9] = (double)szy - mz * my / dn;
+            row[10] = (double)szx - mz * mx / dn;
+            row[11] = (double)syx - my * mx / dn;
+            row[12] = (double)dist_min;
+            row[13] = (double)mmean;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+// ====================================================================== host entry points
+extern "C" int m3d_label(m3d_ctx* ctx, const int16_t* decoded_dev, const int64_t dims[3], int mode2d,
+                         double minimum_pixels, int maximum_pixels, int32_t* labels_dev,
+                         int64_t* n_features_out, void* stream) {
+    if (!ctx || !decoded_dev || !dims || !n_features_out) return m3d_fail(M3D_ERR_ARG, "m3d_label: null argument");
+    if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return m3d_fail(M3D_ERR_ARG, "m3d_label: bad dims");
+    const size_t n_vox = (size_t)dims[0] * dims[1] * dims[2];
+    if (n_vox >= 0xFFFFFFF0ull) return m3d_fail(M3D_ERR_ARG, "m3d_label: volume exceeds 2^32 voxels per call");
+    if (maximum_pixels < 1 || maximum_pixels > FEAT_MAX_PX)
+        return m3d_fail(M3D_ERR_ARG, "m3d_label: maximum_pixels must be in [1, %d]", FEAT_MAX_PX);
+    M3D_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int Z = (int)dims[0], Y = (int)dims[1], X = (int)dims[2];
+    ctx->lab_n_features = -1;
+
+    if (ctx->s_counters.ensure(256)) return M3D_ERR_CUDA;
+    if (ctx->s_fg.ensure(2 * n_vox * sizeof(uint32_t))) return M3D_ERR_CUDA;  // fg list + root_of
+    if (ctx->s_parent.ensure(n_vox * sizeof(uint32_t))) return M3D_ERR_CUDA;
+    if (ctx->s_aux.ensure(n_vox * sizeof(uint32_t))) return M3D_ERR_CUDA;
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ctx->s_counters.ptr);
+    uint32_t* fg = reinterpret_cast<uint32_t*>(ctx->s_fg.ptr);
+    uint32_t* root_of = fg + n_vox;
+    uint32_t* parent = reinterpret_cast<uint32_t*>(ctx->s_parent.ptr);
+    uint32_t* aux = reinterpret_cast<uint32_t*>(ctx->s_aux.ptr);
+    M3D_CUDA(cudaMemsetAsync(counters + CNT_FG, 0, 2 * sizeof(unsigned int), st));
+    if (labels_dev) M3D_CUDA(cudaMemsetAsync(labels_dev, 0, n_vox * sizeof(int32_t), st));
+
+    {
+        const int vec = ((reinterpret_cast<uintptr_t>(decoded_dev) & 15u) == 0) ? 1 : 0;
+        const size_t threads = (n_vox + 7) / 8;
+        const int blocks = (int)((threads + 255) / 256);
+        ccl_collect_kernel<<<blocks, 256, 0, st>>>(decoded_dev, n_vox, vec, fg, counters + CNT_FG, parent, aux);
+        M3D_CHECK_LAUNCH();
+        count_launch(ctx, KF_CCL_COLLECT);
+    }
+    const int sparse_blocks = ctx->num_sms * 8;
+    ccl_merge_kernel<<<sparse_blocks, 256, 0, st>>>(decoded_dev, fg, counters + CNT_FG, parent, Z, Y, X, mode2d ? 1 : 0);
+    M3D_CHECK_LAUNCH();
+    count_launch(ctx, KF_CCL_MERGE);
+    ccl_compress_kernel<<<sparse_blocks, 256, 0, st>>>(fg, counters + CNT_FG, parent, aux, root_of);
+    M3D_CHECK_LAUNCH();
+    count_launch(ctx, KF_CCL_COMPRESS);
+
+    // PD:2976-2989: drop area > maximum_pixels; drop area <= max(int(minimum_pixels)-1, 0)
+    long long max_size = (long long)minimum_pixels - 1;  // int() truncates toward zero like Python for >= 0
+    if (minimum_pixels < 0) max_size = (long long)minimum_pixels - 1;
+    if (max_size < 0) max_size = 0;
+    const uint32_t min_keep = (uint32_t)(max_size + 1);
+    // roots list shares the candidate scratch (n_vox uint32 is an upper bound)
+    if (ctx->s_roots.ensure((n_vox / (min_keep ? min_keep : 1) + 64) * 2 * sizeof(uint32_t))) return M3D_ERR_CUDA;
+    uint32_t* roots = reinterpret_cast<uint32_t*>(ctx->s_roots.ptr);
+    const size_t roots_cap = ctx->s_roots.cap / (2 * sizeof(uint32_t));
+    uint32_t* roots_sorted = roots + roots_cap;
+    ccl_select_kernel<<<sparse_blocks, 256, 0, st>>>(fg, counters + CNT_FG, root_of, aux, min_keep,
+                                                     (uint32_t)maximum_pixels, roots, counters + CNT_ROOTS);
+    M3D_CHECK_LAUNCH();
+    count_launch(ctx, KF_CCL_SELECT);
+
+    unsigned int h_counts[2];
+    M3D_CUDA(cudaMemcpyAsync(h_counts, counters + CNT_FG, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    M3D_CUDA(cudaStreamSynchronize(st));
+    const unsigned n_fg = h_counts[0], n_roots = h_counts[1];
+    ctx->lab_n_fg = n_fg;
+    ctx->lab_dims[0] = Z; ctx->lab_dims[1] = Y; ctx->lab_dims[2] = X;
+    ctx->lab_max_px = maximum_pixels;
+    if (n_roots == 0) {
+        ctx->lab_n_features = 0;
+        *n_features_out = 0;
+        return M3D_OK;
+    }
+    // canonical order = ascending first-voxel index
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, roots, roots_sorted, (int)n_roots, 0, 32, st);
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_roots, st);
+    if (scan_bytes > tmp_bytes) tmp_bytes = scan_bytes;
+    if (ctx->s_sort.ensure(tmp_bytes)) return M3D_ERR_CUDA;
+    M3D_CUDA(cub::DeviceRadixSort::SortKeys(ctx->s_sort.ptr, tmp_bytes, roots, roots_sorted, (int)n_roots, 0, 32, st));
+    count_launch(ctx, KF_CCL_SORT);
+    // area_by_id | offs | cursor
+    if (ctx->s_area.ensure((size_t)n_roots * 3 * sizeof(uint32_t))) return M3D_ERR_CUDA;
+    uint32_t* area_by_id = reinterpret_cast<uint32_t*>(ctx->s_area.ptr);
+    uint32_t* offs = area_by_id + n_roots;
+    uint32_t* cursor = offs + n_roots;
+    ccl_assign_kernel<<<(n_roots + 255) / 256, 256, 0, st>>>(roots_sorted, n_roots, aux, area_by_id);
+    M3D_CHECK_LAUNCH();
+    count_launch(ctx, KF_CCL_ASSIGN);
+    M3D_CUDA(cub::DeviceScan::ExclusiveSum(ctx->s_sort.ptr, tmp_bytes, area_by_id, offs, (int)n_roots, st));
+    count_launch(ctx, KF_CCL_SCAN);
+    M3D_CUDA(cudaMemsetAsync(cursor, 0, (size_t)n_roots * sizeof(uint32_t), st));
+    if (ctx->s_vox.ensure((size_t)n_fg * sizeof(uint32_t))) return M3D_ERR_CUDA;
+    uint32_t* vox = reinterpret_cast<uint32_t*>(ctx->s_vox.ptr);
+    ccl_scatter_kernel<<<sparse_blocks, 256, 0, st>>>(fg, counters + CNT_FG, root_of, aux, offs, cursor, vox, labels_dev);
+    M3D_CHECK_LAUNCH();
+    count_launch(ctx, KF_CCL_SCATTER);
+    ctx->lab_n_features = n_roots;
+    *n_features_out = n_roots;
+    return M3D_OK;
+}
+
+extern "C" int m3d_features(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t dims[3],
+                            const int16_t* decoded_dev, int optimize_mode, double* table_dev, int64_t n_rows,
+                            void* stream) {
+    if (!ctx || !stack_dev || !dims || !decoded_dev) return m3d_fail(M3D_ERR_ARG, "m3d_features: null argument");
+    if (ctx->lab_n_features < 0) return m3d_fail(M3D_ERR_STATE, "m3d_features: call m3d_label first");
+    if (dims[0] != ctx->lab_dims[0] || dims[1] != ctx->lab_dims[1] || dims[2] != ctx->lab_dims[2])
+        return m3d_fail(M3D_ERR_STATE, "m3d_features: dims differ from the last m3d_label call");
+    if (n_rows < ctx->lab_n_features)
+        return m3d_fail(M3D_ERR_CAPACITY, "m3d_features: table holds %lld rows, need %lld", (long long)n_rows,
+                        (long long)ctx->lab_n_features);
+    if (ctx->lab_n_features == 0) return M3D_OK;
+    if (!table_dev) return m3d_fail(M3D_ERR_ARG, "m3d_features: null table");
+    M3D_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t n_vox = (size_t)dims[0] * dims[1] * dims[2];
+    const unsigned n_feat = (unsigned)ctx->lab_n_features;
+    DecodeParams P = ctx->params();
+    const uint32_t* area_by_id = reinterpret_cast<const uint32_t*>(ctx->s_area.ptr);
+    const uint32_t* offs = area_by_id + n_feat;
+    const uint32_t* vox = reinterpret_cast<const uint32_t*>(ctx->s_vox.ptr);
+    const int n_cols = M3D_TABLE_FIXED_COLS + ctx->n_bits;
+    int blocks = (int)((n_feat + FEAT_WARPS - 1) / FEAT_WARPS);
+    const int cap = ctx->num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    if (dtype == M3D_DTYPE_U16)
+        features_kernel<uint16_t><<<blocks, FEAT_WARPS * 32, 0, st>>>(
+            reinterpret_cast<const uint16_t*>(stack_dev), n_vox, (int)dims[1], (int)dims[2], P, decoded_dev, vox, offs,
+            area_by_id, n_feat, optimize_mode, table_dev, n_cols);
+    else if (dtype == M3D_DTYPE_F32)
+        features_kernel<float><<<blocks, FEAT_WARPS * 32, 0, st>>>(
+            reinterpret_cast<const float*>(stack_dev), n_vox, (int)dims[1], (int)dims[2], P, decoded_dev, vox, offs,
+            area_by_id, n_feat, optimize_mode, table_dev, n_cols);
+    else
+        return m3d_fail(M3D_ERR_ARG, "m3d_features: dtype %d", dtype);
+    M3D_CHECK_LAUNCH();
+    count_launch(ctx, KF_FEATURES);
+    return M3D_OK;
+}

@@ -1,0 +1,322 @@
+// lowpass.cu -- separable Gaussian low-pass (replaces PD:1948-2024).
+//
+// Semantics = scipy.ndimage.gaussian_filter(float32 volume, sigma, mode='reflect',
+// truncate=4): axes filtered in order z, y, x; every 1-D pass accumulates in float64 with
+// SciPy's symmetric formula  o = x[c]*w[c]; for j=-r..-1: o += (x[c+j] + x[c-j]) * w[c+j]
+// and stores float32.  The predictor weighting float32(readout)*float32(predictor)
+// (PD:1879-1881) is fused into the first pass's loads.
+//
+// Kernels
+//   lowpass_z_kernel<T,R>   : one thread per (y,x) column marching along z with a register
+//                             ring of 2R+1 float64 samples (loop unrolled by the ring length so
+//                             every ring index is static).  Reads each input sample once
+//                             (+2R reflected planes), writes float32.  Bound by the FP64 pipe.
+//   lowpass_yx_kernel<T,RY,RX>: 32x64 output tile per CTA; the (32+2RY)x(64+2RX) input tile is
+//                             staged in shared memory as float64, y pass -> float32-rounded
+//                             intermediate in shared memory -> x pass -> float32 store.
+//   lowpass_axis_generic_kernel: any radius <= 64 / any shape, one thread per output; used
+//                             when no templated radius matches.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int LP_MAX_RADIUS = 64;
+
+struct Weights {
+    int r;
+    double w[LP_MAX_RADIUS + 1];  // w[i] = weight at offset -(r - i) ... i.e. w[0]=edge, w[r]=centre
+};
+
+// SciPy _gaussian_kernel1d (order 0), float64; symmetric so only the first r+1 entries are kept.
+static Weights make_weights(double sigma) {
+    Weights W;
+    int lw = (int)(4.0 * sigma + 0.5);
+    if (lw > LP_MAX_RADIUS) lw = -1;
+    W.r = lw;
+    if (lw < 0) return W;
+    std::vector<double> phi(2 * lw + 1);
+    double sum = 0.0;
+    const double s2 = sigma * sigma;
+    for (int i = -lw; i <= lw; ++i) {
+        phi[i + lw] = exp(-0.5 / s2 * (double)(i * i));
+    }
+    // NumPy's phi.sum() is a pairwise sum; for <= 128 elements with n >= 8 it uses eight
+    // interleaved accumulators.  Reproduce it so the normalised weights match bit for bit.
+    const int n = 2 * lw + 1;
+    if (n < 8) {
+        sum = 0.0;
+        for (int i = 0; i < n; ++i) sum += phi[i];
+    } else {
+        double r[8];
+        for (int j = 0; j < 8; ++j) r[j] = phi[j];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += phi[i + j];
+        sum = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) sum += phi[i];
+    }
+    for (int i = 0; i <= lw; ++i) W.w[i] = phi[i] / sum;  // phi[::-1] is symmetric
+    return W;
+}
+
+__device__ __forceinline__ int reflect_index(int j, int n) {
+    if (j >= 0 && j < n) return j;
+    const int per = 2 * n;
+    int m = j % per;
+    if (m < 0) m += per;
+    return (m >= n) ? (per - 1 - m) : m;
+}
+
+template <typename T>
+__device__ __forceinline__ float in_as_f32(const T* p, size_t i);
+template <>
+__device__ __forceinline__ float in_as_f32<uint16_t>(const uint16_t* p, size_t i) { return (float)__ldg(p + i); }
+template <>
+__device__ __forceinline__ float in_as_f32<float>(const float* p, size_t i) { return __ldg(p + i); }
+
+template <typename T, bool PRED>
+__device__ __forceinline__ double load_weighted(const T* in, const float* pred, size_t i) {
+    float v = in_as_f32<T>(in, i);
+    if (PRED) v = __fmul_rn(v, __ldg(pred + i));
+    return (double)v;
+}
+
+// ------------------------------------------------------------------ z pass, register ring
+template <typename T, int R, bool PRED>
+__global__ void __launch_bounds__(128)
+lowpass_z_kernel(const T* __restrict__ in, const float* __restrict__ pred, float* __restrict__ out,
+                 int Z, size_t plane, Weights W) {
+    constexpr int RING = 2 * R + 1;
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= plane) return;
+    double ring[RING];
+    // slot of ext[j] is (j + R) mod RING
+#pragma unroll
+    for (int i = 0; i < 2 * R; ++i)
+        ring[i] = load_weighted<T, PRED>(in, pred, (size_t)reflect_index(i - R, Z) * plane + c);
+    for (int o0 = 0; o0 < Z; o0 += RING) {
+#pragma unroll
+        for (int u = 0; u < RING; ++u) {
+            const int o = o0 + u;
+            if (o < Z) {
+                ring[(u + 2 * R) % RING] =
+                    load_weighted<T, PRED>(in, pred, (size_t)reflect_index(o + R, Z) * plane + c);
+                double acc = __dmul_rn(ring[(u + R) % RING], W.w[R]);
+#pragma unroll
+                for (int jj = -R; jj < 0; ++jj) {
+                    double pr = __dadd_rn(ring[(u + R + jj + RING) % RING], ring[(u + R - jj) % RING]);
+                    acc = __dadd_rn(acc, __dmul_rn(pr, W.w[jj + R]));
+                }
+                out[(size_t)o * plane + c] = (float)acc;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ fused y,x pass, shared tile
+constexpr int YX_TX = 64;
+constexpr int YX_TY = 32;
+constexpr int YX_THREADS = 256;
+
+template <typename T, int RY, int RX, bool PRED>
+__global__ void __launch_bounds__(YX_THREADS)
+lowpass_yx_kernel(const T* __restrict__ in, const float* __restrict__ pred, float* __restrict__ out,
+                  int Y, int X, Weights WY, Weights WX) {
+    constexpr int IN_H = YX_TY + 2 * RY;
+    constexpr int IN_W = YX_TX + 2 * RX;
+    __shared__ double s_in[IN_H][IN_W + 1];
+    __shared__ double s_mid[YX_TY][IN_W + 1];
+    const int x0 = blockIdx.x * YX_TX;
+    const int y0 = blockIdx.y * YX_TY;
+    const size_t zoff = (size_t)blockIdx.z * (size_t)Y * X;
+    for (int i = threadIdx.x; i < IN_H * IN_W; i += YX_THREADS) {
+        const int ly = i / IN_W, lx = i - ly * IN_W;
+        const int gy = reflect_index(y0 + ly - RY, Y);
+        const int gx = reflect_index(x0 + lx - RX, X);
+        s_in[ly][lx] = load_weighted<T, PRED>(in, pred, zoff + (size_t)gy * X + gx);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < YX_TY * IN_W; i += YX_THREADS) {
+        const int ly = i / IN_W, lx = i - ly * IN_W;
+        double acc = __dmul_rn(s_in[ly + RY][lx], WY.w[RY]);
+#pragma unroll
+        for (int jj = -RY; jj < 0; ++jj) {
+            double pr = __dadd_rn(s_in[ly + RY + jj][lx], s_in[ly + RY - jj][lx]);
+            acc = __dadd_rn(acc, __dmul_rn(pr, WY.w[jj + RY]));
+        }
+        s_mid[ly][lx] = (double)(float)acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < YX_TY * YX_TX; i += YX_THREADS) {
+        const int ly = i / YX_TX, lx = i - ly * YX_TX;
+        const int gy = y0 + ly, gx = x0 + lx;
+        if (gy < Y && gx < X) {
+            double acc = __dmul_rn(s_mid[ly][lx + RX], WX.w[RX]);
+#pragma unroll
+            for (int jj = -RX; jj < 0; ++jj) {
+                double pr = __dadd_rn(s_mid[ly][lx + RX + jj], s_mid[ly][lx + RX - jj]);
+                acc = __dadd_rn(acc, __dmul_rn(pr, WX.w[jj + RX]));
+            }
+            out[zoff + (size_t)gy * X + gx] = (float)acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ generic single-axis pass
+template <typename T, bool PRED>
+__global__ void __launch_bounds__(256)
+lowpass_axis_generic_kernel(const T* __restrict__ in, const float* __restrict__ pred,
+                            float* __restrict__ out, size_t total, int len, size_t stride, Weights W) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int pos = (int)((i / stride) % (size_t)len);
+    const size_t base = i - (size_t)pos * stride;
+    const int r = W.r;
+    double acc = __dmul_rn(load_weighted<T, PRED>(in, pred, i), W.w[r]);
+    for (int jj = -r; jj < 0; ++jj) {
+        double a = load_weighted<T, PRED>(in, pred, base + (size_t)reflect_index(pos + jj, len) * stride);
+        double b = load_weighted<T, PRED>(in, pred, base + (size_t)reflect_index(pos - jj, len) * stride);
+        acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(a, b), W.w[jj + r]));
+    }
+    out[i] = (float)acc;
+}
+
+template <typename T, bool PRED>
+int run_generic_axis(m3d_ctx* ctx, const T* in, const float* pred, float* out, size_t total, int len,
+                     size_t stride, const Weights& W, cudaStream_t st) {
+    int blocks = (int)((total + 255) / 256);
+    lowpass_axis_generic_kernel<T, PRED><<<blocks, 256, 0, st>>>(in, pred, out, total, len, stride, W);
+    M3D_CHECK_LAUNCH();
+    count_launch(ctx, KF_LOWPASS_GENERIC);
+    return M3D_OK;
+}
+
+template <typename T, bool PRED>
+int run_z(m3d_ctx* ctx, const T* in, const float* pred, float* out, int Z, int Y, int X, const Weights& W,
+          cudaStream_t st) {
+    const size_t plane = (size_t)Y * X;
+    const int blocks = (int)((plane + 127) / 128);
+    switch (W.r) {
+        case 12: lowpass_z_kernel<T, 12, PRED><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W); break;
+        case 8: lowpass_z_kernel<T, 8, PRED><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W); break;
+        case 6: lowpass_z_kernel<T, 6, PRED><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W); break;
+        case 4: lowpass_z_kernel<T, 4, PRED><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W); break;
+        case 2: lowpass_z_kernel<T, 2, PRED><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W); break;
+        default:
+            return run_generic_axis<T, PRED>(ctx, in, pred, out, (size_t)Z * plane, Z, plane, W, st);
+    }
+    M3D_CHECK_LAUNCH();
+    count_launch(ctx, KF_LOWPASS_Z);
+    return M3D_OK;
+}
+
+// y then x on `n_planes` planes.  Returns 1 when no templated instance matches.
+template <typename T, bool PRED>
+int run_yx_fast(m3d_ctx* ctx, const T* in, const float* pred, float* out, int n_planes, int Y, int X,
+                const Weights& WY, const Weights& WX, cudaStream_t st) {
+    dim3 grid((X + YX_TX - 1) / YX_TX, (Y + YX_TY - 1) / YX_TY, n_planes);
+    if (grid.y > 65535 || grid.z > 65535) return 1;
+    if (WY.r == 4 && WX.r == 4)
+        lowpass_yx_kernel<T, 4, 4, PRED><<<grid, YX_THREADS, 0, st>>>(in, pred, out, Y, X, WY, WX);
+    else if (WY.r == 2 && WX.r == 2)
+        lowpass_yx_kernel<T, 2, 2, PRED><<<grid, YX_THREADS, 0, st>>>(in, pred, out, Y, X, WY, WX);
+    else if (WY.r == 6 && WX.r == 6)
+        lowpass_yx_kernel<T, 6, 6, PRED><<<grid, YX_THREADS, 0, st>>>(in, pred, out, Y, X, WY, WX);
+    else
+        return 1;
+    M3D_CHECK_LAUNCH();
+    count_launch(ctx, KF_LOWPASS_YX);
+    return M3D_OK;
+}
+
+template <typename T, bool PRED>
+int lowpass_volume(m3d_ctx* ctx, const T* in, const float* pred, int Z, int Y, int X, const Weights& WZ,
+                   const Weights& WY, const Weights& WX, int mode2d, float* out, cudaStream_t st) {
+    const size_t vol = (size_t)Z * Y * X;
+    if (mode2d) {
+        int rc = run_yx_fast<T, PRED>(ctx, in, pred, out, Z, Y, X, WY, WX, st);
+        if (rc <= 0) return rc;
+        if (ctx->s_lp_tmp.ensure(vol * sizeof(float))) return M3D_ERR_CUDA;
+        float* tmp = reinterpret_cast<float*>(ctx->s_lp_tmp.ptr);
+        rc = run_generic_axis<T, PRED>(ctx, in, pred, tmp, vol, Y, (size_t)X, WY, st);
+        if (rc) return rc;
+        return run_generic_axis<float, false>(ctx, tmp, nullptr, out, vol, X, 1, WX, st);
+    }
+    if (ctx->s_lp_tmp.ensure(2 * vol * sizeof(float))) return M3D_ERR_CUDA;
+    float* tmp = reinterpret_cast<float*>(ctx->s_lp_tmp.ptr);
+    float* tmp2 = tmp + vol;
+    int rc = run_z<T, PRED>(ctx, in, pred, tmp, Z, Y, X, WZ, st);
+    if (rc) return rc;
+    rc = run_yx_fast<float, false>(ctx, tmp, nullptr, out, Z, Y, X, WY, WX, st);
+    if (rc <= 0) return rc;
+    rc = run_generic_axis<float, false>(ctx, tmp, nullptr, tmp2, vol, Y, (size_t)X, WY, st);
+    if (rc) return rc;
+    return run_generic_axis<float, false>(ctx, tmp2, nullptr, out, vol, X, 1, WX, st);
+}
+
+template <typename T>
+int lowpass_all(m3d_ctx* ctx, const T* in, const float* pred, int n_vols, int Z, int Y, int X,
+                const double sigma[3], int mode2d, float* out, cudaStream_t st) {
+    Weights WZ = make_weights(sigma[0]);
+    Weights WY = make_weights(sigma[1]);
+    Weights WX = make_weights(sigma[2]);
+    if ((!mode2d && WZ.r < 0) || WY.r < 0 || WX.r < 0)
+        return m3d_fail(M3D_ERR_ARG, "m3d_lowpass: sigma too large (radius > %d)", LP_MAX_RADIUS);
+    const size_t vol = (size_t)Z * Y * X;
+    for (int v = 0; v < n_vols; ++v) {
+        int rc = pred ? lowpass_volume<T, true>(ctx, in + v * vol, pred + v * vol, Z, Y, X, WZ, WY, WX, mode2d,
+                                                out + v * vol, st)
+                      : lowpass_volume<T, false>(ctx, in + v * vol, nullptr, Z, Y, X, WZ, WY, WX, mode2d,
+                                                 out + v * vol, st);
+        if (rc) return rc;
+    }
+    return M3D_OK;
+}
+
+__global__ void weight_kernel(const uint16_t* __restrict__ r, const float* __restrict__ p,
+                              float* __restrict__ o, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        float v = (float)__ldg(r + i);
+        o[i] = p ? __fmul_rn(v, __ldg(p + i)) : v;
+    }
+}
+
+}  // namespace
+
+extern "C" int m3d_lowpass(m3d_ctx* ctx, const void* in_dev, int in_dtype, const float* predictor_dev,
+                           int n_vols, const int64_t dims[3], const double sigma[3], int mode2d,
+                           float* out_dev, void* stream) {
+    if (!ctx || !in_dev || !out_dev || !dims || !sigma) return m3d_fail(M3D_ERR_ARG, "m3d_lowpass: null argument");
+    if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0 || n_vols <= 0)
+        return m3d_fail(M3D_ERR_ARG, "m3d_lowpass: bad dims");
+    if (dims[0] > 0x7fffffff || dims[1] > 0x7fffffff || dims[2] > 0x7fffffff)
+        return m3d_fail(M3D_ERR_ARG, "m3d_lowpass: dims exceed int32");
+    for (int a = mode2d ? 1 : 0; a < 3; ++a)
+        if (!(sigma[a] > 0.0)) return m3d_fail(M3D_ERR_ARG, "m3d_lowpass: sigma must be > 0 (inactive filters are the caller's no-op)");
+    if ((const void*)out_dev == in_dev) return m3d_fail(M3D_ERR_ARG, "m3d_lowpass: in-place not supported");
+    M3D_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int Z = (int)dims[0], Y = (int)dims[1], X = (int)dims[2];
+    if (in_dtype == M3D_DTYPE_U16)
+        return lowpass_all<uint16_t>(ctx, reinterpret_cast<const uint16_t*>(in_dev), predictor_dev, n_vols, Z, Y, X,
+                                     sigma, mode2d, out_dev, st);
+    if (in_dtype == M3D_DTYPE_F32)
+        return lowpass_all<float>(ctx, reinterpret_cast<const float*>(in_dev), predictor_dev, n_vols, Z, Y, X, sigma,
+                                  mode2d, out_dev, st);
+    return m3d_fail(M3D_ERR_ARG, "m3d_lowpass: dtype %d", in_dtype);
+}
+
+extern "C" int m3d_weight(m3d_ctx* ctx, const uint16_t* readout_dev, const float* predictor_dev, int64_t n,
+                          float* out_dev, void* stream) {
+    if (!ctx || !readout_dev || !out_dev || n <= 0) return m3d_fail(M3D_ERR_ARG, "m3d_weight: bad argument");
+    M3D_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int blocks = (int)(((size_t)n + 255) / 256);
+    weight_kernel<<<blocks, 256, 0, st>>>(readout_dev, predictor_dev, out_dev, (size_t)n);
+    M3D_CHECK_LAUNCH();
+    count_launch(ctx, KF_WEIGHT);
+    return M3D_OK;
+}
