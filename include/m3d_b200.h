@@ -123,8 +123,17 @@ int m3d_replace_above(m3d_ctx* ctx, float* data_dev, int64_t n, float threshold,
 
 /* number of kernels this context has launched since creation (bench.py gpu_launches). */
 int64_t m3d_launch_count(m3d_ctx* ctx);
-/* name and cumulative launches of the i-th kernel family; NULL when i is out of range. */
+/* name of the i-th kernel family; NULL when i is out of range. */
 const char* m3d_kernel_name(int i);
+/* launches of the i-th kernel family by this context (0 when i is out of range). */
+int64_t m3d_kernel_launches(m3d_ctx* ctx, int i);
+/* Per-family device timing for bench.py's roofline: when enabled, every launch is bracketed
+ * by CUDA events on its own stream; m3d_kernel_time_ms synchronises on the recorded events
+ * and returns the family's accumulated milliseconds.  m3d_reset_counters zeroes launches and
+ * times. */
+int m3d_set_timing(m3d_ctx* ctx, int enable);
+int m3d_reset_counters(m3d_ctx* ctx);
+double m3d_kernel_time_ms(m3d_ctx* ctx, int i);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,1115 @@
+"""B200-native ``PixelDecoder``: the reference class' decode stage behind the same API.
+
+Mirrors ``src/merfish3danalysis/PixelDecoder.py`` (0.13.0, "PD") for the hot path only
+(SURVEY.md section 8): constructor and method names, argument meaning, return tuples and error
+behaviour are the reference's (PD:449-461, PD:4471-4483, PD:4581-4592, PD:4759-4772);
+the arithmetic runs in hand-written sm_100a kernels behind the C ABI of
+``libm3d_b200.so`` (``include/m3d_b200.h``).  There is no CPU fallback: without a CUDA
+device or without the shared library every decode call raises.
+
+What differs from the reference by design
+  * the whole tile stays resident in HBM: one H2D of the uint16 stack, one small D2H of the
+    feature table (the reference round-trips every z plane, PD:2561-2632);
+  * result images (float16 magnitude / distance / scaled) are only materialised for
+    ``return_results=True``; otherwise the feature kernel recomputes what it needs;
+  * multi-GPU work runs on persistent ranks (``torch.distributed``) or, without a
+    launcher, on one host thread per device -- never a process spawn per iteration.
+
+Out of scope here: decode-time warping with non-identity transforms,
+transcript filters / de-duplication / cell assignment, chromatic-affine estimation.
+"""
+
+from __future__ import annotations
+
+import hashlib
+import shutil
+import tempfile
+import warnings
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+from random import sample
+from typing import Literal, Sequence
+
+import numpy as np
+import pandas as pd
+
+from . import normalization as _norm
+from ._capi import M3D_TABLE_FIXED_COLS, DecodeContext, M3dError
+
+DEFAULT_DECODE_LOWPASS_SIGMA = (3.0, 1.0, 1.0)  # PD:128
+DEFAULT_DECODE_MAGNITUDE_THRESHOLD = (1.5, 10.0)  # PD:129
+DEFAULT_2D_MINIMUM_PIXELS = 7.0  # PD:130
+DEFAULT_3D_MINIMUM_PIXELS = 16.0  # PD:131
+MAXIMUM_PIXELS = 500  # PD:2909
+
+# feature-table columns written by m3d_features (include/m3d_b200.h)
+_COL_FIRST, _COL_AREA, _COL_DEC = 0, 1, 2
+_COL_CZ, _COL_CY, _COL_CX = 3, 4, 5
+_COL_MU = 6  # zz, yy, xx, zy, zx, yx
+_COL_DMIN, _COL_MAGMEAN = 12, 13
+
+
+def _is_identity_store(datastore) -> bool:
+    return bool(getattr(datastore, "has_identity_decode_transforms", False))
+
+
+class PixelDecoder:
+    """Decode one or many tiles of a qi2labdatastore-shaped dataset on B200 GPUs.
+
+    Parameters are the reference's (PD:449-461).  ``use_mask``, ``estimate_chromatic_affines``
+    and ``chromatic_affine_config`` are accepted for signature compatibility; the opt-in
+    chromatic estimation is outside the hot path and raises ``NotImplementedError`` when
+    requested.
+    """
+
+    def __init__(
+        self,
+        datastore,
+        merfish_bits: int = 16,
+        num_gpus: int = 1,
+        verbose: int = 1,
+        use_mask: bool | None = False,
+        z_range: Sequence[int] | None = None,
+        decode_mode: Literal["auto", "2d", "3d"] = "auto",
+        estimate_chromatic_affines: bool = False,
+        chromatic_affine_config=None,
+        excluded_gene_ids: Sequence[str] | None = None,
+    ) -> None:
+        self._datastore_path = Path(datastore._datastore_path)
+        self._datastore = datastore
+        self._num_gpus = num_gpus
+        self._verbose = verbose
+        self._barcodes_filtered = False
+        self._n_merfish_bits = merfish_bits
+        if decode_mode not in {"auto", "2d", "3d"}:
+            raise ValueError("decode_mode must be one of 'auto', '2d', or '3d'.")
+        self._decode_mode = decode_mode
+        self._estimate_chromatic_affines = bool(estimate_chromatic_affines)
+        self._chromatic_affine_config = chromatic_affine_config
+        if decode_mode == "auto":
+            effective = "2d" if self._datastore.microscope_type == "2D" else "3d"
+        else:
+            effective = decode_mode
+        self._effective_decode_mode = effective
+        self._is_3D = effective != "2d"
+        self._decode_run_key = None
+        if z_range is None:
+            self._z_crop = False
+            self._z_range = [0, None]
+        else:
+            self._z_crop = True
+            self._z_range = [z_range[0], z_range[1]]
+        self._z_slice = slice(self._z_range[0], self._z_range[1])
+
+        self._load_codebook()
+        self._excluded_gene_ids, self._excluded_codeword_indices = self._resolve_excluded_gene_ids(
+            excluded_gene_ids
+        )
+        self._optimization_excluded_gene_ids = self._excluded_gene_ids
+        self._decoding_matrix_no_errors = self._normalize_codebook(include_errors=False)
+        self._decoding_matrix = self._decoding_matrix_no_errors.copy()
+        self._barcode_count = self._decoding_matrix.shape[0]
+        self._bit_count = self._decoding_matrix.shape[1]
+        self._mask_image = None
+        self._codebook_style = 1
+        self._optimize_normalization_weights = False
+        self._collect_chromatic_centroids = False
+        self._global_normalization_loaded = False
+        self._iterative_normalization_loaded = False
+        self._global_normalization_vector = None
+        self._global_background_vector = None
+        self._iterative_normalization_vector = None
+        self._iterative_background_vector = None
+        self._load_tile_decoding = False
+        self._contexts: dict[int, DecodeContext] = {}
+        self._context_excluded: dict[int, tuple] = {}
+        self._device_state: dict[int, dict] = {}
+
+    # ================================================================== codebook (PD:756-932)
+    def _load_codebook(self) -> None:
+        """PD:756-800: drop 1-on-bit rows, derive both thresholds from the code geometry."""
+        self._df_codebook = self._datastore.codebook.copy()
+        self._df_codebook = self._df_codebook.fillna(0)
+        bit_columns = self._df_codebook.columns[1 : self._n_merfish_bits + 1]
+        on_counts = self._df_codebook.loc[:, bit_columns].to_numpy(dtype=np.int8).sum(axis=1)
+        self._df_codebook = self._df_codebook.loc[on_counts != 1].reset_index(drop=True)
+        self._codebook_matrix = self._df_codebook.loc[:, bit_columns].to_numpy(dtype=int)
+        on = int(np.median(on_counts[on_counts != 1]))
+        self._pixel_assignment_threshold = float(
+            np.sqrt(2.0 - 2.0 * ((on - 2.0) / np.sqrt(on * (on - 2.0))))
+        )
+        self._transcript_distance_threshold = float(
+            np.sqrt(2.0 - 2.0 * (on / np.sqrt(on * (on + 2.0))))
+        )
+        self._blank_count = int(
+            self._df_codebook.iloc[:, 0].astype("string").str.lower().str.startswith("blank", na=False).sum()
+        )
+        self._gene_ids = self._df_codebook.iloc[:, 0].tolist()
+
+    def _resolve_excluded_gene_ids(self, excluded_gene_ids):
+        """PD:802-841: requested gene IDs -> (resolved ids, full-codebook row indices)."""
+        if not excluded_gene_ids:
+            return (), ()
+        requested, seen = [], set()
+        for value in excluded_gene_ids:
+            gene_id = str(value).strip()
+            if not gene_id or gene_id in seen:
+                continue
+            requested.append(gene_id)
+            seen.add(gene_id)
+        index_by_gene: dict[str, list[int]] = {}
+        for index, value in enumerate(self._gene_ids):
+            index_by_gene.setdefault(str(value), []).append(index)
+        unknown = [g for g in requested if g not in index_by_gene]
+        if unknown:
+            raise ValueError(
+                "Optimization exclusion gene IDs are not present in the active "
+                f"codebook: {', '.join(unknown)}. Matching is case-sensitive."
+            )
+        excluded_indices = tuple(i for g in requested for i in index_by_gene[g])
+        if len(excluded_indices) >= len(self._gene_ids):
+            raise ValueError("Optimization exclusions cannot remove every codeword.")
+        resolved_set = set(requested)
+        resolved = tuple(str(g) for g in self._gene_ids if str(g) in resolved_set)
+        return tuple(dict.fromkeys(resolved)), excluded_indices
+
+    def _codebook_fingerprint(self) -> str:
+        """PD:843-853."""
+        digest = hashlib.sha256()
+        matrix = np.ascontiguousarray(self._codebook_matrix, dtype=np.int8)
+        digest.update(np.asarray(matrix.shape, dtype=np.int64).tobytes())
+        for gene_id in self._gene_ids:
+            encoded = str(gene_id).encode("utf-8")
+            digest.update(len(encoded).to_bytes(8, byteorder="little"))
+            digest.update(encoded)
+        digest.update(matrix.tobytes())
+        return digest.hexdigest()
+
+    def _iterative_normalization_metadata(self) -> dict:
+        """PD:855-861."""
+        return {
+            "scope": "iterative_optimization",
+            "excluded_gene_ids": list(self._optimization_excluded_gene_ids),
+            "codebook_sha256": self._codebook_fingerprint(),
+        }
+
+    @staticmethod
+    def _suppress_excluded_codeword_assignments(decoded_trace, codebook_index_trace,
+                                                excluded_codeword_indices) -> None:
+        """PD:863-877 (host arrays; the device path fuses this into the decode kernels).
+
+        Works on NumPy arrays and torch tensors alike: excluded *winners* become background,
+        the signal never falls through to another codeword."""
+        if not excluded_codeword_indices:
+            return
+        if isinstance(decoded_trace, np.ndarray):
+            ex = np.asarray(excluded_codeword_indices, dtype=codebook_index_trace.dtype)
+            decoded_trace[np.isin(codebook_index_trace, ex)] = -1
+        else:
+            import torch
+
+            ex = torch.as_tensor(list(excluded_codeword_indices), dtype=codebook_index_trace.dtype,
+                                 device=codebook_index_trace.device)
+            decoded_trace[torch.isin(codebook_index_trace, ex)] = -1
+
+    def _normalize_codebook(self, gpu_id: int = 0, include_errors: bool = False) -> np.ndarray:
+        """PD:879-906: rows / ||row||_2 (zero norm -> 1), float64 on the host.  The reference's
+        ``include_errors=True`` expansion is dead code in 0.13 (PD:537) and not offered."""
+        if include_errors:
+            raise NotImplementedError("single-bit-error codebook expansion is not on the 0.13 decode path")
+        m = np.asarray(self._codebook_matrix[:, 0 : self._n_merfish_bits])
+        mag = np.linalg.norm(m, axis=1, keepdims=True)
+        mag[mag == 0] = 1
+        return m / mag
+
+    # ================================================================== device contexts
+    def _ctx(self, gpu_id: int = 0) -> DecodeContext:
+        """One C-ABI context per device; rebuilt when the exclusion set changes."""
+        key = tuple(self._excluded_codeword_indices)
+        ctx = self._contexts.get(gpu_id)
+        if ctx is None or self._context_excluded.get(gpu_id) != key:
+            if ctx is not None:
+                ctx.close()
+            ctx = DecodeContext(self._decoding_matrix.astype(np.float32), key, device=gpu_id)
+            self._contexts[gpu_id] = ctx
+            self._context_excluded[gpu_id] = key
+        return ctx
+
+    def launch_count(self) -> int:
+        """Kernels launched so far by this decoder's contexts (bench accounting)."""
+        return sum(c.launch_count() for c in self._contexts.values())
+
+    # ================================================================== normalisation state
+    def _effective_lowpass_sigma(self, sigma):
+        """PD:2026-2035."""
+        if sigma is None:
+            return None
+        sigma_zyx = tuple(float(v) for v in sigma)
+        if len(sigma_zyx) != 3:
+            raise ValueError("lowpass_sigma must contain three values: z, y, x.")
+        return sigma_zyx
+
+    @staticmethod
+    def _lowpass_active(sigma) -> bool:
+        return sigma is not None and not np.any(np.asarray(sigma, dtype=float) == 0)
+
+    def _default_minimum_pixels(self) -> float:
+        """PD:2037-2041."""
+        return DEFAULT_3D_MINIMUM_PIXELS if self._is_3D else DEFAULT_2D_MINIMUM_PIXELS
+
+    def _load_global_normalization_vectors(self, gpu_id: int = 0, recalculate: bool = False,
+                                           tile_indices=None,
+                                           lowpass_sigma=DEFAULT_DECODE_LOWPASS_SIGMA) -> None:
+        """PD:934-979."""
+        nv, bv = self._datastore.load_decode_normalization_vectors(self._decode_run_key, "global")
+        if not recalculate and nv is not None and bv is not None:
+            self._global_normalization_vector = np.asarray(nv, dtype=np.float32)
+            self._global_background_vector = np.asarray(bv, dtype=np.float32)
+            self._global_normalization_loaded = True
+        else:
+            self._global_normalization_vectors(gpu_id=gpu_id, tile_indices=tile_indices,
+                                               lowpass_sigma=lowpass_sigma)
+
+    def _global_normalization_vectors(self, low_percentile_cut: float = 10.0,
+                                      high_percentile_cut: float = 90.0,
+                                      hot_pixel_threshold: int = 50000, gpu_id: int = 0,
+                                      tile_indices=None,
+                                      lowpass_sigma=DEFAULT_DECODE_LOWPASS_SIGMA) -> None:
+        """PD:981-1199 on the device: per bit, hot-pixel replace -> z-crop -> low-pass ->
+        percentile-gated medians through a radix select (no sort, no host copy)."""
+        import torch
+
+        sigma = self._effective_lowpass_sigma(lowpass_sigma)
+        if tile_indices is not None:
+            tiles = [self._datastore.tile_ids[t] for t in tile_indices]
+        elif len(self._datastore.tile_ids) > 5:
+            tiles = sample(list(self._datastore.tile_ids), 5)
+        else:
+            tiles = list(self._datastore.tile_ids)
+        ctx = self._ctx(gpu_id)
+        dev = ctx.device
+        stats = _norm.DeviceOrderStats(ctx)
+        bit_ids = list(self._datastore.bit_ids)
+        per_bit = []
+        for bit_id in bit_ids:
+            vols = []
+            for tile_id in tiles:
+                readout = self._datastore.load_local_readout_image(tile=tile_id, bit=bit_id, return_future=False)
+                predictor = self._datastore.load_local_feature_predictor_image(
+                    tile=tile_id, bit=bit_id, return_future=False
+                )
+                self._require_identity_warp(tile_id, bit_id)
+                img = self._weighted_volume_device(readout, predictor, ctx)
+                # PD:1072-1074: hot pixels -> median of the middle plane
+                mid = img[img.shape[0] // 2]
+                med = stats.median([mid])
+                ctx.replace_above(img, float(hot_pixel_threshold), float(med))
+                img = img[self._z_slice].contiguous()
+                if self._lowpass_active(sigma) and img.numel():
+                    img = ctx.lowpass(img[None], sigma, not self._is_3D)[0]
+                vols.append(img)
+            per_bit.append(vols)
+            # one bit at a time keeps the peak at <= 5 volumes (+ low-pass temporaries)
+            nv1, bv1 = _norm.global_normalization_vectors(ctx, [vols], low_percentile_cut, high_percentile_cut)
+            per_bit[-1] = (nv1[0], bv1[0])
+            del vols
+        torch.cuda.synchronize(dev)
+        normalization_vector = np.asarray([p[0] for p in per_bit], dtype=np.float32)
+        background_vector = np.asarray([p[1] for p in per_bit], dtype=np.float32)
+        self._datastore.save_decode_normalization_vectors(
+            self._decode_run_key, "global", normalization_vector, background_vector,
+            decode_mode=self._effective_decode_mode,
+        )
+        self._global_background_vector = background_vector
+        self._global_normalization_vector = normalization_vector
+        self._global_normalization_loaded = True
+
+    def _load_iterative_normalization_vectors(self, gpu_id: int = 0) -> None:
+        """PD:1201-1248 (stale-codebook fingerprint -> ValueError)."""
+        load_md = getattr(self._datastore, "load_decode_normalization_metadata", None)
+        md = load_md(self._decode_run_key, "iterative") if callable(load_md) else None
+        expected = md.get("codebook_sha256") if isinstance(md, dict) else None
+        if expected is not None and expected != self._codebook_fingerprint():
+            raise ValueError(
+                "Cached iterative normalization vectors were fitted with a "
+                "different active codebook. Re-run iterative optimization."
+            )
+        nv, bv = self._datastore.load_decode_normalization_vectors(self._decode_run_key, "iterative")
+        if nv is not None and bv is not None:
+            bv = np.nan_to_num(bv, 0.0)
+            nv = np.nan_to_num(nv, 1.0)
+            self._iterative_normalization_vector = np.asarray(nv)
+            self._iterative_background_vector = np.asarray(bv)
+            self._iterative_normalization_loaded = True
+        else:
+            self._iterative_normalization_vectors(gpu_id=gpu_id)
+
+    def _iterative_normalization_vectors(self, gpu_id: int = 0) -> None:
+        """PD:1250-1421: per-bit medians over the pooled transcript table."""
+        if not hasattr(self, "_df_barcodes_loaded"):
+            raise ValueError("No decoded transcripts loaded: run optimize_normalization_by_decoding first.")
+        if self._iterative_background_vector is None and self._iterative_normalization_vector is None:
+            old_b = np.round(np.asarray(self._global_background_vector[0 : self._n_merfish_bits]), 1)
+            old_n = np.round(np.asarray(self._global_normalization_vector[0 : self._n_merfish_bits]), 1)
+        else:
+            old_b = np.asarray(self._iterative_background_vector)
+            old_n = np.asarray(self._iterative_normalization_vector)
+        res = _norm.iterative_normalization_vectors(self._df_barcodes_loaded, self._n_merfish_bits)
+        if res is None:
+            self._datastore.save_decode_normalization_vectors(
+                self._decode_run_key, "iterative", old_n.astype(np.float32), old_b.astype(np.float32),
+                decode_mode=self._effective_decode_mode, metadata=self._iterative_normalization_metadata(),
+            )
+            return
+        nv, bv = res
+        if self._verbose > 1:
+            print("Background delta:", np.round(np.abs(bv - old_b), 1))
+            print("Foreground delta:", np.round(np.abs(nv - old_n), 1))
+        self._iterative_normalization_vector = nv
+        self._iterative_background_vector = bv
+        self._datastore.save_decode_normalization_vectors(
+            self._decode_run_key, "iterative", nv, bv, decode_mode=self._effective_decode_mode,
+            metadata=self._iterative_normalization_metadata(),
+        )
+        self._iterative_normalization_loaded = True
+
+    def _prepare_normalization_state(self, normalization_method, use_normalization, gpu_id: int = 0,
+                                     lowpass_sigma=DEFAULT_DECODE_LOWPASS_SIGMA) -> None:
+        """PD:3274-3320."""
+        if normalization_method is None:
+            normalization_method = "iterative" if use_normalization else "none"
+        if normalization_method == "iterative":
+            self._load_iterative_normalization_vectors(gpu_id=gpu_id)
+        elif normalization_method == "global":
+            self._iterative_normalization_loaded = False
+            self._load_global_normalization_vectors(gpu_id=gpu_id, lowpass_sigma=lowpass_sigma)
+        elif normalization_method == "none":
+            self._iterative_normalization_loaded = False
+            self._global_normalization_loaded = False
+        else:
+            raise ValueError(
+                "normalization_method must be one of 'iterative', 'global', "
+                f"'none', or None. Got {normalization_method!r}."
+            )
+
+    def _active_vectors(self):
+        """Vector pair ``_decode_pixels`` applies (iterative wins, PD:2577-2592)."""
+        if self._iterative_normalization_loaded:
+            return self._iterative_background_vector, self._iterative_normalization_vector
+        if self._global_normalization_loaded:
+            return self._global_background_vector, self._global_normalization_vector
+        return None, None
+
+    # ================================================================== tile loading (PD:1828-1946)
+    def _require_identity_warp(self, tile, bit_id) -> None:
+        """Decode-time resampling (PD:1882-1889) is the 'next' row 8f-1; identity only here."""
+        if _is_identity_store(self._datastore):
+            return
+        ds = self._datastore
+        try:
+            rnd = ds.load_local_round_linker(tile=tile, bit=bit_id)
+            xf = ds.load_local_round_transform_zyx_um(tile=tile, round=rnd)
+            ok = xf is None or np.allclose(np.asarray(xf, dtype=float), np.eye(4))
+        except Exception as exc:  # unknown store surface -> refuse rather than silently skip warping
+            raise NotImplementedError(
+                "decode-time warping needs the reference's decode_warping path (SURVEY 8f-1); "
+                "this build decodes registered (identity-transform) data only"
+            ) from exc
+        if not ok:
+            raise NotImplementedError(
+                "non-identity round transform: decode-time warping is not built yet (SURVEY 8f-1)"
+            )
+
+    @staticmethod
+    def _is_unit_predictor(predictor) -> bool:
+        return predictor is None or type(predictor).__name__ == "UnitPredictor"
+
+    def _weighted_volume_device(self, readout, predictor, ctx):
+        """float32(readout) * float32(predictor) for one (z, y, x) volume, on the device."""
+        import torch
+
+        r = torch.from_numpy(np.ascontiguousarray(readout)).to(ctx.device, non_blocking=True)
+        if r.dtype == torch.float32:
+            img = r
+            if not self._is_unit_predictor(predictor):
+                img = img * torch.from_numpy(np.ascontiguousarray(predictor, dtype=np.float32)).to(ctx.device)
+            return img
+        if r.dtype not in (torch.uint16, torch.int16):
+            r = torch.from_numpy(np.ascontiguousarray(readout, dtype=np.uint16)).to(ctx.device)
+        p = None
+        if not self._is_unit_predictor(predictor):
+            p = torch.from_numpy(np.ascontiguousarray(predictor, dtype=np.float32)).to(ctx.device)
+        return ctx.weight(r, p)
+
+    def _load_bit_data(self, feature_predictor_threshold: float | None = 0.1, gpu_id: int = 0) -> None:
+        """PD:1828-1946: gather the tile's bit volumes into one device stack + coordinate metadata.
+
+        Device state: ``readout`` (bits, z, y, x) uint16 (or float32 when the store holds float
+        data) and ``predictor`` float32 / None (None = weight exactly 1, multiply skipped)."""
+        import torch
+
+        ctx = self._ctx(gpu_id)
+        bit_ids = list(self._datastore.bit_ids)[0 : self._n_merfish_bits]
+        readouts, predictors = [], []
+        self._em_wvl = []
+        for bit_id in bit_ids:
+            fr = self._datastore.load_local_readout_image(tile=self._tile_idx, bit=bit_id)
+            fp = self._datastore.load_local_feature_predictor_image(tile=self._tile_idx, bit=bit_id)
+            pa = fp.result() if hasattr(fp, "result") else fp
+            ra = fr.result() if hasattr(fr, "result") else fr
+            _ex, em = self._datastore.load_local_wavelengths_um(tile=self._tile_idx, bit=bit_id)
+            self._require_identity_warp(self._tile_idx, bit_id)
+            readouts.append(ra[self._z_slice, :, :])
+            predictors.append(None if self._is_unit_predictor(pa) else pa[self._z_slice, :, :])
+            self._em_wvl.append(em)
+        shape = tuple(readouts[0].shape)
+        if self._decode_mode == "3d" and shape[0] < 2:
+            raise ValueError("decode_mode='3d' requires at least two z planes after applying z_range.")
+        float_input = any(np.asarray(r).dtype.kind == "f" for r in readouts)
+        dt = torch.float32 if float_input else torch.uint16
+        npdt = np.float32 if float_input else np.uint16
+        stack = torch.empty((len(bit_ids), *shape), dtype=dt, device=ctx.device)
+        for b, r in enumerate(readouts):
+            stack[b].copy_(torch.from_numpy(np.ascontiguousarray(r, dtype=npdt)), non_blocking=True)
+        pred = None
+        if any(p is not None for p in predictors):
+            pred = torch.empty((len(bit_ids), *shape), dtype=torch.float32, device=ctx.device)
+            for b, p in enumerate(predictors):
+                if p is None:
+                    pred[b].fill_(1.0)
+                else:
+                    pred[b].copy_(torch.from_numpy(np.ascontiguousarray(p, dtype=np.float32)), non_blocking=True)
+        st = self._device_state.setdefault(gpu_id, {})
+        st.clear()
+        st["readout"], st["predictor"] = stack, pred
+        self._load_coordinate_metadata()
+
+    def _load_coordinate_metadata(self) -> None:
+        """PD:1900-1943."""
+        voxel = self._datastore.voxel_size_zyx_um
+        self._pixel_size = voxel[1]
+        self._axial_step = voxel[0]
+        stage_metadata = self._datastore.load_local_stage_position_zyx_um(tile=self._tile_idx, round=0)
+        stage_origin = None
+        cam = np.eye(4, dtype=np.float32)
+        if stage_metadata is not None:
+            stage_origin, cam = stage_metadata
+            stage_origin = np.asarray(stage_origin, dtype=np.float32)
+            cam = np.asarray(cam, dtype=np.float32)
+        affine, origin, spacing = self._datastore.load_global_coord_xforms_um(tile=self._tile_idx)
+        if affine is None or origin is None or spacing is None:
+            affine = np.eye(4)
+            if self._is_3D:
+                origin = stage_origin if stage_origin is not None else np.zeros(3, dtype=np.float32)
+            elif stage_origin is None:
+                origin = np.zeros(3, dtype=np.float32)
+            elif stage_origin.size == 2:
+                origin = np.asarray([0, stage_origin[0], stage_origin[1]], dtype=np.float32)
+            else:
+                origin = stage_origin
+            spacing = self._datastore.voxel_size_zyx_um
+        self._affine = np.asarray(affine, dtype=np.float32)
+        self._origin = np.asarray(origin, dtype=np.float32)
+        self._spacing = np.asarray(spacing, dtype=np.float32)
+        self._camera_to_stage_affine = cam
+
+    # ================================================================== kernels (PD:1948-2643)
+    def _lp_filter(self, gpu_id: int = 0, sigma=DEFAULT_DECODE_LOWPASS_SIGMA) -> None:
+        """PD:1982-2024: Gaussian low-pass of every bit volume (predictor multiply fused in)."""
+        st = self._device_state[gpu_id]
+        ctx = self._ctx(gpu_id)
+        st["stack"] = ctx.lowpass(st["readout"], sigma, not self._is_3D, predictor=st["predictor"])
+        self._filter_type = "lp"
+
+    def _prepare_decode_stack(self, gpu_id: int = 0) -> None:
+        """Raw path: the decode input is float32(readout) * predictor (PD:1879-1881)."""
+        st = self._device_state[gpu_id]
+        if "stack" in st:
+            return
+        if st["predictor"] is None:
+            st["stack"] = st["readout"]  # float32(uint16) is exact; kernels convert on load
+        else:
+            import torch
+
+            ctx = self._ctx(gpu_id)
+            if st["readout"].dtype == torch.float32:
+                st["stack"] = st["readout"] * st["predictor"]
+            else:
+                st["stack"] = ctx.weight(st["readout"], st["predictor"])
+
+    def _decode_pixels(self, magnitude_threshold=(1.1, 2.0), gpu_id: int = 0,
+                       materialize_images: bool = False) -> None:
+        """PD:2523-2643 as one fused pass: scale, clip, L2-normalise, nearest codeword, pixel
+        gate, magnitude gates, exclusions.  ``materialize_images`` also writes the float16
+        magnitude / distance / scaled images (the reference always does; here only for
+        ``return_results=True`` -- the feature kernel recomputes them otherwise)."""
+        import torch
+
+        st = self._device_state[gpu_id]
+        ctx = self._ctx(gpu_id)
+        self._prepare_decode_stack(gpu_id)
+        stack = st["stack"]
+        bkg, nrm = self._active_vectors()
+        ctx.set_normalization(bkg, nrm)
+        ctx.set_thresholds(self._pixel_assignment_threshold, magnitude_threshold[0], magnitude_threshold[1])
+        shape = tuple(stack.shape[1:])
+        st["decoded"] = torch.empty(shape, dtype=torch.int16, device=ctx.device)
+        mag = dist = scaled = None
+        if materialize_images:
+            mag = torch.empty(shape, dtype=torch.float16, device=ctx.device)
+            dist = torch.empty(shape, dtype=torch.float16, device=ctx.device)
+            scaled = torch.empty(tuple(stack.shape), dtype=torch.float16, device=ctx.device)
+        ctx.decode(stack, st["decoded"], mag, dist, scaled)
+        st["magnitude"], st["distance"], st["scaled"] = mag, dist, scaled
+
+    @staticmethod
+    def _warp_pixel(pixel_space_point, spacing, origin, affine, camera_to_stage_affine=None):
+        """PD:2645-2683: pixel -> physical -> stage -> global."""
+        physical = pixel_space_point * spacing + origin
+        if camera_to_stage_affine is not None:
+            physical = (np.asarray(camera_to_stage_affine) @ np.array([*list(physical), 1]))[:-1]
+        return (np.array(affine) @ np.array([*list(physical), 1]))[:-1]
+
+    def _decoded_z_to_source_z(self, decoded_z):
+        """PD:2685-2699."""
+        return float(self._z_range[0]) + decoded_z
+
+    # ================================================================== features (PD:2908-3201)
+    def _extract_barcodes(self, minimum_pixels: float = 3, maximum_pixels: int = MAXIMUM_PIXELS,
+                          gpu_id: int = 0) -> None:
+        """Connected components + size filters + regionprops on the device, annotation on
+        the host over the (small) feature table."""
+        st = self._device_state[gpu_id]
+        ctx = self._ctx(gpu_id)
+        n = ctx.label(st["decoded"], not self._is_3D, float(minimum_pixels), int(maximum_pixels))
+        table = ctx.features(st["stack"], st["decoded"], self._optimize_normalization_weights, n)
+        tab = table.cpu().numpy()
+        self._df_barcodes = self._annotate_table(tab)
+
+    def _table_columns(self) -> list[str]:
+        nb = self._n_merfish_bits
+        return (
+            ["area", "z", "y", "x"]
+            + [f"bit{i:02d}_mean_intensity" for i in range(1, nb + 1)]
+            + [f"inertia_tensor_eigvals-{k}" for k in range(3)]
+            + ["distance_min", "magnitude_mean", "barcode_id", "gene_id", "tile_idx"]
+            + [f"on_bit_{k}" for k in range(1, 5)]
+            + ["tile_z", "tile_y", "tile_x", "global_z", "global_y", "global_x"]
+            + ["signal_mean", "bkd_mean", "s-b_mean"]
+        )
+
+    @staticmethod
+    def _inertia_eigvals(tab: np.ndarray) -> np.ndarray:
+        """scikit-image ``inertia_tensor_eigvals`` from the central second moments."""
+        n = tab[:, _COL_AREA]
+        mu = tab[:, _COL_MU : _COL_MU + 6]
+        zz, yy, xx, zy, zx, yx = (mu[:, i] for i in range(6))
+        T = np.empty((tab.shape[0], 3, 3))
+        T[:, 0, 0] = (yy + xx) / n
+        T[:, 1, 1] = (zz + xx) / n
+        T[:, 2, 2] = (zz + yy) / n
+        T[:, 0, 1] = T[:, 1, 0] = -zy / n
+        T[:, 0, 2] = T[:, 2, 0] = -zx / n
+        T[:, 1, 2] = T[:, 2, 1] = -yx / n
+        ev = np.linalg.eigvalsh(T)
+        ev = np.clip(ev, 0, None)
+        return np.sort(ev, axis=1)[:, ::-1]
+
+    def _annotate_table(self, tab: np.ndarray) -> pd.DataFrame:
+        """PD:3066-3177 vectorised over the feature rows (row order = canonical id order)."""
+        nb = self._n_merfish_bits
+        cols = self._table_columns()
+        if tab.shape[0] == 0:
+            return pd.DataFrame({c: [] for c in cols})
+        dec = tab[:, _COL_DEC].astype(np.int32)
+        tab = tab[dec >= 0]
+        dec = dec[dec >= 0]
+        df = pd.DataFrame(
+            {"area": tab[:, _COL_AREA], "z": tab[:, _COL_CZ], "y": tab[:, _COL_CY], "x": tab[:, _COL_CX]}
+        )
+        bit_means = tab[:, M3D_TABLE_FIXED_COLS : M3D_TABLE_FIXED_COLS + nb]
+        for i in range(nb):
+            df[f"bit{i + 1:02d}_mean_intensity"] = bit_means[:, i]
+        ev = self._inertia_eigvals(tab) if tab.shape[0] else np.zeros((0, 3))
+        for k in range(3):
+            df[f"inertia_tensor_eigvals-{k}"] = ev[:, k]
+        df["distance_min"] = tab[:, _COL_DMIN]
+        df["magnitude_mean"] = tab[:, _COL_MAGMEAN]
+        df["barcode_id"] = dec + 1
+        df["gene_id"] = [self._gene_ids[i] for i in dec]
+        df["tile_idx"] = self._tile_idx
+        codebook_bool = self._codebook_matrix.astype(bool, copy=False)
+        on0 = np.argsort(~codebook_bool, axis=1)[:, :4].astype(np.int32)  # PD:3101, verbatim
+        on_sel = (on0 + 1)[dec]
+        for k in range(4):
+            df[f"on_bit_{k + 1}"] = on_sel[:, k]
+        if self._z_crop:
+            df["z"] = self._decoded_z_to_source_z(df["z"])
+        df["tile_z"] = np.round(df["z"], 0).astype(int)
+        df["tile_y"] = np.round(df["y"], 0).astype(int)
+        df["tile_x"] = np.round(df["x"], 0).astype(int)
+        pts = df[["z", "y", "x"]].to_numpy(dtype=np.float64, copy=True)
+        # _warp_pixel over all rows at once (same float64 operations per row, PD:3134-3141)
+        phys = pts * self._spacing + self._origin
+        cam = np.asarray(self._camera_to_stage_affine)
+        hom = np.concatenate([phys, np.ones((phys.shape[0], 1))], axis=1)
+        phys = np.stack([(cam @ h)[:-1] for h in hom]) if len(hom) else phys
+        hom = np.concatenate([phys, np.ones((phys.shape[0], 1))], axis=1)
+        aff = np.array(self._affine)
+        glob = np.stack([(aff @ h)[:-1] for h in hom]) if len(hom) else phys
+        df["global_z"] = np.round(glob[:, 0], 2)
+        df["global_y"] = np.round(glob[:, 1], 2)
+        df["global_x"] = np.round(glob[:, 2], 2)
+        total = bit_means.sum(axis=1)
+        sig = np.take_along_axis(bit_means, on_sel - 1, axis=1).sum(axis=1)
+        df["signal_mean"] = sig / 4.0
+        df["bkd_mean"] = (total - sig) / float(nb - 4)
+        df["s-b_mean"] = df["signal_mean"] - df["bkd_mean"]
+        df = df[df["distance_min"] <= self._transcript_distance_threshold].reset_index(drop=True)
+        return df[cols]
+
+    # ================================================================== results / persistence
+    def _save_barcodes(self) -> None:
+        """PD:3203-3233."""
+        if self._optimize_normalization_weights:
+            d = Path(self._temp_dir)
+            d.mkdir(parents=True, exist_ok=True)
+            self._df_barcodes.to_parquet(d / ("tile" + str(self._tile_idx).zfill(3) + "_temp_decoded.parquet"))
+        elif not self._barcodes_filtered:
+            self._datastore.save_local_decoded_spots(self._df_barcodes, tile=self._tile_idx,
+                                                     decode_run_key=self._decode_run_key)
+        else:
+            self._datastore.save_global_filtered_decoded_spots(self._df_filtered_barcodes,
+                                                               decode_run_key=self._decode_run_key)
+
+    @property
+    def decoded_barcodes(self) -> pd.DataFrame:
+        """PD:3235-3247."""
+        if not hasattr(self, "_df_barcodes"):
+            return pd.DataFrame()
+        return self._df_barcodes.copy()
+
+    @property
+    def decoded_image(self) -> np.ndarray:
+        """PD:3249-3261 (device -> host on access)."""
+        for st in self._device_state.values():
+            if st.get("decoded") is not None:
+                return st["decoded"].cpu().numpy()
+        return np.empty((0,), dtype=np.int16)
+
+    def save_decoded_barcodes(self) -> None:
+        """PD:3263-3272."""
+        self._save_barcodes()
+
+    def _load_all_barcodes(self) -> None:
+        """PD:3322-3384 (cell restriction is out of scope: no segmentation in the configs)."""
+        if self._optimize_normalization_weights:
+            files = sorted(Path(self._temp_dir).glob("*.parquet"), key=lambda p: p.name)
+            data = [pd.read_parquet(f) for f in files]
+            self._df_barcodes_loaded = pd.concat(data) if data else pd.DataFrame()
+        elif self._load_tile_decoding:
+            data = [
+                self._datastore.load_local_decoded_spots(t, decode_run_key=self._decode_run_key)
+                for t in self._datastore.tile_ids
+            ]
+            self._df_barcodes_loaded = pd.concat([d for d in data if d is not None])
+        else:
+            self._df_filtered_barcodes = self._datastore.load_global_filtered_decoded_spots(
+                decode_run_key=self._decode_run_key
+            )
+            self._df_barcodes_loaded = self._df_filtered_barcodes.copy()
+            self._barcodes_filtered = True
+        if self._df_barcodes_loaded.empty:
+            if "gene_id" not in self._df_barcodes_loaded.columns:
+                self._df_barcodes_loaded["gene_id"] = pd.Series(dtype="string")
+            for column in ("distance_min", "magnitude_mean", "area"):
+                if column not in self._df_barcodes_loaded.columns:
+                    self._df_barcodes_loaded[column] = pd.Series(dtype=np.float32)
+        g = self._df_barcodes_loaded["gene_id"]
+        self._df_barcodes_loaded = self._df_barcodes_loaded[g.notna() & g.astype(str).str.strip().ne("")]
+        if "distance_min" not in self._df_barcodes_loaded.columns:
+            raise ValueError(
+                "Decoded transcripts are missing 'distance_min'. "
+                "Re-decode local transcript parquet files with the exact two-threshold caller."
+            )
+
+    def _cleanup(self) -> None:
+        """PD:4426-4469: drop device buffers and per-tile results."""
+        for st in self._device_state.values():
+            st.clear()
+        for name in ("_df_barcodes", "_df_filtered_barcodes"):
+            if hasattr(self, name):
+                delattr(self, name)
+
+    # ================================================================== public API
+    def decode_one_tile(
+        self,
+        tile_idx: int = 0,
+        gpu_id: int = 0,
+        display_results: bool = False,
+        return_results: bool = False,
+        lowpass_sigma: Sequence[float] | None = DEFAULT_DECODE_LOWPASS_SIGMA,
+        magnitude_threshold: Sequence[float] | None = None,
+        minimum_pixels: float | None = None,
+        use_normalization: bool | None = True,
+        normalization_method: Literal["iterative", "global", "none"] | None = None,
+        feature_predictor_threshold: float | None = 0.1,
+    ):
+        """PD:4471-4579.  With ``return_results=True`` returns the reference's tuple
+        ``(image[_lp] float32 (bits,z,y,x), scaled float16, magnitude float16, distance
+        float16, decoded int16)`` as host arrays."""
+        if display_results:
+            raise NotImplementedError("napari display is outside the decode hot path")
+        if magnitude_threshold is None:
+            magnitude_threshold = DEFAULT_DECODE_MAGNITUDE_THRESHOLD
+        if minimum_pixels is None:
+            minimum_pixels = self._default_minimum_pixels()
+        self._prepare_normalization_state(normalization_method, use_normalization, gpu_id, lowpass_sigma)
+        self._tile_idx = tile_idx
+        self._load_bit_data(feature_predictor_threshold=feature_predictor_threshold, gpu_id=gpu_id)
+        self._filter_type = "raw"
+        sigma = self._effective_lowpass_sigma(lowpass_sigma)
+        if self._lowpass_active(sigma):
+            self._lp_filter(sigma=sigma, gpu_id=gpu_id)
+        self._decode_pixels(magnitude_threshold=magnitude_threshold, gpu_id=gpu_id,
+                            materialize_images=return_results)
+        self._extract_barcodes(minimum_pixels=minimum_pixels, gpu_id=gpu_id)
+        if return_results:
+            import torch
+
+            st = self._device_state[gpu_id]
+            image = st["stack"]
+            if image.dtype != torch.float32:
+                image = image.to(torch.float32)
+            return (
+                image.cpu().numpy(),
+                st["scaled"].cpu().numpy(),
+                st["magnitude"].cpu().numpy(),
+                st["distance"].cpu().numpy(),
+                st["decoded"].cpu().numpy(),
+            )
+        return None
+
+    # ------------------------------------------------------------------ multi-GPU plumbing
+    @staticmethod
+    def _dist():
+        """(rank, world_size, module) when running under an initialised process group."""
+        try:
+            import torch.distributed as dist
+        except Exception:  # pragma: no cover
+            return 0, 1, None
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size(), dist
+        return 0, 1, None
+
+    @staticmethod
+    def _contiguous_chunks(items, n_parts):
+        """PD:4811-4818: ceil-sized contiguous subsets, one per GPU (empty ones dropped)."""
+        chunk = (len(items) + n_parts - 1) // n_parts if n_parts > 0 else len(items)
+        out = []
+        for g in range(n_parts):
+            sub = items[g * chunk : min((g + 1) * chunk, len(items))]
+            out.append(list(sub))
+        return out
+
+    def _worker_clone(self, gpu_id: int) -> "PixelDecoder":
+        """Per-device decoder sharing the datastore and the loaded vectors (the reference
+        builds a fresh decoder per worker process, PD:249-268)."""
+        w = PixelDecoder(
+            self._datastore, merfish_bits=self._n_merfish_bits, num_gpus=1, verbose=0,
+            z_range=None if not self._z_crop else self._z_range, decode_mode=self._decode_mode,
+            excluded_gene_ids=self._optimization_excluded_gene_ids
+            if self._optimize_normalization_weights else self._excluded_gene_ids,
+        )
+        w._optimize_normalization_weights = self._optimize_normalization_weights
+        w._temp_dir = getattr(self, "_temp_dir", None)
+        return w
+
+    def _run_tiles(self, tiles, per_tile):
+        """Run ``per_tile(decoder, tile_idx, gpu_id)`` for this rank's tiles.
+
+        Under torch.distributed: contiguous chunk of ``tiles`` for this rank, on the current
+        device.  Otherwise: one host thread per local GPU, contiguous chunks like PD:4811."""
+        import torch
+
+        rank, world, dist = self._dist()
+        if dist is not None and world > 1:
+            mine = self._contiguous_chunks(list(tiles), world)[rank]
+            gpu = torch.cuda.current_device()
+            for t in mine:
+                per_tile(self, t, gpu)
+            return
+        n = max(1, min(int(self._num_gpus), torch.cuda.device_count() or 1))
+        chunks = [c for c in self._contiguous_chunks(list(tiles), n) if c]
+        if len(chunks) <= 1:
+            for t in (chunks[0] if chunks else []):
+                per_tile(self, t, 0)
+            return
+
+        def work(args):
+            gpu, subset = args
+            torch.cuda.set_device(gpu)
+            dec = self._worker_clone(gpu)
+            dec._global_normalization_vector = self._global_normalization_vector
+            dec._global_background_vector = self._global_background_vector
+            dec._global_normalization_loaded = self._global_normalization_loaded
+            for t in subset:
+                per_tile(dec, t, gpu)
+            dec._cleanup()
+
+        with ThreadPoolExecutor(max_workers=len(chunks)) as ex:
+            list(ex.map(work, list(enumerate(chunks))))
+
+    def _barrier(self):
+        _r, world, dist = self._dist()
+        if dist is not None and world > 1:
+            dist.barrier()
+
+    def _gather_tables(self, local: pd.DataFrame) -> pd.DataFrame:
+        """All-gather the per-rank transcript tables (variable length) so every rank computes
+        identical medians (the statistic is a median -- a sum all-reduce would
+        change the result)."""
+        _r, world, dist = self._dist()
+        if dist is None or world == 1:
+            return local
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local)
+        parts = [g for g in gathered if g is not None and len(g)]
+        return pd.concat(parts, ignore_index=True) if parts else local
+
+    def optimize_normalization_by_decoding(
+        self,
+        n_random_tiles: int = 5,
+        n_iterations: int = 10,
+        minimum_pixels: float | None = None,
+        feature_predictor_threshold: float | None = 0.1,
+        lowpass_sigma: Sequence[float] | None = DEFAULT_DECODE_LOWPASS_SIGMA,
+        magnitude_threshold: Sequence[float] | None = None,
+        tile_indices: Sequence[int] | None = None,
+        estimate_chromatic_affines: bool | None = None,
+        excluded_gene_ids: Sequence[str] | None = None,
+    ) -> None:
+        """PD:4581-4757: global seed, then ``n_iterations`` of decode -> per-bit medians.
+
+        Iteration 0 decodes with the global vectors, later ones with the iterative vectors
+        (PD:395-405).  Tables are handed over in memory (and all-gathered across ranks);
+        the per-tile parquet files of the reference are still written to the temporary
+        directory so the on-disk layout matches."""
+        if self._num_gpus < 1:
+            raise RuntimeError("No GPUs allocated.")
+        if magnitude_threshold is None:
+            magnitude_threshold = DEFAULT_DECODE_MAGNITUDE_THRESHOLD
+        if minimum_pixels is None:
+            minimum_pixels = self._default_minimum_pixels()
+        self._optimization_excluded_gene_ids, excluded_idx = self._resolve_excluded_gene_ids(excluded_gene_ids)
+        blank_excl = [g for g in self._optimization_excluded_gene_ids if g.lower().startswith("blank")]
+        if blank_excl:
+            warnings.warn(
+                "Blank codewords already do not contribute to iterative "
+                "normalization; excluding them only suppresses their temporary "
+                "assignments: " + ", ".join(blank_excl),
+                stacklevel=2,
+            )
+        run_chromatic = (
+            self._estimate_chromatic_affines if estimate_chromatic_affines is None else bool(estimate_chromatic_affines)
+        )
+        if run_chromatic:
+            raise NotImplementedError("RNA-derived chromatic affine estimation is outside the hot path (SURVEY 2 #9)")
+        all_tiles = list(range(len(self._datastore.tile_ids)))
+        self._iterative_background_vector = None
+        self._iterative_normalization_vector = None
+        self._global_background_vector = None
+        self._optimize_normalization_weights = True
+        saved_excluded = (self._excluded_gene_ids, self._excluded_codeword_indices)
+        self._excluded_gene_ids = self._optimization_excluded_gene_ids
+        self._excluded_codeword_indices = excluded_idx
+        rank, world, dist = self._dist()
+        try:
+            if rank == 0:
+                self._load_global_normalization_vectors(gpu_id=self._local_gpu(), recalculate=True,
+                                                        tile_indices=tile_indices, lowpass_sigma=lowpass_sigma)
+            self._barrier()
+            if rank != 0:
+                self._load_global_normalization_vectors(gpu_id=self._local_gpu(), lowpass_sigma=lowpass_sigma)
+            temp_dir = Path(tempfile.mkdtemp()) if self._decode_run_key is None else \
+                self._datastore.decoded_temporary_dir(self._decode_run_key)
+            temp_dir.mkdir(parents=True, exist_ok=True)
+            self._temp_dir = temp_dir
+            if tile_indices is not None:
+                random_tiles = list(tile_indices)
+            elif len(all_tiles) > n_random_tiles:
+                random_tiles = sample(all_tiles, n_random_tiles)
+                if dist is not None and world > 1:
+                    box = [random_tiles]
+                    dist.broadcast_object_list(box, src=0)
+                    random_tiles = box[0]
+            else:
+                random_tiles = all_tiles
+            for iteration in range(n_iterations):
+                use_norm = iteration > 0
+                tables: list[pd.DataFrame] = []
+
+                def per_tile(dec, tile_idx, gpu, _use=use_norm):
+                    dec.decode_one_tile(
+                        tile_idx=tile_idx, gpu_id=gpu, lowpass_sigma=lowpass_sigma,
+                        magnitude_threshold=magnitude_threshold, minimum_pixels=minimum_pixels,
+                        feature_predictor_threshold=feature_predictor_threshold,
+                        normalization_method="iterative" if _use else "global",
+                    )
+                    dec._save_barcodes()
+                    tables.append((tile_idx, dec._df_barcodes))
+
+                self._run_tiles(random_tiles, per_tile)
+                tables.sort(key=lambda t: t[0])
+                local = pd.concat([t[1] for t in tables], ignore_index=True) if tables else pd.DataFrame()
+                pooled = self._gather_tables(local)
+                if len(pooled) == 0 and "gene_id" not in pooled.columns:
+                    pooled = pd.DataFrame({"gene_id": pd.Series(dtype="string")})
+                g = pooled["gene_id"]
+                self._df_barcodes_loaded = pooled[g.notna() & g.astype(str).str.strip().ne("")]
+                if not self._is_3D:
+                    self._remove_duplicates_within_tile(
+                        radius_xy=self._datastore.voxel_size_zyx_um[-1],
+                        radius_z=self._datastore.voxel_size_zyx_um[0],
+                    )
+                self._load_global_normalization_vectors(gpu_id=self._local_gpu(), lowpass_sigma=lowpass_sigma)
+                if rank == 0:
+                    self._iterative_normalization_vectors(gpu_id=self._local_gpu())
+                self._barrier()
+                if rank != 0:
+                    self._iterative_normalization_vector = None
+                    self._load_iterative_normalization_vectors(gpu_id=self._local_gpu())
+                self._global_background_vector = None
+                self._global_normalization_vector = None
+        finally:
+            self._excluded_gene_ids, self._excluded_codeword_indices = saved_excluded
+            self._cleanup()
+            self._optimize_normalization_weights = False
+        if self._decode_run_key is None and rank == 0:
+            shutil.rmtree(temp_dir, ignore_errors=True)
+
+    def _local_gpu(self) -> int:
+        import torch
+
+        _r, world, dist = self._dist()
+        return torch.cuda.current_device() if (dist is not None and world > 1) else 0
+
+    def _remove_duplicates_within_tile(self, radius_xy: float, radius_z: float) -> None:
+        """PD:4179-4363 (2-D mode only): collapse same-gene detections split across adjacent z
+        planes.  Same tile, same gene, XY distance <= radius_xy, 0 < |dz| <= radius_z;
+        union-find clusters; keep the smallest ``distance_min`` (ties: first row)."""
+        from scipy.spatial import cKDTree
+
+        df = self._df_barcodes_loaded
+        if df is None or len(df) == 0:
+            return
+        df = df.reset_index(drop=True)
+        keep = np.ones(len(df), dtype=bool)
+        for (_tile, _gene), grp in df.groupby(["tile_idx", "gene_id"], sort=False):
+            if len(grp) < 2:
+                continue
+            idx = grp.index.to_numpy()
+            xy = grp[["global_y", "global_x"]].to_numpy(dtype=float)
+            z = grp["global_z"].to_numpy(dtype=float)
+            pairs = cKDTree(xy).query_pairs(float(radius_xy), output_type="ndarray")
+            if pairs.size == 0:
+                continue
+            dz = np.abs(z[pairs[:, 0]] - z[pairs[:, 1]])
+            pairs = pairs[(dz > 0) & (dz <= float(radius_z) + 1e-9)]
+            if pairs.size == 0:
+                continue
+            parent = np.arange(len(idx))
+
+            def find(a):
+                while parent[a] != a:
+                    parent[a] = parent[parent[a]]
+                    a = parent[a]
+                return a
+
+            for a, b in pairs:
+                ra, rb = find(a), find(b)
+                if ra != rb:
+                    parent[max(ra, rb)] = min(ra, rb)
+            roots = np.array([find(a) for a in range(len(idx))])
+            dmin = grp["distance_min"].to_numpy(dtype=float)
+            for r in np.unique(roots):
+                members = np.flatnonzero(roots == r)
+                if members.size > 1:
+                    best = members[np.argmin(dmin[members])]
+                    drop = members[members != best]
+                    keep[idx[drop]] = False
+        self._df_barcodes_loaded = df[keep].reset_index(drop=True)
+
+    def decode_all_tiles(
+        self,
+        assign_to_cells: bool = True,
+        lowpass_sigma: Sequence[float] | None = DEFAULT_DECODE_LOWPASS_SIGMA,
+        magnitude_threshold: Sequence[float] | None = None,
+        minimum_pixels: float | None = None,
+        feature_predictor_threshold: float | None = 0.1,
+        normalization_method: Literal["iterative", "global", "none"] = "iterative",
+        duplicate_radius_xy: float | None = None,
+        duplicate_radius_z: float | None = None,
+        filter_method: Literal["blank_fraction", "lr"] = "blank_fraction",
+        target_gross_misid_rate: float = 0.05,
+        lr_fdr_target: float = 0.05,
+    ) -> None:
+        """PD:4759-4870, decode stage: every tile -> ``decoded/<tile>_decoded_features.parquet``.
+
+        Tiles are sharded in contiguous chunks over GPUs (ranks or local devices) with no
+        data-path collective.  The downstream table filters (blank-fraction / LR, overlap
+        de-duplication, cell assignment: SURVEY 8f-3) are not part of this build; the pooled
+        unfiltered table is left in ``_df_barcodes_loaded``."""
+        if self._num_gpus < 1:
+            raise RuntimeError("No GPUs allocated.")
+        if magnitude_threshold is None:
+            magnitude_threshold = DEFAULT_DECODE_MAGNITUDE_THRESHOLD
+        if minimum_pixels is None:
+            minimum_pixels = self._default_minimum_pixels()
+        self._validate_filter_configuration(filter_method, float(target_gross_misid_rate), float(lr_fdr_target))
+        all_tiles = list(range(len(self._datastore.tile_ids)))
+        self._optimize_normalization_weights = False
+
+        def per_tile(dec, tile_idx, gpu):
+            dec.decode_one_tile(
+                tile_idx=tile_idx, gpu_id=gpu, lowpass_sigma=lowpass_sigma,
+                magnitude_threshold=magnitude_threshold, minimum_pixels=minimum_pixels,
+                feature_predictor_threshold=feature_predictor_threshold,
+                normalization_method=normalization_method,
+            )
+            dec._save_barcodes()
+            dec._cleanup()
+
+        self._run_tiles(all_tiles, per_tile)
+        self._barrier()
+        self._load_tile_decoding = True
+        self._load_all_barcodes()
+        if self._verbose >= 1:
+            print(f"Number of loaded barcodes: {len(self._df_barcodes_loaded)}")
+
+    @staticmethod
+    def _validate_filter_configuration(filter_method, target_gross_misid_rate, lr_fdr_target) -> None:
+        """PD:4872-4913."""
+        if filter_method == "blank_fraction":
+            if lr_fdr_target != 0.05:
+                raise ValueError(
+                    "lr_fdr_target only applies when filter_method='lr'. "
+                    "Use target_gross_misid_rate with filter_method='blank_fraction'."
+                )
+            return
+        if filter_method == "lr":
+            if target_gross_misid_rate != 0.05:
+                raise ValueError(
+                    "target_gross_misid_rate only applies when "
+                    "filter_method='blank_fraction'. Use lr_fdr_target with "
+                    "filter_method='lr'."
+                )
+            return
+        raise ValueError("filter_method must be one of 'blank_fraction' or 'lr'.")
+
+    def optimize_filtering(self, *args, **kwargs) -> None:
+        """PD:4952-5029 re-filters saved tables on the CPU; outside the hot path (8f-3)."""
+        raise NotImplementedError("transcript filtering is the 'next' row 8f-3, not part of this build")
+
+
+__all__ = ["PixelDecoder", "M3dError"]

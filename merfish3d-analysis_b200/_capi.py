@@ -1,0 +1,339 @@
+"""ctypes binding of ``libm3d_b200.so`` (the C ABI declared in ``include/m3d_b200.h``).
+
+PyTorch is used only for device memory and streams: every array crossing this boundary is
+a raw device pointer taken from a torch tensor.  There is NO CPU fallback -- if the shared
+library is missing or no CUDA device is visible, calls raise.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libm3d_b200.so"
+
+M3D_DTYPE_U16 = 0
+M3D_DTYPE_F32 = 1
+M3D_TABLE_FIXED_COLS = 14
+M3D_MAX_BITS = 32
+
+_c_i64_3 = C.c_int64 * 3
+_c_f64_3 = C.c_double * 3
+
+# name -> (restype, argtypes); must list every symbol the header declares
+SIGNATURES = {
+    "m3d_abi_version": (C.c_int, []),
+    "m3d_last_error": (C.c_char_p, []),
+    "m3d_create": (
+        C.c_int,
+        [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)],
+    ),
+    "m3d_destroy": (C.c_int, [C.c_void_p]),
+    "m3d_set_normalization": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "m3d_set_thresholds": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float]),
+    "m3d_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "m3d_lowpass": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int64),
+         C.POINTER(C.c_double), C.c_int, C.c_void_p, C.c_void_p],
+    ),
+    "m3d_decode": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "m3d_label": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_double, C.c_int,
+         C.c_void_p, C.POINTER(C.c_int64), C.c_void_p],
+    ),
+    "m3d_features": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_int,
+         C.c_void_p, C.c_int64, C.c_void_p],
+    ),
+    "m3d_select_hist": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_int, C.c_int, C.c_float,
+         C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p],
+    ),
+    "m3d_replace_above": (
+        C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p]
+    ),
+    "m3d_launch_count": (C.c_int64, [C.c_void_p]),
+    "m3d_kernel_name": (C.c_char_p, [C.c_int]),
+    "m3d_kernel_launches": (C.c_int64, [C.c_void_p, C.c_int]),
+    "m3d_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "m3d_reset_counters": (C.c_int, [C.c_void_p]),
+    "m3d_kernel_time_ms": (C.c_double, [C.c_void_p, C.c_int]),
+}
+
+_lib = None
+
+
+class M3dError(RuntimeError):
+    """Raised when a libm3d_b200 call returns a negative status."""
+
+
+def load_library():
+    """dlopen the in-tree shared library and attach signatures.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise M3dError(
+            f"{LIB_PATH} is missing: build it with `python -m merfish3d_analysis_b200.build` "
+            "(there is no CPU fallback)"
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load_library().m3d_last_error()
+        raise M3dError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def _ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise M3dError("libm3d_b200 takes device memory only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise M3dError("libm3d_b200 takes contiguous tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _dtype_code(t) -> int:
+    import torch
+
+    if t.dtype == torch.uint16 or t.dtype == torch.int16:
+        return M3D_DTYPE_U16
+    if t.dtype == torch.float32:
+        return M3D_DTYPE_F32
+    raise M3dError(f"unsupported stack dtype {t.dtype}; expected uint16 or float32")
+
+
+class DecodeContext:
+    """One ``m3d_ctx`` per process/GPU: resident codebook, thresholds, scratch."""
+
+    def __init__(self, codebook_unit: np.ndarray, excluded=(), device: int = 0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise M3dError("no CUDA device visible: the B200 decode path has no CPU fallback")
+        self._lib = load_library()
+        cb = np.ascontiguousarray(codebook_unit, dtype=np.float32)
+        if cb.ndim != 2:
+            raise ValueError("codebook_unit must be (K, bits)")
+        self.n_codewords, self.n_bits = int(cb.shape[0]), int(cb.shape[1])
+        ex = np.ascontiguousarray(np.asarray(list(excluded), dtype=np.int32))
+        self.device = torch.device("cuda", int(device))
+        handle = C.c_void_p()
+        _check(
+            self._lib.m3d_create(
+                int(device), self.n_bits, self.n_codewords, cb.ctypes.data_as(C.c_void_p),
+                ex.ctypes.data_as(C.c_void_p) if ex.size else None, int(ex.size), C.byref(handle),
+            ),
+            "m3d_create",
+        )
+        self._h = handle
+        self._n_features = -1
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.m3d_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ state
+    def set_normalization(self, background, normalization):
+        if background is None or normalization is None:
+            _check(self._lib.m3d_set_normalization(self._h, None, None), "m3d_set_normalization")
+            return
+        b = np.ascontiguousarray(np.asarray(background, dtype=np.float32)[: self.n_bits])
+        n = np.ascontiguousarray(np.asarray(normalization, dtype=np.float32)[: self.n_bits])
+        if b.size != self.n_bits or n.size != self.n_bits:
+            raise ValueError("normalisation vectors shorter than the bit count")
+        _check(
+            self._lib.m3d_set_normalization(
+                self._h, b.ctypes.data_as(C.c_void_p), n.ctypes.data_as(C.c_void_p)
+            ),
+            "m3d_set_normalization",
+        )
+
+    def set_thresholds(self, pixel_threshold: float, magnitude_lo: float, magnitude_hi: float):
+        # the reference compares float32 arrays with weak Python scalars (NEP 50): thresholds
+        # act as float32 values
+        _check(
+            self._lib.m3d_set_thresholds(
+                self._h, float(np.float32(pixel_threshold)), float(np.float32(magnitude_lo)),
+                float(np.float32(magnitude_hi)),
+            ),
+            "m3d_set_thresholds",
+        )
+
+    # ------------------------------------------------------------------ kernels
+    @staticmethod
+    def _dims(shape_zyx):
+        return _c_i64_3(*[int(s) for s in shape_zyx])
+
+    def weight(self, readout, predictor, out=None):
+        import torch
+
+        if out is None:
+            out = torch.empty(readout.shape, dtype=torch.float32, device=readout.device)
+        _check(
+            self._lib.m3d_weight(self._h, _ptr(readout), _ptr(predictor), readout.numel(),
+                                 _ptr(out), _stream(self.device)),
+            "m3d_weight",
+        )
+        return out
+
+    def lowpass(self, stack, sigma, mode2d: bool, predictor=None, out=None):
+        """stack: (n_vols, z, y, x) uint16/float32 device tensor -> float32 low-passed."""
+        import torch
+
+        if stack.dim() != 4:
+            raise ValueError("stack must be (n_vols, z, y, x)")
+        if out is None:
+            out = torch.empty(stack.shape, dtype=torch.float32, device=stack.device)
+        sg = _c_f64_3(*[float(s) for s in sigma])
+        _check(
+            self._lib.m3d_lowpass(
+                self._h, _ptr(stack), _dtype_code(stack), _ptr(predictor), int(stack.shape[0]),
+                self._dims(stack.shape[1:]), sg, 1 if mode2d else 0, _ptr(out),
+                _stream(self.device),
+            ),
+            "m3d_lowpass",
+        )
+        return out
+
+    def decode(self, stack, decoded=None, magnitude=None, distance=None, scaled=None):
+        """stack: (bits, z, y, x).  Writes int16 decoded (z, y, x); optional float16 images."""
+        import torch
+
+        if stack.dim() != 4 or stack.shape[0] != self.n_bits:
+            raise ValueError(f"stack must be ({self.n_bits}, z, y, x)")
+        if decoded is None:
+            decoded = torch.empty(stack.shape[1:], dtype=torch.int16, device=stack.device)
+        _check(
+            self._lib.m3d_decode(
+                self._h, _ptr(stack), _dtype_code(stack), self._dims(stack.shape[1:]),
+                _ptr(decoded), _ptr(magnitude), _ptr(distance), _ptr(scaled),
+                _stream(self.device),
+            ),
+            "m3d_decode",
+        )
+        return decoded
+
+    def label(self, decoded, mode2d: bool, minimum_pixels: float, maximum_pixels: int = 500,
+              labels=None) -> int:
+        n = C.c_int64(-1)
+        _check(
+            self._lib.m3d_label(
+                self._h, _ptr(decoded), self._dims(decoded.shape), 1 if mode2d else 0,
+                float(minimum_pixels), int(maximum_pixels), _ptr(labels), C.byref(n),
+                _stream(self.device),
+            ),
+            "m3d_label",
+        )
+        self._n_features = int(n.value)
+        return self._n_features
+
+    def features(self, stack, decoded, optimize_mode: bool, n_rows: int | None = None):
+        """Feature table (n_rows, 14 + bits) float64 on the device for the last ``label``."""
+        import torch
+
+        n = self._n_features if n_rows is None else int(n_rows)
+        if n < 0:
+            raise M3dError("features() before label()")
+        table = torch.empty((n, M3D_TABLE_FIXED_COLS + self.n_bits), dtype=torch.float64,
+                            device=stack.device)
+        if n == 0:
+            return table
+        _check(
+            self._lib.m3d_features(
+                self._h, _ptr(stack), _dtype_code(stack), self._dims(stack.shape[1:]),
+                _ptr(decoded), 1 if optimize_mode else 0, _ptr(table), n, _stream(self.device),
+            ),
+            "m3d_features",
+        )
+        return table
+
+    def select_hist(self, data, hist, sub=0.0, clip0=False, pred=0, cutoff=0.0, prefix_mask=0,
+                    prefix_value=0, shift=21):
+        _check(
+            self._lib.m3d_select_hist(
+                self._h, _ptr(data), data.numel(), float(sub), 1 if clip0 else 0, int(pred),
+                float(cutoff), int(prefix_mask), int(prefix_value), int(shift), _ptr(hist),
+                _stream(self.device),
+            ),
+            "m3d_select_hist",
+        )
+
+    def replace_above(self, data, threshold: float, value: float):
+        _check(
+            self._lib.m3d_replace_above(self._h, _ptr(data), data.numel(), float(threshold),
+                                        float(value), _stream(self.device)),
+            "m3d_replace_above",
+        )
+
+    # ------------------------------------------------------------------ accounting
+    def launch_count(self) -> int:
+        return int(self._lib.m3d_launch_count(self._h))
+
+    def set_timing(self, enable: bool) -> None:
+        _check(self._lib.m3d_set_timing(self._h, 1 if enable else 0), "m3d_set_timing")
+
+    def reset_counters(self) -> None:
+        _check(self._lib.m3d_reset_counters(self._h), "m3d_reset_counters")
+
+    def kernel_times_ms(self) -> dict:
+        """Accumulated device milliseconds per kernel family (needs ``set_timing(True)``)."""
+        out = {}
+        i = 0
+        while True:
+            name = self._lib.m3d_kernel_name(i)
+            if name is None:
+                break
+            t = float(self._lib.m3d_kernel_time_ms(self._h, i))
+            if t:
+                out[name.decode()] = t
+            i += 1
+        return out
+
+    def launches_by_kernel(self) -> dict:
+        out = {}
+        i = 0
+        while True:
+            name = self._lib.m3d_kernel_name(i)
+            if name is None:
+                break
+            n = int(self._lib.m3d_kernel_launches(self._h, i))
+            if n:
+                out[name.decode()] = n
+            i += 1
+        return out

@@ -72,6 +72,7 @@ extern "C" int m3d_create(int device, int n_bits, int n_codewords, const float* 
     ctx->nb_pad = n_bits <= 16 ? 16 : (n_bits <= 24 ? 24 : 32);
     ctx->K = n_codewords;
     memset(ctx->launches, 0, sizeof(ctx->launches));
+    for (int i = 0; i < KF_COUNT; ++i) ctx->time_ms[i] = 0.0;
     for (int b = 0; b < M3D_MAX_BITS; ++b) {
         ctx->bkg[b] = 0.f;
         ctx->nrm[b] = 1.f;
@@ -141,6 +142,11 @@ extern "C" int m3d_create(int device, int n_bits, int n_codewords, const float* 
 extern "C" int m3d_destroy(m3d_ctx* ctx) {
     if (!ctx) return M3D_OK;
     cudaSetDevice(ctx->device);
+    for (auto& sp : ctx->spans) {
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    ctx->spans.clear();
     cudaFree(ctx->d_codebook);
     cudaFree(ctx->d_onbits);
     cudaFree(ctx->d_cw_a);
@@ -203,6 +209,40 @@ extern "C" int64_t m3d_launch_count(m3d_ctx* ctx) {
 }
 
 extern "C" const char* m3d_kernel_name(int i) { return (i >= 0 && i < KF_COUNT) ? kKernelNames[i] : nullptr; }
+static void resolve_spans(m3d_ctx* ctx) {
+    for (auto& sp : ctx->spans) {
+        cudaEventSynchronize(sp.b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) ctx->time_ms[sp.k] += (double)ms;
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    ctx->spans.clear();
+}
+extern "C" int m3d_set_timing(m3d_ctx* ctx, int enable) {
+    if (!ctx) return m3d_fail(M3D_ERR_ARG, "m3d_set_timing: null ctx");
+    cudaSetDevice(ctx->device);
+    resolve_spans(ctx);
+    ctx->timing = enable ? 1 : 0;
+    return M3D_OK;
+}
+extern "C" int m3d_reset_counters(m3d_ctx* ctx) {
+    if (!ctx) return m3d_fail(M3D_ERR_ARG, "m3d_reset_counters: null ctx");
+    cudaSetDevice(ctx->device);
+    resolve_spans(ctx);
+    memset(ctx->launches, 0, sizeof(ctx->launches));
+    for (int i = 0; i < KF_COUNT; ++i) ctx->time_ms[i] = 0.0;
+    return M3D_OK;
+}
+extern "C" double m3d_kernel_time_ms(m3d_ctx* ctx, int i) {
+    if (!ctx || i < 0 || i >= KF_COUNT) return 0.0;
+    cudaSetDevice(ctx->device);
+    resolve_spans(ctx);
+    return ctx->time_ms[i];
+}
+extern "C" int64_t m3d_kernel_launches(m3d_ctx* ctx, int i) {
+    return (ctx && i >= 0 && i < KF_COUNT) ? ctx->launches[i] : 0;
+}
 
 // ------------------------------------------------------------------ order statistics (PD:1113-1177)
 namespace {
@@ -253,10 +293,10 @@ extern "C" int m3d_select_hist(m3d_ctx* ctx, const float* data_dev, int64_t n, f
     size_t want = ((size_t)n + 255) / 256;
     size_t cap = (size_t)ctx->num_sms * 8;
     int blocks = (int)(want < cap ? want : cap);
-    select_hist_kernel<<<blocks, 256, 0, st>>>(data_dev, (size_t)n, sub, clip0, pred, cutoff, prefix_mask,
-                                                prefix_value, shift, hist_dev);
+    M3D_LAUNCH(ctx, KF_SELECT_HIST, st,
+               select_hist_kernel<<<blocks, 256, 0, st>>>(data_dev, (size_t)n, sub, clip0, pred, cutoff, prefix_mask,
+                                                          prefix_value, shift, hist_dev));
     M3D_CHECK_LAUNCH();
-    count_launch(ctx, KF_SELECT_HIST);
     return M3D_OK;
 }
 
@@ -268,8 +308,8 @@ extern "C" int m3d_replace_above(m3d_ctx* ctx, float* data_dev, int64_t n, float
     size_t want = ((size_t)n + 255) / 256;
     size_t cap = (size_t)ctx->num_sms * 8;
     int blocks = (int)(want < cap ? want : cap);
-    replace_above_kernel<<<blocks, 256, 0, st>>>(data_dev, (size_t)n, threshold, value);
+    M3D_LAUNCH(ctx, KF_REPLACE_ABOVE, st,
+               replace_above_kernel<<<blocks, 256, 0, st>>>(data_dev, (size_t)n, threshold, value));
     M3D_CHECK_LAUNCH();
-    count_launch(ctx, KF_REPLACE_ABOVE);
     return M3D_OK;
 }

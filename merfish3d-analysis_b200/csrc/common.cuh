@@ -139,9 +139,42 @@ struct m3d_ctx {
     int lab_max_px = 0;
     // accounting
     int64_t launches[KF_COUNT];
+    // optional per-kernel-family device timing (m3d_set_timing): event pairs recorded on the
+    // launch stream around every launch, resolved lazily by m3d_kernel_time_ms
+    int timing = 0;
+    struct TimedSpan { int k; cudaEvent_t a, b; };
+    std::vector<TimedSpan> spans;
+    double time_ms[KF_COUNT];
     DecodeParams params() const;
 };
 
-static inline void count_launch(m3d_ctx* ctx, M3dKernel k, int64_t n = 1) { ctx->launches[k] += n; }
+// Scoped launch accounting: construct right before a launch (or a library call that launches),
+// destruct right after.  Counts the launch and, when timing is on, brackets it with events.
+struct KernelScope {
+    m3d_ctx* ctx;
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int k;
+    KernelScope(m3d_ctx* c, M3dKernel kf, cudaStream_t s, int64_t n = 1) : ctx(c), st(s), k((int)kf) {
+        ctx->launches[k] += n;
+        if (ctx->timing) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, st);
+        }
+    }
+    ~KernelScope() {
+        if (a) {
+            cudaEventRecord(b, st);
+            ctx->spans.push_back({k, a, b});
+        }
+    }
+};
+
+#define M3D_LAUNCH(ctx, kf, st, ...)            \
+    do {                                        \
+        KernelScope ks__((ctx), (kf), (st));    \
+        __VA_ARGS__;                            \
+    } while (0)
 
 static inline int ceil_div_i64(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

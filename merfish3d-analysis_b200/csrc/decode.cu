@@ -240,9 +240,9 @@ int launch_decode(m3d_ctx* ctx, const T* stack, size_t n_vox, int16_t* decoded, 
         size_t cap = (size_t)ctx->num_sms * 16;
         int blocks = (int)(want < cap ? want : cap);
         if (blocks < 1) blocks = 1;
-        kern<<<blocks, SEARCH_THREADS, smem, st>>>(stack, n_vox, P, decoded, mag, dist, scaled);
+        M3D_LAUNCH(ctx, KF_DECODE_DENSE, st,
+                   kern<<<blocks, SEARCH_THREADS, smem, st>>>(stack, n_vox, P, decoded, mag, dist, scaled));
         M3D_CHECK_LAUNCH();
-        count_launch(ctx, KF_DECODE_DENSE);
         return M3D_OK;
     }
     // fast path
@@ -256,21 +256,22 @@ int launch_decode(m3d_ctx* ctx, const T* stack, size_t n_vox, int16_t* decoded, 
     if (vec) {
         size_t units = n_vox / 4;
         int blocks = (int)((units + GATE_THREADS - 1) / GATE_THREADS);
-        decode_gate_kernel<T, NB, SAFE><<<blocks, GATE_THREADS, 0, st>>>(stack, n_vox, P, decoded, cand, cand_count);
+        M3D_LAUNCH(ctx, KF_DECODE_GATE, st,
+                   decode_gate_kernel<T, NB, SAFE><<<blocks, GATE_THREADS, 0, st>>>(stack, n_vox, P, decoded, cand, cand_count));
     } else {
         int blocks = (int)((n_vox + GATE_THREADS - 1) / GATE_THREADS);
-        decode_gate_scalar_kernel<T, NB, SAFE><<<blocks, GATE_THREADS, 0, st>>>(stack, n_vox, P, decoded, cand, cand_count);
+        M3D_LAUNCH(ctx, KF_DECODE_GATE, st,
+                   decode_gate_scalar_kernel<T, NB, SAFE><<<blocks, GATE_THREADS, 0, st>>>(stack, n_vox, P, decoded, cand, cand_count));
     }
     M3D_CHECK_LAUNCH();
-    count_launch(ctx, KF_DECODE_GATE);
     {
         size_t smem = search_smem_bytes(NB, SEARCH_THREADS, P.K, P.max_on);
         auto kern = decode_search_kernel<T, NB, SAFE>;
         M3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int blocks = ctx->num_sms * 8;
-        kern<<<blocks, SEARCH_THREADS, smem, st>>>(stack, n_vox, P, decoded, cand, cand_count);
+        M3D_LAUNCH(ctx, KF_DECODE_SEARCH, st,
+                   kern<<<blocks, SEARCH_THREADS, smem, st>>>(stack, n_vox, P, decoded, cand, cand_count));
         M3D_CHECK_LAUNCH();
-        count_launch(ctx, KF_DECODE_SEARCH);
     }
     return M3D_OK;
 }

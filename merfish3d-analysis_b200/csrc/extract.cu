@@ -382,17 +382,17 @@ extern "C" int m3d_label(m3d_ctx* ctx, const int16_t* decoded_dev, const int64_t
         const int vec = ((reinterpret_cast<uintptr_t>(decoded_dev) & 15u) == 0) ? 1 : 0;
         const size_t threads = (n_vox + 7) / 8;
         const int blocks = (int)((threads + 255) / 256);
-        ccl_collect_kernel<<<blocks, 256, 0, st>>>(decoded_dev, n_vox, vec, fg, counters + CNT_FG, parent, aux);
+        M3D_LAUNCH(ctx, KF_CCL_COLLECT, st,
+                   ccl_collect_kernel<<<blocks, 256, 0, st>>>(decoded_dev, n_vox, vec, fg, counters + CNT_FG, parent, aux));
         M3D_CHECK_LAUNCH();
-        count_launch(ctx, KF_CCL_COLLECT);
     }
     const int sparse_blocks = ctx->num_sms * 8;
-    ccl_merge_kernel<<<sparse_blocks, 256, 0, st>>>(decoded_dev, fg, counters + CNT_FG, parent, Z, Y, X, mode2d ? 1 : 0);
+    M3D_LAUNCH(ctx, KF_CCL_MERGE, st,
+               ccl_merge_kernel<<<sparse_blocks, 256, 0, st>>>(decoded_dev, fg, counters + CNT_FG, parent, Z, Y, X, mode2d ? 1 : 0));
     M3D_CHECK_LAUNCH();
-    count_launch(ctx, KF_CCL_MERGE);
-    ccl_compress_kernel<<<sparse_blocks, 256, 0, st>>>(fg, counters + CNT_FG, parent, aux, root_of);
+    M3D_LAUNCH(ctx, KF_CCL_COMPRESS, st,
+               ccl_compress_kernel<<<sparse_blocks, 256, 0, st>>>(fg, counters + CNT_FG, parent, aux, root_of));
     M3D_CHECK_LAUNCH();
-    count_launch(ctx, KF_CCL_COMPRESS);
 
     // PD:2976-2989: drop area > maximum_pixels; drop area <= max(int(minimum_pixels)-1, 0)
     long long max_size = (long long)minimum_pixels - 1;  // int() truncates toward zero like Python for >= 0
@@ -404,10 +404,10 @@ extern "C" int m3d_label(m3d_ctx* ctx, const int16_t* decoded_dev, const int64_t
     uint32_t* roots = reinterpret_cast<uint32_t*>(ctx->s_roots.ptr);
     const size_t roots_cap = ctx->s_roots.cap / (2 * sizeof(uint32_t));
     uint32_t* roots_sorted = roots + roots_cap;
-    ccl_select_kernel<<<sparse_blocks, 256, 0, st>>>(fg, counters + CNT_FG, root_of, aux, min_keep,
-                                                     (uint32_t)maximum_pixels, roots, counters + CNT_ROOTS);
+    M3D_LAUNCH(ctx, KF_CCL_SELECT, st,
+               ccl_select_kernel<<<sparse_blocks, 256, 0, st>>>(fg, counters + CNT_FG, root_of, aux, min_keep,
+                                                                (uint32_t)maximum_pixels, roots, counters + CNT_ROOTS));
     M3D_CHECK_LAUNCH();
-    count_launch(ctx, KF_CCL_SELECT);
 
     unsigned int h_counts[2];
     M3D_CUDA(cudaMemcpyAsync(h_counts, counters + CNT_FG, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
@@ -428,24 +428,28 @@ extern "C" int m3d_label(m3d_ctx* ctx, const int16_t* decoded_dev, const int64_t
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_roots, st);
     if (scan_bytes > tmp_bytes) tmp_bytes = scan_bytes;
     if (ctx->s_sort.ensure(tmp_bytes)) return M3D_ERR_CUDA;
-    M3D_CUDA(cub::DeviceRadixSort::SortKeys(ctx->s_sort.ptr, tmp_bytes, roots, roots_sorted, (int)n_roots, 0, 32, st));
-    count_launch(ctx, KF_CCL_SORT);
+    {
+        KernelScope ks(ctx, KF_CCL_SORT, st);
+        M3D_CUDA(cub::DeviceRadixSort::SortKeys(ctx->s_sort.ptr, tmp_bytes, roots, roots_sorted, (int)n_roots, 0, 32, st));
+    }
     // area_by_id | offs | cursor
     if (ctx->s_area.ensure((size_t)n_roots * 3 * sizeof(uint32_t))) return M3D_ERR_CUDA;
     uint32_t* area_by_id = reinterpret_cast<uint32_t*>(ctx->s_area.ptr);
     uint32_t* offs = area_by_id + n_roots;
     uint32_t* cursor = offs + n_roots;
-    ccl_assign_kernel<<<(n_roots + 255) / 256, 256, 0, st>>>(roots_sorted, n_roots, aux, area_by_id);
+    M3D_LAUNCH(ctx, KF_CCL_ASSIGN, st,
+               ccl_assign_kernel<<<(n_roots + 255) / 256, 256, 0, st>>>(roots_sorted, n_roots, aux, area_by_id));
     M3D_CHECK_LAUNCH();
-    count_launch(ctx, KF_CCL_ASSIGN);
-    M3D_CUDA(cub::DeviceScan::ExclusiveSum(ctx->s_sort.ptr, tmp_bytes, area_by_id, offs, (int)n_roots, st));
-    count_launch(ctx, KF_CCL_SCAN);
+    {
+        KernelScope ks(ctx, KF_CCL_SCAN, st);
+        M3D_CUDA(cub::DeviceScan::ExclusiveSum(ctx->s_sort.ptr, tmp_bytes, area_by_id, offs, (int)n_roots, st));
+    }
     M3D_CUDA(cudaMemsetAsync(cursor, 0, (size_t)n_roots * sizeof(uint32_t), st));
     if (ctx->s_vox.ensure((size_t)n_fg * sizeof(uint32_t))) return M3D_ERR_CUDA;
     uint32_t* vox = reinterpret_cast<uint32_t*>(ctx->s_vox.ptr);
-    ccl_scatter_kernel<<<sparse_blocks, 256, 0, st>>>(fg, counters + CNT_FG, root_of, aux, offs, cursor, vox, labels_dev);
+    M3D_LAUNCH(ctx, KF_CCL_SCATTER, st,
+               ccl_scatter_kernel<<<sparse_blocks, 256, 0, st>>>(fg, counters + CNT_FG, root_of, aux, offs, cursor, vox, labels_dev));
     M3D_CHECK_LAUNCH();
-    count_launch(ctx, KF_CCL_SCATTER);
     ctx->lab_n_features = n_roots;
     *n_features_out = n_roots;
     return M3D_OK;
@@ -463,6 +467,7 @@ extern "C" int m3d_features(m3d_ctx* ctx, const void* stack_dev, int dtype, cons
                         (long long)ctx->lab_n_features);
     if (ctx->lab_n_features == 0) return M3D_OK;
     if (!table_dev) return m3d_fail(M3D_ERR_ARG, "m3d_features: null table");
+    if (dtype != M3D_DTYPE_U16 && dtype != M3D_DTYPE_F32) return m3d_fail(M3D_ERR_ARG, "m3d_features: dtype %d", dtype);
     M3D_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const size_t n_vox = (size_t)dims[0] * dims[1] * dims[2];
@@ -475,17 +480,15 @@ extern "C" int m3d_features(m3d_ctx* ctx, const void* stack_dev, int dtype, cons
     int blocks = (int)((n_feat + FEAT_WARPS - 1) / FEAT_WARPS);
     const int cap = ctx->num_sms * 16;
     if (blocks > cap) blocks = cap;
+    KernelScope ks(ctx, KF_FEATURES, st);
     if (dtype == M3D_DTYPE_U16)
         features_kernel<uint16_t><<<blocks, FEAT_WARPS * 32, 0, st>>>(
             reinterpret_cast<const uint16_t*>(stack_dev), n_vox, (int)dims[1], (int)dims[2], P, decoded_dev, vox, offs,
             area_by_id, n_feat, optimize_mode, table_dev, n_cols);
-    else if (dtype == M3D_DTYPE_F32)
+    else
         features_kernel<float><<<blocks, FEAT_WARPS * 32, 0, st>>>(
             reinterpret_cast<const float*>(stack_dev), n_vox, (int)dims[1], (int)dims[2], P, decoded_dev, vox, offs,
             area_by_id, n_feat, optimize_mode, table_dev, n_cols);
-    else
-        return m3d_fail(M3D_ERR_ARG, "m3d_features: dtype %d", dtype);
     M3D_CHECK_LAUNCH();
-    count_launch(ctx, KF_FEATURES);
     return M3D_OK;
 }

@@ -187,9 +187,9 @@ template <typename T, bool PRED>
 int run_generic_axis(m3d_ctx* ctx, const T* in, const float* pred, float* out, size_t total, int len,
                      size_t stride, const Weights& W, cudaStream_t st) {
     int blocks = (int)((total + 255) / 256);
-    lowpass_axis_generic_kernel<T, PRED><<<blocks, 256, 0, st>>>(in, pred, out, total, len, stride, W);
+    M3D_LAUNCH(ctx, KF_LOWPASS_GENERIC, st,
+               lowpass_axis_generic_kernel<T, PRED><<<blocks, 256, 0, st>>>(in, pred, out, total, len, stride, W));
     M3D_CHECK_LAUNCH();
-    count_launch(ctx, KF_LOWPASS_GENERIC);
     return M3D_OK;
 }
 
@@ -198,17 +198,17 @@ int run_z(m3d_ctx* ctx, const T* in, const float* pred, float* out, int Z, int Y
           cudaStream_t st) {
     const size_t plane = (size_t)Y * X;
     const int blocks = (int)((plane + 127) / 128);
+    if (W.r != 12 && W.r != 8 && W.r != 6 && W.r != 4 && W.r != 2)
+        return run_generic_axis<T, PRED>(ctx, in, pred, out, (size_t)Z * plane, Z, plane, W, st);
+    KernelScope ks(ctx, KF_LOWPASS_Z, st);
     switch (W.r) {
         case 12: lowpass_z_kernel<T, 12, PRED><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W); break;
         case 8: lowpass_z_kernel<T, 8, PRED><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W); break;
         case 6: lowpass_z_kernel<T, 6, PRED><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W); break;
         case 4: lowpass_z_kernel<T, 4, PRED><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W); break;
         case 2: lowpass_z_kernel<T, 2, PRED><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W); break;
-        default:
-            return run_generic_axis<T, PRED>(ctx, in, pred, out, (size_t)Z * plane, Z, plane, W, st);
     }
     M3D_CHECK_LAUNCH();
-    count_launch(ctx, KF_LOWPASS_Z);
     return M3D_OK;
 }
 
@@ -218,16 +218,15 @@ int run_yx_fast(m3d_ctx* ctx, const T* in, const float* pred, float* out, int n_
                 const Weights& WY, const Weights& WX, cudaStream_t st) {
     dim3 grid((X + YX_TX - 1) / YX_TX, (Y + YX_TY - 1) / YX_TY, n_planes);
     if (grid.y > 65535 || grid.z > 65535) return 1;
+    if (!((WY.r == 4 && WX.r == 4) || (WY.r == 2 && WX.r == 2) || (WY.r == 6 && WX.r == 6))) return 1;
+    KernelScope ks(ctx, KF_LOWPASS_YX, st);
     if (WY.r == 4 && WX.r == 4)
         lowpass_yx_kernel<T, 4, 4, PRED><<<grid, YX_THREADS, 0, st>>>(in, pred, out, Y, X, WY, WX);
     else if (WY.r == 2 && WX.r == 2)
         lowpass_yx_kernel<T, 2, 2, PRED><<<grid, YX_THREADS, 0, st>>>(in, pred, out, Y, X, WY, WX);
     else if (WY.r == 6 && WX.r == 6)
         lowpass_yx_kernel<T, 6, 6, PRED><<<grid, YX_THREADS, 0, st>>>(in, pred, out, Y, X, WY, WX);
-    else
-        return 1;
     M3D_CHECK_LAUNCH();
-    count_launch(ctx, KF_LOWPASS_YX);
     return M3D_OK;
 }
 
@@ -315,8 +314,7 @@ extern "C" int m3d_weight(m3d_ctx* ctx, const uint16_t* readout_dev, const float
     M3D_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int blocks = (int)(((size_t)n + 255) / 256);
-    weight_kernel<<<blocks, 256, 0, st>>>(readout_dev, predictor_dev, out_dev, (size_t)n);
+    M3D_LAUNCH(ctx, KF_WEIGHT, st, weight_kernel<<<blocks, 256, 0, st>>>(readout_dev, predictor_dev, out_dev, (size_t)n));
     M3D_CHECK_LAUNCH();
-    count_launch(ctx, KF_WEIGHT);
     return M3D_OK;
 }

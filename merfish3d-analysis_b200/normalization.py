@@ -1,0 +1,178 @@
+"""Order statistics for the normalisation optimiser (PD:981-1199, PD:1250-1421).
+
+``DeviceOrderStats`` answers rank queries over float32 device volumes with a three-pass
+radix select built on ``m3d_select_hist`` (11 + 11 + 10 key bits); the volumes are never
+sorted, copied or brought to the host.  The interpolation / median arithmetic on the two
+or four selected values follows NumPy exactly (``np.percentile`` ``linear`` method,
+``np.median``), which is what the oracle calls.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+PRED_ALL, PRED_LT, PRED_GT = 0, 1, 2
+_SHIFTS = (21, 10, 0)
+_WIDTHS = (11, 11, 10)
+
+
+def _f32_at_or_above(c: float) -> np.float32:
+    """smallest float32 >= c   (so that  v < c  <=>  v < result  for float32 v)."""
+    f = np.float32(c)
+    if float(f) < c:
+        f = np.nextafter(f, np.float32(np.inf))
+    return f
+
+
+def _f32_at_or_below(c: float) -> np.float32:
+    """largest float32 <= c    (so that  v > c  <=>  v > result  for float32 v)."""
+    f = np.float32(c)
+    if float(f) > c:
+        f = np.nextafter(f, np.float32(-np.inf))
+    return f
+
+
+def _key_to_f32(key: int) -> np.float32:
+    u = np.uint32(key)
+    u = (u & np.uint32(0x7FFFFFFF)) if (int(u) & 0x80000000) else ~u
+    return np.array([u], dtype=np.uint32).view(np.float32)[0]
+
+
+class DeviceOrderStats:
+    """Rank selection over ``v = clip0 ? max(x - sub, 0) : x - sub`` of several volumes."""
+
+    def __init__(self, ctx):
+        import torch
+
+        self._ctx = ctx
+        self._torch = torch
+        self._hist = torch.zeros(2048, dtype=torch.int64, device=ctx.device)
+
+    def _pass(self, volumes, sub, clip0, pred, cutoffs, prefix_mask, prefix_value, shift):
+        self._hist.zero_()
+        for vol, cut in zip(volumes, cutoffs):
+            self._ctx.select_hist(
+                vol, self._hist, sub=sub, clip0=clip0, pred=pred, cutoff=cut,
+                prefix_mask=prefix_mask, prefix_value=prefix_value, shift=shift,
+            )
+        return self._hist.cpu().numpy()
+
+    def count(self, volumes, sub=0.0, clip0=False, pred=PRED_ALL, cutoffs=None) -> int:
+        cutoffs = [0.0] * len(volumes) if cutoffs is None else cutoffs
+        return int(self._pass(volumes, sub, clip0, pred, cutoffs, 0, 0, _SHIFTS[0]).sum())
+
+    def select(self, volumes, ranks, sub=0.0, clip0=False, pred=PRED_ALL, cutoffs=None):
+        """Values at the given 0-based ranks of the pooled, predicate-filtered multiset."""
+        cutoffs = [0.0] * len(volumes) if cutoffs is None else cutoffs
+        out = []
+        cache = {}
+        for rank in ranks:
+            rank = int(rank)
+            if rank in cache:
+                out.append(cache[rank])
+                continue
+            prefix_mask = 0
+            prefix_value = 0
+            remaining = rank
+            for shift, width in zip(_SHIFTS, _WIDTHS):
+                h = self._pass(volumes, sub, clip0, pred, cutoffs, prefix_mask, prefix_value, shift)
+                h = h[: 1 << width]
+                cum = np.cumsum(h)
+                b = int(np.searchsorted(cum, remaining, side="right"))
+                if b >= h.size:
+                    raise ValueError("rank beyond the population")
+                remaining -= int(cum[b - 1]) if b > 0 else 0
+                prefix_value |= b << shift
+                prefix_mask |= ((1 << width) - 1) << shift
+            cache[rank] = _key_to_f32(prefix_value)
+            out.append(cache[rank])
+        return out
+
+    # ------------------------------------------------------------------ NumPy-exact wrappers
+    def percentile(self, volume, q: float, sub=0.0, clip0=False):
+        """``np.percentile(v.ravel(), q)`` (method 'linear'): float64 like NumPy returns."""
+        n = volume.numel()
+        if n == 0:
+            return None
+        virtual = (n - 1) * np.true_divide(q, 100.0)
+        prev = int(np.floor(virtual))
+        nxt = min(prev + 1, n - 1)
+        a, b = self.select([volume], [prev, nxt], sub=sub, clip0=clip0)
+        gamma = np.float64(virtual - prev)
+        diff = np.subtract(np.float32(b), np.float32(a))  # float32, like NumPy's _lerp
+        if gamma >= 0.5:
+            return np.float64(np.float32(b)) - np.float64(diff) * (1 - gamma)
+        return np.float64(np.float32(a)) + np.float64(diff) * gamma
+
+    def median(self, volumes, sub=0.0, clip0=False, pred=PRED_ALL, cutoffs=None):
+        """``np.median`` of the pooled selected float32 values; None when empty."""
+        n = self.count(volumes, sub, clip0, pred, cutoffs)
+        if n == 0:
+            return None
+        if n % 2 == 1:
+            (v,) = self.select(volumes, [n // 2], sub, clip0, pred, cutoffs)
+            return np.float32(v)
+        a, b = self.select(volumes, [n // 2 - 1, n // 2], sub, clip0, pred, cutoffs)
+        # np.median -> np.mean of the two middle float32 values (float32 add, then / 2)
+        return np.float32(np.float32(a) + np.float32(b)) / np.float32(2.0)
+
+
+def global_normalization_vectors(ctx, bit_volume_lists, low_percentile_cut=10.0,
+                                 high_percentile_cut=90.0):
+    """PD:1113-1183 -- per bit: bkg = median(pooled pixels < P10_t), nrm = median(pooled
+    clip(img - bkg, 0) > P90_t).  ``bit_volume_lists[b]`` = list of float32 device volumes (one
+    per sampled tile), already hot-pixel-corrected, z-cropped and low-passed."""
+    stats = DeviceOrderStats(ctx)
+    n_bits = len(bit_volume_lists)
+    nrm = np.ones(n_bits, dtype=np.float32)
+    bkg = np.zeros(n_bits, dtype=np.float32)
+    for b, vols in enumerate(bit_volume_lists):
+        vols = [v for v in vols if v.numel() > 0]
+        if not vols:
+            continue
+        cuts = [float(_f32_at_or_above(float(stats.percentile(v, low_percentile_cut)))) for v in vols]
+        m = stats.median(vols, pred=PRED_LT, cutoffs=cuts)
+        bkg[b] = 0 if m is None else m
+        sub = float(bkg[b])
+        cuts = [
+            float(_f32_at_or_below(float(stats.percentile(v, high_percentile_cut, sub=sub, clip0=True))))
+            for v in vols
+        ]
+        m = stats.median(vols, sub=sub, clip0=True, pred=PRED_GT, cutoffs=cuts)
+        nrm[b] = 1 if m is None else m
+    return nrm, bkg
+
+
+def iterative_normalization_vectors(df, n_bits: int):
+    """PD:1263-1368 vectorised: per-bit medians of on-bit / off-bit feature means over
+    non-blank transcripts, cast float32, rounded to 0.1, NaN -> 1/0, 0 -> 1.
+
+    Returns ``(normalization, background)`` or ``None`` when the reference keeps the
+    previous vectors (no non-blank transcripts or no bit columns).
+    """
+    import pandas as pd  # noqa: F401  (df is a DataFrame)
+
+    keep = ~df["gene_id"].astype("string").str.lower().str.startswith("blank", na=False)
+    d = df[keep]
+    bit_cols = [c for c in d.columns if c.startswith("bit") and c.endswith("_mean_intensity")]
+    if d.empty or not bit_cols:
+        return None
+    # the reference sorts the column names (PD:1338-1343) before the median
+    bit_cols = sorted(bit_cols)
+    vals = d[bit_cols].to_numpy(dtype=np.float64)
+    col_bit = np.array([int(c[3:5]) for c in bit_cols])
+    on = d[[f"on_bit_{k}" for k in range(1, 5)]].to_numpy(dtype=np.int64)
+    is_on = (on[:, :, None] == col_bit[None, None, :]).any(axis=1)
+    with np.errstate(all="ignore"):
+        import warnings
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            med_on = np.nanmedian(np.where(is_on, vals, np.nan), axis=0)
+            med_off = np.nanmedian(np.where(is_on, np.nan, vals), axis=0)
+    nv = np.round(med_on.astype(np.float32), 1)
+    bv = np.round(med_off.astype(np.float32), 1)
+    nv = np.nan_to_num(nv, 1.0)
+    nv = np.where(nv == 0.0, 1.0, nv)
+    bv = np.nan_to_num(bv, 0.0)
+    return nv.astype(np.float32), bv.astype(np.float32)

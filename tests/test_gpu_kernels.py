@@ -1,0 +1,325 @@
+"""GPU parity tests: every C-ABI kernel against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): codeword image and canonically relabelled feature ids
+bit-exact; distances / intensities within 1e-5 relative.  Because the kernels reproduce
+the oracle's float32 operation order, most comparisons below are in fact exact.
+"""
+import numpy as np
+import pytest
+from scipy import ndimage as ndi
+
+import cases
+from oracle import decode_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+
+    return torch
+
+
+def _same_f16(a, b, name=""):
+    """bit-identical float16 images (NaN payloads aside: NaN must sit in the same voxels)."""
+    assert a.dtype == np.float16 and b.dtype == np.float16
+    nan_a, nan_b = np.isnan(a), np.isnan(b)
+    np.testing.assert_array_equal(nan_a, nan_b, err_msg=name + " NaN mask")
+    np.testing.assert_array_equal(
+        np.where(nan_a, 0, a.view(np.uint16)), np.where(nan_b, 0, b.view(np.uint16)), err_msg=name
+    )
+
+
+def _ctx(cb, excluded=()):
+    from merfish3d_analysis_b200._capi import DecodeContext
+
+    unit = orc.normalize_codebook(cb["matrix"]).astype(np.float32)
+    return DecodeContext(unit, excluded, device=0), unit
+
+
+def _dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _decode_both(torch, cb, stack, bkg, nrm, mag=(1.5, 10.0), excluded=(), dense=True):
+    ctx, unit = _ctx(cb, excluded)
+    ctx.set_normalization(bkg, nrm)
+    ctx.set_thresholds(cb["pixel_assignment_threshold"], mag[0], mag[1])
+    d_stack = _dev(torch, stack)
+    shape = stack.shape[1:]
+    dec = torch.empty(shape, dtype=torch.int16, device="cuda")
+    imgs = {}
+    if dense:
+        m = torch.empty(shape, dtype=torch.float16, device="cuda")
+        d = torch.empty(shape, dtype=torch.float16, device="cuda")
+        s = torch.empty(stack.shape, dtype=torch.float16, device="cuda")
+        ctx.decode(d_stack, dec, m, d, s)
+        imgs = dict(magnitude=m.cpu().numpy(), distance=d.cpu().numpy(), scaled=s.cpu().numpy())
+    else:
+        ctx.decode(d_stack, dec)
+    torch.cuda.synchronize()
+    imgs["decoded"] = dec.cpu().numpy()
+    ref = orc.decode_pixels(
+        np.asarray(stack, dtype=np.float32), unit, bkg, nrm, cb["pixel_assignment_threshold"], mag, excluded
+    )
+    return ctx, d_stack, dec, imgs, ref
+
+
+@pytest.mark.parametrize("dense", [True, False])
+@pytest.mark.parametrize("use_norm", [True, False])
+def test_decode_u16_bit_exact(torch, dense, use_norm):
+    _df, cb = cases.codebook16()
+    stack = cases.small_stack(cb["matrix"], shape=(10, 40, 64), seed=11)
+    bkg, nrm = cases.simple_vectors(16) if use_norm else (None, None)
+    mag = (1.5, 10.0) if use_norm else (2000.0, 1.0e6)
+    _c, _s, _d, got, ref = _decode_both(torch, cb, stack, bkg, nrm, mag=mag, dense=dense)
+    np.testing.assert_array_equal(got["decoded"], ref["decoded"])
+    assert (ref["decoded"] >= 0).sum() > 100
+    if dense:
+        for k in ("magnitude", "distance", "scaled"):
+            _same_f16(got[k], ref[k], k)
+
+
+def test_decode_f32_input_with_specials(torch):
+    """float32 stack (the low-passed case) including zeros, negatives, NaN and inf voxels."""
+    _df, cb = cases.codebook16()
+    stack = cases.small_stack(cb["matrix"], shape=(6, 32, 48), seed=5).astype(np.float32)
+    rng = np.random.default_rng(3)
+    stack += rng.normal(0, 0.37, stack.shape).astype(np.float32)
+    stack[:, 0, 0, :8] = 0.0
+    stack[3, 1, 1, 1] = np.nan
+    stack[4, 1, 2, 2] = np.inf
+    stack[5, 1, 3, 3] = -np.inf
+    bkg, nrm = cases.simple_vectors(16, seed=2)
+    with np.errstate(all="ignore"):
+        _c, _s, _d, got, ref = _decode_both(torch, cb, stack, bkg, nrm)
+    np.testing.assert_array_equal(got["decoded"], ref["decoded"])
+    for k in ("magnitude", "distance", "scaled"):
+        _same_f16(got[k], ref[k], k)
+
+
+def test_decode_degenerate_vectors_use_safe_division(torch):
+    """normalisation entries of 0 / tiny / huge force the IEEE-division instantiation."""
+    _df, cb = cases.codebook16()
+    stack = cases.small_stack(cb["matrix"], shape=(4, 32, 32), seed=9)
+    bkg, nrm = cases.simple_vectors(16, seed=4)
+    nrm[2] = 0.0
+    nrm[5] = 1e-30
+    bkg[7] = 0.0
+    with np.errstate(all="ignore"):
+        _c, _s, _d, got, ref = _decode_both(torch, cb, stack, bkg, nrm)
+        _c2, _s2, _d2, got2, _ = _decode_both(torch, cb, stack, bkg, nrm, dense=False)
+    np.testing.assert_array_equal(got["decoded"], ref["decoded"])
+    np.testing.assert_array_equal(got2["decoded"], ref["decoded"])
+    for k in ("magnitude", "distance", "scaled"):
+        _same_f16(got[k], ref[k], k)
+
+
+def test_decode_all_foreground_worst_case(torch):
+    """every voxel passes the magnitude gate: the search cannot hide behind sparsity."""
+    _df, cb = cases.codebook16()
+    rng = np.random.default_rng(21)
+    stack = rng.integers(200, 1400, size=(16, 4, 32, 64)).astype(np.uint16)
+    bkg, nrm = cases.simple_vectors(16, seed=6)
+    for dense in (True, False):
+        _c, _s, _d, got, ref = _decode_both(torch, cb, stack, bkg, nrm, mag=(0.5, 10.0), dense=dense)
+        np.testing.assert_array_equal(got["decoded"], ref["decoded"])
+    assert (ref["magnitude"].astype(np.float32) >= 0.5).mean() > 0.99
+
+
+def test_decode_exclusions_do_not_fall_through(torch):
+    _df, cb = cases.codebook16()
+    stack = cases.small_stack(cb["matrix"], shape=(6, 40, 40), seed=13)
+    bkg, nrm = cases.simple_vectors(16)
+    _c, _s, _d, base, _ = _decode_both(torch, cb, stack, bkg, nrm, dense=False)
+    present = np.unique(base["decoded"][base["decoded"] >= 0])
+    excluded = tuple(int(v) for v in present[:3])
+    _c, _s, _d, got, ref = _decode_both(torch, cb, stack, bkg, nrm, excluded=excluded, dense=False)
+    np.testing.assert_array_equal(got["decoded"], ref["decoded"])
+    assert not np.isin(got["decoded"], excluded).any()
+    changed = base["decoded"] != got["decoded"]
+    assert np.all(got["decoded"][changed] == -1) and changed.any()
+
+
+def test_decode_22bit_codebook(torch):
+    _df, cb = cases.codebook22(n_words=300)
+    stack = cases.small_stack(cb["matrix"], shape=(4, 40, 64), seed=17)
+    bkg, nrm = cases.simple_vectors(22, seed=8)
+    for dense in (True, False):
+        _c, _s, _d, got, ref = _decode_both(torch, cb, stack, bkg, nrm, dense=dense)
+        np.testing.assert_array_equal(got["decoded"], ref["decoded"])
+    assert (ref["decoded"] >= 0).sum() > 50
+
+
+def test_decode_non_binary_codebook_generic_path(torch):
+    """mixed on-bit counts (3/4/5) -> rows have different non-zero values -> generic search."""
+    import pandas as pd
+
+    rng = np.random.default_rng(31)
+    rows = []
+    for k in range(40):
+        r = np.zeros(16, dtype=np.int64)
+        r[rng.choice(16, size=int(rng.integers(3, 6)), replace=False)] = 1
+        rows.append(r)
+    m = np.unique(np.stack(rows), axis=0)
+    df = pd.DataFrame(m, columns=[f"bit{i + 1:02d}" for i in range(16)])
+    df.insert(0, "gene_id", [f"g{i}" for i in range(len(m))])
+    cb = orc.load_codebook(df, 16)
+    stack = cases.small_stack(m[(m.sum(1) == 4)], shape=(4, 32, 48), seed=19)
+    bkg, nrm = cases.simple_vectors(16, seed=10)
+    _c, _s, _d, got, ref = _decode_both(torch, cb, stack, bkg, nrm)
+    np.testing.assert_array_equal(got["decoded"], ref["decoded"])
+    _same_f16(got["distance"], ref["distance"], "distance")
+
+
+@pytest.mark.parametrize("shape", [(5, 33, 47), (30, 40, 72), (2, 8, 8)])
+@pytest.mark.parametrize("mode2d", [False, True])
+def test_lowpass_matches_scipy_bit_exact(torch, shape, mode2d):
+    _df, cb = cases.codebook16()
+    ctx, _ = _ctx(cb)
+    rng = np.random.default_rng(41)
+    vols = rng.integers(0, 4000, size=(3, *shape)).astype(np.uint16)
+    got = ctx.lowpass(_dev(torch, vols), (3.0, 1.0, 1.0), mode2d).cpu().numpy()
+    ref = orc.lowpass_stack(vols.astype(np.float32), (3.0, 1.0, 1.0), not mode2d)
+    np.testing.assert_array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_lowpass_f32_with_predictor_and_other_sigmas(torch):
+    _df, cb = cases.codebook16()
+    ctx, _ = _ctx(cb)
+    rng = np.random.default_rng(43)
+    vols = rng.integers(0, 4000, size=(2, 9, 31, 40)).astype(np.uint16)
+    pred = rng.uniform(0, 1, size=vols.shape).astype(np.float32)
+    for sigma in [(3.0, 1.0, 1.0), (2.0, 1.5, 1.5), (1.0, 2.0, 0.7)]:
+        got = ctx.lowpass(_dev(torch, vols), sigma, False, predictor=_dev(torch, pred)).cpu().numpy()
+        w = orc.weight_readout(vols, pred)
+        ref = orc.lowpass_stack(w, sigma, True)
+        np.testing.assert_array_equal(got.view(np.uint32), ref.view(np.uint32), err_msg=str(sigma))
+    f = (vols.astype(np.float32) * pred).astype(np.float32)
+    got = ctx.lowpass(_dev(torch, f), (3.0, 1.0, 1.0), False).cpu().numpy()
+    ref = ndi.gaussian_filter(f[0], (3.0, 1.0, 1.0))
+    np.testing.assert_array_equal(got[0].view(np.uint32), ref.view(np.uint32))
+
+
+def test_weight_kernel(torch):
+    _df, cb = cases.codebook16()
+    ctx, _ = _ctx(cb)
+    rng = np.random.default_rng(47)
+    r = rng.integers(0, 65535, size=(3, 17, 19)).astype(np.uint16)
+    p = rng.uniform(0, 1, size=r.shape).astype(np.float32)
+    got = ctx.weight(_dev(torch, r), _dev(torch, p)).cpu().numpy()
+    np.testing.assert_array_equal(got, orc.weight_readout(r, p))
+
+
+def _random_decoded(rng, shape, n_codes=6, fill=0.3):
+    dec = np.full(shape, -1, dtype=np.int16)
+    m = rng.uniform(size=shape) < fill
+    dec[m] = rng.integers(0, n_codes, size=int(m.sum())).astype(np.int16)
+    return dec
+
+
+@pytest.mark.parametrize("mode2d", [False, True])
+@pytest.mark.parametrize("fill", [0.08, 0.35])
+def test_label_matches_oracle(torch, mode2d, fill):
+    """equal-value CCL + both size filters; canonical ids = raster order of first voxel."""
+    _df, cb = cases.codebook16()
+    ctx, _ = _ctx(cb)
+    rng = np.random.default_rng(53)
+    dec = _random_decoded(rng, (7, 37, 45), fill=fill)
+    # one oversized uniform block (> maximum_pixels) that must be dropped
+    dec[1:5, 2:14, 2:14] = 3
+    labels = torch.zeros(dec.shape, dtype=torch.int32, device="cuda")
+    n = ctx.label(_dev(torch, dec), mode2d, 3.0, 500, labels=labels)
+    ref = orc.filter_label_sizes(orc.label_decoded(dec, not mode2d), 3.0, 500)
+    ref = cases.canonical_labels(ref)
+    np.testing.assert_array_equal(labels.cpu().numpy(), ref)
+    assert n == ref.max() and n > 5
+
+
+def test_label_edge_cases(torch):
+    _df, cb = cases.codebook16()
+    ctx, _ = _ctx(cb)
+    empty = np.full((3, 8, 8), -1, dtype=np.int16)
+    assert ctx.label(_dev(torch, empty), False, 1.0, 500) == 0
+    full = np.zeros((3, 8, 8), dtype=np.int16)  # one 192-voxel component
+    lab = torch.zeros(full.shape, dtype=torch.int32, device="cuda")
+    assert ctx.label(_dev(torch, full), False, 16.0, 500, labels=lab) == 1
+    assert int(lab.min()) == 1 and int(lab.max()) == 1
+    assert ctx.label(_dev(torch, full), False, 16.0, 100) == 0  # larger than maximum_pixels
+    # float minimum_pixels: int() truncation like the reference (16.9 -> keeps area >= 16)
+    dec = np.full((2, 8, 8), -1, dtype=np.int16)
+    dec[0, 0, :8] = 1
+    dec[0, 1, :8] = 1
+    assert ctx.label(_dev(torch, dec), False, 16.9, 500) == 1
+    assert ctx.label(_dev(torch, dec), False, 17.0, 500) == 0
+    # odd, unaligned sizes
+    rng = np.random.default_rng(59)
+    dec = _random_decoded(rng, (3, 5, 7), fill=0.5)
+    lab = torch.zeros(dec.shape, dtype=torch.int32, device="cuda")
+    ctx.label(_dev(torch, dec), False, 1.0, 500, labels=lab)
+    ref = cases.canonical_labels(orc.filter_label_sizes(orc.label_decoded(dec, True), 1.0, 500))
+    np.testing.assert_array_equal(lab.cpu().numpy(), ref)
+
+
+def _check_table(tab, ref_df, n_bits, optimize):
+    assert tab.shape[0] == len(ref_df)
+    np.testing.assert_array_equal(tab[:, 0].astype(np.int64), ref_df["first_voxel"].to_numpy())
+    np.testing.assert_array_equal(tab[:, 1], ref_df["area"].to_numpy())
+    for j, c in enumerate(("z", "y", "x")):
+        np.testing.assert_allclose(tab[:, 3 + j], ref_df[c].to_numpy(dtype=np.float64), rtol=1e-12)
+    np.testing.assert_allclose(tab[:, 12], ref_df["distance_min"].to_numpy(dtype=np.float64), rtol=REL)
+    np.testing.assert_allclose(tab[:, 13], ref_df["magnitude_mean"].to_numpy(dtype=np.float64), rtol=REL)
+    ref_bits = np.stack([ref_df[f"intensity_mean-{b}"].to_numpy(dtype=np.float64) for b in range(n_bits)], axis=1)
+    np.testing.assert_allclose(tab[:, 14 : 14 + n_bits], ref_bits, rtol=REL, atol=1e-7)
+
+
+@pytest.mark.parametrize("optimize", [False, True])
+@pytest.mark.parametrize("in_dtype", ["u16", "f32"])
+def test_features_match_oracle(torch, optimize, in_dtype):
+    _df, cb = cases.codebook16()
+    stack = cases.small_stack(cb["matrix"], shape=(10, 40, 64), seed=23)
+    if in_dtype == "f32":
+        stack = orc.lowpass_stack(stack.astype(np.float32), (1.0, 0.6, 0.6), True)
+    bkg, nrm = cases.simple_vectors(16, nrm=600.0 if in_dtype == "f32" else 900.0)
+    ctx, d_stack, dec, _got, ref = _decode_both(torch, cb, stack, bkg, nrm, dense=False)
+    n = ctx.label(dec, False, 3.0, 500)
+    tab = ctx.features(d_stack, dec, optimize).cpu().numpy()
+    labels = orc.filter_label_sizes(orc.label_decoded(ref["decoded"], True), 3.0, 500)
+    intensity = np.asarray(stack, dtype=np.float32) if optimize else ref["scaled"]
+    ref_df = orc.region_table(labels, ref["distance"], ref["magnitude"], intensity)
+    assert n == len(ref_df) and n > 20
+    _check_table(tab, ref_df, 16, optimize)
+    # decoded id of every row = value at its first voxel
+    np.testing.assert_array_equal(
+        tab[:, 2].astype(np.int64), ref["decoded"].ravel()[ref_df["first_voxel"].to_numpy()].astype(np.int64)
+    )
+    # second central moments -> inertia eigenvalues (scikit-image semantics)
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    ev = PixelDecoder._inertia_eigvals(tab)
+    ref_ev = np.stack([ref_df[f"inertia_tensor_eigvals-{k}"].to_numpy(dtype=np.float64) for k in range(3)], axis=1)
+    np.testing.assert_allclose(ev, ref_ev, rtol=1e-9, atol=1e-9)
+
+
+def test_select_hist_order_statistics(torch):
+    from merfish3d_analysis_b200 import normalization as nz
+
+    _df, cb = cases.codebook16()
+    ctx, _ = _ctx(cb)
+    rng = np.random.default_rng(61)
+    a = rng.gamma(2.0, 150.0, size=(9, 33, 41)).astype(np.float32)
+    a[0, 0, :5] = 0.0
+    b = rng.gamma(2.0, 170.0, size=(5, 20, 31)).astype(np.float32)
+    da, db = _dev(torch, a), _dev(torch, b)
+    stats = nz.DeviceOrderStats(ctx)
+    for q in (10.0, 50.0, 90.0, 99.9):
+        assert float(stats.percentile(da, q)) == float(np.percentile(a.ravel(), q))
+    assert float(stats.median([da, db])) == float(np.median(np.concatenate([a.ravel(), b.ravel()])))
+    got = nz.global_normalization_vectors(ctx, [[da, db]])
+    nrm, bkg = orc.global_normalization_vectors(
+        [a[None], b[None]], 1, True, lowpass_sigma=None, hot_pixel_threshold=1e30
+    )
+    assert got[0][0] == nrm[0] and got[1][0] == bkg[0]

@@ -1,0 +1,169 @@
+"""GPU parity tests through the reference-facing API: ``PixelDecoder`` (C ABI underneath)
+against the oracle's ``decode_tile`` / ``optimize_normalization`` on the same inputs."""
+import numpy as np
+import pandas as pd
+import pytest
+
+import cases
+from oracle import decode_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+
+
+def _store(tmp_path, df_cb, stacks, predictors=None, microscope_type="3D", **tile_kw):
+    from merfish3d_analysis_b200.datastore import ArrayDataStore
+
+    ds = ArrayDataStore(tmp_path / "qi2labdatastore", codebook=df_cb, voxel_size_zyx_um=(0.315, 0.098, 0.098),
+                        microscope_type=microscope_type)
+    for i, st in enumerate(stacks):
+        ds.add_tile(st, None if predictors is None else predictors[i], **tile_kw)
+    return ds
+
+
+def _compare_tables(got: pd.DataFrame, ref: pd.DataFrame, n_bits=16):
+    assert list(got.columns) == list(ref.columns)
+    assert len(got) == len(ref)
+    exact = ["area", "barcode_id", "gene_id", "tile_idx", "on_bit_1", "on_bit_2", "on_bit_3", "on_bit_4",
+             "tile_z", "tile_y", "tile_x"]
+    for c in exact:
+        assert got[c].tolist() == ref[c].tolist(), c
+    close = ["z", "y", "x", "distance_min", "magnitude_mean", "global_z", "global_y", "global_x",
+             "signal_mean", "bkd_mean", "s-b_mean"] + [f"bit{i:02d}_mean_intensity" for i in range(1, n_bits + 1)]
+    for c in close:
+        np.testing.assert_allclose(
+            got[c].to_numpy(dtype=np.float64), ref[c].to_numpy(dtype=np.float64), rtol=REL, atol=1e-7, err_msg=c
+        )
+    for k in range(3):
+        c = f"inertia_tensor_eigvals-{k}"
+        np.testing.assert_allclose(got[c].to_numpy(dtype=np.float64), ref[c].to_numpy(dtype=np.float64),
+                                   rtol=1e-7, atol=1e-9, err_msg=c)
+
+
+@pytest.mark.parametrize("lowpass", [None, (3.0, 1.0, 1.0)])
+@pytest.mark.parametrize("mode", ["3d", "2d"])
+def test_decode_one_tile_matches_oracle(tmp_path, lowpass, mode):
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    df_cb, cb = cases.codebook16()
+    stack = cases.small_stack(cb["matrix"], shape=(14, 48, 64), seed=29, density=3e-3)
+    bkg, nrm = cases.simple_vectors(16, nrm=300.0 if lowpass else 900.0)
+    origin = np.array([100.0, 20.0, -3.0], dtype=np.float32)
+    cam = np.array([[1, 0, 0, 0], [0, -0.07, -1, 0], [0, -1, 0.07, 0], [0, 0, 0, 1]], dtype=np.float32)
+    ds = _store(tmp_path, df_cb, [stack], stage_origin_zyx_um=origin, camera_to_stage_affine=cam)
+    ds.save_decode_normalization_vectors(None, "global", nrm, bkg)
+    dec = PixelDecoder(ds, merfish_bits=16, verbose=0, decode_mode=mode)
+    out = dec.decode_one_tile(0, lowpass_sigma=lowpass, minimum_pixels=4, normalization_method="global",
+                              return_results=True)
+    got = dec.decoded_barcodes
+    ref, imgs = orc.decode_tile(
+        stack, None, cb, bkg, nrm, is_3d=(mode == "3d"), lowpass_sigma=lowpass, minimum_pixels=4,
+        spacing=ds.voxel_size_zyx_um, origin=origin, camera_to_stage=cam,
+    )
+    assert len(ref) > 10
+    image, scaled, magnitude, distance, decoded = out
+    np.testing.assert_array_equal(decoded, imgs["decoded"])
+    np.testing.assert_array_equal(image, imgs["image"].astype(np.float32))
+    np.testing.assert_array_equal(scaled, imgs["scaled"])
+    np.testing.assert_array_equal(magnitude, imgs["magnitude"])
+    np.testing.assert_array_equal(distance, imgs["distance"])
+    _compare_tables(got, ref)
+    # production path (no result images) must give the same table
+    dec2 = PixelDecoder(ds, merfish_bits=16, verbose=0, decode_mode=mode)
+    assert dec2.decode_one_tile(0, lowpass_sigma=lowpass, minimum_pixels=4, normalization_method="global") is None
+    pd.testing.assert_frame_equal(dec2.decoded_barcodes, got)
+    np.testing.assert_array_equal(dec2.decoded_image, decoded)
+
+
+def test_decode_with_predictor_zcrop_and_exclusions(tmp_path):
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    df_cb, cb = cases.codebook16()
+    stack = cases.small_stack(cb["matrix"], shape=(16, 40, 56), seed=31, density=3e-3)
+    rng = np.random.default_rng(5)
+    pred = (rng.uniform(size=stack.shape) > 0.05).astype(np.float32) * rng.uniform(0.9, 1.0, size=stack.shape).astype(np.float32)
+    bkg, nrm = cases.simple_vectors(16)
+    ds = _store(tmp_path, df_cb, [stack], [pred])
+    ds.save_decode_normalization_vectors(None, "iterative", nrm, bkg)
+    excluded_gene = "gene0003"
+    dec = PixelDecoder(ds, merfish_bits=16, verbose=0, z_range=(2, 14), excluded_gene_ids=[excluded_gene])
+    dec.decode_one_tile(0, lowpass_sigma=None, minimum_pixels=4)
+    got = dec.decoded_barcodes
+    ref, _ = orc.decode_tile(
+        stack[:, 2:14], pred[:, 2:14], cb, bkg, nrm, lowpass_sigma=None, minimum_pixels=4,
+        excluded=(cb["gene_ids"].index(excluded_gene),), spacing=ds.voxel_size_zyx_um, z_offset=2.0,
+    )
+    assert len(ref) > 5 and excluded_gene not in set(ref["gene_id"])
+    _compare_tables(got, ref)
+
+
+def test_decode_api_errors(tmp_path):
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    df_cb, cb = cases.codebook16()
+    stack = cases.small_stack(cb["matrix"], shape=(1, 16, 16), seed=1)
+    ds = _store(tmp_path, df_cb, [stack])
+    with pytest.raises(ValueError, match="decode_mode"):
+        PixelDecoder(ds, decode_mode="4d")
+    dec = PixelDecoder(ds, verbose=0, decode_mode="3d")
+    with pytest.raises(ValueError, match="two z planes"):
+        dec.decode_one_tile(0, normalization_method="none")
+    with pytest.raises(ValueError, match="three values"):
+        dec.decode_one_tile(0, normalization_method="none", lowpass_sigma=(1, 1))
+    with pytest.raises(ValueError, match="normalization_method"):
+        dec.decode_one_tile(0, normalization_method="bogus")
+
+
+def test_optimize_normalization_matches_oracle(tmp_path):
+    """global percentile seed + 3 iterations of decode -> per-bit medians (sim-like config)."""
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    df_cb, cb = cases.codebook16()
+    stacks = [cases.small_stack(cb["matrix"], shape=(12, 48, 64), seed=37 + i, density=4e-3) for i in range(2)]
+    ds = _store(tmp_path, df_cb, stacks)
+    dec = PixelDecoder(ds, merfish_bits=16, verbose=0)
+    sigma = (1.0, 0.5, 0.5)
+    dec.optimize_normalization_by_decoding(n_iterations=3, minimum_pixels=4, lowpass_sigma=sigma,
+                                           magnitude_threshold=(0.9, 10.0), tile_indices=[0, 1])
+    ref = orc.optimize_normalization([(s, None) for s in stacks], cb, 3, True, sigma, (0.9, 10.0), 4)
+    g_n, g_b = ds.load_decode_normalization_vectors(None, "global")
+    np.testing.assert_array_equal(g_n, ref["global_"][0])
+    np.testing.assert_array_equal(g_b, ref["global_"][1])
+    i_n, i_b = ds.load_decode_normalization_vectors(None, "iterative")
+    assert ref["history"][-1][2] > 20
+    np.testing.assert_array_equal(i_n, ref["iterative"][0])
+    np.testing.assert_array_equal(i_b, ref["iterative"][1])
+    md = ds.load_decode_normalization_metadata(None, "iterative")
+    assert md["codebook_sha256"] == orc.codebook_fingerprint(cb["matrix"], cb["gene_ids"])
+    # a decoder with a different codebook must refuse the cached vectors (PD:1220-1230)
+    df2 = df_cb.iloc[:-1].reset_index(drop=True)
+    from merfish3d_analysis_b200.datastore import ArrayDataStore
+
+    ds2 = ArrayDataStore(tmp_path / "qi2labdatastore")
+    ds2._codebook = df2
+    dec2 = PixelDecoder(ds2, merfish_bits=16, verbose=0)
+    ds2.add_tile(stacks[0])
+    with pytest.raises(ValueError, match="different active codebook"):
+        dec2.decode_one_tile(0, normalization_method="iterative")
+
+
+def test_decode_all_tiles_writes_reference_layout(tmp_path):
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    df_cb, cb = cases.codebook16()
+    stacks = [cases.small_stack(cb["matrix"], shape=(8, 32, 48), seed=51 + i, density=4e-3) for i in range(3)]
+    ds = _store(tmp_path, df_cb, stacks)
+    bkg, nrm = cases.simple_vectors(16)
+    ds.save_decode_normalization_vectors(None, "global", nrm, bkg)
+    ds.save_decode_normalization_vectors(None, "iterative", nrm, bkg)
+    dec = PixelDecoder(ds, merfish_bits=16, verbose=0)
+    dec.decode_all_tiles(lowpass_sigma=None, minimum_pixels=4)
+    for i, tile_id in enumerate(ds.tile_ids):
+        p = tmp_path / "qi2labdatastore" / "decoded" / f"{tile_id}_decoded_features.parquet"
+        assert p.exists()
+        got = pd.read_parquet(p)
+        ref, _ = orc.decode_tile(stacks[i], None, cb, bkg, nrm, lowpass_sigma=None, minimum_pixels=4,
+                                 tile_idx=i, spacing=ds.voxel_size_zyx_um)
+        _compare_tables(got, ref)
+    assert len(dec._df_barcodes_loaded) == sum(len(pd.read_parquet(p)) for p in (tmp_path / "qi2labdatastore" / "decoded").glob("*.parquet"))
