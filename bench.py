@@ -224,8 +224,7 @@ def run_b200(args):
     decoded = torch.empty(shape, dtype=torch.int16, device=dev)
 
     def step_resident():
-        ctx.decode(stack, decoded)
-        n = ctx.label(decoded, False, MIN_PX, 500)
+        n = ctx.decode_label(stack, decoded, False, MIN_PX, 500)
         table = ctx.features(stack, decoded, False, n)
         return n, table
 
@@ -326,7 +325,7 @@ def run_b200(args):
             "data": "synthetic",
             "config": {
                 "workload": WORKLOAD if shape == SHAPE else f"reduced tile 16x{shape[0]}x{shape[1]}x{shape[2]} uint16",
-                "step": "m3d_decode (fast path) + m3d_label + m3d_features on the HBM-resident stack",
+                "step": "m3d_decode_label (gate + search + CCL) + m3d_features on the HBM-resident stack",
                 "lowpass": "off (north_star kernel sequence)", "parallelism": f"tile-sharded x{world}",
                 "l2": f"input {stack_bytes(shape) / 1e9:.1f} GB per step >> 126 MB L2",
                 "foreground_voxels": n_fg, "features": int(n_feat),

@@ -96,8 +96,15 @@ int m3d_label(m3d_ctx* ctx, const int16_t* decoded_dev, const int64_t dims[3], i
               double minimum_pixels, int maximum_pixels, int32_t* labels_dev,
               int64_t* n_features_out, void* stream);
 
-/* _extract_barcodes regionprops (PD:2991-3062) for the components of the last m3d_label
- * call, one row per component in canonical order.  table_dev = (n_rows, 14 + n_bits)
+/* Fused production path: m3d_decode (no result images) + m3d_label in one call.  The candidate
+ * search kernel hands the decoded foreground voxels straight to the labelling stage, so the
+ * decoded image is never re-read.  Same results as the two separate calls. */
+int m3d_decode_label(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t dims[3],
+                     int16_t* decoded_dev, int mode2d, double minimum_pixels, int maximum_pixels,
+                     int32_t* labels_dev, int64_t* n_features_out, void* stream);
+
+/* _extract_barcodes regionprops (PD:2991-3062) for the components of the last m3d_label /
+ * m3d_decode_label call, one row per component in canonical order.  table_dev = (n_rows, 14 + n_bits)
  * float64, columns:
  *   0 first_voxel (linear index)  1 area  2 decoded_id
  *   3..5 centroid z,y,x           6..11 central 2nd moments zz,yy,xx,zy,zx,yx (sums)

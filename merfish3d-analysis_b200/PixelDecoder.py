@@ -121,6 +121,7 @@ class PixelDecoder:
         self._iterative_normalization_vector = None
         self._iterative_background_vector = None
         self._load_tile_decoding = False
+        self._fuse_label_args = None
         self._contexts: dict[int, DecodeContext] = {}
         self._context_excluded: dict[int, tuple] = {}
         self._device_state: dict[int, dict] = {}
@@ -559,8 +560,14 @@ class PixelDecoder:
             mag = torch.empty(shape, dtype=torch.float16, device=ctx.device)
             dist = torch.empty(shape, dtype=torch.float16, device=ctx.device)
             scaled = torch.empty(tuple(stack.shape), dtype=torch.float16, device=ctx.device)
-        ctx.decode(stack, st["decoded"], mag, dist, scaled)
         st["magnitude"], st["distance"], st["scaled"] = mag, dist, scaled
+        st["n_features"] = None
+        if materialize_images or self._fuse_label_args is None:
+            ctx.decode(stack, st["decoded"], mag, dist, scaled)
+        else:
+            # production path: the search kernel hands its foreground list to the labelling stage
+            min_px, max_px = self._fuse_label_args
+            st["n_features"] = ctx.decode_label(stack, st["decoded"], not self._is_3D, float(min_px), int(max_px))
 
     @staticmethod
     def _warp_pixel(pixel_space_point, spacing, origin, affine, camera_to_stage_affine=None):
@@ -581,7 +588,9 @@ class PixelDecoder:
         the host over the (small) feature table."""
         st = self._device_state[gpu_id]
         ctx = self._ctx(gpu_id)
-        n = ctx.label(st["decoded"], not self._is_3D, float(minimum_pixels), int(maximum_pixels))
+        n = st.get("n_features")
+        if n is None:
+            n = ctx.label(st["decoded"], not self._is_3D, float(minimum_pixels), int(maximum_pixels))
         table = ctx.features(st["stack"], st["decoded"], self._optimize_normalization_weights, n)
         tab = table.cpu().numpy()
         self._df_barcodes = self._annotate_table(tab)
@@ -771,8 +780,12 @@ class PixelDecoder:
         sigma = self._effective_lowpass_sigma(lowpass_sigma)
         if self._lowpass_active(sigma):
             self._lp_filter(sigma=sigma, gpu_id=gpu_id)
-        self._decode_pixels(magnitude_threshold=magnitude_threshold, gpu_id=gpu_id,
-                            materialize_images=return_results)
+        self._fuse_label_args = (minimum_pixels, MAXIMUM_PIXELS)
+        try:
+            self._decode_pixels(magnitude_threshold=magnitude_threshold, gpu_id=gpu_id,
+                                materialize_images=return_results)
+        finally:
+            self._fuse_label_args = None
         self._extract_barcodes(minimum_pixels=minimum_pixels, gpu_id=gpu_id)
         if return_results:
             import torch

@@ -50,6 +50,11 @@ SIGNATURES = {
         [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_double, C.c_int,
          C.c_void_p, C.POINTER(C.c_int64), C.c_void_p],
     ),
+    "m3d_decode_label": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_int, C.c_double,
+         C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p],
+    ),
     "m3d_features": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_int,
@@ -259,6 +264,23 @@ class DecodeContext:
                 _stream(self.device),
             ),
             "m3d_label",
+        )
+        self._n_features = int(n.value)
+        return self._n_features
+
+    def decode_label(self, stack, decoded, mode2d: bool, minimum_pixels: float,
+                     maximum_pixels: int = 500, labels=None) -> int:
+        """Fused production path: decode (no result images) + connected components."""
+        if stack.dim() != 4 or stack.shape[0] != self.n_bits:
+            raise ValueError(f"stack must be ({self.n_bits}, z, y, x)")
+        n = C.c_int64(-1)
+        _check(
+            self._lib.m3d_decode_label(
+                self._h, _ptr(stack), _dtype_code(stack), self._dims(stack.shape[1:]), _ptr(decoded),
+                1 if mode2d else 0, float(minimum_pixels), int(maximum_pixels), _ptr(labels),
+                C.byref(n), _stream(self.device),
+            ),
+            "m3d_decode_label",
         )
         self._n_features = int(n.value)
         return self._n_features

@@ -27,18 +27,19 @@ DecodeParams m3d_ctx::params() const {
     DecodeParams P;
     memset(&P, 0, sizeof(P));
     for (int b = 0; b < M3D_MAX_BITS; ++b) {
-        P.bkg[b] = bkg[b];
-        P.nrm[b] = nrm[b];
-        P.rcp[b] = rcp[b];
+        const bool live = use_norm && b < n_bits;
+        P.bkg[b] = live ? bkg[b] : 0.f;
+        P.nrm[b] = live ? nrm[b] : 1.f;
     }
     P.pix_thr = pix_thr;
     P.mag_lo = mag_lo;
     P.mag_hi = mag_hi;
-    P.use_norm = use_norm;
     P.n_bits = n_bits;
     P.K = K;
+    P.mode = mode;
     P.max_on = max_on;
-    P.binary = binary;
+    P.cval = cval;
+    P.hash_bits = hash_bits;
     P.codebook = d_codebook;
     P.onbits = d_onbits;
     P.cw_a = d_cw_a;
@@ -46,7 +47,38 @@ DecodeParams m3d_ctx::params() const {
     P.cw_c = d_cw_c;
     P.cw_mask = d_cw_mask;
     P.excluded = d_excluded;
+    P.hash_keys = d_hash_keys;
+    P.hash_vals = d_hash_vals;
     return P;
+}
+
+// Conservative gate window.  The streaming kernel evaluates q = clamp((s - bkg) * rcp, 0, 1)
+// and acc = sum fma(q, q, acc): (s - bkg) is the reference's own first rounding, the
+// reciprocal multiply is within 1.5 ulp of the IEEE quotient, so acc is within ~3e-6
+// (relative) of the reference's squared norm; the exact kernel compares sqrt(acc_exact)
+// against the thresholds, one more half-ulp.  A 1e-5 relative widening is >3x that bound.
+// Outside the proof's preconditions (tiny/huge/non-finite vectors, tiny thresholds) every
+// voxel is sent to the exact kernel instead.
+GateParams m3d_ctx::gate_params() const {
+    GateParams G;
+    memset(&G, 0, sizeof(G));
+    G.n_bits = n_bits;
+    int all = 0;
+    for (int b = 0; b < n_bits; ++b) {
+        const float bg = use_norm ? bkg[b] : 0.f;
+        const float nm = use_norm ? nrm[b] : 1.f;
+        const float an = fabsf(nm);
+        if (!(an >= 1.0e-30f && an <= 1.0e30f) || !(fabsf(bg) <= 3.0e38f)) all = 1;
+        G.bkg[b] = bg;
+        G.rcp[b] = (float)(1.0 / (double)nm);
+    }
+    const double lo = (double)mag_lo, hi = (double)mag_hi;
+    if (!(lo >= 1.0e-3) || !(hi >= lo) || !(lo <= 1.0e15)) all = 1;  // also catches NaN thresholds
+    G.lo2 = (float)(lo * lo * (1.0 - 1.0e-5));
+    const double h2 = hi * hi * (1.0 + 1.0e-5);
+    G.hi2 = h2 > 3.0e38 ? __builtin_inff() : (float)h2;
+    G.all_candidates = all;
+    return G;
 }
 
 extern "C" int m3d_abi_version(void) { return M3D_ABI_VERSION; }
@@ -69,21 +101,21 @@ extern "C" int m3d_create(int device, int n_bits, int n_codewords, const float* 
     M3D_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->num_sms = prop.multiProcessorCount;
     ctx->n_bits = n_bits;
-    ctx->nb_pad = n_bits <= 16 ? 16 : (n_bits <= 24 ? 24 : 32);
+    ctx->nb_pad = n_bits <= 8 ? 8 : (n_bits <= 16 ? 16 : (n_bits <= 24 ? 24 : 32));
     ctx->K = n_codewords;
     memset(ctx->launches, 0, sizeof(ctx->launches));
     for (int i = 0; i < KF_COUNT; ++i) ctx->time_ms[i] = 0.0;
     for (int b = 0; b < M3D_MAX_BITS; ++b) {
         ctx->bkg[b] = 0.f;
         ctx->nrm[b] = 1.f;
-        ctx->rcp[b] = 1.f;
     }
     const int K = n_codewords;
     // padded codebook + structure analysis
     std::vector<float> cb((size_t)K * M3D_MAX_BITS, 0.f);
     std::vector<float> cw_a(K), cw_g(K), cw_c(K);
     std::vector<uint32_t> mask(K, 0u);
-    int binary = 1, max_on = 1;
+    int binary = 1, uniform = 1, max_on = 1, first_on = -1;
+    float first_c = 0.f;
     for (int k = 0; k < K; ++k) {
         float cval = 0.f;
         int n_on = 0;
@@ -101,18 +133,44 @@ extern "C" int m3d_create(int device, int n_bits, int n_codewords, const float* 
             if (!(v == v)) binary = 0;
         }
         if (n_on > max_on) max_on = n_on;
+        if (k == 0) {
+            first_on = n_on;
+            first_c = cval;
+        } else if (n_on != first_on || cval != first_c) {
+            uniform = 0;
+        }
         cw_a[k] = (float)nn;
         cw_g[k] = 2.f * cval;
         cw_c[k] = cval;
     }
     if (max_on > 16) binary = 0;  // proxy path keeps short on-bit lists only
-    ctx->binary = binary;
+    // mode 2 needs positive entries (S ordering) and at least one off bit per row
+    if (!binary || first_on < 1 || first_on >= n_bits || !(first_c > 0.f)) uniform = 0;
+    ctx->mode = binary ? (uniform ? 2 : 1) : 0;
     ctx->max_on = max_on;
+    ctx->cval = first_c;
     std::vector<uint8_t> on((size_t)K * max_on, (uint8_t)ctx->nb_pad);  // pad -> zero slot
     for (int k = 0; k < K; ++k) {
         int j = 0;
         for (int b = 0; b < n_bits && j < max_on; ++b)
             if (mask[k] & (1u << b)) on[(size_t)k * max_on + j++] = (uint8_t)b;
+    }
+    // mask -> first codeword index, open addressing (mode 2)
+    int hash_bits = 4;
+    while ((1 << hash_bits) < 4 * K) ++hash_bits;
+    ctx->hash_bits = hash_bits;
+    std::vector<uint32_t> hkeys((size_t)1 << hash_bits, 0u);
+    std::vector<int16_t> hvals((size_t)1 << hash_bits, (int16_t)-1);
+    if (ctx->mode == 2) {
+        const uint32_t hm = (1u << hash_bits) - 1u;
+        for (int k = 0; k < K; ++k) {
+            uint32_t h = (mask[k] * 2654435761u) >> (32 - hash_bits);
+            while (hkeys[h] != 0u && hkeys[h] != mask[k]) h = (h + 1u) & hm;
+            if (hkeys[h] == 0u) {
+                hkeys[h] = mask[k];
+                hvals[h] = (int16_t)k;  // duplicates keep the first (lowest) index, like argmin
+            }
+        }
     }
     std::vector<uint8_t> excl(K, 0);
     for (int i = 0; i < n_excluded; ++i) {
@@ -134,7 +192,10 @@ extern "C" int m3d_create(int device, int n_bits, int n_codewords, const float* 
     UP(d_cw_c, cw_c, float)
     UP(d_cw_mask, mask, uint32_t)
     UP(d_excluded, excl, uint8_t)
+    UP(d_hash_keys, hkeys, uint32_t)
+    UP(d_hash_vals, hvals, int16_t)
 #undef UP
+    M3D_CUDA(cudaMallocHost((void**)&ctx->h_pinned, 64));
     *out = ctx;
     return M3D_OK;
 }
@@ -154,6 +215,9 @@ extern "C" int m3d_destroy(m3d_ctx* ctx) {
     cudaFree(ctx->d_cw_c);
     cudaFree(ctx->d_cw_mask);
     cudaFree(ctx->d_excluded);
+    cudaFree(ctx->d_hash_keys);
+    cudaFree(ctx->d_hash_vals);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     ctx->s_cand.release();
     ctx->s_counters.release();
     ctx->s_lp_tmp.release();
@@ -172,24 +236,13 @@ extern "C" int m3d_set_normalization(m3d_ctx* ctx, const float* background_host,
     if (!ctx) return m3d_fail(M3D_ERR_ARG, "m3d_set_normalization: null ctx");
     if (!background_host || !normalization_host) {
         ctx->use_norm = 0;
-        ctx->safe_div = 0;
         return M3D_OK;
     }
     ctx->use_norm = 1;
-    int safe = 0;
     for (int b = 0; b < ctx->n_bits; ++b) {
-        const float bg = background_host[b], nm = normalization_host[b];
-        ctx->bkg[b] = bg;
-        ctx->nrm[b] = nm;
-        // correctly rounded reciprocal: double division rounded once more is innocuous for p=24
-        ctx->rcp[b] = (float)(1.0 / (double)nm);
-        const float an = fabsf(nm), ab = fabsf(bg);
-        // reciprocal-division preconditions (voxel_math.cuh): finite, mid-range divisor and a
-        // background large enough that (s - bkg) is either 0 or far from the subnormal range
-        if (!(an >= 9.3132257e-10f && an <= 1.0737418e9f)) safe = 1;
-        if (!(ab >= 9.5367432e-7f && ab <= 1.0e30f)) safe = 1;
+        ctx->bkg[b] = background_host[b];
+        ctx->nrm[b] = normalization_host[b];
     }
-    ctx->safe_div = safe;
     return M3D_OK;
 }
 

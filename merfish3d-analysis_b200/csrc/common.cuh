@@ -78,23 +78,37 @@ struct Scratch {
 };
 
 // ---------------------------------------------------------------- per-call decode parameters (by value)
+// Exact-arithmetic parameters.  Without normalisation vectors bkg = 0 and nrm = 1 (identity).
 struct DecodeParams {
     float bkg[M3D_MAX_BITS];
     float nrm[M3D_MAX_BITS];
-    float rcp[M3D_MAX_BITS];  // correctly rounded 1/nrm (fast exact division)
     float pix_thr, mag_lo, mag_hi;
-    int use_norm;
     int n_bits;
     int K;
-    int max_on;        // padded on-bit list length (binary codebooks)
-    int binary;        // 1: every row's non-zeros share one value
-    const float* codebook;       // K x NBPAD fp32 (zero padded)
-    const uint8_t* onbits;       // K x max_on bit indices (pad = NBPAD -> zero slot)
+    int mode;          // 0: generic rows (direct scan); 1: every row's non-zeros share one value
+                       // (proxy scan); 2: mode 1 + one on-bit count and value for all rows
+                       // (top-w selection + hash lookup, warp-cooperative fallback)
+    int max_on;        // padded on-bit list length (modes 1, 2); the on-bit count w in mode 2
+    float cval;        // mode 2: the common non-zero entry (1/sqrt(w))
+    int hash_bits;     // mode 2: log2 of the mask -> codeword hash table size
+    const float* codebook;       // K x M3D_MAX_BITS fp32 (zero padded)
+    const uint8_t* onbits;       // K x max_on bit indices (pad = zero slot)
     const float* cw_a;           // K: ||c_k||^2
     const float* cw_g;           // K: 2*c_k
     const float* cw_c;           // K: c_k (value of the non-zero entries)
     const uint32_t* cw_mask;     // K: on-bit mask
     const uint8_t* excluded;     // K flags
+    const uint32_t* hash_keys;   // 2^hash_bits on-bit masks (0 = empty)
+    const int16_t* hash_vals;    // 2^hash_bits codeword indices
+};
+
+// Parameters of the conservative streaming gate (decode_gate_kernel).
+struct GateParams {
+    float bkg[M3D_MAX_BITS];
+    float rcp[M3D_MAX_BITS];  // ~1/nrm; 0 for padding bits
+    float lo2, hi2;           // squared-magnitude window, widened by the proven error margin
+    int n_bits;
+    int all_candidates;       // 1: vectors outside the margin proof -> every voxel goes to the exact kernel
 };
 
 struct m3d_ctx {
@@ -104,7 +118,9 @@ struct m3d_ctx {
     int nb_pad = 0;  // 16 / 24 / 32
     int K = 0;
     int max_on = 0;
-    int binary = 0;
+    int mode = 0;
+    float cval = 0.f;
+    int hash_bits = 0;
     // device-side codebook artefacts
     float* d_codebook = nullptr;
     uint8_t* d_onbits = nullptr;
@@ -113,12 +129,12 @@ struct m3d_ctx {
     float* d_cw_c = nullptr;
     uint32_t* d_cw_mask = nullptr;
     uint8_t* d_excluded = nullptr;
-    // normalisation state
+    uint32_t* d_hash_keys = nullptr;
+    int16_t* d_hash_vals = nullptr;
+    // normalisation state (identity when use_norm == 0)
     float bkg[M3D_MAX_BITS];
     float nrm[M3D_MAX_BITS];
-    float rcp[M3D_MAX_BITS];
     int use_norm = 0;
-    int safe_div = 1;
     float pix_thr = 0.f, mag_lo = 0.f, mag_hi = 0.f;
     // scratch
     Scratch s_cand;      // decode candidates
@@ -146,6 +162,7 @@ struct m3d_ctx {
     std::vector<TimedSpan> spans;
     double time_ms[KF_COUNT];
     DecodeParams params() const;
+    GateParams gate_params() const;
 };
 
 // Scoped launch accounting: construct right before a launch (or a library call that launches),

@@ -1,15 +1,23 @@
 // decode.cu -- fused per-voxel barcode decode (replaces PD:2354-2643).
 //
-// Fast path (production, result images not requested), two kernels:
-//   decode_gate_kernel   : streaming pass over the (bits,z,y,x) stack, 4 voxels per thread,
-//                          128-bit / 64-bit vector loads.  scale -> clip -> L2 norm ->
-//                          magnitude gates.  Writes decoded = -1 everywhere and appends the
-//                          voxels that pass the gates to a candidate list.  HBM-bound:
-//                          n_bits*sizeof(in) + 2 bytes per voxel.
-//   decode_search_kernel : one thread per candidate; recomputes the trace, L2-normalises,
-//                          finds the nearest codeword (codebook resident in shared memory,
-//                          proxy score + exact float32 re-evaluation), applies the pixel
-//                          gate and exclusions, overwrites decoded[v].
+// Production path (result images not requested), two kernels:
+//   decode_gate_kernel   : ONE streaming pass over the (bits,z,y,x) stack.  Every thread issues all
+//                          of its 128-bit loads (one per bit plane) before touching any of them,
+//                          evaluates a conservative squared-magnitude window, writes decoded = -1
+//                          with a 128-bit store and appends possible foreground voxels to a
+//                          candidate list (warp-aggregated).  It never decides a result: the
+//                          window is widened by a proven margin so the list is a superset.
+//                          HBM-bound: n_bits*sizeof(in) + 2 bytes per voxel.
+//   decode_search_kernel : one lane per candidate.  Exact reference arithmetic (IEEE division,
+//                          sequential sums), exact magnitude gates, nearest codeword with the
+//                          codebook resident in shared memory:
+//                            mode 2 (all rows share on-bit count w and value, e.g. MHD4): top-(w+1)
+//                              selection in registers + hash lookup of the top-w mask; voxels that
+//                              this cannot settle are finished warp-cooperatively (32 lanes split
+//                              the codebook, shuffle arg-max, exact re-evaluation of the near-ties);
+//                            mode 1 / 0: proxy scan with exact re-evaluation / direct scan.
+//                          Winners overwrite decoded[v]; optionally the foreground list and the
+//                          union-find slots for the labelling stage are emitted in the same pass.
 // Dense path (reference-complete images, return_results=True):
 //   decode_dense_kernel  : one thread per voxel, search everywhere, writes decoded int16 and
 //                          magnitude / distance / scaled float16 after round(.,5).
@@ -19,297 +27,583 @@ namespace {
 
 constexpr int GATE_THREADS = 256;
 constexpr int SEARCH_THREADS = 128;
+constexpr int XS_STRIDE = SEARCH_THREADS + 1;  // odd stride: conflict-free rows AND columns
+constexpr int COOP_SWITCH = 12;                // more unresolved lanes than this -> lane-parallel scan
 
-template <typename T>
-struct Vec4;
+// ------------------------------------------------------------------ vector access
+template <typename T, int VPT>
+struct Vec;
 template <>
-struct Vec4<float> {
-    static __device__ __forceinline__ void load(const float* p, float (&o)[4]) {
-        float4 v = __ldcs(reinterpret_cast<const float4*>(p));
-        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-    }
-};
-template <>
-struct Vec4<uint16_t> {
-    static __device__ __forceinline__ void load(const uint16_t* p, float (&o)[4]) {
-        uint2 v = __ldcs(reinterpret_cast<const uint2*>(p));
+struct Vec<uint16_t, 8> {
+    using type = uint4;
+    static __device__ __forceinline__ float get(const uint4& v, int j) {
+        const uint32_t w = (j < 2) ? v.x : (j < 4) ? v.y : (j < 6) ? v.z : v.w;
         // exact uint16 -> float32 through the 2^23 magic number (PRMT + FADD, no I2F)
-        o[0] = __uint_as_float(__byte_perm(v.x, 0x4B000000u, 0x7410)) - 8388608.0f;
-        o[1] = __uint_as_float(__byte_perm(v.x, 0x4B000000u, 0x7432)) - 8388608.0f;
-        o[2] = __uint_as_float(__byte_perm(v.y, 0x4B000000u, 0x7410)) - 8388608.0f;
-        o[3] = __uint_as_float(__byte_perm(v.y, 0x4B000000u, 0x7432)) - 8388608.0f;
+        return __uint_as_float(__byte_perm(w, 0x4B000000u, (j & 1) ? 0x7432 : 0x7410)) - 8388608.0f;
     }
 };
-
-template <typename T>
-struct IsFloatIn { static constexpr bool value = false; };
 template <>
-struct IsFloatIn<float> { static constexpr bool value = true; };
+struct Vec<uint16_t, 4> {
+    using type = uint2;
+    static __device__ __forceinline__ float get(const uint2& v, int j) {
+        const uint32_t w = (j < 2) ? v.x : v.y;
+        return __uint_as_float(__byte_perm(w, 0x4B000000u, (j & 1) ? 0x7432 : 0x7410)) - 8388608.0f;
+    }
+};
+template <>
+struct Vec<uint16_t, 1> {
+    using type = unsigned short;
+    static __device__ __forceinline__ float get(const unsigned short& v, int) { return (float)v; }
+};
+template <>
+struct Vec<float, 4> {
+    using type = float4;
+    static __device__ __forceinline__ float get(const float4& v, int j) {
+        return (j == 0) ? v.x : (j == 1) ? v.y : (j == 2) ? v.z : v.w;
+    }
+};
+template <>
+struct Vec<float, 2> {
+    using type = float2;
+    static __device__ __forceinline__ float get(const float2& v, int j) { return j == 0 ? v.x : v.y; }
+};
+template <>
+struct Vec<float, 1> {
+    using type = float;
+    static __device__ __forceinline__ float get(const float& v, int) { return v; }
+};
 
-// ------------------------------------------------------------------ gate (streaming) kernel
-template <typename T, int NB, bool SAFE>
-__global__ void __launch_bounds__(GATE_THREADS)
-decode_gate_kernel(const T* __restrict__ stack, size_t n_vox, DecodeParams P,
-                   int16_t* __restrict__ decoded, uint32_t* __restrict__ cand,
-                   unsigned int* __restrict__ cand_count) {
-    constexpr bool NANCLIP = IsFloatIn<T>::value;
-    const size_t v0 = ((size_t)blockIdx.x * GATE_THREADS + threadIdx.x) * 4;
-    const bool active = v0 < n_vox;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (active) {
-        float raw[NB][4];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            if (b < P.n_bits) Vec4<T>::load(stack + (size_t)b * n_vox + v0, raw[b]);
-        }
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            if (b < P.n_bits) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float x = scale_clip<SAFE, NANCLIP>(raw[b][j], P.bkg[b], P.nrm[b], P.rcp[b], P.use_norm);
-                    float s = __fmul_rn(x, x);
-                    acc[j] = (b == 0) ? s : __fadd_rn(acc[j], s);
-                }
-            }
-        }
-        // decoded = -1 for the whole vector; the search kernel overwrites decoded voxels
-        uint2 neg;
-        neg.x = 0xFFFFFFFFu;
-        neg.y = 0xFFFFFFFFu;
-        __stcs(reinterpret_cast<uint2*>(decoded + v0), neg);
-    }
-    const unsigned lane = threadIdx.x & 31u;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float mag = __fsqrt_rn(acc[j]);
-        // zero norm is reported as -1 (PD:2462) and can only pass when mag_lo <= -1
-        if (acc[j] == 0.f) mag = -1.f;
-        bool pass = active && (mag >= P.mag_lo) && (mag <= P.mag_hi);
-        unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m) {
-            unsigned base = 0;
-            if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(cand_count, (unsigned)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-            if (pass) cand[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(v0 + j);
-        }
-    }
+template <int VPT>
+__device__ __forceinline__ void store_background(int16_t* p);
+template <>
+__device__ __forceinline__ void store_background<8>(int16_t* p) {
+    __stcs(reinterpret_cast<uint4*>(p), make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu));
+}
+template <>
+__device__ __forceinline__ void store_background<4>(int16_t* p) {
+    __stcs(reinterpret_cast<uint2*>(p), make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu));
+}
+template <>
+__device__ __forceinline__ void store_background<2>(int16_t* p) {
+    __stcs(reinterpret_cast<unsigned int*>(p), 0xFFFFFFFFu);
+}
+template <>
+__device__ __forceinline__ void store_background<1>(int16_t* p) {
+    *p = (int16_t)-1;
 }
 
-// scalar variant for volumes whose voxel count is not a multiple of 4
-template <typename T, int NB, bool SAFE>
+// ------------------------------------------------------------------ gate (streaming) kernel
+template <typename T, int NB, int VPT>
 __global__ void __launch_bounds__(GATE_THREADS)
-decode_gate_scalar_kernel(const T* __restrict__ stack, size_t n_vox, DecodeParams P,
-                          int16_t* __restrict__ decoded, uint32_t* __restrict__ cand,
-                          unsigned int* __restrict__ cand_count) {
-    constexpr bool NANCLIP = IsFloatIn<T>::value;
-    const size_t v = (size_t)blockIdx.x * GATE_THREADS + threadIdx.x;
-    const bool active = v < n_vox;
-    float acc = 0.f;
-    if (active) {
+decode_gate_kernel(const T* __restrict__ stack, size_t n_vox, size_t n_units, GateParams G,
+                   int16_t* __restrict__ decoded, uint32_t* __restrict__ cand,
+                   unsigned int* __restrict__ cand_count) {
+    using V = typename Vec<T, VPT>::type;
+    const size_t unit = (size_t)blockIdx.x * GATE_THREADS + threadIdx.x;
+    const bool active = unit < n_units;
+    const size_t v0 = (active ? unit : n_units - 1) * VPT;  // clamped: loads stay unpredicated
+    V raw[NB];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            if (b < P.n_bits) {
-                float x = scale_clip<SAFE, NANCLIP>(load_elem(stack, (size_t)b * n_vox + v), P.bkg[b],
-                                                    P.nrm[b], P.rcp[b], P.use_norm);
-                float s = __fmul_rn(x, x);
-                acc = (b == 0) ? s : __fadd_rn(acc, s);
-            }
-        }
-        decoded[v] = -1;
+    for (int b = 0; b < NB; ++b) {
+        const int pb = (b < G.n_bits) ? b : (G.n_bits - 1);  // padding planes re-read the last one (L1 hit)
+        raw[b] = __ldcs(reinterpret_cast<const V*>(stack + (size_t)pb * n_vox + v0));
     }
-    float mag = __fsqrt_rn(acc);
-    if (acc == 0.f) mag = -1.f;
-    bool pass = active && (mag >= P.mag_lo) && (mag <= P.mag_hi);
-    unsigned m = __ballot_sync(0xffffffffu, pass);
-    const unsigned lane = threadIdx.x & 31u;
-    if (m) {
+    float acc[VPT];
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const float bg = G.bkg[b], rc = G.rcp[b];  // rcp == 0 on padding planes
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            float q = __fmul_rn(__fsub_rn(Vec<T, VPT>::get(raw[b], j), bg), rc);
+            q = fminf(fmaxf(q, 0.f), 1.f);
+            acc[j] = __fmaf_rn(q, q, acc[j]);
+        }
+    }
+    if (active) store_background<VPT>(decoded + v0);
+    unsigned bits = 0;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+        const bool pass = G.all_candidates || (acc[j] >= G.lo2 && acc[j] <= G.hi2);
+        bits |= (pass ? 1u : 0u) << j;
+    }
+    if (!active) bits = 0;
+    const unsigned cnt = __popc(bits);
+    if (__any_sync(0xffffffffu, cnt != 0)) {
+        const unsigned lane = threadIdx.x & 31u;
+        unsigned incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += n;
+        }
         unsigned base = 0;
-        if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(cand_count, (unsigned)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (pass) cand[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)v;
+        if (lane == 31) base = atomicAdd(cand_count, incl);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        unsigned pos = base + incl - cnt;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j)
+            if ((bits >> j) & 1u) cand[pos++] = (uint32_t)(v0 + j);
     }
 }
 
 // ------------------------------------------------------------------ shared-memory codebook staging
 struct SearchSmem {
-    float* xs;       // [(NB+1)][BLOCK]
-    uint8_t* on;     // [K][max_on]
-    float* a;        // [K]
-    float* g;        // [K]
+    float* xs;           // [(NB+1)][XS_STRIDE]  xh of every thread's voxel; row NB is the zero slot
+    float* a;            // [K]   (mode 1/2 proxy scan)
+    float* g;            // [K]
+    uint32_t* hkeys;     // [1 << hash_bits] (mode 2)
+    int16_t* hvals;      // [1 << hash_bits]
+    uint8_t* on;         // [K][max_on]
 };
 
-template <int NB, int BLOCK>
+static size_t search_smem_bytes(int nb, const DecodeParams& P) {
+    size_t n = (size_t)(nb + 1) * XS_STRIDE * 4;
+    if (P.mode >= 1) n += (size_t)P.K * 8 + (size_t)P.K * P.max_on;
+    if (P.mode == 2) n += ((size_t)1 << P.hash_bits) * 6;
+    return n + 16;
+}
+
+template <int NB>
 __device__ __forceinline__ SearchSmem stage_codebook(unsigned char* smem, const DecodeParams& P) {
     SearchSmem s;
     s.xs = reinterpret_cast<float*>(smem);
-    s.a = s.xs + (NB + 1) * BLOCK;
-    s.g = s.a + P.K;
-    s.on = reinterpret_cast<uint8_t*>(s.g + P.K);
-    if (P.binary) {
-        for (int i = threadIdx.x; i < P.K; i += BLOCK) {
+    float* p = s.xs + (NB + 1) * XS_STRIDE;
+    s.a = s.g = nullptr;
+    s.hkeys = nullptr;
+    s.hvals = nullptr;
+    s.on = nullptr;
+    if (P.mode >= 1) {
+        s.a = p;
+        s.g = p + P.K;
+        p += 2 * P.K;
+        for (int i = threadIdx.x; i < P.K; i += SEARCH_THREADS) {
             s.a[i] = P.cw_a[i];
             s.g[i] = P.cw_g[i];
         }
-        for (int i = threadIdx.x; i < P.K * P.max_on; i += BLOCK) s.on[i] = P.onbits[i];
     }
-    s.xs[NB * BLOCK + threadIdx.x] = 0.f;  // zero slot addressed by padded on-bit entries
+    if (P.mode == 2) {
+        const int hs = 1 << P.hash_bits;
+        s.hkeys = reinterpret_cast<uint32_t*>(p);
+        s.hvals = reinterpret_cast<int16_t*>(s.hkeys + hs);
+        for (int i = threadIdx.x; i < hs; i += SEARCH_THREADS) {
+            s.hkeys[i] = P.hash_keys[i];
+            s.hvals[i] = P.hash_vals[i];
+        }
+        s.on = reinterpret_cast<uint8_t*>(s.hvals + hs);
+    } else if (P.mode == 1) {
+        s.on = reinterpret_cast<uint8_t*>(p);
+    }
+    if (P.mode >= 1)
+        for (int i = threadIdx.x; i < P.K * P.max_on; i += SEARCH_THREADS) s.on[i] = P.onbits[i];
+    s.xs[NB * XS_STRIDE + threadIdx.x] = 0.f;  // zero slot addressed by padded on-bit entries
     __syncthreads();
     return s;
 }
 
-static size_t search_smem_bytes(int nb, int block, int K, int max_on) {
-    return (size_t)(nb + 1) * block * 4 + (size_t)K * 8 + (size_t)K * max_on + 16;
-}
-
-// full per-voxel decode from the raw trace; shared by search and dense kernels
-template <typename T, int NB, bool SAFE, int BLOCK>
-__device__ __forceinline__ void decode_one(const T* __restrict__ stack, size_t n_vox, size_t v,
-                                           const DecodeParams& P, const SearchSmem& S, float (&x)[NB],
-                                           float& mag, float& d, int& k) {
-    constexpr bool NANCLIP = IsFloatIn<T>::value;
+// ------------------------------------------------------------------ exact per-voxel trace
+template <typename T, int NB>
+__device__ __forceinline__ void exact_trace(const T* __restrict__ stack, size_t n_vox, size_t v,
+                                            const DecodeParams& P, float (&x)[NB], float (&xh)[NB], float& mag) {
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        x[b] = 0.f;
-        if (b < P.n_bits)
-            x[b] = scale_clip<SAFE, NANCLIP>(load_elem(stack, (size_t)b * n_vox + v), P.bkg[b], P.nrm[b],
-                                             P.rcp[b], P.use_norm);
+        const int pb = (b < P.n_bits) ? b : (P.n_bits - 1);
+        const float s = load_elem(stack, (size_t)pb * n_vox + v);
+        x[b] = (b < P.n_bits) ? scale_clip(s, P.bkg[b], P.nrm[b]) : 0.f;
     }
-    float n = l2_norm<NB>(x);
-    float xh[NB];
-    mag = unit_vector<NB, SAFE>(x, n, xh);
+    const float n = l2_norm<NB>(x);
+    mag = unit_vector<NB>(x, n, xh);
+}
+
+// ------------------------------------------------------------------ lane-parallel scans (modes 0, 1, 2)
+// Returns first-argmin index and direct-form distance.  col = this thread's xs column.
+template <int NB>
+__device__ __forceinline__ void scan_codebook(const float (&xh)[NB], const DecodeParams& P, const SearchSmem& S,
+                                              const float* __restrict__ col, float& d_out, int& k_out) {
+    float best_d = __int_as_float(0x7f800000);
+    int best_k = 0;
+    if (P.mode >= 1) {
+        float best_p = __int_as_float(0x7f800000);
+        const int mo = P.max_on;
+        for (int k = 0; k < P.K; ++k) {
+            const uint8_t* on = S.on + k * mo;
+            float sum = 0.f;
+            for (int j = 0; j < mo; ++j) sum += col[on[j] * XS_STRIDE];
+            const float p = S.a[k] - S.g[k] * sum;
+            if (p <= best_p + M3D_PROXY_MARGIN) {
+                const float d = direct_distance_binary<NB>(xh, __ldg(P.cw_mask + k), __ldg(P.cw_c + k));
+                if (d < best_d) {
+                    best_d = d;
+                    best_k = k;
+                }
+            }
+            best_p = fminf(best_p, p);
+        }
+        // NaN traces: every comparison is false; NumPy's argmin returns the first NaN (index 0)
+        if (!(best_d == best_d) || best_d == __int_as_float(0x7f800000)) {
+            best_d = direct_distance<NB>(xh, P.codebook);
+            best_k = 0;
+        }
+    } else {
+        for (int k = 0; k < P.K; ++k) {
+            const float d = direct_distance<NB>(xh, P.codebook + (size_t)k * M3D_MAX_BITS);
+            if (d < best_d || k == 0) {
+                best_d = d;
+                best_k = k;
+            }
+        }
+    }
+    d_out = best_d;
+    k_out = best_k;
+}
+
+// ------------------------------------------------------------------ mode 2 fast path
+// Top-(w+1) selection on order-preserving integer keys (xh >= 0): the low 5 mantissa bits carry
+// the bit index, so every key is unique and "remove the maximum" is an equality test.  If the
+// top-w on-bit set is a codeword and beats every other w-subset by more than the float32
+// uncertainty (T_w - T_{w+1} > M3D_SUM_MARGIN), it is THE argmin; its distance is then evaluated
+// with the exact direct form.  Returns false when the voxel needs a real search.
+template <int NB>
+__device__ __forceinline__ bool topw_lookup(const float (&xh)[NB], const DecodeParams& P, const SearchSmem& S,
+                                            float& d_out, int& k_out) {
+    uint32_t key[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) key[b] = (__float_as_uint(xh[b]) & ~31u) | (uint32_t)b;
+    uint32_t mask = 0, kmax = 0;
+    float last = 0.f;
+    const int w = P.max_on;
+    for (int i = 0; i <= w; ++i) {
+        kmax = key[0];
+#pragma unroll
+        for (int b = 1; b < NB; ++b) kmax = max(kmax, key[b]);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) key[b] = (key[b] == kmax) ? 0u : key[b];
+        if (i < w) {
+            mask |= 1u << (kmax & 31u);
+            last = __uint_as_float(kmax & ~31u);
+        }
+    }
+    const float next = __uint_as_float(kmax & ~31u);
+    if (!(last - next > M3D_SUM_MARGIN)) return false;
+    const uint32_t hm = (1u << P.hash_bits) - 1u;
+    uint32_t h = (mask * 2654435761u) >> (32 - P.hash_bits);
+    while (true) {
+        const uint32_t kk = S.hkeys[h];
+        if (kk == mask) break;
+        if (kk == 0u) return false;
+        h = (h + 1u) & hm;
+    }
+    k_out = S.hvals[h];
+    d_out = direct_distance_binary<NB>(xh, mask, P.cval);
+    return true;
+}
+
+// Warp-cooperative search for the voxel held by lane `src` (mode 2): the 32 lanes split the
+// codebook, shuffle-reduce the maximum on-bit sum, re-evaluate every codeword within the margin
+// with the exact direct form and shuffle-reduce (distance, index) lexicographically.
+__device__ __forceinline__ void coop_search(int src, const DecodeParams& P, const SearchSmem& S, int warp_col0,
+                                            float& d_out, int& k_out) {
+    const unsigned lane = threadIdx.x & 31u;
+    const float* col = S.xs + warp_col0 + src;
+    const int mo = P.max_on;
+    float smax = -1.f;
+    for (int k = lane; k < P.K; k += 32) {
+        const uint8_t* on = S.on + k * mo;
+        float sum = 0.f;
+        for (int j = 0; j < mo; ++j) sum += col[on[j] * XS_STRIDE];
+        smax = fmaxf(smax, sum);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+    float best_d = __int_as_float(0x7f800000);
+    int best_k = 0x7fffffff;
+    for (int k = lane; k < P.K; k += 32) {
+        const uint8_t* on = S.on + k * mo;
+        float sum = 0.f;
+        for (int j = 0; j < mo; ++j) sum += col[on[j] * XS_STRIDE];
+        if (sum >= smax - M3D_SUM_MARGIN) {
+            const float d = direct_distance_binary_smem(col, XS_STRIDE, P.n_bits, __ldg(P.cw_mask + k), P.cval);
+            if (d < best_d) {  // k ascends within a lane: ties keep the lower index
+                best_d = d;
+                best_k = k;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, best_d, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+        if (od < best_d || (od == best_d && ok < best_k)) {
+            best_d = od;
+            best_k = ok;
+        }
+    }
+    d_out = best_d;
+    k_out = best_k;
+}
+
+// nearest codeword for the voxels of one warp; `want` = this lane holds a voxel to search.
+// All 32 lanes must call (warp-synchronous).
+template <int NB>
+__device__ __forceinline__ void nearest_codeword_warp(bool want, const float (&xh)[NB], const DecodeParams& P,
+                                                      const SearchSmem& S, float& d, int& k) {
     float* col = S.xs + threadIdx.x;
 #pragma unroll
-    for (int b = 0; b < NB; ++b) col[b * BLOCK] = xh[b];
-    nearest_codeword<NB>(xh, P, col, BLOCK, S.on, S.a, S.g, d, k);
-}
-
-template <typename T, int NB, bool SAFE>
-__global__ void __launch_bounds__(SEARCH_THREADS)
-decode_search_kernel(const T* __restrict__ stack, size_t n_vox, DecodeParams P,
-                     int16_t* __restrict__ decoded, const uint32_t* __restrict__ cand,
-                     const unsigned int* __restrict__ cand_count) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    SearchSmem S = stage_codebook<NB, SEARCH_THREADS>(smem, P);
-    const unsigned n = *cand_count;
-    for (unsigned i = blockIdx.x * SEARCH_THREADS + threadIdx.x; i < n; i += gridDim.x * SEARCH_THREADS) {
-        size_t v = cand[i];
-        float x[NB];
-        float mag, d;
-        int k;
-        decode_one<T, NB, SAFE, SEARCH_THREADS>(stack, n_vox, v, P, S, x, mag, d, k);
-        int16_t dec = apply_gates(d, k, mag, P);
-        if (dec >= 0) decoded[v] = dec;
+    for (int b = 0; b < NB; ++b) col[b * XS_STRIDE] = xh[b];
+    __syncwarp();
+    if (P.mode == 2) {
+        bool done = !want;
+        if (want) done = topw_lookup<NB>(xh, P, S, d, k);
+        unsigned pending = __ballot_sync(0xffffffffu, !done);
+        if (__popc(pending) > COOP_SWITCH) {
+            if (!done) scan_codebook<NB>(xh, P, S, col, d, k);
+        } else {
+            const int warp_col0 = (int)(threadIdx.x & ~31u);
+            while (pending) {
+                const int src = __ffs(pending) - 1;
+                pending &= pending - 1u;
+                float cd;
+                int ck;
+                coop_search(src, P, S, warp_col0, cd, ck);
+                if ((int)(threadIdx.x & 31u) == src) {
+                    d = cd;
+                    k = ck;
+                }
+            }
+        }
+    } else if (want) {
+        scan_codebook<NB>(xh, P, S, col, d, k);
     }
+    __syncwarp();
 }
 
-template <typename T, int NB, bool SAFE>
+// ------------------------------------------------------------------ candidate search kernel
+struct FgSink {  // optional hand-off to the labelling stage (m3d_decode_label)
+    uint32_t* fg;
+    unsigned int* fg_count;
+    uint32_t* parent;
+    uint32_t* aux;
+};
+
+template <typename T, int NB>
 __global__ void __launch_bounds__(SEARCH_THREADS)
-decode_dense_kernel(const T* __restrict__ stack, size_t n_vox, DecodeParams P,
-                    int16_t* __restrict__ decoded, __half* __restrict__ magnitude,
-                    __half* __restrict__ distance, __half* __restrict__ scaled) {
+decode_search_kernel(const T* __restrict__ stack, size_t n_vox, DecodeParams P, int16_t* __restrict__ decoded,
+                     const uint32_t* __restrict__ cand, const unsigned int* __restrict__ cand_count, FgSink sink) {
     extern __shared__ __align__(16) unsigned char smem[];
-    SearchSmem S = stage_codebook<NB, SEARCH_THREADS>(smem, P);
-    for (size_t v = (size_t)blockIdx.x * SEARCH_THREADS + threadIdx.x; v < n_vox;
-         v += (size_t)gridDim.x * SEARCH_THREADS) {
-        float x[NB];
-        float mag, d;
-        int k;
-        decode_one<T, NB, SAFE, SEARCH_THREADS>(stack, n_vox, v, P, S, x, mag, d, k);
-        decoded[v] = apply_gates(d, k, mag, P);
-        if (magnitude) magnitude[v] = round5_f16(mag);
-        if (distance) distance[v] = round5_f16(d);
-        if (scaled) {
+    SearchSmem S = stage_codebook<NB>(smem, P);
+    const unsigned n = *cand_count;
+    const unsigned n_round = (n + 31u) & ~31u;
+    for (unsigned i = blockIdx.x * SEARCH_THREADS + threadIdx.x; i < n_round; i += gridDim.x * SEARCH_THREADS) {
+        const bool valid = i < n;
+        const size_t v = valid ? cand[i] : 0;
+        float x[NB], xh[NB];
+        float mag = -1.f, d = 0.f;
+        int k = 0;
+        bool want = false;
+        if (valid) {
+            exact_trace<T, NB>(stack, n_vox, v, P, x, xh, mag);
+            want = (mag >= P.mag_lo) && (mag <= P.mag_hi);  // exact magnitude gates (PD:2613-2614)
+        } else {
 #pragma unroll
-            for (int b = 0; b < NB; ++b)
-                if (b < P.n_bits) scaled[(size_t)b * n_vox + v] = round5_f16(x[b]);
+            for (int b = 0; b < NB; ++b) xh[b] = 0.f;
+        }
+        nearest_codeword_warp<NB>(want, xh, P, S, d, k);
+        bool fg = false;
+        if (want) {
+            const int16_t dec = apply_gates(d, k, mag, P);
+            if (dec >= 0) {
+                decoded[v] = dec;
+                fg = true;
+            }
+        }
+        if (sink.fg) {
+            if (fg) {
+                sink.parent[v] = (uint32_t)v;
+                sink.aux[v] = 0u;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, fg);
+            if (m) {
+                const unsigned lane = threadIdx.x & 31u;
+                unsigned base = 0;
+                const int leader = __ffs(m) - 1;
+                if ((int)lane == leader) base = atomicAdd(sink.fg_count, (unsigned)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (fg) sink.fg[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)v;
+            }
         }
     }
 }
 
-template <typename T, int NB, bool SAFE>
+// ------------------------------------------------------------------ dense kernel (all result images)
+template <typename T, int NB>
+__global__ void __launch_bounds__(SEARCH_THREADS)
+decode_dense_kernel(const T* __restrict__ stack, size_t n_vox, DecodeParams P, int16_t* __restrict__ decoded,
+                    __half* __restrict__ magnitude, __half* __restrict__ distance, __half* __restrict__ scaled) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SearchSmem S = stage_codebook<NB>(smem, P);
+    const size_t n_round = (n_vox + 31u) & ~(size_t)31u;
+    for (size_t v = (size_t)blockIdx.x * SEARCH_THREADS + threadIdx.x; v < n_round;
+         v += (size_t)gridDim.x * SEARCH_THREADS) {
+        const bool valid = v < n_vox;
+        float x[NB], xh[NB];
+        float mag = -1.f, d = 0.f;
+        int k = 0;
+        if (valid) {
+            exact_trace<T, NB>(stack, n_vox, v, P, x, xh, mag);
+        } else {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) x[b] = xh[b] = 0.f;
+        }
+        // the reference stores the distance of EVERY voxel (PD:2630-2632): search everywhere.
+        // NaN traces skip the ordered searches: NumPy's argmin of an all-NaN column is index 0.
+        bool nan_trace = false;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) nan_trace |= !(xh[b] == xh[b]);
+        nearest_codeword_warp<NB>(valid && !nan_trace, xh, P, S, d, k);
+        if (valid && nan_trace) {
+            d = direct_distance<NB>(xh, P.codebook);
+            k = 0;
+        }
+        if (valid) {
+            decoded[v] = apply_gates(d, k, mag, P);
+            if (magnitude) magnitude[v] = round5_f16(mag);
+            if (distance) distance[v] = round5_f16(d);
+            if (scaled) {
+#pragma unroll
+                for (int b = 0; b < NB; ++b)
+                    if (b < P.n_bits) scaled[(size_t)b * n_vox + v] = round5_f16(x[b]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ launch helpers
+template <typename T, int NB, int VPT>
+int launch_gate(m3d_ctx* ctx, const T* stack, size_t n_vox, int16_t* decoded, uint32_t* cand,
+                unsigned int* cand_count, cudaStream_t st) {
+    const GateParams G = ctx->gate_params();
+    const size_t n_units = n_vox / VPT;
+    const size_t blocks = (n_units + GATE_THREADS - 1) / GATE_THREADS;
+    if (blocks > 0x7fffffffull) return m3d_fail(M3D_ERR_ARG, "m3d_decode: grid too large");
+    M3D_LAUNCH(ctx, KF_DECODE_GATE, st,
+               decode_gate_kernel<T, NB, VPT><<<(unsigned)blocks, GATE_THREADS, 0, st>>>(stack, n_vox, n_units, G,
+                                                                                            decoded, cand, cand_count));
+    M3D_CHECK_LAUNCH();
+    return M3D_OK;
+}
+
+template <typename T>
+struct GateWidth;
+template <>
+struct GateWidth<uint16_t> {  // 128-bit loads; halve when the register file would not hold all planes
+    static constexpr int wide(int nb) { return nb <= 24 ? 8 : 4; }
+    static constexpr int narrow(int nb) { return nb <= 24 ? 4 : 1; }
+};
+template <>
+struct GateWidth<float> {
+    static constexpr int wide(int nb) { return nb <= 24 ? 4 : 2; }
+    static constexpr int narrow(int nb) { return nb <= 24 ? 2 : 1; }
+};
+
+template <typename T, int NB>
+int run_gate(m3d_ctx* ctx, const T* stack, size_t n_vox, int16_t* decoded, uint32_t* cand,
+             unsigned int* cand_count, cudaStream_t st) {
+    constexpr int W = GateWidth<T>::wide(NB);
+    constexpr int N = GateWidth<T>::narrow(NB);
+    const uintptr_t sa = reinterpret_cast<uintptr_t>(stack), da = reinterpret_cast<uintptr_t>(decoded);
+    auto ok = [&](int vpt) {
+        return (n_vox % vpt == 0) && (sa % (vpt * sizeof(T)) == 0) && (da % (vpt * sizeof(int16_t)) == 0);
+    };
+    if (ok(W)) return launch_gate<T, NB, W>(ctx, stack, n_vox, decoded, cand, cand_count, st);
+    if (N > 1 && ok(N)) return launch_gate<T, NB, N>(ctx, stack, n_vox, decoded, cand, cand_count, st);
+    return launch_gate<T, NB, 1>(ctx, stack, n_vox, decoded, cand, cand_count, st);
+}
+
+template <typename T, int NB>
 int launch_decode(m3d_ctx* ctx, const T* stack, size_t n_vox, int16_t* decoded, __half* mag, __half* dist,
-                  __half* scaled, cudaStream_t st) {
-    DecodeParams P = ctx->params();
+                  __half* scaled, const FgSink& sink, cudaStream_t st) {
+    const DecodeParams P = ctx->params();
+    const size_t smem = search_smem_bytes(NB, P);
+    if (smem > 200 * 1024) return m3d_fail(M3D_ERR_CAPACITY, "m3d_decode: codebook needs %zu B of shared memory", smem);
     const bool dense = (mag != nullptr) || (dist != nullptr) || (scaled != nullptr);
     if (dense) {
-        size_t smem = search_smem_bytes(NB, SEARCH_THREADS, P.K, P.max_on);
-        auto kern = decode_dense_kernel<T, NB, SAFE>;
+        auto kern = decode_dense_kernel<T, NB>;
         M3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        size_t want = (n_vox + SEARCH_THREADS - 1) / SEARCH_THREADS;
-        size_t cap = (size_t)ctx->num_sms * 16;
-        int blocks = (int)(want < cap ? want : cap);
-        if (blocks < 1) blocks = 1;
+        const size_t want = (n_vox + SEARCH_THREADS - 1) / SEARCH_THREADS;
+        const size_t cap = (size_t)ctx->num_sms * 16;
+        const int blocks = (int)(want < cap ? want : cap);
         M3D_LAUNCH(ctx, KF_DECODE_DENSE, st,
                    kern<<<blocks, SEARCH_THREADS, smem, st>>>(stack, n_vox, P, decoded, mag, dist, scaled));
         M3D_CHECK_LAUNCH();
         return M3D_OK;
     }
-    // fast path
     if (ctx->s_cand.ensure(n_vox * sizeof(uint32_t))) return M3D_ERR_CUDA;
     if (ctx->s_counters.ensure(256)) return M3D_ERR_CUDA;
     unsigned int* cand_count = reinterpret_cast<unsigned int*>(ctx->s_counters.ptr);
     uint32_t* cand = reinterpret_cast<uint32_t*>(ctx->s_cand.ptr);
     M3D_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(unsigned int), st));
-    const bool vec = (n_vox % 4 == 0) && ((reinterpret_cast<uintptr_t>(stack) & 15u) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(decoded) & 7u) == 0);
-    if (vec) {
-        size_t units = n_vox / 4;
-        int blocks = (int)((units + GATE_THREADS - 1) / GATE_THREADS);
-        M3D_LAUNCH(ctx, KF_DECODE_GATE, st,
-                   decode_gate_kernel<T, NB, SAFE><<<blocks, GATE_THREADS, 0, st>>>(stack, n_vox, P, decoded, cand, cand_count));
-    } else {
-        int blocks = (int)((n_vox + GATE_THREADS - 1) / GATE_THREADS);
-        M3D_LAUNCH(ctx, KF_DECODE_GATE, st,
-                   decode_gate_scalar_kernel<T, NB, SAFE><<<blocks, GATE_THREADS, 0, st>>>(stack, n_vox, P, decoded, cand, cand_count));
-    }
+    int rc = run_gate<T, NB>(ctx, stack, n_vox, decoded, cand, cand_count, st);
+    if (rc) return rc;
+    auto kern = decode_search_kernel<T, NB>;
+    M3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = ctx->num_sms * 8;
+    M3D_LAUNCH(ctx, KF_DECODE_SEARCH, st,
+               kern<<<blocks, SEARCH_THREADS, smem, st>>>(stack, n_vox, P, decoded, cand, cand_count, sink));
     M3D_CHECK_LAUNCH();
-    {
-        size_t smem = search_smem_bytes(NB, SEARCH_THREADS, P.K, P.max_on);
-        auto kern = decode_search_kernel<T, NB, SAFE>;
-        M3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int blocks = ctx->num_sms * 8;
-        M3D_LAUNCH(ctx, KF_DECODE_SEARCH, st,
-                   kern<<<blocks, SEARCH_THREADS, smem, st>>>(stack, n_vox, P, decoded, cand, cand_count));
-        M3D_CHECK_LAUNCH();
-    }
     return M3D_OK;
 }
 
-template <typename T, bool SAFE>
+template <typename T>
 int dispatch_nb(m3d_ctx* ctx, const T* stack, size_t n_vox, int16_t* decoded, __half* mag, __half* dist,
-                __half* scaled, cudaStream_t st) {
+                __half* scaled, const FgSink& sink, cudaStream_t st) {
     switch (ctx->nb_pad) {
-        case 16: return launch_decode<T, 16, SAFE>(ctx, stack, n_vox, decoded, mag, dist, scaled, st);
-        case 24: return launch_decode<T, 24, SAFE>(ctx, stack, n_vox, decoded, mag, dist, scaled, st);
-        case 32: return launch_decode<T, 32, SAFE>(ctx, stack, n_vox, decoded, mag, dist, scaled, st);
+        case 8: return launch_decode<T, 8>(ctx, stack, n_vox, decoded, mag, dist, scaled, sink, st);
+        case 16: return launch_decode<T, 16>(ctx, stack, n_vox, decoded, mag, dist, scaled, sink, st);
+        case 24: return launch_decode<T, 24>(ctx, stack, n_vox, decoded, mag, dist, scaled, sink, st);
+        case 32: return launch_decode<T, 32>(ctx, stack, n_vox, decoded, mag, dist, scaled, sink, st);
     }
     return m3d_fail(M3D_ERR_ARG, "unsupported padded bit count %d", ctx->nb_pad);
 }
 
 }  // namespace
 
+// shared with extract.cu (m3d_decode_label)
+int m3d_check_decode_args(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t dims[3],
+                          int16_t* decoded_dev, size_t* n_vox) {
+    if (!ctx || !stack_dev || !decoded_dev || !dims) return m3d_fail(M3D_ERR_ARG, "m3d_decode: null argument");
+    if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return m3d_fail(M3D_ERR_ARG, "m3d_decode: bad dims");
+    if (dtype != M3D_DTYPE_U16 && dtype != M3D_DTYPE_F32) return m3d_fail(M3D_ERR_ARG, "m3d_decode: dtype %d", dtype);
+    *n_vox = (size_t)dims[0] * dims[1] * dims[2];
+    if (*n_vox >= 0xFFFFFFF0ull) return m3d_fail(M3D_ERR_ARG, "m3d_decode: volume exceeds 2^32 voxels per call");
+    return M3D_OK;
+}
+
+int m3d_decode_internal(m3d_ctx* ctx, const void* stack_dev, int dtype, size_t n_vox, int16_t* decoded_dev,
+                        uint32_t* fg, unsigned int* fg_count, uint32_t* parent, uint32_t* aux, cudaStream_t st) {
+    const FgSink sink{fg, fg_count, parent, aux};
+    if (dtype == M3D_DTYPE_U16)
+        return dispatch_nb<uint16_t>(ctx, reinterpret_cast<const uint16_t*>(stack_dev), n_vox, decoded_dev, nullptr,
+                                     nullptr, nullptr, sink, st);
+    return dispatch_nb<float>(ctx, reinterpret_cast<const float*>(stack_dev), n_vox, decoded_dev, nullptr, nullptr,
+                              nullptr, sink, st);
+}
+
 extern "C" int m3d_decode(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t dims[3],
                           int16_t* decoded_dev, uint16_t* magnitude_f16_dev, uint16_t* distance_f16_dev,
                           uint16_t* scaled_f16_dev, void* stream) {
-    if (!ctx || !stack_dev || !decoded_dev || !dims) return m3d_fail(M3D_ERR_ARG, "m3d_decode: null argument");
-    if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return m3d_fail(M3D_ERR_ARG, "m3d_decode: bad dims");
-    const size_t n_vox = (size_t)dims[0] * dims[1] * dims[2];
-    if (n_vox >= 0xFFFFFFF0ull) return m3d_fail(M3D_ERR_ARG, "m3d_decode: volume exceeds 2^32 voxels per call");
+    size_t n_vox = 0;
+    int rc = m3d_check_decode_args(ctx, stack_dev, dtype, dims, decoded_dev, &n_vox);
+    if (rc) return rc;
     M3D_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     __half* mag = reinterpret_cast<__half*>(magnitude_f16_dev);
     __half* dist = reinterpret_cast<__half*>(distance_f16_dev);
     __half* scaled = reinterpret_cast<__half*>(scaled_f16_dev);
-    const bool safe = ctx->use_norm && ctx->safe_div;
-    if (dtype == M3D_DTYPE_U16) {
-        const uint16_t* s = reinterpret_cast<const uint16_t*>(stack_dev);
-        return safe ? dispatch_nb<uint16_t, true>(ctx, s, n_vox, decoded_dev, mag, dist, scaled, st)
-                    : dispatch_nb<uint16_t, false>(ctx, s, n_vox, decoded_dev, mag, dist, scaled, st);
-    } else if (dtype == M3D_DTYPE_F32) {
-        const float* s = reinterpret_cast<const float*>(stack_dev);
-        return safe ? dispatch_nb<float, true>(ctx, s, n_vox, decoded_dev, mag, dist, scaled, st)
-                    : dispatch_nb<float, false>(ctx, s, n_vox, decoded_dev, mag, dist, scaled, st);
-    }
-    return m3d_fail(M3D_ERR_ARG, "m3d_decode: dtype %d", dtype);
+    const FgSink none{nullptr, nullptr, nullptr, nullptr};
+    if (dtype == M3D_DTYPE_U16)
+        return dispatch_nb<uint16_t>(ctx, reinterpret_cast<const uint16_t*>(stack_dev), n_vox, decoded_dev, mag, dist,
+                                     scaled, none, st);
+    return dispatch_nb<float>(ctx, reinterpret_cast<const float*>(stack_dev), n_vox, decoded_dev, mag, dist, scaled,
+                              none, st);
 }

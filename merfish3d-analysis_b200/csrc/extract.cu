@@ -26,7 +26,7 @@
 namespace {
 
 constexpr uint32_t DROPPED = 0xFFFFFFFFu;
-constexpr int FEAT_MAX_PX = 1024;  // upper bound on maximum_pixels supported by the warp-sort path
+constexpr int FEAT_MAX_PX = 2048;  // upper bound on maximum_pixels supported by the warp-sort path
 
 // counters layout inside ctx->s_counters (uint32 each)
 enum { CNT_CAND = 0, CNT_FG = 1, CNT_ROOTS = 2 };
@@ -195,7 +195,7 @@ ccl_scatter_kernel(const uint32_t* __restrict__ fg, const unsigned int* __restri
 }
 
 // ------------------------------------------------------------------ regionprops
-// NumPy's float32 pairwise sum (numpy/_core/src/umath/loops_utils.h.src), n <= 1024.
+// NumPy's float32 pairwise sum (numpy/_core/src/umath/loops_utils.h.src), n <= 2048.
 __device__ float np_pairwise_sum(const float* a, int n) {
     if (n < 8) {
         float res = 0.f;
@@ -222,20 +222,33 @@ __device__ float np_pairwise_sum(const float* a, int n) {
 }
 
 constexpr int FEAT_WARPS = 4;
+constexpr int FEAT_TILE_STRIDE = M3D_MAX_BITS + 1;
 
-template <typename T>
+static size_t features_smem_bytes(int cap_px) {
+    // per warp: sorted voxel list + magnitude list (cap_px each) + one 32-voxel value tile
+    return (size_t)FEAT_WARPS * ((size_t)cap_px * 8 + 32 * FEAT_TILE_STRIDE * 4);
+}
+
+// One warp per component.  Phase A (lane = voxel): every lane recomputes one voxel's exact trace
+// with the decode kernels' device functions -- float16-rounded scaled values, magnitude and the
+// distance to the component's codeword -- and stages the per-bit values in a shared tile.
+// Phase B (lane = bit): each lane adds its bit's 32 staged values SEQUENTIALLY in raster order,
+// which is the order NumPy's axis-0 reduction uses inside scikit-image's intensity_mean.
+// Integer coordinate sums and the distance minimum are order independent and warp-reduced.
+template <typename T, int NB>
 __global__ void __launch_bounds__(FEAT_WARPS * 32)
 features_kernel(const T* __restrict__ stack, size_t n_vox, int Y, int X, DecodeParams P,
                 const int16_t* __restrict__ decoded, const uint32_t* __restrict__ vox,
                 const uint32_t* __restrict__ offs, const uint32_t* __restrict__ area_by_id, unsigned n_feat,
-                int optimize_mode, double* __restrict__ table, int n_cols) {
-    __shared__ uint32_t s_vox[FEAT_WARPS][FEAT_MAX_PX];
-    __shared__ float s_mag[FEAT_WARPS][FEAT_MAX_PX];
+                int optimize_mode, int cap_px, double* __restrict__ table, int n_cols) {
+    extern __shared__ __align__(16) unsigned char fsm[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    unsigned char* base = fsm + (size_t)warp * ((size_t)cap_px * 8 + 32 * FEAT_TILE_STRIDE * 4);
+    uint32_t* sv = reinterpret_cast<uint32_t*>(base);
+    float* sm = reinterpret_cast<float*>(base + (size_t)cap_px * 4);
+    float* tile = reinterpret_cast<float*>(base + (size_t)cap_px * 8);
     const uint32_t plane = (uint32_t)Y * (uint32_t)X;
-    uint32_t* sv = s_vox[warp];
-    float* sm = s_mag[warp];
     for (unsigned id = blockIdx.x * FEAT_WARPS + warp; id < n_feat; id += gridDim.x * FEAT_WARPS) {
         const int n = (int)area_by_id[id];
         const uint32_t* seg = vox + offs[id];
@@ -243,7 +256,7 @@ features_kernel(const T* __restrict__ stack, size_t n_vox, int Y, int X, DecodeP
         while (Pn < n) Pn <<= 1;
         for (int i = lane; i < Pn; i += 32) sv[i] = (i < n) ? seg[i] : 0xFFFFFFFFu;
         __syncwarp();
-        // bitonic sort, ascending
+        // bitonic sort, ascending (raster order)
         for (int k = 2; k <= Pn; k <<= 1) {
             for (int j = k >> 1; j > 0; j >>= 1) {
                 for (int i = lane; i < Pn; i += 32) {
@@ -267,45 +280,31 @@ features_kernel(const T* __restrict__ stack, size_t n_vox, int Y, int X, DecodeP
         const int x0 = (int)(rem0 - (uint32_t)y0 * (uint32_t)X);
         const int dec_id = decoded[v_first];
         const float* crow = P.codebook + (size_t)(dec_id < 0 ? 0 : dec_id) * M3D_MAX_BITS;
-        const bool bit_lane = lane < P.n_bits;
-        const float c_b = bit_lane ? __ldg(crow + lane) : 0.f;
         float bit_acc = 0.f;
         float dist_min = __int_as_float(0x7f800000);
-        long long sz = 0, sy = 0, sx = 0;
-        long long szz = 0, syy = 0, sxx = 0, szy = 0, szx = 0, syx = 0;
-        for (int j = 0; j < n; ++j) {
-            const uint32_t v = sv[j];
-            float raw = 0.f, x = 0.f;
-            if (bit_lane) {
-                raw = load_elem(stack, (size_t)lane * n_vox + v);
-                x = raw;
-                if (P.use_norm) x = __fdiv_rn(__fsub_rn(raw, P.bkg[lane]), P.nrm[lane]);
-                x = clip01_nan(x);
-            }
-            const float sq = __fmul_rn(x, x);
-            float acc = __shfl_sync(0xffffffffu, sq, 0);
-            for (int b = 1; b < P.n_bits; ++b) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, sq, b));
-            const float nrm2 = __fsqrt_rn(acc);
-            float mag = nrm2, xh;
-            if (nrm2 == 0.f) {
-                mag = -1.f;
-                xh = __fdiv_rn(x, __int_as_float(0x7f800000));
-            } else {
-                xh = __fdiv_rn(x, nrm2);
-            }
-            const float t = __fsub_rn(xh, c_b);
-            const float tsq = __fmul_rn(t, t);
-            float dacc = __shfl_sync(0xffffffffu, tsq, 0);
-            for (int b = 1; b < P.n_bits; ++b) dacc = __fadd_rn(dacc, __shfl_sync(0xffffffffu, tsq, b));
-            const float d = __fsqrt_rn(dacc);
-            const float d16 = __half2float(round5_f16(d));
-            dist_min = fminf(dist_min, d16);
-            if (lane == 0) sm[j] = __half2float(round5_f16(mag));
-            if (bit_lane) {
-                const float val = optimize_mode ? raw : __half2float(round5_f16(x));
-                bit_acc = (j == 0) ? val : __fadd_rn(bit_acc, val);
-            }
-            if (lane == 0) {
+        long long sz = 0, sy = 0, sx = 0, szz = 0, syy = 0, sxx = 0, szy = 0, szx = 0, syx = 0;
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            const int j = c0 + lane;
+            if (j < n) {
+                const uint32_t v = sv[j];
+                float x[NB], xh[NB];
+                float raw_or_scaled;
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    x[b] = 0.f;
+                    raw_or_scaled = 0.f;
+                    if (b < P.n_bits) {
+                        const float raw = load_elem(stack, (size_t)b * n_vox + v);
+                        x[b] = scale_clip(raw, P.bkg[b], P.nrm[b]);
+                        raw_or_scaled = optimize_mode ? raw : __half2float(round5_f16(x[b]));
+                    }
+                    tile[lane * FEAT_TILE_STRIDE + b] = raw_or_scaled;
+                }
+                const float nrm2 = l2_norm<NB>(x);
+                const float mag = unit_vector<NB>(x, nrm2, xh);
+                const float d = direct_distance<NB>(xh, crow);
+                dist_min = fminf(dist_min, __half2float(round5_f16(d)));
+                sm[j] = __half2float(round5_f16(mag));
                 const int z = (int)(v / plane);
                 const uint32_t rem = v - (uint32_t)z * plane;
                 const int y = (int)(rem / (uint32_t)X);
@@ -315,18 +314,39 @@ features_kernel(const T* __restrict__ stack, size_t n_vox, int Y, int X, DecodeP
                 szz += dz * dz; syy += dy * dy; sxx += dx * dx;
                 szy += dz * dy; szx += dz * dx; syx += dy * dx;
             }
+            __syncwarp();
+            if (lane < P.n_bits) {
+                const int cnt = min(32, n - c0);
+                for (int jj = 0; jj < cnt; ++jj) {
+                    const float val = tile[jj * FEAT_TILE_STRIDE + lane];
+                    bit_acc = (c0 == 0 && jj == 0) ? val : __fadd_rn(bit_acc, val);
+                }
+            }
+            __syncwarp();
         }
-        __syncwarp();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            dist_min = fminf(dist_min, __shfl_xor_sync(0xffffffffu, dist_min, o));
+            sz += __shfl_xor_sync(0xffffffffu, sz, o);
+            sy += __shfl_xor_sync(0xffffffffu, sy, o);
+            sx += __shfl_xor_sync(0xffffffffu, sx, o);
+            szz += __shfl_xor_sync(0xffffffffu, szz, o);
+            syy += __shfl_xor_sync(0xffffffffu, syy, o);
+            sxx += __shfl_xor_sync(0xffffffffu, sxx, o);
+            szy += __shfl_xor_sync(0xffffffffu, szy, o);
+            szx += __shfl_xor_sync(0xffffffffu, szx, o);
+            syx += __shfl_xor_sync(0xffffffffu, syx, o);
+        }
         double* row = table + (size_t)id * n_cols;
-        if (bit_lane) {
+        if (lane < P.n_bits) {
             float mean = __fdiv_rn(bit_acc, (float)n);
             if (!optimize_mode) mean = __half2float(__float2half_rn(mean));
             row[M3D_TABLE_FIXED_COLS + lane] = (double)mean;
         }
         if (lane == 0) {
             const double dn = (double)n;
-            float msum = np_pairwise_sum(sm, n);
-            float mmean = __half2float(__float2half_rn(__fdiv_rn(msum, (float)n)));
+            const float msum = np_pairwise_sum(sm, n);
+            const float mmean = __half2float(__float2half_rn(__fdiv_rn(msum, (float)n)));
             row[0] = (double)v_first;
             row[1] = dn;
             row[2] = (double)dec_id;
@@ -349,67 +369,110 @@ features_kernel(const T* __restrict__ stack, size_t n_vox, int Y, int X, DecodeP
     }
 }
 
+template <typename T, int NB>
+int launch_features(m3d_ctx* ctx, const T* stack, size_t n_vox, int Y, int X, const int16_t* decoded,
+                    int optimize_mode, double* table, cudaStream_t st) {
+    const unsigned n_feat = (unsigned)ctx->lab_n_features;
+    const DecodeParams P = ctx->params();
+    const uint32_t* area_by_id = reinterpret_cast<const uint32_t*>(ctx->s_area.ptr);
+    const uint32_t* offs = area_by_id + n_feat;
+    const uint32_t* vox = reinterpret_cast<const uint32_t*>(ctx->s_vox.ptr);
+    const int n_cols = M3D_TABLE_FIXED_COLS + ctx->n_bits;
+    int cap_px = 32;
+    while (cap_px < ctx->lab_max_px) cap_px <<= 1;
+    const size_t smem = features_smem_bytes(cap_px);
+    auto kern = features_kernel<T, NB>;
+    M3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks = (int)((n_feat + FEAT_WARPS - 1) / FEAT_WARPS);
+    const int cap = ctx->num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    M3D_LAUNCH(ctx, KF_FEATURES, st,
+               kern<<<blocks, FEAT_WARPS * 32, smem, st>>>(stack, n_vox, Y, X, P, decoded, vox, offs, area_by_id, n_feat,
+                                                           optimize_mode, cap_px, table, n_cols));
+    M3D_CHECK_LAUNCH();
+    return M3D_OK;
+}
+
+template <typename T>
+int dispatch_features(m3d_ctx* ctx, const T* stack, size_t n_vox, int Y, int X, const int16_t* decoded,
+                      int optimize_mode, double* table, cudaStream_t st) {
+    switch (ctx->nb_pad) {
+        case 8: return launch_features<T, 8>(ctx, stack, n_vox, Y, X, decoded, optimize_mode, table, st);
+        case 16: return launch_features<T, 16>(ctx, stack, n_vox, Y, X, decoded, optimize_mode, table, st);
+        case 24: return launch_features<T, 24>(ctx, stack, n_vox, Y, X, decoded, optimize_mode, table, st);
+        case 32: return launch_features<T, 32>(ctx, stack, n_vox, Y, X, decoded, optimize_mode, table, st);
+    }
+    return m3d_fail(M3D_ERR_ARG, "unsupported padded bit count %d", ctx->nb_pad);
+}
+
 }  // namespace
 
 // ====================================================================== host entry points
-extern "C" int m3d_label(m3d_ctx* ctx, const int16_t* decoded_dev, const int64_t dims[3], int mode2d,
-                         double minimum_pixels, int maximum_pixels, int32_t* labels_dev,
-                         int64_t* n_features_out, void* stream) {
-    if (!ctx || !decoded_dev || !dims || !n_features_out) return m3d_fail(M3D_ERR_ARG, "m3d_label: null argument");
+// defined in decode.cu
+int m3d_check_decode_args(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t dims[3],
+                          int16_t* decoded_dev, size_t* n_vox);
+int m3d_decode_internal(m3d_ctx* ctx, const void* stack_dev, int dtype, size_t n_vox, int16_t* decoded_dev,
+                        uint32_t* fg, unsigned int* fg_count, uint32_t* parent, uint32_t* aux, cudaStream_t st);
+
+namespace {
+
+struct LabelScratch {
+    unsigned int* counters;
+    uint32_t *fg, *root_of, *parent, *aux;
+};
+
+int label_prepare(m3d_ctx* ctx, const int64_t dims[3], int maximum_pixels, int32_t* labels_dev, size_t* n_vox_out,
+                  LabelScratch* L, cudaStream_t st) {
     if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return m3d_fail(M3D_ERR_ARG, "m3d_label: bad dims");
     const size_t n_vox = (size_t)dims[0] * dims[1] * dims[2];
     if (n_vox >= 0xFFFFFFF0ull) return m3d_fail(M3D_ERR_ARG, "m3d_label: volume exceeds 2^32 voxels per call");
     if (maximum_pixels < 1 || maximum_pixels > FEAT_MAX_PX)
         return m3d_fail(M3D_ERR_ARG, "m3d_label: maximum_pixels must be in [1, %d]", FEAT_MAX_PX);
-    M3D_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int Z = (int)dims[0], Y = (int)dims[1], X = (int)dims[2];
     ctx->lab_n_features = -1;
-
     if (ctx->s_counters.ensure(256)) return M3D_ERR_CUDA;
     if (ctx->s_fg.ensure(2 * n_vox * sizeof(uint32_t))) return M3D_ERR_CUDA;  // fg list + root_of
     if (ctx->s_parent.ensure(n_vox * sizeof(uint32_t))) return M3D_ERR_CUDA;
     if (ctx->s_aux.ensure(n_vox * sizeof(uint32_t))) return M3D_ERR_CUDA;
-    unsigned int* counters = reinterpret_cast<unsigned int*>(ctx->s_counters.ptr);
-    uint32_t* fg = reinterpret_cast<uint32_t*>(ctx->s_fg.ptr);
-    uint32_t* root_of = fg + n_vox;
-    uint32_t* parent = reinterpret_cast<uint32_t*>(ctx->s_parent.ptr);
-    uint32_t* aux = reinterpret_cast<uint32_t*>(ctx->s_aux.ptr);
-    M3D_CUDA(cudaMemsetAsync(counters + CNT_FG, 0, 2 * sizeof(unsigned int), st));
+    L->counters = reinterpret_cast<unsigned int*>(ctx->s_counters.ptr);
+    L->fg = reinterpret_cast<uint32_t*>(ctx->s_fg.ptr);
+    L->root_of = L->fg + n_vox;
+    L->parent = reinterpret_cast<uint32_t*>(ctx->s_parent.ptr);
+    L->aux = reinterpret_cast<uint32_t*>(ctx->s_aux.ptr);
+    M3D_CUDA(cudaMemsetAsync(L->counters + CNT_FG, 0, 2 * sizeof(unsigned int), st));
     if (labels_dev) M3D_CUDA(cudaMemsetAsync(labels_dev, 0, n_vox * sizeof(int32_t), st));
+    *n_vox_out = n_vox;
+    return M3D_OK;
+}
 
-    {
-        const int vec = ((reinterpret_cast<uintptr_t>(decoded_dev) & 15u) == 0) ? 1 : 0;
-        const size_t threads = (n_vox + 7) / 8;
-        const int blocks = (int)((threads + 255) / 256);
-        M3D_LAUNCH(ctx, KF_CCL_COLLECT, st,
-                   ccl_collect_kernel<<<blocks, 256, 0, st>>>(decoded_dev, n_vox, vec, fg, counters + CNT_FG, parent, aux));
-        M3D_CHECK_LAUNCH();
-    }
+// union-find over the foreground list -> size filters -> canonical ids -> voxels grouped by id
+int label_finish(m3d_ctx* ctx, const int16_t* decoded_dev, const int64_t dims[3], size_t n_vox, int mode2d,
+                 double minimum_pixels, int maximum_pixels, int32_t* labels_dev, int64_t* n_features_out,
+                 const LabelScratch& L, cudaStream_t st) {
+    const int Z = (int)dims[0], Y = (int)dims[1], X = (int)dims[2];
+    unsigned int* counters = L.counters;
     const int sparse_blocks = ctx->num_sms * 8;
     M3D_LAUNCH(ctx, KF_CCL_MERGE, st,
-               ccl_merge_kernel<<<sparse_blocks, 256, 0, st>>>(decoded_dev, fg, counters + CNT_FG, parent, Z, Y, X, mode2d ? 1 : 0));
+               ccl_merge_kernel<<<sparse_blocks, 256, 0, st>>>(decoded_dev, L.fg, counters + CNT_FG, L.parent, Z, Y, X,
+                                                               mode2d ? 1 : 0));
     M3D_CHECK_LAUNCH();
     M3D_LAUNCH(ctx, KF_CCL_COMPRESS, st,
-               ccl_compress_kernel<<<sparse_blocks, 256, 0, st>>>(fg, counters + CNT_FG, parent, aux, root_of));
+               ccl_compress_kernel<<<sparse_blocks, 256, 0, st>>>(L.fg, counters + CNT_FG, L.parent, L.aux, L.root_of));
     M3D_CHECK_LAUNCH();
 
     // PD:2976-2989: drop area > maximum_pixels; drop area <= max(int(minimum_pixels)-1, 0)
-    long long max_size = (long long)minimum_pixels - 1;  // int() truncates toward zero like Python for >= 0
-    if (minimum_pixels < 0) max_size = (long long)minimum_pixels - 1;
+    long long max_size = (long long)minimum_pixels - 1;  // (long long) truncates toward zero like Python's int()
     if (max_size < 0) max_size = 0;
     const uint32_t min_keep = (uint32_t)(max_size + 1);
-    // roots list shares the candidate scratch (n_vox uint32 is an upper bound)
-    if (ctx->s_roots.ensure((n_vox / (min_keep ? min_keep : 1) + 64) * 2 * sizeof(uint32_t))) return M3D_ERR_CUDA;
+    if (ctx->s_roots.ensure((n_vox / min_keep + 64) * 2 * sizeof(uint32_t))) return M3D_ERR_CUDA;
     uint32_t* roots = reinterpret_cast<uint32_t*>(ctx->s_roots.ptr);
     const size_t roots_cap = ctx->s_roots.cap / (2 * sizeof(uint32_t));
     uint32_t* roots_sorted = roots + roots_cap;
     M3D_LAUNCH(ctx, KF_CCL_SELECT, st,
-               ccl_select_kernel<<<sparse_blocks, 256, 0, st>>>(fg, counters + CNT_FG, root_of, aux, min_keep,
+               ccl_select_kernel<<<sparse_blocks, 256, 0, st>>>(L.fg, counters + CNT_FG, L.root_of, L.aux, min_keep,
                                                                 (uint32_t)maximum_pixels, roots, counters + CNT_ROOTS));
     M3D_CHECK_LAUNCH();
 
-    unsigned int h_counts[2];
+    unsigned int* h_counts = reinterpret_cast<unsigned int*>(ctx->h_pinned);
     M3D_CUDA(cudaMemcpyAsync(h_counts, counters + CNT_FG, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     M3D_CUDA(cudaStreamSynchronize(st));
     const unsigned n_fg = h_counts[0], n_roots = h_counts[1];
@@ -438,7 +501,7 @@ extern "C" int m3d_label(m3d_ctx* ctx, const int16_t* decoded_dev, const int64_t
     uint32_t* offs = area_by_id + n_roots;
     uint32_t* cursor = offs + n_roots;
     M3D_LAUNCH(ctx, KF_CCL_ASSIGN, st,
-               ccl_assign_kernel<<<(n_roots + 255) / 256, 256, 0, st>>>(roots_sorted, n_roots, aux, area_by_id));
+               ccl_assign_kernel<<<(n_roots + 255) / 256, 256, 0, st>>>(roots_sorted, n_roots, L.aux, area_by_id));
     M3D_CHECK_LAUNCH();
     {
         KernelScope ks(ctx, KF_CCL_SCAN, st);
@@ -448,11 +511,57 @@ extern "C" int m3d_label(m3d_ctx* ctx, const int16_t* decoded_dev, const int64_t
     if (ctx->s_vox.ensure((size_t)n_fg * sizeof(uint32_t))) return M3D_ERR_CUDA;
     uint32_t* vox = reinterpret_cast<uint32_t*>(ctx->s_vox.ptr);
     M3D_LAUNCH(ctx, KF_CCL_SCATTER, st,
-               ccl_scatter_kernel<<<sparse_blocks, 256, 0, st>>>(fg, counters + CNT_FG, root_of, aux, offs, cursor, vox, labels_dev));
+               ccl_scatter_kernel<<<sparse_blocks, 256, 0, st>>>(L.fg, counters + CNT_FG, L.root_of, L.aux, offs, cursor,
+                                                                 vox, labels_dev));
     M3D_CHECK_LAUNCH();
     ctx->lab_n_features = n_roots;
     *n_features_out = n_roots;
     return M3D_OK;
+}
+
+}  // namespace
+
+extern "C" int m3d_label(m3d_ctx* ctx, const int16_t* decoded_dev, const int64_t dims[3], int mode2d,
+                         double minimum_pixels, int maximum_pixels, int32_t* labels_dev,
+                         int64_t* n_features_out, void* stream) {
+    if (!ctx || !decoded_dev || !dims || !n_features_out) return m3d_fail(M3D_ERR_ARG, "m3d_label: null argument");
+    M3D_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    size_t n_vox = 0;
+    LabelScratch L;
+    int rc = label_prepare(ctx, dims, maximum_pixels, labels_dev, &n_vox, &L, st);
+    if (rc) return rc;
+    {
+        const int vec = ((reinterpret_cast<uintptr_t>(decoded_dev) & 15u) == 0) ? 1 : 0;
+        const size_t threads = (n_vox + 7) / 8;
+        const int blocks = (int)((threads + 255) / 256);
+        M3D_LAUNCH(ctx, KF_CCL_COLLECT, st,
+                   ccl_collect_kernel<<<blocks, 256, 0, st>>>(decoded_dev, n_vox, vec, L.fg, L.counters + CNT_FG, L.parent,
+                                                              L.aux));
+        M3D_CHECK_LAUNCH();
+    }
+    return label_finish(ctx, decoded_dev, dims, n_vox, mode2d, minimum_pixels, maximum_pixels, labels_dev,
+                        n_features_out, L, st);
+}
+
+extern "C" int m3d_decode_label(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t dims[3],
+                                int16_t* decoded_dev, int mode2d, double minimum_pixels, int maximum_pixels,
+                                int32_t* labels_dev, int64_t* n_features_out, void* stream) {
+    if (!n_features_out) return m3d_fail(M3D_ERR_ARG, "m3d_decode_label: null argument");
+    size_t n_vox = 0;
+    int rc = m3d_check_decode_args(ctx, stack_dev, dtype, dims, decoded_dev, &n_vox);
+    if (rc) return rc;
+    M3D_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    LabelScratch L;
+    rc = label_prepare(ctx, dims, maximum_pixels, labels_dev, &n_vox, &L, st);
+    if (rc) return rc;
+    // the search kernel emits the foreground list and initialises the union-find slots: no
+    // second pass over the decoded image
+    rc = m3d_decode_internal(ctx, stack_dev, dtype, n_vox, decoded_dev, L.fg, L.counters + CNT_FG, L.parent, L.aux, st);
+    if (rc) return rc;
+    return label_finish(ctx, decoded_dev, dims, n_vox, mode2d, minimum_pixels, maximum_pixels, labels_dev,
+                        n_features_out, L, st);
 }
 
 extern "C" int m3d_features(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t dims[3],
@@ -471,24 +580,9 @@ extern "C" int m3d_features(m3d_ctx* ctx, const void* stack_dev, int dtype, cons
     M3D_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const size_t n_vox = (size_t)dims[0] * dims[1] * dims[2];
-    const unsigned n_feat = (unsigned)ctx->lab_n_features;
-    DecodeParams P = ctx->params();
-    const uint32_t* area_by_id = reinterpret_cast<const uint32_t*>(ctx->s_area.ptr);
-    const uint32_t* offs = area_by_id + n_feat;
-    const uint32_t* vox = reinterpret_cast<const uint32_t*>(ctx->s_vox.ptr);
-    const int n_cols = M3D_TABLE_FIXED_COLS + ctx->n_bits;
-    int blocks = (int)((n_feat + FEAT_WARPS - 1) / FEAT_WARPS);
-    const int cap = ctx->num_sms * 16;
-    if (blocks > cap) blocks = cap;
-    KernelScope ks(ctx, KF_FEATURES, st);
     if (dtype == M3D_DTYPE_U16)
-        features_kernel<uint16_t><<<blocks, FEAT_WARPS * 32, 0, st>>>(
-            reinterpret_cast<const uint16_t*>(stack_dev), n_vox, (int)dims[1], (int)dims[2], P, decoded_dev, vox, offs,
-            area_by_id, n_feat, optimize_mode, table_dev, n_cols);
-    else
-        features_kernel<float><<<blocks, FEAT_WARPS * 32, 0, st>>>(
-            reinterpret_cast<const float*>(stack_dev), n_vox, (int)dims[1], (int)dims[2], P, decoded_dev, vox, offs,
-            area_by_id, n_feat, optimize_mode, table_dev, n_cols);
-    M3D_CHECK_LAUNCH();
-    return M3D_OK;
+        return dispatch_features<uint16_t>(ctx, reinterpret_cast<const uint16_t*>(stack_dev), n_vox, (int)dims[1],
+                                           (int)dims[2], decoded_dev, optimize_mode, table_dev, st);
+    return dispatch_features<float>(ctx, reinterpret_cast<const float*>(stack_dev), n_vox, (int)dims[1], (int)dims[2],
+                                    decoded_dev, optimize_mode, table_dev, st);
 }

@@ -76,14 +76,15 @@ class DeviceOrderStats:
             remaining = rank
             for shift, width in zip(_SHIFTS, _WIDTHS):
                 h = self._pass(volumes, sub, clip0, pred, cutoffs, prefix_mask, prefix_value, shift)
-                h = h[: 1 << width]
+                # the last digit (10 bits) is histogrammed with the kernel's fixed 11-bit mask: its
+                # top bit repeats the previous digit's lowest bit, already pinned by the prefix
                 cum = np.cumsum(h)
                 b = int(np.searchsorted(cum, remaining, side="right"))
                 if b >= h.size:
                     raise ValueError("rank beyond the population")
                 remaining -= int(cum[b - 1]) if b > 0 else 0
                 prefix_value |= b << shift
-                prefix_mask |= ((1 << width) - 1) << shift
+                prefix_mask |= (((1 << width) - 1) << shift) & 0xFFFFFFFF
             cache[rank] = _key_to_f32(prefix_value)
             out.append(cache[rank])
         return out

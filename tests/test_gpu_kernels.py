@@ -74,8 +74,9 @@ def test_decode_u16_bit_exact(torch, dense, use_norm):
     _df, cb = cases.codebook16()
     stack = cases.small_stack(cb["matrix"], shape=(10, 40, 64), seed=11)
     bkg, nrm = cases.simple_vectors(16) if use_norm else (None, None)
-    mag = (1.5, 10.0) if use_norm else (2000.0, 1.0e6)
-    _c, _s, _d, got, ref = _decode_both(torch, cb, stack, bkg, nrm, mag=mag, dense=dense)
+    if not use_norm:  # unnormalised decode of a float stack that already lives in [0, 1]-ish units
+        stack = ((stack.astype(np.float32) - 200.0) / 900.0).astype(np.float32)
+    _c, _s, _d, got, ref = _decode_both(torch, cb, stack, bkg, nrm, dense=dense)
     np.testing.assert_array_equal(got["decoded"], ref["decoded"])
     assert (ref["decoded"] >= 0).sum() > 100
     if dense:
@@ -237,6 +238,27 @@ def test_label_matches_oracle(torch, mode2d, fill):
     ref = cases.canonical_labels(ref)
     np.testing.assert_array_equal(labels.cpu().numpy(), ref)
     assert n == ref.max() and n > 5
+
+
+@pytest.mark.parametrize("mode2d", [False, True])
+def test_fused_decode_label_equals_separate_calls(torch, mode2d):
+    _df, cb = cases.codebook16()
+    stack = cases.small_stack(cb["matrix"], shape=(9, 40, 56), seed=67)
+    bkg, nrm = cases.simple_vectors(16)
+    ctx, d_stack, dec, got, ref = _decode_both(torch, cb, stack, bkg, nrm, dense=False)
+    lab_a = torch.zeros(dec.shape, dtype=torch.int32, device="cuda")
+    n_a = ctx.label(dec, mode2d, 4.0, 500, labels=lab_a)
+    tab_a = ctx.features(d_stack, dec, False).cpu().numpy()
+    dec_b = torch.empty_like(dec)
+    lab_b = torch.zeros(dec.shape, dtype=torch.int32, device="cuda")
+    n_b = ctx.decode_label(d_stack, dec_b, mode2d, 4.0, 500, labels=lab_b)
+    tab_b = ctx.features(d_stack, dec_b, False).cpu().numpy()
+    assert n_a == n_b and n_a > 10
+    np.testing.assert_array_equal(dec_b.cpu().numpy(), ref["decoded"])
+    np.testing.assert_array_equal(lab_a.cpu().numpy(), lab_b.cpu().numpy())
+    np.testing.assert_array_equal(tab_a, tab_b)
+    ref_lab = cases.canonical_labels(orc.filter_label_sizes(orc.label_decoded(ref["decoded"], not mode2d), 4.0, 500))
+    np.testing.assert_array_equal(lab_b.cpu().numpy(), ref_lab)
 
 
 def test_label_edge_cases(torch):

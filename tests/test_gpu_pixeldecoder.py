@@ -109,10 +109,13 @@ def test_decode_api_errors(tmp_path):
     dec = PixelDecoder(ds, verbose=0, decode_mode="3d")
     with pytest.raises(ValueError, match="two z planes"):
         dec.decode_one_tile(0, normalization_method="none")
+    auto = PixelDecoder(ds, verbose=0)  # 'auto' does not enforce the two-plane rule (PD:1895)
     with pytest.raises(ValueError, match="three values"):
-        dec.decode_one_tile(0, normalization_method="none", lowpass_sigma=(1, 1))
+        auto.decode_one_tile(0, normalization_method="none", lowpass_sigma=(1, 1))
     with pytest.raises(ValueError, match="normalization_method"):
-        dec.decode_one_tile(0, normalization_method="bogus")
+        auto.decode_one_tile(0, normalization_method="bogus")
+    assert auto.decode_one_tile(0, normalization_method="none", lowpass_sigma=None) is None
+    assert len(auto.decoded_barcodes) == 0 and list(auto.decoded_barcodes.columns)[:4] == ["area", "z", "y", "x"]
 
 
 def test_optimize_normalization_matches_oracle(tmp_path):
