@@ -206,12 +206,15 @@ __device__ __forceinline__ SearchSmem stage_codebook(unsigned char* smem, const 
 template <typename T, int NB>
 __device__ __forceinline__ void exact_trace(const T* __restrict__ stack, size_t n_vox, size_t v,
                                             const DecodeParams& P, float (&x)[NB], float (&xh)[NB], float& mag) {
+    // issue every bit-plane load before the (branchy) IEEE divisions consume them
+    float s[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const int pb = (b < P.n_bits) ? b : (P.n_bits - 1);
-        const float s = load_elem(stack, (size_t)pb * n_vox + v);
-        x[b] = (b < P.n_bits) ? scale_clip(s, P.bkg[b], P.nrm[b]) : 0.f;
+        s[b] = load_elem(stack, (size_t)pb * n_vox + v);
     }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) x[b] = (b < P.n_bits) ? scale_clip(s[b], P.bkg[b], P.nrm[b]) : 0.f;
     const float n = l2_norm<NB>(x);
     mag = unit_vector<NB>(x, n, xh);
 }

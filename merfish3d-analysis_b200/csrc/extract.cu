@@ -99,6 +99,35 @@ __device__ __forceinline__ void uf_union(uint32_t* L, uint32_t a, uint32_t b) {
     }
 }
 
+// Backward half of the 26-neighbourhood, ordered by how many of the others each one touches.
+// If neighbour j has the voxel's value, every other same-valued neighbour adjacent to j is already
+// joined to j by its own backward edge, so one union covers them all (ADJ masks below); a blob
+// interior voxel needs a single union through (-1,0,0) instead of 13.
+__host__ __device__ constexpr int nb_off(int j, int axis) {
+    constexpr int t[13][3] = {{-1, 0, 0},  {0, -1, 0},  {0, 0, -1}, {-1, -1, 0}, {-1, 1, 0},
+                              {-1, 0, -1}, {-1, 0, 1},  {0, -1, -1}, {0, -1, 1}, {-1, -1, -1},
+                              {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1}};
+    return t[j][axis];
+}
+__host__ __device__ constexpr uint32_t nb_adj(int j) {
+    uint32_t m = 0;
+    for (int k = 0; k < 13; ++k) {
+        bool near = true;
+        for (int a = 0; a < 3; ++a) {
+            const int d = nb_off(j, a) - nb_off(k, a);
+            if (d > 1 || d < -1) near = false;
+        }
+        if (near) m |= 1u << k;
+    }
+    return m;
+}
+__constant__ int8_t c_nb_off[13][3] = {{-1, 0, 0},  {0, -1, 0},  {0, 0, -1}, {-1, -1, 0}, {-1, 1, 0},
+                                       {-1, 0, -1}, {-1, 0, 1},  {0, -1, -1}, {0, -1, 1}, {-1, -1, -1},
+                                       {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1}};
+__constant__ uint32_t c_nb_adj[13] = {nb_adj(0), nb_adj(1), nb_adj(2),  nb_adj(3),  nb_adj(4),  nb_adj(5), nb_adj(6),
+                                      nb_adj(7), nb_adj(8), nb_adj(9), nb_adj(10), nb_adj(11), nb_adj(12)};
+static_assert(nb_adj(0) == 0x1FFFu, "(-1,0,0) touches every backward neighbour");
+
 __global__ void __launch_bounds__(256)
 ccl_merge_kernel(const int16_t* __restrict__ decoded, const uint32_t* __restrict__ fg,
                  const unsigned int* __restrict__ fg_count, uint32_t* __restrict__ parent, int Z, int Y, int X,
@@ -112,22 +141,24 @@ ccl_merge_kernel(const int16_t* __restrict__ decoded, const uint32_t* __restrict
         const uint32_t rem = v - (uint32_t)z * plane;
         const int y = (int)(rem / (uint32_t)X);
         const int x = (int)(rem - (uint32_t)y * (uint32_t)X);
-        // backward half of the neighbourhood, lexicographic (dz,dy,dx) < (0,0,0)
-        for (int dz = mode2d ? 0 : -1; dz <= 0; ++dz) {
-            const int zz = z + dz;
-            if (zz < 0) continue;
-            const int dy_hi = (dz < 0) ? 1 : 0;
-            for (int dy = -1; dy <= dy_hi; ++dy) {
-                const int yy = y + dy;
-                if (yy < 0 || yy >= Y) continue;
-                const int dx_hi = (dz < 0 || dy < 0) ? 1 : -1;
-                for (int dx = -1; dx <= dx_hi; ++dx) {
-                    const int xx = x + dx;
-                    if (xx < 0 || xx >= X) continue;
-                    const uint32_t nb = (uint32_t)zz * plane + (uint32_t)yy * (uint32_t)X + (uint32_t)xx;
-                    if (decoded[nb] == val) uf_union(parent, v, nb);
-                }
-            }
+        // all 13 neighbour loads are issued before any is used
+        int16_t nv[13];
+#pragma unroll
+        for (int j = 0; j < 13; ++j) {
+            const int dz = nb_off(j, 0), dy = nb_off(j, 1), dx = nb_off(j, 2);
+            const bool inb = (z + dz >= 0) && (y + dy >= 0) && (y + dy < Y) && (x + dx >= 0) && (x + dx < X) &&
+                             !(mode2d && dz != 0);
+            const long long off = (long long)dz * plane + (long long)dy * X + dx;
+            nv[j] = inb ? decoded[(long long)v + off] : (int16_t)-2;
+        }
+        uint32_t same = 0;
+#pragma unroll
+        for (int j = 0; j < 13; ++j) same |= (nv[j] == val ? 1u : 0u) << j;
+        while (same) {
+            const int j = __ffs(same) - 1;
+            same &= ~c_nb_adj[j];
+            const long long off = (long long)c_nb_off[j][0] * plane + (long long)c_nb_off[j][1] * X + c_nb_off[j][2];
+            uf_union(parent, v, (uint32_t)((long long)v + off));
         }
     }
 }
@@ -287,18 +318,18 @@ features_kernel(const T* __restrict__ stack, size_t n_vox, int Y, int X, DecodeP
             const int j = c0 + lane;
             if (j < n) {
                 const uint32_t v = sv[j];
-                float x[NB], xh[NB];
-                float raw_or_scaled;
+                float x[NB], xh[NB], raw[NB];
+                // issue every bit-plane load before the (branchy) IEEE divisions consume them
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
-                    x[b] = 0.f;
-                    raw_or_scaled = 0.f;
-                    if (b < P.n_bits) {
-                        const float raw = load_elem(stack, (size_t)b * n_vox + v);
-                        x[b] = scale_clip(raw, P.bkg[b], P.nrm[b]);
-                        raw_or_scaled = optimize_mode ? raw : __half2float(round5_f16(x[b]));
-                    }
-                    tile[lane * FEAT_TILE_STRIDE + b] = raw_or_scaled;
+                    const int pb = (b < P.n_bits) ? b : (P.n_bits - 1);
+                    raw[b] = load_elem(stack, (size_t)pb * n_vox + v);
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    x[b] = (b < P.n_bits) ? scale_clip(raw[b], P.bkg[b], P.nrm[b]) : 0.f;
+                    const float val = optimize_mode ? raw[b] : __half2float(round5_f16(x[b]));
+                    tile[lane * FEAT_TILE_STRIDE + b] = (b < P.n_bits) ? val : 0.f;
                 }
                 const float nrm2 = l2_norm<NB>(x);
                 const float mag = unit_vector<NB>(x, nrm2, xh);

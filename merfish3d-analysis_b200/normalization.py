@@ -91,19 +91,28 @@ class DeviceOrderStats:
 
     # ------------------------------------------------------------------ NumPy-exact wrappers
     def percentile(self, volume, q: float, sub=0.0, clip0=False):
-        """``np.percentile(v.ravel(), q)`` (method 'linear'): float64 like NumPy returns."""
-        n = volume.numel()
+        """``np.percentile(v.ravel(), q)`` for a float32 volume, method 'linear'.
+
+        NumPy (2.x) keeps the whole computation in the array's dtype: q/100, the virtual index
+        (n-1)*q and the interpolation weight are float32 -- for 4e8-voxel volumes the index is
+        therefore quantised, and so it is here.  Returns np.float32 like NumPy."""
+        n = int(volume.numel())
         if n == 0:
             return None
-        virtual = (n - 1) * np.true_divide(q, 100.0)
+        q32 = np.true_divide(q, np.float32(100))
+        virtual = np.float32((n - 1) * q32)
         prev = int(np.floor(virtual))
-        nxt = min(prev + 1, n - 1)
-        a, b = self.select([volume], [prev, nxt], sub=sub, clip0=clip0)
-        gamma = np.float64(virtual - prev)
-        diff = np.subtract(np.float32(b), np.float32(a))  # float32, like NumPy's _lerp
-        if gamma >= 0.5:
-            return np.float64(np.float32(b)) - np.float64(diff) * (1 - gamma)
-        return np.float64(np.float32(a)) + np.float64(diff) * gamma
+        nxt = prev + 1
+        if virtual >= n - 1:
+            prev = nxt = n - 1
+        if virtual < 0:
+            prev = nxt = 0
+        a, b = (np.float32(v) for v in self.select([volume], [prev, nxt], sub=sub, clip0=clip0))
+        gamma = np.float32(np.float64(virtual) - prev)
+        diff = np.float32(b - a)
+        if gamma >= np.float32(0.5):
+            return np.float32(b - np.float32(diff * np.float32(1 - gamma)))
+        return np.float32(a + np.float32(diff * gamma))
 
     def median(self, volumes, sub=0.0, clip0=False, pred=PRED_ALL, cutoffs=None):
         """``np.median`` of the pooled selected float32 values; None when empty."""
@@ -131,14 +140,11 @@ def global_normalization_vectors(ctx, bit_volume_lists, low_percentile_cut=10.0,
         vols = [v for v in vols if v.numel() > 0]
         if not vols:
             continue
-        cuts = [float(_f32_at_or_above(float(stats.percentile(v, low_percentile_cut)))) for v in vols]
+        cuts = [float(stats.percentile(v, low_percentile_cut)) for v in vols]  # float32 cut-offs, like NumPy
         m = stats.median(vols, pred=PRED_LT, cutoffs=cuts)
         bkg[b] = 0 if m is None else m
         sub = float(bkg[b])
-        cuts = [
-            float(_f32_at_or_below(float(stats.percentile(v, high_percentile_cut, sub=sub, clip0=True))))
-            for v in vols
-        ]
+        cuts = [float(stats.percentile(v, high_percentile_cut, sub=sub, clip0=True)) for v in vols]
         m = stats.median(vols, sub=sub, clip0=True, pred=PRED_GT, cutoffs=cuts)
         nrm[b] = 1 if m is None else m
     return nrm, bkg
