@@ -275,6 +275,54 @@ def run_b200(args):
     }
     gpu_launches = int(sum(klaunch.values()))
 
+    # ---- secondary measurements (not the headline): reference-default low-pass on, and the
+    # all-foreground worst case where every voxel passes the magnitude gate
+    extras = {}
+    if not args.no_extras and world == 1:
+        ctx.reset_counters()
+        ctx.set_timing(True)
+        lp = None
+        for i in range(3):
+            if i == 1:
+                torch.cuda.synchronize()
+                ctx.reset_counters()
+                t0 = time.perf_counter()
+            lp = ctx.lowpass(stack, (3.0, 1.0, 1.0), False, out=lp)
+            nl = ctx.decode_label(lp, decoded, False, MIN_PX, 500)
+            ctx.features(lp, decoded, False, nl)
+        torch.cuda.synchronize()
+        lp_ms = (time.perf_counter() - t0) * 1e3 / 2
+        kt = ctx.kernel_times_ms()
+        extras["lowpass_on"] = {
+            "ms_per_step": lp_ms, "gvoxel_per_s": n_vox / lp_ms / 1e6, "features": int(nl),
+            "note": "m3d_lowpass sigma=(3,1,1) (SciPy-exact fp64 accumulation) + decode_label + features on float32",
+            "kernel_ms_per_step": {k: v / 2 for k, v in sorted(kt.items(), key=lambda kv: -kv[1])[:6]},
+        }
+        del lp
+        torch.cuda.empty_cache()
+        # worst case: thresholds that let every voxel through the magnitude gate
+        ctx.set_thresholds(dec._pixel_assignment_threshold, 1.0e-3, 10.0)
+        ctx.set_normalization(np.full(16, 0.0, dtype=np.float32), np.full(16, 250.0, dtype=np.float32))
+        ctx.reset_counters()
+        for i in range(3):
+            if i == 1:
+                torch.cuda.synchronize()
+                ctx.reset_counters()
+                t0 = time.perf_counter()
+            ctx.decode(stack, decoded)
+        torch.cuda.synchronize()
+        wc_ms = (time.perf_counter() - t0) * 1e3 / 2
+        kt = ctx.kernel_times_ms()
+        extras["all_foreground"] = {
+            "ms_per_decode": wc_ms, "gvoxel_per_s": n_vox / wc_ms / 1e6,
+            "decoded_fraction": float((decoded >= 0).float().mean().item()),
+            "note": "every voxel is a candidate (magnitude gate open): exact search at all voxels, m3d_decode only",
+            "kernel_ms_per_step": {k: v / 2 for k, v in sorted(kt.items(), key=lambda kv: -kv[1])[:3]},
+        }
+        ctx.set_timing(False)
+        ctx.set_normalization(bkg, nrm)
+        ctx.set_thresholds(dec._pixel_assignment_threshold, MAG[0], MAG[1])
+
     # ---- e2e: the reference-facing call, stack in pinned host memory
     e2e = None
     if not args.no_e2e:
@@ -331,6 +379,7 @@ def run_b200(args):
                 "foreground_voxels": n_fg, "features": int(n_feat),
             },
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
+            "extras": extras,
             "clocks": clocks.summary(),
         }
         print(json.dumps(line))
@@ -354,6 +403,7 @@ def main():
     ap.add_argument("--shape", type=int, nargs=3, default=None, help="z y x override (debug only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -848,7 +848,7 @@ class PixelDecoder:
         rank, world, dist = self._dist()
         if dist is not None and world > 1:
             mine = self._contiguous_chunks(list(tiles), world)[rank]
-            gpu = torch.cuda.current_device()
+            gpu = self._local_gpu()
             for t in mine:
                 per_tile(self, t, gpu)
             return
@@ -1005,7 +1005,9 @@ class PixelDecoder:
         import torch
 
         _r, world, dist = self._dist()
-        return torch.cuda.current_device() if (dist is not None and world > 1) else 0
+        if dist is not None and world > 1 and torch.cuda.is_available():
+            return torch.cuda.current_device()
+        return 0
 
     def _remove_duplicates_within_tile(self, radius_xy: float, radius_z: float) -> None:
         """PD:4179-4363 (2-D mode only): collapse same-gene detections split across adjacent z

@@ -1,0 +1,129 @@
+"""world_size-2 gloo tests (CPU) of the multi-rank host logic: contiguous tile sharding, the
+all-gather of variable-length transcript tables and the rank-0 -> JSON -> other-ranks hand-off
+of the normalisation vectors.  The device work is replaced by a deterministic fake so that no
+GPU is needed; the kernels themselves are covered by the `gpu` tests."""
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _fake_table(decoder, tile_idx, vectors):
+    """Deterministic transcript table that depends on the tile and on the vectors in use."""
+    rng = np.random.default_rng(1000 + tile_idx)
+    n = 40 + 7 * tile_idx
+    words = rng.integers(0, len(decoder._gene_ids), n)
+    on = np.argsort(~decoder._codebook_matrix.astype(bool), axis=1)[:, :4] + 1
+    scale = float(np.mean(vectors)) if vectors is not None else 1.0
+    data = {f"bit{i:02d}_mean_intensity": (rng.gamma(2.0, 100.0, n) + scale).astype(np.float32) for i in range(1, 17)}
+    df = pd.DataFrame(data)
+    df["gene_id"] = [decoder._gene_ids[w] for w in words]
+    df["tile_idx"] = tile_idx
+    for k in range(4):
+        df[f"on_bit_{k + 1}"] = on[words, k]
+    df["distance_min"] = 0.1
+    return df
+
+
+def _patch(decoder, log):
+    import types
+
+    def fake_global(self, **kw):
+        nv = np.linspace(500, 800, 16, dtype=np.float32)
+        bv = np.linspace(90, 120, 16, dtype=np.float32)
+        self._datastore.save_decode_normalization_vectors(None, "global", nv, bv, decode_mode="3d")
+        self._global_normalization_vector, self._global_background_vector = nv, bv
+        self._global_normalization_loaded = True
+
+    def fake_decode(self, tile_idx=0, gpu_id=0, normalization_method=None, **kw):
+        self._prepare_normalization_state(normalization_method, True, gpu_id, kw.get("lowpass_sigma"))
+        self._tile_idx = tile_idx
+        _b, nrm = self._active_vectors()
+        self._df_barcodes = _fake_table(self, tile_idx, nrm)
+        log.append((tile_idx, normalization_method))
+
+    decoder._global_normalization_vectors = types.MethodType(fake_global, decoder)
+    decoder.decode_one_tile = types.MethodType(fake_decode, decoder)
+
+
+def _make_store(path, n_tiles):
+    import cases
+    from merfish3d_analysis_b200.datastore import ArrayDataStore
+
+    df_cb, _cb = cases.codebook16()
+    ds = ArrayDataStore(path, codebook=df_cb)
+    for _ in range(n_tiles):
+        ds.add_tile(np.zeros((16, 2, 4, 4), dtype=np.uint16))
+    return ds
+
+
+def _worker(rank, world, port, root, n_tiles, out_q):
+    import torch.distributed as dist
+
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    from merfish3d_analysis_b200.datastore import ArrayDataStore
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        ds = ArrayDataStore(root)
+        dec = PixelDecoder(ds, merfish_bits=16, num_gpus=world, verbose=0)
+        log = []
+        _patch(dec, log)
+        dec.optimize_normalization_by_decoding(n_iterations=3, tile_indices=list(range(n_tiles)))
+        nv, bv = ds.load_decode_normalization_vectors(None, "iterative")
+        out_q.put((rank, log, nv.tolist(), bv.tolist(), dec._iterative_normalization_vector.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_optimiser_matches_single_process(tmp_path):
+    import torch.multiprocessing as mp
+
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    n_tiles = 5
+    # single-process reference
+    ds1 = _make_store(tmp_path / "single", n_tiles)
+    dec1 = PixelDecoder(ds1, merfish_bits=16, num_gpus=1, verbose=0)
+    log1 = []
+    _patch(dec1, log1)
+    dec1.optimize_normalization_by_decoding(n_iterations=3, tile_indices=list(range(n_tiles)))
+    nv1, bv1 = ds1.load_decode_normalization_vectors(None, "iterative")
+    assert [t for t, _ in log1[:n_tiles]] == list(range(n_tiles))
+    assert [m for _, m in log1] == ["global"] * n_tiles + ["iterative"] * (2 * n_tiles)
+
+    # two ranks over gloo
+    _make_store(tmp_path / "dist", n_tiles)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path / "dist"), n_tiles, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, log_a, nv_a, bv_a, mem_a), (r1, log_b, nv_b, bv_b, mem_b) = results
+    # contiguous chunks like PD:4811-4818: ceil(5/2) = 3 -> rank 0: tiles 0-2, rank 1: tiles 3-4
+    assert sorted({t for t, _ in log_a}) == [0, 1, 2] and sorted({t for t, _ in log_b}) == [3, 4]
+    # every rank ends with the same vectors, equal to the single-process result (median of the
+    # pooled table, not a sum all-reduce)
+    np.testing.assert_array_equal(np.float32(nv_a), nv1)
+    np.testing.assert_array_equal(np.float32(bv_a), bv1)
+    assert nv_a == nv_b and bv_a == bv_b and mem_a == mem_b == nv_a
