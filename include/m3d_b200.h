@@ -128,6 +128,11 @@ int m3d_select_hist(m3d_ctx* ctx, const float* data_dev, int64_t n, float sub, i
 int m3d_replace_above(m3d_ctx* ctx, float* data_dev, int64_t n, float threshold, float value,
                       void* stream);
 
+/* Capacity (entries) of the search -> regionprops record buffers; 0 = automatic
+ * (max(2^20, n_vox/16)).  When the foreground exceeds it the regionprops kernel recomputes the
+ * traces instead; results are identical.  Exposed so tests can force the overflow path. */
+int m3d_set_sparse_capacity(m3d_ctx* ctx, int64_t entries);
+
 /* number of kernels this context has launched since creation (bench.py gpu_launches). */
 int64_t m3d_launch_count(m3d_ctx* ctx);
 /* name of the i-th kernel family; NULL when i is out of range. */

@@ -68,6 +68,7 @@ SIGNATURES = {
     "m3d_replace_above": (
         C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p]
     ),
+    "m3d_set_sparse_capacity": (C.c_int, [C.c_void_p, C.c_int64]),
     "m3d_launch_count": (C.c_int64, [C.c_void_p]),
     "m3d_kernel_name": (C.c_char_p, [C.c_int]),
     "m3d_kernel_launches": (C.c_int64, [C.c_void_p, C.c_int]),
@@ -322,6 +323,9 @@ class DecodeContext:
                                         float(value), _stream(self.device)),
             "m3d_replace_above",
         )
+
+    def set_sparse_capacity(self, entries: int) -> None:
+        _check(self._lib.m3d_set_sparse_capacity(self._h, int(entries)), "m3d_set_sparse_capacity")
 
     # ------------------------------------------------------------------ accounting
     def launch_count(self) -> int:

@@ -36,12 +36,17 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; libm3d_b200.so cannot be built")
 
 
+def _extra_flags() -> list[str]:
+    """Experiment hook: extra nvcc flags (e.g. -DM3D_GATE_MINB=4) from $M3D_NVCC_EXTRA."""
+    return os.environ.get("M3D_NVCC_EXTRA", "").split()
+
+
 def _digest() -> str:
     h = hashlib.sha256()
     for p in sorted(CSRC.glob("*.cu*")) + [PKG_DIR.parent / "include" / "m3d_b200.h"]:
         h.update(p.name.encode())
         h.update(p.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + _extra_flags()).encode())
     return h.hexdigest()
 
 
@@ -55,7 +60,7 @@ def build(force: bool = False, verbose: bool = True) -> Path:
 
     def compile_one(src: str) -> Path:
         obj = BUILD_DIR / (Path(src).stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *_extra_flags(), "-c", str(CSRC / src), "-o", str(obj)]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{res.stdout}\n{res.stderr}")

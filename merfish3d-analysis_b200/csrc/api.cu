@@ -219,6 +219,8 @@ extern "C" int m3d_destroy(m3d_ctx* ctx) {
     cudaFree(ctx->d_hash_vals);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     ctx->s_cand.release();
+    ctx->s_rec_x.release();
+    ctx->s_rec_md.release();
     ctx->s_counters.release();
     ctx->s_lp_tmp.release();
     ctx->s_fg.release();
@@ -234,6 +236,7 @@ extern "C" int m3d_destroy(m3d_ctx* ctx) {
 
 extern "C" int m3d_set_normalization(m3d_ctx* ctx, const float* background_host, const float* normalization_host) {
     if (!ctx) return m3d_fail(M3D_ERR_ARG, "m3d_set_normalization: null ctx");
+    ctx->lab_rec_valid = 0;
     if (!background_host || !normalization_host) {
         ctx->use_norm = 0;
         return M3D_OK;
@@ -248,9 +251,17 @@ extern "C" int m3d_set_normalization(m3d_ctx* ctx, const float* background_host,
 
 extern "C" int m3d_set_thresholds(m3d_ctx* ctx, float pixel_threshold, float magnitude_lo, float magnitude_hi) {
     if (!ctx) return m3d_fail(M3D_ERR_ARG, "m3d_set_thresholds: null ctx");
+    ctx->lab_rec_valid = 0;
     ctx->pix_thr = pixel_threshold;
     ctx->mag_lo = magnitude_lo;
     ctx->mag_hi = magnitude_hi;
+    return M3D_OK;
+}
+
+extern "C" int m3d_set_sparse_capacity(m3d_ctx* ctx, int64_t entries) {
+    if (!ctx || entries < 0) return m3d_fail(M3D_ERR_ARG, "m3d_set_sparse_capacity: bad argument");
+    ctx->sparse_cap_override = (size_t)entries;
+    ctx->lab_rec_valid = 0;
     return M3D_OK;
 }
 

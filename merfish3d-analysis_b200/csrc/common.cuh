@@ -138,6 +138,8 @@ struct m3d_ctx {
     float pix_thr = 0.f, mag_lo = 0.f, mag_hi = 0.f;
     // scratch
     Scratch s_cand;      // decode candidates
+    Scratch s_rec_x;     // float16 scaled values of foreground voxels (search -> features hand-off)
+    Scratch s_rec_md;    // float16 magnitude | distance of foreground voxels
     Scratch s_counters;  // small device counters
     Scratch s_lp_tmp;    // low-pass intermediate volume
     Scratch s_fg;        // CCL foreground list
@@ -153,6 +155,8 @@ struct m3d_ctx {
     int64_t lab_n_fg = 0;
     int64_t lab_n_features = -1;
     int lab_max_px = 0;
+    int lab_rec_valid = 0;
+    size_t sparse_cap_override = 0;  // m3d_set_sparse_capacity (tests); 0 = automatic  // records of the last m3d_decode_label cover every foreground voxel
     // accounting
     int64_t launches[KF_COUNT];
     // optional per-kernel-family device timing (m3d_set_timing): event pairs recorded on the
@@ -193,5 +197,15 @@ struct KernelScope {
         KernelScope ks__((ctx), (kf), (st));    \
         __VA_ARGS__;                            \
     } while (0)
+
+// capacity (entries) of the sparse hand-off buffers: ample for real data (a few % foreground),
+// bounded so that degenerate all-foreground inputs cannot exhaust HBM -- overflow entries take the
+// recompute paths
+static inline size_t m3d_sparse_capacity(const m3d_ctx* ctx, size_t n_vox) {
+    if (ctx->sparse_cap_override) return ctx->sparse_cap_override;
+    size_t c = n_vox / 16;
+    if (c < ((size_t)1 << 20)) c = (size_t)1 << 20;
+    return c < n_vox ? c : n_vox;
+}
 
 static inline int ceil_div_i64(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -203,20 +203,32 @@ __device__ __forceinline__ SearchSmem stage_codebook(unsigned char* smem, const 
 }
 
 // ------------------------------------------------------------------ exact per-voxel trace
+// raw values of one voxel: every bit-plane load is issued before the (branchy) IEEE divisions
 template <typename T, int NB>
-__device__ __forceinline__ void exact_trace(const T* __restrict__ stack, size_t n_vox, size_t v,
-                                            const DecodeParams& P, float (&x)[NB], float (&xh)[NB], float& mag) {
-    // issue every bit-plane load before the (branchy) IEEE divisions consume them
-    float s[NB];
+__device__ __forceinline__ void load_stack_trace(const T* __restrict__ stack, size_t n_vox, size_t v,
+                                                 const DecodeParams& P, float (&s)[NB]) {
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const int pb = (b < P.n_bits) ? b : (P.n_bits - 1);
         s[b] = load_elem(stack, (size_t)pb * n_vox + v);
     }
+}
+
+template <int NB>
+__device__ __forceinline__ void finish_trace(const float (&s)[NB], const DecodeParams& P, float (&x)[NB],
+                                             float (&xh)[NB], float& mag) {
 #pragma unroll
     for (int b = 0; b < NB; ++b) x[b] = (b < P.n_bits) ? scale_clip(s[b], P.bkg[b], P.nrm[b]) : 0.f;
     const float n = l2_norm<NB>(x);
     mag = unit_vector<NB>(x, n, xh);
+}
+
+template <typename T, int NB>
+__device__ __forceinline__ void exact_trace(const T* __restrict__ stack, size_t n_vox, size_t v,
+                                            const DecodeParams& P, float (&x)[NB], float (&xh)[NB], float& mag) {
+    float s[NB];
+    load_stack_trace<T, NB>(stack, n_vox, v, P, s);
+    finish_trace<NB>(s, P, x, xh, mag);
 }
 
 // ------------------------------------------------------------------ lane-parallel scans (modes 0, 1, 2)
@@ -382,11 +394,14 @@ __device__ __forceinline__ void nearest_codeword_warp(bool want, const float (&x
 }
 
 // ------------------------------------------------------------------ candidate search kernel
-struct FgSink {  // optional hand-off to the labelling stage (m3d_decode_label)
+struct FgSink {  // optional hand-off to the labelling / regionprops stages (m3d_decode_label)
     uint32_t* fg;
     unsigned int* fg_count;
     uint32_t* parent;
     uint32_t* aux;
+    __half* rec_x;      // [rec_cap][NB] float16 scaled image values (round(.,5)) of foreground voxels
+    uint32_t* rec_md;   // [rec_cap]     float16 magnitude | float16 distance << 16
+    unsigned rec_cap;
 };
 
 template <typename T, int NB>
@@ -432,7 +447,23 @@ decode_search_kernel(const T* __restrict__ stack, size_t n_vox, DecodeParams P, 
                 const int leader = __ffs(m) - 1;
                 if ((int)lane == leader) base = atomicAdd(sink.fg_count, (unsigned)__popc(m));
                 base = __shfl_sync(0xffffffffu, base, leader);
-                if (fg) sink.fg[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)v;
+                if (fg) {
+                    const unsigned idx = base + __popc(m & ((1u << lane) - 1u));
+                    sink.fg[idx] = (uint32_t)v;
+                    if (idx < sink.rec_cap) {  // per-voxel values the regionprops stage would recompute
+                        sink.rec_md[idx] = (uint32_t)__half_as_ushort(round5_f16(mag)) |
+                                           ((uint32_t)__half_as_ushort(round5_f16(d)) << 16);
+                        uint32_t hw[NB / 2];
+#pragma unroll
+                        for (int b = 0; b < NB; b += 2)
+                            hw[b / 2] = (uint32_t)__half_as_ushort(round5_f16(x[b])) |
+                                        ((uint32_t)__half_as_ushort(round5_f16(x[b + 1])) << 16);
+                        uint4* dst = reinterpret_cast<uint4*>(sink.rec_x + (size_t)idx * NB);
+#pragma unroll
+                        for (int q = 0; q < NB / 8; ++q)
+                            dst[q] = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+                    }
+                }
             }
         }
     }
@@ -583,8 +614,9 @@ int m3d_check_decode_args(m3d_ctx* ctx, const void* stack_dev, int dtype, const 
 }
 
 int m3d_decode_internal(m3d_ctx* ctx, const void* stack_dev, int dtype, size_t n_vox, int16_t* decoded_dev,
-                        uint32_t* fg, unsigned int* fg_count, uint32_t* parent, uint32_t* aux, cudaStream_t st) {
-    const FgSink sink{fg, fg_count, parent, aux};
+                        uint32_t* fg, unsigned int* fg_count, uint32_t* parent, uint32_t* aux, void* rec_x,
+                        uint32_t* rec_md, unsigned rec_cap, cudaStream_t st) {
+    const FgSink sink{fg, fg_count, parent, aux, reinterpret_cast<__half*>(rec_x), rec_md, rec_cap};
     if (dtype == M3D_DTYPE_U16)
         return dispatch_nb<uint16_t>(ctx, reinterpret_cast<const uint16_t*>(stack_dev), n_vox, decoded_dev, nullptr,
                                      nullptr, nullptr, sink, st);
@@ -603,7 +635,7 @@ extern "C" int m3d_decode(m3d_ctx* ctx, const void* stack_dev, int dtype, const 
     __half* mag = reinterpret_cast<__half*>(magnitude_f16_dev);
     __half* dist = reinterpret_cast<__half*>(distance_f16_dev);
     __half* scaled = reinterpret_cast<__half*>(scaled_f16_dev);
-    const FgSink none{nullptr, nullptr, nullptr, nullptr};
+    const FgSink none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0u};
     if (dtype == M3D_DTYPE_U16)
         return dispatch_nb<uint16_t>(ctx, reinterpret_cast<const uint16_t*>(stack_dev), n_vox, decoded_dev, mag, dist,
                                      scaled, none, st);

@@ -219,7 +219,7 @@ ccl_scatter_kernel(const uint32_t* __restrict__ fg, const unsigned int* __restri
         if (id != DROPPED) {
             const uint32_t v = fg[i];
             const uint32_t slot = atomicAdd(cursor + id, 1u);
-            vox[offs[id] + slot] = v;
+            vox[offs[id] + slot] = i;  // position in the foreground list (also indexes the records)
             if (labels) labels[v] = (int32_t)(id + 1u);
         }
     }
@@ -256,55 +256,69 @@ constexpr int FEAT_WARPS = 4;
 constexpr int FEAT_TILE_STRIDE = M3D_MAX_BITS + 1;
 
 static size_t features_smem_bytes(int cap_px) {
-    // per warp: sorted voxel list + magnitude list (cap_px each) + one 32-voxel value tile
-    return (size_t)FEAT_WARPS * ((size_t)cap_px * 8 + 32 * FEAT_TILE_STRIDE * 4);
+    // per warp: sorted (voxel, fg index) keys + magnitude list + one 32-voxel value tile
+    return (size_t)FEAT_WARPS * ((size_t)cap_px * 12 + 32 * FEAT_TILE_STRIDE * 4);
 }
 
-// One warp per component.  Phase A (lane = voxel): every lane recomputes one voxel's exact trace
-// with the decode kernels' device functions -- float16-rounded scaled values, magnitude and the
-// distance to the component's codeword -- and stages the per-bit values in a shared tile.
-// Phase B (lane = bit): each lane adds its bit's 32 staged values SEQUENTIALLY in raster order,
-// which is the order NumPy's axis-0 reduction uses inside scikit-image's intensity_mean.
-// Integer coordinate sums and the distance minimum are order independent and warp-reduced.
-template <typename T, int NB>
+struct FeatRecords {
+    const __half* rec_x;     // [n_fg][NB]
+    const uint32_t* rec_md;  // [n_fg]
+};
+
+// One warp per component.  Phase A (lane = voxel): every lane produces one voxel's float16-rounded
+// scaled values, magnitude and distance to the component's codeword -- read from the records the
+// search kernel wrote (FROM_REC) or recomputed with the decode kernels' device functions -- and
+// stages the per-bit values in a shared tile.  Phase B (lane = bit): each lane adds its bit's 32
+// staged values SEQUENTIALLY in raster order, the order NumPy's axis-0 reduction uses inside
+// scikit-image's intensity_mean.  Integer coordinate sums and the distance minimum are order
+// independent and warp-reduced.
+template <typename T, int NB, bool FROM_REC>
 __global__ void __launch_bounds__(FEAT_WARPS * 32)
 features_kernel(const T* __restrict__ stack, size_t n_vox, int Y, int X, DecodeParams P,
-                const int16_t* __restrict__ decoded, const uint32_t* __restrict__ vox,
-                const uint32_t* __restrict__ offs, const uint32_t* __restrict__ area_by_id, unsigned n_feat,
-                int optimize_mode, int cap_px, double* __restrict__ table, int n_cols) {
+                const int16_t* __restrict__ decoded, const uint32_t* __restrict__ fg,
+                const uint32_t* __restrict__ vox, const uint32_t* __restrict__ offs,
+                const uint32_t* __restrict__ area_by_id, unsigned n_feat, int optimize_mode, int cap_px,
+                FeatRecords R, double* __restrict__ table, int n_cols) {
     extern __shared__ __align__(16) unsigned char fsm[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    unsigned char* base = fsm + (size_t)warp * ((size_t)cap_px * 8 + 32 * FEAT_TILE_STRIDE * 4);
-    uint32_t* sv = reinterpret_cast<uint32_t*>(base);
-    float* sm = reinterpret_cast<float*>(base + (size_t)cap_px * 4);
-    float* tile = reinterpret_cast<float*>(base + (size_t)cap_px * 8);
+    unsigned char* base = fsm + (size_t)warp * ((size_t)cap_px * 12 + 32 * FEAT_TILE_STRIDE * 4);
+    unsigned long long* sk = reinterpret_cast<unsigned long long*>(base);
+    float* sm = reinterpret_cast<float*>(base + (size_t)cap_px * 8);
+    float* tile = reinterpret_cast<float*>(base + (size_t)cap_px * 12);
     const uint32_t plane = (uint32_t)Y * (uint32_t)X;
     for (unsigned id = blockIdx.x * FEAT_WARPS + warp; id < n_feat; id += gridDim.x * FEAT_WARPS) {
         const int n = (int)area_by_id[id];
         const uint32_t* seg = vox + offs[id];
         int Pn = 32;
         while (Pn < n) Pn <<= 1;
-        for (int i = lane; i < Pn; i += 32) sv[i] = (i < n) ? seg[i] : 0xFFFFFFFFu;
+        for (int i = lane; i < Pn; i += 32) {
+            unsigned long long key = ~0ull;
+            if (i < n) {
+                const uint32_t fi = seg[i];
+                key = ((unsigned long long)fg[fi] << 32) | fi;
+            }
+            sk[i] = key;
+        }
         __syncwarp();
-        // bitonic sort, ascending (raster order)
+        // bitonic sort, ascending voxel index (raster order)
         for (int k = 2; k <= Pn; k <<= 1) {
             for (int j = k >> 1; j > 0; j >>= 1) {
                 for (int i = lane; i < Pn; i += 32) {
                     const int ixj = i ^ j;
                     if (ixj > i) {
-                        const uint32_t a = sv[i], b = sv[ixj];
+                        const unsigned long long a = sk[i], b = sk[ixj];
                         const bool up = ((i & k) == 0);
                         if ((a > b) == up) {
-                            sv[i] = b;
-                            sv[ixj] = a;
+                            sk[i] = b;
+                            sk[ixj] = a;
                         }
                     }
                 }
                 __syncwarp();
             }
         }
-        const uint32_t v_first = sv[0];
+        const uint32_t v_first = (uint32_t)(sk[0] >> 32);
         const int z0 = (int)(v_first / plane);
         const uint32_t rem0 = v_first - (uint32_t)z0 * plane;
         const int y0 = (int)(rem0 / (uint32_t)X);
@@ -317,25 +331,56 @@ features_kernel(const T* __restrict__ stack, size_t n_vox, int Y, int X, DecodeP
         for (int c0 = 0; c0 < n; c0 += 32) {
             const int j = c0 + lane;
             if (j < n) {
-                const uint32_t v = sv[j];
-                float x[NB], xh[NB], raw[NB];
-                // issue every bit-plane load before the (branchy) IEEE divisions consume them
+                const unsigned long long key = sk[j];
+                const uint32_t v = (uint32_t)(key >> 32);
+                const uint32_t fi = (uint32_t)key;
+                float mag16, d16;
+                if (FROM_REC) {
+                    const uint32_t md = __ldg(R.rec_md + fi);
+                    mag16 = __half2float(__ushort_as_half((unsigned short)(md & 0xFFFFu)));
+                    d16 = __half2float(__ushort_as_half((unsigned short)(md >> 16)));
+                    if (optimize_mode) {
+                        float raw[NB];
 #pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    const int pb = (b < P.n_bits) ? b : (P.n_bits - 1);
-                    raw[b] = load_elem(stack, (size_t)pb * n_vox + v);
-                }
+                        for (int b = 0; b < NB; ++b) {
+                            const int pb = (b < P.n_bits) ? b : (P.n_bits - 1);
+                            raw[b] = load_elem(stack, (size_t)pb * n_vox + v);
+                        }
 #pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    x[b] = (b < P.n_bits) ? scale_clip(raw[b], P.bkg[b], P.nrm[b]) : 0.f;
-                    const float val = optimize_mode ? raw[b] : __half2float(round5_f16(x[b]));
-                    tile[lane * FEAT_TILE_STRIDE + b] = (b < P.n_bits) ? val : 0.f;
+                        for (int b = 0; b < NB; ++b) tile[lane * FEAT_TILE_STRIDE + b] = (b < P.n_bits) ? raw[b] : 0.f;
+                    } else {
+                        const uint4* src = reinterpret_cast<const uint4*>(R.rec_x + (size_t)fi * NB);
+#pragma unroll
+                        for (int q = 0; q < NB / 8; ++q) {
+                            const uint4 t = __ldg(src + q);
+                            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                tile[lane * FEAT_TILE_STRIDE + q * 8 + e] = __half2float(
+                                    __ushort_as_half((unsigned short)((w[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu)));
+                        }
+                    }
+                } else {
+                    float x[NB], xh[NB], raw[NB];
+                    // issue every bit-plane load before the (branchy) IEEE divisions consume them
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        const int pb = (b < P.n_bits) ? b : (P.n_bits - 1);
+                        raw[b] = load_elem(stack, (size_t)pb * n_vox + v);
+                    }
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        x[b] = (b < P.n_bits) ? scale_clip(raw[b], P.bkg[b], P.nrm[b]) : 0.f;
+                        const float val = optimize_mode ? raw[b] : __half2float(round5_f16(x[b]));
+                        tile[lane * FEAT_TILE_STRIDE + b] = (b < P.n_bits) ? val : 0.f;
+                    }
+                    const float nrm2 = l2_norm<NB>(x);
+                    const float mag = unit_vector<NB>(x, nrm2, xh);
+                    mag16 = __half2float(round5_f16(mag));
+                    d16 = __half2float(round5_f16(direct_distance<NB>(xh, crow)));
                 }
-                const float nrm2 = l2_norm<NB>(x);
-                const float mag = unit_vector<NB>(x, nrm2, xh);
-                const float d = direct_distance<NB>(xh, crow);
-                dist_min = fminf(dist_min, __half2float(round5_f16(d)));
-                sm[j] = __half2float(round5_f16(mag));
+                dist_min = fminf(dist_min, d16);
+                sm[j] = mag16;
                 const int z = (int)(v / plane);
                 const uint32_t rem = v - (uint32_t)z * plane;
                 const int y = (int)(rem / (uint32_t)X);
@@ -400,7 +445,7 @@ features_kernel(const T* __restrict__ stack, size_t n_vox, int Y, int X, DecodeP
     }
 }
 
-template <typename T, int NB>
+template <typename T, int NB, bool FROM_REC>
 int launch_features(m3d_ctx* ctx, const T* stack, size_t n_vox, int Y, int X, const int16_t* decoded,
                     int optimize_mode, double* table, cudaStream_t st) {
     const unsigned n_feat = (unsigned)ctx->lab_n_features;
@@ -408,30 +453,43 @@ int launch_features(m3d_ctx* ctx, const T* stack, size_t n_vox, int Y, int X, co
     const uint32_t* area_by_id = reinterpret_cast<const uint32_t*>(ctx->s_area.ptr);
     const uint32_t* offs = area_by_id + n_feat;
     const uint32_t* vox = reinterpret_cast<const uint32_t*>(ctx->s_vox.ptr);
+    const uint32_t* fg = reinterpret_cast<const uint32_t*>(ctx->s_fg.ptr);
+    const FeatRecords R{reinterpret_cast<const __half*>(ctx->s_rec_x.ptr),
+                        reinterpret_cast<const uint32_t*>(ctx->s_rec_md.ptr)};
     const int n_cols = M3D_TABLE_FIXED_COLS + ctx->n_bits;
     int cap_px = 32;
     while (cap_px < ctx->lab_max_px) cap_px <<= 1;
     const size_t smem = features_smem_bytes(cap_px);
-    auto kern = features_kernel<T, NB>;
+    auto kern = features_kernel<T, NB, FROM_REC>;
     M3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = (int)((n_feat + FEAT_WARPS - 1) / FEAT_WARPS);
     const int cap = ctx->num_sms * 16;
     if (blocks > cap) blocks = cap;
     M3D_LAUNCH(ctx, KF_FEATURES, st,
-               kern<<<blocks, FEAT_WARPS * 32, smem, st>>>(stack, n_vox, Y, X, P, decoded, vox, offs, area_by_id, n_feat,
-                                                           optimize_mode, cap_px, table, n_cols));
+               kern<<<blocks, FEAT_WARPS * 32, smem, st>>>(stack, n_vox, Y, X, P, decoded, fg, vox, offs, area_by_id,
+                                                           n_feat, optimize_mode, cap_px, R, table, n_cols));
     M3D_CHECK_LAUNCH();
     return M3D_OK;
+}
+
+template <typename T, int NB>
+int launch_features_any(m3d_ctx* ctx, const T* stack, size_t n_vox, int Y, int X, const int16_t* decoded,
+                        int optimize_mode, double* table, cudaStream_t st) {
+    // records are only valid for the stack / vectors / thresholds of the m3d_decode_label call
+    // that wrote them; m3d_label and parameter changes clear the flag
+    if (ctx->lab_rec_valid)
+        return launch_features<T, NB, true>(ctx, stack, n_vox, Y, X, decoded, optimize_mode, table, st);
+    return launch_features<T, NB, false>(ctx, stack, n_vox, Y, X, decoded, optimize_mode, table, st);
 }
 
 template <typename T>
 int dispatch_features(m3d_ctx* ctx, const T* stack, size_t n_vox, int Y, int X, const int16_t* decoded,
                       int optimize_mode, double* table, cudaStream_t st) {
     switch (ctx->nb_pad) {
-        case 8: return launch_features<T, 8>(ctx, stack, n_vox, Y, X, decoded, optimize_mode, table, st);
-        case 16: return launch_features<T, 16>(ctx, stack, n_vox, Y, X, decoded, optimize_mode, table, st);
-        case 24: return launch_features<T, 24>(ctx, stack, n_vox, Y, X, decoded, optimize_mode, table, st);
-        case 32: return launch_features<T, 32>(ctx, stack, n_vox, Y, X, decoded, optimize_mode, table, st);
+        case 8: return launch_features_any<T, 8>(ctx, stack, n_vox, Y, X, decoded, optimize_mode, table, st);
+        case 16: return launch_features_any<T, 16>(ctx, stack, n_vox, Y, X, decoded, optimize_mode, table, st);
+        case 24: return launch_features_any<T, 24>(ctx, stack, n_vox, Y, X, decoded, optimize_mode, table, st);
+        case 32: return launch_features_any<T, 32>(ctx, stack, n_vox, Y, X, decoded, optimize_mode, table, st);
     }
     return m3d_fail(M3D_ERR_ARG, "unsupported padded bit count %d", ctx->nb_pad);
 }
@@ -443,7 +501,8 @@ int dispatch_features(m3d_ctx* ctx, const T* stack, size_t n_vox, int Y, int X, 
 int m3d_check_decode_args(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t dims[3],
                           int16_t* decoded_dev, size_t* n_vox);
 int m3d_decode_internal(m3d_ctx* ctx, const void* stack_dev, int dtype, size_t n_vox, int16_t* decoded_dev,
-                        uint32_t* fg, unsigned int* fg_count, uint32_t* parent, uint32_t* aux, cudaStream_t st);
+                        uint32_t* fg, unsigned int* fg_count, uint32_t* parent, uint32_t* aux, void* rec_x,
+                        uint32_t* rec_md, unsigned rec_cap, cudaStream_t st);
 
 namespace {
 
@@ -460,6 +519,7 @@ int label_prepare(m3d_ctx* ctx, const int64_t dims[3], int maximum_pixels, int32
     if (maximum_pixels < 1 || maximum_pixels > FEAT_MAX_PX)
         return m3d_fail(M3D_ERR_ARG, "m3d_label: maximum_pixels must be in [1, %d]", FEAT_MAX_PX);
     ctx->lab_n_features = -1;
+    ctx->lab_rec_valid = 0;
     if (ctx->s_counters.ensure(256)) return M3D_ERR_CUDA;
     if (ctx->s_fg.ensure(2 * n_vox * sizeof(uint32_t))) return M3D_ERR_CUDA;  // fg list + root_of
     if (ctx->s_parent.ensure(n_vox * sizeof(uint32_t))) return M3D_ERR_CUDA;
@@ -589,10 +649,18 @@ extern "C" int m3d_decode_label(m3d_ctx* ctx, const void* stack_dev, int dtype, 
     if (rc) return rc;
     // the search kernel emits the foreground list and initialises the union-find slots: no
     // second pass over the decoded image
-    rc = m3d_decode_internal(ctx, stack_dev, dtype, n_vox, decoded_dev, L.fg, L.counters + CNT_FG, L.parent, L.aux, st);
+    const size_t rec_cap = m3d_sparse_capacity(ctx, n_vox);
+    if (ctx->s_rec_x.ensure(rec_cap * (size_t)ctx->nb_pad * 2)) return M3D_ERR_CUDA;
+    if (ctx->s_rec_md.ensure(rec_cap * sizeof(uint32_t))) return M3D_ERR_CUDA;
+    rc = m3d_decode_internal(ctx, stack_dev, dtype, n_vox, decoded_dev, L.fg, L.counters + CNT_FG, L.parent, L.aux,
+                             ctx->s_rec_x.ptr, reinterpret_cast<uint32_t*>(ctx->s_rec_md.ptr), (unsigned)rec_cap, st);
     if (rc) return rc;
-    return label_finish(ctx, decoded_dev, dims, n_vox, mode2d, minimum_pixels, maximum_pixels, labels_dev,
-                        n_features_out, L, st);
+    rc = label_finish(ctx, decoded_dev, dims, n_vox, mode2d, minimum_pixels, maximum_pixels, labels_dev,
+                      n_features_out, L, st);
+    if (rc) return rc;
+    // the regionprops stage may read the search kernel's records instead of recomputing traces
+    ctx->lab_rec_valid = ((size_t)ctx->lab_n_fg <= rec_cap) ? 1 : 0;
+    return M3D_OK;
 }
 
 extern "C" int m3d_features(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t dims[3],

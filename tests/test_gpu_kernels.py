@@ -241,18 +241,23 @@ def test_label_matches_oracle(torch, mode2d, fill):
 
 
 @pytest.mark.parametrize("mode2d", [False, True])
-def test_fused_decode_label_equals_separate_calls(torch, mode2d):
+@pytest.mark.parametrize("optimize", [False, True])
+@pytest.mark.parametrize("capacity", [0, 37])
+def test_fused_decode_label_equals_separate_calls(torch, mode2d, optimize, capacity):
+    """fused path (gate->search raw hand-off, search->regionprops records) == separate calls;
+    capacity=37 forces both hand-off buffers to overflow into the recompute paths."""
     _df, cb = cases.codebook16()
     stack = cases.small_stack(cb["matrix"], shape=(9, 40, 56), seed=67)
     bkg, nrm = cases.simple_vectors(16)
     ctx, d_stack, dec, got, ref = _decode_both(torch, cb, stack, bkg, nrm, dense=False)
     lab_a = torch.zeros(dec.shape, dtype=torch.int32, device="cuda")
     n_a = ctx.label(dec, mode2d, 4.0, 500, labels=lab_a)
-    tab_a = ctx.features(d_stack, dec, False).cpu().numpy()
+    tab_a = ctx.features(d_stack, dec, optimize).cpu().numpy()
+    ctx.set_sparse_capacity(capacity)
     dec_b = torch.empty_like(dec)
     lab_b = torch.zeros(dec.shape, dtype=torch.int32, device="cuda")
     n_b = ctx.decode_label(d_stack, dec_b, mode2d, 4.0, 500, labels=lab_b)
-    tab_b = ctx.features(d_stack, dec_b, False).cpu().numpy()
+    tab_b = ctx.features(d_stack, dec_b, optimize).cpu().numpy()
     assert n_a == n_b and n_a > 10
     np.testing.assert_array_equal(dec_b.cpu().numpy(), ref["decoded"])
     np.testing.assert_array_equal(lab_a.cpu().numpy(), lab_b.cpu().numpy())
