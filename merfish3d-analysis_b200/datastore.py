@@ -257,7 +257,7 @@ class ArrayDataStore:
             if not p.exists():
                 print("Readout image not found.")
                 return None
-            arr = np.load(p, mmap_mode="r")
+            arr = np.load(p, mmap_mode="c")  # copy-on-write: read-only on disk, writable view for torch
         return _Ready(arr) if return_future else arr
 
     def load_local_feature_predictor_image(self, tile, bit, return_future: bool = True):
@@ -269,7 +269,7 @@ class ArrayDataStore:
             arr = self._mem_predictor.get((tile_id, bit_id))
         else:
             p = self._readouts_root_path / tile_id / bit_id / "feature_predictor_data.npy"
-            arr = np.load(p, mmap_mode="r") if p.exists() else None
+            arr = np.load(p, mmap_mode="c") if p.exists() else None
         if arr is None:
             arr = UnitPredictor(self.load_local_readout_image(tile, bit, False).shape)
         return _Ready(arr) if return_future else arr

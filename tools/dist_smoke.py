@@ -1,0 +1,71 @@
+"""Multi-rank smoke (run under torchrun, NCCL): tile-sharded optimiser loop + decode_all_tiles,
+checked against the CPU oracle on rank 0.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tools/dist_smoke.py
+"""
+import os
+import shutil
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import cases  # noqa: E402
+from merfish3d_analysis_b200.datastore import ArrayDataStore  # noqa: E402
+from merfish3d_analysis_b200.PixelDecoder import PixelDecoder  # noqa: E402
+from oracle import decode_oracle as orc  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    root = Path("/tmp/m3d_dist_smoke/qi2labdatastore")
+    df_cb, cb = cases.codebook16()
+    n_tiles = 5
+    stacks = [cases.small_stack(cb["matrix"], shape=(10, 48, 64), seed=71 + i, density=4e-3) for i in range(n_tiles)]
+    if rank == 0:
+        shutil.rmtree(root.parent, ignore_errors=True)
+        ds = ArrayDataStore(root, codebook=df_cb)
+        for st in stacks:
+            ds.add_tile(st, persist=True)
+    dist.barrier()
+    ds = ArrayDataStore(root)
+    dec = PixelDecoder(ds, merfish_bits=16, num_gpus=world, verbose=0)
+    sigma = (1.0, 0.5, 0.5)
+    dec.optimize_normalization_by_decoding(n_iterations=3, minimum_pixels=4, lowpass_sigma=sigma,
+                                           magnitude_threshold=(0.9, 10.0), tile_indices=list(range(n_tiles)))
+    dec.decode_all_tiles(lowpass_sigma=sigma, minimum_pixels=4, magnitude_threshold=(0.9, 10.0))
+    n_local = len(dec._df_barcodes_loaded)
+    counts = [None] * world
+    dist.all_gather_object(counts, n_local)
+    if rank == 0:
+        ref = orc.optimize_normalization([(s, None) for s in stacks], cb, 3, True, sigma, (0.9, 10.0), 4)
+        i_n, i_b = ds.load_decode_normalization_vectors(None, "iterative")
+        np.testing.assert_array_equal(i_n, ref["iterative"][0])
+        np.testing.assert_array_equal(i_b, ref["iterative"][1])
+        total = 0
+        for t, st in enumerate(stacks):
+            df, _ = orc.decode_tile(st, None, cb, i_b, i_n, True, sigma, (0.9, 10.0), 4, tile_idx=t,
+                                    spacing=ds.voxel_size_zyx_um)
+            got = ds.load_local_decoded_spots(t)
+            assert got["gene_id"].tolist() == df["gene_id"].tolist(), t
+            np.testing.assert_allclose(got["distance_min"].to_numpy(float), df["distance_min"].to_numpy(float), rtol=1e-5)
+            total += len(df)
+        assert all(c == total for c in counts), (counts, total)
+        print(f"dist_smoke ok: world={world} tiles={n_tiles} transcripts={total} vectors match the oracle")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
