@@ -91,7 +91,7 @@ int m3d_decode(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t dim
  * components (26-conn 3D / 8-conn per plane when mode2d), drop area > maximum_pixels and
  * area <= max(int(minimum_pixels)-1, 0).  Surviving components get canonical ids 0..n-1 in
  * raster order of their first voxel.  labels_dev (nullable, int32 (z,y,x)) receives id+1
- * (0 = background).  Synchronises the stream to return *n_features_out. */
+ * (0 = background or dropped for being too small, -1 = dropped for being too large).  Synchronises the stream to return *n_features_out. */
 int m3d_label(m3d_ctx* ctx, const int16_t* decoded_dev, const int64_t dims[3], int mode2d,
               double minimum_pixels, int maximum_pixels, int32_t* labels_dev,
               int64_t* n_features_out, void* stream);
@@ -102,6 +102,17 @@ int m3d_label(m3d_ctx* ctx, const int16_t* decoded_dev, const int64_t dims[3], i
 int m3d_decode_label(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t dims[3],
                      int16_t* decoded_dev, int mode2d, double minimum_pixels, int maximum_pixels,
                      int32_t* labels_dev, int64_t* n_features_out, void* stream);
+
+/* Z-slab sharding of one volume (no reference counterpart; contract: same result as the unsharded
+ * volume).  Given the LAST decoded / label plane of the lower slab and the FIRST plane of
+ * the upper slab (labels = ids + 1 from m3d_label / m3d_decode_label with a labels image; 0 =
+ * background or dropped-small, -1 = dropped because oversized), emits (label_hi, label_lo) pairs of
+ * components joined across the interface under the 26-neighbour equal-value rule.  pairs_dev =
+ * capacity x 2 int32; *n_pairs_out may exceed capacity (then only `capacity` pairs were stored).
+ * Synchronises the stream. */
+int m3d_interface_pairs(m3d_ctx* ctx, const int16_t* decoded_lo_dev, const int32_t* labels_lo_dev,
+                        const int16_t* decoded_hi_dev, const int32_t* labels_hi_dev, int64_t Y, int64_t X,
+                        int32_t* pairs_dev, int64_t capacity, int64_t* n_pairs_out, void* stream);
 
 /* _extract_barcodes regionprops (PD:2991-3062) for the components of the last m3d_label /
  * m3d_decode_label call, one row per component in canonical order.  table_dev = (n_rows, 14 + n_bits)

@@ -442,7 +442,8 @@ class PixelDecoder:
             p = torch.from_numpy(np.ascontiguousarray(predictor, dtype=np.float32)).to(ctx.device)
         return ctx.weight(r, p)
 
-    def _load_bit_data(self, feature_predictor_threshold: float | None = 0.1, gpu_id: int = 0) -> None:
+    def _load_bit_data(self, feature_predictor_threshold: float | None = 0.1, gpu_id: int = 0,
+                       z_bounds: tuple[int, int] | None = None) -> None:
         """PD:1828-1946: gather the tile's bit volumes into one device stack + coordinate metadata.
 
         Device state: ``readout`` (bits, z, y, x) uint16 (or float32 when the store holds float
@@ -460,11 +461,17 @@ class PixelDecoder:
             ra = fr.result() if hasattr(fr, "result") else fr
             _ex, em = self._datastore.load_local_wavelengths_um(tile=self._tile_idx, bit=bit_id)
             self._require_identity_warp(self._tile_idx, bit_id)
-            readouts.append(ra[self._z_slice, :, :])
-            predictors.append(None if self._is_unit_predictor(pa) else pa[self._z_slice, :, :])
+            ra = ra[self._z_slice, :, :]
+            pa = None if self._is_unit_predictor(pa) else pa[self._z_slice, :, :]
+            self._full_z = int(ra.shape[0])
+            if z_bounds is not None:  # z-slab sharding: this rank / pass holds planes [a, b) only
+                ra = ra[z_bounds[0] : z_bounds[1]]
+                pa = None if pa is None else pa[z_bounds[0] : z_bounds[1]]
+            readouts.append(ra)
+            predictors.append(pa)
             self._em_wvl.append(em)
         shape = tuple(readouts[0].shape)
-        if self._decode_mode == "3d" and shape[0] < 2:
+        if self._decode_mode == "3d" and self._full_z < 2:
             raise ValueError("decode_mode='3d' requires at least two z planes after applying z_range.")
         float_input = any(np.asarray(r).dtype.kind == "f" for r in readouts)
         dt = torch.float32 if float_input else torch.uint16
@@ -801,6 +808,180 @@ class PixelDecoder:
                 st["distance"].cpu().numpy(),
                 st["decoded"].cpu().numpy(),
             )
+        return None
+
+    # ------------------------------------------------------------------ z-slab sharding of one volume
+    def decode_one_tile_sharded(
+        self,
+        tile_idx: int = 0,
+        gpu_id: int | None = None,
+        n_slabs: int | None = None,
+        lowpass_sigma: Sequence[float] | None = DEFAULT_DECODE_LOWPASS_SIGMA,
+        magnitude_threshold: Sequence[float] | None = None,
+        minimum_pixels: float | None = None,
+        use_normalization: bool | None = True,
+        normalization_method: Literal["iterative", "global", "none"] | None = None,
+    ):
+        """Decode ONE tile split into z-slabs; result identical to ``decode_one_tile``.
+
+        Under ``torch.distributed`` (world > 1, ``n_slabs`` None) every rank holds one slab: the
+        boundary planes travel by send/recv, the small equivalence / area lists by all_gather, and
+        rank 0 ends up with the complete transcript table (``decoded_barcodes``); each rank keeps
+        its slab of the decoded image.  With ``n_slabs`` given, the slabs are processed one after
+        another on this GPU (volumes larger than HBM or than 2^32 voxels).  No reference
+        counterpart: SURVEY.md 8e."""
+        from . import sharded as sh
+
+        import torch
+
+        if not self._is_3D:
+            raise ValueError("z-slab sharding applies to 3-D decoding; 2-D mode shards by plane (tiles)")
+        if magnitude_threshold is None:
+            magnitude_threshold = DEFAULT_DECODE_MAGNITUDE_THRESHOLD
+        if minimum_pixels is None:
+            minimum_pixels = self._default_minimum_pixels()
+        rank, world, dist = self._dist()
+        distributed = n_slabs is None and dist is not None and world > 1
+        if gpu_id is None:
+            gpu_id = self._local_gpu()
+        self._prepare_normalization_state(normalization_method, use_normalization, gpu_id, lowpass_sigma)
+        self._tile_idx = tile_idx
+        sigma = self._effective_lowpass_sigma(lowpass_sigma)
+        lp = self._lowpass_active(sigma)
+        halo = sh.lowpass_z_radius(sigma) if lp else 0
+        ctx = self._ctx(gpu_id)
+        bkg, nrm = self._active_vectors()
+        optimize = self._optimize_normalization_weights
+        nb = self._n_merfish_bits
+
+        def load_slab(z0, z1, full_z):
+            a, b = max(0, z0 - halo), min(full_z, z1 + halo)
+            self._load_bit_data(gpu_id=gpu_id, z_bounds=(a, b))
+            st = self._device_state[gpu_id]
+            if lp:
+                self._lp_filter(sigma=sigma, gpu_id=gpu_id)
+                stack = st["stack"][:, z0 - a : z0 - a + (z1 - z0)].contiguous()
+            else:
+                self._prepare_decode_stack(gpu_id)
+                stack = st["stack"]
+            st.clear()
+            ctx.set_normalization(bkg, nrm)
+            ctx.set_thresholds(self._pixel_assignment_threshold, magnitude_threshold[0], magnitude_threshold[1])
+            return stack
+
+        # the volume's z extent (after z_range cropping) without loading it
+        probe = self._datastore.load_local_readout_image(tile=tile_idx, bit=list(self._datastore.bit_ids)[0])
+        probe = probe.result() if hasattr(probe, "result") else probe
+        full_z = int(probe[self._z_slice].shape[0])
+        bounds = sh.split_z(full_z, world if distributed else int(n_slabs or 1))
+        mine = [rank] if distributed else list(range(len(bounds)))
+        if distributed and rank >= len(bounds):
+            mine = []
+        results: dict[int, sh.SlabResult] = {}
+        kept: dict[int, tuple] = {}  # slab -> (stack, decoded, labels) still on the device
+        records: dict[tuple, dict] = {}
+        decoded_slabs = []
+        prev_planes = None
+
+        def crossing_ids(r):
+            """slab-local ids of r known to touch an interface (superset of what resolve keeps)."""
+            ids = [results[r].pairs[:, 0].astype(np.int64)] if len(results[r].pairs) else []
+            if r + 1 in results and len(results[r + 1].pairs):
+                ids.append(results[r + 1].pairs[:, 1].astype(np.int64))
+            return np.unique(np.concatenate(ids)) if ids else np.zeros(0, dtype=np.int64)
+
+        def retire(r):
+            """in-process mode: take the records slab r may have to contribute, then free it."""
+            stack_r, decoded_r, labels_r = kept.pop(r)
+            for cid, rec in sh.slab_records(ctx, stack_r, decoded_r, labels_r, crossing_ids(r), optimize).items():
+                records[(r, cid)] = rec
+            decoded_slabs.append(decoded_r)
+
+        for r in mine:
+            z0, z1 = bounds[r]
+            stack = load_slab(z0, z1, full_z)
+            decoded, labels, table = sh.decode_slab(ctx, stack, False, MAXIMUM_PIXELS, optimize)
+            res = sh.SlabResult(z0, z1, tuple(stack.shape[2:]), table)
+            if distributed:
+                reqs = []
+                if rank + 1 < len(bounds):
+                    reqs.append(dist.isend(decoded[-1].contiguous(), rank + 1))
+                    reqs.append(dist.isend(labels[-1].contiguous(), rank + 1))
+                if rank > 0:
+                    d_lo = torch.empty(stack.shape[2:], dtype=torch.int16, device=stack.device)
+                    l_lo = torch.empty(stack.shape[2:], dtype=torch.int32, device=stack.device)
+                    dist.recv(d_lo, rank - 1)
+                    dist.recv(l_lo, rank - 1)
+                    prev_planes = (d_lo, l_lo)
+                for q in reqs:
+                    q.wait()
+            if prev_planes is not None:
+                res.pairs, res.poisoned_here, poisoned_prev = sh.interface(ctx, prev_planes, decoded, labels)
+            else:
+                poisoned_prev = np.zeros(0, dtype=np.int64)
+            res._poisoned_prev = poisoned_prev
+            results[r] = res
+            kept[r] = (stack, decoded, labels)
+            prev_planes = (decoded[-1].contiguous(), labels[-1].contiguous())
+            del stack
+            if not distributed and (r - 1) in kept:
+                retire(r - 1)  # both of its interfaces are known now: at most two slabs stay resident
+        if not distributed and mine:
+            retire(mine[-1])
+        # ---- resolve (identical on every rank)
+        summary = {
+            r: dict(z0=s.z0, z1=s.z1, shape_yx=s.shape_yx, areas=s.table[:, _COL_AREA].copy(), pairs=s.pairs,
+                    poisoned_here=s.poisoned_here, poisoned_prev=s._poisoned_prev)
+            for r, s in results.items()
+        }
+        if distributed:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, summary)
+            summary = {k: v for g in gathered for k, v in g.items()}
+        order = sorted(summary)
+        areas = [summary[r]["areas"] for r in order]
+        pairs = [summary[r]["pairs"] for r in order]
+        poisoned = [np.asarray(summary[r]["poisoned_here"], dtype=np.int64) for r in order]
+        for i, r in enumerate(order):
+            if i > 0 and len(summary[r]["poisoned_prev"]):
+                poisoned[i - 1] = np.union1d(poisoned[i - 1], summary[r]["poisoned_prev"])
+        keep_local, groups = sh.resolve(areas, pairs, poisoned, minimum_pixels, MAXIMUM_PIXELS)
+        # ---- records of the crossing components this rank holds
+        need: dict[int, list[int]] = {}
+        for g in groups:
+            for r, cid in g:
+                need.setdefault(order[r], []).append(cid)
+        if distributed:
+            for r in mine:
+                stack, decoded, labels = kept[r]
+                for cid, rec in sh.slab_records(ctx, stack, decoded, labels, sorted(need.get(r, [])), optimize).items():
+                    records[(r, cid)] = rec
+                decoded_slabs.append(decoded)
+        local_tabs = {r: results[r].table[keep_local[order.index(r)]] for r in mine}
+        if distributed:
+            gathered = [None] * world if rank == 0 else None
+            dist.gather_object((records, local_tabs), gathered, dst=0)
+            if rank == 0:
+                records = {k: v for g in gathered for k, v in g[0].items()}
+                local_tabs = {k: v for g in gathered for k, v in g[1].items()}
+        # ---- assemble on rank 0 (or the only process)
+        st = self._device_state.setdefault(gpu_id, {})
+        st.clear()
+        if decoded_slabs:
+            st["decoded"] = torch.cat(decoded_slabs, dim=0) if len(decoded_slabs) > 1 else decoded_slabs[0]
+        kept.clear()
+        self._slab_bounds = [bounds[r] for r in mine]
+        if distributed and rank != 0:
+            self._df_barcodes = pd.DataFrame({c: [] for c in self._table_columns()})
+            return None
+        self._load_coordinate_metadata()
+        merged = []
+        for g in groups:
+            parts = [(summary[order[r]]["z0"], records[(order[r], cid)]) for r, cid in g]
+            merged.append(sh.merged_row(parts, summary[order[0]]["shape_yx"], nb, optimize))
+        slabs = [sh.SlabResult(summary[r]["z0"], summary[r]["z1"], summary[r]["shape_yx"], local_tabs[r]) for r in order]
+        tab = sh.assemble(slabs, [np.ones(len(local_tabs[r]), dtype=bool) for r in order], merged, nb)
+        self._df_barcodes = self._annotate_table(tab)
         return None
 
     # ------------------------------------------------------------------ multi-GPU plumbing

@@ -55,6 +55,11 @@ SIGNATURES = {
         [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_int, C.c_double,
          C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p],
     ),
+    "m3d_interface_pairs": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+         C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p],
+    ),
     "m3d_features": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_int,
@@ -285,6 +290,27 @@ class DecodeContext:
         )
         self._n_features = int(n.value)
         return self._n_features
+
+    def interface_pairs(self, dec_lo, lab_lo, dec_hi, lab_hi):
+        """(label_hi, label_lo) pairs joined across a z-slab interface, de-duplicated (int32 (n, 2))."""
+        import torch
+
+        Y, X = int(dec_hi.shape[-2]), int(dec_hi.shape[-1])
+        cap = 1 << 16
+        while True:
+            pairs = torch.empty((cap, 2), dtype=torch.int32, device=dec_hi.device)
+            n = C.c_int64(0)
+            _check(
+                self._lib.m3d_interface_pairs(self._h, _ptr(dec_lo), _ptr(lab_lo), _ptr(dec_hi), _ptr(lab_hi),
+                                              Y, X, _ptr(pairs), cap, C.byref(n), _stream(self.device)),
+                "m3d_interface_pairs",
+            )
+            if n.value <= cap:
+                break
+            cap = int(n.value)
+        if n.value == 0:
+            return np.zeros((0, 2), dtype=np.int32)
+        return np.unique(pairs[: n.value].cpu().numpy(), axis=0)
 
     def features(self, stack, decoded, optimize_mode: bool, n_rows: int | None = None):
         """Feature table (n_rows, 14 + bits) float64 on the device for the last ``label``."""

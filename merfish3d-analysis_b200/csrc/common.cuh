@@ -44,7 +44,7 @@ enum M3dKernel {
     KF_CCL_ASSIGN,
     KF_CCL_SCAN,
     KF_CCL_SCATTER,
-    KF_CCL_LABELS,
+    KF_CCL_INTERFACE,
     KF_FEATURES,
     KF_SELECT_HIST,
     KF_REPLACE_ABOVE,

@@ -25,7 +25,8 @@
 
 namespace {
 
-constexpr uint32_t DROPPED = 0xFFFFFFFFu;
+constexpr uint32_t DROPPED = 0xFFFFFFFFu;        // failed the minimum-size filter
+constexpr uint32_t DROPPED_LARGE = 0xFFFFFFFEu;  // failed the maximum-size filter
 constexpr int FEAT_MAX_PX = 2048;  // upper bound on maximum_pixels supported by the warp-sort path
 
 // counters layout inside ctx->s_counters (uint32 each)
@@ -190,7 +191,7 @@ ccl_select_kernel(const uint32_t* __restrict__ fg, const unsigned int* __restric
             if (root_of[i] == v) {
                 const uint32_t a = aux[v];
                 keep = (a >= min_keep) && (a <= max_keep);
-                if (!keep) aux[v] = DROPPED;
+                if (!keep) aux[v] = (a > max_keep) ? DROPPED_LARGE : DROPPED;
             }
         }
         warp_append(keep, v, roots, root_count);
@@ -216,7 +217,11 @@ ccl_scatter_kernel(const uint32_t* __restrict__ fg, const unsigned int* __restri
     const unsigned n = *fg_count;
     for (unsigned i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
         const uint32_t id = aux[root_of[i]];
-        if (id != DROPPED) {
+        if (id == DROPPED_LARGE) {
+            // z-slab sharding: a neighbouring slab must learn that this voxel belongs to an
+            // oversized component (its merged component is oversized too) -> label -1
+            if (labels) labels[fg[i]] = -1;
+        } else if (id != DROPPED) {
             const uint32_t v = fg[i];
             const uint32_t slot = atomicAdd(cursor + id, 1u);
             vox[offs[id] + slot] = i;  // position in the foreground list (also indexes the records)
@@ -494,7 +499,67 @@ int dispatch_features(m3d_ctx* ctx, const T* stack, size_t n_vox, int Y, int X, 
     return m3d_fail(M3D_ERR_ARG, "unsupported padded bit count %d", ctx->nb_pad);
 }
 
+// ------------------------------------------------------------------ z-slab interface
+// One thread per voxel of the upper slab's FIRST plane: every equal-valued 26-neighbour in the lower
+// slab's LAST plane (dz = -1, dy, dx in {-1,0,1}) yields a (label_hi, label_lo) equivalence.  Labels
+// are the per-slab canonical ids + 1 (0 = background / dropped small, -1 = oversized component).
+// Consecutive duplicates are suppressed per thread; the host de-duplicates the rest.
+__global__ void __launch_bounds__(256)
+ccl_interface_kernel(const int16_t* __restrict__ dec_lo, const int32_t* __restrict__ lab_lo,
+                     const int16_t* __restrict__ dec_hi, const int32_t* __restrict__ lab_hi, int Y, int X,
+                     int32_t* __restrict__ pairs, unsigned capacity, unsigned int* __restrict__ n_pairs) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (size_t)Y * X) return;
+    const int16_t val = dec_hi[i];
+    const int32_t lh = lab_hi[i];
+    if (val < 0 || lh == 0) return;
+    const int y = (int)(i / X), x = (int)(i - (size_t)y * X);
+    int32_t last = 0;
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= Y) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= X) continue;
+            const size_t j = (size_t)yy * X + xx;
+            const int32_t ll = lab_lo[j];
+            if (dec_lo[j] == val && ll != 0 && ll != last) {
+                last = ll;
+                const unsigned slot = atomicAdd(n_pairs, 1u);
+                if (slot < capacity) {
+                    pairs[2 * (size_t)slot] = lh;
+                    pairs[2 * (size_t)slot + 1] = ll;
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int m3d_interface_pairs(m3d_ctx* ctx, const int16_t* decoded_lo_dev, const int32_t* labels_lo_dev,
+                                   const int16_t* decoded_hi_dev, const int32_t* labels_hi_dev, int64_t Y, int64_t X,
+                                   int32_t* pairs_dev, int64_t capacity, int64_t* n_pairs_out, void* stream) {
+    if (!ctx || !decoded_lo_dev || !labels_lo_dev || !decoded_hi_dev || !labels_hi_dev || !pairs_dev || !n_pairs_out)
+        return m3d_fail(M3D_ERR_ARG, "m3d_interface_pairs: null argument");
+    if (Y <= 0 || X <= 0 || capacity <= 0 || Y * X >= 0x7fffffffll)
+        return m3d_fail(M3D_ERR_ARG, "m3d_interface_pairs: bad dims");
+    M3D_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (ctx->s_counters.ensure(256)) return M3D_ERR_CUDA;
+    unsigned int* counter = reinterpret_cast<unsigned int*>(ctx->s_counters.ptr) + 8;
+    M3D_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    const int blocks = (int)(((size_t)Y * X + 255) / 256);
+    M3D_LAUNCH(ctx, KF_CCL_INTERFACE, st,
+               ccl_interface_kernel<<<blocks, 256, 0, st>>>(decoded_lo_dev, labels_lo_dev, decoded_hi_dev, labels_hi_dev,
+                                                            (int)Y, (int)X, pairs_dev, (unsigned)capacity, counter));
+    M3D_CHECK_LAUNCH();
+    unsigned int* h = reinterpret_cast<unsigned int*>(ctx->h_pinned) + 8;
+    M3D_CUDA(cudaMemcpyAsync(h, counter, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    M3D_CUDA(cudaStreamSynchronize(st));
+    *n_pairs_out = (int64_t)*h;  // may exceed capacity: the caller retries with a larger buffer
+    return M3D_OK;
+}
 
 // ====================================================================== host entry points
 // defined in decode.cu

@@ -205,6 +205,25 @@ def test_contiguous_tile_chunks_like_reference():
     assert PixelDecoder._contiguous_chunks([0, 1], 4) == [[0], [1], [], []]
 
 
+def test_sharded_resolve_merges_filters_and_poisons():
+    """pure host logic of the z-slab merge (merfish3d-analysis_b200/sharded.py)."""
+    from merfish3d_analysis_b200 import sharded as sh
+
+    assert sh.split_z(10, 3) == [(0, 3), (3, 7), (7, 10)] and sh.split_z(2, 4) == [(0, 1), (1, 2)]
+    assert sh.lowpass_z_radius((3.0, 1.0, 1.0)) == 12
+    # slab0 ids: 0 (area 10, alone) 1 (area 9, crosses) 2 (area 300, crosses) 3 (area 3, alone, too small)
+    # slab1 ids: 0 (area 8, joins slab0:1 and slab2:0) 1 (area 300, joins slab0:2 -> 600 > 500) 2 (area 20, poisoned)
+    # slab2 ids: 0 (area 2, joins slab1:0)
+    areas = [np.array([10.0, 9.0, 300.0, 3.0]), np.array([8.0, 300.0, 20.0]), np.array([2.0])]
+    pairs = [np.zeros((0, 2), int), np.array([[0, 1], [1, 2]]), np.array([[0, 0]])]
+    poisoned = [np.zeros(0, int), np.array([2]), np.zeros(0, int)]
+    keep, groups = sh.resolve(areas, pairs, poisoned, minimum_pixels=16.9, maximum_pixels=500)
+    assert [k.tolist() for k in keep] == [[False, False, False, False], [False, False, False], [False]]
+    assert groups == [[(0, 1), (1, 0), (2, 0)]]  # 9 + 8 + 2 = 19 >= 16; the 600-voxel and poisoned ones are gone
+    keep, groups = sh.resolve(areas, pairs, poisoned, minimum_pixels=10, maximum_pixels=500)
+    assert keep[0].tolist() == [True, False, False, False]
+
+
 # ------------------------------------------------------------------ C ABI
 def test_shared_library_exports_every_declared_symbol():
     from merfish3d_analysis_b200 import _capi

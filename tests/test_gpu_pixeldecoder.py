@@ -170,3 +170,38 @@ def test_decode_all_tiles_writes_reference_layout(tmp_path):
                                  tile_idx=i, spacing=ds.voxel_size_zyx_um)
         _compare_tables(got, ref)
     assert len(dec._df_barcodes_loaded) == sum(len(pd.read_parquet(p)) for p in (tmp_path / "qi2labdatastore" / "decoded").glob("*.parquet"))
+
+
+@pytest.mark.parametrize("lowpass", [None, (3.0, 1.0, 1.0)])
+@pytest.mark.parametrize("n_slabs", [2, 3, 5])
+def test_z_slab_sharding_equals_unsharded(tmp_path, lowpass, n_slabs):
+    """z-slab sharding (here: sequential slabs on one GPU) == the unsharded volume,
+    including components cut by an interface, merged size filters and oversized components."""
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    df_cb, cb = cases.codebook16()
+    stack = cases.small_stack(cb["matrix"], shape=(30, 40, 56), seed=83, density=4e-3)
+    # a long uniform column crossing every interface (> 500 voxels -> dropped everywhere) and a
+    # thin one that is only large enough once its pieces are merged
+    on = np.flatnonzero(cb["matrix"][7])
+    stack[:, :, 2:8, 2:8] = 210
+    stack[np.ix_(on, np.arange(30), np.arange(2, 8), np.arange(2, 8))] = 2000
+    on2 = np.flatnonzero(cb["matrix"][21])
+    stack[:, 3:27, 30, 40] = 205
+    stack[np.ix_(on2, np.arange(3, 27), [30], [40])] = 1900
+    bkg, nrm = cases.simple_vectors(16, nrm=300.0 if lowpass else 900.0)
+    ds = _store(tmp_path, df_cb, [stack])
+    ds.save_decode_normalization_vectors(None, "global", nrm, bkg)
+    ref_dec = PixelDecoder(ds, merfish_bits=16, verbose=0)
+    ref_dec.decode_one_tile(0, lowpass_sigma=lowpass, minimum_pixels=12, normalization_method="global")
+    ref = ref_dec.decoded_barcodes
+    ref_img = ref_dec.decoded_image
+    dec = PixelDecoder(ds, merfish_bits=16, verbose=0)
+    dec.decode_one_tile_sharded(0, n_slabs=n_slabs, lowpass_sigma=lowpass, minimum_pixels=12,
+                                normalization_method="global")
+    got = dec.decoded_barcodes
+    np.testing.assert_array_equal(dec.decoded_image, ref_img)
+    assert len(ref) > 10
+    pd.testing.assert_frame_equal(got, ref)  # bit-identical table, same row order
+    if lowpass is None:
+        assert (ref["area"] == 24).any()  # the thin column survives only as a merged component

@@ -64,6 +64,34 @@ def main():
         assert all(c == total for c in counts), (counts, total)
         print(f"dist_smoke ok: world={world} tiles={n_tiles} transcripts={total} vectors match the oracle")
     dist.barrier()
+    # ---- z-slab sharding of ONE tile across the ranks == unsharded decode
+    big = cases.small_stack(cb["matrix"], shape=(8 * world + 3, 48, 64), seed=97, density=4e-3)
+    on = np.flatnonzero(cb["matrix"][7])
+    big[:, :, 2:8, 2:8] = 210
+    big[np.ix_(on, np.arange(big.shape[1]), np.arange(2, 8), np.arange(2, 8))] = 2000  # oversized, crosses all slabs
+    on2 = np.flatnonzero(cb["matrix"][21])
+    big[:, 2:-2, 30, 40] = 205
+    big[np.ix_(on2, np.arange(2, big.shape[1] - 2), [30], [40])] = 1900  # only large enough once merged
+    if rank == 0:
+        ds0 = ArrayDataStore(root)
+        ds0.add_tile(big, persist=True)
+    dist.barrier()
+    ds = ArrayDataStore(root)
+    t_big = len(ds.tile_ids) - 1
+    for sig in (None, (3.0, 1.0, 1.0)):
+        d = PixelDecoder(ds, merfish_bits=16, num_gpus=world, verbose=0)
+        d.decode_one_tile_sharded(t_big, lowpass_sigma=sig, minimum_pixels=12)
+        slab = d.decoded_image
+        if rank == 0:
+            u = PixelDecoder(ds, merfish_bits=16, num_gpus=1, verbose=0)
+            u.decode_one_tile(t_big, lowpass_sigma=sig, minimum_pixels=12)
+            import pandas as pd
+
+            pd.testing.assert_frame_equal(d.decoded_barcodes, u.decoded_barcodes)
+            z0, z1 = d._slab_bounds[0]
+            np.testing.assert_array_equal(slab, u.decoded_image[z0:z1])
+            print(f"dist_smoke ok: z-slab sharded x{world} lowpass={sig}: {len(u.decoded_barcodes)} transcripts identical")
+        dist.barrier()
     dist.destroy_process_group()
 
 
