@@ -905,14 +905,13 @@ class PixelDecoder:
             if distributed:
                 reqs = []
                 if rank + 1 < len(bounds):
-                    reqs.append(dist.isend(decoded[-1].contiguous(), rank + 1))
-                    reqs.append(dist.isend(labels[-1].contiguous(), rank + 1))
+                    # one int32 (2, Y, X) message: decoded plane (NCCL has no int16) + label plane
+                    out_planes = torch.stack([decoded[-1].to(torch.int32), labels[-1]]).contiguous()
+                    reqs.append(dist.isend(out_planes, rank + 1))
                 if rank > 0:
-                    d_lo = torch.empty(stack.shape[2:], dtype=torch.int16, device=stack.device)
-                    l_lo = torch.empty(stack.shape[2:], dtype=torch.int32, device=stack.device)
-                    dist.recv(d_lo, rank - 1)
-                    dist.recv(l_lo, rank - 1)
-                    prev_planes = (d_lo, l_lo)
+                    in_planes = torch.empty((2, *stack.shape[2:]), dtype=torch.int32, device=stack.device)
+                    dist.recv(in_planes, rank - 1)
+                    prev_planes = (in_planes[0].to(torch.int16).contiguous(), in_planes[1].contiguous())
                 for q in reqs:
                     q.wait()
             if prev_planes is not None:
