@@ -69,6 +69,14 @@ __device__ __forceinline__ int reflect_index(int j, int n) {
     return (m >= n) ? (per - 1 - m) : m;
 }
 
+// reflect for indices that overshoot the end by less than one period: no integer division on the
+// marching kernels' per-plane path (the general form stays behind a real branch)
+__device__ __forceinline__ int reflect_high(int j, int n) {
+    if (j < n) return j;
+    if (j < 2 * n) return 2 * n - 1 - j;
+    return reflect_index(j, n);
+}
+
 template <typename T>
 __device__ __forceinline__ float in_as_f32(const T* p, size_t i);
 template <>
@@ -84,25 +92,46 @@ __device__ __forceinline__ double load_weighted(const T* in, const float* pred, 
 }
 
 // ------------------------------------------------------------------ z pass, register ring
+// One thread per (y,x) column marching along z.  The 2R+1 float64 samples live in a register ring
+// (loop unrolled by the ring length so every index is static); the sample entering the ring is
+// fetched PF planes ahead, so the float64 pipe never waits on the load of the plane it is about
+// to consume.
 template <typename T, int R, bool PRED>
 __global__ void __launch_bounds__(128)
 lowpass_z_kernel(const T* __restrict__ in, const float* __restrict__ pred, float* __restrict__ out,
                  int Z, size_t plane, Weights W) {
     constexpr int RING = 2 * R + 1;
+    constexpr int PF = (RING % 5 == 0) ? 5 : ((RING % 3 == 0) ? 3 : 1);  // divides the unroll length
     const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= plane) return;
     double ring[RING];
+    T pre[PF];         // prefetched samples stay in their storage type: converting them on arrival
+    float pre_w[PF];   // would make the warp wait on the very load the prefetch is meant to hide
     // slot of ext[j] is (j + R) mod RING
 #pragma unroll
     for (int i = 0; i < 2 * R; ++i)
         ring[i] = load_weighted<T, PRED>(in, pred, (size_t)reflect_index(i - R, Z) * plane + c);
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+        const size_t a = (size_t)reflect_index(R + i, Z) * plane + c;
+        pre[i] = __ldg(in + a);
+        pre_w[i] = PRED ? __ldg(pred + a) : 1.f;
+    }
     for (int o0 = 0; o0 < Z; o0 += RING) {
 #pragma unroll
         for (int u = 0; u < RING; ++u) {
             const int o = o0 + u;
             if (o < Z) {
-                ring[(u + 2 * R) % RING] =
-                    load_weighted<T, PRED>(in, pred, (size_t)reflect_index(o + R, Z) * plane + c);
+                {
+                    float v = (float)pre[u % PF];
+                    if (PRED) v = __fmul_rn(v, pre_w[u % PF]);
+                    ring[(u + 2 * R) % RING] = (double)v;
+                }
+                {   // the sample for output o + PF (reflect keeps the address valid past the end)
+                    const size_t a = (size_t)reflect_high(o + R + PF, Z) * plane + c;
+                    pre[u % PF] = __ldg(in + a);
+                    if (PRED) pre_w[u % PF] = __ldg(pred + a);
+                }
                 double acc = __dmul_rn(ring[(u + R) % RING], W.w[R]);
 #pragma unroll
                 for (int jj = -R; jj < 0; ++jj) {
@@ -116,51 +145,96 @@ lowpass_z_kernel(const T* __restrict__ in, const float* __restrict__ pred, float
 }
 
 // ------------------------------------------------------------------ fused y,x pass, shared tile
-constexpr int YX_TX = 64;
+// Tile of YX_TY x (64 - 2*RX) outputs per CTA.  The float32 input tile (with halo) is staged in
+// shared memory once; both passes are REGISTER BLOCKED: a work item loads 8 + 2R consecutive
+// samples along the filter axis (conflict-free), converts them to float64 once and produces 8
+// outputs with SciPy's symmetric formula -- ~3 shared-memory words per output instead of 20, so the
+// kernel is bound by the float64 pipe, not by shared memory.
+//   y pass: item = (column, group of 8 rows); lanes = consecutive columns.
+//   x pass: item = (row, group of 8 columns); lanes = consecutive rows (row stride 73 words is
+//           coprime with the 32 banks); results go back through shared memory for coalesced stores.
 constexpr int YX_TY = 32;
+constexpr int YX_W = 64;             // staged columns = outputs + 2*RX
+constexpr int YX_STRIDE = YX_W + 9;  // 73 words: odd and coprime with 32
 constexpr int YX_THREADS = 256;
+constexpr int YX_BLK = 8;            // outputs per work item
 
 template <typename T, int RY, int RX, bool PRED>
 __global__ void __launch_bounds__(YX_THREADS)
 lowpass_yx_kernel(const T* __restrict__ in, const float* __restrict__ pred, float* __restrict__ out,
                   int Y, int X, Weights WY, Weights WX) {
     constexpr int IN_H = YX_TY + 2 * RY;
-    constexpr int IN_W = YX_TX + 2 * RX;
-    __shared__ double s_in[IN_H][IN_W + 1];
-    __shared__ double s_mid[YX_TY][IN_W + 1];
-    const int x0 = blockIdx.x * YX_TX;
+    constexpr int TX = YX_W - 2 * RX;
+    constexpr int XG = (TX + YX_BLK - 1) / YX_BLK;  // column groups (the last may be partial)
+    static_assert(YX_TY % YX_BLK == 0 && TX > 0, "tile must split into 8-output items");
+    __shared__ float s_in[IN_H][YX_STRIDE];
+    __shared__ float s_mid[YX_TY][YX_STRIDE];
+    const int x0 = blockIdx.x * TX;
     const int y0 = blockIdx.y * YX_TY;
     const size_t zoff = (size_t)blockIdx.z * (size_t)Y * X;
-    for (int i = threadIdx.x; i < IN_H * IN_W; i += YX_THREADS) {
-        const int ly = i / IN_W, lx = i - ly * IN_W;
-        const int gy = reflect_index(y0 + ly - RY, Y);
+    {
+        // thread = (column lx, row phase): the column reflection is computed once, all of the
+        // thread's loads are issued before the first shared-memory store
+        constexpr int ROWS_PER_PASS = YX_THREADS / YX_W;            // 4
+        constexpr int N_LD = (IN_H + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
+        const int lx = threadIdx.x % YX_W, lr = threadIdx.x / YX_W;
         const int gx = reflect_index(x0 + lx - RX, X);
-        s_in[ly][lx] = load_weighted<T, PRED>(in, pred, zoff + (size_t)gy * X + gx);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < YX_TY * IN_W; i += YX_THREADS) {
-        const int ly = i / IN_W, lx = i - ly * IN_W;
-        double acc = __dmul_rn(s_in[ly + RY][lx], WY.w[RY]);
+        T raw[N_LD];
+        float wv[N_LD];
 #pragma unroll
-        for (int jj = -RY; jj < 0; ++jj) {
-            double pr = __dadd_rn(s_in[ly + RY + jj][lx], s_in[ly + RY - jj][lx]);
-            acc = __dadd_rn(acc, __dmul_rn(pr, WY.w[jj + RY]));
+        for (int k = 0; k < N_LD; ++k) {
+            const int ly = lr + k * ROWS_PER_PASS;
+            const int gy = reflect_index(y0 + (ly < IN_H ? ly : IN_H - 1) - RY, Y);
+            const size_t a = zoff + (size_t)gy * X + gx;
+            raw[k] = __ldg(in + a);
+            wv[k] = PRED ? __ldg(pred + a) : 1.f;
         }
-        s_mid[ly][lx] = (double)(float)acc;
+#pragma unroll
+        for (int k = 0; k < N_LD; ++k) {
+            const int ly = lr + k * ROWS_PER_PASS;
+            float v = (float)raw[k];
+            if (PRED) v = __fmul_rn(v, wv[k]);
+            if (ly < IN_H) s_in[ly][lx] = v;
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < YX_TY * YX_TX; i += YX_THREADS) {
-        const int ly = i / YX_TX, lx = i - ly * YX_TX;
+    // ---- y pass: YX_W columns x (YX_TY / 8) row groups = 256 items
+    for (int it = threadIdx.x; it < YX_W * (YX_TY / YX_BLK); it += YX_THREADS) {
+        const int col = it % YX_W, r0 = (it / YX_W) * YX_BLK;
+        double v[YX_BLK + 2 * RY];
+#pragma unroll
+        for (int k = 0; k < YX_BLK + 2 * RY; ++k) v[k] = (double)s_in[r0 + k][col];
+#pragma unroll
+        for (int o = 0; o < YX_BLK; ++o) {
+            double acc = __dmul_rn(v[o + RY], WY.w[RY]);
+#pragma unroll
+            for (int jj = -RY; jj < 0; ++jj)
+                acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v[o + RY + jj], v[o + RY - jj]), WY.w[jj + RY]));
+            s_mid[r0 + o][col] = (float)acc;
+        }
+    }
+    __syncthreads();
+    // ---- x pass: YX_TY rows x (TX / 8) column groups; lanes = rows
+    for (int it = threadIdx.x; it < YX_TY * XG; it += YX_THREADS) {
+        const int row = it % YX_TY, c0 = (it / YX_TY) * YX_BLK;
+        double v[YX_BLK + 2 * RX];
+#pragma unroll
+        for (int k = 0; k < YX_BLK + 2 * RX; ++k) v[k] = (c0 + k < YX_W) ? (double)s_mid[row][c0 + k] : 0.0;
+#pragma unroll
+        for (int o = 0; o < YX_BLK; ++o) {
+            if (c0 + o >= TX) break;
+            double acc = __dmul_rn(v[o + RX], WX.w[RX]);
+#pragma unroll
+            for (int jj = -RX; jj < 0; ++jj)
+                acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v[o + RX + jj], v[o + RX - jj]), WX.w[jj + RX]));
+            s_in[row][c0 + o] = (float)acc;  // the input tile is dead: reuse it as the output stage
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < YX_TY * TX; i += YX_THREADS) {
+        const int ly = i / TX, lx = i - ly * TX;
         const int gy = y0 + ly, gx = x0 + lx;
-        if (gy < Y && gx < X) {
-            double acc = __dmul_rn(s_mid[ly][lx + RX], WX.w[RX]);
-#pragma unroll
-            for (int jj = -RX; jj < 0; ++jj) {
-                double pr = __dadd_rn(s_mid[ly][lx + RX + jj], s_mid[ly][lx + RX - jj]);
-                acc = __dadd_rn(acc, __dmul_rn(pr, WX.w[jj + RX]));
-            }
-            out[zoff + (size_t)gy * X + gx] = (float)acc;
-        }
+        if (gy < Y && gx < X) out[zoff + (size_t)gy * X + gx] = s_in[ly][lx];
     }
 }
 
@@ -216,7 +290,8 @@ int run_z(m3d_ctx* ctx, const T* in, const float* pred, float* out, int Z, int Y
 template <typename T, bool PRED>
 int run_yx_fast(m3d_ctx* ctx, const T* in, const float* pred, float* out, int n_planes, int Y, int X,
                 const Weights& WY, const Weights& WX, cudaStream_t st) {
-    dim3 grid((X + YX_TX - 1) / YX_TX, (Y + YX_TY - 1) / YX_TY, n_planes);
+    const int tx = YX_W - 2 * WX.r;  // outputs per tile row (see lowpass_yx_kernel)
+    dim3 grid((X + tx - 1) / tx, (Y + YX_TY - 1) / YX_TY, n_planes);
     if (grid.y > 65535 || grid.z > 65535) return 1;
     if (!((WY.r == 4 && WX.r == 4) || (WY.r == 2 && WX.r == 2) || (WY.r == 6 && WX.r == 6))) return 1;
     KernelScope ks(ctx, KF_LOWPASS_YX, st);
