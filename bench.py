@@ -325,9 +325,17 @@ def run_b200(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     gate_ms = ktimes.get("decode_gate_kernel", 0.0) / max(klaunch.get("decode_gate_kernel", 1), 1)
     achieved = GATE_BYTES_PER_VOXEL * n_vox / (gate_ms * 1e-3) / 1e9 if gate_ms else 0.0
+    # measured DRAM traffic of that kernel from the committed ncu --set full capture (same shape only)
+    traffic = None
+    tf = ROOT / "profiles" / "r1_gate_traffic.json"
+    if tf.exists():
+        tj = json.loads(tf.read_text())
+        if tuple(tj.get("shape_zyx", ())) == tuple(shape) and tj.get("n_bits") == N_BITS:
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / 1e9
     roofline = {
         "bound": "hbm", "kernel": "decode_gate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak if peak else None, "traffic": None,
+        "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_unit": "GB per launch (ncu dram__bytes_read+write)",
+        "algorithmic_gb_per_launch": GATE_BYTES_PER_VOXEL * n_vox / 1e9,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6.65 TB/s (of fallback)",
         "ms_per_launch": gate_ms, "algorithmic_bytes_per_voxel": GATE_BYTES_PER_VOXEL,
         "frac_of_nominal_8TBs": achieved / 8000.0,
