@@ -68,6 +68,18 @@ int m3d_set_thresholds(m3d_ctx* ctx, float pixel_threshold, float magnitude_lo,
 int m3d_weight(m3d_ctx* ctx, const uint16_t* readout_dev, const float* predictor_dev,
                int64_t n, float* out_dev, void* stream);
 
+/* Decode-time warp of one bit volume into the round-1 frame (PD:1882-1889 ->
+ * utils/decode_warping.py:184-245 -> utils/multiview_registration.py:797-902):
+ * scipy.ndimage.affine_transform(float32(in) * predictor, matrix, offset, order=1,
+ * mode='constant', cval=0) evaluated in float64 like SciPy.  matrix_host (3x3 row-major) and
+ * offset_host are the PIXEL-space matrix_px / offset_px of the reference.  in_dev holds the full
+ * (z,y,x) volume; only output planes [out_z0, out_z0 + out_nz) are written to out_dev (float32,
+ * (out_nz,y,x)), which is how z_range cropping and z-slab sharding request their planes.
+ * predictor_dev is nullable.  SOFIMA flow-field warping is not part of this build. */
+int m3d_warp_affine(m3d_ctx* ctx, const void* in_dev, int in_dtype, const float* predictor_dev,
+                    const int64_t dims[3], const double matrix_host[9], const double offset_host[3],
+                    int64_t out_z0, int64_t out_nz, float* out_dev, void* stream);
+
 /* _lp_filter / _lowpass_image (PD:1948-2024): per-volume Gaussian, reflect boundary,
  * radius int(4*sigma+0.5), axis order z,y,x, fp64 accumulation, fp32 result per pass
  * (scipy.ndimage.gaussian_filter semantics).  mode2d!=0 filters y,x only (per plane).

@@ -299,8 +299,9 @@ class PixelDecoder:
                 predictor = self._datastore.load_local_feature_predictor_image(
                     tile=tile_id, bit=bit_id, return_future=False
                 )
-                self._require_identity_warp(tile_id, bit_id)
-                img = self._weighted_volume_device(readout, predictor, ctx)
+                _ex, em = self._datastore.load_local_wavelengths_um(tile=tile_id, bit=bit_id)
+                img = self._weighted_volume_device(readout, predictor, ctx,
+                                                   warp=self._bit_warp_px(tile_id, bit_id, em))
                 # PD:1072-1074: hot pixels -> median of the middle plane
                 mid = img[img.shape[0] // 2]
                 med = stats.median([mid])
@@ -402,34 +403,61 @@ class PixelDecoder:
         return None, None
 
     # ================================================================== tile loading (PD:1828-1946)
-    def _require_identity_warp(self, tile, bit_id) -> None:
-        """Decode-time resampling (PD:1882-1889) is the 'next' row 8f-1; identity only here."""
-        if _is_identity_store(self._datastore):
-            return
+    def _bit_warp_px(self, tile, bit_id, emission_wavelength_um):
+        """Decode-time warp of one bit as scipy ``affine_transform`` arguments, or None (identity).
+
+        utils/decode_warping.py:184-245 (round transform x inverse chromatic transform) and
+        utils/multiview_registration.py:857-870 (physical -> pixel matrix / offset), float32 like
+        the reference.  SOFIMA flow fields are refused (not part of this build)."""
         ds = self._datastore
-        try:
-            rnd = ds.load_local_round_linker(tile=tile, bit=bit_id)
-            xf = ds.load_local_round_transform_zyx_um(tile=tile, round=rnd)
-            ok = xf is None or np.allclose(np.asarray(xf, dtype=float), np.eye(4))
-        except Exception as exc:  # unknown store surface -> refuse rather than silently skip warping
-            raise NotImplementedError(
-                "decode-time warping needs the reference's decode_warping path (SURVEY 8f-1); "
-                "this build decodes registered (identity-transform) data only"
-            ) from exc
-        if not ok:
-            raise NotImplementedError(
-                "non-identity round transform: decode-time warping is not built yet (SURVEY 8f-1)"
-            )
+        if _is_identity_store(ds):
+            return None
+        round_index = ds.load_local_round_linker(tile=tile, bit=bit_id) - 1
+        round_id = None
+        round_xf = np.eye(4, dtype=np.float32)
+        if round_index > 0:
+            round_id = ds.round_ids[round_index]
+            xf = ds.load_local_round_transform_zyx_um(tile=tile, round=round_id)
+            if xf is None:
+                raise RuntimeError(f"Missing local round transform for tile={tile} round={round_id}.")
+            round_xf = np.asarray(xf, dtype=np.float32)
+        chroma = ds.load_chromatic_affine_transform_zyx_um(wavelength_um=emission_wavelength_um)
+        chroma = np.eye(4, dtype=np.float32) if chroma is None else np.asarray(chroma, dtype=np.float32)
+        transform = np.linalg.inv(chroma) @ round_xf  # decode_warping.py:70-72
+        flow = None
+        if round_id is not None and hasattr(ds, "load_local_sofima_flow_field"):
+            flow = ds.load_local_sofima_flow_field(tile=tile, round=round_id, return_future=False)
+        if flow is not None:
+            _field, attrs = flow
+            if not str(attrs.get("sofima_status", "")).startswith("identity_fallback"):
+                raise NotImplementedError("SOFIMA flow-field warping is not part of this build (SURVEY 8f-1)")
+        if np.allclose(transform, np.eye(4, dtype=np.float32)):  # decode_warping.py:152-157
+            return None
+        spacing = np.asarray(ds.voxel_size_zyx_um, dtype=np.float32)
+        origin = np.zeros(3, dtype=np.float32)
+        transform = np.asarray(transform, dtype=np.float32)
+        linear_um, translation_um = transform[:3, :3], transform[:3, 3]
+        matrix_px = (linear_um * spacing[np.newaxis, :]) / spacing[:, np.newaxis]
+        offset_px = (linear_um @ origin + translation_um - origin) / spacing
+        return np.asarray(matrix_px, dtype=np.float32), np.asarray(offset_px, dtype=np.float32)
 
     @staticmethod
     def _is_unit_predictor(predictor) -> bool:
         return predictor is None or type(predictor).__name__ == "UnitPredictor"
 
-    def _weighted_volume_device(self, readout, predictor, ctx):
-        """float32(readout) * float32(predictor) for one (z, y, x) volume, on the device."""
+    def _weighted_volume_device(self, readout, predictor, ctx, warp=None):
+        """float32(readout) * float32(predictor) for one (z, y, x) volume, on the device, warped
+        into the round-1 frame when the bit carries a decode-time transform."""
         import torch
 
         r = torch.from_numpy(np.ascontiguousarray(readout)).to(ctx.device, non_blocking=True)
+        if warp is not None:
+            if r.dtype not in (torch.uint16, torch.float32):
+                r = torch.from_numpy(np.ascontiguousarray(readout, dtype=np.uint16)).to(ctx.device)
+            p = None
+            if not self._is_unit_predictor(predictor):
+                p = torch.from_numpy(np.ascontiguousarray(predictor, dtype=np.float32)).to(ctx.device)
+            return ctx.warp_affine(r, warp[0], warp[1], predictor=p)
         if r.dtype == torch.float32:
             img = r
             if not self._is_unit_predictor(predictor):
@@ -446,13 +474,18 @@ class PixelDecoder:
                        z_bounds: tuple[int, int] | None = None) -> None:
         """PD:1828-1946: gather the tile's bit volumes into one device stack + coordinate metadata.
 
-        Device state: ``readout`` (bits, z, y, x) uint16 (or float32 when the store holds float
-        data) and ``predictor`` float32 / None (None = weight exactly 1, multiply skipped)."""
+        Registered data (every bit's decode-time transform is the identity): device state
+        ``readout`` (bits, z, y, x) uint16 (float32 when the store holds float data) + ``predictor``
+        float32 / None (None = weight exactly 1, multiply skipped).
+        Otherwise the reference's warp (PD:1882-1889) runs on the device per bit --
+        ``m3d_warp_affine`` with the predictor multiply fused -- and the state holds the float32
+        ``stack`` directly.  ``z_bounds`` (z-slab sharding) selects planes [a, b) of the z-cropped
+        volume; warped bits still read their full input volume."""
         import torch
 
         ctx = self._ctx(gpu_id)
         bit_ids = list(self._datastore.bit_ids)[0 : self._n_merfish_bits]
-        readouts, predictors = [], []
+        loaded = []
         self._em_wvl = []
         for bit_id in bit_ids:
             fr = self._datastore.load_local_readout_image(tile=self._tile_idx, bit=bit_id)
@@ -460,36 +493,55 @@ class PixelDecoder:
             pa = fp.result() if hasattr(fp, "result") else fp
             ra = fr.result() if hasattr(fr, "result") else fr
             _ex, em = self._datastore.load_local_wavelengths_um(tile=self._tile_idx, bit=bit_id)
-            self._require_identity_warp(self._tile_idx, bit_id)
-            ra = ra[self._z_slice, :, :]
-            pa = None if self._is_unit_predictor(pa) else pa[self._z_slice, :, :]
-            self._full_z = int(ra.shape[0])
-            if z_bounds is not None:  # z-slab sharding: this rank / pass holds planes [a, b) only
-                ra = ra[z_bounds[0] : z_bounds[1]]
-                pa = None if pa is None else pa[z_bounds[0] : z_bounds[1]]
-            readouts.append(ra)
-            predictors.append(pa)
+            warp = self._bit_warp_px(self._tile_idx, bit_id, em)
+            loaded.append((ra, None if self._is_unit_predictor(pa) else pa, warp))
             self._em_wvl.append(em)
-        shape = tuple(readouts[0].shape)
+        z_full = int(loaded[0][0].shape[0])
+        zs, ze, _step = self._z_slice.indices(z_full)
+        self._full_z = max(ze - zs, 0)
         if self._decode_mode == "3d" and self._full_z < 2:
             raise ValueError("decode_mode='3d' requires at least two z planes after applying z_range.")
-        float_input = any(np.asarray(r).dtype.kind == "f" for r in readouts)
-        dt = torch.float32 if float_input else torch.uint16
+        a, b = (zs, ze) if z_bounds is None else (zs + int(z_bounds[0]), zs + int(z_bounds[1]))
+        shape = (b - a, *loaded[0][0].shape[1:])
+        float_input = any(np.asarray(r).dtype.kind == "f" for r, _p, _w in loaded)
         npdt = np.float32 if float_input else np.uint16
-        stack = torch.empty((len(bit_ids), *shape), dtype=dt, device=ctx.device)
-        for b, r in enumerate(readouts):
-            stack[b].copy_(torch.from_numpy(np.ascontiguousarray(r, dtype=npdt)), non_blocking=True)
-        pred = None
-        if any(p is not None for p in predictors):
-            pred = torch.empty((len(bit_ids), *shape), dtype=torch.float32, device=ctx.device)
-            for b, p in enumerate(predictors):
-                if p is None:
-                    pred[b].fill_(1.0)
-                else:
-                    pred[b].copy_(torch.from_numpy(np.ascontiguousarray(p, dtype=np.float32)), non_blocking=True)
         st = self._device_state.setdefault(gpu_id, {})
         st.clear()
-        st["readout"], st["predictor"] = stack, pred
+
+        def to_dev(arr, dtype):
+            return torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(ctx.device, non_blocking=True)
+
+        if any(w is not None for _r, _p, w in loaded):
+            stack = torch.empty((len(bit_ids), *shape), dtype=torch.float32, device=ctx.device)
+            for i, (ra, pa, warp) in enumerate(loaded):
+                if warp is None:
+                    r = to_dev(ra[a:b], npdt)
+                    p = None if pa is None else to_dev(pa[a:b], np.float32)
+                    if r.dtype == torch.float32:
+                        stack[i].copy_(r if p is None else r * p)
+                    else:
+                        ctx.weight(r, p, out=stack[i])
+                else:
+                    r = to_dev(ra, npdt)  # the warp samples the whole native volume
+                    p = None if pa is None else to_dev(pa, np.float32)
+                    ctx.warp_affine(r, warp[0], warp[1], predictor=p, out_z0=a, out_nz=b - a, out=stack[i])
+                del r, p
+            st["readout"], st["predictor"], st["stack"] = None, None, stack
+        else:
+            dt = torch.float32 if float_input else torch.uint16
+            stack = torch.empty((len(bit_ids), *shape), dtype=dt, device=ctx.device)
+            for i, (ra, _pa, _w) in enumerate(loaded):
+                stack[i].copy_(torch.from_numpy(np.ascontiguousarray(ra[a:b], dtype=npdt)), non_blocking=True)
+            pred = None
+            if any(pa is not None for _r, pa, _w in loaded):
+                pred = torch.empty((len(bit_ids), *shape), dtype=torch.float32, device=ctx.device)
+                for i, (_ra, pa, _w) in enumerate(loaded):
+                    if pa is None:
+                        pred[i].fill_(1.0)
+                    else:
+                        pred[i].copy_(torch.from_numpy(np.ascontiguousarray(pa[a:b], dtype=np.float32)),
+                                      non_blocking=True)
+            st["readout"], st["predictor"] = stack, pred
         self._load_coordinate_metadata()
 
     def _load_coordinate_metadata(self) -> None:
@@ -526,13 +578,16 @@ class PixelDecoder:
         """PD:1982-2024: Gaussian low-pass of every bit volume (predictor multiply fused in)."""
         st = self._device_state[gpu_id]
         ctx = self._ctx(gpu_id)
-        st["stack"] = ctx.lowpass(st["readout"], sigma, not self._is_3D, predictor=st["predictor"])
+        if st.get("stack") is not None:  # warped on load: already float32(readout) * predictor
+            st["stack"] = ctx.lowpass(st["stack"], sigma, not self._is_3D)
+        else:
+            st["stack"] = ctx.lowpass(st["readout"], sigma, not self._is_3D, predictor=st["predictor"])
         self._filter_type = "lp"
 
     def _prepare_decode_stack(self, gpu_id: int = 0) -> None:
         """Raw path: the decode input is float32(readout) * predictor (PD:1879-1881)."""
         st = self._device_state[gpu_id]
-        if "stack" in st:
+        if st.get("stack") is not None:
             return
         if st["predictor"] is None:
             st["stack"] = st["readout"]  # float32(uint16) is exact; kernels convert on load
@@ -872,7 +927,8 @@ class PixelDecoder:
         # the volume's z extent (after z_range cropping) without loading it
         probe = self._datastore.load_local_readout_image(tile=tile_idx, bit=list(self._datastore.bit_ids)[0])
         probe = probe.result() if hasattr(probe, "result") else probe
-        full_z = int(probe[self._z_slice].shape[0])
+        zs_, ze_, _ = self._z_slice.indices(int(probe.shape[0]))
+        full_z = max(ze_ - zs_, 0)
         bounds = sh.split_z(full_z, world if distributed else int(n_slabs or 1))
         mine = [rank] if distributed else list(range(len(bounds)))
         if distributed and rank >= len(bounds):

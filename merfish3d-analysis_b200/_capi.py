@@ -35,6 +35,11 @@ SIGNATURES = {
     "m3d_set_normalization": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "m3d_set_thresholds": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float]),
     "m3d_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "m3d_warp_affine": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double),
+         C.POINTER(C.c_double), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p],
+    ),
     "m3d_lowpass": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int64),
@@ -220,6 +225,25 @@ class DecodeContext:
             self._lib.m3d_weight(self._h, _ptr(readout), _ptr(predictor), readout.numel(),
                                  _ptr(out), _stream(self.device)),
             "m3d_weight",
+        )
+        return out
+
+    def warp_affine(self, volume, matrix_px, offset_px, predictor=None, out_z0: int = 0, out_nz=None, out=None):
+        """scipy-style order-1 affine resampling of one (z, y, x) volume -> float32 planes."""
+        import torch
+
+        if volume.dim() != 3:
+            raise ValueError("volume must be (z, y, x)")
+        nz = int(volume.shape[0]) if out_nz is None else int(out_nz)
+        if out is None:
+            out = torch.empty((nz, *volume.shape[1:]), dtype=torch.float32, device=volume.device)
+        m = (C.c_double * 9)(*[float(v) for v in np.asarray(matrix_px, dtype=np.float64).reshape(9)])
+        o = (C.c_double * 3)(*[float(v) for v in np.asarray(offset_px, dtype=np.float64).reshape(3)])
+        _check(
+            self._lib.m3d_warp_affine(self._h, _ptr(volume), _dtype_code(volume), _ptr(predictor),
+                                      self._dims(volume.shape), m, o, int(out_z0), nz, _ptr(out),
+                                      _stream(self.device)),
+            "m3d_warp_affine",
         )
         return out
 

@@ -48,6 +48,7 @@ enum M3dKernel {
     KF_FEATURES,
     KF_SELECT_HIST,
     KF_REPLACE_ABOVE,
+    KF_WARP_AFFINE,
     KF_COUNT
 };
 

@@ -358,7 +358,106 @@ __global__ void weight_kernel(const uint16_t* __restrict__ r, const float* __res
     }
 }
 
+// ------------------------------------------------------------------ decode-time affine warp
+// scipy.ndimage.affine_transform(order=1, mode='constant', cval=0) semantics (the reference's
+// warp_array_to_reference_gpu, utils/multiview_registration.py:797-902): input coordinate
+// c_a = ((offset_a + z*m_a0) + y*m_a1) + x*m_a2 in float64; a sample whose coordinate falls outside
+// [0, dim-1] on any axis is cval; otherwise the 8 taps are accumulated in float64 in z,y,x nesting
+// order as ((v*wz)*wy)*wx, taps outside the image contributing 0.  The predictor multiply of
+// PD:1879-1881 is fused into the tap loads.
+struct AffineParams {
+    double m[9];
+    double off[3];
+};
+
+template <typename T, bool PRED>
+__global__ void __launch_bounds__(256)
+warp_affine_kernel(const T* __restrict__ in, const float* __restrict__ pred, int Z, int Y, int X, int oz0,
+                   size_t n_out, AffineParams A, float* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_out) return;
+    const size_t plane = (size_t)Y * X;
+    const int oz = (int)(i / plane);
+    const size_t rem = i - (size_t)oz * plane;
+    const int y = (int)(rem / X), x = (int)(rem - (size_t)y * X);
+    const double zc = (double)(oz0 + oz), yc = (double)y, xc = (double)x;
+    const int dims[3] = {Z, Y, X};
+    int st[3];
+    double w[3][2];
+    bool outside = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double c = __dadd_rn(A.off[a], __dmul_rn(zc, A.m[3 * a]));
+        c = __dadd_rn(c, __dmul_rn(yc, A.m[3 * a + 1]));
+        c = __dadd_rn(c, __dmul_rn(xc, A.m[3 * a + 2]));
+        outside |= !(c >= 0.0 && c <= (double)(dims[a] - 1));  // NaN coordinates are outside too
+        const double fl = floor(c);
+        st[a] = (int)fl;
+        const double f = __dadd_rn(c, -fl);
+        w[a][0] = __dadd_rn(1.0, -f);
+        w[a][1] = f;
+    }
+    double t = 0.0;
+    if (!outside) {
+#pragma unroll
+        for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int iz = st[0] + dz, iy = st[1] + dy, ix = st[2] + dx;
+                    double v = 0.0;
+                    if (iz < Z && iy < Y && ix < X) {  // lower bounds hold: coordinates are >= 0
+                        const size_t j = (size_t)iz * plane + (size_t)iy * X + ix;
+                        float fv = in_as_f32<T>(in, j);
+                        if (PRED) fv = __fmul_rn(fv, __ldg(pred + j));
+                        v = (double)fv;
+                    }
+                    const double term = __dmul_rn(__dmul_rn(__dmul_rn(v, w[0][dz]), w[1][dy]), w[2][dx]);
+                    t = __dadd_rn(t, term);
+                }
+    }
+    out[i] = (float)t;
+}
+
 }  // namespace
+
+extern "C" int m3d_warp_affine(m3d_ctx* ctx, const void* in_dev, int in_dtype, const float* predictor_dev,
+                               const int64_t dims[3], const double matrix_host[9], const double offset_host[3],
+                               int64_t out_z0, int64_t out_nz, float* out_dev, void* stream) {
+    if (!ctx || !in_dev || !out_dev || !dims || !matrix_host || !offset_host)
+        return m3d_fail(M3D_ERR_ARG, "m3d_warp_affine: null argument");
+    if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0 || dims[0] > 0x7fffffff || dims[1] > 0x7fffffff ||
+        dims[2] > 0x7fffffff || out_nz <= 0 || out_z0 < -0x7fffffffll || out_z0 > 0x7fffffffll)
+        return m3d_fail(M3D_ERR_ARG, "m3d_warp_affine: bad dims");
+    if (in_dtype != M3D_DTYPE_U16 && in_dtype != M3D_DTYPE_F32)
+        return m3d_fail(M3D_ERR_ARG, "m3d_warp_affine: dtype %d", in_dtype);
+    M3D_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    AffineParams A;
+    for (int i = 0; i < 9; ++i) A.m[i] = matrix_host[i];
+    for (int i = 0; i < 3; ++i) A.off[i] = offset_host[i];
+    const int Z = (int)dims[0], Y = (int)dims[1], X = (int)dims[2];
+    const size_t n_out = (size_t)out_nz * Y * X;
+    const size_t blocks = (n_out + 255) / 256;
+    if (blocks > 0x7fffffffull) return m3d_fail(M3D_ERR_ARG, "m3d_warp_affine: grid too large");
+    KernelScope ks(ctx, KF_WARP_AFFINE, st);
+    if (in_dtype == M3D_DTYPE_U16) {
+        const uint16_t* p = reinterpret_cast<const uint16_t*>(in_dev);
+        if (predictor_dev)
+            warp_affine_kernel<uint16_t, true><<<(unsigned)blocks, 256, 0, st>>>(p, predictor_dev, Z, Y, X, (int)out_z0, n_out, A, out_dev);
+        else
+            warp_affine_kernel<uint16_t, false><<<(unsigned)blocks, 256, 0, st>>>(p, nullptr, Z, Y, X, (int)out_z0, n_out, A, out_dev);
+    } else {
+        const float* p = reinterpret_cast<const float*>(in_dev);
+        if (predictor_dev)
+            warp_affine_kernel<float, true><<<(unsigned)blocks, 256, 0, st>>>(p, predictor_dev, Z, Y, X, (int)out_z0, n_out, A, out_dev);
+        else
+            warp_affine_kernel<float, false><<<(unsigned)blocks, 256, 0, st>>>(p, nullptr, Z, Y, X, (int)out_z0, n_out, A, out_dev);
+    }
+    M3D_CHECK_LAUNCH();
+    return M3D_OK;
+}
 
 extern "C" int m3d_lowpass(m3d_ctx* ctx, const void* in_dev, int in_dtype, const float* predictor_dev,
                            int n_vols, const int64_t dims[3], const double sigma[3], int mode2d,

@@ -135,7 +135,10 @@ class ArrayDataStore:
 
     @property
     def round_ids(self):
-        return ["round001"]
+        n = 1
+        for meta in self._tile_meta.values():
+            n = max(n, max(meta.get("bit_round", [1]) or [1]))
+        return [f"round{i:03d}" for i in range(1, n + 1)]
 
     @property
     def voxel_size_zyx_um(self):
@@ -201,6 +204,8 @@ class ArrayDataStore:
         global_xform: tuple | None = None,
         wavelengths_um: Sequence[tuple[float, float]] | None = None,
         persist: bool = False,
+        bit_round: Sequence[int] | None = None,
+        round_transforms_zyx_um: Mapping[int, np.ndarray] | None = None,
     ) -> str:
         """Register one tile: ``readouts`` (bits, z, y, x) uint16, ``predictors`` float32/None."""
         readouts = np.asarray(readouts)
@@ -227,6 +232,11 @@ class ArrayDataStore:
             meta["global_spacing"] = [float(v) for v in spc]
         if wavelengths_um is not None:
             meta["wavelengths_um"] = [[float(a), float(b)] for a, b in wavelengths_um]
+        if bit_round is not None:  # 1-based imaging round of every bit (round 1 = reference frame)
+            meta["bit_round"] = [int(r) for r in bit_round]
+            meta["round_transforms_zyx_um"] = {
+                str(int(k)): np.asarray(v, dtype=float).tolist() for k, v in (round_transforms_zyx_um or {}).items()
+            }
         attrs.setdefault("tile_meta", {})[tile_id] = meta
         self._save_calibrations_attributes(attrs)
         self._refresh(attrs)
@@ -302,12 +312,18 @@ class ArrayDataStore:
             np.asarray(meta["global_spacing"], dtype=np.float32),
         )
 
-    # warping inputs: this store only holds already-registered data (identity transforms)
+    # decode-time warping inputs (utils/decode_warping.py:39-52): imaging round of each bit and the
+    # physical transform from the reference round into that round; identity unless add_tile got them
     def load_local_round_linker(self, tile, bit):
-        return 1
+        meta = self._tile_meta.get(self._tile_id(tile), {})
+        br = meta.get("bit_round")
+        return 1 if br is None else int(br[self._bit_ids.index(self._bit_id(bit))])
 
     def load_local_round_transform_zyx_um(self, tile, round):
-        return np.eye(4, dtype=np.float32)
+        meta = self._tile_meta.get(self._tile_id(tile), {})
+        idx = round if isinstance(round, (int, np.integer)) else int(str(round)[-3:])
+        xf = meta.get("round_transforms_zyx_um", {}).get(str(int(idx)))
+        return np.eye(4, dtype=np.float32) if xf is None else np.asarray(xf, dtype=np.float32)
 
     def load_chromatic_affine_transform_zyx_um(self, *a, **k):
         return np.eye(4, dtype=np.float32)
@@ -315,7 +331,9 @@ class ArrayDataStore:
     def load_local_sofima_flow_field(self, *a, **k):
         return None
 
-    has_identity_decode_transforms = True
+    @property
+    def has_identity_decode_transforms(self) -> bool:
+        return not any("bit_round" in m for m in self._tile_meta.values())
 
     # ------------------------------------------------------------------ normalisation vectors
     @staticmethod

@@ -119,6 +119,31 @@ def weight_readout(readout: np.ndarray, predictor: np.ndarray | None) -> np.ndar
     return r * np.asarray(predictor, dtype=F32)
 
 
+def warp_px_arguments(transform_zyx_um, spacing_zyx_um):
+    """utils/multiview_registration.py:857-870 -- physical 4x4 transform -> affine_transform
+    ``matrix`` / ``offset`` in pixel units, float32 like the reference (origin = 0)."""
+    spacing = np.asarray(spacing_zyx_um, dtype=F32)
+    origin = np.zeros(3, dtype=F32)
+    transform = np.asarray(transform_zyx_um, dtype=F32)
+    linear_um = transform[:3, :3]
+    translation_um = transform[:3, 3]
+    matrix_px = (linear_um * spacing[np.newaxis, :]) / spacing[:, np.newaxis]
+    offset_px = (linear_um @ origin + translation_um - origin) / spacing
+    return matrix_px, offset_px
+
+
+def warp_to_reference(image: np.ndarray, transform_zyx_um, spacing_zyx_um) -> np.ndarray:
+    """utils/decode_warping.py:118-182 + utils/multiview_registration.py:797-902 -- order-1 affine
+    resampling into the round-1 frame; identity transforms return the input unchanged.
+    ``cupyx.scipy.ndimage.affine_transform`` is restated by SciPy's (same family, float64 inside)."""
+    image = np.asarray(image, dtype=F32)
+    if transform_zyx_um is None or np.allclose(transform_zyx_um, np.eye(4, dtype=F32)):
+        return image
+    matrix_px, offset_px = warp_px_arguments(transform_zyx_um, spacing_zyx_um)
+    return ndi.affine_transform(image, matrix_px, offset=offset_px, output_shape=image.shape, order=1,
+                                mode="constant", cval=0.0).astype(F32, copy=False)
+
+
 def lowpass_active(sigma) -> bool:
     """PD:1969, PD:4543-4546."""
     return sigma is not None and not np.any(np.asarray(sigma, dtype=float) == 0)
@@ -500,12 +525,19 @@ def decode_tile(
     excluded=(),
     optimize_mode: bool = False,
     tile_idx: int = 0,
+    bit_transforms_zyx_um=None,
     **coords,
 ):
-    """PD:4471-4579 -- one tile end to end; returns (table, images dict)."""
+    """PD:4471-4579 -- one tile end to end; returns (table, images dict).
+
+    ``bit_transforms_zyx_um``: optional per-bit physical 4x4 decode-time transforms (PD:1882-1889)."""
     if minimum_pixels is None:
         minimum_pixels = DEFAULT_3D_MINIMUM_PIXELS if is_3d else DEFAULT_2D_MINIMUM_PIXELS
     stack = weight_readout(readout, predictor)
+    if bit_transforms_zyx_um is not None:
+        spacing_um = coords.get("spacing", (1.0, 1.0, 1.0))
+        stack = np.stack([warp_to_reference(stack[b], bit_transforms_zyx_um[b], spacing_um)
+                          for b in range(stack.shape[0])])
     if is_3d and stack.shape[1] < 2:
         raise ValueError("decode_mode='3d' requires at least two z planes after applying z_range.")
     stack = lowpass_stack(stack, lowpass_sigma, is_3d)

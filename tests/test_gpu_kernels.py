@@ -205,6 +205,33 @@ def test_lowpass_f32_with_predictor_and_other_sigmas(torch):
     np.testing.assert_array_equal(got[0].view(np.uint32), ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("in_dtype", ["u16", "f32"])
+def test_warp_affine_matches_scipy_bit_exact(torch, in_dtype):
+    """decode-time warp = scipy.ndimage.affine_transform(order=1, mode='constant', cval=0)."""
+    _df, cb = cases.codebook16()
+    ctx, _ = _ctx(cb)
+    rng = np.random.default_rng(71)
+    vol = rng.integers(0, 60000, size=(14, 45, 52)).astype(np.uint16)
+    if in_dtype == "f32":
+        vol = (vol.astype(np.float32) * np.float32(0.37)).astype(np.float32)
+    pred = rng.uniform(0, 1, size=vol.shape).astype(np.float32)
+    spacing = (0.315, 0.098, 0.098)
+    for k in range(4):
+        xf = np.eye(4, dtype=np.float32)
+        xf[:3, :3] += rng.normal(0, 0.004, (3, 3)).astype(np.float32)
+        xf[:3, 3] = (rng.uniform(-1.0, 1.0, 3) * np.asarray(spacing) * (1 + k)).astype(np.float32)  # <= 4 px
+        m, o = orc.warp_px_arguments(xf, spacing)
+        for p in (None, pred):
+            w = orc.weight_readout(vol, p)
+            ref = orc.warp_to_reference(w, xf, spacing)
+            got = ctx.warp_affine(_dev(torch, vol), m, o, predictor=None if p is None else _dev(torch, p)).cpu().numpy()
+            np.testing.assert_array_equal(got.view(np.uint32), ref.view(np.uint32))
+            assert 0.05 < (ref != 0).mean() <= 1.0
+        # plane window (z_range cropping / z-slab sharding)
+        part = ctx.warp_affine(_dev(torch, vol), m, o, out_z0=3, out_nz=6).cpu().numpy()
+        np.testing.assert_array_equal(part, orc.warp_to_reference(orc.weight_readout(vol, None), xf, spacing)[3:9])
+
+
 def test_weight_kernel(torch):
     _df, cb = cases.codebook16()
     ctx, _ = _ctx(cb)

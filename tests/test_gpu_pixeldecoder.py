@@ -13,6 +13,7 @@ REL = 1e-5
 
 
 def _store(tmp_path, df_cb, stacks, predictors=None, microscope_type="3D", **tile_kw):
+    """array-fed datastore; extra keywords go to add_tile (stage / round transform metadata)."""
     from merfish3d_analysis_b200.datastore import ArrayDataStore
 
     ds = ArrayDataStore(tmp_path / "qi2labdatastore", codebook=df_cb, voxel_size_zyx_um=(0.315, 0.098, 0.098),
@@ -205,3 +206,43 @@ def test_z_slab_sharding_equals_unsharded(tmp_path, lowpass, n_slabs):
     pd.testing.assert_frame_equal(got, ref)  # bit-identical table, same row order
     if lowpass is None:
         assert (ref["area"] == 24).any()  # the thin column survives only as a merged component
+
+
+@pytest.mark.parametrize("lowpass", [None, (3.0, 1.0, 1.0)])
+def test_decode_with_round_transforms_matches_oracle(tmp_path, lowpass):
+    """bits of later rounds are resampled into the round-1 frame on load (affine, order 1)."""
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    df_cb, cb = cases.codebook16()
+    stack = cases.small_stack(cb["matrix"], shape=(14, 48, 64), seed=91, density=3e-3)
+    rng = np.random.default_rng(7)
+    bit_round = [1 + (b // 2) % 4 for b in range(16)]  # rounds 1..4, two bits each, repeating
+    xfs = {}
+    for r in (2, 3, 4):
+        xf = np.eye(4, dtype=np.float32)
+        xf[:3, :3] += rng.normal(0, 0.002, (3, 3)).astype(np.float32)
+        xf[:3, 3] = (rng.uniform(-1.0, 1.0, 3) * np.array([0.315, 0.098, 0.098])).astype(np.float32)
+        xfs[r] = xf
+    pred = rng.uniform(0.9, 1.0, size=stack.shape).astype(np.float32)
+    ds = _store(tmp_path, df_cb, [stack], [pred], bit_round=bit_round, round_transforms_zyx_um=xfs)
+    bkg, nrm = cases.simple_vectors(16, nrm=300.0 if lowpass else 800.0)
+    ds.save_decode_normalization_vectors(None, "global", nrm, bkg)
+    dec = PixelDecoder(ds, merfish_bits=16, verbose=0, z_range=(1, 13))
+    out = dec.decode_one_tile(0, lowpass_sigma=lowpass, minimum_pixels=4, normalization_method="global",
+                              return_results=True)
+    per_bit = [None if r == 1 else xfs[r] for r in bit_round]
+    # the reference warps the full volume, then crops z (PD:1890)
+    w = orc.weight_readout(stack, pred)
+    w = np.stack([orc.warp_to_reference(w[b], per_bit[b], ds.voxel_size_zyx_um) for b in range(16)])[:, 1:13]
+    ref, imgs = orc.decode_tile(w, None, cb, bkg, nrm, lowpass_sigma=lowpass, minimum_pixels=4,
+                                spacing=ds.voxel_size_zyx_um, z_offset=1.0)
+    np.testing.assert_array_equal(out[0], imgs["image"])
+    np.testing.assert_array_equal(out[4], imgs["decoded"])
+    assert len(ref) > 5
+    _compare_tables(dec.decoded_barcodes, ref)
+    # sharded decode of warped data gives the same table
+    dec2 = PixelDecoder(ds, merfish_bits=16, verbose=0, z_range=(1, 13))
+    dec2.decode_one_tile_sharded(0, n_slabs=3, lowpass_sigma=lowpass, minimum_pixels=4, normalization_method="global")
+    dec3 = PixelDecoder(ds, merfish_bits=16, verbose=0, z_range=(1, 13))
+    dec3.decode_one_tile(0, lowpass_sigma=lowpass, minimum_pixels=4, normalization_method="global")
+    pd.testing.assert_frame_equal(dec2.decoded_barcodes, dec3.decoded_barcodes)
