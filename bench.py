@@ -255,66 +255,9 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step_serial = float(t.item()) / args.steps
-    serial = {"ms_per_step": ms_step_serial, "value": world * n_vox / (ms_step_serial * 1e-3) / 1e9,
-              "note": "one stream, steps back to back (tile latency); the roofline block is measured here"}
     gpu_launches = int(sum(klaunch.values()))
     ms_step = ms_step_serial
 
-    # ---- throughput mode: the same K steps on `depth` streams (one context + host thread each), so
-    # the latency-bound sparse stages of one tile overlap the HBM-bound gate kernel of the next --
-    # what decode_all_tiles does per GPU.  All K steps start and finish inside the timed region.
-    depth = max(1, int(args.pipeline))
-    if depth > 1:
-        import threading
-
-        ctxs = [ctx] + [DecodeContext(unit, (), device=local) for _ in range(depth - 1)]
-        decs = [decoded] + [torch.empty_like(decoded) for _ in range(depth - 1)]
-        streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
-        for c in ctxs[1:]:
-            c.set_normalization(bkg, nrm)
-            c.set_thresholds(dec._pixel_assignment_threshold, MAG[0], MAG[1])
-
-        def run_steps(w, n_steps, start_evt, done):
-            torch.cuda.set_device(local)
-            with torch.cuda.stream(streams[w]):
-                if start_evt is not None:
-                    streams[w].wait_event(start_evt)
-                for _ in range(n_steps):
-                    n = ctxs[w].decode_label(stack, decs[w], False, MIN_PX, 500)
-                    ctxs[w].features(stack, decs[w], False, n)
-                done[w] = torch.cuda.Event()
-                done[w].record(streams[w])
-
-        def run_all(n_total, start_evt):
-            done = [None] * depth
-            share = [n_total // depth + (1 if w < n_total % depth else 0) for w in range(depth)]
-            ths = [threading.Thread(target=run_steps, args=(w, share[w], start_evt, done)) for w in range(depth)]
-            for th in ths:
-                th.start()
-            for th in ths:
-                th.join()
-            for d in done:
-                torch.cuda.current_stream().wait_event(d)
-
-        run_all(max(args.warmup, 3) * depth, None)
-        barrier()
-        for c in ctxs:
-            c.reset_counters()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local) as clocks:
-            barrier()
-            p0.record()
-            run_all(args.steps, p0)
-            p1.record()
-            barrier()
-        tp = torch.tensor([p0.elapsed_time(p1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-        ms_step = float(tp.item()) / args.steps
-        gpu_launches = int(sum(sum(c.launches_by_kernel().values()) for c in ctxs))
-        for c in ctxs[1:]:
-            c.close()
-        del decs
     value = world * n_vox / (ms_step * 1e-3) / 1e9
 
     # ---- roofline of the dominant kernel (per launch, measured live)
@@ -442,11 +385,10 @@ def run_b200(args):
                 "workload": WORKLOAD if shape == SHAPE else f"reduced tile 16x{shape[0]}x{shape[1]}x{shape[2]} uint16",
                 "step": "m3d_decode_label (gate + search + CCL) + m3d_features on the HBM-resident stack",
                 "lowpass": "off (north_star kernel sequence)", "parallelism": f"tile-sharded x{world}",
-                "pipeline_depth": depth,
                 "l2": f"input {stack_bytes(shape) / 1e9:.1f} GB per step >> 126 MB L2",
                 "foreground_voxels": n_fg, "features": int(n_feat),
             },
-            "serial": serial, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
             "extras": extras,
             "clocks": clocks.summary(),
         }
@@ -472,7 +414,6 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=1, help="streams per GPU in the throughput measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -720,14 +720,15 @@ class PixelDecoder:
         df["tile_y"] = np.round(df["y"], 0).astype(int)
         df["tile_x"] = np.round(df["x"], 0).astype(int)
         pts = df[["z", "y", "x"]].to_numpy(dtype=np.float64, copy=True)
-        # _warp_pixel over all rows at once (same float64 operations per row, PD:3134-3141)
+        # _warp_pixel over all rows at once (PD:3134-3141): p*spacing+origin -> camera_to_stage -> global
+        # affine, float64 like the reference's per-row `A @ [p, 1]`
         phys = pts * self._spacing + self._origin
-        cam = np.asarray(self._camera_to_stage_affine)
+        cam = np.asarray(self._camera_to_stage_affine, dtype=np.float64)
+        aff = np.asarray(self._affine, dtype=np.float64)
         hom = np.concatenate([phys, np.ones((phys.shape[0], 1))], axis=1)
-        phys = np.stack([(cam @ h)[:-1] for h in hom]) if len(hom) else phys
+        phys = (hom @ cam.T)[:, :3]
         hom = np.concatenate([phys, np.ones((phys.shape[0], 1))], axis=1)
-        aff = np.array(self._affine)
-        glob = np.stack([(aff @ h)[:-1] for h in hom]) if len(hom) else phys
+        glob = (hom @ aff.T)[:, :3]
         df["global_z"] = np.round(glob[:, 0], 2)
         df["global_y"] = np.round(glob[:, 1], 2)
         df["global_x"] = np.round(glob[:, 2], 2)
