@@ -5,8 +5,9 @@ from pathlib import Path
 import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
-if str(ROOT) not in sys.path:
-    sys.path.insert(0, str(ROOT))
+for _p in (ROOT, ROOT / "tests", ROOT / "tests" / "golden"):
+    if str(_p) not in sys.path:
+        sys.path.insert(0, str(_p))
 
 
 def pytest_configure(config):

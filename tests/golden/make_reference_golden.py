@@ -1,0 +1,138 @@
+"""Golden vectors produced by the REFERENCE's own code (``/root/reference``, unmodified).
+
+    python tests/golden/make_reference_golden.py        # writes tests/golden/reference_*.npz
+
+``reference_shims.py`` answers the reference's CuPy / cuVS / cuCIM / scikit-image calls with
+NumPy / SciPy so ``merfish3danalysis.PixelDecoder.PixelDecoder`` runs here without a GPU.  Each
+fixture stores the seeded inputs and everything ``decode_one_tile(return_results=True)`` returned
+plus the transcript table, so the oracle (CPU tests) and the CUDA path (GPU tests) are compared
+with what the reference computed, not with each other only.  ``/root/reference`` is needed to
+(re)generate, never to run the tests.
+"""
+from __future__ import annotations
+
+import shutil
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+sys.path.insert(0, str(ROOT / "tests" / "golden"))
+
+import cases  # noqa: E402
+import reference_shims as rs  # noqa: E402
+from scenarios import SCENARIOS, scenario_inputs  # noqa: E402
+from merfish3d_analysis_b200.datastore import ArrayDataStore  # noqa: E402
+
+OUT = ROOT / "tests" / "golden"
+
+def table_arrays(df):
+    num = [c for c in df.columns if c != "gene_id"]
+    return dict(
+        table_columns=np.array(num), table=df[num].to_numpy(dtype=np.float64),
+        gene_id=np.array([str(g) for g in df["gene_id"]]),
+    )
+
+
+def run_tile_scenario(name, sc, RefPD):
+    df_cb, cb, stack, pred, bkg, nrm, excluded = scenario_inputs(sc)
+    tmp = Path(tempfile.mkdtemp())
+    try:
+        ds = ArrayDataStore(tmp / "qi2labdatastore", codebook=df_cb, microscope_type=sc.get("microscope", "3D"))
+        ds.add_tile(stack, predictors=pred, stage_origin_zyx_um=sc.get("origin"))
+        ds.save_decode_normalization_vectors(None, "global", nrm, bkg)
+        dec = RefPD(ds, merfish_bits=16, verbose=0, z_range=sc.get("z_range"), excluded_gene_ids=excluded)
+        with rs.pandas2_semantics():
+            res = dec.decode_one_tile(
+                0, return_results=True, lowpass_sigma=sc["lowpass"], minimum_pixels=sc["min_px"],
+                magnitude_threshold=sc.get("mag"), normalization_method=sc["norm"],
+            )
+        df = dec._df_barcodes
+        out = dict(
+            stack=stack, bkg=bkg, nrm=nrm,
+            image=np.asarray(res[0], dtype=np.float32), scaled=np.asarray(res[1]), magnitude=np.asarray(res[2]),
+            distance=np.asarray(res[3]), decoded=np.asarray(res[4]),
+            pixel_threshold=np.float64(dec._pixel_assignment_threshold),
+            transcript_threshold=np.float64(dec._transcript_distance_threshold),
+            excluded=np.array([] if excluded is None else excluded, dtype=str),
+            **table_arrays(df),
+        )
+        np.savez_compressed(OUT / f"reference_{name}.npz", **out)
+        print(f"{name}: {len(df)} transcripts, {int((out['decoded'] >= 0).sum())} decoded voxels")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def run_optimizer_scenario(RefPD):
+    """optimize_normalization_by_decoding (PD:4581-4757) over 3 tiles x 3 iterations, in-process.
+
+    The reference spawns one process per GPU (PD:142-204); here the worker function runs
+    synchronously in this process (same code, same order) because the stand-in modules live
+    in this interpreter.  The datastore is re-opened by path inside the worker as upstream."""
+    import torch
+
+    import merfish3danalysis.PixelDecoder as refmod
+
+    df_cb, cb = cases.codebook16()
+    tmp = Path(tempfile.mkdtemp())
+    try:
+        ds = ArrayDataStore(tmp / "qi2labdatastore", codebook=df_cb)
+        stacks = []
+        for t in range(3):
+            st = cases.small_stack(cb["matrix"], shape=(8, 40, 48), seed=300 + t, density=5e-3)
+            stacks.append(st)
+            ds.add_tile(st, persist=True)
+
+        class _Done:
+            exitcode = 0
+            pid = 0
+
+            def join(self):
+                return None
+
+        def run_inline(*, target, args, physical_gpu_id):
+            with rs.pandas2_semantics():
+                target(*args)
+            return _Done()
+
+        saved = (refmod._start_gpu_worker_process, refmod.qi2labDataStore, torch.cuda.set_device)
+        refmod._start_gpu_worker_process = run_inline
+        refmod.qi2labDataStore = lambda path, validate=False: ArrayDataStore(path)
+        torch.cuda.set_device = lambda *_a, **_k: None
+        try:
+            dec = RefPD(ds, merfish_bits=16, verbose=0)
+            with rs.pandas2_semantics():
+                dec.optimize_normalization_by_decoding(
+                    n_iterations=3, minimum_pixels=4, lowpass_sigma=None, magnitude_threshold=(0.9, 10.0),
+                    tile_indices=[0, 1, 2],
+                )
+        finally:
+            refmod._start_gpu_worker_process, refmod.qi2labDataStore, torch.cuda.set_device = saved
+        ds2 = ArrayDataStore(tmp / "qi2labdatastore")
+        g = ds2.load_decode_normalization_vectors(None, "global")
+        it = ds2.load_decode_normalization_vectors(None, "iterative")
+        np.savez_compressed(
+            OUT / "reference_optimizer.npz", stacks=np.stack(stacks),
+            global_normalization=np.asarray(g[0], dtype=np.float32), global_background=np.asarray(g[1], dtype=np.float32),
+            iterative_normalization=np.asarray(it[0], dtype=np.float32),
+            iterative_background=np.asarray(it[1], dtype=np.float32),
+        )
+        print("optimizer: global", np.asarray(g[0])[:4], np.asarray(g[1])[:4], "iterative", np.asarray(it[0])[:4],
+              np.asarray(it[1])[:4])
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def main():
+    RefPD = rs.load_reference_pixeldecoder()
+    for name, sc in SCENARIOS.items():
+        run_tile_scenario(name, sc, RefPD)
+    run_optimizer_scenario(RefPD)
+
+
+if __name__ == "__main__":
+    main()

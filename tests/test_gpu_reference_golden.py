@@ -1,0 +1,67 @@
+"""The CUDA path (``PixelDecoder`` over the C ABI) against golden vectors produced by the
+REFERENCE's own code (``tests/golden/reference_*.npz``, see ``make_reference_golden.py``):
+result images bit-exact, codeword assignments / areas / ids bit-exact, table floats within the
+north-star tolerance (1e-5 relative)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import cases
+from scenarios import SCENARIOS, scenario_inputs
+from test_cpu_reference_golden import compare_with_reference_table, golden_table
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+REL = 1e-5
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_cuda_path_equals_reference_golden(tmp_path, name):
+    from merfish3d_analysis_b200.datastore import ArrayDataStore
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    sc = SCENARIOS[name]
+    g = np.load(GOLDEN / f"reference_{name}.npz")
+    df_cb, _cb, stack, pred, bkg, nrm, excluded = scenario_inputs(sc)
+    np.testing.assert_array_equal(stack, g["stack"])  # the seeded inputs are the fixture's inputs
+    ds = ArrayDataStore(tmp_path / "qi2labdatastore", codebook=df_cb, microscope_type=sc.get("microscope", "3D"))
+    ds.add_tile(stack, predictors=pred, stage_origin_zyx_um=sc.get("origin"))
+    ds.save_decode_normalization_vectors(None, "global", nrm, bkg)
+    ref = golden_table(g)
+    kw = dict(lowpass_sigma=sc["lowpass"], minimum_pixels=sc["min_px"], magnitude_threshold=sc.get("mag"),
+              normalization_method=sc["norm"])
+    dec = PixelDecoder(ds, merfish_bits=16, verbose=0, z_range=sc.get("z_range"), excluded_gene_ids=excluded)
+    image, scaled, magnitude, distance, decoded = dec.decode_one_tile(0, return_results=True, **kw)
+    np.testing.assert_array_equal(image, g["image"])
+    np.testing.assert_array_equal(decoded, g["decoded"])
+    np.testing.assert_array_equal(magnitude, g["magnitude"])
+    np.testing.assert_array_equal(distance, g["distance"])
+    np.testing.assert_array_equal(scaled, g["scaled"])
+    compare_with_reference_table(dec.decoded_barcodes, ref, rel=REL)
+    # production path: gate + search + fused labelling, no result images
+    dec2 = PixelDecoder(ds, merfish_bits=16, verbose=0, z_range=sc.get("z_range"), excluded_gene_ids=excluded)
+    assert dec2.decode_one_tile(0, **kw) is None
+    np.testing.assert_array_equal(dec2.decoded_image, g["decoded"])
+    compare_with_reference_table(dec2.decoded_barcodes, ref, rel=REL)
+
+
+def test_cuda_optimizer_equals_reference_golden(tmp_path):
+    from merfish3d_analysis_b200.datastore import ArrayDataStore
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    g = np.load(GOLDEN / "reference_optimizer.npz")
+    df_cb, _cb = cases.codebook16()
+    ds = ArrayDataStore(tmp_path / "qi2labdatastore", codebook=df_cb)
+    for st in g["stacks"]:
+        ds.add_tile(st)
+    dec = PixelDecoder(ds, merfish_bits=16, verbose=0)
+    dec.optimize_normalization_by_decoding(n_iterations=3, minimum_pixels=4, lowpass_sigma=None,
+                                           magnitude_threshold=(0.9, 10.0), tile_indices=[0, 1, 2])
+    g_n, g_b = ds.load_decode_normalization_vectors(None, "global")
+    i_n, i_b = ds.load_decode_normalization_vectors(None, "iterative")
+    np.testing.assert_array_equal(g_n, g["global_normalization"])
+    np.testing.assert_array_equal(g_b, g["global_background"])
+    np.testing.assert_array_equal(i_n, g["iterative_normalization"])
+    np.testing.assert_array_equal(i_b, g["iterative_background"])
