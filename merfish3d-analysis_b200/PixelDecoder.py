@@ -695,31 +695,33 @@ class PixelDecoder:
         dec = tab[:, _COL_DEC].astype(np.int32)
         tab = tab[dec >= 0]
         dec = dec[dec >= 0]
-        df = pd.DataFrame(
-            {"area": tab[:, _COL_AREA], "z": tab[:, _COL_CZ], "y": tab[:, _COL_CY], "x": tab[:, _COL_CX]}
-        )
-        bit_means = tab[:, M3D_TABLE_FIXED_COLS : M3D_TABLE_FIXED_COLS + nb]
+        # columns are assembled as plain arrays and the frame is built once (a per-column
+        # DataFrame insert costs ~0.5 ms; the table has 40+ columns)
+        col: dict[str, np.ndarray] = {"area": tab[:, _COL_AREA]}
+        z = tab[:, _COL_CZ]
+        if self._z_crop:
+            z = self._decoded_z_to_source_z(z)
+        col["z"], col["y"], col["x"] = z, tab[:, _COL_CY], tab[:, _COL_CX]
+        bit_means = np.ascontiguousarray(tab[:, M3D_TABLE_FIXED_COLS : M3D_TABLE_FIXED_COLS + nb])
         for i in range(nb):
-            df[f"bit{i + 1:02d}_mean_intensity"] = bit_means[:, i]
+            col[f"bit{i + 1:02d}_mean_intensity"] = bit_means[:, i]
         ev = self._inertia_eigvals(tab) if tab.shape[0] else np.zeros((0, 3))
         for k in range(3):
-            df[f"inertia_tensor_eigvals-{k}"] = ev[:, k]
-        df["distance_min"] = tab[:, _COL_DMIN]
-        df["magnitude_mean"] = tab[:, _COL_MAGMEAN]
-        df["barcode_id"] = dec + 1
-        df["gene_id"] = [self._gene_ids[i] for i in dec]
-        df["tile_idx"] = self._tile_idx
+            col[f"inertia_tensor_eigvals-{k}"] = ev[:, k]
+        col["distance_min"] = tab[:, _COL_DMIN]
+        col["magnitude_mean"] = tab[:, _COL_MAGMEAN]
+        col["barcode_id"] = dec + 1
+        col["gene_id"] = np.asarray(self._gene_ids, dtype=object)[dec]
+        col["tile_idx"] = np.full(dec.shape[0], self._tile_idx)
         codebook_bool = self._codebook_matrix.astype(bool, copy=False)
         on0 = np.argsort(~codebook_bool, axis=1)[:, :4].astype(np.int32)  # PD:3101, verbatim
         on_sel = (on0 + 1)[dec]
         for k in range(4):
-            df[f"on_bit_{k + 1}"] = on_sel[:, k]
-        if self._z_crop:
-            df["z"] = self._decoded_z_to_source_z(df["z"])
-        df["tile_z"] = np.round(df["z"], 0).astype(int)
-        df["tile_y"] = np.round(df["y"], 0).astype(int)
-        df["tile_x"] = np.round(df["x"], 0).astype(int)
-        pts = df[["z", "y", "x"]].to_numpy(dtype=np.float64, copy=True)
+            col[f"on_bit_{k + 1}"] = on_sel[:, k]
+        col["tile_z"] = np.round(col["z"], 0).astype(int)
+        col["tile_y"] = np.round(col["y"], 0).astype(int)
+        col["tile_x"] = np.round(col["x"], 0).astype(int)
+        pts = np.stack([col["z"], col["y"], col["x"]], axis=1).astype(np.float64)
         # _warp_pixel over all rows at once (PD:3134-3141): p*spacing+origin -> camera_to_stage -> global
         # affine, float64 like the reference's per-row `A @ [p, 1]`
         phys = pts * self._spacing + self._origin
@@ -729,16 +731,18 @@ class PixelDecoder:
         phys = (hom @ cam.T)[:, :3]
         hom = np.concatenate([phys, np.ones((phys.shape[0], 1))], axis=1)
         glob = (hom @ aff.T)[:, :3]
-        df["global_z"] = np.round(glob[:, 0], 2)
-        df["global_y"] = np.round(glob[:, 1], 2)
-        df["global_x"] = np.round(glob[:, 2], 2)
+        col["global_z"] = np.round(glob[:, 0], 2)
+        col["global_y"] = np.round(glob[:, 1], 2)
+        col["global_x"] = np.round(glob[:, 2], 2)
         total = bit_means.sum(axis=1)
         sig = np.take_along_axis(bit_means, on_sel - 1, axis=1).sum(axis=1)
-        df["signal_mean"] = sig / 4.0
-        df["bkd_mean"] = (total - sig) / float(nb - 4)
-        df["s-b_mean"] = df["signal_mean"] - df["bkd_mean"]
-        df = df[df["distance_min"] <= self._transcript_distance_threshold].reset_index(drop=True)
-        return df[cols]
+        col["signal_mean"] = sig / 4.0
+        col["bkd_mean"] = (total - sig) / float(nb - 4)
+        col["s-b_mean"] = col["signal_mean"] - col["bkd_mean"]
+        keep = col["distance_min"] <= self._transcript_distance_threshold
+        if not keep.all():
+            col = {k: v[keep] for k, v in col.items()}
+        return pd.DataFrame({c: col[c] for c in cols})
 
     # ================================================================== results / persistence
     def _save_barcodes(self) -> None:

@@ -7,24 +7,24 @@ Every function cites the reference lines it restates.  ``PD`` abbreviates
 
 Pin status
 ----------
-The reference module cannot be imported in this image (CuPy / cuCIM / cuVS /
-scikit-image are absent) and upstream ships no numeric golden
-vectors for ``_decode_pixels`` / ``_extract_barcodes``.  What IS pinned:
+PINNED against the reference's own code.  ``tests/golden/reference_shims.py`` executes
+``/root/reference/src/merfish3danalysis/PixelDecoder.py`` UNMODIFIED with its GPU wheels
+(CuPy / cupyx / cuVS / cuCIM / scikit-image, none installed here) answered by NumPy / SciPy,
+and ``tests/golden/make_reference_golden.py`` stores what it computes for seeded tiles
+(raw 3-D, low-pass + predictor weights, 2-D mode, exclusions + z crop) and for a 3-tile x
+3-iteration ``optimize_normalization_by_decoding`` run.  ``tests/test_cpu_reference_golden.py``
+requires this oracle to reproduce those fixtures: decoded / magnitude / distance / scaled images
+bit-exact, every table column identical (eigenvalues to 1e-9), normalisation vectors identical;
+one more case runs the reference live when ``/root/reference`` is present.  Also restated from
+upstream's known-answer tests: exclusion semantics, ``_warp_pixel``, codebook thresholds
+(``tests/test_optimization_codeword_exclusions.py:114-120``,
+``tests/test_pixeldecoder_coordinates.py:6-41``, ``PD:778-791``).
 
-* low-pass: ``scipy.ndimage.gaussian_filter`` itself is the oracle (the SciPy
-  family routine the reference's ``cupyx.scipy.ndimage.gaussian_filter``
-  mirrors); ``correlate1d_restated`` is checked bit-for-bit against it.
-* exclusion semantics, ``_warp_pixel`` and codebook thresholds are checked
-  against the upstream known-answer tests
-  (``tests/test_optimization_codeword_exclusions.py:114-120``,
-  ``tests/test_pixeldecoder_coordinates.py:6-41``, ``PD:778-791``).
-* the per-voxel decode arithmetic, CCL, regionprops and the normalisation
-  loop: **parity unpinned** at the arithmetic boundary (third-party wheels not
-  vendored).  Documented choices: direct-form fp32 Euclidean distance,
-  sequential over bits; ``remove_small_objects(max_size=m)`` removes
-  ``area <= m``; NumPy ``linear`` percentile; NumPy reduction orders for
-  ``np.mean`` (sequential over voxels for the (n, bits) case, pairwise for the
-  1-D magnitude case -- both obtained by calling NumPy itself).
+What the pin cannot reach (third-party GPU kernels, not vendored, no GPU here): cuVS computes
+the Euclidean distance in expanded form (this oracle and the stand-in use the direct form,
+float32, sequential over bits -- O(1e-7) apart, inside the north-star 1e-6 tie allowance) and
+``cupyx.scipy.ndimage.gaussian_filter`` may accumulate float32 where SciPy accumulates
+float64.  ``correlate1d_restated`` is checked bit-for-bit against SciPy.
 """
 
 from __future__ import annotations

@@ -38,3 +38,50 @@ def scenario_inputs(sc):
         genes = [g for g in df_cb["gene_id"] if not str(g).lower().startswith("blank")]
         excluded = genes[: sc["exclude"]]
     return df_cb, cb, stack, pred, bkg, nrm, excluded
+
+
+def synthetic_transcript_table(df_cb, seed: int, mode: str = "3d", n: int = 6000):
+    """Seeded decoded-transcript table for the post-decode stage: coding genes with
+    good statistics, blank genes with poor ones, duplicates across overlapping tiles (3-D radius)
+    and -- in 2-D mode -- same-gene detections split across adjacent z planes."""
+    import pandas as pd
+
+    rng = np.random.default_rng(seed)
+    genes = [str(g) for g in df_cb["gene_id"]]
+    blanks = [g for g in genes if g.lower().startswith("blank")]
+    coding = [g for g in genes if not g.lower().startswith("blank")]
+    n_blank = n // 12
+    gene = np.array(list(rng.choice(coding, n - n_blank)) + list(rng.choice(blanks, n_blank)), dtype=object)
+    blank = np.array([g.lower().startswith("blank") for g in gene])
+    area = np.where(blank, rng.integers(4, 14, n), rng.integers(6, 60, n)).astype(np.float64)
+    mag = np.where(blank, rng.normal(1.7, 0.15, n), rng.normal(2.4, 0.4, n)).astype(np.float16).astype(np.float64)
+    dist = np.where(blank, rng.uniform(0.35, 0.6, n), rng.uniform(0.05, 0.55, n)).astype(np.float16).astype(np.float64)
+    tile = rng.integers(0, 4, n)
+    vz = 0.315 if mode == "3d" else 1.5
+    z = np.round(rng.integers(0, 12, n) * vz if mode == "2d" else rng.uniform(0, 12 * vz, n), 2)
+    y = np.round(rng.uniform(0, 60, n) + (tile // 2) * 50.0, 2)
+    x = np.round(rng.uniform(0, 60, n) + (tile % 2) * 50.0, 2)
+    df = pd.DataFrame({"gene_id": gene, "area": area, "magnitude_mean": mag, "distance_min": dist,
+                       "tile_idx": tile, "global_z": z, "global_y": y, "global_x": x})
+    # cross-tile duplicates: the same molecule seen by a neighbouring tile, jittered by < 0.75 um
+    dup = df.iloc[rng.choice(n, n // 8, replace=False)].copy()
+    dup["tile_idx"] = (dup["tile_idx"] + rng.integers(1, 4, len(dup))) % 4
+    for c, s in (("global_z", 0.2), ("global_y", 0.3), ("global_x", 0.3)):
+        dup[c] = np.round(dup[c] + rng.uniform(-s, s, len(dup)), 2)
+    dup["distance_min"] = (dup["distance_min"] + rng.uniform(-0.02, 0.02, len(dup))).astype(np.float16).astype(float)
+    parts = [df, dup]
+    if mode == "2d":
+        # same tile, same gene, next plane(s), XY within one pixel: chains of 2-3 detections
+        split = df.iloc[rng.choice(n, n // 6, replace=False)].copy()
+        split["global_z"] = np.round(split["global_z"] + vz, 2)
+        for c in ("global_y", "global_x"):
+            split[c] = np.round(split[c] + rng.uniform(-0.06, 0.06, len(split)), 2)
+        split["distance_min"] = (split["distance_min"] + rng.uniform(-0.03, 0.03, len(split))).astype(
+            np.float16).astype(float)
+        chain = split.iloc[: len(split) // 3].copy()
+        chain["global_z"] = np.round(chain["global_z"] + vz, 2)
+        parts += [split, chain]
+    out = pd.concat(parts, ignore_index=True)
+    out = out.iloc[rng.permutation(len(out))].reset_index(drop=True)
+    out["gene_id"] = out["gene_id"].astype(str)
+    return out

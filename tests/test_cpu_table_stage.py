@@ -1,0 +1,81 @@
+"""Post-decode table stage: the oracle (``oracle/table_oracle.py``) against golden
+vectors produced by the reference's own ``_filter_all_barcodes_blank_fraction`` /
+``_remove_duplicates_within_tile`` / ``_remove_duplicates_in_tile_overlap`` (see
+``tests/golden/make_table_golden.py``)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import table_oracle as tor
+from scenarios import synthetic_transcript_table
+
+GOLDEN = Path(__file__).resolve().parent / "golden" / "reference_table_stage.npz"
+VOXEL = {"3d": (0.315, 0.098, 0.098), "2d": (1.5, 0.1085, 0.1085)}
+SEED = {"3d": 5150, "2d": 5151}
+
+
+def table_for(mode):
+    df_cb, cb = cases.codebook16()
+    table = synthetic_transcript_table(df_cb, seed=SEED[mode], mode=mode)
+    n_blank = sum(str(g).lower().startswith("blank") for g in cb["gene_ids"])
+    return table, n_blank, len(cb["gene_ids"])
+
+
+def oracle_chain(table, mode, blank_count, barcode_count):
+    """filter -> (2-D: within-tile collapse) -> tile-overlap de-duplication, as decode_all_tiles does
+    (PD:4849-4868).  Returns the surviving original row numbers after each step + diagnostics."""
+    rows = np.arange(len(table))
+    keep, diag = tor.blank_fraction_filter(table, blank_count, barcode_count, 0.05)
+    cur = table[keep].reset_index(drop=True)
+    rows = rows[keep]
+    steps = {"filter": rows.copy()}
+    if mode == "2d":
+        vs = VOXEL[mode]
+        drop = tor.within_tile_duplicates(cur[["global_z", "global_y", "global_x"]].to_numpy(float),
+                                          cur["tile_idx"].to_numpy(), cur["gene_id"].to_numpy(),
+                                          cur["distance_min"].to_numpy(float), vs[-1], vs[0])
+        cur, rows = cur[~drop].reset_index(drop=True), rows[~drop]
+        steps["within"] = rows.copy()
+    drop = tor.overlap_duplicates(cur[["global_z", "global_y", "global_x"]].to_numpy(float),
+                                  cur["tile_idx"].to_numpy(), cur["distance_min"].to_numpy(float), 0.75)
+    steps["overlap"] = rows[~drop]
+    return steps, diag
+
+
+@pytest.mark.parametrize("mode", ["3d", "2d"])
+def test_table_oracle_equals_reference_golden(mode):
+    g = np.load(GOLDEN)
+    table, blank_count, barcode_count = table_for(mode)
+    steps, diag = oracle_chain(table, mode, blank_count, barcode_count)
+    np.testing.assert_array_equal(diag["all_histogram"], g[f"all_histogram_{mode}"])
+    np.testing.assert_array_equal(diag["blank_histogram"], g[f"blank_histogram_{mode}"])
+    np.testing.assert_array_equal(diag["blank_fraction_histogram"], g[f"blank_fraction_histogram_{mode}"])
+    for k in ("intensity_bins", "voxel_number_bins", "vector_distance_bins"):
+        np.testing.assert_array_equal(diag[k], g[f"{k}_{mode}"])
+    np.testing.assert_array_equal(diag["threshold_sweep"].to_numpy(float), g[f"sweep_{mode}"])
+    assert diag["chosen_threshold"] == float(g[f"chosen_threshold_{mode}"])
+    assert diag["achieved_gross_misid_rate"] == float(g[f"achieved_rate_{mode}"])
+    assert bool(diag["target_reached"]) == bool(g[f"target_reached_{mode}"])
+    np.testing.assert_array_equal(steps["filter"], g[f"kept_filter_{mode}"])
+    if mode == "2d":
+        assert len(g["kept_within_2d"]) < len(g["kept_filter_2d"])
+        np.testing.assert_array_equal(steps["within"], g["kept_within_2d"])
+    assert len(g[f"kept_overlap_{mode}"]) < len(steps["filter"])
+    np.testing.assert_array_equal(steps["overlap"], g[f"kept_overlap_{mode}"])
+
+
+def test_blank_fraction_edge_cases():
+    table, blank_count, barcode_count = table_for("3d")
+    keep, diag = tor.blank_fraction_filter(table.iloc[:0], blank_count, barcode_count)
+    assert diag["reason"] == "no_transcripts" and keep.size == 0
+    keep, diag = tor.blank_fraction_filter(table, 0, barcode_count)
+    assert diag["reason"] == "no_blank_barcodes" and keep.all()
+    coding = table[~tor.is_blank(table["gene_id"])].reset_index(drop=True)
+    keep, diag = tor.blank_fraction_filter(coding, blank_count, barcode_count)
+    assert diag["reason"] == "no_blank_transcripts" and keep.all()
+    bad = table.copy()
+    bad["area"] = np.nan
+    keep, diag = tor.blank_fraction_filter(bad, blank_count, barcode_count)
+    assert diag["reason"] == "no_valid_features" and not keep.any()
