@@ -151,6 +151,36 @@ int m3d_select_hist(m3d_ctx* ctx, const float* data_dev, int64_t n, float sub, i
 int m3d_replace_above(m3d_ctx* ctx, float* data_dev, int64_t n, float threshold, float value,
                       void* stream);
 
+/* ---- post-decode transcript-table stage; rows = decoded transcripts ----
+ *
+ * _filter_all_barcodes_blank_fraction binning (PD:3656-3742): per row
+ * b_a = searchsorted(edges_a, v_a, side='right') - 1 on float32 values and float32 edges for the three
+ * feature axes (magnitude_mean, area, distance_min); rows with a non-finite feature or a bin outside
+ * [0, n_a - 2] are out of range.  Writes flat_bin_dev[i] = ravel_multi_index(b0, b1, b2) or -1 and
+ * accumulates the all-rows and blank-rows histograms ((n0-1)(n1-1)(n2-1) int32 each, caller zeroes).
+ * edges_*_host: ascending, 2..64 entries. */
+int m3d_table_hist3d(m3d_ctx* ctx, const float* v0_dev, const float* v1_dev, const float* v2_dev,
+                     const uint8_t* blank_dev, int64_t n, const float* edges0_host, int n0,
+                     const float* edges1_host, int n1, const float* edges2_host, int n2,
+                     int32_t* flat_bin_dev, int32_t* all_hist_dev, int32_t* blank_hist_dev, void* stream);
+
+/* _remove_duplicates_in_tile_overlap (PD:4137-4177).  zyx_dev = (n,3) float64 global coordinates.
+ * drop_dev[i] = 1 iff some row j of a different tile lies within `radius` (3-D Euclidean, inclusive,
+ * float64 sum-of-squares vs radius^2 like SciPy's cKDTree) and (distance_min[j], j) < (distance_min[i], i)
+ * -- the outcome of the reference's loop over query_pairs.  distance_min must not be NaN.
+ * Synchronises the stream once (coordinate bounds for the grid hash). */
+int m3d_overlap_duplicates(m3d_ctx* ctx, const double* zyx_dev, const int32_t* tile_dev,
+                           const double* distance_min_dev, int64_t n, double radius, uint8_t* drop_dev,
+                           void* stream);
+
+/* _remove_duplicates_within_tile (PD:4179-4363, 2-D decode mode).  Rows are neighbours iff same tile,
+ * same gene code, XY distance <= radius_xy and 0 < |dz| <= radius_z; per connected cluster every row but
+ * the one with the smallest (distance_min, row index) gets drop_dev[i] = 1.  gene_dev = any int32
+ * coding of gene_id equality.  Synchronises the stream once. */
+int m3d_within_tile_duplicates(m3d_ctx* ctx, const double* zyx_dev, const int32_t* tile_dev,
+                               const int32_t* gene_dev, const double* distance_min_dev, int64_t n,
+                               double radius_xy, double radius_z, uint8_t* drop_dev, void* stream);
+
 /* Capacity (entries) of the search -> regionprops record buffers; 0 = automatic
  * (max(2^20, n_vox/16)).  When the foreground exceeds it the regionprops kernel recomputes the
  * traces instead; results are identical.  Exposed so tests can force the overflow path. */

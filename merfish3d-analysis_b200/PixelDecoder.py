@@ -34,6 +34,7 @@ import numpy as np
 import pandas as pd
 
 from . import normalization as _norm
+from . import table_stage
 from ._capi import M3D_TABLE_FIXED_COLS, DecodeContext, M3dError
 
 DEFAULT_DECODE_LOWPASS_SIGMA = (3.0, 1.0, 1.0)  # PD:128
@@ -1250,51 +1251,83 @@ class PixelDecoder:
             return torch.cuda.current_device()
         return 0
 
-    def _remove_duplicates_within_tile(self, radius_xy: float, radius_z: float) -> None:
-        """PD:4179-4363 (2-D mode only): collapse same-gene detections split across adjacent z
-        planes.  Same tile, same gene, XY distance <= radius_xy, 0 < |dz| <= radius_z;
-        union-find clusters; keep the smallest ``distance_min`` (ties: first row)."""
-        from scipy.spatial import cKDTree
+    # ================================================================== post-decode table stage (8f-3)
+    def _filter_all_barcodes_blank_fraction(self, target_gross_misid_rate: float = 0.05, intensity_bins=None,
+                                            voxel_number_bins=None, vector_distance_bins=None) -> None:
+        """PD:3386-3846: blank-fraction histogram filter over (magnitude_mean, area, distance_min);
+        binning and histograms on the device (``m3d_table_hist3d``)."""
+        self._df_filtered_barcodes, self._blank_fraction_filter_results = table_stage.filter_blank_fraction(
+            self._ctx(self._local_gpu()), self._df_barcodes_loaded, self._blank_count, self._barcode_count,
+            target_gross_misid_rate, intensity_bins, voxel_number_bins, vector_distance_bins,
+        )
+        self._barcodes_filtered = True
+        if self._verbose > 1:
+            print("blank fraction filter diagnostics:")
+            for key, value in self._blank_fraction_filter_results.items():
+                if isinstance(value, (float, int, str, bool)):
+                    print(f"{key}: {value}")
+                else:
+                    print(f"{key}: {type(value)} with shape {getattr(value, 'shape', 'N/A')}")
 
-        df = self._df_barcodes_loaded
-        if df is None or len(df) == 0:
+    @staticmethod
+    def _calculate_lr_fdr(df: pd.DataFrame, threshold: float, blank_count: int, barcode_count: int,
+                          verbose: bool = False) -> float:
+        """PD:3849-3905."""
+        return table_stage.calculate_lr_fdr(df, threshold, blank_count, barcode_count)
+
+    def _filter_all_barcodes_LR(self, lr_fdr_target: float = 0.05) -> None:
+        """PD:3907-4058 (scikit-learn on the host, like the reference)."""
+        self._df_filtered_barcodes = table_stage.filter_lr(
+            self._df_barcodes_loaded, self._is_3D, self._blank_count, self._barcode_count, lr_fdr_target,
+            self._verbose,
+        )
+        self._barcodes_filtered = True
+
+    def _apply_filter_method(self, filter_method, target_gross_misid_rate: float, lr_fdr_target: float) -> None:
+        """PD:4914-4950."""
+        if filter_method == "blank_fraction":
+            self._filter_all_barcodes_blank_fraction(target_gross_misid_rate=float(target_gross_misid_rate))
             return
-        df = df.reset_index(drop=True)
-        keep = np.ones(len(df), dtype=bool)
-        for (_tile, _gene), grp in df.groupby(["tile_idx", "gene_id"], sort=False):
-            if len(grp) < 2:
-                continue
-            idx = grp.index.to_numpy()
-            xy = grp[["global_y", "global_x"]].to_numpy(dtype=float)
-            z = grp["global_z"].to_numpy(dtype=float)
-            pairs = cKDTree(xy).query_pairs(float(radius_xy), output_type="ndarray")
-            if pairs.size == 0:
-                continue
-            dz = np.abs(z[pairs[:, 0]] - z[pairs[:, 1]])
-            pairs = pairs[(dz > 0) & (dz <= float(radius_z) + 1e-9)]
-            if pairs.size == 0:
-                continue
-            parent = np.arange(len(idx))
+        if filter_method == "lr":
+            self._filter_all_barcodes_LR(lr_fdr_target=float(lr_fdr_target))
+            return
+        raise ValueError("filter_method must be one of 'blank_fraction' or 'lr'.")
 
-            def find(a):
-                while parent[a] != a:
-                    parent[a] = parent[parent[a]]
-                    a = parent[a]
-                return a
+    def _remove_duplicates_in_tile_overlap(self, radius: float = 0.75) -> None:
+        """PD:4137-4177: of two detections from different tiles within ``radius`` um (3-D), the one
+        with the larger (distance_min, row) is dropped; radius search on the device."""
+        self._df_filtered_barcodes, drop = table_stage.remove_duplicates_in_tile_overlap(
+            self._ctx(self._local_gpu()), self._df_filtered_barcodes, radius)
+        if self._verbose > 1:
+            print("Dropped points: " + str(int(drop.sum())))
 
-            for a, b in pairs:
-                ra, rb = find(a), find(b)
-                if ra != rb:
-                    parent[max(ra, rb)] = min(ra, rb)
-            roots = np.array([find(a) for a in range(len(idx))])
-            dmin = grp["distance_min"].to_numpy(dtype=float)
-            for r in np.unique(roots):
-                members = np.flatnonzero(roots == r)
-                if members.size > 1:
-                    best = members[np.argmin(dmin[members])]
-                    drop = members[members != best]
-                    keep[idx[drop]] = False
-        self._df_barcodes_loaded = df[keep].reset_index(drop=True)
+    def _remove_duplicates_within_tile(self, radius_xy: float = 0.1, radius_z: float = 0.50) -> None:
+        """PD:4179-4363 (2-D mode): collapse same-gene detections split across adjacent z planes.
+        Same tile, same gene, XY distance <= radius_xy, 0 < |dz| <= radius_z; union-find clusters on
+        the device; keep the smallest ``distance_min`` (ties: first row).  Acts on the filtered
+        table when there is one, else on the loaded table, like the reference."""
+        filtered = getattr(self, "_df_filtered_barcodes", None) is not None
+        df = self._df_filtered_barcodes if filtered else getattr(self, "_df_barcodes_loaded", None)
+        if df is None or df.empty or len(df) < 2:
+            return
+        out, drop = table_stage.remove_duplicates_within_tile(self._ctx(self._local_gpu()), df, radius_xy, radius_z)
+        if self._verbose > 1:
+            print("Dropped points: " + str(int(drop.sum())))
+        if filtered:
+            self._df_filtered_barcodes = out
+        else:
+            self._df_barcodes_loaded = out
+
+    def _assign_cells(self) -> None:
+        """PD:4076-4135.  Needs Cellpose ImageJ ROIs (``segmentation/cellpose/imagej_rois/
+        global_coords_rois.zip``); like the reference, a missing file is reported and skipped.
+        Reading ROI archives (roifile / shapely / rtree upstream) is outside this build."""
+        roi = Path(self._datastore._datastore_path) / "segmentation" / "cellpose" / "imagej_rois" / \
+            "global_coords_rois.zip"
+        if not roi.exists():
+            print(f"Failed to read ROIs: [Errno 2] No such file or directory: '{roi}'")
+            return
+        raise NotImplementedError("cell assignment from ImageJ ROI archives is outside this build (SURVEY 8f-3)")
 
     def decode_all_tiles(
         self,
@@ -1313,9 +1346,8 @@ class PixelDecoder:
         """PD:4759-4870, decode stage: every tile -> ``decoded/<tile>_decoded_features.parquet``.
 
         Tiles are sharded in contiguous chunks over GPUs (ranks or local devices) with no
-        data-path collective.  The downstream table filters (blank-fraction / LR, overlap
-        de-duplication, cell assignment: SURVEY 8f-3) are not part of this build; the pooled
-        unfiltered table is left in ``_df_barcodes_loaded``."""
+        data-path collective; then the pooled table stage (PD:4849-4870): blank-fraction / LR
+        filter, de-duplication, optional cell assignment, ``all_tiles_filtered_decoded_features``."""
         if self._num_gpus < 1:
             raise RuntimeError("No GPUs allocated.")
         if magnitude_threshold is None:
@@ -1342,6 +1374,29 @@ class PixelDecoder:
         self._load_all_barcodes()
         if self._verbose >= 1:
             print(f"Number of loaded barcodes: {len(self._df_barcodes_loaded)}")
+        rank, _world, _dist = self._dist()
+        if rank != 0:  # the pooled table stage runs once (the reference runs it in the parent process)
+            self._barrier()
+            return
+        self._finish_filtering(assign_to_cells, duplicate_radius_xy, duplicate_radius_z, filter_method,
+                               target_gross_misid_rate, lr_fdr_target, overlap=len(all_tiles) > 1)
+        self._barrier()
+
+    def _finish_filtering(self, assign_to_cells, duplicate_radius_xy, duplicate_radius_z, filter_method,
+                          target_gross_misid_rate, lr_fdr_target, overlap: bool) -> None:
+        """PD:4849-4870: filter -> (2-D) within-tile collapse -> tile-overlap de-duplication ->
+        cell assignment -> ``all_tiles_filtered_decoded_features``."""
+        self._apply_filter_method(filter_method, float(target_gross_misid_rate), float(lr_fdr_target))
+        if not self._is_3D:
+            vs = self._datastore.voxel_size_zyx_um
+            radius_xy = vs[-1] if duplicate_radius_xy is None else float(duplicate_radius_xy)
+            radius_z = vs[0] if duplicate_radius_z is None else float(duplicate_radius_z)
+            self._remove_duplicates_within_tile(radius_xy=radius_xy, radius_z=radius_z)
+        if overlap:
+            self._remove_duplicates_in_tile_overlap()
+        if assign_to_cells:
+            self._assign_cells()
+        self._save_barcodes()
 
     @staticmethod
     def _validate_filter_configuration(filter_method, target_gross_misid_rate, lr_fdr_target) -> None:
@@ -1363,9 +1418,40 @@ class PixelDecoder:
             return
         raise ValueError("filter_method must be one of 'blank_fraction' or 'lr'.")
 
-    def optimize_filtering(self, *args, **kwargs) -> None:
-        """PD:4952-5029 re-filters saved tables on the CPU; outside the hot path (8f-3)."""
-        raise NotImplementedError("transcript filtering is the 'next' row 8f-3, not part of this build")
+    def optimize_filtering(
+        self,
+        assign_to_cells: bool = True,
+        duplicate_radius_xy: float | None = None,
+        duplicate_radius_z: float | None = None,
+        filter_method: Literal["blank_fraction", "lr"] = "blank_fraction",
+        target_gross_misid_rate: float = 0.05,
+        lr_fdr_target: float = 0.05,
+    ) -> None:
+        """PD:4952-5029: re-apply the downstream filters to previously decoded tiles
+        (``decoded/<tile>_decoded_features.parquet``)."""
+        if self._verbose >= 1:
+            print("reprocess existing: load decoded transcripts")
+        self._load_tile_decoding = True
+        self._load_all_barcodes()
+        if self._verbose >= 1:
+            print(f"Number of loaded barcodes: {len(self._df_barcodes_loaded)}")
+        self._load_tile_decoding = False
+        self._validate_filter_configuration(filter_method, float(target_gross_misid_rate), float(lr_fdr_target))
+        n_tiles = len(self._datastore.tile_ids)
+        self._apply_filter_method(filter_method, float(target_gross_misid_rate), float(lr_fdr_target))
+        if n_tiles or not self._is_3D:  # PD:5002-5019: 2-D collapses within tiles, 3-D de-duplicates overlaps
+            if not self._is_3D:
+                vs = self._datastore.voxel_size_zyx_um
+                radius_xy = vs[-1] if duplicate_radius_xy is None else float(duplicate_radius_xy)
+                radius_z = vs[0] if duplicate_radius_z is None else float(duplicate_radius_z)
+                self._remove_duplicates_within_tile(radius_xy=radius_xy, radius_z=radius_z)
+            else:
+                self._remove_duplicates_in_tile_overlap()
+        if assign_to_cells:
+            self._assign_cells()
+        self._save_barcodes()
+        if self._verbose >= 1:
+            print(f"Number of retained barcodes: {len(self._df_filtered_barcodes)}")
 
 
 __all__ = ["PixelDecoder", "M3dError"]

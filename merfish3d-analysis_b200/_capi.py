@@ -78,6 +78,20 @@ SIGNATURES = {
     "m3d_replace_above": (
         C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p]
     ),
+    "m3d_table_hist3d": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int,
+         C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "m3d_overlap_duplicates": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p],
+    ),
+    "m3d_within_tile_duplicates": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double,
+         C.c_void_p, C.c_void_p],
+    ),
     "m3d_set_sparse_capacity": (C.c_int, [C.c_void_p, C.c_int64]),
     "m3d_launch_count": (C.c_int64, [C.c_void_p]),
     "m3d_kernel_name": (C.c_char_p, [C.c_int]),
@@ -373,6 +387,57 @@ class DecodeContext:
                                         float(value), _stream(self.device)),
             "m3d_replace_above",
         )
+
+    # ------------------------------------------------------------------ post-decode table stage
+    def table_hist3d(self, v0, v1, v2, blank, edges0, edges1, edges2):
+        """Row bins + all / blank histograms of the blank-fraction filter (PD:3656-3742).
+        v*: float32 device vectors, blank: uint8 device vector, edges*: float32 host arrays.
+        Returns (flat_bin int32 (n,), all_hist int32, blank_hist int32) device tensors."""
+        import torch
+
+        n = int(v0.numel())
+        es = [np.ascontiguousarray(e, dtype=np.float32) for e in (edges0, edges1, edges2)]
+        shape = tuple(int(e.size) - 1 for e in es)
+        flat = torch.empty(n, dtype=torch.int32, device=self.device)
+        all_h = torch.zeros(shape, dtype=torch.int32, device=self.device)
+        blank_h = torch.zeros(shape, dtype=torch.int32, device=self.device)
+        _check(
+            self._lib.m3d_table_hist3d(
+                self._h, _ptr(v0), _ptr(v1), _ptr(v2), _ptr(blank), n,
+                es[0].ctypes.data_as(C.c_void_p), int(es[0].size), es[1].ctypes.data_as(C.c_void_p), int(es[1].size),
+                es[2].ctypes.data_as(C.c_void_p), int(es[2].size), _ptr(flat), _ptr(all_h), _ptr(blank_h),
+                _stream(self.device),
+            ),
+            "m3d_table_hist3d",
+        )
+        return flat, all_h, blank_h
+
+    def overlap_duplicates(self, zyx, tile, distance_min, radius: float):
+        """uint8 drop flags of ``_remove_duplicates_in_tile_overlap`` (PD:4137-4177)."""
+        import torch
+
+        n = int(tile.numel())
+        drop = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        _check(
+            self._lib.m3d_overlap_duplicates(self._h, _ptr(zyx), _ptr(tile), _ptr(distance_min), n, float(radius),
+                                             _ptr(drop), _stream(self.device)),
+            "m3d_overlap_duplicates",
+        )
+        return drop
+
+    def within_tile_duplicates(self, zyx, tile, gene, distance_min, radius_xy: float, radius_z: float):
+        """uint8 drop flags of ``_remove_duplicates_within_tile`` (PD:4179-4363)."""
+        import torch
+
+        n = int(tile.numel())
+        drop = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        _check(
+            self._lib.m3d_within_tile_duplicates(self._h, _ptr(zyx), _ptr(tile), _ptr(gene), _ptr(distance_min), n,
+                                                 float(radius_xy), float(radius_z), _ptr(drop),
+                                                 _stream(self.device)),
+            "m3d_within_tile_duplicates",
+        )
+        return drop
 
     def set_sparse_capacity(self, entries: int) -> None:
         _check(self._lib.m3d_set_sparse_capacity(self._h, int(entries)), "m3d_set_sparse_capacity")

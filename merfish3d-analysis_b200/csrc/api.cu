@@ -21,7 +21,8 @@ static const char* const kKernelNames[KF_COUNT] = {
     "decode_gate_kernel",  "decode_search_kernel", "decode_dense_kernel", "ccl_collect_kernel",
     "ccl_init_kernel",     "ccl_merge_kernel",    "ccl_compress_kernel", "ccl_select_kernel",
     "cub_radix_sort",      "ccl_assign_kernel",   "cub_exclusive_sum",   "ccl_scatter_kernel",
-    "ccl_interface_kernel",   "features_kernel",     "select_hist_kernel",  "replace_above_kernel", "warp_affine_kernel"};
+    "ccl_interface_kernel",   "features_kernel",     "select_hist_kernel",  "replace_above_kernel", "warp_affine_kernel",
+    "table_hist3d_kernel", "table_grid_kernels", "table_overlap_kernel", "table_within_kernels"};
 
 DecodeParams m3d_ctx::params() const {
     DecodeParams P;

@@ -49,6 +49,10 @@ enum M3dKernel {
     KF_SELECT_HIST,
     KF_REPLACE_ABOVE,
     KF_WARP_AFFINE,
+    KF_TABLE_HIST,
+    KF_TABLE_GRID,
+    KF_TABLE_OVERLAP,
+    KF_TABLE_WITHIN,
     KF_COUNT
 };
 
