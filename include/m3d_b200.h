@@ -181,6 +181,20 @@ int m3d_within_tile_duplicates(m3d_ctx* ctx, const double* zyx_dev, const int32_
                                const int32_t* gene_dev, const double* distance_min_dev, int64_t n,
                                double radius_xy, double radius_z, uint8_t* drop_dev, void* stream);
 
+/* _add_on_bit_weighted_centroids / _plane_wise_weighted_centroid_statistics (PD:2701-2906):
+ * per component and per ON bit of its codeword, over the label image dilated along z by a
+ * `z_support`-plane maximum window: sums of w, w*z, w*y, w*x with w = max(float32(intensity), 0)
+ * (float64 accumulators; w*y and w*x are float32 products like the reference) and, over the undilated
+ * labels, the float32 peak of w.  labels_dev = ids + 1 from m3d_label / m3d_decode_label ((z,y,x) int32;
+ * <= 0 = background); label_code_dev[l] = codeword row of label l (int16, minlength entries, < 0 = skip).
+ * sums_dev = (minlength, n_bits, 4) float64 {w, wz, wy, wx}; peak_dev = (minlength, n_bits) float32;
+ * both are zeroed by the call; entries of bits that are off in the label's codeword stay zero (the
+ * reference never reads them).  One pass for all bits.  float64 atomics: equal to the reference's raster
+ * bincount to round-off, not bit-for-bit. */
+int m3d_centroid_statistics(m3d_ctx* ctx, const int32_t* labels_dev, const void* stack_dev, int dtype,
+                            const int64_t dims[3], int z_support, const int16_t* label_code_dev,
+                            int64_t minlength, double* sums_dev, float* peak_dev, void* stream);
+
 /* Capacity (entries) of the search -> regionprops record buffers; 0 = automatic
  * (max(2^20, n_vox/16)).  When the foreground exceeds it the regionprops kernel recomputes the
  * traces instead; results are identical.  Exposed so tests can force the overflow path. */

@@ -22,6 +22,7 @@ transcript filters / de-duplication / cell assignment, chromatic-affine estimati
 from __future__ import annotations
 
 import hashlib
+from dataclasses import dataclass
 import shutil
 import tempfile
 import warnings
@@ -42,6 +43,16 @@ DEFAULT_DECODE_MAGNITUDE_THRESHOLD = (1.5, 10.0)  # PD:129
 DEFAULT_2D_MINIMUM_PIXELS = 7.0  # PD:130
 DEFAULT_3D_MINIMUM_PIXELS = 16.0  # PD:131
 MAXIMUM_PIXELS = 500  # PD:2909
+_CENTROID_SUFFIXES = ("center_z", "center_y", "center_x", "intensity_sum", "intensity_peak", "voxel_count")
+
+
+@dataclass(frozen=True)
+class ChromaticAffineEstimationConfig:
+    """PD:43-68.  Only the two centroid-collection fields are consumed by this build
+    (``_add_on_bit_weighted_centroids``); the estimator that uses the rest is outside the hot path."""
+
+    centroid_z_support: int = 7
+    centroid_weight_epsilon: float = 1e-6
 
 # feature-table columns written by m3d_features (include/m3d_b200.h)
 _COL_FIRST, _COL_AREA, _COL_DEC = 0, 1, 2
@@ -86,7 +97,7 @@ class PixelDecoder:
             raise ValueError("decode_mode must be one of 'auto', '2d', or '3d'.")
         self._decode_mode = decode_mode
         self._estimate_chromatic_affines = bool(estimate_chromatic_affines)
-        self._chromatic_affine_config = chromatic_affine_config
+        self._chromatic_affine_config = chromatic_affine_config or ChromaticAffineEstimationConfig()
         if decode_mode == "auto":
             effective = "2d" if self._datastore.microscope_type == "2D" else "3d"
         else:
@@ -630,7 +641,11 @@ class PixelDecoder:
         else:
             # production path: the search kernel hands its foreground list to the labelling stage
             min_px, max_px = self._fuse_label_args
-            st["n_features"] = ctx.decode_label(stack, st["decoded"], not self._is_3D, float(min_px), int(max_px))
+            st["labels"] = None
+            if self._wants_chromatic_centroids():
+                st["labels"] = torch.empty(shape, dtype=torch.int32, device=ctx.device)
+            st["n_features"] = ctx.decode_label(stack, st["decoded"], not self._is_3D, float(min_px), int(max_px),
+                                                labels=st["labels"])
 
     @staticmethod
     def _warp_pixel(pixel_space_point, spacing, origin, affine, camera_to_stage_affine=None):
@@ -652,11 +667,41 @@ class PixelDecoder:
         st = self._device_state[gpu_id]
         ctx = self._ctx(gpu_id)
         n = st.get("n_features")
-        if n is None:
-            n = ctx.label(st["decoded"], not self._is_3D, float(minimum_pixels), int(maximum_pixels))
+        labels = st.get("labels")
+        chroma = self._wants_chromatic_centroids()
+        if n is None or (chroma and labels is None):
+            if chroma:
+                import torch
+
+                labels = torch.empty(tuple(st["decoded"].shape), dtype=torch.int32, device=ctx.device)
+            n = ctx.label(st["decoded"], not self._is_3D, float(minimum_pixels), int(maximum_pixels), labels=labels)
         table = ctx.features(st["stack"], st["decoded"], self._optimize_normalization_weights, n)
+        centroid_stats = None
+        if chroma and n > 0:
+            centroid_stats = self._chromatic_centroid_statistics(ctx, st["stack"], labels, table)
         tab = table.cpu().numpy()
-        self._df_barcodes = self._annotate_table(tab)
+        self._df_barcodes = self._annotate_table(tab, centroid_stats)
+
+    def _wants_chromatic_centroids(self) -> bool:
+        """PD:3117-3125: per-on-bit centroids are collected only inside the optimiser."""
+        return bool(self._optimize_normalization_weights and self._collect_chromatic_centroids)
+
+    def _centroid_config(self) -> tuple[int, float]:
+        """(centroid_z_support, centroid_weight_epsilon) of ChromaticAffineEstimationConfig (PD:67-68)."""
+        cfg = self._chromatic_affine_config
+        return (int(getattr(cfg, "centroid_z_support", 7)), float(getattr(cfg, "centroid_weight_epsilon", 1e-6)))
+
+    def _chromatic_centroid_statistics(self, ctx, stack, labels, table):
+        """PD:2742-2790 on the device, all bits in one pass (``m3d_centroid_statistics``)."""
+        import torch
+
+        z_support = min(self._centroid_config()[0], int(labels.shape[0]))
+        if z_support % 2 == 0:
+            z_support -= 1
+        code = torch.full((table.shape[0] + 1,), -1, dtype=torch.int16, device=ctx.device)
+        code[1:] = table[:, _COL_DEC].to(torch.int16)
+        sums, peak = ctx.centroid_statistics(labels, stack, z_support, code)
+        return sums[1:].cpu().numpy(), peak[1:].cpu().numpy()
 
     def _table_columns(self) -> list[str]:
         nb = self._n_merfish_bits
@@ -666,6 +711,8 @@ class PixelDecoder:
             + [f"inertia_tensor_eigvals-{k}" for k in range(3)]
             + ["distance_min", "magnitude_mean", "barcode_id", "gene_id", "tile_idx"]
             + [f"on_bit_{k}" for k in range(1, 5)]
+            + ([f"bit{b:02d}_{sfx}" for b in range(1, nb + 1) for sfx in _CENTROID_SUFFIXES]
+               if self._wants_chromatic_centroids() else [])
             + ["tile_z", "tile_y", "tile_x", "global_z", "global_y", "global_x"]
             + ["signal_mean", "bkd_mean", "s-b_mean"]
         )
@@ -687,13 +734,15 @@ class PixelDecoder:
         ev = np.clip(ev, 0, None)
         return np.sort(ev, axis=1)[:, ::-1]
 
-    def _annotate_table(self, tab: np.ndarray) -> pd.DataFrame:
+    def _annotate_table(self, tab: np.ndarray, centroid_stats=None) -> pd.DataFrame:
         """PD:3066-3177 vectorised over the feature rows (row order = canonical id order)."""
         nb = self._n_merfish_bits
         cols = self._table_columns()
         if tab.shape[0] == 0:
             return pd.DataFrame({c: [] for c in cols})
         dec = tab[:, _COL_DEC].astype(np.int32)
+        if centroid_stats is not None:
+            centroid_stats = tuple(a[dec >= 0] for a in centroid_stats)
         tab = tab[dec >= 0]
         dec = dec[dec >= 0]
         # columns are assembled as plain arrays and the frame is built once (a per-column
@@ -719,6 +768,8 @@ class PixelDecoder:
         on_sel = (on0 + 1)[dec]
         for k in range(4):
             col[f"on_bit_{k + 1}"] = on_sel[:, k]
+        if self._wants_chromatic_centroids():
+            col.update(self._on_bit_centroid_columns(tab, on_sel, centroid_stats))
         col["tile_z"] = np.round(col["z"], 0).astype(int)
         col["tile_y"] = np.round(col["y"], 0).astype(int)
         col["tile_x"] = np.round(col["x"], 0).astype(int)
@@ -744,6 +795,41 @@ class PixelDecoder:
         if not keep.all():
             col = {k: v[keep] for k, v in col.items()}
         return pd.DataFrame({c: col[c] for c in cols})
+
+    def _on_bit_centroid_columns(self, tab: np.ndarray, on_sel: np.ndarray, centroid_stats) -> dict:
+        """PD:2728-2831: sparse per-bit ``center_{z,y,x}``, ``intensity_sum``, ``intensity_peak`` and
+        ``voxel_count`` columns (NaN where the bit is off in the row's codeword)."""
+        nb = self._n_merfish_bits
+        n = tab.shape[0]
+        out = {f"bit{b:02d}_{sfx}": np.full(n, np.nan) for b in range(1, nb + 1) for sfx in _CENTROID_SUFFIXES}
+        if n == 0 or centroid_stats is None:
+            return out
+        sums, peak = centroid_stats
+        eps = np.float64(np.float32(self._centroid_config()[1]))
+        fallback = tab[:, _COL_CZ : _COL_CZ + 3]  # decoded-space centroid (before the z-crop offset)
+        area32 = tab[:, _COL_AREA].astype(np.float32).astype(np.float64)
+        for b in range(1, nb + 1):
+            rows = np.flatnonzero(np.any(on_sel == b, axis=1))
+            if rows.size == 0:
+                continue
+            w = sums[rows, b - 1, 0].copy()
+            centers = sums[rows, b - 1, 1:4] / np.maximum(w, eps)[:, None]
+            invalid = (~np.all(np.isfinite(centers), axis=1)) | (w <= 0)
+            centers[invalid] = fallback[rows][invalid]
+            if self._z_crop:
+                centers[:, 0] = self._decoded_z_to_source_z(centers[:, 0])
+            area = area32[rows].copy()
+            pk = peak[rows, b - 1].astype(np.float64)
+            missing = (~np.isfinite(w)) | (w <= 0)
+            area[missing] = 0.0
+            pk[~np.isfinite(pk)] = 0.0
+            w[missing] = 0.0
+            for k, sfx in enumerate(("center_z", "center_y", "center_x")):
+                out[f"bit{b:02d}_{sfx}"][rows] = centers[:, k]
+            out[f"bit{b:02d}_intensity_sum"][rows] = w
+            out[f"bit{b:02d}_intensity_peak"][rows] = pk
+            out[f"bit{b:02d}_voxel_count"][rows] = area
+        return out
 
     # ================================================================== results / persistence
     def _save_barcodes(self) -> None:
@@ -1454,4 +1540,4 @@ class PixelDecoder:
             print(f"Number of retained barcodes: {len(self._df_filtered_barcodes)}")
 
 
-__all__ = ["PixelDecoder", "M3dError"]
+__all__ = ["PixelDecoder", "ChromaticAffineEstimationConfig", "M3dError"]

@@ -92,6 +92,11 @@ SIGNATURES = {
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double,
          C.c_void_p, C.c_void_p],
     ),
+    "m3d_centroid_statistics": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.c_int64,
+         C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
     "m3d_set_sparse_capacity": (C.c_int, [C.c_void_p, C.c_int64]),
     "m3d_launch_count": (C.c_int64, [C.c_void_p]),
     "m3d_kernel_name": (C.c_char_p, [C.c_int]),
@@ -438,6 +443,25 @@ class DecodeContext:
             "m3d_within_tile_duplicates",
         )
         return drop
+
+    def centroid_statistics(self, labels, stack, z_support: int, label_code):
+        """Per-label, per-on-bit weighted centroid sums (PD:2833-2906) in one pass.
+        labels: int32 (z,y,x) ids + 1; stack: (bits,z,y,x); label_code: int16 (minlength,) codeword row
+        per label.  Returns (sums float64 (minlength, bits, 4) = {w, wz, wy, wx}, peak float32
+        (minlength, bits)) device tensors."""
+        import torch
+
+        minlength = int(label_code.numel())
+        sums = torch.empty((minlength, self.n_bits, 4), dtype=torch.float64, device=self.device)
+        peak = torch.empty((minlength, self.n_bits), dtype=torch.float32, device=self.device)
+        _check(
+            self._lib.m3d_centroid_statistics(
+                self._h, _ptr(labels), _ptr(stack), _dtype_code(stack), self._dims(labels.shape), int(z_support),
+                _ptr(label_code), minlength, _ptr(sums), _ptr(peak), _stream(self.device),
+            ),
+            "m3d_centroid_statistics",
+        )
+        return sums, peak
 
     def set_sparse_capacity(self, entries: int) -> None:
         _check(self._lib.m3d_set_sparse_capacity(self._h, int(entries)), "m3d_set_sparse_capacity")

@@ -1,0 +1,123 @@
+// centroid.cu -- per-on-bit intensity-weighted centroid statistics of decoded components
+// (PD:2701-2906 `_add_on_bit_weighted_centroids` /
+// `_plane_wise_weighted_centroid_statistics`).
+//
+// Reference: for every bit, label image dilated along z (max over a z_support window), weights
+// max(intensity, 0) in float32, per-label float64 bincount sums of w, w*z, w*y, w*x and a float32
+// running maximum over the UNdilated labels -- 16 full-volume passes, one per bit.
+// Here: one pass.  A thread owns one (y, x) column and walks z with a register ring of labels, so the
+// label image is read exactly once, coalesced along x; only the few voxels whose dilated label is
+// foreground touch the stack, and only for the on-bits of that label's codeword (the reference never
+// reads the other (label, bit) pairs).  float64 atomics: summation order differs from bincount's raster
+// order, i.e. results agree to float64 round-off (~1e-16 relative), not bit-for-bit.
+#include "common.cuh"
+
+namespace {
+
+constexpr int CT_THREADS = 128;
+constexpr int MAX_HALF = 15;  // z_support up to 31
+
+template <typename T>
+__device__ __forceinline__ float load_f32(const T* p);
+template <>
+__device__ __forceinline__ float load_f32<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float load_f32<uint16_t>(const uint16_t* p) { return (float)__ldg(p); }
+
+template <typename T>
+__global__ void __launch_bounds__(CT_THREADS)
+centroid_stats_kernel(const int32_t* __restrict__ labels, const T* __restrict__ stack, int Z, int Y, int X, int half,
+                      const int16_t* __restrict__ label_code, const uint32_t* __restrict__ cw_mask, int K, int n_bits,
+                      long long minlength, double* __restrict__ sums, float* __restrict__ peak) {
+    const long long col = (long long)blockIdx.x * CT_THREADS + threadIdx.x;
+    const long long plane = (long long)Y * X;
+    if (col >= plane) return;
+    const int y = (int)(col / X), x = (int)(col % X);
+    const size_t n_vox = (size_t)Z * plane;
+    int32_t ring[2 * MAX_HALF + 1];
+    const int W = 2 * half + 1;
+#pragma unroll
+    for (int i = 0; i < 2 * MAX_HALF + 1; ++i) ring[i] = 0;
+    // ring[(zz) % W] holds labels[zz]; preload planes 0 .. half-1
+    for (int zz = 0; zz < half && zz < Z; ++zz) ring[zz % W] = labels[(size_t)zz * plane + col];
+    for (int z = 0; z < Z; ++z) {
+        const int zin = z + half;
+        if (zin < Z) ring[zin % W] = labels[(size_t)zin * plane + col];
+        const int z0 = z - half < 0 ? 0 : z - half, z1 = z + half >= Z ? Z - 1 : z + half;
+        int32_t cl = 0;
+        for (int zz = z0; zz <= z1; ++zz) {
+            const int32_t v = ring[zz % W];
+            cl = v > cl ? v : cl;
+        }
+        const int32_t own = ring[z % W];
+        if (cl <= 0 && own <= 0) continue;
+        const size_t v_idx = (size_t)z * plane + col;
+        if (cl > 0 && cl < minlength) {
+            const int code = label_code[cl];
+            if (code >= 0 && code < K) {
+                uint32_t m = cw_mask[code];
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (b >= n_bits) break;
+                    const float w = fmaxf(load_f32<T>(stack + (size_t)b * n_vox + v_idx), 0.f);
+                    double* s = sums + ((size_t)cl * n_bits + b) * 4;
+                    atomicAdd(s + 0, (double)w);
+                    atomicAdd(s + 1, (double)w * (double)z);
+                    atomicAdd(s + 2, (double)__fmul_rn(w, (float)y));
+                    atomicAdd(s + 3, (double)__fmul_rn(w, (float)x));
+                }
+            }
+        }
+        if (own > 0 && own < minlength) {
+            const int code = label_code[own];
+            if (code >= 0 && code < K) {
+                uint32_t m = cw_mask[code];
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (b >= n_bits) break;
+                    const float w = fmaxf(load_f32<T>(stack + (size_t)b * n_vox + v_idx), 0.f);
+                    // w >= 0: the int ordering of the bit patterns is the float ordering
+                    atomicMax(reinterpret_cast<int*>(peak + (size_t)own * n_bits + b), __float_as_int(w));
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int m3d_centroid_statistics(m3d_ctx* ctx, const int32_t* labels_dev, const void* stack_dev, int dtype,
+                                       const int64_t dims[3], int z_support, const int16_t* label_code_dev,
+                                       int64_t minlength, double* sums_dev, float* peak_dev, void* stream) {
+    if (!ctx || !labels_dev || !stack_dev || !dims || !label_code_dev || !sums_dev || !peak_dev)
+        return m3d_fail(M3D_ERR_ARG, "m3d_centroid_statistics: null argument");
+    if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0 || minlength < 1)
+        return m3d_fail(M3D_ERR_ARG, "m3d_centroid_statistics: bad dims / minlength");
+    if (dtype != M3D_DTYPE_U16 && dtype != M3D_DTYPE_F32)
+        return m3d_fail(M3D_ERR_ARG, "m3d_centroid_statistics: dtype %d", dtype);
+    int half = z_support / 2;
+    if (half < 0) half = 0;
+    if (half > MAX_HALF) return m3d_fail(M3D_ERR_ARG, "m3d_centroid_statistics: z_support %d exceeds %d", z_support, 2 * MAX_HALF + 1);
+    M3D_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t cells = (size_t)minlength * ctx->n_bits;
+    M3D_CUDA(cudaMemsetAsync(sums_dev, 0, cells * 4 * sizeof(double), st));
+    M3D_CUDA(cudaMemsetAsync(peak_dev, 0, cells * sizeof(float), st));
+    const long long plane = (long long)dims[1] * dims[2];
+    const int blocks = (int)((plane + CT_THREADS - 1) / CT_THREADS);
+    if (dtype == M3D_DTYPE_U16) {
+        M3D_LAUNCH(ctx, KF_CENTROID, st,
+                   centroid_stats_kernel<uint16_t><<<blocks, CT_THREADS, 0, st>>>(
+                       labels_dev, reinterpret_cast<const uint16_t*>(stack_dev), (int)dims[0], (int)dims[1], (int)dims[2],
+                       half, label_code_dev, ctx->d_cw_mask, ctx->K, ctx->n_bits, (long long)minlength, sums_dev, peak_dev));
+    } else {
+        M3D_LAUNCH(ctx, KF_CENTROID, st,
+                   centroid_stats_kernel<float><<<blocks, CT_THREADS, 0, st>>>(
+                       labels_dev, reinterpret_cast<const float*>(stack_dev), (int)dims[0], (int)dims[1], (int)dims[2],
+                       half, label_code_dev, ctx->d_cw_mask, ctx->K, ctx->n_bits, (long long)minlength, sums_dev, peak_dev));
+    }
+    M3D_CHECK_LAUNCH();
+    return M3D_OK;
+}

@@ -53,6 +53,7 @@ enum M3dKernel {
     KF_TABLE_GRID,
     KF_TABLE_OVERLAP,
     KF_TABLE_WITHIN,
+    KF_CENTROID,
     KF_COUNT
 };
 

@@ -417,6 +417,70 @@ def region_table(
     return pd.DataFrame(rows, columns=cols)
 
 
+CENTROID_SUFFIXES = ("center_z", "center_y", "center_x", "intensity_sum", "intensity_peak", "voxel_count")
+
+
+def plane_wise_centroid_statistics(labels: np.ndarray, intensity: np.ndarray, z_support: int, minlength: int):
+    """PD:2833-2906 restated in its full-volume form (the one upstream's own test compares with,
+    tests/test_optimization_codeword_exclusions.py:153-205): labels dilated along z by a
+    ``z_support`` maximum window, weights max(intensity, 0) in float32, float64 bincount sums."""
+    half = max(int(z_support) // 2, 0)
+    dil = ndi.maximum_filter1d(labels, size=2 * half + 1, axis=0, mode="reflect") if half else labels
+    w = np.maximum(np.asarray(intensity, dtype=F32), F32(0))
+    zc = np.arange(labels.shape[0], dtype=np.float64)[:, None, None]
+    yc = np.arange(labels.shape[1], dtype=F32)[None, :, None]
+    xc = np.arange(labels.shape[2], dtype=F32)[None, None, :]
+    flat = dil.ravel()
+    weight = np.bincount(flat, weights=w.ravel(), minlength=minlength)
+    zsum = np.bincount(flat, weights=(w.astype(np.float64) * zc).ravel(), minlength=minlength)
+    ysum = np.bincount(flat, weights=(w * yc).ravel(), minlength=minlength)
+    xsum = np.bincount(flat, weights=(w * xc).ravel(), minlength=minlength)
+    peak = np.zeros(minlength, dtype=F32)
+    np.maximum.at(peak, labels.ravel(), w.ravel())
+    return weight, zsum, ysum, xsum, peak
+
+
+def on_bit_centroid_columns(df: pd.DataFrame, labels: np.ndarray, intensity: np.ndarray, on_sel: np.ndarray,
+                            z_support: int = 7, epsilon: float = 1e-6, z_offset: float | None = None) -> pd.DataFrame:
+    """PD:2701-2831.  ``df`` holds ``label`` and the decoded-space centroid ``z, y, x``;
+    ``intensity`` is (bits, z, y, x)."""
+    n_bits = intensity.shape[0]
+    extra = {f"bit{b:02d}_{s}": np.full(len(df), np.nan) for b in range(1, n_bits + 1) for s in CENTROID_SUFFIXES}
+    if len(df) == 0 or labels.max() < 1:
+        return pd.DataFrame(extra, index=df.index)
+    zs = min(int(z_support), labels.shape[0])
+    if zs % 2 == 0:
+        zs -= 1
+    minlength = int(labels.max()) + 1
+    lab = np.clip(df["label"].to_numpy(dtype=np.int64), 0, minlength - 1)
+    fallback = df[["z", "y", "x"]].to_numpy(dtype=np.float64)
+    area_by_label = np.bincount(labels.ravel(), minlength=minlength).astype(F32)
+    for b in range(1, n_bits + 1):
+        rows = np.flatnonzero(np.any(on_sel == b, axis=1))
+        if rows.size == 0:
+            continue
+        weight, zsum, ysum, xsum, peak = plane_wise_centroid_statistics(labels, intensity[b - 1], zs, minlength)
+        wsum = weight[lab[rows]].astype(np.float64)
+        den = np.maximum(wsum, F32(epsilon))
+        centers = np.column_stack((zsum[lab[rows]] / den, ysum[lab[rows]] / den, xsum[lab[rows]] / den))
+        invalid = (~np.all(np.isfinite(centers), axis=1)) | (wsum <= 0)
+        centers[invalid] = fallback[rows][invalid]
+        if z_offset is not None:
+            centers[:, 0] = float(z_offset) + centers[:, 0]
+        area = area_by_label[lab[rows]].astype(np.float64)
+        pk = peak[lab[rows]].astype(np.float64)
+        missing = (~np.isfinite(wsum)) | (wsum <= 0)
+        area[missing] = 0.0
+        pk[~np.isfinite(pk)] = 0.0
+        wsum[missing] = 0.0
+        for k, sfx in enumerate(("center_z", "center_y", "center_x")):
+            extra[f"bit{b:02d}_{sfx}"][rows] = centers[:, k]
+        extra[f"bit{b:02d}_intensity_sum"][rows] = wsum
+        extra[f"bit{b:02d}_intensity_peak"][rows] = pk
+        extra[f"bit{b:02d}_voxel_count"][rows] = area
+    return pd.DataFrame(extra, index=df.index)
+
+
 def annotate_table(
     df: pd.DataFrame,
     decoded: np.ndarray,
@@ -430,8 +494,12 @@ def annotate_table(
     affine,
     camera_to_stage,
     z_offset: float | None = None,
+    centroid_inputs: tuple | None = None,
 ) -> pd.DataFrame:
-    """PD:3066-3177 -- codeword/gene annotation, coordinates, signal stats, transcript gate."""
+    """PD:3066-3177 -- codeword/gene annotation, coordinates, signal stats, transcript gate.
+
+    ``centroid_inputs`` = (labels, intensity (bits,z,y,x), z_support, epsilon) switches on the
+    optimiser's per-on-bit centroid columns (PD:3117-3125)."""
     df = df.copy()
     dec_flat = decoded.ravel()
     ids = dec_flat[df["first_voxel"].to_numpy(dtype=np.int64)].astype(np.int32)
@@ -445,6 +513,9 @@ def annotate_table(
     on_sel = (on0 + 1)[df["decoded_id"].to_numpy(dtype=np.int32)]
     for k in range(4):
         df[f"on_bit_{k + 1}"] = on_sel[:, k] if len(df) else np.zeros(0, dtype=np.int32)
+    if centroid_inputs is not None:
+        lab_img, inten, zs, eps = centroid_inputs
+        df = pd.concat([df, on_bit_centroid_columns(df, lab_img, inten, on_sel, zs, eps, z_offset)], axis=1)
     if z_offset is not None:
         df["z"] = float(z_offset) + df["z"]  # PD:3126-3127
     df["tile_z"] = np.round(df["z"], 0).astype(int)
@@ -487,8 +558,10 @@ def extract_barcodes(
     z_offset=None,
     maximum_pixels: int = MAXIMUM_PIXELS,
     return_labels: bool = False,
+    collect_centroids: tuple | None = None,
 ):
-    """PD:2908-3201."""
+    """PD:2908-3201.  ``collect_centroids`` = (z_support, epsilon) adds the optimiser's per-on-bit
+    centroid columns (only meaningful with the raw intensity image, PD:3117-3125)."""
     labels = label_decoded(decode_out["decoded"], is_3d)
     labels = filter_label_sizes(labels, minimum_pixels, maximum_pixels)
     tab = region_table(labels, decode_out["distance"], decode_out["magnitude"], intensity)
@@ -506,6 +579,7 @@ def extract_barcodes(
         np.eye(4, dtype=F32) if affine is None else np.asarray(affine, dtype=F32),
         np.eye(4, dtype=F32) if camera_to_stage is None else np.asarray(camera_to_stage, dtype=F32),
         z_offset,
+        None if collect_centroids is None else (labels, intensity, collect_centroids[0], collect_centroids[1]),
     )
     if return_labels:
         return df, labels
@@ -526,6 +600,7 @@ def decode_tile(
     optimize_mode: bool = False,
     tile_idx: int = 0,
     bit_transforms_zyx_um=None,
+    collect_centroids: tuple | None = None,
     **coords,
 ):
     """PD:4471-4579 -- one tile end to end; returns (table, images dict).
@@ -555,6 +630,7 @@ def decode_tile(
         minimum_pixels,
         cb["transcript_distance_threshold"],
         tile_idx=tile_idx,
+        collect_centroids=collect_centroids if optimize_mode else None,
         **coords,
     )
     out["image"] = stack

@@ -46,6 +46,9 @@ def run_tile_scenario(name, sc, RefPD):
         ds.add_tile(stack, predictors=pred, stage_origin_zyx_um=sc.get("origin"))
         ds.save_decode_normalization_vectors(None, "global", nrm, bkg)
         dec = RefPD(ds, merfish_bits=16, verbose=0, z_range=sc.get("z_range"), excluded_gene_ids=excluded)
+        if sc.get("chroma"):
+            dec._optimize_normalization_weights = True
+            dec._collect_chromatic_centroids = True
         with rs.pandas2_semantics():
             res = dec.decode_one_tile(
                 0, return_results=True, lowpass_sigma=sc["lowpass"], minimum_pixels=sc["min_px"],

@@ -78,8 +78,24 @@ class _Device(contextlib.AbstractContextManager):
         return None
 
 
+class _DeviceScalar(np.ndarray):
+    """0-d result of a reduction: CuPy returns a device array with ``.get()`` (PD:2756)."""
+
+    def get(self):
+        return np.asarray(self)[()]
+
+
+def _reduction(fn):
+    def wrapped(*a, **k):
+        r = fn(*a, **k)
+        return np.asarray(r).view(_DeviceScalar) if np.ndim(r) == 0 else r
+
+    return wrapped
+
+
 def _make_cupy() -> types.ModuleType:
     cp = types.ModuleType("cupy")
+    cp.max = _reduction(np.max)
 
     def __getattr__(name):  # everything else is the NumPy function of the same name
         return getattr(np, name)

@@ -17,6 +17,9 @@ SCENARIOS = {
     "mode2d": dict(shape=(5, 48, 48), seed=13, density=6e-3, lowpass=(3.0, 1.0, 1.0), norm="global", min_px=None,
                    microscope="2D", bkg=150.0, nrm=500.0, mag=(0.9, 10.0)),
     # exclusions + z_range crop + unnormalised traces
+    # optimiser mode with per-on-bit weighted centroids (raw float32 intensities, z-crop offset applied)
+    "chroma": dict(shape=(12, 40, 48), seed=15, density=5e-3, lowpass=(1.0, 0.5, 0.5), norm="global", min_px=4,
+                   z_range=(1, 11), chroma=True, bkg=150.0, nrm=500.0, mag=(0.9, 10.0)),
     "excl_crop": dict(shape=(9, 32, 40), seed=14, density=6e-3, lowpass=None, norm="global", min_px=3,
                       z_range=(2, 8), exclude=3),
 }

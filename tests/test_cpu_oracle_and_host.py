@@ -258,3 +258,30 @@ def test_product_package_never_imports_the_oracle():
         assert not pat.search(p.read_text()), p
     for p in pkg.glob("csrc/*"):
         assert "#include" not in "".join(l for l in p.read_text().splitlines() if "oracle" in l), p
+
+
+def _upstream_centroid_case():
+    """tests/test_optimization_codeword_exclusions.py:153-205 of the reference (known-answer case)."""
+    labels = np.asarray(
+        [[[0, 1, 0], [0, 0, 2]], [[0, 0, 0], [3, 0, 0]], [[0, 1, 0], [0, 0, 2]]], dtype=np.int32)
+    intensity = np.arange(1, labels.size + 1, dtype=np.float32).reshape(labels.shape)
+    intensity[0, 0, 0] = -5.0
+    from scipy.ndimage import grey_dilation
+
+    dil = grey_dilation(labels, size=(3, 1, 1))
+    w = np.maximum(intensity, np.float32(0))
+    coords = [np.arange(n, dtype=np.float32).reshape(s) for n, s in
+              zip(labels.shape, ((-1, 1, 1), (1, -1, 1), (1, 1, -1)))]
+    ml = int(labels.max()) + 1
+    expected = [np.bincount(dil.ravel(), weights=w.ravel(), minlength=ml)]
+    expected += [np.bincount(dil.ravel(), weights=(w * c).ravel(), minlength=ml) for c in coords]
+    peak = np.zeros(ml, dtype=np.float32)
+    np.maximum.at(peak, labels.ravel(), w.ravel())
+    return labels, intensity, expected + [peak]
+
+
+def test_plane_wise_centroid_statistics_upstream_known_answer():
+    labels, intensity, expected = _upstream_centroid_case()
+    got = orc.plane_wise_centroid_statistics(labels, intensity, z_support=3, minlength=int(labels.max()) + 1)
+    for g, e in zip(got, expected, strict=True):
+        np.testing.assert_allclose(g, e)

@@ -36,6 +36,10 @@ def compare_with_reference_table(got: pd.DataFrame, ref: pd.DataFrame, rel=0.0):
         b = ref[c].to_numpy(dtype=np.float64)
         if c.startswith("inertia_tensor_eigvals"):
             np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-9, err_msg=c)  # eigensolver round-off
+        elif c.endswith(("_center_z", "_center_y", "_center_x", "_intensity_sum")):
+            # float64 sums of float32 weights: plane-wise vs full-volume vs atomic order differ by round-off
+            assert np.array_equal(np.isnan(a), np.isnan(b)), c
+            np.testing.assert_allclose(a, b, rtol=1e-9 if rel == 0.0 else rel, atol=1e-9, err_msg=c)
         elif rel == 0.0 or c in ("area", "barcode_id", "tile_idx", "on_bit_1", "on_bit_2", "on_bit_3", "on_bit_4",
                                  "tile_z", "tile_y", "tile_x"):
             np.testing.assert_array_equal(a, b, err_msg=c)
@@ -58,6 +62,8 @@ def oracle_on_scenario(sc):
     kw = {}
     if sc.get("mag") is not None:
         kw["magnitude_threshold"] = sc["mag"]
+    if sc.get("chroma"):
+        kw.update(optimize_mode=True, collect_centroids=(7, 1e-6))
     return orc.decode_tile(readout, predictor, cb, bkg, nrm, is_3d=is_3d, lowpass_sigma=sc["lowpass"],
                            minimum_pixels=sc["min_px"], excluded=excl_idx, **kw, **coords)
 

@@ -384,3 +384,54 @@ def test_select_hist_order_statistics(torch):
         [a[None], b[None]], 1, True, lowpass_sigma=None, hot_pixel_threshold=1e30
     )
     assert got[0][0] == nrm[0] and got[1][0] == bkg[0]
+
+
+def test_centroid_statistics_upstream_known_answer_and_random():
+    """m3d_centroid_statistics against the reference's own known-answer case
+    (tests/test_optimization_codeword_exclusions.py:153-205) and the oracle on a random volume."""
+    import torch
+
+    from merfish3d_analysis_b200._capi import DecodeContext
+    from test_cpu_oracle_and_host import _upstream_centroid_case
+
+    labels, intensity, expected = _upstream_centroid_case()
+    ctx = DecodeContext(np.array([[1.0]], dtype=np.float32), (), device=0)  # one bit, one codeword lighting it
+    code = torch.zeros(int(labels.max()) + 1, dtype=torch.int16, device="cuda")
+    sums, peak = ctx.centroid_statistics(torch.from_numpy(labels).cuda(), torch.from_numpy(intensity[None]).cuda(),
+                                         3, code)
+    sums, peak = sums.cpu().numpy(), peak.cpu().numpy()
+    for k in range(4):
+        np.testing.assert_allclose(sums[1:, 0, k], expected[k][1:])
+    np.testing.assert_allclose(peak[1:, 0], expected[4][1:])
+    ctx.close()
+
+    rng = np.random.default_rng(12)
+    Z, Y, X, nb = 9, 33, 47, 6
+    lab = np.zeros((Z, Y, X), dtype=np.int32)
+    n_lab = 60
+    for l in range(1, n_lab + 1):  # small boxes; later labels overwrite earlier ones
+        z, y, x = rng.integers(0, Z - 1), rng.integers(0, Y - 3), rng.integers(0, X - 3)
+        lab[z:z + rng.integers(1, 3), y:y + rng.integers(1, 4), x:x + rng.integers(1, 4)] = l
+    lab[lab == 7] = -1  # an oversized component marked as dropped
+    stack = rng.normal(50, 80, (nb, Z, Y, X)).astype(np.float32)
+    cb = np.zeros((5, nb), dtype=np.float32)
+    for k in range(5):
+        cb[k, rng.choice(nb, 3, replace=False)] = 1 / np.sqrt(3)
+    codes = rng.integers(0, 5, n_lab + 1).astype(np.int16)
+    codes[0] = -1
+    ctx = DecodeContext(cb, (), device=0)
+    for z_support in (1, 3, 7):
+        sums, peak = ctx.centroid_statistics(torch.from_numpy(lab).cuda(), torch.from_numpy(stack).cuda(), z_support,
+                                             torch.from_numpy(codes).cuda())
+        sums, peak = sums.cpu().numpy(), peak.cpu().numpy()
+        pos = np.maximum(lab, 0)
+        for b in range(nb):
+            w, zs, ys, xs, pk = orc.plane_wise_centroid_statistics(pos, stack[b], z_support, n_lab + 1)
+            on = np.array([l > 0 and cb[codes[l], b] > 0 for l in range(n_lab + 1)])
+            np.testing.assert_allclose(sums[on, b, 0], w[on], rtol=1e-12)
+            np.testing.assert_allclose(sums[on, b, 1], zs[on], rtol=1e-12)
+            np.testing.assert_allclose(sums[on, b, 2], ys[on], rtol=1e-12)
+            np.testing.assert_allclose(sums[on, b, 3], xs[on], rtol=1e-12)
+            np.testing.assert_array_equal(peak[on, b], pk[on])
+            assert not sums[~on, b].any() and not peak[~on, b].any()
+    ctx.close()
