@@ -195,6 +195,12 @@ int m3d_centroid_statistics(m3d_ctx* ctx, const int32_t* labels_dev, const void*
                             const int64_t dims[3], int z_support, const int16_t* label_code_dev,
                             int64_t minlength, double* sums_dev, float* peak_dev, void* stream);
 
+/* scikit-image `inertia_tensor_eigvals` of every row of an m3d_features table (PD:3038-3047): eigenvalues of
+ * the inertia tensor from columns 1 (area) and 6..11 (central second moments), clipped at 0, descending;
+ * eigvals_dev = (n_rows, 3) float64.  table_dev rows have n_cols (>= 14) float64 entries. */
+int m3d_inertia_eigvals(m3d_ctx* ctx, const double* table_dev, int64_t n_rows, int64_t n_cols,
+                        double* eigvals_dev, void* stream);
+
 /* Capacity (entries) of the search -> regionprops record buffers; 0 = automatic
  * (max(2^20, n_vox/16)).  When the foreground exceeds it the regionprops kernel recomputes the
  * traces instead; results are identical.  Exposed so tests can force the overflow path. */

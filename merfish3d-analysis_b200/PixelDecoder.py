@@ -499,9 +499,15 @@ class PixelDecoder:
         bit_ids = list(self._datastore.bit_ids)[0 : self._n_merfish_bits]
         loaded = []
         self._em_wvl = []
-        for bit_id in bit_ids:
-            fr = self._datastore.load_local_readout_image(tile=self._tile_idx, bit=bit_id)
-            fp = self._datastore.load_local_feature_predictor_image(tile=self._tile_idx, bit=bit_id)
+        # issue every read first, then collect: a datastore that returns real futures (tensorstore
+        # reads in the reference's qi2labDataStore) overlaps the 2 x bits chunk reads instead of
+        # serialising them bit by bit as PD:1861-1874 does
+        pending = [
+            (self._datastore.load_local_readout_image(tile=self._tile_idx, bit=bit_id),
+             self._datastore.load_local_feature_predictor_image(tile=self._tile_idx, bit=bit_id))
+            for bit_id in bit_ids
+        ]
+        for bit_id, (fr, fp) in zip(bit_ids, pending):
             pa = fp.result() if hasattr(fp, "result") else fp
             ra = fr.result() if hasattr(fr, "result") else fr
             _ex, em = self._datastore.load_local_wavelengths_um(tile=self._tile_idx, bit=bit_id)
@@ -679,8 +685,9 @@ class PixelDecoder:
         centroid_stats = None
         if chroma and n > 0:
             centroid_stats = self._chromatic_centroid_statistics(ctx, st["stack"], labels, table)
+        eigvals = ctx.inertia_eigvals(table).cpu().numpy() if n > 0 else None
         tab = table.cpu().numpy()
-        self._df_barcodes = self._annotate_table(tab, centroid_stats)
+        self._df_barcodes = self._annotate_table(tab, centroid_stats, eigvals)
 
     def _wants_chromatic_centroids(self) -> bool:
         """PD:3117-3125: per-on-bit centroids are collected only inside the optimiser."""
@@ -717,24 +724,17 @@ class PixelDecoder:
             + ["signal_mean", "bkd_mean", "s-b_mean"]
         )
 
-    @staticmethod
-    def _inertia_eigvals(tab: np.ndarray) -> np.ndarray:
-        """scikit-image ``inertia_tensor_eigvals`` from the central second moments."""
-        n = tab[:, _COL_AREA]
-        mu = tab[:, _COL_MU : _COL_MU + 6]
-        zz, yy, xx, zy, zx, yx = (mu[:, i] for i in range(6))
-        T = np.empty((tab.shape[0], 3, 3))
-        T[:, 0, 0] = (yy + xx) / n
-        T[:, 1, 1] = (zz + xx) / n
-        T[:, 2, 2] = (zz + yy) / n
-        T[:, 0, 1] = T[:, 1, 0] = -zy / n
-        T[:, 0, 2] = T[:, 2, 0] = -zx / n
-        T[:, 1, 2] = T[:, 2, 1] = -yx / n
-        ev = np.linalg.eigvalsh(T)
-        ev = np.clip(ev, 0, None)
-        return np.sort(ev, axis=1)[:, ::-1]
+    def _inertia_eigvals(self, tab: np.ndarray) -> np.ndarray:
+        """scikit-image ``inertia_tensor_eigvals`` from the central second moments of a HOST table
+        (the z-slab path assembles its merged rows on the host): uploaded, solved by
+        ``m3d_inertia_eigvals``.  The per-tile path hands the device table over directly."""
+        import torch
 
-    def _annotate_table(self, tab: np.ndarray, centroid_stats=None) -> pd.DataFrame:
+        ctx = self._ctx(self._local_gpu())
+        dev_tab = torch.from_numpy(np.ascontiguousarray(tab[:, :M3D_TABLE_FIXED_COLS], dtype=np.float64)).to(ctx.device)
+        return ctx.inertia_eigvals(dev_tab).cpu().numpy()
+
+    def _annotate_table(self, tab: np.ndarray, centroid_stats=None, eigvals: np.ndarray | None = None) -> pd.DataFrame:
         """PD:3066-3177 vectorised over the feature rows (row order = canonical id order)."""
         nb = self._n_merfish_bits
         cols = self._table_columns()
@@ -743,6 +743,8 @@ class PixelDecoder:
         dec = tab[:, _COL_DEC].astype(np.int32)
         if centroid_stats is not None:
             centroid_stats = tuple(a[dec >= 0] for a in centroid_stats)
+        if eigvals is not None:
+            eigvals = eigvals[dec >= 0]
         tab = tab[dec >= 0]
         dec = dec[dec >= 0]
         # columns are assembled as plain arrays and the frame is built once (a per-column
@@ -755,7 +757,10 @@ class PixelDecoder:
         bit_means = np.ascontiguousarray(tab[:, M3D_TABLE_FIXED_COLS : M3D_TABLE_FIXED_COLS + nb])
         for i in range(nb):
             col[f"bit{i + 1:02d}_mean_intensity"] = bit_means[:, i]
-        ev = self._inertia_eigvals(tab) if tab.shape[0] else np.zeros((0, 3))
+        if eigvals is not None:
+            ev = eigvals
+        else:
+            ev = self._inertia_eigvals(tab) if tab.shape[0] else np.zeros((0, 3))
         for k in range(3):
             col[f"inertia_tensor_eigvals-{k}"] = ev[:, k]
         col["distance_min"] = tab[:, _COL_DMIN]

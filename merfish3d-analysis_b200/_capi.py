@@ -97,6 +97,7 @@ SIGNATURES = {
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.c_int64,
          C.c_void_p, C.c_void_p, C.c_void_p],
     ),
+    "m3d_inertia_eigvals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "m3d_set_sparse_capacity": (C.c_int, [C.c_void_p, C.c_int64]),
     "m3d_launch_count": (C.c_int64, [C.c_void_p]),
     "m3d_kernel_name": (C.c_char_p, [C.c_int]),
@@ -462,6 +463,18 @@ class DecodeContext:
             "m3d_centroid_statistics",
         )
         return sums, peak
+
+    def inertia_eigvals(self, table):
+        """(n, 3) float64 inertia-tensor eigenvalues (descending, clipped at 0) of a feature table."""
+        import torch
+
+        ev = torch.empty((int(table.shape[0]), 3), dtype=torch.float64, device=self.device)
+        _check(
+            self._lib.m3d_inertia_eigvals(self._h, _ptr(table), int(table.shape[0]), int(table.shape[1]), _ptr(ev),
+                                          _stream(self.device)),
+            "m3d_inertia_eigvals",
+        )
+        return ev
 
     def set_sparse_capacity(self, entries: int) -> None:
         _check(self._lib.m3d_set_sparse_capacity(self._h, int(entries)), "m3d_set_sparse_capacity")

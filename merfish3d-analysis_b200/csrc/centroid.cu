@@ -121,3 +121,65 @@ extern "C" int m3d_centroid_statistics(m3d_ctx* ctx, const int32_t* labels_dev, 
     M3D_CHECK_LAUNCH();
     return M3D_OK;
 }
+
+// ------------------------------------------------------------------ inertia-tensor eigenvalues
+// scikit-image `inertia_tensor_eigvals` (PD:3038-3047 requests it): eigenvalues of the 3x3 inertia
+// tensor built from the normalised second central moments, clipped at 0, descending.  The reference
+// gets them from LAPACK on the host, one Python call per region; here one thread per table row runs
+// cyclic Jacobi rotations in float64 (converged to round-off in <= 6 sweeps for 3x3).
+namespace {
+
+__global__ void __launch_bounds__(128)
+inertia_eigvals_kernel(const double* __restrict__ table, long long n_rows, long long stride, double* __restrict__ out) {
+    const long long r = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (r >= n_rows) return;
+    const double* t = table + r * stride;
+    const double n = t[1];
+    const double zz = t[6], yy = t[7], xx = t[8], zy = t[9], zx = t[10], yx = t[11];
+    double a00 = (yy + xx) / n, a11 = (zz + xx) / n, a22 = (zz + yy) / n;
+    double a01 = -zy / n, a02 = -zx / n, a12 = -yx / n;
+    for (int sweep = 0; sweep < 8; ++sweep) {
+        const double off = fabs(a01) + fabs(a02) + fabs(a12);
+        if (off == 0.0) break;
+#define M3D_JACOBI(app, aqq, apq, arp, arq)                                              \
+    if (apq != 0.0) {                                                                    \
+        const double theta = (aqq - app) / (2.0 * apq);                                  \
+        const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0)); \
+        const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;                          \
+        app -= tt * apq;                                                                 \
+        aqq += tt * apq;                                                                 \
+        apq = 0.0;                                                                       \
+        const double rp = arp, rq = arq;                                                 \
+        arp = c * rp - s * rq;                                                           \
+        arq = s * rp + c * rq;                                                           \
+    }
+        M3D_JACOBI(a00, a11, a01, a02, a12)
+        M3D_JACOBI(a00, a22, a02, a01, a12)
+        M3D_JACOBI(a11, a22, a12, a01, a02)
+#undef M3D_JACOBI
+    }
+    double e0 = fmax(a00, 0.0), e1 = fmax(a11, 0.0), e2 = fmax(a22, 0.0), tmp;
+    if (e0 < e1) { tmp = e0; e0 = e1; e1 = tmp; }
+    if (e1 < e2) { tmp = e1; e1 = e2; e2 = tmp; }
+    if (e0 < e1) { tmp = e0; e0 = e1; e1 = tmp; }
+    out[r * 3 + 0] = e0;
+    out[r * 3 + 1] = e1;
+    out[r * 3 + 2] = e2;
+}
+
+}  // namespace
+
+extern "C" int m3d_inertia_eigvals(m3d_ctx* ctx, const double* table_dev, int64_t n_rows, int64_t n_cols,
+                                   double* eigvals_dev, void* stream) {
+    if (!ctx || n_rows < 0 || n_cols < M3D_TABLE_FIXED_COLS)
+        return m3d_fail(M3D_ERR_ARG, "m3d_inertia_eigvals: bad argument");
+    if (n_rows == 0) return M3D_OK;
+    if (!table_dev || !eigvals_dev) return m3d_fail(M3D_ERR_ARG, "m3d_inertia_eigvals: null argument");
+    M3D_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int blocks = (int)((n_rows + 127) / 128);
+    M3D_LAUNCH(ctx, KF_EIGVALS, st,
+               inertia_eigvals_kernel<<<blocks, 128, 0, st>>>(table_dev, (long long)n_rows, (long long)n_cols, eigvals_dev));
+    M3D_CHECK_LAUNCH();
+    return M3D_OK;
+}

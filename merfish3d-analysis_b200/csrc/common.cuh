@@ -54,6 +54,7 @@ enum M3dKernel {
     KF_TABLE_OVERLAP,
     KF_TABLE_WITHIN,
     KF_CENTROID,
+    KF_EIGVALS,
     KF_COUNT
 };
 

@@ -358,9 +358,7 @@ def test_features_match_oracle(torch, optimize, in_dtype):
         tab[:, 2].astype(np.int64), ref["decoded"].ravel()[ref_df["first_voxel"].to_numpy()].astype(np.int64)
     )
     # second central moments -> inertia eigenvalues (scikit-image semantics)
-    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
-
-    ev = PixelDecoder._inertia_eigvals(tab)
+    ev = ctx.inertia_eigvals(torch.from_numpy(tab).cuda()).cpu().numpy()
     ref_ev = np.stack([ref_df[f"inertia_tensor_eigvals-{k}"].to_numpy(dtype=np.float64) for k in range(3)], axis=1)
     np.testing.assert_allclose(ev, ref_ev, rtol=1e-9, atol=1e-9)
 
@@ -435,3 +433,39 @@ def test_centroid_statistics_upstream_known_answer_and_random():
             np.testing.assert_array_equal(peak[on, b], pk[on])
             assert not sums[~on, b].any() and not peak[~on, b].any()
     ctx.close()
+
+
+def test_inertia_eigvals_match_lapack():
+    """m3d_inertia_eigvals (Jacobi, float64) against numpy.linalg.eigvalsh on the scikit-image tensor,
+    including degenerate regions (single voxel, straight lines, planes)."""
+    import torch
+
+    from merfish3d_analysis_b200._capi import DecodeContext
+
+    rng = np.random.default_rng(5)
+    rows = []
+    for i in range(3000):
+        n = int(rng.integers(1, 60))
+        kind = i % 4
+        pts = rng.integers(0, 12, (n, 3)).astype(np.float64)
+        if kind == 1:
+            pts[:, 1:] = 3.0  # line along z
+        elif kind == 2:
+            pts[:, 0] = 5.0  # plane
+        elif kind == 3:
+            pts = pts[:1]  # single voxel
+        d = pts - pts.mean(axis=0)
+        mu = d.T @ d
+        rows.append([0, len(pts), 0, 0, 0, 0, mu[0, 0], mu[1, 1], mu[2, 2], mu[0, 1], mu[0, 2], mu[1, 2], 0, 0])
+    tab = np.asarray(rows, dtype=np.float64)
+    n = tab[:, 1]
+    T = np.empty((len(tab), 3, 3))
+    T[:, 0, 0], T[:, 1, 1], T[:, 2, 2] = (tab[:, 7] + tab[:, 8]) / n, (tab[:, 6] + tab[:, 8]) / n, (tab[:, 6] + tab[:, 7]) / n
+    T[:, 0, 1] = T[:, 1, 0] = -tab[:, 9] / n
+    T[:, 0, 2] = T[:, 2, 0] = -tab[:, 10] / n
+    T[:, 1, 2] = T[:, 2, 1] = -tab[:, 11] / n
+    want = np.sort(np.clip(np.linalg.eigvalsh(T), 0, None), axis=1)[:, ::-1]
+    ctx = DecodeContext(np.array([[1.0]], dtype=np.float32), (), device=0)
+    got = ctx.inertia_eigvals(torch.from_numpy(tab).cuda()).cpu().numpy()
+    ctx.close()
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)

@@ -17,7 +17,10 @@ from merfish3d_analysis_b200.datastore import ArrayDataStore  # noqa: E402
 from merfish3d_analysis_b200.PixelDecoder import PixelDecoder  # noqa: E402
 
 shape = (100, 2048, 2048) if len(sys.argv) < 2 else tuple(int(v) for v in sys.argv[1:4])
-dev = torch.device("cuda", 0)
+import os
+LOCAL = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(LOCAL)
+dev = torch.device("cuda", LOCAL)
 matrix = synthetic.mhd4_codebook_matrix(16)
 df_cb = synthetic.codebook_dataframe(matrix, n_blank=10)
 stack = synthetic.make_stack_device(matrix, shape, 2002, device=dev)
@@ -31,6 +34,7 @@ ds = ArrayDataStore(Path(tmp.name) / "qi2labdatastore", codebook=df_cb)
 ds.add_tile(host.numpy())
 ds.save_decode_normalization_vectors(None, "global", np.full(16, 900.0, np.float32), np.full(16, 200.0, np.float32))
 dec = PixelDecoder(ds, merfish_bits=16, verbose=0)
+GPU = LOCAL
 
 phases = {}
 
@@ -53,19 +57,20 @@ for it in range(4):
     phases.clear()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    dec.decode_one_tile(0, lowpass_sigma=None, magnitude_threshold=(1.5, 10.0), minimum_pixels=16.0,
+    dec.decode_one_tile(0, gpu_id=GPU, lowpass_sigma=None, magnitude_threshold=(1.5, 10.0), minimum_pixels=16.0,
                         normalization_method="global")
     torch.cuda.synchronize()
     total = (time.perf_counter() - t0) * 1e3
-    print(f"iter {it}: total {total:.1f} ms  " + "  ".join(f"{k}={v:.1f}" for k, v in phases.items()),
+    print(f"[rank {LOCAL} omp={os.environ.get('OMP_NUM_THREADS')}] iter {it}: total {total:.1f} ms  " + "  ".join(f"{k}={v:.1f}" for k, v in phases.items()),
           f" rows={len(dec._df_barcodes)}", flush=True)
 
-import cProfile  # noqa: E402
-import pstats  # noqa: E402
-
-pr = cProfile.Profile()
-pr.enable()
-dec.decode_one_tile(0, lowpass_sigma=None, magnitude_threshold=(1.5, 10.0), minimum_pixels=16.0,
-                    normalization_method="global")
-pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(35)
+if os.environ.get("E2E_CPROFILE"):
+    import cProfile  # noqa: E402
+    import pstats  # noqa: E402
+    
+    pr = cProfile.Profile()
+    pr.enable()
+    dec.decode_one_tile(0, gpu_id=GPU, lowpass_sigma=None, magnitude_threshold=(1.5, 10.0), minimum_pixels=16.0,
+                        normalization_method="global")
+    pr.disable()
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(35)
