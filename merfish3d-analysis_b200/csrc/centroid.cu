@@ -24,9 +24,51 @@ __device__ __forceinline__ float load_f32<float>(const float* p) { return __ldg(
 template <>
 __device__ __forceinline__ float load_f32<uint16_t>(const uint16_t* p) { return (float)__ldg(p); }
 
+// per-voxel accumulation, shared by the windowed walk below
 template <typename T>
+__device__ __forceinline__ void accumulate_voxel(int32_t cl, int32_t own, int z, int y, int x, size_t v_idx, size_t n_vox,
+                                                 const T* __restrict__ stack, const int16_t* __restrict__ label_code,
+                                                 const uint32_t* __restrict__ cw_mask, int K, int n_bits,
+                                                 long long minlength, double* __restrict__ sums,
+                                                 float* __restrict__ peak) {
+    if (cl > 0 && cl < minlength) {
+        const int code = label_code[cl];
+        if (code >= 0 && code < K) {
+            uint32_t m = cw_mask[code];
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                if (b >= n_bits) break;
+                const float w = fmaxf(load_f32<T>(stack + (size_t)b * n_vox + v_idx), 0.f);
+                double* s = sums + ((size_t)cl * n_bits + b) * 4;
+                atomicAdd(s + 0, (double)w);
+                atomicAdd(s + 1, (double)w * (double)z);
+                atomicAdd(s + 2, (double)__fmul_rn(w, (float)y));
+                atomicAdd(s + 3, (double)__fmul_rn(w, (float)x));
+            }
+        }
+    }
+    if (own > 0 && own < minlength) {
+        const int code = label_code[own];
+        if (code >= 0 && code < K) {
+            uint32_t m = cw_mask[code];
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                if (b >= n_bits) break;
+                const float w = fmaxf(load_f32<T>(stack + (size_t)b * n_vox + v_idx), 0.f);
+                // w >= 0: the int ordering of the bit patterns is the float ordering
+                atomicMax(reinterpret_cast<int*>(peak + (size_t)own * n_bits + b), __float_as_int(w));
+            }
+        }
+    }
+}
+
+// HALF >= 0: compile-time window, labels of planes z-HALF .. z+HALF live in registers and shift by one per
+// step (no local memory).  HALF < 0: run-time half width with an indexed ring (any z_support up to 31).
+template <typename T, int HALF>
 __global__ void __launch_bounds__(CT_THREADS)
-centroid_stats_kernel(const int32_t* __restrict__ labels, const T* __restrict__ stack, int Z, int Y, int X, int half,
+centroid_stats_kernel(const int32_t* __restrict__ labels, const T* __restrict__ stack, int Z, int Y, int X, int half_rt,
                       const int16_t* __restrict__ label_code, const uint32_t* __restrict__ cw_mask, int K, int n_bits,
                       long long minlength, double* __restrict__ sums, float* __restrict__ peak) {
     const long long col = (long long)blockIdx.x * CT_THREADS + threadIdx.x;
@@ -34,56 +76,78 @@ centroid_stats_kernel(const int32_t* __restrict__ labels, const T* __restrict__ 
     if (col >= plane) return;
     const int y = (int)(col / X), x = (int)(col % X);
     const size_t n_vox = (size_t)Z * plane;
-    int32_t ring[2 * MAX_HALF + 1];
-    const int W = 2 * half + 1;
+    if constexpr (HALF >= 0) {
+        constexpr int W = 2 * HALF + 1;
+        int32_t win[W];  // win[i] = labels[z - HALF + i] (0 outside the volume)
 #pragma unroll
-    for (int i = 0; i < 2 * MAX_HALF + 1; ++i) ring[i] = 0;
-    // ring[(zz) % W] holds labels[zz]; preload planes 0 .. half-1
-    for (int zz = 0; zz < half && zz < Z; ++zz) ring[zz % W] = labels[(size_t)zz * plane + col];
-    for (int z = 0; z < Z; ++z) {
-        const int zin = z + half;
-        if (zin < Z) ring[zin % W] = labels[(size_t)zin * plane + col];
-        const int z0 = z - half < 0 ? 0 : z - half, z1 = z + half >= Z ? Z - 1 : z + half;
-        int32_t cl = 0;
-        for (int zz = z0; zz <= z1; ++zz) {
-            const int32_t v = ring[zz % W];
-            cl = v > cl ? v : cl;
+        for (int i = 0; i < W; ++i) {
+            const int zz = i - HALF - 1;  // state before the first shift
+            win[i] = (zz >= 0 && zz < Z) ? __ldg(labels + (size_t)zz * plane + col) : 0;
         }
-        const int32_t own = ring[z % W];
-        if (cl <= 0 && own <= 0) continue;
-        const size_t v_idx = (size_t)z * plane + col;
-        if (cl > 0 && cl < minlength) {
-            const int code = label_code[cl];
-            if (code >= 0 && code < K) {
-                uint32_t m = cw_mask[code];
-                while (m) {
-                    const int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    if (b >= n_bits) break;
-                    const float w = fmaxf(load_f32<T>(stack + (size_t)b * n_vox + v_idx), 0.f);
-                    double* s = sums + ((size_t)cl * n_bits + b) * 4;
-                    atomicAdd(s + 0, (double)w);
-                    atomicAdd(s + 1, (double)w * (double)z);
-                    atomicAdd(s + 2, (double)__fmul_rn(w, (float)y));
-                    atomicAdd(s + 3, (double)__fmul_rn(w, (float)x));
-                }
+        constexpr int U = 4;  // planes fetched per batch: keeps U independent loads in flight per thread
+        for (int zb = 0; zb < Z; zb += U) {
+            int32_t nxt[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const int zin = zb + j + HALF;
+                nxt[j] = zin < Z ? __ldg(labels + (size_t)zin * plane + col) : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const int z = zb + j;
+#pragma unroll
+                for (int i = 0; i < W - 1; ++i) win[i] = win[i + 1];
+                win[W - 1] = nxt[j];
+                if (z >= Z) continue;
+                int32_t cl = 0;
+#pragma unroll
+                for (int i = 0; i < W; ++i) cl = win[i] > cl ? win[i] : cl;
+                const int32_t own = win[HALF];
+                if (cl <= 0 && own <= 0) continue;
+                accumulate_voxel<T>(cl, own, z, y, x, (size_t)z * plane + col, n_vox, stack, label_code, cw_mask, K,
+                                    n_bits, minlength, sums, peak);
             }
         }
-        if (own > 0 && own < minlength) {
-            const int code = label_code[own];
-            if (code >= 0 && code < K) {
-                uint32_t m = cw_mask[code];
-                while (m) {
-                    const int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    if (b >= n_bits) break;
-                    const float w = fmaxf(load_f32<T>(stack + (size_t)b * n_vox + v_idx), 0.f);
-                    // w >= 0: the int ordering of the bit patterns is the float ordering
-                    atomicMax(reinterpret_cast<int*>(peak + (size_t)own * n_bits + b), __float_as_int(w));
-                }
+    } else {
+        const int half = half_rt;
+        int32_t ring[2 * MAX_HALF + 1];
+        const int W = 2 * half + 1;
+#pragma unroll
+        for (int i = 0; i < 2 * MAX_HALF + 1; ++i) ring[i] = 0;
+        // ring[zz % W] holds labels[zz]; preload planes 0 .. half-1
+        for (int zz = 0; zz < half && zz < Z; ++zz) ring[zz % W] = labels[(size_t)zz * plane + col];
+        for (int z = 0; z < Z; ++z) {
+            const int zin = z + half;
+            if (zin < Z) ring[zin % W] = labels[(size_t)zin * plane + col];
+            const int z0 = z - half < 0 ? 0 : z - half, z1 = z + half >= Z ? Z - 1 : z + half;
+            int32_t cl = 0;
+            for (int zz = z0; zz <= z1; ++zz) {
+                const int32_t v = ring[zz % W];
+                cl = v > cl ? v : cl;
             }
+            const int32_t own = ring[z % W];
+            if (cl <= 0 && own <= 0) continue;
+            accumulate_voxel<T>(cl, own, z, y, x, (size_t)z * plane + col, n_vox, stack, label_code, cw_mask, K, n_bits,
+                                minlength, sums, peak);
         }
     }
+}
+
+template <typename T>
+void launch_centroid(m3d_ctx* ctx, int blocks, cudaStream_t st, int half, const int32_t* labels, const T* stack, int Z,
+                     int Y, int X, const int16_t* label_code, long long minlength, double* sums, float* peak) {
+#define M3D_CT(H)                                                                                                   \
+    centroid_stats_kernel<T, H><<<blocks, CT_THREADS, 0, st>>>(labels, stack, Z, Y, X, half, label_code, ctx->d_cw_mask, \
+                                                               ctx->K, ctx->n_bits, minlength, sums, peak)
+    KernelScope ks(ctx, KF_CENTROID, st);
+    switch (half) {
+        case 0: M3D_CT(0); break;
+        case 1: M3D_CT(1); break;
+        case 2: M3D_CT(2); break;
+        case 3: M3D_CT(3); break;  // the reference default, centroid_z_support = 7
+        default: M3D_CT(-1); break;
+    }
+#undef M3D_CT
 }
 
 }  // namespace
@@ -107,17 +171,14 @@ extern "C" int m3d_centroid_statistics(m3d_ctx* ctx, const int32_t* labels_dev, 
     M3D_CUDA(cudaMemsetAsync(peak_dev, 0, cells * sizeof(float), st));
     const long long plane = (long long)dims[1] * dims[2];
     const int blocks = (int)((plane + CT_THREADS - 1) / CT_THREADS);
-    if (dtype == M3D_DTYPE_U16) {
-        M3D_LAUNCH(ctx, KF_CENTROID, st,
-                   centroid_stats_kernel<uint16_t><<<blocks, CT_THREADS, 0, st>>>(
-                       labels_dev, reinterpret_cast<const uint16_t*>(stack_dev), (int)dims[0], (int)dims[1], (int)dims[2],
-                       half, label_code_dev, ctx->d_cw_mask, ctx->K, ctx->n_bits, (long long)minlength, sums_dev, peak_dev));
-    } else {
-        M3D_LAUNCH(ctx, KF_CENTROID, st,
-                   centroid_stats_kernel<float><<<blocks, CT_THREADS, 0, st>>>(
-                       labels_dev, reinterpret_cast<const float*>(stack_dev), (int)dims[0], (int)dims[1], (int)dims[2],
-                       half, label_code_dev, ctx->d_cw_mask, ctx->K, ctx->n_bits, (long long)minlength, sums_dev, peak_dev));
-    }
+    if (dtype == M3D_DTYPE_U16)
+        launch_centroid<uint16_t>(ctx, blocks, st, half, labels_dev, reinterpret_cast<const uint16_t*>(stack_dev),
+                                  (int)dims[0], (int)dims[1], (int)dims[2], label_code_dev, (long long)minlength,
+                                  sums_dev, peak_dev);
+    else
+        launch_centroid<float>(ctx, blocks, st, half, labels_dev, reinterpret_cast<const float*>(stack_dev),
+                               (int)dims[0], (int)dims[1], (int)dims[2], label_code_dev, (long long)minlength, sums_dev,
+                               peak_dev);
     M3D_CHECK_LAUNCH();
     return M3D_OK;
 }

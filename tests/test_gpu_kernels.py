@@ -418,7 +418,7 @@ def test_centroid_statistics_upstream_known_answer_and_random():
     codes = rng.integers(0, 5, n_lab + 1).astype(np.int16)
     codes[0] = -1
     ctx = DecodeContext(cb, (), device=0)
-    for z_support in (1, 3, 7):
+    for z_support in (1, 3, 5, 7, 9):
         sums, peak = ctx.centroid_statistics(torch.from_numpy(lab).cuda(), torch.from_numpy(stack).cuda(), z_support,
                                              torch.from_numpy(codes).cuda())
         sums, peak = sums.cpu().numpy(), peak.cpu().numpy()
