@@ -405,6 +405,35 @@ def run_b200(args):
             "api": "PixelDecoder.decode_one_tile(lowpass_sigma=None, normalization_method='global')",
         }
 
+        # the same call with the stack in PAGEABLE host memory (what a datastore returning plain NumPy
+        # arrays gives the loader): staged through the library's pinned ring by m3d_upload_batch
+        if world == 1 and not args.no_extras:
+            pageable = np.empty(tuple(host.shape), dtype=np.uint16)
+            np.copyto(pageable, host.numpy())
+            ds2 = ArrayDataStore(Path(tmp.name) / "qi2labdatastore_pageable", codebook=df_cb)
+            ds2.add_tile(pageable)
+            ds2.save_decode_normalization_vectors(None, "global", nrm, bkg)
+            dec2 = PixelDecoder(ds2, merfish_bits=16, verbose=0)
+            for i in range(3):
+                if i == 1:
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                dec2.decode_one_tile(0, gpu_id=local, lowpass_sigma=None, magnitude_threshold=MAG,
+                                     minimum_pixels=MIN_PX, normalization_method="global")
+            pg_s = (time.perf_counter() - t0) / 2
+            t0 = time.perf_counter()
+            plain = torch.from_numpy(pageable[0]).to(dev)
+            torch.cuda.synchronize()
+            plain_gbs = pageable[0].nbytes / (time.perf_counter() - t0) / 1e9
+            extras["e2e_pageable_host"] = {
+                "ms_per_step": pg_s * 1e3, "gvoxel_per_s": n_vox / pg_s / 1e9,
+                "staged_h2d_gb_s_incl_decode": host.numel() * 2 / pg_s / 1e9,
+                "plain_pageable_cudaMemcpy_gb_s": plain_gbs,
+                "note": "decode_one_tile with the tile in pageable NumPy memory; m3d_upload_batch stages through "
+                        "8 x 32 MB pinned slots filled by host threads",
+            }
+            del plain, dec2, pageable
+
     line = None
     if rank == 0:
         cpu = None

@@ -64,6 +64,16 @@ int m3d_set_normalization(m3d_ctx* ctx, const float* background_host,
 int m3d_set_thresholds(m3d_ctx* ctx, float pixel_threshold, float magnitude_lo,
                        float magnitude_hi);
 
+/* Host -> device staging for `_load_bit_data` (PD:1861-1894 hands the GPU NumPy arrays, i.e. pageable memory).
+ * Page-locked sources are copied with one cudaMemcpyAsync; pageable ones go through a ring of pinned slots
+ * owned by the context, filled by a few host threads while earlier slots drain over PCIe (~49 GB/s instead
+ * of the ~11 GB/s of a pageable cudaMemcpy).  The call returns when every byte has been STAGED or enqueued:
+ * the sources may be released, the copies complete in order on `stream`.  m3d_upload_batch runs all pieces
+ * (e.g. the bit volumes of one tile) through one pipeline so the ring never idles between them. */
+int m3d_upload(m3d_ctx* ctx, const void* src_host, void* dst_dev, int64_t n_bytes, void* stream);
+int m3d_upload_batch(m3d_ctx* ctx, int n_pieces, const void* const* src_host, void* const* dst_dev,
+                     const int64_t* n_bytes, void* stream);
+
 /* _load_bit_data weighting (PD:1879-1881): out = float32(readout) * float32(predictor). */
 int m3d_weight(m3d_ctx* ctx, const uint16_t* readout_dev, const float* predictor_dev,
                int64_t n, float* out_dev, void* stream);

@@ -462,24 +462,20 @@ class PixelDecoder:
         into the round-1 frame when the bit carries a decode-time transform."""
         import torch
 
-        r = torch.from_numpy(np.ascontiguousarray(readout)).to(ctx.device, non_blocking=True)
+        def to_dev(arr, dtype):
+            src = np.ascontiguousarray(arr, dtype=dtype)
+            dst = torch.empty(src.shape, dtype=torch.float32 if dtype == np.float32 else torch.uint16,
+                              device=ctx.device)
+            ctx.upload([(src, dst)])
+            return dst
+
+        is_float = np.asarray(readout).dtype.kind == "f"
+        r = to_dev(readout, np.float32 if is_float else np.uint16)
+        p = None if self._is_unit_predictor(predictor) else to_dev(predictor, np.float32)
         if warp is not None:
-            if r.dtype not in (torch.uint16, torch.float32):
-                r = torch.from_numpy(np.ascontiguousarray(readout, dtype=np.uint16)).to(ctx.device)
-            p = None
-            if not self._is_unit_predictor(predictor):
-                p = torch.from_numpy(np.ascontiguousarray(predictor, dtype=np.float32)).to(ctx.device)
             return ctx.warp_affine(r, warp[0], warp[1], predictor=p)
-        if r.dtype == torch.float32:
-            img = r
-            if not self._is_unit_predictor(predictor):
-                img = img * torch.from_numpy(np.ascontiguousarray(predictor, dtype=np.float32)).to(ctx.device)
-            return img
-        if r.dtype not in (torch.uint16, torch.int16):
-            r = torch.from_numpy(np.ascontiguousarray(readout, dtype=np.uint16)).to(ctx.device)
-        p = None
-        if not self._is_unit_predictor(predictor):
-            p = torch.from_numpy(np.ascontiguousarray(predictor, dtype=np.float32)).to(ctx.device)
+        if is_float:
+            return r if p is None else r * p
         return ctx.weight(r, p)
 
     def _load_bit_data(self, feature_predictor_threshold: float | None = 0.1, gpu_id: int = 0,
@@ -527,8 +523,14 @@ class PixelDecoder:
         st.clear()
 
         def to_dev(arr, dtype):
-            return torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(ctx.device, non_blocking=True)
+            src = np.ascontiguousarray(arr, dtype=dtype)
+            dst = torch.empty(src.shape, dtype=torch.float32 if dtype == np.float32 else torch.uint16,
+                              device=ctx.device)
+            ctx.upload([(src, dst)])
+            return dst
 
+        # every host -> device copy goes through m3d_upload_batch: straight DMA for page-locked arrays,
+        # the library's pinned staging ring for the pageable arrays a datastore normally returns
         if any(w is not None for _r, _p, w in loaded):
             stack = torch.empty((len(bit_ids), *shape), dtype=torch.float32, device=ctx.device)
             for i, (ra, pa, warp) in enumerate(loaded):
@@ -548,8 +550,7 @@ class PixelDecoder:
         else:
             dt = torch.float32 if float_input else torch.uint16
             stack = torch.empty((len(bit_ids), *shape), dtype=dt, device=ctx.device)
-            for i, (ra, _pa, _w) in enumerate(loaded):
-                stack[i].copy_(torch.from_numpy(np.ascontiguousarray(ra[a:b], dtype=npdt)), non_blocking=True)
+            pieces = [(np.ascontiguousarray(ra[a:b], dtype=npdt), stack[i]) for i, (ra, _pa, _w) in enumerate(loaded)]
             pred = None
             if any(pa is not None for _r, pa, _w in loaded):
                 pred = torch.empty((len(bit_ids), *shape), dtype=torch.float32, device=ctx.device)
@@ -557,8 +558,8 @@ class PixelDecoder:
                     if pa is None:
                         pred[i].fill_(1.0)
                     else:
-                        pred[i].copy_(torch.from_numpy(np.ascontiguousarray(pa[a:b], dtype=np.float32)),
-                                      non_blocking=True)
+                        pieces.append((np.ascontiguousarray(pa[a:b], dtype=np.float32), pred[i]))
+            ctx.upload(pieces)
             st["readout"], st["predictor"] = stack, pred
         self._load_coordinate_metadata()
 

@@ -34,6 +34,10 @@ SIGNATURES = {
     "m3d_destroy": (C.c_int, [C.c_void_p]),
     "m3d_set_normalization": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "m3d_set_thresholds": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float]),
+    "m3d_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "m3d_upload_batch": (
+        C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p]
+    ),
     "m3d_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "m3d_warp_affine": (
         C.c_int,
@@ -235,6 +239,23 @@ class DecodeContext:
     @staticmethod
     def _dims(shape_zyx):
         return _c_i64_3(*[int(s) for s in shape_zyx])
+
+    def upload(self, pieces):
+        """Host -> device copies of ``[(numpy C-contiguous array, device tensor of the same byte size), ...]``
+        through the library's pinned staging ring (pageable sources) or straight DMA (pinned sources).
+        Returns once the sources are no longer needed; the copies complete on the current stream."""
+        pieces = [(s, d) for s, d in pieces if s.nbytes]
+        if not pieces:
+            return
+        n = len(pieces)
+        srcs, dsts, sizes = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_int64 * n)()
+        for i, (src, dst) in enumerate(pieces):
+            if not src.flags.c_contiguous:
+                raise M3dError("upload() takes C-contiguous host arrays")
+            if src.nbytes != dst.numel() * dst.element_size() or not dst.is_cuda or not dst.is_contiguous():
+                raise M3dError("upload(): destination must be a contiguous device tensor of the source's byte size")
+            srcs[i], dsts[i], sizes[i] = src.ctypes.data, dst.data_ptr(), src.nbytes
+        _check(self._lib.m3d_upload_batch(self._h, n, srcs, dsts, sizes, _stream(self.device)), "m3d_upload_batch")
 
     def weight(self, readout, predictor, out=None):
         import torch

@@ -202,9 +202,12 @@ extern "C" int m3d_create(int device, int n_bits, int n_codewords, const float* 
     return M3D_OK;
 }
 
+void m3d_release_upload_ring(m3d_ctx* ctx);  // upload.cu
+
 extern "C" int m3d_destroy(m3d_ctx* ctx) {
     if (!ctx) return M3D_OK;
     cudaSetDevice(ctx->device);
+    m3d_release_upload_ring(ctx);
     for (auto& sp : ctx->spans) {
         cudaEventDestroy(sp.a);
         cudaEventDestroy(sp.b);

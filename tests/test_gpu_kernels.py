@@ -469,3 +469,36 @@ def test_inertia_eigvals_match_lapack():
     got = ctx.inertia_eigvals(torch.from_numpy(tab).cuda()).cpu().numpy()
     ctx.close()
     np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+
+
+def test_staged_upload_is_byte_identical():
+    """m3d_upload_batch: pageable sources through the pinned ring (ragged sizes, more chunks than ring
+    slots, several pieces in one pipeline, repeated calls reusing the ring) and pinned sources via DMA."""
+    import torch
+
+    from merfish3d_analysis_b200._capi import DecodeContext, M3dError
+
+    ctx = DecodeContext(np.array([[1.0]], dtype=np.float32), (), device=0)
+    rng = np.random.default_rng(3)
+    sizes = [1, 4097, (1 << 20) + 3, (32 << 20), (32 << 20) * 9 + 12345, 7]
+    for rep in range(2):
+        srcs = [rng.integers(0, 256, n, dtype=np.uint8) for n in sizes]
+        dsts = [torch.zeros(n, dtype=torch.uint8, device="cuda") for n in sizes]
+        ctx.upload(list(zip(srcs, dsts)))
+        torch.cuda.synchronize()
+        for s, d in zip(srcs, dsts):
+            assert np.array_equal(d.cpu().numpy(), s), (rep, s.size)
+    # uint16 volume slices (what the tile loader passes) + a pinned source in the same batch
+    vol = rng.integers(0, 65536, (5, 300, 1000), dtype=np.uint16)
+    pinned = torch.empty((2, 300, 1000), dtype=torch.uint16, pin_memory=True)
+    pinned.numpy()[...] = vol[:2]
+    stack = torch.zeros((3, 3, 300, 1000), dtype=torch.uint16, device="cuda")
+    ctx.upload([(vol[1:4], stack[0]), (np.ascontiguousarray(vol[2:5]), stack[1]), (pinned.numpy()[:], stack[2, :2])])
+    torch.cuda.synchronize()
+    got = stack.cpu().numpy()
+    assert np.array_equal(got[0], vol[1:4]) and np.array_equal(got[1], vol[2:5]) and np.array_equal(got[2, :2], vol[:2])
+    with pytest.raises(M3dError):
+        ctx.upload([(vol[:, ::2], stack[0])])  # not contiguous
+    with pytest.raises(M3dError):
+        ctx.upload([(vol[0], stack[0])])  # size mismatch
+    ctx.close()
