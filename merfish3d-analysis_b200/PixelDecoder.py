@@ -974,15 +974,17 @@ class PixelDecoder:
         minimum_pixels: float | None = None,
         use_normalization: bool | None = True,
         normalization_method: Literal["iterative", "global", "none"] | None = None,
+        slabs_per_rank: int = 1,
     ):
         """Decode ONE tile split into z-slabs; result identical to ``decode_one_tile``.
 
-        Under ``torch.distributed`` (world > 1, ``n_slabs`` None) every rank holds one slab: the
-        boundary planes travel by send/recv, the small equivalence / area lists by all_gather, and
-        rank 0 ends up with the complete transcript table (``decoded_barcodes``); each rank keeps
-        its slab of the decoded image.  With ``n_slabs`` given, the slabs are processed one after
-        another on this GPU (volumes larger than HBM or than 2^32 voxels).  No reference
-        counterpart: SURVEY.md 8e."""
+        Under ``torch.distributed`` (world > 1, ``n_slabs`` None) every rank owns a contiguous z range,
+        processed as ``slabs_per_rank`` slabs one after another (at most two resident, so a rank can
+        own more planes than fit in HBM at once: config 5 on 2 GPUs).  The boundary planes between
+        ranks travel by send/recv, the small equivalence / area lists by all_gather, and rank 0 ends up
+        with the complete transcript table (``decoded_barcodes``); each rank keeps its part of the
+        decoded image.  With ``n_slabs`` given, all slabs are processed one after another on this GPU
+        (volumes larger than HBM or than 2^32 voxels).  No reference counterpart: SURVEY.md 8e."""
         from . import sharded as sh
 
         import torch
@@ -1027,10 +1029,16 @@ class PixelDecoder:
         probe = probe.result() if hasattr(probe, "result") else probe
         zs_, ze_, _ = self._z_slice.indices(int(probe.shape[0]))
         full_z = max(ze_ - zs_, 0)
-        bounds = sh.split_z(full_z, world if distributed else int(n_slabs or 1))
-        mine = [rank] if distributed else list(range(len(bounds)))
-        if distributed and rank >= len(bounds):
-            mine = []
+        k = max(1, int(slabs_per_rank))
+        bounds = sh.split_z(full_z, world * k if distributed else int(n_slabs or 1))
+        if distributed:
+            # contiguous runs of slabs per rank; ranks without planes (more ranks than planes) own nothing
+            per = (len(bounds) + world - 1) // world
+            mine = list(range(rank * per, min((rank + 1) * per, len(bounds))))
+            owner = {r: r // per for r in range(len(bounds))}
+        else:
+            mine = list(range(len(bounds)))
+            owner = {r: 0 for r in mine}
         results: dict[int, sh.SlabResult] = {}
         kept: dict[int, tuple] = {}  # slab -> (stack, decoded, labels) still on the device
         records: dict[tuple, dict] = {}
@@ -1058,13 +1066,13 @@ class PixelDecoder:
             res = sh.SlabResult(z0, z1, tuple(stack.shape[2:]), table)
             if distributed:
                 reqs = []
-                if rank + 1 < len(bounds):
+                if r + 1 < len(bounds) and owner[r + 1] != rank:
                     # one int32 (2, Y, X) message: decoded plane (NCCL has no int16) + label plane
                     out_planes = torch.stack([decoded[-1].to(torch.int32), labels[-1]]).contiguous()
-                    reqs.append(dist.isend(out_planes, rank + 1))
-                if rank > 0:
+                    reqs.append(dist.isend(out_planes, owner[r + 1]))
+                if r > 0 and owner[r - 1] != rank:
                     in_planes = torch.empty((2, *stack.shape[2:]), dtype=torch.int32, device=stack.device)
-                    dist.recv(in_planes, rank - 1)
+                    dist.recv(in_planes, owner[r - 1])
                     prev_planes = (in_planes[0].to(torch.int16).contiguous(), in_planes[1].contiguous())
                 for q in reqs:
                     q.wait()
@@ -1077,10 +1085,10 @@ class PixelDecoder:
             kept[r] = (stack, decoded, labels)
             prev_planes = (decoded[-1].contiguous(), labels[-1].contiguous())
             del stack
-            if not distributed and (r - 1) in kept:
+            if (r - 1) in kept:
                 retire(r - 1)  # both of its interfaces are known now: at most two slabs stay resident
-        if not distributed and mine:
-            retire(mine[-1])
+        if mine and (not distributed or mine[-1] == len(bounds) - 1):
+            retire(mine[-1])  # no upper neighbour; otherwise the next rank computes that interface (below)
         # ---- resolve (identical on every rank)
         summary = {
             r: dict(z0=s.z0, z1=s.z1, shape_yx=s.shape_yx, areas=s.table[:, _COL_AREA].copy(), pairs=s.pairs,
@@ -1104,12 +1112,11 @@ class PixelDecoder:
         for g in groups:
             for r, cid in g:
                 need.setdefault(order[r], []).append(cid)
-        if distributed:
-            for r in mine:
-                stack, decoded, labels = kept[r]
-                for cid, rec in sh.slab_records(ctx, stack, decoded, labels, sorted(need.get(r, [])), optimize).items():
-                    records[(r, cid)] = rec
-                decoded_slabs.append(decoded)
+        for r in sorted(kept):  # a rank's last slab: its upper interface was resolved on the next rank
+            stack, decoded, labels = kept[r]
+            for cid, rec in sh.slab_records(ctx, stack, decoded, labels, sorted(need.get(r, [])), optimize).items():
+                records[(r, cid)] = rec
+            decoded_slabs.append(decoded)
         local_tabs = {r: results[r].table[keep_local[order.index(r)]] for r in mine}
         if distributed:
             gathered = [None] * world if rank == 0 else None

@@ -78,19 +78,21 @@ def main():
     dist.barrier()
     ds = ArrayDataStore(root)
     t_big = len(ds.tile_ids) - 1
-    for sig in (None, (3.0, 1.0, 1.0)):
+    for sig, per_rank in ((None, 1), ((3.0, 1.0, 1.0), 1), (None, 3), ((3.0, 1.0, 1.0), 2)):
         d = PixelDecoder(ds, merfish_bits=16, num_gpus=world, verbose=0)
-        d.decode_one_tile_sharded(t_big, lowpass_sigma=sig, minimum_pixels=12)
+        d.decode_one_tile_sharded(t_big, lowpass_sigma=sig, minimum_pixels=12, slabs_per_rank=per_rank)
         slab = d.decoded_image
+        u = PixelDecoder(ds, merfish_bits=16, num_gpus=1, verbose=0)
+        u.decode_one_tile(t_big, gpu_id=local, lowpass_sigma=sig, minimum_pixels=12)
+        z0, z1 = d._slab_bounds[0][0], d._slab_bounds[-1][1]
+        assert len(d._slab_bounds) == per_rank
+        np.testing.assert_array_equal(slab, u.decoded_image[z0:z1])  # every rank: its planes of the decoded image
         if rank == 0:
-            u = PixelDecoder(ds, merfish_bits=16, num_gpus=1, verbose=0)
-            u.decode_one_tile(t_big, lowpass_sigma=sig, minimum_pixels=12)
             import pandas as pd
 
             pd.testing.assert_frame_equal(d.decoded_barcodes, u.decoded_barcodes)
-            z0, z1 = d._slab_bounds[0]
-            np.testing.assert_array_equal(slab, u.decoded_image[z0:z1])
-            print(f"dist_smoke ok: z-slab sharded x{world} lowpass={sig}: {len(u.decoded_barcodes)} transcripts identical")
+            print(f"dist_smoke ok: z-slab sharded x{world}, {per_rank} slab(s) per rank, lowpass={sig}: "
+                  f"{len(u.decoded_barcodes)} transcripts identical")
         dist.barrier()
     dist.destroy_process_group()
 
