@@ -45,7 +45,7 @@ def run_tile_scenario(name, sc, RefPD):
         ds = ArrayDataStore(tmp / "qi2labdatastore", codebook=df_cb, microscope_type=sc.get("microscope", "3D"))
         ds.add_tile(stack, predictors=pred, stage_origin_zyx_um=sc.get("origin"))
         ds.save_decode_normalization_vectors(None, "global", nrm, bkg)
-        dec = RefPD(ds, merfish_bits=16, verbose=0, z_range=sc.get("z_range"), excluded_gene_ids=excluded)
+        dec = RefPD(ds, merfish_bits=int(sc.get("bits", 16)), verbose=0, z_range=sc.get("z_range"), excluded_gene_ids=excluded)
         if sc.get("chroma"):
             dec._optimize_normalization_weights = True
             dec._collect_chromatic_centroids = True

@@ -20,6 +20,9 @@ SCENARIOS = {
     # optimiser mode with per-on-bit weighted centroids (raw float32 intensities, z-crop offset applied)
     "chroma": dict(shape=(12, 40, 48), seed=15, density=5e-3, lowpass=(1.0, 0.5, 0.5), norm="global", min_px=4,
                    z_range=(1, 11), chroma=True, bkg=150.0, nrm=500.0, mag=(0.9, 10.0)),
+    # configs[3] flavour: 22 bits, 300 random weight-4 codewords, 2-D decode mode
+    "bits22": dict(shape=(4, 40, 48), seed=16, density=8e-3, lowpass=None, norm="global", min_px=4, bits=22,
+                   microscope="2D"),
     "excl_crop": dict(shape=(9, 32, 40), seed=14, density=6e-3, lowpass=None, norm="global", min_px=3,
                       z_range=(2, 8), exclude=3),
 }
@@ -29,13 +32,14 @@ SCENARIOS = {
 
 def scenario_inputs(sc):
     """(codebook df, oracle codebook dict, stack uint16, predictor | None, bkg, nrm, excluded gene ids | None)."""
-    df_cb, cb = cases.codebook16()
+    n_bits = int(sc.get("bits", 16))
+    df_cb, cb = cases.codebook16() if n_bits == 16 else cases.codebook22(n_words=300)
     stack = cases.small_stack(cb["matrix"], shape=sc["shape"], seed=sc["seed"], density=sc["density"])
     rng = np.random.default_rng(sc["seed"] + 1000)
     pred = None
     if sc.get("predictor"):
         pred = rng.uniform(0.0, 1.0, size=stack.shape).astype(np.float32)
-    bkg, nrm = cases.simple_vectors(16, bkg=sc.get("bkg", 200.0), nrm=sc.get("nrm", 900.0), seed=sc["seed"])
+    bkg, nrm = cases.simple_vectors(n_bits, bkg=sc.get("bkg", 200.0), nrm=sc.get("nrm", 900.0), seed=sc["seed"])
     excluded = None
     if sc.get("exclude"):
         genes = [g for g in df_cb["gene_id"] if not str(g).lower().startswith("blank")]

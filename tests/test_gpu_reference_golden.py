@@ -32,7 +32,7 @@ def test_cuda_path_equals_reference_golden(tmp_path, name):
     ref = golden_table(g)
     kw = dict(lowpass_sigma=sc["lowpass"], minimum_pixels=sc["min_px"], magnitude_threshold=sc.get("mag"),
               normalization_method=sc["norm"])
-    dec = PixelDecoder(ds, merfish_bits=16, verbose=0, z_range=sc.get("z_range"), excluded_gene_ids=excluded)
+    dec = PixelDecoder(ds, merfish_bits=int(sc.get("bits", 16)), verbose=0, z_range=sc.get("z_range"), excluded_gene_ids=excluded)
     dec._optimize_normalization_weights = dec._collect_chromatic_centroids = bool(sc.get("chroma"))
     image, scaled, magnitude, distance, decoded = dec.decode_one_tile(0, return_results=True, **kw)
     np.testing.assert_array_equal(image, g["image"])
@@ -42,7 +42,7 @@ def test_cuda_path_equals_reference_golden(tmp_path, name):
     np.testing.assert_array_equal(scaled, g["scaled"])
     compare_with_reference_table(dec.decoded_barcodes, ref, rel=REL)
     # production path: gate + search + fused labelling, no result images
-    dec2 = PixelDecoder(ds, merfish_bits=16, verbose=0, z_range=sc.get("z_range"), excluded_gene_ids=excluded)
+    dec2 = PixelDecoder(ds, merfish_bits=int(sc.get("bits", 16)), verbose=0, z_range=sc.get("z_range"), excluded_gene_ids=excluded)
     dec2._optimize_normalization_weights = dec2._collect_chromatic_centroids = bool(sc.get("chroma"))
     assert dec2.decode_one_tile(0, **kw) is None
     np.testing.assert_array_equal(dec2.decoded_image, g["decoded"])
