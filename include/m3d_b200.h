@@ -73,6 +73,12 @@ int m3d_set_thresholds(m3d_ctx* ctx, float pixel_threshold, float magnitude_lo,
 int m3d_upload(m3d_ctx* ctx, const void* src_host, void* dst_dev, int64_t n_bytes, void* stream);
 int m3d_upload_batch(m3d_ctx* ctx, int n_pieces, const void* const* src_host, void* const* dst_dev,
                      const int64_t* n_bytes, void* stream);
+/* Same, and `on_piece(piece, user)` is called on the calling thread as soon as piece `piece` is completely
+ * enqueued on `stream` (pieces complete in order).  The loader uses it to record an event and start the
+ * per-bit low-pass of that volume on another stream while the next bit volumes are still crossing PCIe. */
+typedef void (*m3d_piece_callback)(int piece, void* user);
+int m3d_upload_batch_cb(m3d_ctx* ctx, int n_pieces, const void* const* src_host, void* const* dst_dev,
+                        const int64_t* n_bytes, void* stream, m3d_piece_callback on_piece, void* user);
 
 /* _load_bit_data weighting (PD:1879-1881): out = float32(readout) * float32(predictor). */
 int m3d_weight(m3d_ctx* ctx, const uint16_t* readout_dev, const float* predictor_dev,

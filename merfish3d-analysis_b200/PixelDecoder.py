@@ -134,6 +134,7 @@ class PixelDecoder:
         self._iterative_background_vector = None
         self._load_tile_decoding = False
         self._fuse_label_args = None
+        self._copy_streams: dict[int, object] = {}
         self._contexts: dict[int, DecodeContext] = {}
         self._context_excluded: dict[int, tuple] = {}
         self._device_state: dict[int, dict] = {}
@@ -479,7 +480,7 @@ class PixelDecoder:
         return ctx.weight(r, p)
 
     def _load_bit_data(self, feature_predictor_threshold: float | None = 0.1, gpu_id: int = 0,
-                       z_bounds: tuple[int, int] | None = None) -> None:
+                       z_bounds: tuple[int, int] | None = None, lowpass_sigma=None) -> None:
         """PD:1828-1946: gather the tile's bit volumes into one device stack + coordinate metadata.
 
         Registered data (every bit's decode-time transform is the identity): device state
@@ -550,18 +551,59 @@ class PixelDecoder:
         else:
             dt = torch.float32 if float_input else torch.uint16
             stack = torch.empty((len(bit_ids), *shape), dtype=dt, device=ctx.device)
-            pieces = [(np.ascontiguousarray(ra[a:b], dtype=npdt), stack[i]) for i, (ra, _pa, _w) in enumerate(loaded)]
             pred = None
             if any(pa is not None for _r, pa, _w in loaded):
                 pred = torch.empty((len(bit_ids), *shape), dtype=torch.float32, device=ctx.device)
-                for i, (_ra, pa, _w) in enumerate(loaded):
+            pieces, piece_bit = [], []  # per bit: readout, then its predictor weights (if stored)
+            for i, (ra, pa, _w) in enumerate(loaded):
+                pieces.append((np.ascontiguousarray(ra[a:b], dtype=npdt), stack[i]))
+                piece_bit.append(i)
+                if pred is not None:
                     if pa is None:
                         pred[i].fill_(1.0)
                     else:
                         pieces.append((np.ascontiguousarray(pa[a:b], dtype=np.float32), pred[i]))
-            ctx.upload(pieces)
-            st["readout"], st["predictor"] = stack, pred
+                        piece_bit.append(i)
+            if lowpass_sigma is None:
+                ctx.upload(pieces)
+                st["readout"], st["predictor"] = stack, pred
+            else:
+                st["readout"], st["predictor"] = None, None
+                st["stack"] = self._upload_and_lowpass(ctx, pieces, piece_bit, stack, pred, lowpass_sigma)
+                st["lowpass_done"] = True
         self._load_coordinate_metadata()
+
+    def _upload_and_lowpass(self, ctx, pieces, piece_bit, stack, pred, sigma):
+        """Registered tiles with the low-pass on: the per-bit Gaussian (PD:1982-2024) of bit b runs on the
+        compute stream as soon as its volume has arrived, while the volumes of the later bits are still
+        crossing PCIe on a copy stream -- the filter (float64-pipe bound, ~3.7 ms per bit) hides behind the
+        transfer (~15 ms per bit).  ``piece_bit[i]`` = bit that piece i belongs to (pieces of one bit are
+        adjacent)."""
+        import torch
+
+        out = torch.empty(tuple(stack.shape), dtype=torch.float32, device=ctx.device)
+        compute = torch.cuda.current_stream(ctx.device)
+        copy = self._copy_streams.get(ctx.device.index)
+        if copy is None:
+            copy = self._copy_streams[ctx.device.index] = torch.cuda.Stream(device=ctx.device)
+        last_piece_of = {b: i for i, b in enumerate(piece_bit)}  # later pieces overwrite: the bit's last one
+        bit_done_at = {i: b for b, i in last_piece_of.items()}
+
+        def bit_arrived(piece):
+            b = bit_done_at.get(piece)
+            if b is None:
+                return
+            ev = torch.cuda.Event()
+            ev.record(copy)
+            compute.wait_event(ev)
+            with torch.cuda.stream(compute):
+                ctx.lowpass(stack[b : b + 1], sigma, not self._is_3D,
+                            predictor=None if pred is None else pred[b : b + 1], out=out[b : b + 1])
+
+        copy.wait_stream(compute)  # buffers just allocated / filled on the compute stream
+        with torch.cuda.stream(copy):
+            ctx.upload(pieces, on_piece=bit_arrived)
+        return out
 
     def _load_coordinate_metadata(self) -> None:
         """PD:1900-1943."""
@@ -935,11 +977,16 @@ class PixelDecoder:
             minimum_pixels = self._default_minimum_pixels()
         self._prepare_normalization_state(normalization_method, use_normalization, gpu_id, lowpass_sigma)
         self._tile_idx = tile_idx
-        self._load_bit_data(feature_predictor_threshold=feature_predictor_threshold, gpu_id=gpu_id)
-        self._filter_type = "raw"
         sigma = self._effective_lowpass_sigma(lowpass_sigma)
-        if self._lowpass_active(sigma):
-            self._lp_filter(sigma=sigma, gpu_id=gpu_id)
+        lp_active = self._lowpass_active(sigma)
+        self._load_bit_data(feature_predictor_threshold=feature_predictor_threshold, gpu_id=gpu_id,
+                            lowpass_sigma=sigma if lp_active else None)
+        self._filter_type = "raw"
+        if lp_active:
+            if self._device_state[gpu_id].get("lowpass_done"):
+                self._filter_type = "lp"  # filtered bit by bit behind the upload
+            else:
+                self._lp_filter(sigma=sigma, gpu_id=gpu_id)
         self._fuse_label_args = (minimum_pixels, MAXIMUM_PIXELS)
         try:
             self._decode_pixels(magnitude_threshold=magnitude_threshold, gpu_id=gpu_id,

@@ -38,6 +38,11 @@ SIGNATURES = {
     "m3d_upload_batch": (
         C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p]
     ),
+    "m3d_upload_batch_cb": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p,
+         C.c_void_p, C.c_void_p],
+    ),
     "m3d_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "m3d_warp_affine": (
         C.c_int,
@@ -111,6 +116,7 @@ SIGNATURES = {
     "m3d_kernel_time_ms": (C.c_double, [C.c_void_p, C.c_int]),
 }
 
+_PIECE_CB = C.CFUNCTYPE(None, C.c_int, C.c_void_p)
 _lib = None
 
 
@@ -240,11 +246,13 @@ class DecodeContext:
     def _dims(shape_zyx):
         return _c_i64_3(*[int(s) for s in shape_zyx])
 
-    def upload(self, pieces):
+    def upload(self, pieces, on_piece=None):
         """Host -> device copies of ``[(numpy C-contiguous array, device tensor of the same byte size), ...]``
         through the library's pinned staging ring (pageable sources) or straight DMA (pinned sources).
-        Returns once the sources are no longer needed; the copies complete on the current stream."""
-        pieces = [(s, d) for s, d in pieces if s.nbytes]
+        Returns once the sources are no longer needed; the copies complete on the current stream.
+        ``on_piece(i)`` is called (on this thread) as soon as piece i is completely enqueued on the stream,
+        while later pieces are still being staged."""
+        pieces = list(pieces)
         if not pieces:
             return
         n = len(pieces)
@@ -255,7 +263,25 @@ class DecodeContext:
             if src.nbytes != dst.numel() * dst.element_size() or not dst.is_cuda or not dst.is_contiguous():
                 raise M3dError("upload(): destination must be a contiguous device tensor of the source's byte size")
             srcs[i], dsts[i], sizes[i] = src.ctypes.data, dst.data_ptr(), src.nbytes
-        _check(self._lib.m3d_upload_batch(self._h, n, srcs, dsts, sizes, _stream(self.device)), "m3d_upload_batch")
+        if on_piece is None:
+            _check(self._lib.m3d_upload_batch(self._h, n, srcs, dsts, sizes, _stream(self.device)), "m3d_upload_batch")
+            return
+        failure = []
+
+        def trampoline(piece, _user):
+            if failure:
+                return
+            try:
+                on_piece(int(piece))
+            except BaseException as e:  # noqa: BLE001 - re-raised below, ctypes would swallow it
+                failure.append(e)
+
+        cb = _PIECE_CB(trampoline)
+        rc = self._lib.m3d_upload_batch_cb(self._h, n, srcs, dsts, sizes, _stream(self.device),
+                                           C.cast(cb, C.c_void_p), None)
+        if failure:
+            raise failure[0]
+        _check(rc, "m3d_upload_batch_cb")
 
     def weight(self, readout, predictor, out=None):
         import torch

@@ -56,8 +56,8 @@ void m3d_release_upload_ring(m3d_ctx* ctx) {
     }
 }
 
-extern "C" int m3d_upload_batch(m3d_ctx* ctx, int n_pieces, const void* const* src_host, void* const* dst_dev,
-                                const int64_t* n_bytes, void* stream) {
+extern "C" int m3d_upload_batch_cb(m3d_ctx* ctx, int n_pieces, const void* const* src_host, void* const* dst_dev,
+                                   const int64_t* n_bytes, void* stream, m3d_piece_callback on_piece, void* user) {
     if (!ctx || n_pieces < 0 || (n_pieces > 0 && (!src_host || !dst_dev || !n_bytes)))
         return m3d_fail(M3D_ERR_ARG, "m3d_upload: bad argument");
     M3D_CUDA(cudaSetDevice(ctx->device));
@@ -66,11 +66,16 @@ extern "C" int m3d_upload_batch(m3d_ctx* ctx, int n_pieces, const void* const* s
         const char* src;
         char* dst;
         size_t n;
+        bool direct;  // page-locked source queued behind staged chunks: plain DMA, no slot
     };
     std::vector<Chunk> chunks;
+    std::vector<int> last_chunk_of;  // last_chunk_of[j] = piece whose final chunk is j, else -1
     for (int p = 0; p < n_pieces; ++p) {
         if (n_bytes[p] < 0) return m3d_fail(M3D_ERR_ARG, "m3d_upload: negative size");
-        if (n_bytes[p] == 0) continue;
+        if (n_bytes[p] == 0) {
+            if (on_piece) on_piece(p, user);
+            continue;
+        }
         if (!src_host[p] || !dst_dev[p]) return m3d_fail(M3D_ERR_ARG, "m3d_upload: null pointer");
         cudaPointerAttributes attr;
         const cudaError_t pe = cudaPointerGetAttributes(&attr, src_host[p]);
@@ -79,12 +84,21 @@ extern "C" int m3d_upload_batch(m3d_ctx* ctx, int n_pieces, const void* const* s
             (pe == cudaSuccess) && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
         const size_t total = (size_t)n_bytes[p];
         if (pinned || total <= ((size_t)1 << 20)) {  // page-locked already (or tiny): straight DMA
-            M3D_CUDA(cudaMemcpyAsync(dst_dev[p], src_host[p], total, cudaMemcpyHostToDevice, st));
+            // pieces complete on the stream in issue order: staged chunks of earlier pieces go first
+            if (chunks.empty()) {
+                M3D_CUDA(cudaMemcpyAsync(dst_dev[p], src_host[p], total, cudaMemcpyHostToDevice, st));
+                if (on_piece) on_piece(p, user);
+                continue;
+            }
+            chunks.push_back({reinterpret_cast<const char*>(src_host[p]), reinterpret_cast<char*>(dst_dev[p]), total, true});
+            last_chunk_of.push_back(p);
             continue;
         }
-        for (size_t off = 0; off < total; off += SLOT_BYTES)
+        for (size_t off = 0; off < total; off += SLOT_BYTES) {
             chunks.push_back({reinterpret_cast<const char*>(src_host[p]) + off, reinterpret_cast<char*>(dst_dev[p]) + off,
-                              total - off < SLOT_BYTES ? total - off : SLOT_BYTES});
+                              total - off < SLOT_BYTES ? total - off : SLOT_BYTES, false});
+            last_chunk_of.push_back(off + SLOT_BYTES >= total ? p : -1);
+        }
     }
     const size_t n_chunks = chunks.size();
     if (n_chunks == 0) return M3D_OK;
@@ -100,6 +114,20 @@ extern "C" int m3d_upload_batch(m3d_ctx* ctx, int n_pieces, const void* const* s
     // enqueued its cudaMemcpyAsync and recorded drained[slot] behind it.  Slots still draining from the
     // previous call are waited for through the same events (R->used).
     std::vector<char> staged(n_chunks, 0), issued(n_chunks, 0);
+    std::vector<int> slot_of(n_chunks, -1);
+    std::vector<long long> prev_of(n_chunks, -1);  // previous chunk that used the same slot
+    {
+        long long last_in_slot[N_SLOTS];
+        for (int s = 0; s < N_SLOTS; ++s) last_in_slot[s] = -1;
+        int k = 0;
+        for (size_t j = 0; j < n_chunks; ++j) {
+            if (chunks[j].direct) continue;
+            const int s = k++ % N_SLOTS;
+            slot_of[j] = s;
+            prev_of[j] = last_in_slot[s];
+            last_in_slot[s] = (long long)j;
+        }
+    }
     std::mutex mu;
     std::condition_variable cv;
     std::atomic<size_t> next{0};
@@ -115,11 +143,19 @@ extern "C" int m3d_upload_batch(m3d_ctx* ctx, int n_pieces, const void* const* s
         while (true) {
             const size_t j = next.fetch_add(1);
             if (j >= n_chunks) return;
-            const int s = (int)(j % N_SLOTS);
+            if (chunks[j].direct) {
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    staged[j] = 1;
+                }
+                cv.notify_all();
+                continue;
+            }
+            const int s = slot_of[j];
             bool wait_drain = R->used[s];
-            if (j >= (size_t)N_SLOTS) {  // the slot's previous chunk must have been issued ...
+            if (prev_of[j] >= 0) {  // the slot's previous chunk must have been issued ...
                 std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return issued[j - N_SLOTS] || failed.load(); });
+                cv.wait(lk, [&] { return issued[prev_of[j]] || failed.load(); });
                 wait_drain = true;
             }
             if (failed.load()) return;
@@ -146,9 +182,13 @@ extern "C" int m3d_upload_batch(m3d_ctx* ctx, int n_pieces, const void* const* s
             cv.wait(lk, [&] { return staged[j] || failed.load(); });
         }
         if (failed.load()) break;
-        const int s = (int)(j % N_SLOTS);
-        err = cudaMemcpyAsync(chunks[j].dst, R->slot[s], chunks[j].n, cudaMemcpyHostToDevice, st);
-        if (err == cudaSuccess) err = cudaEventRecord(R->drained[s], st);
+        const int s = slot_of[j];
+        if (chunks[j].direct) {
+            err = cudaMemcpyAsync(chunks[j].dst, chunks[j].src, chunks[j].n, cudaMemcpyHostToDevice, st);
+        } else {
+            err = cudaMemcpyAsync(chunks[j].dst, R->slot[s], chunks[j].n, cudaMemcpyHostToDevice, st);
+            if (err == cudaSuccess) err = cudaEventRecord(R->drained[s], st);
+        }
         if (err != cudaSuccess) {
             failed.store(1);
             cv.notify_all();
@@ -159,12 +199,19 @@ extern "C" int m3d_upload_batch(m3d_ctx* ctx, int n_pieces, const void* const* s
             issued[j] = 1;
         }
         cv.notify_all();
+        if (on_piece && last_chunk_of[j] >= 0) on_piece(last_chunk_of[j], user);  // piece fully enqueued on `stream`
     }
     for (auto& t : pool) t.join();
-    for (int s = 0; s < N_SLOTS && (size_t)s < n_chunks; ++s) R->used[s] = true;
+    for (size_t j = 0; j < n_chunks; ++j)
+        if (slot_of[j] >= 0) R->used[slot_of[j]] = true;
     if (err != cudaSuccess) return m3d_fail(M3D_ERR_CUDA, "m3d_upload: %s", cudaGetErrorString(err));
     if (failed.load()) return m3d_fail(M3D_ERR_CUDA, "m3d_upload: staging failed");
     return M3D_OK;  // the tail of the copies is still in flight on `stream`
+}
+
+extern "C" int m3d_upload_batch(m3d_ctx* ctx, int n_pieces, const void* const* src_host, void* const* dst_dev,
+                                const int64_t* n_bytes, void* stream) {
+    return m3d_upload_batch_cb(ctx, n_pieces, src_host, dst_dev, n_bytes, stream, nullptr, nullptr);
 }
 
 extern "C" int m3d_upload(m3d_ctx* ctx, const void* src_host, void* dst_dev, int64_t n_bytes, void* stream) {
