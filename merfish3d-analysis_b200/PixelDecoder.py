@@ -1267,16 +1267,61 @@ class PixelDecoder:
             dist.barrier()
 
     def _gather_tables(self, local: pd.DataFrame) -> pd.DataFrame:
-        """All-gather the per-rank transcript tables (variable length) so every rank computes
-        identical medians (the statistic is a median -- a sum all-reduce would
-        change the result)."""
+        """The optimiser's one exchange per iteration: all-gather of every rank's
+        transcript rows so that all ranks compute identical per-bit MEDIANS (a sum all-reduce would
+        change the result).  Only what the pooled statistics read travels -- per-bit mean intensities,
+        on-bits, gene code, tile, distance_min, global coordinates -- as one float64 matrix per rank:
+        counts first, then a padded ``all_gather`` of device tensors (NCCL over NVLink; gloo on CPU
+        in the tests).  Rows come back in rank order = tile order (contiguous chunks)."""
         _r, world, dist = self._dist()
         if dist is None or world == 1:
             return local
-        gathered = [None] * world
-        dist.all_gather_object(gathered, local)
-        parts = [g for g in gathered if g is not None and len(g)]
-        return pd.concat(parts, ignore_index=True) if parts else local
+        import torch
+
+        nb = self._n_merfish_bits
+        bit_cols = [f"bit{i:02d}_mean_intensity" for i in range(1, nb + 1)]
+        on_cols = [f"on_bit_{k}" for k in range(1, 5)]
+        extra = ["tile_idx", "distance_min", "global_z", "global_y", "global_x", "area", "magnitude_mean"]
+        have = [c for c in extra if c in local.columns] if len(local.columns) else []
+        flags = torch.zeros(len(extra), dtype=torch.int64)
+        for i, c in enumerate(extra):
+            flags[i] = int(c in have)
+        n_local = len(local) if "gene_id" in local.columns else 0
+        genes = {g: i for i, g in enumerate(self._gene_ids)}
+        mat = np.zeros((n_local, nb + 4 + 1 + len(extra)), dtype=np.float64)
+        if n_local:
+            mat[:, :nb] = local[bit_cols].to_numpy(dtype=np.float64)
+            mat[:, nb : nb + 4] = local[on_cols].to_numpy(dtype=np.float64)
+            mat[:, nb + 4] = [genes.get(str(g), -1) for g in local["gene_id"]]
+            for i, c in enumerate(extra):
+                if c in have:
+                    mat[:, nb + 5 + i] = local[c].to_numpy(dtype=np.float64)
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        head = torch.cat([torch.tensor([n_local], dtype=torch.int64), flags]).to(dev)
+        heads = [torch.empty_like(head) for _ in range(world)]
+        dist.all_gather(heads, head)
+        heads = [h.cpu() for h in heads]
+        counts = [int(h[0]) for h in heads]
+        present = torch.stack([h[1:] for h in heads])[[i for i, c in enumerate(counts) if c > 0]]
+        n_max = max(counts)
+        if n_max == 0:
+            return local
+        send = torch.zeros((n_max, mat.shape[1]), dtype=torch.float64, device=dev)
+        if n_local:
+            send[:n_local] = torch.from_numpy(mat).to(dev)
+        parts = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(parts, send)
+        pooled = np.concatenate([p[:c].cpu().numpy() for p, c in zip(parts, counts) if c > 0], axis=0)
+        out = pd.DataFrame(pooled[:, :nb], columns=bit_cols)
+        for k, c in enumerate(on_cols):
+            out[c] = pooled[:, nb + k].astype(np.int32)
+        codes = pooled[:, nb + 4].astype(np.int64)
+        names = np.asarray(list(self._gene_ids) + [""], dtype=object)
+        out["gene_id"] = names[codes]  # -1 (unknown id) -> ""
+        for i, c in enumerate(extra):
+            if len(present) and bool(present[:, i].all()):
+                out[c] = pooled[:, nb + 5 + i].astype(np.int64) if c == "tile_idx" else pooled[:, nb + 5 + i]
+        return out
 
     def optimize_normalization_by_decoding(
         self,
