@@ -883,6 +883,12 @@ class PixelDecoder:
     def _save_barcodes(self) -> None:
         """PD:3203-3233."""
         if self._optimize_normalization_weights:
+            # the reference hands tiles from its worker processes to the parent through these files; here
+            # the tables travel in memory (all_gather), so they are only written when they are part of the
+            # datastore layout (a decode run key -> decoded/temporary/iteration_XXX), not into a throw-away
+            # mkdtemp directory
+            if self._decode_run_key is None and not getattr(self, "_keep_temp_tables", False):
+                return
             d = Path(self._temp_dir)
             d.mkdir(parents=True, exist_ok=True)
             self._df_barcodes.to_parquet(d / ("tile" + str(self._tile_idx).zfill(3) + "_temp_decoded.parquet"))
@@ -1287,12 +1293,12 @@ class PixelDecoder:
         for i, c in enumerate(extra):
             flags[i] = int(c in have)
         n_local = len(local) if "gene_id" in local.columns else 0
-        genes = {g: i for i, g in enumerate(self._gene_ids)}
         mat = np.zeros((n_local, nb + 4 + 1 + len(extra)), dtype=np.float64)
         if n_local:
             mat[:, :nb] = local[bit_cols].to_numpy(dtype=np.float64)
             mat[:, nb : nb + 4] = local[on_cols].to_numpy(dtype=np.float64)
-            mat[:, nb + 4] = [genes.get(str(g), -1) for g in local["gene_id"]]
+            mat[:, nb + 4] = pd.Categorical(local["gene_id"].astype(str),
+                                            categories=[str(g) for g in self._gene_ids]).codes  # unknown id -> -1
             for i, c in enumerate(extra):
                 if c in have:
                     mat[:, nb + 5 + i] = local[c].to_numpy(dtype=np.float64)

@@ -170,13 +170,18 @@ def iterative_normalization_vectors(df, n_bits: int):
     col_bit = np.array([int(c[3:5]) for c in bit_cols])
     on = d[[f"on_bit_{k}" for k in range(1, 5)]].to_numpy(dtype=np.int64)
     is_on = (on[:, :, None] == col_bit[None, None, :]).any(axis=1)
-    with np.errstate(all="ignore"):
-        import warnings
-
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore", RuntimeWarning)
-            med_on = np.nanmedian(np.where(is_on, vals, np.nan), axis=0)
-            med_off = np.nanmedian(np.where(is_on, np.nan, vals), axis=0)
+    # per-bit medians of the selected entries (pandas ``median(skipna=True)`` of the reference's sparse
+    # frames, PD:1345-1356): NaN = no entry
+    finite = ~np.isnan(vals)
+    med_on = np.full(len(bit_cols), np.nan)
+    med_off = np.full(len(bit_cols), np.nan)
+    for j in range(len(bit_cols)):
+        sel_on = vals[is_on[:, j] & finite[:, j], j]
+        sel_off = vals[~is_on[:, j] & finite[:, j], j]
+        if sel_on.size:
+            med_on[j] = np.median(sel_on)
+        if sel_off.size:
+            med_off[j] = np.median(sel_off)
     nv = np.round(med_on.astype(np.float32), 1)
     bv = np.round(med_off.astype(np.float32), 1)
     nv = np.nan_to_num(nv, 1.0)
