@@ -21,6 +21,8 @@
 // Dense path (reference-complete images, return_results=True):
 //   decode_dense_kernel  : one thread per voxel, search everywhere, writes decoded int16 and
 //                          magnitude / distance / scaled float16 after round(.,5).
+#include <cuda_bf16.h>
+
 #include "voxel_math.cuh"
 
 namespace {
@@ -154,6 +156,8 @@ struct SearchSmem {
     float* a;            // [K]   (mode 1/2 proxy scan)
     float* g;            // [K]
     uint32_t* hkeys;     // [1 << hash_bits] (mode 2)
+    uint32_t* masks;     // [round_up(K, 8)] on-bit masks, 0 beyond K (mode 2, tensor-core on-bit sums)
+    uint32_t* cand_bits; // [SEARCH_THREADS][ceil(K/32)] per-voxel candidate sets marked by the tensor-core pass (mode 2)
     int16_t* hvals;      // [1 << hash_bits]
     uint8_t* on;         // [K][max_on]
 };
@@ -161,7 +165,7 @@ struct SearchSmem {
 static size_t search_smem_bytes(int nb, const DecodeParams& P) {
     size_t n = (size_t)(nb + 1) * XS_STRIDE * 4;
     if (P.mode >= 1) n += (size_t)P.K * 8 + (size_t)P.K * P.max_on;
-    if (P.mode == 2) n += ((size_t)1 << P.hash_bits) * 6;
+    if (P.mode == 2) n += ((size_t)1 << P.hash_bits) * 6 + (size_t)((P.K + 7) & ~7) * 4 + (size_t)SEARCH_THREADS * ((P.K + 31) / 32) * 4;
     return n + 16;
 }
 
@@ -172,6 +176,8 @@ __device__ __forceinline__ SearchSmem stage_codebook(unsigned char* smem, const 
     float* p = s.xs + (NB + 1) * XS_STRIDE;
     s.a = s.g = nullptr;
     s.hkeys = nullptr;
+    s.masks = nullptr;
+    s.cand_bits = nullptr;
     s.hvals = nullptr;
     s.on = nullptr;
     if (P.mode >= 1) {
@@ -185,12 +191,16 @@ __device__ __forceinline__ SearchSmem stage_codebook(unsigned char* smem, const 
     }
     if (P.mode == 2) {
         const int hs = 1 << P.hash_bits;
+        const int kpad = (P.K + 7) & ~7;
         s.hkeys = reinterpret_cast<uint32_t*>(p);
-        s.hvals = reinterpret_cast<int16_t*>(s.hkeys + hs);
+        s.masks = s.hkeys + hs;
+        s.cand_bits = s.masks + kpad;
+        s.hvals = reinterpret_cast<int16_t*>(s.cand_bits + SEARCH_THREADS * ((P.K + 31) / 32));
         for (int i = threadIdx.x; i < hs; i += SEARCH_THREADS) {
             s.hkeys[i] = P.hash_keys[i];
             s.hvals[i] = P.hash_vals[i];
         }
+        for (int i = threadIdx.x; i < kpad; i += SEARCH_THREADS) s.masks[i] = (i < P.K) ? P.cw_mask[i] : 0u;
         s.on = reinterpret_cast<uint8_t*>(s.hvals + hs);
     } else if (P.mode == 1) {
         s.on = reinterpret_cast<uint8_t*>(p);
@@ -358,6 +368,123 @@ __device__ __forceinline__ void coop_search(int src, const DecodeParams& P, cons
     k_out = best_k;
 }
 
+// ------------------------------------------------------------------ mode 2, dense regime: tensor-core on-bit sums
+// When most lanes of a warp need a real search (every voxel passes the magnitude gate: the optimiser's first
+// iteration with percentile-seeded vectors, reference-complete result images, all-foreground data), the
+// voxels x bits x codewords contraction  S = Xh . M^T  (M = 0/1 on-bit matrix) runs on the tensor cores:
+// warp-level mma.sync m16n8k16, bf16 operands, float32 accumulators, everything in registers.  Xh is split
+// into bf16 hi + lo parts (M is exact in bf16), so |S~ - S| <= w * 2^-16 + accumulation noise =: eps.
+// The MMA result never decides: pass 1 finds each voxel's largest S~, pass 2 recomputes the tiles and MARKS
+// every codeword with S~ >= max - (M3D_SUM_MARGIN + 2 eps) -- a superset of the codewords coop_search would
+// re-evaluate -- in a per-voxel bit set in shared memory; each lane then walks the set of its own voxel with
+// the exact float32 direct form on its register copy of the trace, keeping the lexicographic (d, k) minimum
+// = NumPy's first arg-min.  Clipped traces make exact ties among a dozen codewords common (noise-level
+// normalisation saturates many bits at 1), so the candidate set really is a set, not a single winner.
+// (tcgen05 / TMEM is not warranted here: the contraction is only 16-32 deep and the kernel is bound by the
+// per-voxel IEEE arithmetic and the exact re-evaluations, not by MMA issue; the warp-level form keeps operands
+// and accumulators in registers with no shared-memory descriptors or TMEM round trip.)
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(__fsub_rn(x0, __bfloat162float(h0)));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(__fsub_rn(x1, __bfloat162float(h1)));
+    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+}
+
+__device__ __forceinline__ void mma_bf16_m16n8k16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// on-bit sums of one n tile (8 codewords) for the 16 voxels of an m tile; accumulator layout: d0,d1 = row g,
+// codewords 8j+2t, 8j+2t+1; d2,d3 = row g+8
+template <int KS>
+__device__ __forceinline__ void onbit_sums_tile(const uint32_t (&ahi)[KS][4], const uint32_t (&alo)[KS][4], uint32_t m,
+                                                int t, float (&d)[4]) {
+    d[0] = d[1] = d[2] = d[3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t mm = m >> (ks * 16 + 2 * t);  // B fragment: bits 2t, 2t+1, 2t+8, 2t+9 of this lane's codeword
+        const uint32_t b0 = ((mm & 1u) ? 0x3F80u : 0u) | ((mm & 2u) ? 0x3F800000u : 0u);
+        const uint32_t b1 = ((mm & 0x100u) ? 0x3F80u : 0u) | ((mm & 0x200u) ? 0x3F800000u : 0u);
+        mma_bf16_m16n8k16(d, ahi[ks], b0, b1);
+        mma_bf16_m16n8k16(d, alo[ks], b0, b1);
+    }
+}
+
+// For the 32 voxels whose unit traces sit in this warp's xs columns: mark in S.cand_bits every codeword that can be
+// the exact arg-min (nothing is marked for NaN traces).  All lanes must call; the bit sets must be zero on entry.
+template <int NB>
+__device__ __forceinline__ void mma_mark_candidates_warp(const DecodeParams& P, const SearchSmem& S, int warp_col0) {
+    constexpr int KS = (NB + 15) / 16;
+    const unsigned lane = threadIdx.x & 31u;
+    const int g = (int)(lane >> 2), t = (int)(lane & 3u);
+    const int n_tiles = (P.K + 7) >> 3;
+    const int n_words = (P.K + 31) >> 5;
+    const float window = M3D_SUM_MARGIN + 2.f * ((float)P.max_on * 1.5259e-5f + 4.0e-6f);
+    const float inf = __int_as_float(0x7f800000);
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+        // A fragments (row = voxel, column = bit): rows g and g+8, bit columns 2t, 2t+1, 2t+8, 2t+9 per k step
+        uint32_t ahi[KS][4], alo[KS][4];
+        const float* c0 = S.xs + warp_col0 + mt * 16 + g;
+        const float* c1 = c0 + 8;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int b = ks * 16 + h * 8 + 2 * t;
+                const int r0 = (b < NB ? b : NB) * XS_STRIDE, r1 = (b + 1 < NB ? b + 1 : NB) * XS_STRIDE;  // NB = zero row
+                split_bf16x2(c0[r0], c0[r1], ahi[ks][2 * h], alo[ks][2 * h]);
+                split_bf16x2(c1[r0], c1[r1], ahi[ks][2 * h + 1], alo[ks][2 * h + 1]);
+            }
+        }
+        // pass 1: largest on-bit sum per voxel row
+        float rmax[2] = {-inf, -inf};
+        for (int j = 0; j < n_tiles; ++j) {
+            float d[4];
+            onbit_sums_tile<KS>(ahi, alo, S.masks[8 * j + g], t, d);
+            const int k0 = 8 * j + 2 * t;
+            if (k0 < P.K) {
+                rmax[0] = fmaxf(rmax[0], d[0]);
+                rmax[1] = fmaxf(rmax[1], d[2]);
+            }
+            if (k0 + 1 < P.K) {
+                rmax[0] = fmaxf(rmax[0], d[1]);
+                rmax[1] = fmaxf(rmax[1], d[3]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            rmax[r] = fmaxf(rmax[r], __shfl_xor_sync(0xffffffffu, rmax[r], 1));
+            rmax[r] = fmaxf(rmax[r], __shfl_xor_sync(0xffffffffu, rmax[r], 2));
+        }
+        // pass 2: mark every codeword inside the window
+        const float cut[2] = {rmax[0] - window, rmax[1] - window};
+        uint32_t* bits0 = S.cand_bits + (size_t)(warp_col0 + mt * 16 + g) * n_words;
+        uint32_t* bits1 = bits0 + 8 * n_words;
+        for (int j = 0; j < n_tiles; ++j) {
+            float d[4];
+            onbit_sums_tile<KS>(ahi, alo, S.masks[8 * j + g], t, d);
+            const int k0 = 8 * j + 2 * t;  // k0 and k0+1 share a word (k0 is even)
+            uint32_t m0 = 0u, m1 = 0u;
+            if (k0 < P.K) {
+                m0 |= (d[0] >= cut[0]) ? 1u : 0u;
+                m1 |= (d[2] >= cut[1]) ? 1u : 0u;
+            }
+            if (k0 + 1 < P.K) {
+                m0 |= (d[1] >= cut[0]) ? 2u : 0u;
+                m1 |= (d[3] >= cut[1]) ? 2u : 0u;
+            }
+            if (m0) atomicOr(bits0 + (k0 >> 5), m0 << (k0 & 31));
+            if (m1) atomicOr(bits1 + (k0 >> 5), m1 << (k0 & 31));
+        }
+    }
+    __syncwarp();
+}
+
 // nearest codeword for the voxels of one warp; `want` = this lane holds a voxel to search.
 // All 32 lanes must call (warp-synchronous).
 template <int NB>
@@ -371,10 +498,42 @@ __device__ __forceinline__ void nearest_codeword_warp(bool want, const float (&x
         bool done = !want;
         if (want) done = topw_lookup<NB>(xh, P, S, d, k);
         unsigned pending = __ballot_sync(0xffffffffu, !done);
+        const int warp_col0 = (int)(threadIdx.x & ~31u);
         if (__popc(pending) > COOP_SWITCH) {
-            if (!done) scan_codebook<NB>(xh, P, S, col, d, k);
-        } else {
-            const int warp_col0 = (int)(threadIdx.x & ~31u);
+            // dense regime: on-bit sums of all 32 voxels on the tensor cores, exact distance for the settled ones
+            const int n_words = (P.K + 31) >> 5;
+            uint32_t* my_bits = S.cand_bits + (size_t)threadIdx.x * n_words;
+            for (int w = 0; w < n_words; ++w) my_bits[w] = 0u;
+            __syncwarp();
+            mma_mark_candidates_warp<NB>(P, S, warp_col0);
+            if (!done) {
+                float best_d = __int_as_float(0x7f800000);
+                int best_k = -1;
+                for (int w = 0; w < n_words; ++w) {
+                    uint32_t bits = my_bits[w];
+                    while (bits) {  // ascending k: a later equal distance never replaces an earlier one
+                        const int kk = w * 32 + __ffs(bits) - 1;
+                        bits &= bits - 1u;
+                        const float dd = direct_distance_binary<NB>(xh, S.masks[kk], P.cval);
+                        if (dd < best_d) {
+                            best_d = dd;
+                            best_k = kk;
+                        }
+                    }
+                }
+                if (best_k >= 0) {
+                    k = best_k;
+                    d = best_d;
+                    done = true;
+                }
+            }
+            pending = __ballot_sync(0xffffffffu, !done);
+            if (__popc(pending) > COOP_SWITCH) {
+                if (!done) scan_codebook<NB>(xh, P, S, col, d, k);
+                pending = 0u;
+            }
+        }
+        {
             while (pending) {
                 const int src = __ffs(pending) - 1;
                 pending &= pending - 1u;
