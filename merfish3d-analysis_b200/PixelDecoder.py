@@ -134,7 +134,11 @@ class PixelDecoder:
         self._iterative_background_vector = None
         self._load_tile_decoding = False
         self._fuse_label_args = None
-        self._copy_streams: dict[int, object] = {}
+        self._copy_streams: dict[tuple, object] = {}
+        self._prefetch_streams: dict[int, object] = {}
+        self._prefetch_pool = None
+        self._prefetched = None
+        self._next_tile_hint = None
         self._contexts: dict[int, DecodeContext] = {}
         self._context_excluded: dict[int, tuple] = {}
         self._device_state: dict[int, dict] = {}
@@ -481,7 +485,84 @@ class PixelDecoder:
 
     def _load_bit_data(self, feature_predictor_threshold: float | None = 0.1, gpu_id: int = 0,
                        z_bounds: tuple[int, int] | None = None, lowpass_sigma=None) -> None:
-        """PD:1828-1946: gather the tile's bit volumes into one device stack + coordinate metadata.
+        """PD:1828-1946: the tile's bit volumes as one device stack + coordinate metadata.  Takes the
+        tile staged ahead by ``_schedule_prefetch`` when there is one, else stages it now."""
+        import torch
+
+        staged = self._take_prefetched(self._tile_idx, gpu_id, z_bounds, lowpass_sigma)
+        if staged is None:
+            staged = self._stage_tile(self._tile_idx, gpu_id, z_bounds, lowpass_sigma)
+        new_state, meta = staged
+        ready = meta.get("ready")
+        if ready is not None:  # staged on the prefetch stream: order it before this stream's kernels
+            cur = torch.cuda.current_stream(self._ctx(gpu_id).device)
+            cur.wait_event(ready)
+            for v in new_state.values():
+                if isinstance(v, torch.Tensor):
+                    v.record_stream(cur)
+        st = self._device_state.setdefault(gpu_id, {})
+        st.clear()
+        st.update(new_state)
+        self._em_wvl, self._full_z = meta["em_wvl"], meta["full_z"]
+        self._load_coordinate_metadata()
+
+    # ------------------------------------------------------------------ next-tile prefetch
+    def _schedule_prefetch(self, tile_idx, gpu_id: int, z_bounds, lowpass_sigma) -> None:
+        """Stage ``tile_idx`` (datastore reads, host -> device copies, per-bit low-pass) on a side stream
+        from a helper thread while the current tile is decoded, annotated and saved.  Multi-tile loops
+        (``decode_all_tiles``, the optimiser) are transfer-bound: 13.4 GB over PCIe per tile against a few
+        ms of kernels, so hiding everything else behind the next transfer is what is left to win."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        import torch
+
+        self._drop_prefetched()
+        if self._prefetch_pool is None:
+            self._prefetch_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="m3d-prefetch")
+        ctx = self._ctx(gpu_id)
+        stream = self._prefetch_streams.get(gpu_id)
+        if stream is None:
+            stream = self._prefetch_streams[gpu_id] = torch.cuda.Stream(device=ctx.device)
+
+        def job():
+            torch.cuda.set_device(ctx.device)
+            with torch.cuda.stream(stream):
+                st, meta = self._stage_tile(tile_idx, gpu_id, z_bounds, lowpass_sigma)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                meta["ready"] = ev
+            return st, meta
+
+        key = (tile_idx, gpu_id, None if z_bounds is None else tuple(z_bounds),
+               None if lowpass_sigma is None else tuple(float(v) for v in lowpass_sigma))
+        self._prefetched = (key, self._prefetch_pool.submit(job))
+
+    def _take_prefetched(self, tile_idx, gpu_id: int, z_bounds, lowpass_sigma):
+        if self._prefetched is None:
+            return None
+        key, fut = self._prefetched
+        self._prefetched = None
+        want = (tile_idx, gpu_id, None if z_bounds is None else tuple(z_bounds),
+                None if lowpass_sigma is None else tuple(float(v) for v in lowpass_sigma))
+        try:
+            staged = fut.result()
+        except Exception:  # the synchronous path below reports the error with its real traceback
+            return None
+        return staged if key == want else None
+
+    def _drop_prefetched(self) -> None:
+        if self._prefetched is not None:
+            _key, fut = self._prefetched
+            self._prefetched = None
+            try:
+                fut.result()
+            except Exception:
+                pass
+
+    def _stage_tile(self, tile_idx, gpu_id: int = 0, z_bounds: tuple[int, int] | None = None, lowpass_sigma=None):
+        """PD:1828-1946: gather the tile's bit volumes into one device stack.  Returns
+        ``(state dict, {"em_wvl", "full_z"})`` and touches no per-tile attribute of ``self``, so it can
+        run ahead on the prefetch thread / stream.
 
         Registered data (every bit's decode-time transform is the identity): device state
         ``readout`` (bits, z, y, x) uint16 (float32 when the store holds float data) + ``predictor``
@@ -495,33 +576,32 @@ class PixelDecoder:
         ctx = self._ctx(gpu_id)
         bit_ids = list(self._datastore.bit_ids)[0 : self._n_merfish_bits]
         loaded = []
-        self._em_wvl = []
+        em_wvl = []
         # issue every read first, then collect: a datastore that returns real futures (tensorstore
         # reads in the reference's qi2labDataStore) overlaps the 2 x bits chunk reads instead of
         # serialising them bit by bit as PD:1861-1874 does
         pending = [
-            (self._datastore.load_local_readout_image(tile=self._tile_idx, bit=bit_id),
-             self._datastore.load_local_feature_predictor_image(tile=self._tile_idx, bit=bit_id))
+            (self._datastore.load_local_readout_image(tile=tile_idx, bit=bit_id),
+             self._datastore.load_local_feature_predictor_image(tile=tile_idx, bit=bit_id))
             for bit_id in bit_ids
         ]
         for bit_id, (fr, fp) in zip(bit_ids, pending):
             pa = fp.result() if hasattr(fp, "result") else fp
             ra = fr.result() if hasattr(fr, "result") else fr
-            _ex, em = self._datastore.load_local_wavelengths_um(tile=self._tile_idx, bit=bit_id)
-            warp = self._bit_warp_px(self._tile_idx, bit_id, em)
+            _ex, em = self._datastore.load_local_wavelengths_um(tile=tile_idx, bit=bit_id)
+            warp = self._bit_warp_px(tile_idx, bit_id, em)
             loaded.append((ra, None if self._is_unit_predictor(pa) else pa, warp))
-            self._em_wvl.append(em)
+            em_wvl.append(em)
         z_full = int(loaded[0][0].shape[0])
         zs, ze, _step = self._z_slice.indices(z_full)
-        self._full_z = max(ze - zs, 0)
-        if self._decode_mode == "3d" and self._full_z < 2:
+        full_z = max(ze - zs, 0)
+        if self._decode_mode == "3d" and full_z < 2:
             raise ValueError("decode_mode='3d' requires at least two z planes after applying z_range.")
         a, b = (zs, ze) if z_bounds is None else (zs + int(z_bounds[0]), zs + int(z_bounds[1]))
         shape = (b - a, *loaded[0][0].shape[1:])
         float_input = any(np.asarray(r).dtype.kind == "f" for r, _p, _w in loaded)
         npdt = np.float32 if float_input else np.uint16
-        st = self._device_state.setdefault(gpu_id, {})
-        st.clear()
+        st = {}
 
         def to_dev(arr, dtype):
             src = np.ascontiguousarray(arr, dtype=dtype)
@@ -571,7 +651,7 @@ class PixelDecoder:
                 st["readout"], st["predictor"] = None, None
                 st["stack"] = self._upload_and_lowpass(ctx, pieces, piece_bit, stack, pred, lowpass_sigma)
                 st["lowpass_done"] = True
-        self._load_coordinate_metadata()
+        return st, {"em_wvl": em_wvl, "full_z": full_z}
 
     def _upload_and_lowpass(self, ctx, pieces, piece_bit, stack, pred, sigma):
         """Registered tiles with the low-pass on: the per-bit Gaussian (PD:1982-2024) of bit b runs on the
@@ -583,9 +663,12 @@ class PixelDecoder:
 
         out = torch.empty(tuple(stack.shape), dtype=torch.float32, device=ctx.device)
         compute = torch.cuda.current_stream(ctx.device)
-        copy = self._copy_streams.get(ctx.device.index)
+        import threading
+
+        skey = (ctx.device.index, threading.get_ident())  # the prefetch thread gets its own copy stream
+        copy = self._copy_streams.get(skey)
         if copy is None:
-            copy = self._copy_streams[ctx.device.index] = torch.cuda.Stream(device=ctx.device)
+            copy = self._copy_streams[skey] = torch.cuda.Stream(device=ctx.device)
         last_piece_of = {b: i for i, b in enumerate(piece_bit)}  # later pieces overwrite: the bit's last one
         bit_done_at = {i: b for b, i in last_piece_of.items()}
 
@@ -952,6 +1035,7 @@ class PixelDecoder:
 
     def _cleanup(self) -> None:
         """PD:4426-4469: drop device buffers and per-tile results."""
+        self._drop_prefetched()
         for st in self._device_state.values():
             st.clear()
         for name in ("_df_barcodes", "_df_filtered_barcodes"):
@@ -987,6 +1071,9 @@ class PixelDecoder:
         lp_active = self._lowpass_active(sigma)
         self._load_bit_data(feature_predictor_threshold=feature_predictor_threshold, gpu_id=gpu_id,
                             lowpass_sigma=sigma if lp_active else None)
+        nxt, self._next_tile_hint = self._next_tile_hint, None
+        if nxt is not None and _is_identity_store(self._datastore):
+            self._schedule_prefetch(nxt, gpu_id, None, sigma if lp_active else None)
         self._filter_type = "raw"
         if lp_active:
             if self._device_state[gpu_id].get("lowpass_done"):
@@ -1243,13 +1330,16 @@ class PixelDecoder:
         if dist is not None and world > 1:
             mine = self._contiguous_chunks(list(tiles), world)[rank]
             gpu = self._local_gpu()
-            for t in mine:
+            for i, t in enumerate(mine):
+                self._next_tile_hint = mine[i + 1] if i + 1 < len(mine) else None
                 per_tile(self, t, gpu)
             return
         n = max(1, min(int(self._num_gpus), torch.cuda.device_count() or 1))
         chunks = [c for c in self._contiguous_chunks(list(tiles), n) if c]
         if len(chunks) <= 1:
-            for t in (chunks[0] if chunks else []):
+            only = chunks[0] if chunks else []
+            for i, t in enumerate(only):
+                self._next_tile_hint = only[i + 1] if i + 1 < len(only) else None
                 per_tile(self, t, 0)
             return
 
@@ -1260,7 +1350,8 @@ class PixelDecoder:
             dec._global_normalization_vector = self._global_normalization_vector
             dec._global_background_vector = self._global_background_vector
             dec._global_normalization_loaded = self._global_normalization_loaded
-            for t in subset:
+            for i, t in enumerate(subset):
+                dec._next_tile_hint = subset[i + 1] if i + 1 < len(subset) else None
                 per_tile(dec, t, gpu)
             dec._cleanup()
 
