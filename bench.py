@@ -422,6 +422,31 @@ def run_b200(args):
             }
             dec._cleanup()
             torch.cuda.empty_cache()
+        # multi-tile public API: decode_all_tiles over 3 tiles (the same pinned array registered three times),
+        # per-tile parquet output + the pooled table stage; tile t+1 is staged while tile t is finished
+        if world == 1 and not args.no_extras:
+            ds3 = ArrayDataStore(Path(tmp.name) / "qi2labdatastore_multi", codebook=df_cb)
+            for k in range(3):
+                ds3.add_tile(host.numpy(), stage_origin_zyx_um=(0.0, 0.0, 250.0 * k))
+            ds3.save_decode_normalization_vectors(None, "global", nrm, bkg)
+            dec3 = PixelDecoder(ds3, merfish_bits=16, verbose=0)
+            dec3.decode_one_tile(0, gpu_id=local, lowpass_sigma=None, magnitude_threshold=MAG, minimum_pixels=MIN_PX,
+                                 normalization_method="global")  # warm-up (allocations)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dec3.decode_all_tiles(assign_to_cells=False, lowpass_sigma=None, magnitude_threshold=MAG,
+                                  minimum_pixels=MIN_PX, normalization_method="global")
+            torch.cuda.synchronize()
+            all_s = time.perf_counter() - t0
+            extras["decode_all_tiles_3"] = {
+                "s_total": all_s, "ms_per_tile": all_s / 3 * 1e3, "gvoxel_per_s": 3 * n_vox / all_s / 1e9,
+                "filtered_transcripts": int(len(dec3._df_filtered_barcodes)),
+                "note": "decode_all_tiles: 3 tiles from pinned host memory, per-tile parquet files, blank-fraction "
+                        "filter + tile-overlap de-duplication + filtered table written; next tile prefetched",
+            }
+            dec3._cleanup()
+            del dec3
+            torch.cuda.empty_cache()
         # the same call with the stack in PAGEABLE host memory (what a datastore returning plain NumPy
         # arrays gives the loader): staged through the library's pinned ring by m3d_upload_batch
         if world == 1 and not args.no_extras:

@@ -138,6 +138,8 @@ class PixelDecoder:
         self._prefetch_streams: dict[int, object] = {}
         self._prefetch_pool = None
         self._prefetched = None
+        self._buffers: dict[tuple, dict] = {}
+        self._slot: dict[int, int] = {}
         self._next_tile_hint = None
         self._contexts: dict[int, DecodeContext] = {}
         self._context_excluded: dict[int, tuple] = {}
@@ -489,18 +491,19 @@ class PixelDecoder:
         tile staged ahead by ``_schedule_prefetch`` when there is one, else stages it now."""
         import torch
 
+        st = self._device_state.setdefault(gpu_id, {})
         staged = self._take_prefetched(self._tile_idx, gpu_id, z_bounds, lowpass_sigma)
         if staged is None:
-            staged = self._stage_tile(self._tile_idx, gpu_id, z_bounds, lowpass_sigma)
+            st.clear()  # release the previous tile before staging this one
+            # same buffer set as the previous tile: this stream's order already protects it
+            staged = self._stage_tile(self._tile_idx, gpu_id, z_bounds, lowpass_sigma,
+                                      slot=self._slot.get(gpu_id, 0))
         new_state, meta = staged
         ready = meta.get("ready")
         if ready is not None:  # staged on the prefetch stream: order it before this stream's kernels
-            cur = torch.cuda.current_stream(self._ctx(gpu_id).device)
-            cur.wait_event(ready)
-            for v in new_state.values():
-                if isinstance(v, torch.Tensor):
-                    v.record_stream(cur)
-        st = self._device_state.setdefault(gpu_id, {})
+            torch.cuda.current_stream(self._ctx(gpu_id).device).wait_event(ready)
+        if meta.get("slot") is not None:
+            self._slot[gpu_id] = meta["slot"]
         st.clear()
         st.update(new_state)
         self._em_wvl, self._full_z = meta["em_wvl"], meta["full_z"]
@@ -524,10 +527,16 @@ class PixelDecoder:
         if stream is None:
             stream = self._prefetch_streams[gpu_id] = torch.cuda.Stream(device=ctx.device)
 
+        slot = 1 - self._slot.get(gpu_id, 0)  # the buffer set the current tile does NOT occupy
+        main = torch.cuda.current_stream(ctx.device)
+        idle = torch.cuda.Event()
+        idle.record(main)  # everything that touched that buffer set has been enqueued before this point
+
         def job():
             torch.cuda.set_device(ctx.device)
             with torch.cuda.stream(stream):
-                st, meta = self._stage_tile(tile_idx, gpu_id, z_bounds, lowpass_sigma)
+                stream.wait_event(idle)
+                st, meta = self._stage_tile(tile_idx, gpu_id, z_bounds, lowpass_sigma, slot=slot, alloc_stream=main)
                 ev = torch.cuda.Event()
                 ev.record(stream)
                 meta["ready"] = ev
@@ -559,7 +568,29 @@ class PixelDecoder:
             except Exception:
                 pass
 
-    def _stage_tile(self, tile_idx, gpu_id: int = 0, z_bounds: tuple[int, int] | None = None, lowpass_sigma=None):
+    def _tile_buffer(self, gpu_id: int, slot, name: str, shape, dtype, device, alloc_stream=None):
+        """Persistent per-slot device buffers for whole-tile loads: two slots alternate (the tile being decoded
+        / the tile being staged ahead), so multi-tile loops never go back to the allocator and a prefetch
+        never shares memory with the tile in flight.  ``slot`` None = a fresh tensor (z-slab path)."""
+        import torch
+
+        if slot is None:
+            return torch.empty(shape, dtype=dtype, device=device)
+        bufs = self._buffers.setdefault((gpu_id, slot), {})
+        t = bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            bufs.pop(name, None)
+            t = None
+            if alloc_stream is not None:  # helper thread: take the memory from the main stream's pool
+                with torch.cuda.stream(alloc_stream):
+                    t = torch.empty(shape, dtype=dtype, device=device)
+            else:
+                t = torch.empty(shape, dtype=dtype, device=device)
+            bufs[name] = t
+        return t
+
+    def _stage_tile(self, tile_idx, gpu_id: int = 0, z_bounds: tuple[int, int] | None = None, lowpass_sigma=None,
+                    slot=None, alloc_stream=None):
         """PD:1828-1946: gather the tile's bit volumes into one device stack.  Returns
         ``(state dict, {"em_wvl", "full_z"})`` and touches no per-tile attribute of ``self``, so it can
         run ahead on the prefetch thread / stream.
@@ -630,10 +661,13 @@ class PixelDecoder:
             st["readout"], st["predictor"], st["stack"] = None, None, stack
         else:
             dt = torch.float32 if float_input else torch.uint16
-            stack = torch.empty((len(bit_ids), *shape), dtype=dt, device=ctx.device)
+            if z_bounds is not None:
+                slot = None  # z-slabs keep several stacks alive at once: fresh tensors
+            full = (len(bit_ids), *shape)
+            stack = self._tile_buffer(gpu_id, slot, "stack", full, dt, ctx.device, alloc_stream)
             pred = None
             if any(pa is not None for _r, pa, _w in loaded):
-                pred = torch.empty((len(bit_ids), *shape), dtype=torch.float32, device=ctx.device)
+                pred = self._tile_buffer(gpu_id, slot, "pred", full, torch.float32, ctx.device, alloc_stream)
             pieces, piece_bit = [], []  # per bit: readout, then its predictor weights (if stored)
             for i, (ra, pa, _w) in enumerate(loaded):
                 pieces.append((np.ascontiguousarray(ra[a:b], dtype=npdt), stack[i]))
@@ -649,11 +683,13 @@ class PixelDecoder:
                 st["readout"], st["predictor"] = stack, pred
             else:
                 st["readout"], st["predictor"] = None, None
-                st["stack"] = self._upload_and_lowpass(ctx, pieces, piece_bit, stack, pred, lowpass_sigma)
+                out = self._tile_buffer(gpu_id, slot, "lowpassed", full, torch.float32, ctx.device, alloc_stream)
+                st["stack"] = self._upload_and_lowpass(ctx, pieces, piece_bit, stack, pred, lowpass_sigma, out)
                 st["lowpass_done"] = True
+            return st, {"em_wvl": em_wvl, "full_z": full_z, "slot": slot}
         return st, {"em_wvl": em_wvl, "full_z": full_z}
 
-    def _upload_and_lowpass(self, ctx, pieces, piece_bit, stack, pred, sigma):
+    def _upload_and_lowpass(self, ctx, pieces, piece_bit, stack, pred, sigma, out):
         """Registered tiles with the low-pass on: the per-bit Gaussian (PD:1982-2024) of bit b runs on the
         compute stream as soon as its volume has arrived, while the volumes of the later bits are still
         crossing PCIe on a copy stream -- the filter (float64-pipe bound, ~3.7 ms per bit) hides behind the
@@ -661,7 +697,6 @@ class PixelDecoder:
         adjacent)."""
         import torch
 
-        out = torch.empty(tuple(stack.shape), dtype=torch.float32, device=ctx.device)
         compute = torch.cuda.current_stream(ctx.device)
         import threading
 
@@ -1033,9 +1068,12 @@ class PixelDecoder:
                 "Re-decode local transcript parquet files with the exact two-threshold caller."
             )
 
-    def _cleanup(self) -> None:
-        """PD:4426-4469: drop device buffers and per-tile results."""
-        self._drop_prefetched()
+    def _cleanup(self, keep_pipeline: bool = False) -> None:
+        """PD:4426-4469: drop device buffers and per-tile results.  ``keep_pipeline`` (between the tiles of a
+        multi-tile loop) keeps the two persistent tile buffers and the tile being staged ahead."""
+        if not keep_pipeline:
+            self._drop_prefetched()
+            self._buffers.clear()
         for st in self._device_state.values():
             st.clear()
         for name in ("_df_barcodes", "_df_filtered_barcodes"):
@@ -1645,6 +1683,9 @@ class PixelDecoder:
         self._validate_filter_configuration(filter_method, float(target_gross_misid_rate), float(lr_fdr_target))
         all_tiles = list(range(len(self._datastore.tile_ids)))
         self._optimize_normalization_weights = False
+        # the reference decodes in fresh worker processes (PD:249-268); here the same object decodes, so a
+        # filtered table left by an earlier call must not redirect the per-tile saves
+        self._barcodes_filtered = False
 
         def per_tile(dec, tile_idx, gpu):
             dec.decode_one_tile(
@@ -1654,9 +1695,10 @@ class PixelDecoder:
                 normalization_method=normalization_method,
             )
             dec._save_barcodes()
-            dec._cleanup()
+            dec._cleanup(keep_pipeline=True)
 
         self._run_tiles(all_tiles, per_tile)
+        self._cleanup()
         self._barrier()
         self._load_tile_decoding = True
         self._load_all_barcodes()
