@@ -246,3 +246,35 @@ def test_decode_with_round_transforms_matches_oracle(tmp_path, lowpass):
     dec3 = PixelDecoder(ds, merfish_bits=16, verbose=0, z_range=(1, 13))
     dec3.decode_one_tile(0, lowpass_sigma=lowpass, minimum_pixels=4, normalization_method="global")
     pd.testing.assert_frame_equal(dec2.decoded_barcodes, dec3.decoded_barcodes)
+
+
+@pytest.mark.parametrize("lowpass", [None, (3.0, 1.0, 1.0)])
+def test_multi_tile_pipeline_equals_tile_by_tile(tmp_path, lowpass):
+    """decode_all_tiles stages tile t+1 on a side stream (prefetch thread, persistent double buffers, the
+    per-bit low-pass behind the upload) while tile t is finished: every per-tile table must equal a plain
+    decode_one_tile of that tile, also when the whole run is repeated on the same decoder."""
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    df_cb, cb = cases.codebook16()
+    rng = np.random.default_rng(5)
+    stacks = [cases.small_stack(cb["matrix"], shape=(9, 40, 56), seed=400 + i, density=5e-3) for i in range(4)]
+    preds = [None, rng.uniform(0.5, 1.0, stacks[1].shape).astype(np.float32), None, None]
+    ds = _store(tmp_path, df_cb, [stacks[0]])
+    for st, pr in zip(stacks[1:], preds[1:]):
+        ds.add_tile(st, pr)
+    bkg, nrm = cases.simple_vectors(16, nrm=300.0 if lowpass else 900.0)
+    ds.save_decode_normalization_vectors(None, "global", nrm, bkg)
+    kw = dict(lowpass_sigma=lowpass, minimum_pixels=4, normalization_method="global")
+    single = []
+    for t in range(4):
+        one = PixelDecoder(ds, merfish_bits=16, verbose=0)
+        one.decode_one_tile(t, **kw)
+        single.append(one.decoded_barcodes)
+    assert sum(len(s) for s in single) > 40
+    dec = PixelDecoder(ds, merfish_bits=16, verbose=0)
+    for _rep in range(2):
+        dec.decode_all_tiles(assign_to_cells=False, **kw)
+        for t in range(4):
+            got = ds.load_local_decoded_spots(t)
+            pd.testing.assert_frame_equal(got.reset_index(drop=True), single[t].reset_index(drop=True),
+                                          check_dtype=False)
