@@ -40,6 +40,27 @@ def run(world, affinity=None, label=""):
           flush=True)
 
 
+def gpu_cpu_affinity():
+    """{gpu index: set of cpus} from `nvidia-smi topo -m` (CPU Affinity column, e.g. 0-15,32-47)."""
+    out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True).stdout
+    aff = {}
+    for line in out.splitlines():
+        line = line.replace("\x1b[4m", "").replace("\x1b[0m", "")
+        parts = line.split()
+        if not parts or not parts[0].startswith("GPU") or not parts[0][3:].isdigit():
+            continue
+        idx = int(parts[0][3:])
+        for tok in parts[1:]:
+            if tok[0].isdigit() and all(c.isdigit() or c in "-," for c in tok) and ("-" in tok or "," in tok):
+                cpus = set()
+                for rng in tok.split(","):
+                    a, _, b = rng.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+                aff[idx] = cpus
+                break
+    return aff
+
+
 if __name__ == "__main__":
     print(subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True).stdout, flush=True)
     print(subprocess.run(["bash", "-c", "lscpu | grep -i -E 'numa|model name|^CPU\\(s\\)'; nproc; free -g | head -2"],
@@ -48,3 +69,7 @@ if __name__ == "__main__":
     run(1, label="alone")
     if n >= 2:
         run(n, label="concurrent")
+        aff = gpu_cpu_affinity()
+        print("affinity", {k: (min(v), max(v), len(v)) for k, v in aff.items()}, flush=True)
+        if len(aff) >= n:
+            run(n, affinity=[aff[r] for r in range(n)], label="concurrent, NUMA-bound")
