@@ -104,3 +104,35 @@ def test_fullsize_sharded_equals_unsharded(big, tmp_path):
     assert len(ref) > 10000
     pd.testing.assert_frame_equal(b.decoded_barcodes, ref)
     np.testing.assert_array_equal(b.decoded_image, ref_img)
+
+
+def test_fullsize_dense_candidate_regime_matches_oracle_on_sample(big):
+    """Noise-level normalisation vectors (what the optimiser's percentile seed gives): every voxel passes the
+    magnitude gate, clipped traces tie exactly among many codewords, and the search runs through the tensor-core
+    candidate marking.  The decoded image of the whole tile is compared with the CPU oracle on 20 000 random
+    voxels (the oracle's first-arg-min semantics decide the ties)."""
+    import torch
+
+    from oracle import decode_oracle as orc
+
+    ctx, stack, m = big
+    bkg = np.full(16, 187.0, np.float32)
+    nrm = np.full(16, 17.0, np.float32)
+    ctx.set_normalization(bkg, nrm)
+    try:
+        decoded = torch.empty(SHAPE, dtype=torch.int16, device="cuda")
+        ctx.decode(stack, decoded)  # production path: gate (all candidates) + search
+        frac = float((decoded >= 0).float().mean().item())
+        assert 0.05 < frac < 0.6  # noise decodes: this really is the dense regime
+        g = torch.Generator(device="cuda")
+        g.manual_seed(11)
+        lin = torch.randint(0, decoded.numel(), (20000,), device="cuda", generator=g)
+        mini = stack.view(torch.int16).reshape(16, -1)[:, lin].contiguous().view(torch.uint16).reshape(16, 1, 1, -1)
+        unit = orc.normalize_codebook(m)
+        thr = float(np.sqrt(2 - 2 * ((4 - 2) / np.sqrt(4 * (4 - 2)))))
+        ref = orc.decode_pixels(mini.cpu().numpy().astype(np.float32), unit, bkg, nrm, thr, (1.5, 10.0))
+        got = decoded.reshape(-1)[lin].cpu().numpy()
+        np.testing.assert_array_equal(got, ref["decoded"].reshape(-1))
+        assert (got >= 0).sum() > 1000
+    finally:
+        ctx.set_normalization(np.full(16, 200.0, np.float32), np.full(16, 900.0, np.float32))
