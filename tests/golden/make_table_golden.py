@@ -54,6 +54,14 @@ def main():
                     print("within-tile collapse:", len(kept_filter), "->", len(kept_within))
                 dec._remove_duplicates_in_tile_overlap()
                 kept_overlap = dec._df_filtered_barcodes["_row"].to_numpy()
+            # logistic-regression filter (PD:3907-4058, scikit-learn on the host in the reference too)
+            with rs.pandas2_semantics():
+                dec._df_barcodes_loaded = table.copy()
+                dec._barcodes_filtered = False
+                dec._filter_all_barcodes_LR(lr_fdr_target=0.05)
+            out[f"kept_lr_{mode}"] = dec._df_filtered_barcodes["_row"].to_numpy()
+            out[f"lr_probability_{mode}"] = dec._df_filtered_barcodes["predicted_probability"].to_numpy(dtype=float)
+            print(mode, "LR filter keeps", len(out[f"kept_lr_{mode}"]), "of", len(table))
             out[f"kept_filter_{mode}"] = kept_filter
             out[f"kept_overlap_{mode}"] = kept_overlap
             out[f"chosen_threshold_{mode}"] = np.float64(diag["chosen_threshold"])

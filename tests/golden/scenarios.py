@@ -91,4 +91,11 @@ def synthetic_transcript_table(df_cb, seed: int, mode: str = "3d", n: int = 6000
     out = pd.concat(parts, ignore_index=True)
     out = out.iloc[rng.permutation(len(out))].reset_index(drop=True)
     out["gene_id"] = out["gene_id"].astype(str)
+    # the columns the LR filter reads (PD:3929-3950), correlated with blank-ness like real data
+    blank_all = out["gene_id"].str.lower().str.startswith("blank").to_numpy()
+    m = len(out)
+    out["signal_mean"] = np.where(blank_all, rng.normal(0.45, 0.1, m), rng.normal(0.8, 0.12, m))
+    out["s-b_mean"] = out["signal_mean"] - rng.uniform(0.01, 0.1, m)
+    for k, scale in enumerate((2.0, 1.0, 0.5)):
+        out[f"inertia_tensor_eigvals-{k}"] = rng.gamma(2.0, scale, m)
     return out

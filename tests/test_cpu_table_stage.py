@@ -79,3 +79,42 @@ def test_blank_fraction_edge_cases():
     bad["area"] = np.nan
     keep, diag = tor.blank_fraction_filter(bad, blank_count, barcode_count)
     assert diag["reason"] == "no_valid_features" and not keep.any()
+
+
+@pytest.mark.parametrize("mode", ["3d", "2d"])
+def test_lr_filter_equals_reference_golden(mode):
+    """``_filter_all_barcodes_LR`` is host-side scikit-learn in the reference as well: the product's mirror
+    (``table_stage.filter_lr``) must keep the same rows with the same probabilities."""
+    from merfish3d_analysis_b200 import table_stage
+
+    g = np.load(GOLDEN)
+    table, blank_count, barcode_count = table_for(mode)
+    table["_row"] = np.arange(len(table))
+    out = table_stage.filter_lr(table, mode == "3d", blank_count, barcode_count, 0.05)
+    np.testing.assert_array_equal(out["_row"].to_numpy(), g[f"kept_lr_{mode}"])
+    np.testing.assert_allclose(out["predicted_probability"].to_numpy(dtype=float), g[f"lr_probability_{mode}"],
+                               rtol=1e-12)
+    assert (out["cell_id"] == -1).all() and 0 < len(out) < len(table)
+
+
+def test_histogram_edges_host_mirror_equals_oracle():
+    """The product computes the blank-fraction histogram edges on the host (O(bins) work): same edges as the
+    oracle's restatement of PD:3494-3655, including the degenerate single-value axes."""
+    from merfish3d_analysis_b200 import table_stage
+
+    table, _b, _k = table_for("3d")
+    inten = table["magnitude_mean"].to_numpy(float)
+    area = table["area"].to_numpy(float)
+    dist = table["distance_min"].to_numpy(float)
+    e0, e1, e2 = table_stage._edges(inten, area, dist, None, None, None)
+    np.testing.assert_array_equal(e0, tor.intensity_edges(inten))
+    np.testing.assert_array_equal(e1, tor.voxel_number_edges(area))
+    np.testing.assert_array_equal(e2, tor.vector_distance_edges(dist))
+    small = area[:50].clip(5, 9)  # <= 10 distinct integer areas -> unit bins
+    flat = np.full(30, 0.25)
+    e0, e1, e2 = table_stage._edges(flat, small, flat, None, None, None)
+    np.testing.assert_array_equal(e0, tor.intensity_edges(flat))
+    np.testing.assert_array_equal(e1, tor.voxel_number_edges(small))
+    np.testing.assert_array_equal(e2, tor.vector_distance_edges(flat))
+    with pytest.raises(ValueError, match="at least two finite"):
+        table_stage._edges(inten, area, dist, [1.0], None, None)
