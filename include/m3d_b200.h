@@ -217,6 +217,17 @@ int m3d_centroid_statistics(m3d_ctx* ctx, const int32_t* labels_dev, const void*
 int m3d_inertia_eigvals(m3d_ctx* ctx, const double* table_dev, int64_t n_rows, int64_t n_cols,
                         double* eigvals_dev, void* stream);
 
+/* _assign_cells (PD:4076-4135): cell_id_dev[i] = 1 + index of the lowest-numbered polygon containing point i
+ * (yx_dev = (n,2) float64 global_y, global_x), 0 when none does.  Polygons: verts_yx_dev (total,2) float64 with
+ * poly_offsets_dev (P+1) int64, bbox_dev (P,4) = ymin,xmin,ymax,xmax.  Candidate lookup through a uniform grid
+ * built by the caller: cell (gy,gx) of size cell_size at (origin_y, origin_x) lists the polygons whose box
+ * touches it in cell_polys_dev[cell_start_dev[c] .. cell_start_dev[c+1]) (ascending polygon index).  Containment
+ * = even-odd crossing rule in float64 (shapely `contains` away from polygon boundaries). */
+int m3d_assign_cells(m3d_ctx* ctx, const double* yx_dev, int64_t n, const double* verts_yx_dev,
+                     const int64_t* poly_offsets_dev, const double* bbox_dev, const int32_t* cell_start_dev,
+                     const int32_t* cell_polys_dev, double origin_y, double origin_x, double cell_size,
+                     int grid_y, int grid_x, int32_t* cell_id_dev, void* stream);
+
 /* Capacity (entries) of the search -> regionprops record buffers; 0 = automatic
  * (max(2^20, n_vox/16)).  When the foreground exceeds it the regionprops kernel recomputes the
  * traces instead; results are identical.  Exposed so tests can force the overflow path. */

@@ -1645,15 +1645,26 @@ class PixelDecoder:
             self._df_barcodes_loaded = out
 
     def _assign_cells(self) -> None:
-        """PD:4076-4135.  Needs Cellpose ImageJ ROIs (``segmentation/cellpose/imagej_rois/
-        global_coords_rois.zip``); like the reference, a missing file is reported and skipped.
-        Reading ROI archives (roifile / shapely / rtree upstream) is outside this build."""
-        roi = Path(self._datastore._datastore_path) / "segmentation" / "cellpose" / "imagej_rois" / \
+        """PD:4076-4135: ``cell_id`` from the Cellpose ImageJ ROIs in global coordinates
+        (``segmentation/cellpose/imagej_rois/global_coords_rois.zip``): the archive is parsed by ``roi.py``
+        (the reference uses roifile), point-in-polygon runs on the device (``m3d_assign_cells``; the reference
+        uses an R-tree + shapely per row).  A missing / unreadable archive is reported and skipped."""
+        import zipfile
+
+        from . import roi as _roi
+
+        path = Path(self._datastore._datastore_path) / "segmentation" / "cellpose" / "imagej_rois" / \
             "global_coords_rois.zip"
-        if not roi.exists():
-            print(f"Failed to read ROIs: [Errno 2] No such file or directory: '{roi}'")
+        try:
+            rois = _roi.read_roi_zip(path)
+        except (OSError, FileNotFoundError, ValueError, zipfile.BadZipFile) as e:
+            print(f"Failed to read ROIs: {e}")
             return
-        raise NotImplementedError("cell assignment from ImageJ ROI archives is outside this build (SURVEY 8f-3)")
+        # roi.subpixel_coordinates[:, ::-1] (PD:4074): (x, y) vertices -> (y, x) polygons; cell ids count
+        # only the usable polygons, like the reference's shapely_polygons list
+        polygons = [r[:, ::-1] for r in rois if r is not None and len(r) >= 3]
+        self._df_filtered_barcodes["cell_id"] = table_stage.assign_cells(
+            self._ctx(self._local_gpu()), self._df_filtered_barcodes, polygons)
 
     def decode_all_tiles(
         self,

@@ -106,6 +106,11 @@ SIGNATURES = {
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.c_int64,
          C.c_void_p, C.c_void_p, C.c_void_p],
     ),
+    "m3d_assign_cells": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+         C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p],
+    ),
     "m3d_inertia_eigvals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "m3d_set_sparse_capacity": (C.c_int, [C.c_void_p, C.c_int64]),
     "m3d_launch_count": (C.c_int64, [C.c_void_p]),
@@ -510,6 +515,22 @@ class DecodeContext:
             "m3d_centroid_statistics",
         )
         return sums, peak
+
+    def assign_cells(self, yx, verts_yx, poly_offsets, bbox, cell_start, cell_polys, origin_yx, cell_size, grid_yx):
+        """int32 cell ids (0 = none) of the points ``yx`` ((n, 2) float64 device tensor); see m3d_assign_cells."""
+        import torch
+
+        n = int(yx.shape[0])
+        out = torch.zeros(n, dtype=torch.int32, device=self.device)
+        _check(
+            self._lib.m3d_assign_cells(
+                self._h, _ptr(yx), n, _ptr(verts_yx), _ptr(poly_offsets), _ptr(bbox), _ptr(cell_start), _ptr(cell_polys),
+                float(origin_yx[0]), float(origin_yx[1]), float(cell_size), int(grid_yx[0]), int(grid_yx[1]), _ptr(out),
+                _stream(self.device),
+            ),
+            "m3d_assign_cells",
+        )
+        return out
 
     def inertia_eigvals(self, table):
         """(n, 3) float64 inertia-tensor eigenvalues (descending, clipped at 0) of a feature table."""

@@ -55,6 +55,7 @@ enum M3dKernel {
     KF_TABLE_WITHIN,
     KF_CENTROID,
     KF_EIGVALS,
+    KF_TABLE_CELLS,
     KF_COUNT
 };
 

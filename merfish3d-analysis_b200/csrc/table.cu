@@ -291,6 +291,44 @@ within_drop_kernel(size_t n, const uint32_t* __restrict__ parent, const uint32_t
     drop[i] = best_i[parent[i]] != (uint32_t)i ? 1 : 0;
 }
 
+// ------------------------------------------------------------------ PD:4076-4135 cell assignment
+// cell_id = 1 + index of the first polygon (lowest index) that contains the point, 0 when none does.
+// Candidates come from a uniform grid over the polygon bounding boxes (the reference uses an R-tree on the same
+// boxes); containment is the even-odd crossing rule in float64 = shapely's `contains` for every point that is
+// not exactly on a polygon boundary.
+__global__ void __launch_bounds__(TB)
+assign_cells_kernel(const double* __restrict__ yx, size_t n, const double* __restrict__ verts,
+                    const long long* __restrict__ offs, const double* __restrict__ bbox,
+                    const int32_t* __restrict__ cell_start, const int32_t* __restrict__ cell_polys, double oy, double ox,
+                    double inv_cell, int gy, int gx, int32_t* __restrict__ cell_id) {
+    const size_t i = (size_t)blockIdx.x * TB + threadIdx.x;
+    if (i >= n) return;
+    const double py = yx[2 * i], px = yx[2 * i + 1];
+    int out = 0;
+    const double fy = floor((py - oy) * inv_cell), fx = floor((px - ox) * inv_cell);
+    if (fy >= 0.0 && fx >= 0.0 && fy < (double)gy && fx < (double)gx) {
+        const int c = (int)fy * gx + (int)fx;
+        for (int e = cell_start[c]; e < cell_start[c + 1] && out == 0; ++e) {
+            const int p = cell_polys[e];
+            const double* bb = bbox + 4 * (size_t)p;
+            if (py < bb[0] || px < bb[1] || py > bb[2] || px > bb[3]) continue;
+            const long long a = offs[p], b = offs[p + 1];
+            bool inside = false;
+            long long j = b - 1;
+            for (long long k = a; k < b; j = k++) {
+                const double yi = verts[2 * k], xi = verts[2 * k + 1];
+                const double yj = verts[2 * j], xj = verts[2 * j + 1];
+                if ((yi > py) != (yj > py)) {
+                    const double xc = __dadd_rn(__ddiv_rn(__dmul_rn(__dsub_rn(xj, xi), __dsub_rn(py, yi)), __dsub_rn(yj, yi)), xi);
+                    if (px < xc) inside = !inside;
+                }
+            }
+            if (inside) out = p + 1;
+        }
+    }
+    cell_id[i] = out;
+}
+
 // shared set-up: bounds -> grid spec -> sorted (key, row) lists in ctx scratch
 int build_grid(m3d_ctx* ctx, const double* zyx, const int32_t* tile, size_t n, double cell_zyx[3], int use_z,
                GridSpec* G_out, unsigned long long** keys_out, uint32_t** idx_out, cudaStream_t st, const char* who) {
@@ -436,6 +474,27 @@ extern "C" int m3d_within_tile_duplicates(m3d_ctx* ctx, const double* zyx_dev, c
     M3D_LAUNCH(ctx, KF_TABLE_WITHIN, st,
                within_best_i_kernel<<<nb, TB, 0, st>>>(distance_min_dev, nn, parent, best_d, best_i));
     M3D_LAUNCH(ctx, KF_TABLE_WITHIN, st, within_drop_kernel<<<nb, TB, 0, st>>>(nn, parent, best_i, drop_dev));
+    M3D_CHECK_LAUNCH();
+    return M3D_OK;
+}
+
+extern "C" int m3d_assign_cells(m3d_ctx* ctx, const double* yx_dev, int64_t n, const double* verts_yx_dev,
+                                const int64_t* poly_offsets_dev, const double* bbox_dev, const int32_t* cell_start_dev,
+                                const int32_t* cell_polys_dev, double origin_y, double origin_x, double cell_size,
+                                int grid_y, int grid_x, int32_t* cell_id_dev, void* stream) {
+    if (!ctx || n < 0 || grid_y < 1 || grid_x < 1 || !(cell_size > 0.0))
+        return m3d_fail(M3D_ERR_ARG, "m3d_assign_cells: bad argument");
+    if (n == 0) return M3D_OK;
+    if (!yx_dev || !verts_yx_dev || !poly_offsets_dev || !bbox_dev || !cell_start_dev || !cell_polys_dev || !cell_id_dev)
+        return m3d_fail(M3D_ERR_ARG, "m3d_assign_cells: null argument");
+    M3D_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int nb = (int)(((size_t)n + TB - 1) / TB);
+    M3D_LAUNCH(ctx, KF_TABLE_CELLS, st,
+               assign_cells_kernel<<<nb, TB, 0, st>>>(yx_dev, (size_t)n, verts_yx_dev,
+                                                       reinterpret_cast<const long long*>(poly_offsets_dev), bbox_dev,
+                                                       cell_start_dev, cell_polys_dev, origin_y, origin_x, 1.0 / cell_size,
+                                                       grid_y, grid_x, cell_id_dev));
     M3D_CHECK_LAUNCH();
     return M3D_OK;
 }

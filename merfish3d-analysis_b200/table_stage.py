@@ -278,3 +278,68 @@ def remove_duplicates_within_tile(ctx: DecodeContext, table: pd.DataFrame, radiu
     d_gene = torch.from_numpy(np.ascontiguousarray(gene)).to(ctx.device)
     drop = ctx.within_tile_duplicates(zyx, tile, d_gene, dmin, radius_xy, radius_z).cpu().numpy().astype(bool)
     return df[~drop].reset_index(drop=True), drop
+
+
+# ------------------------------------------------------------------------- cell assignment
+def polygon_grid(polygons_yx: list[np.ndarray | None], max_cells_per_axis: int = 2048):
+    """Host index for ``m3d_assign_cells``: flattened vertices, offsets, bounding boxes and a uniform grid whose
+    cells list (ascending) the polygons whose box touches them.  ``None`` / degenerate entries keep their index
+    (cell ids are positions in the ROI archive, PD:4099-4105) but can never contain a point."""
+    P = len(polygons_yx)
+    counts = np.array([0 if p is None or len(p) < 3 else len(p) for p in polygons_yx], dtype=np.int64)
+    offsets = np.zeros(P + 1, dtype=np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    verts = np.zeros((max(int(offsets[-1]), 1), 2), dtype=np.float64)
+    bbox = np.zeros((max(P, 1), 4), dtype=np.float64)
+    bbox[:, :2], bbox[:, 2:] = np.inf, -np.inf  # empty boxes never match
+    for i, p in enumerate(polygons_yx):
+        if counts[i]:
+            q = np.asarray(p, dtype=np.float64)
+            verts[offsets[i] : offsets[i + 1]] = q
+            bbox[i] = (q[:, 0].min(), q[:, 1].min(), q[:, 0].max(), q[:, 1].max())
+    valid = np.flatnonzero(counts > 0)
+    if valid.size == 0:
+        return dict(verts=verts, offsets=offsets, bbox=bbox, cell_start=np.zeros(2, dtype=np.int32),
+                    cell_polys=np.zeros(1, dtype=np.int32), origin=(0.0, 0.0), cell=1.0, grid=(1, 1))
+    lo = bbox[valid, :2].min(axis=0)
+    hi = bbox[valid, 2:].max(axis=0)
+    ext = bbox[valid, 2:] - bbox[valid, :2]
+    cell = float(max(np.median(ext), (hi - lo).max() / max_cells_per_axis, 1e-9))
+    gy = int(np.floor((hi[0] - lo[0]) / cell)) + 1
+    gx = int(np.floor((hi[1] - lo[1]) / cell)) + 1
+    c0 = np.floor((bbox[valid, :2] - lo) / cell).astype(np.int64)
+    c1 = np.floor((bbox[valid, 2:] - lo) / cell).astype(np.int64)
+    c1 = np.minimum(c1, [gy - 1, gx - 1])
+    cells, polys = [], []
+    for (y0, x0), (y1, x1), p in zip(c0, c1, valid):
+        yy, xx = np.meshgrid(np.arange(y0, y1 + 1), np.arange(x0, x1 + 1), indexing="ij")
+        c = (yy * gx + xx).ravel()
+        cells.append(c)
+        polys.append(np.full(c.size, p, dtype=np.int64))
+    cells = np.concatenate(cells)
+    polys = np.concatenate(polys)
+    order = np.lexsort((polys, cells))  # by cell, then ascending polygon index
+    cells, polys = cells[order], polys[order]
+    cell_start = np.zeros(gy * gx + 1, dtype=np.int64)
+    np.add.at(cell_start, cells + 1, 1)
+    np.cumsum(cell_start, out=cell_start)
+    return dict(verts=verts, offsets=offsets, bbox=bbox, cell_start=cell_start.astype(np.int32),
+                cell_polys=polys.astype(np.int32), origin=(float(lo[0]), float(lo[1])), cell=cell, grid=(gy, gx))
+
+
+def assign_cells(ctx: DecodeContext, filtered: pd.DataFrame, polygons_yx: list[np.ndarray | None]) -> np.ndarray:
+    """PD:4107-4135: ``cell_id`` of every transcript = 1 + index of the (first) polygon containing
+    (global_y, global_x), 0 when none does."""
+    import torch
+
+    if len(filtered) == 0:
+        return np.zeros(0, dtype=np.int64)
+    g = polygon_grid(polygons_yx)
+    dev = ctx.device
+    yx = np.array(filtered[["global_y", "global_x"]].to_numpy(dtype=np.float64), order="C", copy=True)
+    ids = ctx.assign_cells(
+        torch.from_numpy(yx).to(dev), torch.from_numpy(g["verts"]).to(dev), torch.from_numpy(g["offsets"]).to(dev),
+        torch.from_numpy(g["bbox"]).to(dev), torch.from_numpy(g["cell_start"]).to(dev),
+        torch.from_numpy(g["cell_polys"]).to(dev), g["origin"], g["cell"], g["grid"],
+    )
+    return ids.cpu().numpy().astype(np.int64)

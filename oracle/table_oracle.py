@@ -209,3 +209,31 @@ def within_tile_duplicates(coords_zyx: np.ndarray, tile_idx: np.ndarray, gene_id
                 best = members[np.lexsort((members, distance_min[members]))][0]
                 drop[members[members != best]] = True
     return drop
+
+
+def assign_cells(points_yx: np.ndarray, polygons_yx: list[np.ndarray]) -> np.ndarray:
+    """PD:4107-4135 restated without rtree / shapely (neither is installed; parity UNPINNED for this function):
+    1 + index of the lowest-numbered polygon whose interior contains the point (even-odd rule, float64), else 0."""
+    pts = np.asarray(points_yx, dtype=np.float64)
+    out = np.zeros(len(pts), dtype=np.int64)
+    for idx in range(len(polygons_yx) - 1, -1, -1):  # descending, so the lowest index is written last
+        poly = np.asarray(polygons_yx[idx], dtype=np.float64)
+        if len(poly) < 3:
+            continue
+        y0, x0, y1, x1 = poly[:, 0].min(), poly[:, 1].min(), poly[:, 0].max(), poly[:, 1].max()
+        cand = np.flatnonzero((pts[:, 0] >= y0) & (pts[:, 0] <= y1) & (pts[:, 1] >= x0) & (pts[:, 1] <= x1))
+        if cand.size == 0:
+            continue
+        py, px = pts[cand, 0], pts[cand, 1]
+        inside = np.zeros(cand.size, dtype=bool)
+        j = len(poly) - 1
+        for k in range(len(poly)):
+            yi, xi = poly[k]
+            yj, xj = poly[j]
+            cross = (yi > py) != (yj > py)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                xc = (xj - xi) * (py - yi) / (yj - yi) + xi
+            inside ^= cross & (px < xc)
+            j = k
+        out[cand[inside]] = idx + 1
+    return out

@@ -164,3 +164,43 @@ def test_decode_all_tiles_runs_the_table_stage(tmp_path):
     dec2.optimize_filtering(assign_to_cells=False)
     out2 = ds.load_global_filtered_decoded_spots()
     assert len(out2) == len(out)
+
+
+def test_assign_cells_from_imagej_rois(tmp_path):
+    """decode_all_tiles' last step: ImageJ ROI archive -> polygons -> device point-in-polygon, against the
+    oracle's even-odd restatement (shapely / rtree are not installed: unpinned), incl. concave and overlapping
+    cells (lowest index wins), an unusable ROI in the archive and points far outside every cell."""
+    import zipfile
+
+    from merfish3d_analysis_b200 import roi
+
+    rng = np.random.default_rng(8)
+    polys_xy = []
+    for i in range(400):  # star-shaped (concave) cells on a jittered lattice, some overlapping
+        cy, cx = (i // 20) * 30.0 + rng.uniform(0, 12), (i % 20) * 30.0 + rng.uniform(0, 12)
+        ang = np.sort(rng.uniform(0, 2 * np.pi, rng.integers(8, 40)))
+        rad = rng.uniform(6, 20, ang.size)
+        polys_xy.append(np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], axis=1))
+    dec, ds = _decoder(tmp_path, "3d")
+    roi_dir = Path(ds._datastore_path) / "segmentation" / "cellpose" / "imagej_rois"
+    roi_dir.mkdir(parents=True)
+    roi.write_roi_zip(roi_dir / "global_coords_rois.zip", polys_xy)
+    with zipfile.ZipFile(roi_dir / "global_coords_rois.zip", "a") as zf:
+        zf.writestr("zzz_line.roi", b"Iout" + bytes(60))  # an ROI without an outline: skipped, ids unchanged
+    n = 50000
+    df = pd.DataFrame({"global_y": np.round(rng.uniform(-50, 650, n), 2), "global_x": np.round(rng.uniform(-50, 650, n), 2),
+                       "gene_id": "g", "cell_id": -1})
+    dec._df_filtered_barcodes = df.copy()
+    dec._assign_cells()
+    got = dec._df_filtered_barcodes["cell_id"].to_numpy()
+    # the archive stores float32 vertices: the oracle sees what the reader returns
+    polys_yx = [p[:, ::-1] for p in roi.read_roi_zip(roi_dir / "global_coords_rois.zip") if p is not None]
+    assert len(polys_yx) == 400
+    want = tor.assign_cells(df[["global_y", "global_x"]].to_numpy(float), polys_yx)
+    np.testing.assert_array_equal(got, want)
+    assert 0.2 < (got > 0).mean() < 0.9 and got.max() <= 400
+    # no archive: reported and skipped like the reference
+    dec2, _ds2 = _decoder(tmp_path / "b", "3d")
+    dec2._df_filtered_barcodes = df.copy()
+    dec2._assign_cells()
+    assert (dec2._df_filtered_barcodes["cell_id"] == -1).all()
