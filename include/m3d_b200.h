@@ -96,6 +96,19 @@ int m3d_warp_affine(m3d_ctx* ctx, const void* in_dev, int in_dtype, const float*
                     const int64_t dims[3], const double matrix_host[9], const double offset_host[3],
                     int64_t out_z0, int64_t out_nz, float* out_dev, void* stream);
 
+/* Affine + SOFIMA flow-field warp of one bit volume (PD:1882-1889 -> utils/decode_warping.py:248-305 ->
+ * utils/multiview_registration.py:905-1131).  flow_dev = (3, fz, fy, fx) float32, channels X, Y, Z displacements in
+ * reference pixels on a grid of stride `stride_zyx` whose first sample sits at `box_start_zyx`.  Per output voxel:
+ * flow interpolated (SciPy order-1, constant 0 outside), added to the voxel index, mapped through
+ * transform (4x4 row-major float32, physical z,y,x) with spacing / origin, and the moving volume sampled once
+ * (SciPy order-1, constant 0) -- float32 coordinate arithmetic in the reference's order of operations.
+ * Output planes [out_z0, out_z0 + out_nz) of the (out_dims) reference grid are written to out_dev. */
+int m3d_warp_flow(m3d_ctx* ctx, const void* in_dev, int in_dtype, const float* predictor_dev,
+                  const int64_t dims[3], const float transform_host[16], const float spacing_host[3],
+                  const float origin_host[3], const float* flow_dev, const int64_t flow_dims[3],
+                  const float stride_zyx_host[3], const float box_start_zyx_host[3],
+                  const int64_t out_dims[3], int64_t out_z0, int64_t out_nz, float* out_dev, void* stream);
+
 /* _lp_filter / _lowpass_image (PD:1948-2024): per-volume Gaussian, reflect boundary,
  * radius int(4*sigma+0.5), axis order z,y,x, fp64 accumulation, fp32 result per pass
  * (scipy.ndimage.gaussian_filter semantics).  mode2d!=0 filters y,x only (per plane).

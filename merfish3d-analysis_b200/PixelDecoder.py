@@ -427,7 +427,8 @@ class PixelDecoder:
 
         utils/decode_warping.py:184-245 (round transform x inverse chromatic transform) and
         utils/multiview_registration.py:857-870 (physical -> pixel matrix / offset), float32 like
-        the reference.  SOFIMA flow fields are refused (not part of this build)."""
+        the reference.  Bits whose round carries a SOFIMA flow field return a ``{"kind": "flow", ...}`` dict
+        for ``m3d_warp_flow`` instead."""
         ds = self._datastore
         if _is_identity_store(ds):
             return None
@@ -447,9 +448,24 @@ class PixelDecoder:
         if round_id is not None and hasattr(ds, "load_local_sofima_flow_field"):
             flow = ds.load_local_sofima_flow_field(tile=tile, round=round_id, return_future=False)
         if flow is not None:
-            _field, attrs = flow
+            field, attrs = flow
             if not str(attrs.get("sofima_status", "")).startswith("identity_fallback"):
-                raise NotImplementedError("SOFIMA flow-field warping is not part of this build (SURVEY 8f-1)")
+                # decode_warping.py:163-174: affine + SOFIMA flow, sampled once on the device (m3d_warp_flow)
+                field = np.asarray(field, dtype=np.float32)
+                if field.ndim != 4:
+                    raise ValueError("sofima_flow_field_xyz_px must have channel plus ZYX axes.")
+                if field.shape[0] != 3 and field.shape[-1] == 3:
+                    field = np.moveaxis(field, -1, 0)
+                if field.shape[0] != 3:
+                    raise ValueError("SOFIMA flow field must have three XYZ channels.")
+                return {
+                    "kind": "flow", "transform": np.asarray(transform, dtype=np.float32),
+                    "flow": np.ascontiguousarray(field),
+                    "stride_zyx": np.asarray(attrs["map_stride_zyx_px"], dtype=np.float32),
+                    "box_start_zyx": np.asarray(attrs["map_box_start_xyz_px"], dtype=np.float32)[[2, 1, 0]],
+                    "reference_shape": tuple(int(v) for v in attrs["reference_shape_zyx_px"]),
+                    "spacing": np.asarray(ds.voxel_size_zyx_um, dtype=np.float32),
+                }
         if np.allclose(transform, np.eye(4, dtype=np.float32)):  # decode_warping.py:152-157
             return None
         spacing = np.asarray(ds.voxel_size_zyx_um, dtype=np.float32)
@@ -459,6 +475,20 @@ class PixelDecoder:
         matrix_px = (linear_um * spacing[np.newaxis, :]) / spacing[:, np.newaxis]
         offset_px = (linear_um @ origin + translation_um - origin) / spacing
         return np.asarray(matrix_px, dtype=np.float32), np.asarray(offset_px, dtype=np.float32)
+
+    def _warp_volume(self, ctx, r, p, warp, out_z0=None, out_nz=None, out=None):
+        """Apply a decode-time warp (tuple = affine matrix/offset in pixels, dict = affine + SOFIMA flow)."""
+        import torch
+
+        if isinstance(warp, dict):
+            flow = torch.empty(warp["flow"].shape, dtype=torch.float32, device=ctx.device)
+            ctx.upload([(warp["flow"], flow)])
+            return ctx.warp_flow(r, warp["transform"], warp["spacing"], flow, warp["stride_zyx"], warp["box_start_zyx"],
+                                 warp["reference_shape"], predictor=p, out_z0=0 if out_z0 is None else out_z0,
+                                 out_nz=out_nz, out=out)
+        if out_z0 is None:
+            return ctx.warp_affine(r, warp[0], warp[1], predictor=p)
+        return ctx.warp_affine(r, warp[0], warp[1], predictor=p, out_z0=out_z0, out_nz=out_nz, out=out)
 
     @staticmethod
     def _is_unit_predictor(predictor) -> bool:
@@ -480,7 +510,7 @@ class PixelDecoder:
         r = to_dev(readout, np.float32 if is_float else np.uint16)
         p = None if self._is_unit_predictor(predictor) else to_dev(predictor, np.float32)
         if warp is not None:
-            return ctx.warp_affine(r, warp[0], warp[1], predictor=p)
+            return self._warp_volume(ctx, r, p, warp)
         if is_float:
             return r if p is None else r * p
         return ctx.weight(r, p)
@@ -656,7 +686,7 @@ class PixelDecoder:
                 else:
                     r = to_dev(ra, npdt)  # the warp samples the whole native volume
                     p = None if pa is None else to_dev(pa, np.float32)
-                    ctx.warp_affine(r, warp[0], warp[1], predictor=p, out_z0=a, out_nz=b - a, out=stack[i])
+                    self._warp_volume(ctx, r, p, warp, out_z0=a, out_nz=b - a, out=stack[i])
                 del r, p
             st["readout"], st["predictor"], st["stack"] = None, None, stack
         else:

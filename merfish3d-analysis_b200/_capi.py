@@ -49,6 +49,12 @@ SIGNATURES = {
         [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double),
          C.POINTER(C.c_double), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p],
     ),
+    "m3d_warp_flow": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_float), C.POINTER(C.c_float),
+         C.POINTER(C.c_float), C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_float), C.POINTER(C.c_float),
+         C.POINTER(C.c_int64), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p],
+    ),
     "m3d_lowpass": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int64),
@@ -316,6 +322,30 @@ class DecodeContext:
                                       self._dims(volume.shape), m, o, int(out_z0), nz, _ptr(out),
                                       _stream(self.device)),
             "m3d_warp_affine",
+        )
+        return out
+
+    def warp_flow(self, volume, transform_zyx_um, spacing_zyx_um, flow, stride_zyx, box_start_zyx, out_shape,
+                  predictor=None, origin_zyx_um=(0.0, 0.0, 0.0), out_z0: int = 0, out_nz=None, out=None):
+        """Affine + SOFIMA flow warp of one (z, y, x) volume; ``flow`` = (3, fz, fy, fx) float32 device tensor."""
+        import torch
+
+        if volume.dim() != 3 or flow.dim() != 4 or flow.shape[0] != 3:
+            raise ValueError("volume must be (z, y, x) and flow (3, fz, fy, fx)")
+        nz = int(out_shape[0]) if out_nz is None else int(out_nz)
+        if out is None:
+            out = torch.empty((nz, int(out_shape[1]), int(out_shape[2])), dtype=torch.float32, device=volume.device)
+        f3 = C.c_float * 3
+        t = (C.c_float * 16)(*[float(v) for v in np.asarray(transform_zyx_um, dtype=np.float32).reshape(16)])
+        _check(
+            self._lib.m3d_warp_flow(
+                self._h, _ptr(volume), _dtype_code(volume), _ptr(predictor), self._dims(volume.shape), t,
+                f3(*[float(np.float32(v)) for v in spacing_zyx_um]), f3(*[float(np.float32(v)) for v in origin_zyx_um]),
+                _ptr(flow), self._dims(flow.shape[1:]), f3(*[float(np.float32(v)) for v in stride_zyx]),
+                f3(*[float(np.float32(v)) for v in box_start_zyx]), self._dims(out_shape), int(out_z0), nz, _ptr(out),
+                _stream(self.device),
+            ),
+            "m3d_warp_flow",
         )
         return out
 

@@ -370,6 +370,96 @@ struct AffineParams {
     double off[3];
 };
 
+// scipy.ndimage order-1 sampling (NI_GeometricTransform, mode='constant', cval=0) of one volume at a float64
+// coordinate: outside [0, dim-1] on any axis -> 0; weights (1-f, f) per axis; taps summed in z,y,x nesting order
+// with value * wz * wy * wx, all in float64, like SciPy.  The predictor multiply (float32) is fused into the taps.
+template <typename T, bool PRED>
+__device__ __forceinline__ double sample_order1(const T* __restrict__ in, const float* __restrict__ pred, int Z, int Y, int X,
+                                                const double (&c)[3]) {
+    const int dims[3] = {Z, Y, X};
+    const size_t plane = (size_t)Y * X;
+    int st[3];
+    double w[3][2];
+    bool outside = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        outside |= !(c[a] >= 0.0 && c[a] <= (double)(dims[a] - 1));  // NaN coordinates are outside too
+        const double fl = floor(c[a]);
+        st[a] = (int)fl;
+        const double f = __dadd_rn(c[a], -fl);
+        w[a][0] = __dadd_rn(1.0, -f);
+        w[a][1] = f;
+    }
+    double t = 0.0;
+    if (!outside) {
+#pragma unroll
+        for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int iz = st[0] + dz, iy = st[1] + dy, ix = st[2] + dx;
+                    double v = 0.0;
+                    if (iz < Z && iy < Y && ix < X) {  // lower bounds hold: coordinates are >= 0
+                        const size_t j = (size_t)iz * plane + (size_t)iy * X + ix;
+                        float fv = in_as_f32<T>(in, j);
+                        if (PRED) fv = __fmul_rn(fv, __ldg(pred + j));
+                        v = (double)fv;
+                    }
+                    const double term = __dmul_rn(__dmul_rn(__dmul_rn(v, w[0][dz]), w[1][dy]), w[2][dx]);
+                    t = __dadd_rn(t, term);
+                }
+    }
+    return t;
+}
+
+// Affine + SOFIMA flow warp (utils/multiview_registration.py:905-1131): the coarse flow field (3 channels X,Y,Z
+// on a strided grid) is interpolated at every output voxel, added to the voxel index, pushed through the
+// physical affine and the moving image is sampled once.  All coordinate arithmetic is float32 in the reference's
+// order of operations; both interpolations are SciPy order-1 in float64.
+struct FlowParams {
+    float t[12];          // rows 0..2 of the 4x4 physical transform (z, y, x)
+    float spacing[3];     // z, y, x
+    float origin[3];
+    float stride[3];      // flow grid stride, z, y, x
+    float box_start[3];   // reference coordinate of the first flow sample, z, y, x
+    int fz, fy, fx;       // flow grid dims
+};
+
+template <typename T, bool PRED>
+__global__ void __launch_bounds__(256)
+warp_flow_kernel(const T* __restrict__ in, const float* __restrict__ pred, int Z, int Y, int X,
+                 const float* __restrict__ flow, FlowParams F, int OY, int OX, int oz0, size_t n_out,
+                 float* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_out) return;
+    const size_t oplane = (size_t)OY * OX;
+    const int oz = (int)(i / oplane);
+    const size_t rem = i - (size_t)oz * oplane;
+    const int y = (int)(rem / OX), x = (int)(rem - (size_t)y * OX);
+    const float g[3] = {(float)(oz0 + oz), (float)y, (float)x};
+    double fc[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) fc[a] = (double)__fdiv_rn(__fsub_rn(g[a], F.box_start[a]), F.stride[a]);
+    const size_t fvol = (size_t)F.fz * F.fy * F.fx;
+    // channels are X, Y, Z displacements; deformed index = identity + flow (float32)
+    const float dx = __fadd_rn(g[2], (float)sample_order1<float, false>(flow, nullptr, F.fz, F.fy, F.fx, fc));
+    const float dy = __fadd_rn(g[1], (float)sample_order1<float, false>(flow + fvol, nullptr, F.fz, F.fy, F.fx, fc));
+    const float dz = __fadd_rn(g[0], (float)sample_order1<float, false>(flow + 2 * fvol, nullptr, F.fz, F.fy, F.fx, fc));
+    const float p[3] = {__fadd_rn(__fmul_rn(dz, F.spacing[0]), F.origin[0]), __fadd_rn(__fmul_rn(dy, F.spacing[1]), F.origin[1]),
+                        __fadd_rn(__fmul_rn(dx, F.spacing[2]), F.origin[2])};
+    double c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float m = __fmul_rn(F.t[4 * a], p[0]);
+        m = __fadd_rn(m, __fmul_rn(F.t[4 * a + 1], p[1]));
+        m = __fadd_rn(m, __fmul_rn(F.t[4 * a + 2], p[2]));
+        m = __fadd_rn(m, F.t[4 * a + 3]);
+        c[a] = (double)__fdiv_rn(__fsub_rn(m, F.origin[a]), F.spacing[a]);
+    }
+    out[i] = (float)sample_order1<T, PRED>(in, pred, Z, Y, X, c);
+}
+
 template <typename T, bool PRED>
 __global__ void __launch_bounds__(256)
 warp_affine_kernel(const T* __restrict__ in, const float* __restrict__ pred, int Z, int Y, int X, int oz0,
@@ -455,6 +545,54 @@ extern "C" int m3d_warp_affine(m3d_ctx* ctx, const void* in_dev, int in_dtype, c
         else
             warp_affine_kernel<float, false><<<(unsigned)blocks, 256, 0, st>>>(p, nullptr, Z, Y, X, (int)out_z0, n_out, A, out_dev);
     }
+    M3D_CHECK_LAUNCH();
+    return M3D_OK;
+}
+
+extern "C" int m3d_warp_flow(m3d_ctx* ctx, const void* in_dev, int in_dtype, const float* predictor_dev,
+                             const int64_t dims[3], const float transform_host[16], const float spacing_host[3],
+                             const float origin_host[3], const float* flow_dev, const int64_t flow_dims[3],
+                             const float stride_zyx_host[3], const float box_start_zyx_host[3],
+                             const int64_t out_dims[3], int64_t out_z0, int64_t out_nz, float* out_dev, void* stream) {
+    if (!ctx || !in_dev || !out_dev || !dims || !transform_host || !spacing_host || !origin_host || !flow_dev ||
+        !flow_dims || !stride_zyx_host || !box_start_zyx_host || !out_dims)
+        return m3d_fail(M3D_ERR_ARG, "m3d_warp_flow: null argument");
+    for (int a = 0; a < 3; ++a)
+        if (dims[a] <= 0 || dims[a] > 0x7fffffff || flow_dims[a] <= 0 || flow_dims[a] > 0x7fffffff || out_dims[a] <= 0 ||
+            out_dims[a] > 0x7fffffff)
+            return m3d_fail(M3D_ERR_ARG, "m3d_warp_flow: bad dims");
+    if (out_nz <= 0 || out_z0 < 0 || out_z0 + out_nz > out_dims[0]) return m3d_fail(M3D_ERR_ARG, "m3d_warp_flow: bad z range");
+    if (in_dtype != M3D_DTYPE_U16 && in_dtype != M3D_DTYPE_F32) return m3d_fail(M3D_ERR_ARG, "m3d_warp_flow: dtype %d", in_dtype);
+    M3D_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    FlowParams F;
+    for (int i = 0; i < 12; ++i) F.t[i] = transform_host[i];
+    for (int a = 0; a < 3; ++a) {
+        F.spacing[a] = spacing_host[a];
+        F.origin[a] = origin_host[a];
+        F.stride[a] = stride_zyx_host[a];
+        F.box_start[a] = box_start_zyx_host[a];
+    }
+    F.fz = (int)flow_dims[0];
+    F.fy = (int)flow_dims[1];
+    F.fx = (int)flow_dims[2];
+    const int Z = (int)dims[0], Y = (int)dims[1], X = (int)dims[2], OY = (int)out_dims[1], OX = (int)out_dims[2];
+    const size_t n_out = (size_t)out_nz * OY * OX;
+    const size_t blocks = (n_out + 255) / 256;
+    if (blocks > 0x7fffffffull) return m3d_fail(M3D_ERR_ARG, "m3d_warp_flow: grid too large");
+    KernelScope ks(ctx, KF_WARP_AFFINE, st);
+#define M3D_WF(TT, PP, ptr) \
+    warp_flow_kernel<TT, PP><<<(unsigned)blocks, 256, 0, st>>>(ptr, predictor_dev, Z, Y, X, flow_dev, F, OY, OX, (int)out_z0, n_out, out_dev)
+    if (in_dtype == M3D_DTYPE_U16) {
+        const uint16_t* p = reinterpret_cast<const uint16_t*>(in_dev);
+        if (predictor_dev) M3D_WF(uint16_t, true, p);
+        else M3D_WF(uint16_t, false, p);
+    } else {
+        const float* p = reinterpret_cast<const float*>(in_dev);
+        if (predictor_dev) M3D_WF(float, true, p);
+        else M3D_WF(float, false, p);
+    }
+#undef M3D_WF
     M3D_CHECK_LAUNCH();
     return M3D_OK;
 }

@@ -206,6 +206,7 @@ class ArrayDataStore:
         persist: bool = False,
         bit_round: Sequence[int] | None = None,
         round_transforms_zyx_um: Mapping[int, np.ndarray] | None = None,
+        sofima_flow_fields: Mapping[int, tuple] | None = None,
     ) -> str:
         """Register one tile: ``readouts`` (bits, z, y, x) uint16, ``predictors`` float32/None."""
         readouts = np.asarray(readouts)
@@ -237,6 +238,18 @@ class ArrayDataStore:
             meta["round_transforms_zyx_um"] = {
                 str(int(k)): np.asarray(v, dtype=float).tolist() for k, v in (round_transforms_zyx_um or {}).items()
             }
+        if sofima_flow_fields:  # {round (1-based): (flow (3, fz, fy, fx) float32 XYZ channels, attrs dict)}, DS:4282-4330
+            self._mem_flow = getattr(self, "_mem_flow", {})
+            meta["sofima_flow_attrs"] = {}
+            for rnd, (field, fattrs) in sofima_flow_fields.items():
+                self._mem_flow[(tile_id, int(rnd))] = np.ascontiguousarray(field, dtype=np.float32)
+                meta["sofima_flow_attrs"][str(int(rnd))] = {
+                    k: (np.asarray(v).tolist() if not isinstance(v, str) else v) for k, v in dict(fattrs).items()
+                }
+                if persist:
+                    d = self._datastore_path / "fiducial" / tile_id / f"round{int(rnd):03d}"
+                    d.mkdir(parents=True, exist_ok=True)
+                    np.save(d / "local_sofima_flow_field.npy", self._mem_flow[(tile_id, int(rnd))])
         attrs.setdefault("tile_meta", {})[tile_id] = meta
         self._save_calibrations_attributes(attrs)
         self._refresh(attrs)
@@ -328,12 +341,24 @@ class ArrayDataStore:
     def load_chromatic_affine_transform_zyx_um(self, *a, **k):
         return np.eye(4, dtype=np.float32)
 
-    def load_local_sofima_flow_field(self, *a, **k):
-        return None
+    def load_local_sofima_flow_field(self, tile, round, return_future: bool | None = True):
+        """(flow field (3, fz, fy, fx) float32 with X, Y, Z channels, attributes) or None (DS:4203-4280)."""
+        tile_id = self._tile_id(tile)
+        idx = round if isinstance(round, (int, np.integer)) else int(str(round)[-3:])
+        fattrs = self._tile_meta.get(tile_id, {}).get("sofima_flow_attrs", {}).get(str(int(idx)))
+        if fattrs is None:
+            return None
+        field = getattr(self, "_mem_flow", {}).get((tile_id, int(idx)))
+        if field is None:
+            p = self._datastore_path / "fiducial" / tile_id / f"round{int(idx):03d}" / "local_sofima_flow_field.npy"
+            if not p.exists():
+                return None
+            field = np.load(p)
+        return field, dict(fattrs)
 
     @property
     def has_identity_decode_transforms(self) -> bool:
-        return not any("bit_round" in m for m in self._tile_meta.values())
+        return not any("bit_round" in m or "sofima_flow_attrs" in m for m in self._tile_meta.values())
 
     # ------------------------------------------------------------------ normalisation vectors
     @staticmethod

@@ -144,6 +144,37 @@ def warp_to_reference(image: np.ndarray, transform_zyx_um, spacing_zyx_um) -> np
                                 mode="constant", cval=0.0).astype(F32, copy=False)
 
 
+def warp_to_reference_with_flow(image: np.ndarray, transform_zyx_um, spacing_zyx_um, flow_xyz: np.ndarray,
+                                stride_zyx, box_start_xyz, reference_shape=None) -> np.ndarray:
+    """utils/decode_warping.py:248-305 + utils/multiview_registration.py:985-1131 -- affine + SOFIMA flow warp:
+    the flow (channels X, Y, Z on a strided grid) is interpolated at every output voxel, added to the voxel
+    index, pushed through the physical affine and the moving image is sampled once; float32 arrays throughout,
+    ``cupyx.scipy.ndimage.map_coordinates`` restated by SciPy's (order 1, constant 0)."""
+    image = np.asarray(image, dtype=F32)
+    ref_shape = tuple(int(v) for v in (image.shape if reference_shape is None else reference_shape))
+    spacing = np.asarray(spacing_zyx_um, dtype=F32)
+    origin = np.zeros(3, dtype=F32)
+    transform = np.asarray(transform_zyx_um, dtype=F32)
+    flow = np.asarray(flow_xyz, dtype=F32)
+    stride = np.asarray(stride_zyx, dtype=F32)
+    box_start_zyx = np.asarray(box_start_xyz, dtype=F32)[[2, 1, 0]]
+    gz, gy, gx = np.meshgrid(np.arange(ref_shape[0], dtype=F32), np.arange(ref_shape[1], dtype=F32),
+                             np.arange(ref_shape[2], dtype=F32), indexing="ij")
+    flow_coords = np.stack([(gz - box_start_zyx[0]) / stride[0], (gy - box_start_zyx[1]) / stride[1],
+                            (gx - box_start_zyx[2]) / stride[2]], axis=0)
+    moved = [ident + ndi.map_coordinates(flow[c], flow_coords, order=1, mode="constant", cval=0.0)
+             for c, ident in enumerate((gx, gy, gz))]
+    pz = moved[2] * spacing[0] + origin[0]
+    py = moved[1] * spacing[1] + origin[1]
+    px = moved[0] * spacing[2] + origin[2]
+    src = []
+    for a in range(3):
+        m = transform[a, 0] * pz + transform[a, 1] * py + transform[a, 2] * px + transform[a, 3]
+        src.append((m - origin[a]) / spacing[a])
+    out = ndi.map_coordinates(image, np.stack(src, axis=0), order=1, mode="constant", cval=0.0)
+    return out.astype(F32, copy=False)
+
+
 def lowpass_active(sigma) -> bool:
     """PD:1969, PD:4543-4546."""
     return sigma is not None and not np.any(np.asarray(sigma, dtype=float) == 0)
@@ -601,18 +632,26 @@ def decode_tile(
     tile_idx: int = 0,
     bit_transforms_zyx_um=None,
     collect_centroids: tuple | None = None,
+    bit_flows=None,
     **coords,
 ):
     """PD:4471-4579 -- one tile end to end; returns (table, images dict).
 
-    ``bit_transforms_zyx_um``: optional per-bit physical 4x4 decode-time transforms (PD:1882-1889)."""
+    ``bit_transforms_zyx_um``: optional per-bit physical 4x4 decode-time transforms (PD:1882-1889);
+    ``bit_flows``: optional per-bit ``(flow, stride_zyx, box_start_xyz)`` SOFIMA fields (None = affine only)."""
     if minimum_pixels is None:
         minimum_pixels = DEFAULT_3D_MINIMUM_PIXELS if is_3d else DEFAULT_2D_MINIMUM_PIXELS
     stack = weight_readout(readout, predictor)
     if bit_transforms_zyx_um is not None:
         spacing_um = coords.get("spacing", (1.0, 1.0, 1.0))
-        stack = np.stack([warp_to_reference(stack[b], bit_transforms_zyx_um[b], spacing_um)
-                          for b in range(stack.shape[0])])
+        vols = []
+        for b in range(stack.shape[0]):
+            fl = None if bit_flows is None else bit_flows[b]
+            if fl is None:
+                vols.append(warp_to_reference(stack[b], bit_transforms_zyx_um[b], spacing_um))
+            else:  # (flow (3,fz,fy,fx), stride_zyx, box_start_xyz)
+                vols.append(warp_to_reference_with_flow(stack[b], bit_transforms_zyx_um[b], spacing_um, *fl))
+        stack = np.stack(vols)
     if is_3d and stack.shape[1] < 2:
         raise ValueError("decode_mode='3d' requires at least two z planes after applying z_range.")
     stack = lowpass_stack(stack, lowpass_sigma, is_3d)

@@ -25,7 +25,7 @@ sys.path.insert(0, str(ROOT / "tests" / "golden"))
 
 import cases  # noqa: E402
 import reference_shims as rs  # noqa: E402
-from scenarios import SCENARIOS, scenario_inputs  # noqa: E402
+from scenarios import SCENARIOS, scenario_inputs, warp_tile_kwargs  # noqa: E402
 from merfish3d_analysis_b200.datastore import ArrayDataStore  # noqa: E402
 
 OUT = ROOT / "tests" / "golden"
@@ -43,7 +43,8 @@ def run_tile_scenario(name, sc, RefPD):
     tmp = Path(tempfile.mkdtemp())
     try:
         ds = ArrayDataStore(tmp / "qi2labdatastore", codebook=df_cb, microscope_type=sc.get("microscope", "3D"))
-        ds.add_tile(stack, predictors=pred, stage_origin_zyx_um=sc.get("origin"))
+        extra = warp_tile_kwargs(sc)[0] if sc.get("warp") else {}
+        ds.add_tile(stack, predictors=pred, stage_origin_zyx_um=sc.get("origin"), **extra)
         ds.save_decode_normalization_vectors(None, "global", nrm, bkg)
         dec = RefPD(ds, merfish_bits=int(sc.get("bits", 16)), verbose=0, z_range=sc.get("z_range"), excluded_gene_ids=excluded)
         if sc.get("chroma"):

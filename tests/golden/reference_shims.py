@@ -281,6 +281,8 @@ def install() -> None:
     _stub("cupyx.scipy")
     _stub("cupyx.scipy.ndimage", gaussian_filter=ndi.gaussian_filter, affine_transform=ndi.affine_transform,
           map_coordinates=ndi.map_coordinates)
+    sys.modules["cupyx.scipy"].ndimage = sys.modules["cupyx.scipy.ndimage"]
+    sys.modules["cupyx"].scipy = sys.modules["cupyx.scipy"]
     _stub("cuvs")
     _stub("cuvs.distance", pairwise_distance=pairwise_distance)
     _stub("cucim")

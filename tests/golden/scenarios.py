@@ -23,6 +23,10 @@ SCENARIOS = {
     # configs[3] flavour: 22 bits, 300 random weight-4 codewords, 2-D decode mode
     "bits22": dict(shape=(4, 40, 48), seed=16, density=8e-3, lowpass=None, norm="global", min_px=4, bits=22,
                    microscope="2D"),
+    # decode-time warp: bits imaged in later rounds carry an affine round transform; rounds 2 and 3 also a SOFIMA
+    # flow field (round 4's is an identity fallback -> affine only); z crop on top
+    "warp": dict(shape=(8, 40, 48), seed=17, density=6e-3, lowpass=None, norm="global", min_px=4, warp=True,
+                 z_range=(1, 7)),
     "excl_crop": dict(shape=(9, 32, 40), seed=14, density=6e-3, lowpass=None, norm="global", min_px=3,
                       z_range=(2, 8), exclude=3),
 }
@@ -99,3 +103,30 @@ def synthetic_transcript_table(df_cb, seed: int, mode: str = "3d", n: int = 6000
     for k, scale in enumerate((2.0, 1.0, 0.5)):
         out[f"inertia_tensor_eigvals-{k}"] = rng.gamma(2.0, scale, m)
     return out
+
+
+def warp_tile_kwargs(sc):
+    """add_tile keywords (bit rounds, round transforms, SOFIMA flow fields) of a ``warp`` scenario, plus the
+    per-bit physical transforms / flows in the form the oracle takes."""
+    shape = sc["shape"]
+    rng = np.random.default_rng(sc["seed"] + 2000)
+    bit_round = [1 + (b // 4) for b in range(16)]  # 4 bits per round, rounds 1..4
+    xf = {}
+    for r in (2, 3, 4):
+        m = np.eye(4)
+        m[:3, :3] += rng.normal(0, 2e-3, (3, 3))
+        m[:3, 3] = rng.normal(0, 1.0, 3) * np.array([0.315, 0.098, 0.098])
+        xf[r] = m
+    stride = (2.0, 8.0, 8.0)
+    box_start_xyz = (4.0, 4.0, 1.0)
+    fshape = (3, shape[0] // 2, shape[1] // 8, shape[2] // 8)
+    flows = {}
+    for r, status in ((2, "ok"), (3, "ok"), (4, "identity_fallback_no_valid_vectors")):
+        field = rng.normal(0, 0.6, fshape).astype(np.float32)
+        attrs = dict(map_stride_zyx_px=stride, map_box_start_xyz_px=box_start_xyz,
+                     reference_shape_zyx_px=tuple(int(v) for v in shape), sofima_status=status)
+        flows[r] = (field, attrs)
+    kwargs = dict(bit_round=bit_round, round_transforms_zyx_um=xf, sofima_flow_fields=flows)
+    bit_xf = [np.eye(4, dtype=np.float32) if r == 1 else np.asarray(xf[r], dtype=np.float32) for r in bit_round]
+    bit_flows = [None if r in (1, 4) else (flows[r][0], stride, box_start_xyz) for r in bit_round]
+    return kwargs, bit_xf, bit_flows

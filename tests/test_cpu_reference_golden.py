@@ -14,7 +14,7 @@ import pytest
 
 import cases
 from oracle import decode_oracle as orc
-from scenarios import SCENARIOS, scenario_inputs
+from scenarios import SCENARIOS, scenario_inputs, warp_tile_kwargs
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
@@ -53,6 +53,15 @@ def oracle_on_scenario(sc):
     zr = sc.get("z_range")
     readout = stack if zr is None else stack[:, zr[0]:zr[1]]
     predictor = pred if (pred is None or zr is None) else pred[:, zr[0]:zr[1]]
+    if sc.get("warp"):  # the warp samples the whole native volume; the z crop follows it (PD:1882-1890)
+        _kw, bit_xf, bit_flows = warp_tile_kwargs(sc)
+        full = orc.weight_readout(stack, pred)
+        vols = [orc.warp_to_reference(full[b], bit_xf[b], (0.315, 0.098, 0.098)) if bit_flows[b] is None
+                else orc.warp_to_reference_with_flow(full[b], bit_xf[b], (0.315, 0.098, 0.098), *bit_flows[b])
+                for b in range(16)]
+        readout = np.stack(vols)
+        readout = readout if zr is None else readout[:, zr[0]:zr[1]]
+        predictor = None
     excl_idx = [] if excluded is None else [cb["gene_ids"].index(g) for g in excluded]
     coords = dict(spacing=(0.315, 0.098, 0.098))
     if sc.get("origin") is not None:

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import cases
-from scenarios import SCENARIOS, scenario_inputs
+from scenarios import SCENARIOS, scenario_inputs, warp_tile_kwargs
 from test_cpu_reference_golden import compare_with_reference_table, golden_table
 
 pytestmark = pytest.mark.gpu
@@ -27,7 +27,8 @@ def test_cuda_path_equals_reference_golden(tmp_path, name):
     df_cb, _cb, stack, pred, bkg, nrm, excluded = scenario_inputs(sc)
     np.testing.assert_array_equal(stack, g["stack"])  # the seeded inputs are the fixture's inputs
     ds = ArrayDataStore(tmp_path / "qi2labdatastore", codebook=df_cb, microscope_type=sc.get("microscope", "3D"))
-    ds.add_tile(stack, predictors=pred, stage_origin_zyx_um=sc.get("origin"))
+    extra = warp_tile_kwargs(sc)[0] if sc.get("warp") else {}
+    ds.add_tile(stack, predictors=pred, stage_origin_zyx_um=sc.get("origin"), **extra)
     ds.save_decode_normalization_vectors(None, "global", nrm, bkg)
     ref = golden_table(g)
     kw = dict(lowpass_sigma=sc["lowpass"], minimum_pixels=sc["min_px"], magnitude_threshold=sc.get("mag"),
