@@ -91,7 +91,7 @@ int m3d_weight(m3d_ctx* ctx, const uint16_t* readout_dev, const float* predictor
  * offset_host are the PIXEL-space matrix_px / offset_px of the reference.  in_dev holds the full
  * (z,y,x) volume; only output planes [out_z0, out_z0 + out_nz) are written to out_dev (float32,
  * (out_nz,y,x)), which is how z_range cropping and z-slab sharding request their planes.
- * predictor_dev is nullable.  SOFIMA flow-field warping is not part of this build. */
+ * predictor_dev is nullable.  Bits whose round carries a SOFIMA flow field go through m3d_warp_flow. */
 int m3d_warp_affine(m3d_ctx* ctx, const void* in_dev, int in_dtype, const float* predictor_dev,
                     const int64_t dims[3], const double matrix_host[9], const double offset_host[3],
                     int64_t out_z0, int64_t out_nz, float* out_dev, void* stream);
