@@ -431,6 +431,36 @@ def run_b200(args):
             }
             dec._cleanup()
             torch.cuda.empty_cache()
+        # unregistered tile (the usual case: only round-1 bits are in the reference frame): 12 of 16 bits carry an
+        # affine round transform and are resampled on the device, then the reference-default low-pass
+        if world == 1 and not args.no_extras:
+            rng_x = np.random.default_rng(7)
+            xf = {}
+            for r in (2, 3, 4):
+                m_ = np.eye(4)
+                m_[:3, :3] += rng_x.normal(0, 1e-3, (3, 3))
+                m_[:3, 3] = rng_x.normal(0, 1.0, 3) * np.array([0.315, 0.098, 0.098])
+                xf[r] = m_
+            ds4 = ArrayDataStore(Path(tmp.name) / "qi2labdatastore_unreg", codebook=df_cb)
+            ds4.add_tile(host.numpy(), bit_round=[1 + b // 4 for b in range(16)], round_transforms_zyx_um=xf)
+            ds4.save_decode_normalization_vectors(None, "global", nrm, bkg)
+            dec4 = PixelDecoder(ds4, merfish_bits=16, verbose=0)
+            for i in range(3):
+                if i == 1:
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                dec4.decode_one_tile(0, gpu_id=local, lowpass_sigma=(3.0, 1.0, 1.0), magnitude_threshold=MAG,
+                                     minimum_pixels=MIN_PX, normalization_method="global")
+            torch.cuda.synchronize()
+            un_s = (time.perf_counter() - t0) / 2
+            extras["e2e_unregistered_lowpass_on"] = {
+                "ms_per_step": un_s * 1e3, "gvoxel_per_s": n_vox / un_s / 1e9, "transcripts": int(len(dec4._df_barcodes)),
+                "note": "decode_one_tile on a tile whose bits 5-16 need the decode-time affine warp (m3d_warp_affine, "
+                        "SciPy-exact float64 taps) + low-pass (3,1,1): both run per bit behind the upload of the next bits",
+            }
+            dec4._cleanup()
+            del dec4
+            torch.cuda.empty_cache()
         # multi-tile public API: decode_all_tiles over 3 tiles (the same pinned array registered three times),
         # per-tile parquet output + the pooled table stage; tile t+1 is staged while tile t is finished
         if world == 1 and not args.no_extras:

@@ -481,8 +481,10 @@ class PixelDecoder:
         import torch
 
         if isinstance(warp, dict):
-            flow = torch.empty(warp["flow"].shape, dtype=torch.float32, device=ctx.device)
-            ctx.upload([(warp["flow"], flow)])
+            flow = warp.get("flow_dev")
+            if flow is None:
+                flow = torch.empty(warp["flow"].shape, dtype=torch.float32, device=ctx.device)
+                ctx.upload([(warp["flow"], flow)])
             return ctx.warp_flow(r, warp["transform"], warp["spacing"], flow, warp["stride_zyx"], warp["box_start_zyx"],
                                  warp["reference_shape"], predictor=p, out_z0=0 if out_z0 is None else out_z0,
                                  out_nz=out_nz, out=out)
@@ -664,31 +666,59 @@ class PixelDecoder:
         npdt = np.float32 if float_input else np.uint16
         st = {}
 
-        def to_dev(arr, dtype):
-            src = np.ascontiguousarray(arr, dtype=dtype)
-            dst = torch.empty(src.shape, dtype=torch.float32 if dtype == np.float32 else torch.uint16,
-                              device=ctx.device)
-            ctx.upload([(src, dst)])
-            return dst
-
         # every host -> device copy goes through m3d_upload_batch: straight DMA for page-locked arrays,
         # the library's pinned staging ring for the pageable arrays a datastore normally returns
         if any(w is not None for _r, _p, w in loaded):
-            stack = torch.empty((len(bit_ids), *shape), dtype=torch.float32, device=ctx.device)
-            for i, (ra, pa, warp) in enumerate(loaded):
+            # unregistered tile: every bit is uploaded in its native frame (full z: the warp samples the whole
+            # volume) and, as soon as it has arrived, weighted / warped into the round-1 frame -- and low-passed
+            # when asked -- on the compute stream while the following bits are still crossing PCIe
+            if z_bounds is not None:
+                slot = None
+            n_b = len(bit_ids)
+            native = tuple(int(v) for v in np.asarray(loaded[0][0]).shape)
+            dt = torch.float32 if float_input else torch.uint16
+            raw = self._tile_buffer(gpu_id, slot, "native", (n_b, *native), dt, ctx.device, alloc_stream)
+            rawp = None
+            if any(pa is not None for _r, pa, _w in loaded):
+                rawp = self._tile_buffer(gpu_id, slot, "native_pred", (n_b, *native), torch.float32, ctx.device,
+                                         alloc_stream)
+            stack = self._tile_buffer(gpu_id, slot, "warped", (n_b, *shape), torch.float32, ctx.device, alloc_stream)
+            lp_out = None
+            if lowpass_sigma is not None:
+                lp_out = self._tile_buffer(gpu_id, slot, "lowpassed", (n_b, *shape), torch.float32, ctx.device,
+                                           alloc_stream)
+            for _ra, _pa, warp in loaded:  # flow fields go up first: the staging ring is not re-entrant
+                if isinstance(warp, dict) and "flow_dev" not in warp:
+                    warp["flow_dev"] = torch.empty(warp["flow"].shape, dtype=torch.float32, device=ctx.device)
+                    ctx.upload([(warp["flow"], warp["flow_dev"])])
+            pieces, piece_bit = [], []
+            for i, (ra, pa, _w) in enumerate(loaded):
+                pieces.append((np.ascontiguousarray(ra, dtype=npdt), raw[i]))
+                piece_bit.append(i)
+                if pa is not None:
+                    pieces.append((np.ascontiguousarray(pa, dtype=np.float32), rawp[i]))
+                    piece_bit.append(i)
+
+            def bit_ready(i):
+                _ra, pa, warp = loaded[i]
+                p_i = None if pa is None else rawp[i]
                 if warp is None:
-                    r = to_dev(ra[a:b], npdt)
-                    p = None if pa is None else to_dev(pa[a:b], np.float32)
+                    r = raw[i, a:b]
                     if r.dtype == torch.float32:
-                        stack[i].copy_(r if p is None else r * p)
+                        stack[i].copy_(r if p_i is None else r * p_i[a:b])
                     else:
-                        ctx.weight(r, p, out=stack[i])
+                        ctx.weight(r.contiguous(), None if p_i is None else p_i[a:b].contiguous(), out=stack[i])
                 else:
-                    r = to_dev(ra, npdt)  # the warp samples the whole native volume
-                    p = None if pa is None else to_dev(pa, np.float32)
-                    self._warp_volume(ctx, r, p, warp, out_z0=a, out_nz=b - a, out=stack[i])
-                del r, p
-            st["readout"], st["predictor"], st["stack"] = None, None, stack
+                    self._warp_volume(ctx, raw[i], p_i, warp, out_z0=a, out_nz=b - a, out=stack[i])
+                if lp_out is not None:
+                    ctx.lowpass(stack[i : i + 1], lowpass_sigma, not self._is_3D, out=lp_out[i : i + 1])
+
+            self._upload_pipelined(ctx, pieces, piece_bit, bit_ready)
+            st["readout"], st["predictor"] = None, None
+            st["stack"] = stack if lp_out is None else lp_out
+            if lp_out is not None:
+                st["lowpass_done"] = True
+            return st, {"em_wvl": em_wvl, "full_z": full_z, "slot": slot}
         else:
             dt = torch.float32 if float_input else torch.uint16
             if z_bounds is not None:
@@ -719,17 +749,15 @@ class PixelDecoder:
             return st, {"em_wvl": em_wvl, "full_z": full_z, "slot": slot}
         return st, {"em_wvl": em_wvl, "full_z": full_z}
 
-    def _upload_and_lowpass(self, ctx, pieces, piece_bit, stack, pred, sigma, out):
-        """Registered tiles with the low-pass on: the per-bit Gaussian (PD:1982-2024) of bit b runs on the
-        compute stream as soon as its volume has arrived, while the volumes of the later bits are still
-        crossing PCIe on a copy stream -- the filter (float64-pipe bound, ~3.7 ms per bit) hides behind the
-        transfer (~15 ms per bit).  ``piece_bit[i]`` = bit that piece i belongs to (pieces of one bit are
-        adjacent)."""
+    def _upload_pipelined(self, ctx, pieces, piece_bit, on_bit):
+        """Upload ``pieces`` on a copy stream and call ``on_bit(b)`` -- with the compute stream current and already
+        ordered behind bit b's copies -- as soon as the last piece of bit b is enqueued, while the pieces of the
+        later bits are still being staged / crossing PCIe.  ``piece_bit[i]`` = bit of piece i (adjacent)."""
+        import threading
+
         import torch
 
         compute = torch.cuda.current_stream(ctx.device)
-        import threading
-
         skey = (ctx.device.index, threading.get_ident())  # the prefetch thread gets its own copy stream
         copy = self._copy_streams.get(skey)
         if copy is None:
@@ -737,7 +765,7 @@ class PixelDecoder:
         last_piece_of = {b: i for i, b in enumerate(piece_bit)}  # later pieces overwrite: the bit's last one
         bit_done_at = {i: b for b, i in last_piece_of.items()}
 
-        def bit_arrived(piece):
+        def piece_arrived(piece):
             b = bit_done_at.get(piece)
             if b is None:
                 return
@@ -745,12 +773,22 @@ class PixelDecoder:
             ev.record(copy)
             compute.wait_event(ev)
             with torch.cuda.stream(compute):
-                ctx.lowpass(stack[b : b + 1], sigma, not self._is_3D,
-                            predictor=None if pred is None else pred[b : b + 1], out=out[b : b + 1])
+                on_bit(b)
 
         copy.wait_stream(compute)  # buffers just allocated / filled on the compute stream
         with torch.cuda.stream(copy):
-            ctx.upload(pieces, on_piece=bit_arrived)
+            ctx.upload(pieces, on_piece=piece_arrived)
+
+    def _upload_and_lowpass(self, ctx, pieces, piece_bit, stack, pred, sigma, out):
+        """Registered tiles with the low-pass on: the per-bit Gaussian (PD:1982-2024) of bit b runs on the
+        compute stream as soon as its volume has arrived -- the filter (float64-pipe bound, ~3.7 ms per bit)
+        hides behind the transfer of the following bits (~15 ms per bit)."""
+
+        def lowpass_bit(b):
+            ctx.lowpass(stack[b : b + 1], sigma, not self._is_3D,
+                        predictor=None if pred is None else pred[b : b + 1], out=out[b : b + 1])
+
+        self._upload_pipelined(ctx, pieces, piece_bit, lowpass_bit)
         return out
 
     def _load_coordinate_metadata(self) -> None:
