@@ -278,3 +278,29 @@ def test_multi_tile_pipeline_equals_tile_by_tile(tmp_path, lowpass):
             got = ds.load_local_decoded_spots(t)
             pd.testing.assert_frame_equal(got.reset_index(drop=True), single[t].reset_index(drop=True),
                                           check_dtype=False)
+
+
+def test_multi_tile_pipeline_with_staged_pageable_uploads(tmp_path):
+    """Same, with bit volumes large enough (10 MB each, pageable NumPy memory) to go through the pinned
+    staging ring: tile t+1 is staged by the prefetch thread's upload workers while tile t runs on the main
+    stream, with the low-pass chained per bit behind the copies."""
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    df_cb, cb = cases.codebook16()
+    stacks = [cases.small_stack(cb["matrix"], shape=(20, 512, 512), seed=500 + i, density=2e-4) for i in range(3)]
+    ds = _store(tmp_path, df_cb, stacks)
+    bkg, nrm = cases.simple_vectors(16, nrm=300.0)
+    ds.save_decode_normalization_vectors(None, "global", nrm, bkg)
+    kw = dict(lowpass_sigma=(3.0, 1.0, 1.0), minimum_pixels=6, normalization_method="global")
+    single = []
+    for t in range(3):
+        one = PixelDecoder(ds, merfish_bits=16, verbose=0)
+        one.decode_one_tile(t, **kw)
+        single.append(one.decoded_barcodes)
+        one._cleanup()
+    assert sum(len(s) for s in single) > 100
+    dec = PixelDecoder(ds, merfish_bits=16, verbose=0)
+    dec.decode_all_tiles(assign_to_cells=False, **kw)
+    for t in range(3):
+        got = ds.load_local_decoded_spots(t)
+        pd.testing.assert_frame_equal(got.reset_index(drop=True), single[t].reset_index(drop=True), check_dtype=False)
