@@ -1,0 +1,61 @@
+"""Small end-to-end exercise of every kernel family for compute-sanitizer (memcheck): tiny volumes only."""
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+sys.path.insert(0, str(ROOT / "tests" / "golden"))
+import cases  # noqa: E402
+from scenarios import SCENARIOS, scenario_inputs, synthetic_transcript_table, warp_tile_kwargs  # noqa: E402
+from merfish3d_analysis_b200.datastore import ArrayDataStore  # noqa: E402
+from merfish3d_analysis_b200.PixelDecoder import PixelDecoder  # noqa: E402
+
+tmp = Path(tempfile.mkdtemp())
+n = 0
+for name in ("raw3d", "lp3d", "mode2d", "chroma", "bits22", "warp"):
+    sc = SCENARIOS[name]
+    df_cb, _cb, stack, pred, bkg, nrm, excluded = scenario_inputs(sc)
+    ds = ArrayDataStore(tmp / name, codebook=df_cb, microscope_type=sc.get("microscope", "3D"))
+    extra = warp_tile_kwargs(sc)[0] if sc.get("warp") else {}
+    ds.add_tile(stack, predictors=pred, **extra)
+    ds.add_tile(stack, predictors=pred, **extra)
+    ds.save_decode_normalization_vectors(None, "global", nrm, bkg)
+    dec = PixelDecoder(ds, merfish_bits=int(sc.get("bits", 16)), verbose=0, z_range=sc.get("z_range"))
+    dec._optimize_normalization_weights = dec._collect_chromatic_centroids = bool(sc.get("chroma"))
+    kw = dict(lowpass_sigma=sc["lowpass"], minimum_pixels=sc["min_px"], magnitude_threshold=sc.get("mag"),
+              normalization_method="global")
+    dec.decode_one_tile(0, return_results=True, **kw)   # dense kernel (tensor-core marking) + all images
+    dec.decode_one_tile(0, **kw)                        # gate + search + fused labelling
+    n += len(dec.decoded_barcodes)
+    if not sc.get("chroma"):
+        dec.decode_all_tiles(assign_to_cells=False, **kw)  # prefetch + table stage
+    dec._cleanup()
+# noise-level vectors: dense-candidate regime through the production path
+sc = SCENARIOS["raw3d"]
+df_cb, cb, stack, *_ = scenario_inputs(sc)
+ds = ArrayDataStore(tmp / "dense", codebook=df_cb)
+ds.add_tile(stack)
+ds.save_decode_normalization_vectors(None, "global", np.full(16, 17.0, np.float32), np.full(16, 187.0, np.float32))
+dec = PixelDecoder(ds, merfish_bits=16, verbose=0)
+dec.decode_one_tile(0, lowpass_sigma=None, minimum_pixels=4, normalization_method="global")
+n += len(dec.decoded_barcodes)
+# table stage incl. 2-D within-tile clusters
+for mode, micro in (("3d", "3D"), ("2d", "2D")):
+    ds = ArrayDataStore(tmp / f"tab{mode}", codebook=df_cb, microscope_type=micro,
+                        voxel_size_zyx_um=(0.315, 0.098, 0.098) if mode == "3d" else (1.5, 0.1085, 0.1085))
+    for _ in range(4):
+        ds.add_tile(np.zeros((16, 2, 4, 4), dtype=np.uint16))
+    dec = PixelDecoder(ds, merfish_bits=16, verbose=0)
+    dec._df_barcodes_loaded = synthetic_transcript_table(df_cb, seed=1, mode=mode, n=1500)
+    dec._filter_all_barcodes_blank_fraction()
+    if mode == "2d":
+        dec._remove_duplicates_within_tile(0.1085, 1.5)
+    dec._remove_duplicates_in_tile_overlap()
+    n += len(dec._df_filtered_barcodes)
+torch.cuda.synchronize()
+print("sanitize_small ok", n)
