@@ -140,8 +140,9 @@ class ClockSampler:
 _CPU_STATE = {}
 
 
-def _cpu_init():
-    """Per-process set-up outside the timed region: imports, codebook."""
+def _cpu_init(counter=None, barrier=None):
+    """Per-process set-up outside the timed region: imports, codebook and this worker's own sub-tile (every
+    worker has its data before the first task arrives, whichever worker a task lands on)."""
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     from merfish3d_analysis_b200 import synthetic
     from oracle import decode_oracle as orc
@@ -149,14 +150,23 @@ def _cpu_init():
     m = synthetic.mhd4_codebook_matrix(16)
     _CPU_STATE["m"] = m
     _CPU_STATE["cb"] = orc.load_codebook(synthetic.codebook_dataframe(m, n_blank=10), 16)
+    idx = 0
+    if counter is not None:
+        with counter.get_lock():
+            idx = counter.value
+            counter.value += 1
+    _CPU_STATE["stack"] = synthetic.make_stack(m, CPU_SAMPLE_SHAPE, SEED + idx)
+    _CPU_STATE["barrier"] = barrier
 
 
-def _cpu_make(seed):
-    from merfish3d_analysis_b200 import synthetic
-
-    if "m" not in _CPU_STATE:
-        _cpu_init()
-    _CPU_STATE["stack"] = synthetic.make_stack(_CPU_STATE["m"], CPU_SAMPLE_SHAPE, seed)
+def _cpu_ready(_):
+    """Blocks until every worker of the pool is initialised (one such task per worker)."""
+    b = _CPU_STATE.get("barrier")
+    if b is not None:
+        try:
+            b.wait(timeout=120)
+        except Exception:
+            pass
     return os.getpid()
 
 
@@ -186,10 +196,14 @@ def cpu_reference_throughput(n_rounds: int = 1):
 
     cores = os.cpu_count() or 1
     vox = int(np.prod(CPU_SAMPLE_SHAPE))
-    with ProcessPoolExecutor(max_workers=cores, initializer=_cpu_init) as ex:
-        # every worker generates its own sub-tile (chunksize 1 + a slow task keeps one per process)
-        pids = set(ex.map(_cpu_make, [SEED + i for i in range(cores)]))
-        n_tasks = len(pids) * n_rounds
+    import multiprocessing as mp
+
+    counter = mp.Value("i", 0)
+    barrier = mp.Barrier(cores)
+    with ProcessPoolExecutor(max_workers=cores, initializer=_cpu_init, initargs=(counter, barrier)) as ex:
+        # one blocking task per worker: all workers exist and have generated their sub-tile before the timer starts
+        pids = set(ex.map(_cpu_ready, range(cores)))
+        n_tasks = cores * n_rounds
         t0 = time.perf_counter()
         res = list(ex.map(_cpu_one, range(n_tasks)))
         wall = time.perf_counter() - t0
