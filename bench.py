@@ -60,7 +60,8 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []  # (sm_mhz, sm_max_mhz, [reason names])
+        self.rows = []  # (sm_mhz, sm_max_mhz, [reason names], time)
+        self.t_start = self.t_end = None
         self._stop = threading.Event()
         self._t = None
         self.source = "nvml"
@@ -96,7 +97,7 @@ class ClockSampler:
             "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
             "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
         }
-        self.rows.append((sm, self._max, [k for k, b in bits.items() if r & b]))
+        self.rows.append((sm, self._max, [k for k, b in bits.items() if r & b], time.perf_counter()))
 
     def _sample_smi(self):
         out = subprocess.run(
@@ -106,7 +107,8 @@ class ClockSampler:
         if out:
             c = [v.strip() for v in out.splitlines()[0].split(",")]
             self.rows.append((float(c[0]), float(c[1]),
-                              [n for n, v in zip(self.NAMES, c[2:6]) if v.lower().startswith("active")]))
+                              [n for n, v in zip(self.NAMES, c[2:6]) if v.lower().startswith("active")],
+                              time.perf_counter()))
 
     def _run(self):
         while not self._stop.is_set():
@@ -128,12 +130,23 @@ class ClockSampler:
         self._stop.set()
         self._t.join(timeout=6)
 
+    def mark_start(self):
+        self.t_start = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
+
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
-        reasons = sorted({r for row in self.rows for r in row[2]})
-        return {"sm_mhz": float(np.median([r[0] for r in self.rows])), "sm_max_mhz": float(max(r[1] for r in self.rows)),
-                "reasons": reasons, "samples": len(self.rows), "source": self.source}
+        rows, window = self.rows, "warm-up + timed steps (same load)"
+        if self.t_start is not None and self.t_end is not None:
+            inside = [r for r in self.rows if self.t_start <= r[3] <= self.t_end]
+            if len(inside) >= 3:
+                rows, window = inside, "timed steps"
+        reasons = sorted({r for row in rows for r in row[2]})
+        return {"sm_mhz": float(np.median([r[0] for r in rows])), "sm_max_mhz": float(max(r[1] for r in rows)),
+                "reasons": reasons, "samples": len(rows), "window": window, "source": self.source}
 
 
 # ---------------------------------------------------------------------------------- CPU arm
@@ -291,19 +304,23 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        n_feat, table = step_resident()
-    barrier()
-    ctx.reset_counters()
-    ctx.set_timing(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the sampler thread runs from the warm-up on (a timed region of a few tens of ms is shorter than a thread
+    # start-up); summary() prefers the samples that fall inside the timed window
     with ClockSampler(local) as clocks:
+        for _ in range(max(args.warmup, 3)):
+            n_feat, table = step_resident()
         barrier()
+        ctx.reset_counters()
+        ctx.set_timing(True)
+        barrier()
+        clocks.mark_start()
         e0.record()
         for _ in range(args.steps):
             n_feat, table = step_resident()
         e1.record()
         barrier()
+        clocks.mark_end()
     ms_total = e0.elapsed_time(e1)
     ktimes = ctx.kernel_times_ms()
     klaunch = ctx.launches_by_kernel()
