@@ -158,6 +158,7 @@ struct SearchSmem {
     uint32_t* hkeys;     // [1 << hash_bits] (mode 2)
     uint32_t* masks;     // [round_up(K, 8)] on-bit masks, 0 beyond K (mode 2, tensor-core on-bit sums)
     uint32_t* cand_bits; // [SEARCH_THREADS][ceil(K/32)] per-voxel candidate sets marked by the tensor-core pass (mode 2)
+    uint2* blut;         // [16] B-fragment registers by 4-bit on/off pattern (bits 2t, 2t+1, 2t+8, 2t+9 of a codeword)
     int16_t* hvals;      // [1 << hash_bits]
     uint8_t* on;         // [K][max_on]
 };
@@ -165,7 +166,7 @@ struct SearchSmem {
 static size_t search_smem_bytes(int nb, const DecodeParams& P) {
     size_t n = (size_t)(nb + 1) * XS_STRIDE * 4;
     if (P.mode >= 1) n += (size_t)P.K * 8 + (size_t)P.K * P.max_on;
-    if (P.mode == 2) n += ((size_t)1 << P.hash_bits) * 6 + (size_t)((P.K + 7) & ~7) * 4 + (size_t)SEARCH_THREADS * ((P.K + 31) / 32) * 4;
+    if (P.mode == 2) n += ((size_t)1 << P.hash_bits) * 6 + (size_t)((P.K + 7) & ~7) * 4 + (size_t)SEARCH_THREADS * ((P.K + 31) / 32) * 4 + 16 * 8 + 8;
     return n + 16;
 }
 
@@ -178,6 +179,7 @@ __device__ __forceinline__ SearchSmem stage_codebook(unsigned char* smem, const 
     s.hkeys = nullptr;
     s.masks = nullptr;
     s.cand_bits = nullptr;
+    s.blut = nullptr;
     s.hvals = nullptr;
     s.on = nullptr;
     if (P.mode >= 1) {
@@ -195,7 +197,15 @@ __device__ __forceinline__ SearchSmem stage_codebook(unsigned char* smem, const 
         s.hkeys = reinterpret_cast<uint32_t*>(p);
         s.masks = s.hkeys + hs;
         s.cand_bits = s.masks + kpad;
-        s.hvals = reinterpret_cast<int16_t*>(s.cand_bits + SEARCH_THREADS * ((P.K + 31) / 32));
+        uint32_t* after_bits = s.cand_bits + SEARCH_THREADS * ((P.K + 31) / 32);
+        after_bits += (reinterpret_cast<uintptr_t>(after_bits) & 7u) ? 1 : 0;  // 8-byte alignment for the uint2 table
+        s.blut = reinterpret_cast<uint2*>(after_bits);
+        if (threadIdx.x < 16) {
+            const uint32_t i = threadIdx.x;  // bit0: k row 2t, bit1: 2t+1, bit2: 2t+8, bit3: 2t+9; 0x3F80 = bf16(1.0)
+            s.blut[i] = make_uint2(((i & 1u) ? 0x3F80u : 0u) | ((i & 2u) ? 0x3F800000u : 0u),
+                                   ((i & 4u) ? 0x3F80u : 0u) | ((i & 8u) ? 0x3F800000u : 0u));
+        }
+        s.hvals = reinterpret_cast<int16_t*>(s.blut + 16);
         for (int i = threadIdx.x; i < hs; i += SEARCH_THREADS) {
             s.hkeys[i] = P.hash_keys[i];
             s.hvals[i] = P.hash_vals[i];
@@ -402,15 +412,14 @@ __device__ __forceinline__ void mma_bf16_m16n8k16(float (&d)[4], const uint32_t 
 // codewords 8j+2t, 8j+2t+1; d2,d3 = row g+8
 template <int KS>
 __device__ __forceinline__ void onbit_sums_tile(const uint32_t (&ahi)[KS][4], const uint32_t (&alo)[KS][4], uint32_t m,
-                                                int t, float (&d)[4]) {
+                                                int t, const uint2* __restrict__ blut, float (&d)[4]) {
     d[0] = d[1] = d[2] = d[3] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
         const uint32_t mm = m >> (ks * 16 + 2 * t);  // B fragment: bits 2t, 2t+1, 2t+8, 2t+9 of this lane's codeword
-        const uint32_t b0 = ((mm & 1u) ? 0x3F80u : 0u) | ((mm & 2u) ? 0x3F800000u : 0u);
-        const uint32_t b1 = ((mm & 0x100u) ? 0x3F80u : 0u) | ((mm & 0x200u) ? 0x3F800000u : 0u);
-        mma_bf16_m16n8k16(d, ahi[ks], b0, b1);
-        mma_bf16_m16n8k16(d, alo[ks], b0, b1);
+        const uint2 b = blut[(mm & 3u) | ((mm >> 6) & 12u)];
+        mma_bf16_m16n8k16(d, ahi[ks], b.x, b.y);
+        mma_bf16_m16n8k16(d, alo[ks], b.x, b.y);
     }
 }
 
@@ -445,7 +454,7 @@ __device__ __forceinline__ void mma_mark_candidates_warp(const DecodeParams& P, 
         float rmax[2] = {-inf, -inf};
         for (int j = 0; j < n_tiles; ++j) {
             float d[4];
-            onbit_sums_tile<KS>(ahi, alo, S.masks[8 * j + g], t, d);
+            onbit_sums_tile<KS>(ahi, alo, S.masks[8 * j + g], t, S.blut, d);
             const int k0 = 8 * j + 2 * t;
             if (k0 < P.K) {
                 rmax[0] = fmaxf(rmax[0], d[0]);
@@ -467,7 +476,7 @@ __device__ __forceinline__ void mma_mark_candidates_warp(const DecodeParams& P, 
         uint32_t* bits1 = bits0 + 8 * n_words;
         for (int j = 0; j < n_tiles; ++j) {
             float d[4];
-            onbit_sums_tile<KS>(ahi, alo, S.masks[8 * j + g], t, d);
+            onbit_sums_tile<KS>(ahi, alo, S.masks[8 * j + g], t, S.blut, d);
             const int k0 = 8 * j + 2 * t;  // k0 and k0+1 share a word (k0 is even)
             uint32_t m0 = 0u, m1 = 0u;
             if (k0 < P.K) {
