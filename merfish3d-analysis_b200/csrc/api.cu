@@ -279,6 +279,7 @@ extern "C" int64_t m3d_launch_count(m3d_ctx* ctx) {
 
 extern "C" const char* m3d_kernel_name(int i) { return (i >= 0 && i < KF_COUNT) ? kKernelNames[i] : nullptr; }
 static void resolve_spans(m3d_ctx* ctx) {
+    std::lock_guard<std::mutex> lk(ctx->span_mu);
     for (auto& sp : ctx->spans) {
         cudaEventSynchronize(sp.b);
         float ms = 0.f;

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -172,6 +173,7 @@ struct m3d_ctx {
     int timing = 0;
     struct TimedSpan { int k; cudaEvent_t a, b; };
     std::vector<TimedSpan> spans;
+    std::mutex span_mu;  // launches may come from the prefetch thread as well
     double time_ms[KF_COUNT];
     DecodeParams params() const;
     GateParams gate_params() const;
@@ -185,7 +187,7 @@ struct KernelScope {
     cudaEvent_t a = nullptr, b = nullptr;
     int k;
     KernelScope(m3d_ctx* c, M3dKernel kf, cudaStream_t s, int64_t n = 1) : ctx(c), st(s), k((int)kf) {
-        ctx->launches[k] += n;
+        __atomic_fetch_add(&ctx->launches[k], n, __ATOMIC_RELAXED);  // the prefetch thread launches too
         if (ctx->timing) {
             cudaEventCreate(&a);
             cudaEventCreate(&b);
@@ -195,6 +197,7 @@ struct KernelScope {
     ~KernelScope() {
         if (a) {
             cudaEventRecord(b, st);
+            std::lock_guard<std::mutex> lk(ctx->span_mu);
             ctx->spans.push_back({k, a, b});
         }
     }
