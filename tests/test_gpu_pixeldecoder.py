@@ -304,3 +304,27 @@ def test_multi_tile_pipeline_with_staged_pageable_uploads(tmp_path):
     for t in range(3):
         got = ds.load_local_decoded_spots(t)
         pd.testing.assert_frame_equal(got.reset_index(drop=True), single[t].reset_index(drop=True), check_dtype=False)
+
+
+def test_decode_all_tiles_without_any_transcript(tmp_path):
+    """Background-only tiles: every stage must pass empty tables through (per-tile parquet, filter, overlap
+    de-duplication, filtered table) without raising, and the optimiser keeps the rounded global vectors."""
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    df_cb, _cb = cases.codebook16()
+    rng = np.random.default_rng(2)
+    stacks = [(rng.poisson(100, (16, 6, 32, 40)) + 100).astype(np.uint16) for _ in range(2)]
+    ds = _store(tmp_path, df_cb, stacks)
+    bkg, nrm = cases.simple_vectors(16)
+    ds.save_decode_normalization_vectors(None, "global", nrm, bkg)
+    dec = PixelDecoder(ds, merfish_bits=16, verbose=0)
+    dec.decode_all_tiles(assign_to_cells=True, lowpass_sigma=None, normalization_method="global")
+    for t in range(2):
+        got = ds.load_local_decoded_spots(t)
+        assert got is not None and len(got) == 0 and "gene_id" in got.columns
+    out = ds.load_global_filtered_decoded_spots()
+    assert out is not None and len(out) == 0
+    dec.optimize_normalization_by_decoding(n_iterations=2, lowpass_sigma=None, tile_indices=[0, 1])
+    i_n, i_b = ds.load_decode_normalization_vectors(None, "iterative")
+    g_n, g_b = ds.load_decode_normalization_vectors(None, "global")
+    assert np.all(np.isfinite(i_n)) and np.all(np.isfinite(i_b)) and i_n.shape == (16,)
