@@ -42,9 +42,10 @@ SEED = 2002
 MAG = (1.5, 10.0)
 MIN_PX = 16.0
 BKG, NRM = 200.0, 900.0
-# algorithmic bytes per voxel of the dominant (gate) kernel:
-# reads bits x 2 B of uint16 input, writes the 2 B int16 decoded image.
-GATE_BYTES_PER_VOXEL = N_BITS * 2 + 2
+# algorithmic bytes per voxel of the dominant (gate) kernel: it reads bits x 2 B of uint16 input.
+# The 2 B/voxel dense "decoded = -1" fill of SURVEY's 34 B figure is not part of the steady-state step any more: the
+# decoded image is persistent and only the previous tile's foreground voxels are reset (m3d_decode_label_persistent).
+GATE_BYTES_PER_VOXEL = N_BITS * 2
 CPU_SAMPLE_SHAPE = (8, 256, 256)
 
 
@@ -295,7 +296,8 @@ def run_b200(args):
     decoded = torch.empty(shape, dtype=torch.int16, device=dev)
 
     def step_resident():
-        n = ctx.decode_label(stack, decoded, False, MIN_PX, 500)
+        # `decoded` is the persistent per-GPU image of the production path (PixelDecoder._decode_pixels)
+        n = ctx.decode_label(stack, decoded, False, MIN_PX, 500, persistent=True)
         table = ctx.features(stack, decoded, False, n)
         return n, table
 

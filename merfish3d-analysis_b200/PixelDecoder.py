@@ -863,7 +863,11 @@ class PixelDecoder:
         ctx.set_normalization(bkg, nrm)
         ctx.set_thresholds(self._pixel_assignment_threshold, magnitude_threshold[0], magnitude_threshold[1])
         shape = tuple(stack.shape[1:])
-        st["decoded"] = torch.empty(shape, dtype=torch.int16, device=ctx.device)
+        # the decoded image lives in one persistent buffer per GPU: between two production decodes only the
+        # previous tile's foreground voxels have to go back to -1 (m3d_decode_label_persistent)
+        had = self._buffers.get((gpu_id, "dec"), {}).get("decoded")
+        st["decoded"] = self._tile_buffer(gpu_id, "dec", "decoded", shape, torch.int16, ctx.device)
+        fresh = had is None or had.data_ptr() != st["decoded"].data_ptr()
         mag = dist = scaled = None
         if materialize_images:
             mag = torch.empty(shape, dtype=torch.float16, device=ctx.device)
@@ -880,7 +884,7 @@ class PixelDecoder:
             if self._wants_chromatic_centroids():
                 st["labels"] = torch.empty(shape, dtype=torch.int32, device=ctx.device)
             st["n_features"] = ctx.decode_label(stack, st["decoded"], not self._is_3D, float(min_px), int(max_px),
-                                                labels=st["labels"])
+                                                labels=st["labels"], persistent=not fresh)
 
     @staticmethod
     def _warp_pixel(pixel_space_point, spacing, origin, affine, camera_to_stage_affine=None):

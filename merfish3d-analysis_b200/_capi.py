@@ -75,6 +75,11 @@ SIGNATURES = {
         [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_int, C.c_double,
          C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p],
     ),
+    "m3d_decode_label_persistent": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_int, C.c_double,
+         C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p],
+    ),
     "m3d_interface_pairs": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
@@ -401,13 +406,15 @@ class DecodeContext:
         return self._n_features
 
     def decode_label(self, stack, decoded, mode2d: bool, minimum_pixels: float,
-                     maximum_pixels: int = 500, labels=None) -> int:
-        """Fused production path: decode (no result images) + connected components."""
+                     maximum_pixels: int = 500, labels=None, persistent: bool = False) -> int:
+        """Fused production path: decode (no result images) + connected components.  ``persistent``: ``decoded``
+        is a buffer kept across calls and untouched in between (see m3d_decode_label_persistent)."""
         if stack.dim() != 4 or stack.shape[0] != self.n_bits:
             raise ValueError(f"stack must be ({self.n_bits}, z, y, x)")
         n = C.c_int64(-1)
+        fn = self._lib.m3d_decode_label_persistent if persistent else self._lib.m3d_decode_label
         _check(
-            self._lib.m3d_decode_label(
+            fn(
                 self._h, _ptr(stack), _dtype_code(stack), self._dims(stack.shape[1:]), _ptr(decoded),
                 1 if mode2d else 0, float(minimum_pixels), int(maximum_pixels), _ptr(labels),
                 C.byref(n), _stream(self.device),

@@ -57,6 +57,7 @@ enum M3dKernel {
     KF_CENTROID,
     KF_EIGVALS,
     KF_TABLE_CELLS,
+    KF_RESET_FG,
     KF_COUNT
 };
 
@@ -166,6 +167,12 @@ struct m3d_ctx {
     int lab_max_px = 0;
     int lab_rec_valid = 0;
     size_t sparse_cap_override = 0;  // m3d_set_sparse_capacity (tests); 0 = automatic  // records of the last m3d_decode_label cover every foreground voxel
+    // persistent decoded image (m3d_decode_label_persistent): the previous call's foreground list is still in
+    // s_fg, so the next call resets those voxels instead of re-filling the whole image with -1
+    const void* prev_decoded = nullptr;
+    size_t prev_n_vox = 0;
+    int prev_fg_valid = 0;
+    int gate_skip_background = 0;  // set around the gate launch only
     // accounting
     int64_t launches[KF_COUNT];
     // optional per-kernel-family device timing (m3d_set_timing): event pairs recorded on the

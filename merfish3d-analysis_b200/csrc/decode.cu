@@ -99,7 +99,7 @@ template <typename T, int NB, int VPT>
 __global__ void __launch_bounds__(GATE_THREADS)
 decode_gate_kernel(const T* __restrict__ stack, size_t n_vox, size_t n_units, GateParams G,
                    int16_t* __restrict__ decoded, uint32_t* __restrict__ cand,
-                   unsigned int* __restrict__ cand_count) {
+                   unsigned int* __restrict__ cand_count, int write_background) {
     using V = typename Vec<T, VPT>::type;
     const size_t unit = (size_t)blockIdx.x * GATE_THREADS + threadIdx.x;
     const bool active = unit < n_units;
@@ -123,7 +123,7 @@ decode_gate_kernel(const T* __restrict__ stack, size_t n_vox, size_t n_units, Ga
             acc[j] = __fmaf_rn(q, q, acc[j]);
         }
     }
-    if (active) store_background<VPT>(decoded + v0);
+    if (active && write_background) store_background<VPT>(decoded + v0);  // skipped when the image is already clean
     unsigned bits = 0;
 #pragma unroll
     for (int j = 0; j < VPT; ++j) {
@@ -689,8 +689,8 @@ int launch_gate(m3d_ctx* ctx, const T* stack, size_t n_vox, int16_t* decoded, ui
     const size_t blocks = (n_units + GATE_THREADS - 1) / GATE_THREADS;
     if (blocks > 0x7fffffffull) return m3d_fail(M3D_ERR_ARG, "m3d_decode: grid too large");
     M3D_LAUNCH(ctx, KF_DECODE_GATE, st,
-               decode_gate_kernel<T, NB, VPT><<<(unsigned)blocks, GATE_THREADS, 0, st>>>(stack, n_vox, n_units, G,
-                                                                                            decoded, cand, cand_count));
+               decode_gate_kernel<T, NB, VPT><<<(unsigned)blocks, GATE_THREADS, 0, st>>>(
+                   stack, n_vox, n_units, G, decoded, cand, cand_count, ctx->gate_skip_background ? 0 : 1));
     M3D_CHECK_LAUNCH();
     return M3D_OK;
 }
@@ -798,6 +798,7 @@ extern "C" int m3d_decode(m3d_ctx* ctx, const void* stack_dev, int dtype, const 
     size_t n_vox = 0;
     int rc = m3d_check_decode_args(ctx, stack_dev, dtype, dims, decoded_dev, &n_vox);
     if (rc) return rc;
+    ctx->prev_fg_valid = 0;  // this call may rewrite a persistent decoded image without leaving a foreground list
     M3D_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     __half* mag = reinterpret_cast<__half*>(magnitude_f16_dev);

@@ -21,6 +21,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
+
 #include "voxel_math.cuh"
 
 namespace {
@@ -571,6 +573,12 @@ int m3d_decode_internal(m3d_ctx* ctx, const void* stack_dev, int dtype, size_t n
 
 namespace {
 
+// persistent decoded image: put the previous tile's foreground voxels back to background (-1)
+__global__ void __launch_bounds__(256)
+reset_foreground_kernel(const uint32_t* __restrict__ fg, unsigned n, int16_t* __restrict__ decoded) {
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) decoded[fg[i]] = (int16_t)-1;
+}
+
 struct LabelScratch {
     unsigned int* counters;
     uint32_t *fg, *root_of, *parent, *aux;
@@ -681,6 +689,7 @@ extern "C" int m3d_label(m3d_ctx* ctx, const int16_t* decoded_dev, const int64_t
                          double minimum_pixels, int maximum_pixels, int32_t* labels_dev,
                          int64_t* n_features_out, void* stream) {
     if (!ctx || !decoded_dev || !dims || !n_features_out) return m3d_fail(M3D_ERR_ARG, "m3d_label: null argument");
+    ctx->prev_fg_valid = 0;  // the foreground list is rebuilt from another image
     M3D_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     size_t n_vox = 0;
@@ -700,32 +709,63 @@ extern "C" int m3d_label(m3d_ctx* ctx, const int16_t* decoded_dev, const int64_t
                         n_features_out, L, st);
 }
 
-extern "C" int m3d_decode_label(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t dims[3],
-                                int16_t* decoded_dev, int mode2d, double minimum_pixels, int maximum_pixels,
-                                int32_t* labels_dev, int64_t* n_features_out, void* stream) {
+static int decode_label_impl(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t dims[3],
+                             int16_t* decoded_dev, int mode2d, double minimum_pixels, int maximum_pixels,
+                             int32_t* labels_dev, int64_t* n_features_out, int persistent, void* stream) {
     if (!n_features_out) return m3d_fail(M3D_ERR_ARG, "m3d_decode_label: null argument");
     size_t n_vox = 0;
     int rc = m3d_check_decode_args(ctx, stack_dev, dtype, dims, decoded_dev, &n_vox);
     if (rc) return rc;
     M3D_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // the caller vouches that decoded_dev still holds exactly what the previous persistent call left there
+    const bool reuse = persistent && ctx->prev_fg_valid && ctx->prev_decoded == (const void*)decoded_dev &&
+                       ctx->prev_n_vox == n_vox && ctx->s_fg.ptr != nullptr;
+    const unsigned prev_fg = reuse ? (unsigned)ctx->lab_n_fg : 0u;
+    ctx->prev_fg_valid = 0;
     LabelScratch L;
     rc = label_prepare(ctx, dims, maximum_pixels, labels_dev, &n_vox, &L, st);
     if (rc) return rc;
+    if (reuse && prev_fg) {
+        const int blocks = (int)std::min<size_t>((prev_fg + 255u) / 256u, (size_t)ctx->num_sms * 8);
+        M3D_LAUNCH(ctx, KF_RESET_FG, st, reset_foreground_kernel<<<blocks, 256, 0, st>>>(L.fg, prev_fg, decoded_dev));
+        M3D_CHECK_LAUNCH();
+    }
     // the search kernel emits the foreground list and initialises the union-find slots: no
     // second pass over the decoded image
     const size_t rec_cap = m3d_sparse_capacity(ctx, n_vox);
     if (ctx->s_rec_x.ensure(rec_cap * (size_t)ctx->nb_pad * 2)) return M3D_ERR_CUDA;
     if (ctx->s_rec_md.ensure(rec_cap * sizeof(uint32_t))) return M3D_ERR_CUDA;
+    ctx->gate_skip_background = reuse ? 1 : 0;
     rc = m3d_decode_internal(ctx, stack_dev, dtype, n_vox, decoded_dev, L.fg, L.counters + CNT_FG, L.parent, L.aux,
                              ctx->s_rec_x.ptr, reinterpret_cast<uint32_t*>(ctx->s_rec_md.ptr), (unsigned)rec_cap, st);
+    ctx->gate_skip_background = 0;
     if (rc) return rc;
     rc = label_finish(ctx, decoded_dev, dims, n_vox, mode2d, minimum_pixels, maximum_pixels, labels_dev,
                       n_features_out, L, st);
     if (rc) return rc;
     // the regionprops stage may read the search kernel's records instead of recomputing traces
     ctx->lab_rec_valid = ((size_t)ctx->lab_n_fg <= rec_cap) ? 1 : 0;
+    if (persistent) {
+        ctx->prev_decoded = decoded_dev;
+        ctx->prev_n_vox = n_vox;
+        ctx->prev_fg_valid = 1;
+    }
     return M3D_OK;
+}
+
+extern "C" int m3d_decode_label(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t dims[3],
+                                int16_t* decoded_dev, int mode2d, double minimum_pixels, int maximum_pixels,
+                                int32_t* labels_dev, int64_t* n_features_out, void* stream) {
+    return decode_label_impl(ctx, stack_dev, dtype, dims, decoded_dev, mode2d, minimum_pixels, maximum_pixels, labels_dev,
+                             n_features_out, 0, stream);
+}
+
+extern "C" int m3d_decode_label_persistent(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t dims[3],
+                                           int16_t* decoded_dev, int mode2d, double minimum_pixels, int maximum_pixels,
+                                           int32_t* labels_dev, int64_t* n_features_out, void* stream) {
+    return decode_label_impl(ctx, stack_dev, dtype, dims, decoded_dev, mode2d, minimum_pixels, maximum_pixels, labels_dev,
+                             n_features_out, 1, stream);
 }
 
 extern "C" int m3d_features(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t dims[3],

@@ -502,3 +502,36 @@ def test_staged_upload_is_byte_identical():
     with pytest.raises(M3dError):
         ctx.upload([(vol[0], stack[0])])  # size mismatch
     ctx.close()
+
+
+def test_persistent_decoded_image_equals_fresh_fill(torch):
+    """m3d_decode_label_persistent: the decoded image kept across calls (previous foreground reset, dense -1 fill
+    skipped) must equal a fresh m3d_decode_label for every tile of a sequence, also after calls that invalidate
+    the remembered foreground list (m3d_decode, m3d_label) and after the caller scribbles over the buffer and
+    says so by making one non-persistent call."""
+    _df, cb = cases.codebook16()
+    ctx, _ = _ctx(cb)
+    bkg, nrm = cases.simple_vectors(16)
+    ctx.set_normalization(bkg, nrm)
+    ctx.set_thresholds(cb["pixel_assignment_threshold"], 1.5, 10.0)
+    shape = (10, 40, 64)
+    stacks = [torch.from_numpy(cases.small_stack(cb["matrix"], shape=shape, seed=700 + i, density=4e-3)).cuda()
+              for i in range(5)]
+    keep = torch.empty(shape, dtype=torch.int16, device="cuda")
+    for i, st in enumerate(stacks + stacks[::-1]):
+        fresh = torch.empty(shape, dtype=torch.int16, device="cuda")
+        n_ref = ctx.decode_label(st, fresh, False, 4.0, 500)
+        t_ref = ctx.features(st, fresh, False, n_ref)
+        if i == 3:
+            ctx.decode(st, keep)  # dense rewrite of the kept buffer: must invalidate the remembered list
+        if i == 5:
+            ctx.label(fresh, False, 4.0, 500)  # rebuilds the foreground list from another image
+        if i == 7:
+            keep.fill_(5)  # caller wrote to the buffer -> one non-persistent call re-establishes it
+            ctx.decode_label(st, keep, False, 4.0, 500)
+        n = ctx.decode_label(st, keep, False, 4.0, 500, persistent=True)
+        tab = ctx.features(st, keep, False, n)
+        assert n == n_ref and n > 10
+        assert torch.equal(keep, fresh), i
+        assert torch.equal(tab, t_ref), i
+    ctx.close()
