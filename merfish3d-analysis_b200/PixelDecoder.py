@@ -919,7 +919,8 @@ class PixelDecoder:
         if chroma and n > 0:
             centroid_stats = self._chromatic_centroid_statistics(ctx, st["stack"], labels, table)
         eigvals = ctx.inertia_eigvals(table).cpu().numpy() if n > 0 else None
-        tab = table.cpu().numpy()
+        # column-major on the host: the annotation works column by column (transposed on the device, a view here)
+        tab = table.t().contiguous().cpu().numpy().T
         self._df_barcodes = self._annotate_table(tab, centroid_stats, eigvals)
 
     def _wants_chromatic_centroids(self) -> bool:
@@ -974,12 +975,13 @@ class PixelDecoder:
         if tab.shape[0] == 0:
             return pd.DataFrame({c: [] for c in cols})
         dec = tab[:, _COL_DEC].astype(np.int32)
-        if centroid_stats is not None:
-            centroid_stats = tuple(a[dec >= 0] for a in centroid_stats)
-        if eigvals is not None:
-            eigvals = eigvals[dec >= 0]
-        tab = tab[dec >= 0]
-        dec = dec[dec >= 0]
+        if not (dec >= 0).all():  # components of decoded voxels always carry a codeword; kept for foreign tables
+            if centroid_stats is not None:
+                centroid_stats = tuple(a[dec >= 0] for a in centroid_stats)
+            if eigvals is not None:
+                eigvals = eigvals[dec >= 0]
+            tab = tab[dec >= 0]
+            dec = dec[dec >= 0]
         # columns are assembled as plain arrays and the frame is built once (a per-column
         # DataFrame insert costs ~0.5 ms; the table has 40+ columns)
         col: dict[str, np.ndarray] = {"area": tab[:, _COL_AREA]}
