@@ -118,3 +118,47 @@ def test_histogram_edges_host_mirror_equals_oracle():
     np.testing.assert_array_equal(e2, tor.vector_distance_edges(flat))
     with pytest.raises(ValueError, match="at least two finite"):
         table_stage._edges(inten, area, dist, [1.0], None, None)
+
+
+def test_imagej_roi_round_trip_and_grid_index(tmp_path):
+    """ROI archive reader (published ImageJ layout) and the host grid index behind m3d_assign_cells: every
+    (point, containing polygon) pair of the oracle must be reachable through the point's grid cell."""
+    import zipfile
+
+    from merfish3d_analysis_b200 import roi, table_stage
+
+    rng = np.random.default_rng(4)
+    polys_xy = []
+    for i in range(60):
+        cy, cx = rng.uniform(0, 300, 2)
+        ang = np.sort(rng.uniform(0, 2 * np.pi, rng.integers(3, 30)))
+        rad = rng.uniform(3, 25, ang.size)
+        polys_xy.append(np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], axis=1))
+    path = tmp_path / "rois.zip"
+    roi.write_roi_zip(path, polys_xy)
+    with zipfile.ZipFile(path, "a") as zf:
+        zf.writestr("junk.roi", b"not an roi")
+        zf.writestr("readme.txt", b"ignored")
+    back = roi.read_roi_zip(path)
+    assert len(back) == 61 and back[-1] is None
+    for a, b in zip(polys_xy, back):
+        np.testing.assert_allclose(b, a.astype(np.float32).astype(np.float64), rtol=0, atol=0)
+    # integer-only ROI (no sub-pixel block): vertices = int16 offsets + bounding-box corner
+    raw = bytearray(roi.encode_polygon_roi(np.array([[10.0, 20.0], [40.0, 20.0], [40.0, 60.0]])))
+    raw[50:52] = (0).to_bytes(2, "big")
+    np.testing.assert_array_equal(roi.parse_roi(bytes(raw[: 64 + 4 * 3])), [[10, 20], [40, 20], [40, 60]])
+    polys_yx = [p[:, ::-1] for p in back if p is not None]
+    pts = np.round(rng.uniform(-20, 340, (4000, 2)), 2)
+    want = tor.assign_cells(pts, polys_yx)
+    g = table_stage.polygon_grid(polys_yx)
+    gy, gx = g["grid"]
+    cy = np.floor((pts[:, 0] - g["origin"][0]) / g["cell"]).astype(int)
+    cx = np.floor((pts[:, 1] - g["origin"][1]) / g["cell"]).astype(int)
+    hits = 0
+    for i in np.flatnonzero(want > 0):
+        assert 0 <= cy[i] < gy and 0 <= cx[i] < gx
+        c = cy[i] * gx + cx[i]
+        cand = g["cell_polys"][g["cell_start"][c] : g["cell_start"][c + 1]]
+        assert want[i] - 1 in cand and np.all(np.diff(cand) > 0)  # reachable, candidates ascending
+        hits += 1
+    assert hits > 300
