@@ -56,6 +56,20 @@ def test_fullsize_fused_path_properties(big):
     n2 = ctx.decode_label(stack, decoded2, False, 16.0, 500)
     table2 = ctx.features(stack, decoded2, False, n2)
     assert n2 == n and torch.equal(decoded, decoded2) and torch.equal(table, table2)
+    # persistent decoded image (previous foreground reset instead of the dense -1 fill): alternate two
+    # normalisation settings with different foreground sets on ONE kept buffer; every result must equal a
+    # fresh decode under the same setting
+    keep = torch.empty_like(decoded)
+    for rep, nrm_v in enumerate((900.0, 600.0, 900.0, 600.0)):
+        ctx.set_normalization(np.full(16, 200.0, np.float32), np.full(16, nrm_v, np.float32))
+        nk = ctx.decode_label(stack, keep, False, 16.0, 500, persistent=True)
+        if nrm_v == 900.0:
+            assert nk == n and torch.equal(keep, decoded), rep
+        else:
+            nf = ctx.decode_label(stack, decoded2, False, 16.0, 500)
+            assert nk == nf and nk != n and torch.equal(keep, decoded2), rep
+    ctx.set_normalization(np.full(16, 200.0, np.float32), np.full(16, 900.0, np.float32))
+    del keep
     # fused production path == dense reference-complete kernel on a random sample of 2^20 voxels
     # (all decoded voxels of 64 random planes' rows would bias; take uniform voxels + all foreground of one plane)
     g = torch.Generator(device="cuda")
