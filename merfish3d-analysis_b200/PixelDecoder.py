@@ -1034,7 +1034,7 @@ class PixelDecoder:
         keep = col["distance_min"] <= self._transcript_distance_threshold
         if not keep.all():
             col = {k: v[keep] for k, v in col.items()}
-        return pd.DataFrame({c: col[c] for c in cols})
+        return pd.DataFrame({c: col[c] for c in cols}, copy=False)  # one block per column, no consolidation copy
 
     def _on_bit_centroid_columns(self, tab: np.ndarray, on_sel: np.ndarray, centroid_stats) -> dict:
         """PD:2728-2831: sparse per-bit ``center_{z,y,x}``, ``intensity_sum``, ``intensity_peak`` and
