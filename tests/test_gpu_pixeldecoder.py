@@ -328,3 +328,32 @@ def test_decode_all_tiles_without_any_transcript(tmp_path):
     i_n, i_b = ds.load_decode_normalization_vectors(None, "iterative")
     g_n, g_b = ds.load_decode_normalization_vectors(None, "global")
     assert np.all(np.isfinite(i_n)) and np.all(np.isfinite(i_b)) and i_n.shape == (16,)
+
+
+def test_local_multi_gpu_threads_equal_single_gpu(tmp_path):
+    """``num_gpus=2`` without torch.distributed: one host thread and one decoder clone per local GPU,
+    contiguous tile chunks like PD:4811-4838.  Same per-tile tables and filtered table as one GPU."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from merfish3d_analysis_b200.datastore import ArrayDataStore
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    df_cb, cb = cases.codebook16()
+    stacks = [cases.small_stack(cb["matrix"], shape=(9, 40, 56), seed=600 + i, density=5e-3) for i in range(5)]
+    bkg, nrm = cases.simple_vectors(16)
+    outs = []
+    for n_gpus in (1, 2):
+        ds = ArrayDataStore(tmp_path / f"store{n_gpus}", codebook=df_cb)
+        for st in stacks:
+            ds.add_tile(st)
+        ds.save_decode_normalization_vectors(None, "global", nrm, bkg)
+        dec = PixelDecoder(ds, merfish_bits=16, num_gpus=n_gpus, verbose=0)
+        dec.decode_all_tiles(assign_to_cells=False, lowpass_sigma=(3.0, 1.0, 1.0), minimum_pixels=4,
+                             normalization_method="global")
+        outs.append(([ds.load_local_decoded_spots(t) for t in range(5)], ds.load_global_filtered_decoded_spots()))
+    for a, b in zip(outs[0][0], outs[1][0]):
+        pd.testing.assert_frame_equal(a, b)
+    pd.testing.assert_frame_equal(outs[0][1], outs[1][1])
+    assert sum(len(a) for a in outs[0][0]) > 30
