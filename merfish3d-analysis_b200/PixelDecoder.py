@@ -36,6 +36,7 @@ import pandas as pd
 
 from . import normalization as _norm
 from . import table_stage
+from . import zarr_store as _zs
 from ._capi import M3D_TABLE_FIXED_COLS, DecodeContext, M3dError
 
 DEFAULT_DECODE_LOWPASS_SIGMA = (3.0, 1.0, 1.0)  # PD:128
@@ -493,6 +494,12 @@ class PixelDecoder:
         return ctx.warp_affine(r, warp[0], warp[1], predictor=p, out_z0=out_z0, out_nz=out_nz, out=out)
 
     @staticmethod
+    def _image_dtype(image) -> np.dtype:
+        """dtype of a loader's return value without materialising a lazy store image."""
+        dt = getattr(image, "dtype", None)
+        return np.dtype(dt) if dt is not None else np.asarray(image).dtype
+
+    @staticmethod
     def _is_unit_predictor(predictor) -> bool:
         return predictor is None or type(predictor).__name__ == "UnitPredictor"
 
@@ -502,13 +509,13 @@ class PixelDecoder:
         import torch
 
         def to_dev(arr, dtype):
-            src = np.ascontiguousarray(arr, dtype=dtype)
-            dst = torch.empty(src.shape, dtype=torch.float32 if dtype == np.float32 else torch.uint16,
+            src = _zs.host_piece(arr, 0, int(arr.shape[0]), dtype)  # lazy store images decode straight to HBM
+            dst = torch.empty(tuple(src.shape), dtype=torch.float32 if dtype == np.float32 else torch.uint16,
                               device=ctx.device)
-            ctx.upload([(src, dst)])
+            _zs.transfer(ctx, [(src, dst)])
             return dst
 
-        is_float = np.asarray(readout).dtype.kind == "f"
+        is_float = self._image_dtype(readout).kind == "f"
         r = to_dev(readout, np.float32 if is_float else np.uint16)
         p = None if self._is_unit_predictor(predictor) else to_dev(predictor, np.float32)
         if warp is not None:
@@ -662,7 +669,7 @@ class PixelDecoder:
             raise ValueError("decode_mode='3d' requires at least two z planes after applying z_range.")
         a, b = (zs, ze) if z_bounds is None else (zs + int(z_bounds[0]), zs + int(z_bounds[1]))
         shape = (b - a, *loaded[0][0].shape[1:])
-        float_input = any(np.asarray(r).dtype.kind == "f" for r, _p, _w in loaded)
+        float_input = any(self._image_dtype(r).kind == "f" for r, _p, _w in loaded)
         npdt = np.float32 if float_input else np.uint16
         st = {}
 
@@ -675,7 +682,7 @@ class PixelDecoder:
             if z_bounds is not None:
                 slot = None
             n_b = len(bit_ids)
-            native = tuple(int(v) for v in np.asarray(loaded[0][0]).shape)
+            native = tuple(int(v) for v in loaded[0][0].shape)
             dt = torch.float32 if float_input else torch.uint16
             raw = self._tile_buffer(gpu_id, slot, "native", (n_b, *native), dt, ctx.device, alloc_stream)
             rawp = None
@@ -693,10 +700,10 @@ class PixelDecoder:
                     ctx.upload([(warp["flow"], warp["flow_dev"])])
             pieces, piece_bit = [], []
             for i, (ra, pa, _w) in enumerate(loaded):
-                pieces.append((np.ascontiguousarray(ra, dtype=npdt), raw[i]))
+                pieces.append((_zs.host_piece(ra, 0, native[0], npdt), raw[i]))
                 piece_bit.append(i)
                 if pa is not None:
-                    pieces.append((np.ascontiguousarray(pa, dtype=np.float32), rawp[i]))
+                    pieces.append((_zs.host_piece(pa, 0, native[0], np.float32), rawp[i]))
                     piece_bit.append(i)
 
             def bit_ready(i):
@@ -730,16 +737,16 @@ class PixelDecoder:
                 pred = self._tile_buffer(gpu_id, slot, "pred", full, torch.float32, ctx.device, alloc_stream)
             pieces, piece_bit = [], []  # per bit: readout, then its predictor weights (if stored)
             for i, (ra, pa, _w) in enumerate(loaded):
-                pieces.append((np.ascontiguousarray(ra[a:b], dtype=npdt), stack[i]))
+                pieces.append((_zs.host_piece(ra, a, b, npdt), stack[i]))
                 piece_bit.append(i)
                 if pred is not None:
                     if pa is None:
                         pred[i].fill_(1.0)
                     else:
-                        pieces.append((np.ascontiguousarray(pa[a:b], dtype=np.float32), pred[i]))
+                        pieces.append((_zs.host_piece(pa, a, b, np.float32), pred[i]))
                         piece_bit.append(i)
             if lowpass_sigma is None:
-                ctx.upload(pieces)
+                _zs.transfer(ctx, pieces)
                 st["readout"], st["predictor"] = stack, pred
             else:
                 st["readout"], st["predictor"] = None, None
@@ -777,7 +784,7 @@ class PixelDecoder:
 
         copy.wait_stream(compute)  # buffers just allocated / filled on the compute stream
         with torch.cuda.stream(copy):
-            ctx.upload(pieces, on_piece=piece_arrived)
+            _zs.transfer(ctx, pieces, on_piece=piece_arrived)
 
     def _upload_and_lowpass(self, ctx, pieces, piece_bit, stack, pred, sigma, out):
         """Registered tiles with the low-pass on: the per-bit Gaussian (PD:1982-2024) of bit b runs on the

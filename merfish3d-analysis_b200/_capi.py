@@ -43,6 +43,19 @@ SIGNATURES = {
         [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p,
          C.c_void_p, C.c_void_p],
     ),
+    "m3d_zarr_read_chunks": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "m3d_zarr_read_chunks_host": (C.c_int, [C.c_int, C.c_void_p]),
+    "m3d_blosc_info": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "m3d_blosc_decode_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+    "m3d_blosc_encode_bound": (C.c_int64, [C.c_int64, C.c_int64]),
+    "m3d_blosc_encode_host": (
+        C.c_int,
+        [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64,
+         C.POINTER(C.c_int64)],
+    ),
+    "m3d_zstd_host": (
+        C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int64)]
+    ),
     "m3d_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "m3d_warp_affine": (
         C.c_int,
@@ -133,6 +146,91 @@ SIGNATURES = {
 }
 
 _PIECE_CB = C.CFUNCTYPE(None, C.c_int, C.c_void_p)
+
+M3D_ZARR_RAW, M3D_ZARR_BLOSC, M3D_ZARR_ZSTD, M3D_ZARR_ABSENT = 0, 1, 2, 3
+
+
+class ZarrChunk(C.Structure):
+    """``m3d_zarr_chunk`` (include/m3d_b200.h)."""
+
+    _fields_ = [
+        ("path", C.c_char_p),
+        ("offset", C.c_int64),
+        ("length", C.c_int64),
+        ("codec", C.c_int32),
+        ("elem_size", C.c_int32),
+        ("chunk_shape", C.c_int64 * 3),
+        ("origin", C.c_int64 * 3),
+        ("dst", C.c_void_p),
+        ("dst_shape", C.c_int64 * 3),
+        ("fill_bits", C.c_uint64),
+        ("piece", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+def zarr_chunk_array(chunks):
+    """ctypes array of ``m3d_zarr_chunk`` from dicts with the struct's field names."""
+    arr = (ZarrChunk * len(chunks))()
+    for rec, c in zip(arr, chunks):
+        rec.path = c["path"].encode() if isinstance(c["path"], str) else c["path"]
+        rec.offset, rec.length = int(c.get("offset", 0)), int(c.get("length", -1))
+        rec.codec, rec.elem_size = int(c["codec"]), int(c["elem_size"])
+        rec.chunk_shape = _c_i64_3(*[int(v) for v in c["chunk_shape"]])
+        rec.origin = _c_i64_3(*[int(v) for v in c["origin"]])
+        rec.dst = int(c["dst"])
+        rec.dst_shape = _c_i64_3(*[int(v) for v in c["dst_shape"]])
+        rec.fill_bits = int(c.get("fill_bits", 0))
+        rec.piece = int(c.get("piece", 0))
+    return arr
+
+
+def zarr_read_chunks_host(chunks) -> None:
+    """Decode chunks into HOST destinations (``dst`` = host addresses); needs no GPU."""
+    if not chunks:
+        return
+    arr = zarr_chunk_array(chunks)
+    _check(load_library().m3d_zarr_read_chunks_host(len(chunks), C.cast(arr, C.c_void_p)), "m3d_zarr_read_chunks_host")
+
+
+def blosc_info(frame: bytes) -> dict:
+    out = (C.c_int64 * 6)()
+    buf = np.frombuffer(frame, dtype=np.uint8)
+    _check(load_library().m3d_blosc_info(buf.ctypes.data, buf.size, out), "m3d_blosc_info")
+    return dict(zip(("nbytes", "blocksize", "cbytes", "typesize", "flags", "codec"), [int(v) for v in out]))
+
+
+def blosc_decode_host(frame: bytes) -> bytes:
+    info = blosc_info(frame)
+    buf = np.frombuffer(frame, dtype=np.uint8)
+    out = np.empty(max(info["nbytes"], 1), dtype=np.uint8)
+    _check(load_library().m3d_blosc_decode_host(buf.ctypes.data, buf.size, out.ctypes.data, out.size),
+           "m3d_blosc_decode_host")
+    return out[: info["nbytes"]].tobytes()
+
+
+def blosc_encode_host(data, typesize: int, cname: str = "zstd", clevel: int = 5, shuffle: str = "bitshuffle",
+                      blocksize: int = 0) -> bytes:
+    lib = load_library()
+    src = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data.reshape(-1).view(np.uint8)
+    src = np.ascontiguousarray(src)
+    cap = int(lib.m3d_blosc_encode_bound(src.size, blocksize))
+    out = np.empty(cap, dtype=np.uint8)
+    n = C.c_int64(0)
+    _check(lib.m3d_blosc_encode_host(src.ctypes.data, src.size, int(typesize), {"zstd": 4, "lz4": 1}[cname], int(clevel),
+                                     {"noshuffle": 0, "shuffle": 1, "bitshuffle": 2}[shuffle], int(blocksize),
+                                     out.ctypes.data, cap, C.byref(n)), "m3d_blosc_encode_host")
+    return out[: n.value].tobytes()
+
+
+def zstd_host(data, compress: bool, decoded_size: int = 0, level: int = 3) -> bytes:
+    src = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8))
+    cap = int(src.size + src.size // 128 + 1024) if compress else int(decoded_size)
+    out = np.empty(max(cap, 1), dtype=np.uint8)
+    n = C.c_int64(0)
+    _check(load_library().m3d_zstd_host(int(bool(compress)), src.ctypes.data, src.size, out.ctypes.data, cap, int(level),
+                                        C.byref(n)), "m3d_zstd_host")
+    return out[: n.value].tobytes()
 _lib = None
 
 
@@ -298,6 +396,29 @@ class DecodeContext:
         if failure:
             raise failure[0]
         _check(rc, "m3d_upload_batch_cb")
+
+    def zarr_read(self, chunks, on_piece=None):
+        """``m3d_zarr_read_chunks``: decode the listed chunks (dicts with the ``m3d_zarr_chunk`` fields, ``dst`` a
+        device address) into their device volumes on the current stream.  ``on_piece(i)`` as in :meth:`upload`."""
+        if not chunks:
+            return
+        arr = zarr_chunk_array(chunks)
+        failure = []
+
+        def trampoline(piece, _user):
+            if failure or on_piece is None:
+                return
+            try:
+                on_piece(int(piece))
+            except BaseException as e:  # noqa: BLE001 - re-raised below, ctypes would swallow it
+                failure.append(e)
+
+        cb = _PIECE_CB(trampoline)
+        rc = self._lib.m3d_zarr_read_chunks(self._h, len(chunks), C.cast(arr, C.c_void_p), _stream(self.device),
+                                            C.cast(cb, C.c_void_p), None)
+        if failure:
+            raise failure[0]
+        _check(rc, "m3d_zarr_read_chunks")
 
     def weight(self, readout, predictor, out=None):
         import torch

@@ -19,7 +19,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 BUILD_DIR = PKG_DIR / "build"
 LIB_PATH = PKG_DIR / "libm3d_b200.so"
-SOURCES = ["api.cu", "decode.cu", "lowpass.cu", "extract.cu", "table.cu", "centroid.cu", "upload.cu"]
+SOURCES = ["api.cu", "decode.cu", "lowpass.cu", "extract.cu", "table.cu", "centroid.cu", "upload.cu", "zarrio.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -23,7 +23,8 @@ static const char* const kKernelNames[KF_COUNT] = {
     "cub_radix_sort",      "ccl_assign_kernel",   "cub_exclusive_sum",   "ccl_scatter_kernel",
     "ccl_interface_kernel",   "features_kernel",     "select_hist_kernel",  "replace_above_kernel", "warp_affine_kernel",
     "table_hist3d_kernel", "table_grid_kernels", "table_overlap_kernel", "table_within_kernels",
-    "centroid_stats_kernel", "inertia_eigvals_kernel", "assign_cells_kernel", "reset_foreground_kernel"};
+    "centroid_stats_kernel", "inertia_eigvals_kernel", "assign_cells_kernel", "reset_foreground_kernel",
+    "zarr_unshuffle_place_kernel", "zarr_fill_chunk_kernel"};
 
 DecodeParams m3d_ctx::params() const {
     DecodeParams P;
@@ -203,11 +204,13 @@ extern "C" int m3d_create(int device, int n_bits, int n_codewords, const float* 
 }
 
 void m3d_release_upload_ring(m3d_ctx* ctx);  // upload.cu
+void m3d_release_zarr_ring(m3d_ctx* ctx);    // zarrio.cu
 
 extern "C" int m3d_destroy(m3d_ctx* ctx) {
     if (!ctx) return M3D_OK;
     cudaSetDevice(ctx->device);
     m3d_release_upload_ring(ctx);
+    m3d_release_zarr_ring(ctx);
     for (auto& sp : ctx->spans) {
         cudaEventDestroy(sp.a);
         cudaEventDestroy(sp.b);

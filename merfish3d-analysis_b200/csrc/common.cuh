@@ -58,6 +58,8 @@ enum M3dKernel {
     KF_EIGVALS,
     KF_TABLE_CELLS,
     KF_RESET_FG,
+    KF_ZARR_UNSHUFFLE,
+    KF_ZARR_FILL,
     KF_COUNT
 };
 

@@ -1,0 +1,833 @@
+// zarrio.cu -- the image store the decode stage reads, straight into HBM.
+//
+// The reference keeps every bit volume as an OME-NGFF v0.5 image: a Zarr v3 array of (16, 512, 512) chunks,
+// each a Blosc-1 frame of zstd blocks over bit-shuffled uint16 / float32 (qi2labDataStore.py:1425-1529), and
+// `_load_bit_data` (PD:1861-1874) has tensorstore decode them into NumPy arrays that are then copied to the
+// GPU.  Here the host only does what must be sequential -- read the chunk file and entropy-decode its blocks,
+// a pool of threads writing straight into page-locked slots -- and everything that is data-parallel happens on
+// the device behind the DMA of the slot: undoing the bit / byte shuffle and placing the chunk (cropped at the
+// volume edge and to the requested z window) into the tile's (z, y, x) volume.  No full-size host array, no
+// host-side bit transposition, no pageable copy.
+//
+// The entropy coders are the system's libzstd.so.1 / liblz4.so.1, bound at run time (no headers needed for
+// their stable C ABI).
+#include <dlfcn.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ entropy coders
+struct HostCodecs {
+    size_t (*zstd_decompress)(void*, size_t, const void*, size_t) = nullptr;
+    size_t (*zstd_compress)(void*, size_t, const void*, size_t, int) = nullptr;
+    size_t (*zstd_bound)(size_t) = nullptr;
+    unsigned (*zstd_is_error)(size_t) = nullptr;
+    int (*lz4_decompress)(const char*, char*, int, int) = nullptr;
+    int (*lz4_compress)(const char*, char*, int, int) = nullptr;
+    int (*lz4_bound)(int) = nullptr;
+};
+
+const HostCodecs& codecs() {
+    static HostCodecs c;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        if (void* z = dlopen("libzstd.so.1", RTLD_NOW | RTLD_LOCAL)) {
+            c.zstd_decompress = reinterpret_cast<decltype(c.zstd_decompress)>(dlsym(z, "ZSTD_decompress"));
+            c.zstd_compress = reinterpret_cast<decltype(c.zstd_compress)>(dlsym(z, "ZSTD_compress"));
+            c.zstd_bound = reinterpret_cast<decltype(c.zstd_bound)>(dlsym(z, "ZSTD_compressBound"));
+            c.zstd_is_error = reinterpret_cast<decltype(c.zstd_is_error)>(dlsym(z, "ZSTD_isError"));
+        }
+        if (void* l = dlopen("liblz4.so.1", RTLD_NOW | RTLD_LOCAL)) {
+            c.lz4_decompress = reinterpret_cast<decltype(c.lz4_decompress)>(dlsym(l, "LZ4_decompress_safe"));
+            c.lz4_compress = reinterpret_cast<decltype(c.lz4_compress)>(dlsym(l, "LZ4_compress_default"));
+            c.lz4_bound = reinterpret_cast<decltype(c.lz4_bound)>(dlsym(l, "LZ4_compressBound"));
+        }
+    });
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------ Blosc-1 frames
+constexpr int BLOSC_HEADER = 16;
+constexpr int FLAG_SHUFFLE = 0x1, FLAG_MEMCPY = 0x2, FLAG_BITSHUFFLE = 0x4, FLAG_DONT_SPLIT = 0x10;
+constexpr int BLOSC_LZ4 = 1, BLOSC_ZSTD = 4;
+constexpr int MAX_SPLITS = 16, MIN_BUFFERSIZE = 128;
+
+struct BloscHeader {
+    int version, versionlz, flags, typesize, codec;
+    int64_t nbytes, blocksize, cbytes;
+};
+
+inline uint32_t le32(const uint8_t* p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+inline void put32(uint8_t* p, uint32_t v) {
+    p[0] = (uint8_t)v;
+    p[1] = (uint8_t)(v >> 8);
+    p[2] = (uint8_t)(v >> 16);
+    p[3] = (uint8_t)(v >> 24);
+}
+
+bool parse_blosc_header(const uint8_t* p, size_t n, BloscHeader& h) {
+    if (n < (size_t)BLOSC_HEADER) return false;
+    h.version = p[0];
+    h.versionlz = p[1];
+    h.flags = p[2];
+    h.typesize = p[3];
+    h.nbytes = le32(p + 4);
+    h.blocksize = le32(p + 8);
+    h.cbytes = le32(p + 12);
+    h.codec = (h.flags >> 5) & 7;
+    return h.typesize >= 1 && (h.nbytes == 0 || h.blocksize >= 1) && (size_t)h.cbytes <= n;
+}
+
+// how the decoded bytes of a chunk are still arranged when they reach the device
+enum ShuffleMode { SH_NONE = 0, SH_BYTE = 1, SH_BIT = 2 };
+
+// Entropy-decode every block of a Blosc frame into `out` (h.nbytes bytes), leaving the per-block shuffle in
+// place; *mode says which un-shuffle the consumer still owes.  Every offset is bounds-checked: the frame is a
+// file from disk.  Returns nullptr on success, else a static description of what is wrong.
+const char* blosc_decode_blocks(const uint8_t* frame, size_t n, const BloscHeader& h, uint8_t* out, int* mode) {
+    *mode = SH_NONE;
+    if (h.nbytes == 0) return nullptr;
+    if (h.flags & FLAG_MEMCPY) {
+        if ((size_t)(BLOSC_HEADER + h.nbytes) > n) return "blosc: stored frame is truncated";
+        memcpy(out, frame + BLOSC_HEADER, (size_t)h.nbytes);
+        return nullptr;
+    }
+    if ((h.flags & FLAG_SHUFFLE) && h.typesize > 1) *mode = SH_BYTE;
+    else if (h.flags & FLAG_BITSHUFFLE) *mode = SH_BIT;
+    const HostCodecs& C = codecs();
+    if (h.codec == BLOSC_ZSTD && !C.zstd_decompress) return "blosc: libzstd.so.1 is not available";
+    if (h.codec == BLOSC_LZ4 && !C.lz4_decompress) return "blosc: liblz4.so.1 is not available";
+    if (h.codec != BLOSC_ZSTD && h.codec != BLOSC_LZ4) return "blosc: unsupported inner codec (zstd and lz4 only)";
+    const int64_t nblocks = (h.nbytes + h.blocksize - 1) / h.blocksize;
+    const int64_t leftover = h.nbytes % h.blocksize;
+    if ((size_t)(BLOSC_HEADER + 4 * nblocks) > n) return "blosc: block index is truncated";
+    for (int64_t j = 0; j < nblocks; ++j) {
+        const bool is_left = (j == nblocks - 1) && leftover > 0;
+        const int64_t bsize = is_left ? leftover : h.blocksize;
+        const int nsplits = (!(h.flags & FLAG_DONT_SPLIT) && h.typesize <= MAX_SPLITS &&
+                             bsize / h.typesize >= MIN_BUFFERSIZE && !is_left) ? h.typesize : 1;
+        const int64_t neblock = bsize / nsplits;
+        size_t pos = le32(frame + BLOSC_HEADER + 4 * j);
+        uint8_t* dst = out + j * h.blocksize;
+        for (int s = 0; s < nsplits; ++s) {
+            if (pos + 4 > n) return "blosc: block start outside the frame";
+            const int64_t cb = (int32_t)le32(frame + pos);
+            pos += 4;
+            if (cb < 0 || pos + (size_t)cb > n) return "blosc: stream runs past the frame";
+            if (cb == neblock) {
+                memcpy(dst, frame + pos, (size_t)cb);
+            } else if (h.codec == BLOSC_ZSTD) {
+                const size_t r = C.zstd_decompress(dst, (size_t)neblock, frame + pos, (size_t)cb);
+                if (C.zstd_is_error(r) || r != (size_t)neblock) return "blosc: zstd stream is corrupt";
+            } else {
+                const int r = C.lz4_decompress(reinterpret_cast<const char*>(frame + pos),
+                                               reinterpret_cast<char*>(dst), (int)cb, (int)neblock);
+                if (r != (int)neblock) return "blosc: lz4 stream is corrupt";
+            }
+            pos += (size_t)cb;
+            dst += neblock;
+        }
+    }
+    return nullptr;
+}
+
+// 8 x 8 bit-matrix transpose (byte i, bit j) <-> (byte j, bit i), both LSB first
+__host__ __device__ inline uint64_t transpose8x8(uint64_t x) {
+    uint64_t t;
+    t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull;
+    x ^= t ^ (t << 7);
+    t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull;
+    x ^= t ^ (t << 14);
+    t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull;
+    x ^= t ^ (t << 28);
+    return x;
+}
+
+// The 8 elements (typesize TS) of group k of one block, whatever the shuffle.  `blk` = the block's decoded
+// bytes, n_elem its element count, n8 = n_elem rounded down to a multiple of 8 (the bit-shuffled part).
+template <int TS>
+__host__ __device__ inline void fetch_group(const uint8_t* blk, int64_t n_elem, int mode, int64_t k, uint8_t out[8][TS]) {
+    const int64_t n8 = n_elem & ~(int64_t)7;
+    if (mode == SH_BIT && 8 * k + 8 <= n8) {
+        const int64_t row = n8 >> 3;
+#pragma unroll
+        for (int b = 0; b < TS; ++b) {
+            uint64_t x = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x |= (uint64_t)blk[(int64_t)(b * 8 + i) * row + k] << (8 * i);
+            x = transpose8x8(x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) out[j][b] = (uint8_t)(x >> (8 * j));
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int64_t e = 8 * k + j;
+#pragma unroll
+        for (int b = 0; b < TS; ++b) {
+            uint8_t v = 0;
+            if (e < n_elem) v = (mode == SH_BYTE) ? blk[(int64_t)b * n_elem + e] : blk[e * TS + b];
+            out[j][b] = v;
+        }
+    }
+}
+
+struct ChunkGeom {
+    int64_t nbytes;       // decoded bytes of the chunk
+    int64_t blocksize;    // Blosc block size (== nbytes for the other codecs)
+    int mode;             // ShuffleMode
+    int64_t cshape[3];    // chunk shape (z, y, x)
+    int64_t origin[3];    // where chunk element (0,0,0) lands in the destination (may be negative / beyond)
+    int64_t dshape[3];    // destination volume
+};
+
+template <int TS>
+__host__ __device__ inline void place_group(const uint8_t v[8][TS], int64_t e0, int n_valid, const ChunkGeom& g,
+                                            uint8_t* dst) {
+    const int64_t plane = g.cshape[1] * g.cshape[2];
+    const int64_t cz = e0 / plane;
+    const int64_t rem = e0 - cz * plane;
+    const int64_t cy = rem / g.cshape[2];
+    const int64_t cx = rem - cy * g.cshape[2];
+    if (n_valid == 8 && cx + 8 <= g.cshape[2]) {  // one row of the chunk
+        const int64_t z = g.origin[0] + cz, y = g.origin[1] + cy, x = g.origin[2] + cx;
+        if (z < 0 || z >= g.dshape[0] || y < 0 || y >= g.dshape[1]) return;
+        uint8_t* p = dst + ((z * g.dshape[1] + y) * g.dshape[2] + x) * TS;
+        if (x >= 0 && x + 8 <= g.dshape[2] && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (TS == 2 || TS == 4)) {
+            if (TS == 2) {
+                uint4 w;
+                w.x = v[0][0] | (v[0][1] << 8) | (v[1][0] << 16) | ((uint32_t)v[1][1] << 24);
+                w.y = v[2][0] | (v[2][1] << 8) | (v[3][0] << 16) | ((uint32_t)v[3][1] << 24);
+                w.z = v[4][0] | (v[4][1] << 8) | (v[5][0] << 16) | ((uint32_t)v[5][1] << 24);
+                w.w = v[6][0] | (v[6][1] << 8) | (v[7][0] << 16) | ((uint32_t)v[7][1] << 24);
+                *reinterpret_cast<uint4*>(p) = w;
+            } else {
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    w[j] = v[j][0] | (v[j][1 % TS] << 8) | (v[j][2 % TS] << 16) | ((uint32_t)v[j][3 % TS] << 24);
+                reinterpret_cast<uint4*>(p)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                reinterpret_cast<uint4*>(p)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+            return;
+        }
+    }
+    for (int j = 0; j < n_valid; ++j) {
+        const int64_t e = e0 + j;
+        const int64_t ez = e / plane;
+        const int64_t er = e - ez * plane;
+        const int64_t ey = er / g.cshape[2];
+        const int64_t ex = er - ey * g.cshape[2];
+        const int64_t z = g.origin[0] + ez, y = g.origin[1] + ey, x = g.origin[2] + ex;
+        if (z < 0 || z >= g.dshape[0] || y < 0 || y >= g.dshape[1] || x < 0 || x >= g.dshape[2]) continue;
+        uint8_t* p = dst + ((z * g.dshape[1] + y) * g.dshape[2] + x) * TS;
+#pragma unroll
+        for (int b = 0; b < TS; ++b) p[b] = v[j][b];
+    }
+}
+
+// group t of the chunk: block t / groups_per_block, group t % groups_per_block of that block
+template <int TS>
+__host__ __device__ inline void unshuffle_place_group(const uint8_t* staged, const ChunkGeom& g, int64_t t, uint8_t* dst) {
+    const int64_t nb = g.blocksize / TS;  // elements per full block
+    const int64_t gpb = (nb + 7) >> 3;
+    const int64_t j = t / gpb, k = t - j * gpb;
+    const int64_t first = j * nb;
+    const int64_t total = g.nbytes / TS;
+    if (first >= total) return;
+    const int64_t n_elem = (total - first < nb) ? total - first : nb;
+    if (8 * k >= n_elem) return;
+    uint8_t v[8][TS];
+    fetch_group<TS>(staged + j * g.blocksize, n_elem, g.mode, k, v);
+    const int64_t left = n_elem - 8 * k;
+    place_group<TS>(v, first + 8 * k, left < 8 ? (int)left : 8, g, dst);
+}
+
+template <int TS>
+__global__ void __launch_bounds__(256) zarr_unshuffle_place_kernel(const uint8_t* __restrict__ staged, ChunkGeom g,
+                                                                   int64_t n_groups, uint8_t* __restrict__ dst) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_groups; t += (int64_t)gridDim.x * blockDim.x)
+        unshuffle_place_group<TS>(staged, g, t, dst);
+}
+
+// a chunk that was never written holds the array's fill value
+template <typename T>
+__global__ void __launch_bounds__(256) zarr_fill_chunk_kernel(ChunkGeom g, T fill, T* __restrict__ dst) {
+    const int64_t n = g.cshape[0] * g.cshape[1] * g.cshape[2];
+    const int64_t plane = g.cshape[1] * g.cshape[2];
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t ez = e / plane, er = e - ez * plane, ey = er / g.cshape[2], ex = er - ey * g.cshape[2];
+        const int64_t z = g.origin[0] + ez, y = g.origin[1] + ey, x = g.origin[2] + ex;
+        if (z < 0 || z >= g.dshape[0] || y < 0 || y >= g.dshape[1] || x < 0 || x >= g.dshape[2]) continue;
+        dst[(z * g.dshape[1] + y) * g.dshape[2] + x] = fill;
+    }
+}
+
+inline int64_t group_count(const ChunkGeom& g, int ts) {
+    const int64_t nb = g.blocksize / ts;
+    const int64_t nblocks = (g.nbytes + g.blocksize - 1) / g.blocksize;
+    return nblocks * ((nb + 7) >> 3);
+}
+
+template <int TS>
+void unshuffle_place_host(const uint8_t* staged, const ChunkGeom& g, uint8_t* dst) {
+    const int64_t n = group_count(g, TS);
+    for (int64_t t = 0; t < n; ++t) unshuffle_place_group<TS>(staged, g, t, dst);
+}
+
+// ------------------------------------------------------------------------------------------ chunk sources
+bool read_range(const char* path, int64_t offset, int64_t length, std::vector<uint8_t>& buf, bool* missing) {
+    *missing = false;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) {
+        *missing = (errno == ENOENT);
+        return *missing;
+    }
+    if (length < 0) {
+        struct stat sb;
+        if (fstat(fd, &sb) != 0) {
+            close(fd);
+            return false;
+        }
+        length = (int64_t)sb.st_size - offset;
+        if (length < 0) length = 0;
+    }
+    buf.resize((size_t)length);
+    size_t got = 0;
+    while (got < (size_t)length) {
+        const ssize_t r = pread(fd, buf.data() + got, (size_t)length - got, (off_t)(offset + (int64_t)got));
+        if (r <= 0) break;
+        got += (size_t)r;
+    }
+    close(fd);
+    return got == (size_t)length;
+}
+
+struct Decoded {
+    int mode = SH_NONE;
+    int64_t blocksize = 0;
+};
+
+// entropy-decode one encoded chunk into `out` (expected bytes); the shuffle stays in place
+const char* decode_chunk_bytes(const m3d_zarr_chunk& c, const std::vector<uint8_t>& enc, int64_t expected, uint8_t* out,
+                               Decoded* d) {
+    d->mode = SH_NONE;
+    d->blocksize = expected;
+    if (c.codec == M3D_ZARR_RAW) {
+        if ((int64_t)enc.size() != expected) return "zarr: raw chunk has the wrong size";
+        memcpy(out, enc.data(), (size_t)expected);
+        return nullptr;
+    }
+    if (c.codec == M3D_ZARR_ZSTD) {
+        const HostCodecs& C = codecs();
+        if (!C.zstd_decompress) return "zarr: libzstd.so.1 is not available";
+        const size_t r = C.zstd_decompress(out, (size_t)expected, enc.data(), enc.size());
+        if (C.zstd_is_error(r) || r != (size_t)expected) return "zarr: zstd chunk is corrupt";
+        return nullptr;
+    }
+    if (c.codec != M3D_ZARR_BLOSC) return "zarr: unknown chunk codec";
+    BloscHeader h;
+    if (!parse_blosc_header(enc.data(), enc.size(), h)) return "blosc: bad frame header";
+    if (h.nbytes != expected) return "blosc: frame does not hold one whole chunk";
+    int mode = SH_NONE;
+    if (const char* err = blosc_decode_blocks(enc.data(), enc.size(), h, out, &mode)) return err;
+    if (mode != SH_NONE) {
+        if (h.typesize != c.elem_size) return "blosc: typesize differs from the array's element size";
+        if (h.blocksize % h.typesize != 0) return "blosc: block size is not a whole number of elements";
+    }
+    d->mode = mode;
+    d->blocksize = (h.flags & FLAG_MEMCPY) ? expected : h.blocksize;
+    return nullptr;
+}
+
+int check_chunk(const m3d_zarr_chunk& c) {
+    if (!c.path || !c.dst) return m3d_fail(M3D_ERR_ARG, "m3d_zarr_read: null path / destination");
+    if (c.elem_size != 1 && c.elem_size != 2 && c.elem_size != 4 && c.elem_size != 8)
+        return m3d_fail(M3D_ERR_ARG, "m3d_zarr_read: element size %d", c.elem_size);
+    for (int a = 0; a < 3; ++a)
+        if (c.chunk_shape[a] < 1 || c.dst_shape[a] < 1) return m3d_fail(M3D_ERR_ARG, "m3d_zarr_read: empty shape");
+    return M3D_OK;
+}
+
+ChunkGeom geom_of(const m3d_zarr_chunk& c, const Decoded& d) {
+    ChunkGeom g;
+    g.nbytes = c.chunk_shape[0] * c.chunk_shape[1] * c.chunk_shape[2] * c.elem_size;
+    g.blocksize = d.blocksize > 0 ? d.blocksize : g.nbytes;
+    g.mode = d.mode;
+    for (int a = 0; a < 3; ++a) {
+        g.cshape[a] = c.chunk_shape[a];
+        g.origin[a] = c.origin[a];
+        g.dshape[a] = c.dst_shape[a];
+    }
+    return g;
+}
+
+// ------------------------------------------------------------------------------------------ slot ring
+struct ZarrRing {
+    std::vector<void*> pinned, dev;
+    std::vector<cudaEvent_t> drained;
+    std::vector<char> used;
+    size_t slot_bytes = 0;
+};
+
+std::mutex g_zring_mu;
+std::vector<std::pair<m3d_ctx*, ZarrRing*>> g_zrings;
+
+ZarrRing* zring_of(m3d_ctx* ctx) {
+    std::lock_guard<std::mutex> lk(g_zring_mu);
+    for (auto& p : g_zrings)
+        if (p.first == ctx) return p.second;
+    ZarrRing* r = new ZarrRing();
+    g_zrings.push_back({ctx, r});
+    return r;
+}
+
+void zring_free(ZarrRing* r) {
+    for (size_t s = 0; s < r->pinned.size(); ++s) {
+        if (r->used[s]) cudaEventSynchronize(r->drained[s]);
+        cudaFreeHost(r->pinned[s]);
+        cudaFree(r->dev[s]);
+        cudaEventDestroy(r->drained[s]);
+    }
+    r->pinned.clear();
+    r->dev.clear();
+    r->drained.clear();
+    r->used.clear();
+    r->slot_bytes = 0;
+}
+
+int zring_ensure(ZarrRing* r, int n_slots, size_t slot_bytes) {
+    if (r->slot_bytes >= slot_bytes && (int)r->pinned.size() >= n_slots) return M3D_OK;
+    if (slot_bytes < r->slot_bytes) slot_bytes = r->slot_bytes;
+    if (n_slots < (int)r->pinned.size()) n_slots = (int)r->pinned.size();
+    zring_free(r);
+    for (int s = 0; s < n_slots; ++s) {
+        void *h = nullptr, *d = nullptr;
+        cudaEvent_t ev = nullptr;
+        M3D_CUDA(cudaHostAlloc(&h, slot_bytes, cudaHostAllocDefault));
+        r->pinned.push_back(h);
+        r->dev.push_back(nullptr);
+        r->drained.push_back(nullptr);
+        r->used.push_back(0);
+        M3D_CUDA(cudaMalloc(&d, slot_bytes));
+        r->dev.back() = d;
+        M3D_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        r->drained.back() = ev;
+    }
+    r->slot_bytes = slot_bytes;
+    return M3D_OK;
+}
+
+int io_threads() {
+    if (const char* e = getenv("M3D_IO_THREADS")) {
+        const int v = atoi(e);
+        if (v >= 1) return v > 64 ? 64 : v;
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    int w = hw ? (int)hw : 8;
+    return w > 32 ? 32 : w;
+}
+
+template <int TS>
+void launch_unshuffle(m3d_ctx* ctx, const uint8_t* staged, const ChunkGeom& g, uint8_t* dst, cudaStream_t st) {
+    const int64_t n = group_count(g, TS);
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)ctx->num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    M3D_LAUNCH(ctx, KF_ZARR_UNSHUFFLE, st, zarr_unshuffle_place_kernel<TS><<<(unsigned)blocks, 256, 0, st>>>(staged, g, n, dst));
+}
+
+int launch_for(m3d_ctx* ctx, int ts, const uint8_t* staged, const ChunkGeom& g, void* dst, cudaStream_t st) {
+    uint8_t* d = reinterpret_cast<uint8_t*>(dst);
+    switch (ts) {
+        case 1: launch_unshuffle<1>(ctx, staged, g, d, st); break;
+        case 2: launch_unshuffle<2>(ctx, staged, g, d, st); break;
+        case 4: launch_unshuffle<4>(ctx, staged, g, d, st); break;
+        default: launch_unshuffle<8>(ctx, staged, g, d, st); break;
+    }
+    M3D_CHECK_LAUNCH();
+    return M3D_OK;
+}
+
+int launch_fill(m3d_ctx* ctx, const m3d_zarr_chunk& c, cudaStream_t st) {
+    const ChunkGeom g = geom_of(c, Decoded());
+    const int64_t n = g.cshape[0] * g.cshape[1] * g.cshape[2];
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)ctx->num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    switch (c.elem_size) {
+        case 1: M3D_LAUNCH(ctx, KF_ZARR_FILL, st, zarr_fill_chunk_kernel<uint8_t><<<(unsigned)blocks, 256, 0, st>>>(g, (uint8_t)c.fill_bits, reinterpret_cast<uint8_t*>(c.dst))); break;
+        case 2: M3D_LAUNCH(ctx, KF_ZARR_FILL, st, zarr_fill_chunk_kernel<uint16_t><<<(unsigned)blocks, 256, 0, st>>>(g, (uint16_t)c.fill_bits, reinterpret_cast<uint16_t*>(c.dst))); break;
+        case 4: M3D_LAUNCH(ctx, KF_ZARR_FILL, st, zarr_fill_chunk_kernel<uint32_t><<<(unsigned)blocks, 256, 0, st>>>(g, (uint32_t)c.fill_bits, reinterpret_cast<uint32_t*>(c.dst))); break;
+        default: M3D_LAUNCH(ctx, KF_ZARR_FILL, st, zarr_fill_chunk_kernel<unsigned long long><<<(unsigned)blocks, 256, 0, st>>>(g, (unsigned long long)c.fill_bits, reinterpret_cast<unsigned long long*>(c.dst))); break;
+    }
+    M3D_CHECK_LAUNCH();
+    return M3D_OK;
+}
+
+}  // namespace
+
+void m3d_release_zarr_ring(m3d_ctx* ctx) {
+    std::lock_guard<std::mutex> lk(g_zring_mu);
+    for (size_t i = 0; i < g_zrings.size(); ++i) {
+        if (g_zrings[i].first != ctx) continue;
+        zring_free(g_zrings[i].second);
+        delete g_zrings[i].second;
+        g_zrings.erase(g_zrings.begin() + i);
+        return;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ C ABI
+extern "C" int m3d_blosc_info(const void* frame, int64_t n_bytes, int64_t out[6]) {
+    BloscHeader h;
+    if (!frame || !out || !parse_blosc_header(reinterpret_cast<const uint8_t*>(frame), (size_t)n_bytes, h))
+        return m3d_fail(M3D_ERR_ARG, "m3d_blosc_info: not a Blosc-1 frame");
+    out[0] = h.nbytes;
+    out[1] = h.blocksize;
+    out[2] = h.cbytes;
+    out[3] = h.typesize;
+    out[4] = h.flags;
+    out[5] = h.codec;
+    return M3D_OK;
+}
+
+extern "C" int m3d_blosc_decode_host(const void* frame, int64_t n_bytes, void* dst, int64_t dst_capacity) {
+    BloscHeader h;
+    const uint8_t* f = reinterpret_cast<const uint8_t*>(frame);
+    if (!frame || !dst || !parse_blosc_header(f, (size_t)n_bytes, h))
+        return m3d_fail(M3D_ERR_ARG, "m3d_blosc_decode_host: not a Blosc-1 frame");
+    if (h.nbytes > dst_capacity) return m3d_fail(M3D_ERR_CAPACITY, "m3d_blosc_decode_host: destination too small");
+    std::vector<uint8_t> tmp((size_t)h.nbytes);
+    int mode = SH_NONE;
+    if (const char* err = blosc_decode_blocks(f, (size_t)n_bytes, h, tmp.data(), &mode)) return m3d_fail(M3D_ERR_ARG, "%s", err);
+    if (mode == SH_NONE) {
+        memcpy(dst, tmp.data(), (size_t)h.nbytes);
+        return M3D_OK;
+    }
+    // a flat run of elements: a 1 x 1 x n "chunk" placed at the origin of a 1 x 1 x n volume; trailing bytes
+    // that do not make a whole element are never shuffled
+    const int ts = h.typesize;
+    if (ts != 1 && ts != 2 && ts != 4 && ts != 8) return m3d_fail(M3D_ERR_ARG, "m3d_blosc_decode_host: typesize %d", ts);
+    if (h.blocksize % ts) return m3d_fail(M3D_ERR_ARG, "m3d_blosc_decode_host: block size is not whole elements");
+    const int64_t n_el = h.nbytes / ts;
+    ChunkGeom g;
+    g.nbytes = n_el * ts;
+    g.blocksize = h.blocksize;
+    g.mode = mode;
+    g.cshape[0] = g.cshape[1] = 1;
+    g.cshape[2] = n_el;
+    g.origin[0] = g.origin[1] = g.origin[2] = 0;
+    g.dshape[0] = g.dshape[1] = 1;
+    g.dshape[2] = n_el;
+    uint8_t* d = reinterpret_cast<uint8_t*>(dst);
+    if (n_el > 0) switch (ts) {
+            case 1: unshuffle_place_host<1>(tmp.data(), g, d); break;
+            case 2: unshuffle_place_host<2>(tmp.data(), g, d); break;
+            case 4: unshuffle_place_host<4>(tmp.data(), g, d); break;
+            default: unshuffle_place_host<8>(tmp.data(), g, d); break;
+        }
+    memcpy(d + n_el * ts, tmp.data() + n_el * ts, (size_t)(h.nbytes - n_el * ts));
+    return M3D_OK;
+}
+
+namespace {
+// forward shuffles of one block (the writer; element planes / bit rows as blosc_decode_blocks expects them)
+void shuffle_block(const uint8_t* src, int64_t bsize, int ts, int mode, uint8_t* out) {
+    const int64_t n = bsize / ts;
+    if (mode == SH_BYTE) {
+        for (int64_t e = 0; e < n; ++e)
+            for (int b = 0; b < ts; ++b) out[(int64_t)b * n + e] = src[e * ts + b];
+        memcpy(out + n * ts, src + n * ts, (size_t)(bsize - n * ts));
+        return;
+    }
+    const int64_t n8 = n & ~(int64_t)7, row = n8 >> 3;
+    for (int64_t k = 0; k < row; ++k)
+        for (int b = 0; b < ts; ++b) {
+            uint64_t x = 0;
+            for (int j = 0; j < 8; ++j) x |= (uint64_t)src[(8 * k + j) * ts + b] << (8 * j);
+            x = transpose8x8(x);
+            for (int i = 0; i < 8; ++i) out[(int64_t)(b * 8 + i) * row + k] = (uint8_t)(x >> (8 * i));
+        }
+    memcpy(out + n8 * ts, src + n8 * ts, (size_t)(bsize - n8 * ts));
+}
+}  // namespace
+
+extern "C" int64_t m3d_blosc_encode_bound(int64_t n_bytes, int64_t blocksize) {
+    if (n_bytes < 0) return -1;
+    if (blocksize <= 0) blocksize = 256 * 1024;
+    if (blocksize > n_bytes) blocksize = n_bytes;
+    // the encoder rounds the block size down to whole elements (never below half of it); incompressible blocks
+    // are stored, so a block costs at most its size + its index entry + its length word
+    const int64_t half = blocksize / 2 > 0 ? blocksize / 2 : 1;
+    return BLOSC_HEADER + n_bytes + (n_bytes / half + 2) * 8 + 64;
+}
+
+extern "C" int m3d_blosc_encode_host(const void* src, int64_t n_bytes, int typesize, int cname, int clevel, int shuffle,
+                                     int64_t blocksize, void* dst, int64_t dst_capacity, int64_t* out_bytes) {
+    if (!src || !dst || !out_bytes || n_bytes < 0 || n_bytes > 0x7fffffff - 64 || typesize < 1 || typesize > 255)
+        return m3d_fail(M3D_ERR_ARG, "m3d_blosc_encode_host: bad argument");
+    if (cname != BLOSC_ZSTD && cname != BLOSC_LZ4) return m3d_fail(M3D_ERR_ARG, "m3d_blosc_encode_host: zstd (4) or lz4 (1)");
+    if (shuffle < SH_NONE || shuffle > SH_BIT) return m3d_fail(M3D_ERR_ARG, "m3d_blosc_encode_host: shuffle 0, 1 or 2");
+    const HostCodecs& C = codecs();
+    if (cname == BLOSC_ZSTD && !C.zstd_compress) return m3d_fail(M3D_ERR_STATE, "libzstd.so.1 is not available");
+    if (cname == BLOSC_LZ4 && !C.lz4_compress) return m3d_fail(M3D_ERR_STATE, "liblz4.so.1 is not available");
+    if (blocksize <= 0) {  // c-blosc's choice for the non-split high-ratio codecs at clevel 5: 256 KiB
+        blocksize = 32 * 1024 * (cname == BLOSC_ZSTD ? 2 : 1) * 4;
+    }
+    if (blocksize > n_bytes) blocksize = n_bytes > 0 ? n_bytes : 1;
+    if (blocksize > typesize) blocksize = blocksize / typesize * typesize;
+    if (dst_capacity < BLOSC_HEADER + n_bytes + 8 * ((n_bytes + blocksize - 1) / blocksize) + 8)
+        return m3d_fail(M3D_ERR_CAPACITY, "m3d_blosc_encode_host: destination too small");
+    const uint8_t* s = reinterpret_cast<const uint8_t*>(src);
+    uint8_t* o = reinterpret_cast<uint8_t*>(dst);
+    int flags = (cname << 5) | FLAG_DONT_SPLIT;
+    if (shuffle == SH_BYTE) flags |= FLAG_SHUFFLE;
+    if (shuffle == SH_BIT) flags |= FLAG_BITSHUFFLE;
+    o[0] = 2;
+    o[1] = 1;
+    o[3] = (uint8_t)typesize;
+    put32(o + 4, (uint32_t)n_bytes);
+    put32(o + 8, (uint32_t)blocksize);
+    if (n_bytes < MIN_BUFFERSIZE || clevel <= 0) {
+        o[2] = (uint8_t)(flags | FLAG_MEMCPY);
+        memcpy(o + BLOSC_HEADER, s, (size_t)n_bytes);
+        put32(o + 12, (uint32_t)(n_bytes + BLOSC_HEADER));
+        *out_bytes = n_bytes + BLOSC_HEADER;
+        return M3D_OK;
+    }
+    o[2] = (uint8_t)flags;
+    const int64_t nblocks = (n_bytes + blocksize - 1) / blocksize;
+    int64_t pos = BLOSC_HEADER + 4 * nblocks;
+    std::vector<uint8_t> tmp((size_t)blocksize), comp;
+    const int level = clevel * 2 - 1 < 1 ? 1 : clevel * 2 - 1;
+    for (int64_t j = 0; j < nblocks; ++j) {
+        const int64_t bsize = (j == nblocks - 1) ? n_bytes - j * blocksize : blocksize;
+        const uint8_t* blk = s + j * blocksize;
+        const bool do_byte = shuffle == SH_BYTE && typesize > 1, do_bit = shuffle == SH_BIT && bsize >= typesize;
+        if (do_byte || do_bit) {
+            shuffle_block(blk, bsize, typesize, do_byte ? SH_BYTE : SH_BIT, tmp.data());
+            blk = tmp.data();
+        }
+        int64_t cb;
+        if (cname == BLOSC_ZSTD) {
+            comp.resize(C.zstd_bound((size_t)bsize));
+            const size_t r = C.zstd_compress(comp.data(), comp.size(), blk, (size_t)bsize, level);
+            cb = C.zstd_is_error(r) ? bsize : (int64_t)r;
+        } else {
+            comp.resize((size_t)C.lz4_bound((int)bsize));
+            const int r = C.lz4_compress(reinterpret_cast<const char*>(blk), reinterpret_cast<char*>(comp.data()), (int)bsize, (int)comp.size());
+            cb = r <= 0 ? bsize : r;
+        }
+        put32(o + BLOSC_HEADER + 4 * j, (uint32_t)pos);
+        if (cb >= bsize) {  // stored
+            put32(o + pos, (uint32_t)bsize);
+            memcpy(o + pos + 4, blk, (size_t)bsize);
+            pos += 4 + bsize;
+        } else {
+            put32(o + pos, (uint32_t)cb);
+            memcpy(o + pos + 4, comp.data(), (size_t)cb);
+            pos += 4 + cb;
+        }
+    }
+    put32(o + 12, (uint32_t)pos);
+    *out_bytes = pos;
+    return M3D_OK;
+}
+
+extern "C" int m3d_zstd_host(int compress, const void* src, int64_t n_bytes, void* dst, int64_t dst_capacity, int level,
+                             int64_t* out_bytes) {
+    const HostCodecs& C = codecs();
+    if (!C.zstd_compress || !C.zstd_decompress) return m3d_fail(M3D_ERR_STATE, "libzstd.so.1 is not available");
+    if (!src || !dst || !out_bytes || n_bytes < 0) return m3d_fail(M3D_ERR_ARG, "m3d_zstd_host: bad argument");
+    if (compress && (size_t)dst_capacity < C.zstd_bound((size_t)n_bytes)) return m3d_fail(M3D_ERR_CAPACITY, "m3d_zstd_host: destination too small");
+    const size_t r = compress ? C.zstd_compress(dst, (size_t)dst_capacity, src, (size_t)n_bytes, level)
+                              : C.zstd_decompress(dst, (size_t)dst_capacity, src, (size_t)n_bytes);
+    if (C.zstd_is_error(r)) return m3d_fail(M3D_ERR_ARG, "m3d_zstd_host: corrupt frame or destination too small");
+    *out_bytes = (int64_t)r;
+    return M3D_OK;
+}
+
+// Host destination: the same chunk decode, the un-shuffle and placement run on the calling threads.  This is the
+// reference's `tensorstore.read().result()` (DS:2235-2267) for callers that want a NumPy array (metadata probes,
+// the normalisation sampler); the decode path proper uses m3d_zarr_read_chunks.
+extern "C" int m3d_zarr_read_chunks_host(int n_chunks, const m3d_zarr_chunk* chunks) {
+    if (n_chunks < 0 || (n_chunks > 0 && !chunks)) return m3d_fail(M3D_ERR_ARG, "m3d_zarr_read_chunks_host: bad argument");
+    for (int j = 0; j < n_chunks; ++j)
+        if (int rc = check_chunk(chunks[j])) return rc;
+    std::atomic<int> next{0};
+    std::mutex mu;
+    std::string first_error;
+    int workers = io_threads();
+    if (workers > n_chunks) workers = n_chunks;
+    auto work = [&]() {
+        std::vector<uint8_t> enc, dec;
+        while (true) {
+            const int j = next.fetch_add(1);
+            if (j >= n_chunks) return;
+            const m3d_zarr_chunk& c = chunks[j];
+            bool missing = false;
+            const char* err = nullptr;
+            Decoded d;
+            const int64_t expected = c.chunk_shape[0] * c.chunk_shape[1] * c.chunk_shape[2] * c.elem_size;
+            if (c.codec == M3D_ZARR_ABSENT) missing = true;
+            else if (!read_range(c.path, c.offset, c.length, enc, &missing)) err = "zarr: cannot read the chunk file";
+            if (!err && missing) {  // fill value, element by element through the same placement
+                dec.assign((size_t)expected, 0);
+                for (int64_t e = 0; e < expected / c.elem_size; ++e) memcpy(dec.data() + e * c.elem_size, &c.fill_bits, (size_t)c.elem_size);
+            } else if (!err) {
+                dec.resize((size_t)expected);
+                err = decode_chunk_bytes(c, enc, expected, dec.data(), &d);
+            }
+            if (err) {
+                std::lock_guard<std::mutex> lk(mu);
+                if (first_error.empty()) first_error = std::string(err) + " (" + c.path + ")";
+                continue;
+            }
+            const ChunkGeom g = geom_of(c, d);
+            uint8_t* dst = reinterpret_cast<uint8_t*>(c.dst);
+            switch (c.elem_size) {
+                case 1: unshuffle_place_host<1>(dec.data(), g, dst); break;
+                case 2: unshuffle_place_host<2>(dec.data(), g, dst); break;
+                case 4: unshuffle_place_host<4>(dec.data(), g, dst); break;
+                default: unshuffle_place_host<8>(dec.data(), g, dst); break;
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int w = 1; w < workers; ++w) pool.emplace_back(work);
+    if (n_chunks > 0) work();
+    for (auto& t : pool) t.join();
+    if (!first_error.empty()) return m3d_fail(M3D_ERR_ARG, "%s", first_error.c_str());
+    return M3D_OK;
+}
+
+extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_chunk* chunks, void* stream,
+                                    m3d_piece_callback on_piece, void* user) {
+    if (!ctx || n_chunks < 0 || (n_chunks > 0 && !chunks)) return m3d_fail(M3D_ERR_ARG, "m3d_zarr_read_chunks: bad argument");
+    if (n_chunks == 0) return M3D_OK;
+    M3D_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    size_t slot_bytes = 0;
+    for (int j = 0; j < n_chunks; ++j) {
+        if (int rc = check_chunk(chunks[j])) return rc;
+        if (j > 0 && chunks[j].piece < chunks[j - 1].piece) return m3d_fail(M3D_ERR_ARG, "m3d_zarr_read_chunks: pieces must be grouped in ascending order");
+        const size_t b = (size_t)(chunks[j].chunk_shape[0] * chunks[j].chunk_shape[1] * chunks[j].chunk_shape[2]) * chunks[j].elem_size;
+        if (b > slot_bytes) slot_bytes = b;
+    }
+    if (slot_bytes > ((size_t)1 << 30)) return m3d_fail(M3D_ERR_ARG, "m3d_zarr_read_chunks: chunk larger than 1 GiB");
+    int workers = io_threads();
+    if (workers > n_chunks) workers = n_chunks;
+    // enough slots that every worker can decode while a few finished slots drain; bounded in bytes
+    int n_slots = workers + 4;
+    while (n_slots > 3 && (size_t)n_slots * slot_bytes > ((size_t)768 << 20)) --n_slots;
+    ZarrRing* R = zring_of(ctx);
+    if (int rc = zring_ensure(R, n_slots, (slot_bytes + 255) & ~(size_t)255)) return rc;
+    n_slots = (int)R->pinned.size();
+
+    // chunk j decodes into slot j % n_slots once chunk j - n_slots has been issued and its slot has drained
+    std::vector<char> staged((size_t)n_chunks, 0), issued((size_t)n_chunks, 0), absent((size_t)n_chunks, 0);
+    std::vector<Decoded> info((size_t)n_chunks);
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<int> next{0};
+    std::atomic<int> failed{0};
+    std::string first_error;
+    const int device = ctx->device;
+    auto fail = [&](const std::string& what) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (first_error.empty()) first_error = what;
+        }
+        failed.store(1);
+        cv.notify_all();
+    };
+    auto work = [&]() {
+        cudaSetDevice(device);
+        std::vector<uint8_t> enc;
+        while (true) {
+            const int j = next.fetch_add(1);
+            if (j >= n_chunks || failed.load()) return;
+            const m3d_zarr_chunk& c = chunks[j];
+            bool missing = false;
+            if (c.codec == M3D_ZARR_ABSENT) missing = true;
+            else if (!read_range(c.path, c.offset, c.length, enc, &missing)) return fail(std::string("zarr: cannot read ") + c.path);
+            if (!missing) {
+                const int s = j % n_slots;
+                bool wait_drain = R->used[s];
+                if (j >= n_slots) {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return issued[j - n_slots] || failed.load(); });
+                    wait_drain = true;
+                }
+                if (failed.load()) return;
+                if (wait_drain && cudaEventSynchronize(R->drained[s]) != cudaSuccess) return fail("zarr: slot event failed");
+                const int64_t expected = c.chunk_shape[0] * c.chunk_shape[1] * c.chunk_shape[2] * c.elem_size;
+                if (const char* err = decode_chunk_bytes(c, enc, expected, reinterpret_cast<uint8_t*>(R->pinned[s]), &info[j]))
+                    return fail(std::string(err) + " (" + c.path + ")");
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                absent[j] = missing ? 1 : 0;
+                staged[j] = 1;
+            }
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> pool;
+    pool.reserve(workers);
+    for (int w = 0; w < workers; ++w) pool.emplace_back(work);
+    int rc = M3D_OK;
+    for (int j = 0; j < n_chunks && rc == M3D_OK; ++j) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return staged[j] || failed.load(); });
+        }
+        if (failed.load()) break;
+        const m3d_zarr_chunk& c = chunks[j];
+        const int s = j % n_slots;
+        if (absent[j]) {
+            rc = launch_fill(ctx, c, st);
+            // the slot was not used: keep its event as it is (still valid for the previous user)
+        } else {
+            const ChunkGeom g = geom_of(c, info[j]);
+            cudaError_t e = cudaMemcpyAsync(R->dev[s], R->pinned[s], (size_t)g.nbytes, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) rc = m3d_fail(M3D_ERR_CUDA, "m3d_zarr_read_chunks: %s", cudaGetErrorString(e));
+            if (rc == M3D_OK) rc = launch_for(ctx, c.elem_size, reinterpret_cast<const uint8_t*>(R->dev[s]), g, c.dst, st);
+            if (rc == M3D_OK) {
+                e = cudaEventRecord(R->drained[s], st);
+                if (e != cudaSuccess) rc = m3d_fail(M3D_ERR_CUDA, "m3d_zarr_read_chunks: %s", cudaGetErrorString(e));
+                R->used[s] = 1;
+            }
+        }
+        if (rc != M3D_OK) {
+            failed.store(1);
+            cv.notify_all();
+            break;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            issued[j] = 1;
+        }
+        cv.notify_all();
+        if (on_piece && (j == n_chunks - 1 || chunks[j + 1].piece != c.piece)) on_piece(c.piece, user);
+    }
+    for (auto& t : pool) t.join();
+    if (rc != M3D_OK) return rc;
+    if (failed.load()) return m3d_fail(M3D_ERR_ARG, "%s", first_error.empty() ? "m3d_zarr_read_chunks failed" : first_error.c_str());
+    return M3D_OK;  // the tail of the copies / kernels is still in flight on `stream`
+}

@@ -1,0 +1,791 @@
+"""The qi2labdatastore image store, read straight into HBM.
+
+The reference keeps every image as an OME-NGFF v0.5 group ``<name>.ome.zarr`` with one level ``0``: a Zarr v3
+array written through tensorstore with ``bytes`` + ``blosc`` (zstd, clevel 5, bit shuffle) chunks of
+``(16, 512, 512)``, optionally inside ``sharding_indexed`` shards (qi2labDataStore.py:1425-1529, 1562-1609,
+2270-2362), and reads it back whole with ``tensorstore.read()`` (DS:2235-2267).  zarr / tensorstore / yaozarrs are
+not needed here:
+
+* :class:`ZarrArray` parses ``zarr.json`` and lists the chunks (``m3d_zarr_chunk`` records);
+* ``libm3d_b200.so`` (csrc/zarrio.cu) reads + entropy-decodes them on host threads into pinned slots and the
+  GPU undoes the Blosc shuffle and places each chunk in the destination volume -- :func:`transfer` is what the
+  tile loader calls, with the same per-piece callback as the pinned-ring upload, so the per-bit low-pass / warp
+  still overlaps the arrival of the following bits;
+* :class:`ZarrImage` is the lazy handle the loaders return (``.result()``, ``.shape``, ``.dtype``,
+  ``np.asarray``): a host array is only materialised (same C decoder, no GPU needed) for callers that ask;
+* :func:`write_ome_image` writes the same layout (the C Blosc encoder), so upstream stages and tests can
+  produce stores;
+* :class:`Qi2labZarrDataStore` opens a datastore directory in the reference's layout and metadata conventions
+  (``calibrations/attributes.json``, per-entity ``attributes.json`` + image extra attributes,
+  ``docs/datastore.md:211-311``) with the decode-stage surface of ``qi2labDataStore``.
+"""
+
+from __future__ import annotations
+
+import json
+import struct
+from collections.abc import Mapping
+from pathlib import Path
+from typing import Any, Sequence
+
+import numpy as np
+import pandas as pd
+
+from . import _capi
+from .datastore import ArrayDataStore, UnitPredictor
+
+_ABSENT = (1 << 64) - 1
+DEFAULT_SPATIAL_CHUNK_ZYX = (16, 512, 512)  # DS:1562-1609
+
+
+class ZarrFormatError(ValueError):
+    """``zarr.json`` describes something this reader does not handle (it never guesses)."""
+
+
+def _crc32c_table():
+    t = np.arange(256, dtype=np.uint32)
+    for _ in range(8):
+        t = np.where(t & 1, (t >> 1) ^ np.uint32(0x82F63B78), t >> 1).astype(np.uint32)
+    return t
+
+
+_CRC = _crc32c_table()
+
+
+def crc32c(data: bytes) -> int:
+    """CRC-32C (Castagnoli) of a shard index (a few KB: a byte loop is fine)."""
+    c = 0xFFFFFFFF
+    for b in data:
+        c = int(_CRC[(c ^ b) & 0xFF]) ^ (c >> 8)
+    return c ^ 0xFFFFFFFF
+
+
+def _fill_bits(fill, dtype: np.dtype) -> int:
+    if isinstance(fill, str):
+        fill = {"NaN": np.nan, "Infinity": np.inf, "-Infinity": -np.inf}.get(fill, fill)
+        if isinstance(fill, str) and fill.startswith("0x"):
+            return int(fill, 16)
+    v = np.array(0 if fill is None else fill).astype(dtype)
+    return int(np.frombuffer(v.tobytes().ljust(8, b"\0"), dtype="<u8")[0])
+
+
+def _chunk_codec(codecs: Sequence[Mapping], dtype: np.dtype) -> int:
+    """The bytes->bytes part of a chunk's codec chain as an ``M3D_ZARR_*`` id."""
+    names = [c["name"] for c in codecs]
+    if not names or names[0] != "bytes":
+        raise ZarrFormatError(f"codec chain {names}: expected `bytes` first")
+    endian = (codecs[0].get("configuration") or {}).get("endian", "little")
+    if dtype.itemsize > 1 and endian != "little":
+        raise ZarrFormatError("big-endian arrays are not supported")
+    rest = names[1:]
+    if rest == []:
+        return _capi.M3D_ZARR_RAW
+    if rest == ["blosc"]:
+        return _capi.M3D_ZARR_BLOSC
+    if rest == ["zstd"]:
+        return _capi.M3D_ZARR_ZSTD
+    raise ZarrFormatError(f"codec chain {names} is not supported (bytes [+ blosc | zstd])")
+
+
+class ZarrArray:
+    """One Zarr v3 array directory (``zarr.json`` + chunk files), little endian, up to 5-D with the three
+    trailing axes (z, y, x) chunked freely and every leading axis chunked by 1 (DS:1562-1609)."""
+
+    def __init__(self, path: str | Path):
+        self.path = Path(path)
+        try:
+            meta = json.loads((self.path / "zarr.json").read_text())
+        except FileNotFoundError as e:
+            raise FileNotFoundError(f"{self.path} is not a Zarr v3 array (no zarr.json)") from e
+        if meta.get("zarr_format") != 3 or meta.get("node_type") != "array":
+            raise ZarrFormatError(f"{self.path}: not a Zarr v3 array")
+        self.shape = tuple(int(v) for v in meta["shape"])
+        self.dtype = np.dtype(meta["data_type"]).newbyteorder("=")
+        if self.dtype.kind not in "uifb" or self.dtype.itemsize not in (1, 2, 4, 8):
+            raise ZarrFormatError(f"data type {meta['data_type']} is not supported")
+        grid = meta["chunk_grid"]
+        if grid.get("name") != "regular":
+            raise ZarrFormatError("only regular chunk grids are supported")
+        self.grid = tuple(int(v) for v in grid["configuration"]["chunk_shape"])
+        enc = meta.get("chunk_key_encoding") or {"name": "default"}
+        cfg = enc.get("configuration") or {}
+        if enc["name"] == "default":
+            self._sep, self._prefix = cfg.get("separator", "/"), "c"
+        elif enc["name"] == "v2":
+            self._sep, self._prefix = cfg.get("separator", "."), None
+        else:
+            raise ZarrFormatError(f"chunk key encoding {enc['name']}")
+        codecs = meta["codecs"]
+        self.sharded = bool(codecs) and codecs[0]["name"] == "sharding_indexed"
+        if self.sharded:
+            if len(codecs) != 1:
+                raise ZarrFormatError("codecs after sharding_indexed are not supported")
+            sc = codecs[0]["configuration"]
+            self.chunks = tuple(int(v) for v in sc["chunk_shape"])
+            self.codec = _chunk_codec(sc["codecs"], self.dtype)
+            idx = [c["name"] for c in sc.get("index_codecs", [{"name": "bytes"}, {"name": "crc32c"}])]
+            if idx not in (["bytes"], ["bytes", "crc32c"]):
+                raise ZarrFormatError(f"shard index codecs {idx}")
+            self._index_crc = idx == ["bytes", "crc32c"]
+            self._index_at_end = sc.get("index_location", "end") == "end"
+            if any(g % c for g, c in zip(self.grid, self.chunks)):
+                raise ZarrFormatError("shard shape is not a multiple of the inner chunk shape")
+        else:
+            self.chunks = self.grid
+            self.codec = _chunk_codec(codecs, self.dtype)
+        self.fill_bits = _fill_bits(meta.get("fill_value", 0), self.dtype)
+        self.ndim = len(self.shape)
+        if self.ndim > 3 and any(c != 1 for c in self.chunks[: self.ndim - 3]):
+            raise ZarrFormatError("leading (non-spatial) axes must be chunked by 1")
+
+    # ------------------------------------------------------------------ geometry
+    @property
+    def volume_shape(self) -> tuple[int, int, int]:
+        s = self.shape[-3:]
+        return (1,) * (3 - len(s)) + tuple(s)
+
+    @property
+    def lead_shape(self) -> tuple[int, ...]:
+        return self.shape[: max(self.ndim - 3, 0)]
+
+    def _key(self, idx: Sequence[int]) -> Path:
+        name = self._sep.join(str(int(i)) for i in idx)
+        if self._prefix is not None:
+            name = self._prefix + self._sep + name if idx else self._prefix
+        return self.path / name
+
+    def _shard_index(self, f: Path):
+        """(offset, nbytes) uint64 pairs of one shard, C order over its inner chunks; None = shard absent."""
+        per = [g // c for g, c in zip(self.grid, self.chunks)]
+        n = int(np.prod(per))
+        size = n * 16 + (4 if self._index_crc else 0)
+        try:
+            with open(f, "rb") as fh:
+                if self._index_at_end:
+                    fh.seek(0, 2)
+                    if fh.tell() < size:
+                        raise ZarrFormatError(f"{f}: shard smaller than its index")
+                    fh.seek(-size, 2)
+                raw = fh.read(size)
+        except FileNotFoundError:
+            return None
+        body = raw[: n * 16]
+        if self._index_crc and struct.unpack("<I", raw[n * 16 :])[0] != crc32c(body):
+            raise ZarrFormatError(f"{f}: shard index checksum mismatch")
+        return np.frombuffer(body, dtype="<u8").reshape(tuple(per) + (2,))
+
+    def chunk_records(self, dst_addr: int, z0: int = 0, z1: int | None = None, piece: int = 0) -> list[dict]:
+        """``m3d_zarr_chunk`` records that fill planes [z0, z1) of every (z, y, x) volume of the array into a
+        C-ordered destination of shape ``lead_shape + (z1 - z0, y, x)`` starting at address ``dst_addr``."""
+        vz, vy, vx = self.volume_shape
+        z1 = vz if z1 is None else int(z1)
+        z0 = int(z0)
+        if not 0 <= z0 <= z1 <= vz:
+            raise ValueError(f"z window [{z0}, {z1}) outside 0..{vz}")
+        dst_shape = (z1 - z0, vy, vx)
+        if dst_shape[0] == 0:
+            return []
+        nd3 = min(self.ndim, 3)
+        cz, cy, cx = (1,) * (3 - nd3) + tuple(self.chunks[-nd3:])
+        gz, gy, gx = (1,) * (3 - nd3) + tuple(self.grid[-nd3:])
+        vol_bytes = int(np.prod(dst_shape)) * self.dtype.itemsize
+        base = dict(codec=self.codec, elem_size=self.dtype.itemsize, chunk_shape=(cz, cy, cx), dst_shape=dst_shape,
+                    fill_bits=self.fill_bits, piece=piece, offset=0, length=-1)
+        out = []
+        for li, lead in enumerate(np.ndindex(*self.lead_shape)):
+            dst = dst_addr + li * vol_bytes
+            for iz in range(z0 // gz, (z1 - 1) // gz + 1):
+                for iy in range(-(-vy // gy)):
+                    for ix in range(-(-vx // gx)):
+                        key = self._key(tuple(lead) + (iz, iy, ix)[3 - nd3 :])
+                        if not self.sharded:
+                            out.append(dict(base, path=str(key), dst=dst, origin=(iz * gz - z0, iy * gy, ix * gx)))
+                            continue
+                        index = self._shard_index(key)
+                        per = (gz // cz, gy // cy, gx // cx)
+                        for sz in range(per[0]):
+                            oz = iz * gz + sz * cz
+                            if oz >= z1 or oz + cz <= z0 or oz >= vz:
+                                continue
+                            for sy in range(per[1]):
+                                for sx in range(per[2]):
+                                    oy, ox = iy * gy + sy * cy, ix * gx + sx * cx
+                                    if oy >= vy or ox >= vx:
+                                        continue
+                                    rec = dict(base, path=str(key), dst=dst, origin=(oz - z0, oy, ox))
+                                    if index is None:
+                                        rec["codec"] = _capi.M3D_ZARR_ABSENT
+                                    else:
+                                        sub = (0,) * (index.ndim - 4) + (sz, sy, sx)[3 - nd3 :]
+                                        off, nb = (int(v) for v in index[sub])
+                                        if off == _ABSENT and nb == _ABSENT:
+                                            rec["codec"] = _capi.M3D_ZARR_ABSENT
+                                        else:
+                                            rec["offset"], rec["length"] = off, nb
+                                    out.append(rec)
+        return out
+
+    def read(self, z0: int = 0, z1: int | None = None) -> np.ndarray:
+        """Host array of planes [z0, z1) (all leading indices), decoded by the C library on host threads."""
+        vz = self.volume_shape[0]
+        z1 = vz if z1 is None else int(z1)
+        nd3 = min(self.ndim, 3)
+        shape = self.lead_shape + ((z1 - z0,) + self.volume_shape[1:])[3 - nd3 :]
+        out = np.empty(shape, dtype=self.dtype)
+        if out.size:
+            _capi.zarr_read_chunks_host(self.chunk_records(out.ctypes.data, z0, z1))
+        return out
+
+
+class ZarrImage:
+    """Lazy level-``0`` array of an OME-NGFF image: what the datastore's image loaders return.  Quacks like the
+    reference's read future (``.result()``) and like an array (``shape``, ``dtype``, ``np.asarray``, slicing);
+    the tile loader recognises it and sends the chunks straight to the device instead."""
+
+    def __init__(self, image_path: str | Path):
+        self.image_path = Path(image_path)
+        self.array = ZarrArray(self.image_path / "0")
+        self.shape = self.array.shape
+        self.dtype = self.array.dtype
+        self.ndim = self.array.ndim
+        self.size = int(np.prod(self.shape))
+        self.nbytes = self.size * self.dtype.itemsize
+
+    def result(self):
+        return self
+
+    def read(self, z0: int = 0, z1: int | None = None) -> np.ndarray:
+        return self.array.read(z0, z1)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.read()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, idx):
+        first = idx[0] if isinstance(idx, tuple) else idx
+        if self.ndim == 3 and isinstance(first, slice):  # a z window: decode only the chunks it touches
+            a, b, step = first.indices(self.shape[0])
+            if step == 1:
+                vol = self.read(a, max(a, b))
+                return vol[(slice(None),) + idx[1:]] if isinstance(idx, tuple) else vol
+        return self.read()[idx]
+
+    def window(self, z0: int, z1: int) -> "ZarrWindow":
+        return ZarrWindow(self, int(z0), int(z1))
+
+    @property
+    def extra_attributes(self) -> dict[str, Any]:
+        return read_extra_attributes(self.image_path)
+
+
+class ZarrWindow:
+    """Planes [z0, z1) of a 3-D :class:`ZarrImage` as an upload source for :func:`transfer`."""
+
+    def __init__(self, image: ZarrImage, z0: int, z1: int):
+        if image.ndim != 3:
+            raise ValueError("z windows are taken of (z, y, x) images")
+        self.image, self.z0, self.z1 = image, z0, z1
+        self.shape = (z1 - z0,) + tuple(image.shape[1:])
+        self.dtype = image.dtype
+        self.nbytes = int(np.prod(self.shape)) * image.dtype.itemsize
+
+
+def host_piece(image, a: int, b: int, dtype) -> Any:
+    """Upload source for planes [a, b) of ``image`` as ``dtype``: a lazy :class:`ZarrWindow` when the store already
+    holds that type (the chunks then go disk -> pinned slot -> device), else a contiguous NumPy array."""
+    if isinstance(image, ZarrImage) and image.ndim == 3 and image.dtype == np.dtype(dtype):
+        return image.window(a, b)
+    return np.ascontiguousarray(image[a:b], dtype=dtype)
+
+
+def transfer(ctx, pieces, on_piece=None) -> None:
+    """``DecodeContext.upload`` for mixed sources: ``pieces`` = ``[(source, device tensor), ...]`` where a source is
+    a C-contiguous NumPy array (pinned ring / DMA) or a :class:`ZarrWindow` / :class:`ZarrImage` (chunk decode on
+    the device side).  Pieces complete in order on the current stream; ``on_piece(i)`` as in ``upload``."""
+    pieces = list(pieces)
+    i = 0
+    while i < len(pieces):
+        lazy = isinstance(pieces[i][0], (ZarrWindow, ZarrImage))
+        j = i
+        while j < len(pieces) and isinstance(pieces[j][0], (ZarrWindow, ZarrImage)) == lazy:
+            j += 1
+        run = pieces[i:j]
+        cb = None if on_piece is None else (lambda k, base=i: on_piece(base + k))
+        if not lazy:
+            ctx.upload(run, on_piece=cb)
+        else:
+            records = []
+            empty = []
+            for k, (src, dst) in enumerate(run):
+                if isinstance(src, ZarrImage):
+                    src = ZarrWindow(src, 0, src.shape[0]) if src.ndim == 3 else src
+                nbytes = src.nbytes
+                if not dst.is_cuda or not dst.is_contiguous() or dst.numel() * dst.element_size() != nbytes:
+                    raise _capi.M3dError("transfer(): destination must be a contiguous device tensor of the source's size")
+                if isinstance(src, ZarrWindow):
+                    recs = src.image.array.chunk_records(dst.data_ptr(), src.z0, src.z1, piece=k)
+                else:
+                    recs = src.array.chunk_records(dst.data_ptr(), piece=k)
+                if not recs:
+                    empty.append(k)
+                records.extend(recs)
+            done = set()
+
+            def note(k, cb=cb, done=done):
+                done.add(k)
+                if cb is not None:
+                    cb(k)
+
+            ctx.zarr_read(records, on_piece=note)
+            for k in empty:  # zero-sized windows have no chunk to wait for
+                if k not in done and cb is not None:
+                    cb(k)
+        i = j
+
+
+# ---------------------------------------------------------------------- OME-NGFF v0.5 image groups
+def image_store_path(image_path: str | Path) -> Path:
+    """DS:1693-1718: logical image name -> ``<name>.ome.zarr``."""
+    p = Path(image_path)
+    if p.name.endswith(".ome.zarr"):
+        return p
+    if p.suffixes:
+        raise ValueError(f"Invalid image store name '{p.name}'. Use bare logical names or '.ome.zarr'.")
+    return p.with_name(p.name + ".ome.zarr")
+
+
+def read_extra_attributes(image_path: str | Path) -> dict[str, Any]:
+    """DS:1721-1739: the image group's attributes without the ``ome`` block."""
+    meta = json.loads((image_store_path(image_path) / "zarr.json").read_text())
+    attrs = dict(meta.get("attributes") or {})
+    attrs.pop("ome", None)
+    return attrs
+
+
+def _jsonable(v):
+    if isinstance(v, np.ndarray):
+        return v.tolist()
+    if isinstance(v, np.generic):
+        return v.item()
+    if isinstance(v, Mapping):
+        return {str(k): _jsonable(x) for k, x in v.items()}
+    if isinstance(v, (list, tuple)):
+        return [_jsonable(x) for x in v]
+    if isinstance(v, Path):
+        return str(v)
+    return v
+
+
+def default_chunks(shape: Sequence[int], spatial_chunk_zyx=DEFAULT_SPATIAL_CHUNK_ZYX) -> tuple[int, ...]:
+    """DS:1562-1609."""
+    n = len(shape)
+    if n < 2 or n > 5:
+        raise ValueError(f"Unsupported array ndim for image write: {n}")
+    spatial = tuple(spatial_chunk_zyx)[-min(n, 3) :]
+    tail = tuple(min(int(s), int(c)) for s, c in zip(shape[-len(spatial) :], spatial))
+    return (1,) * (n - len(tail)) + tail
+
+
+def _encode(block: np.ndarray, compression: str) -> bytes:
+    if compression in ("blosc-zstd", "blosc-lz4"):
+        return _capi.blosc_encode_host(block, block.dtype.itemsize, compression[6:], 5, "bitshuffle")
+    if compression == "zstd":
+        return _capi.zstd_host(block.tobytes(), True, level=3)
+    if compression == "none":
+        return block.tobytes()
+    raise ValueError(f"Unknown compression: {compression}")
+
+
+def write_zarr_array(path: str | Path, array: np.ndarray, chunks: Sequence[int], compression: str = "blosc-zstd",
+                     shards: Sequence[int] | None = None, dimension_names: Sequence[str] | None = None) -> None:
+    """A Zarr v3 array as ``_create_array_tensorstore_qi2lab`` (DS:1425-1529) lays it out."""
+    path = Path(path)
+    array = np.asarray(array)
+    dt = array.dtype.newbyteorder("<") if array.dtype.itemsize > 1 else array.dtype
+    chunks = tuple(int(c) for c in chunks)
+    inner = [{"name": "bytes", "configuration": {"endian": "little"}}]
+    if compression in ("blosc-zstd", "blosc-lz4"):
+        inner.append({"name": "blosc", "configuration": {"cname": compression[6:], "clevel": 5, "shuffle": "bitshuffle",
+                                                         "typesize": array.dtype.itemsize, "blocksize": 0}})
+    elif compression == "zstd":
+        inner.append({"name": "zstd", "configuration": {"level": 3, "checksum": False}})
+    elif compression != "none":
+        raise ValueError(f"Unknown compression: {compression}")
+    grid = chunks if shards is None else tuple(int(s) for s in shards)
+    codecs = inner if shards is None else [{"name": "sharding_indexed", "configuration": {
+        "chunk_shape": list(chunks), "codecs": inner, "index_location": "end",
+        "index_codecs": [{"name": "bytes", "configuration": {"endian": "little"}}, {"name": "crc32c"}]}}]
+    meta = {"zarr_format": 3, "node_type": "array", "shape": [int(s) for s in array.shape],
+            "data_type": array.dtype.name, "fill_value": 0,
+            "chunk_grid": {"name": "regular", "configuration": {"chunk_shape": list(grid)}},
+            "chunk_key_encoding": {"name": "default", "configuration": {"separator": "/"}},
+            "codecs": codecs, "attributes": {}}
+    if dimension_names:
+        meta["dimension_names"] = list(dimension_names)
+    path.mkdir(parents=True, exist_ok=True)
+    (path / "zarr.json").write_text(json.dumps(meta, indent=2))
+
+    def block_at(origin):
+        blk = np.zeros(chunks, dtype=dt)
+        src = array[tuple(slice(o, o + c) for o, c in zip(origin, chunks))]
+        blk[tuple(slice(0, s) for s in src.shape)] = src
+        return blk
+
+    for idx in np.ndindex(*[-(-s // g) for s, g in zip(array.shape, grid)]):
+        f = path / "c" / "/".join(str(i) for i in idx)
+        f.parent.mkdir(parents=True, exist_ok=True)
+        origin = tuple(i * g for i, g in zip(idx, grid))
+        if shards is None:
+            f.write_bytes(_encode(block_at(origin), compression))
+            continue
+        parts, index = [], []
+        pos = 0
+        for sub in np.ndindex(*[g // c for g, c in zip(grid, chunks)]):
+            o = tuple(a + i * c for a, i, c in zip(origin, sub, chunks))
+            if any(a >= s for a, s in zip(o, array.shape)):
+                index += [_ABSENT, _ABSENT]
+                continue
+            enc = _encode(block_at(o), compression)
+            index += [pos, len(enc)]
+            parts.append(enc)
+            pos += len(enc)
+        ib = np.asarray(index, dtype="<u8").tobytes()
+        f.write_bytes(b"".join(parts) + ib + struct.pack("<I", crc32c(ib)))
+
+
+def write_ome_image(image_path: str | Path, array, chunks: Sequence[int] | None = None,
+                    compression: str = "blosc-zstd", shards: Sequence[int] | None = None,
+                    extra_attributes: Mapping[str, Any] | None = None, scale: Sequence[float] | None = None,
+                    translation: Sequence[float] | None = None) -> Path:
+    """DS:2270-2362 (`_save_to_zarr_array`): one-level OME-NGFF v0.5 image, extra attributes beside ``ome``."""
+    path = image_store_path(image_path)
+    array = np.asarray(array)
+    if array.dtype == np.float64:
+        array = array.astype(np.float32)
+    if chunks is None or len(chunks) != array.ndim:
+        chunks = default_chunks(array.shape)
+    names = ["t", "c", "z", "y", "x"][-array.ndim :]
+    axes = []
+    for n in names:
+        axes.append({"name": n, "type": "space", "unit": "micrometer"} if n in "zyx" else
+                    {"name": n, "type": "time" if n == "t" else "channel"})
+    scale = [1.0] * array.ndim if scale is None else [float(v) for v in scale][-array.ndim :]
+    translation = [0.0] * array.ndim if translation is None else [float(v) for v in translation][-array.ndim :]
+    attrs = {"ome": {"version": "0.5", "multiscales": [{"axes": axes, "datasets": [{"path": "0", "coordinateTransformations": [
+        {"type": "scale", "scale": scale}, {"type": "translation", "translation": translation}]}]}]}}
+    attrs.update(_jsonable(dict(extra_attributes or {})))
+    path.mkdir(parents=True, exist_ok=True)
+    (path / "zarr.json").write_text(json.dumps({"zarr_format": 3, "node_type": "group", "attributes": attrs}, indent=2))
+    write_zarr_array(path / "0", array, chunks, compression=compression, shards=shards, dimension_names=names)
+    return path
+
+
+# ---------------------------------------------------------------------- the datastore
+class Qi2labZarrDataStore(ArrayDataStore):
+    """A qi2labdatastore directory (reference layout, version 0.6) with the decode-stage surface.
+
+    Metadata follows the reference: experiment-wide values in ``calibrations/attributes.json``
+    (DS:2455-2515), per-entity values = the extra attributes of the entity's images merged with its
+    ``attributes.json`` sidecar (DS:1860-1901).  Image loaders return :class:`ZarrImage` handles."""
+
+    _ENTITY_IMAGES = ("corrected_data", "decon_data", "feature_predictor_data", "opticalflow_xform_px")
+
+    def __init__(self, datastore_path: str | Path, validate: bool = False) -> None:
+        self._datastore_path = Path(datastore_path)
+        self._calibrations_zarr_path = self._datastore_path / "calibrations"
+        self._decoded_root_path = self._datastore_path / "decoded"
+        self._readouts_root_path = self._datastore_path / "readouts"
+        self._fiducial_root_path = self._datastore_path / "fiducial"
+        self._mem_readout, self._mem_predictor = {}, {}
+        state_path = self._datastore_path / "datastore_state.json"
+        if not state_path.exists():
+            raise FileNotFoundError(f"{self._datastore_path} is not a qi2labdatastore (no datastore_state.json)")
+        self._datastore_state = json.loads(state_path.read_text())
+        if float(self._datastore_state.get("Version", 0)) != 0.6:
+            raise ValueError("Only datastore version 0.6 is supported by this build.")
+        self._decoded_root_path.mkdir(parents=True, exist_ok=True)
+        self._refresh()
+        if validate:
+            for tile_id in self._tile_ids:
+                for bit_id in self._bit_ids:
+                    if self.load_local_readout_image(tile_id, bit_id, return_future=None) is None:
+                        raise FileNotFoundError(f"readouts/{tile_id}/{bit_id} holds no image")
+
+    # ---- creation (what the reference's conversion stage does, DS:1306-1351 + setters)
+    @classmethod
+    def create(cls, datastore_path: str | Path, codebook: pd.DataFrame, num_tiles: int = 0, num_rounds: int = 1,
+               voxel_size_zyx_um: Sequence[float] = (0.315, 0.098, 0.098), microscope_type: str = "3D",
+               **calibrations) -> "Qi2labZarrDataStore":
+        root = Path(datastore_path)
+        for sub in ("calibrations", "fiducial", "readouts", "feature_predictor_localizations", "decoded", "fused",
+                    "segmentation"):
+            (root / sub).mkdir(parents=True, exist_ok=True)
+        state = {"Version": 0.6, "Initialized": True, "Calibrations": True, "Corrected": True, "LocalRegistered": True,
+                 "GlobalRegistered": True, "Fused": False, "SegmentedCells": False, "DecodedSpots": False,
+                 "FilteredSpots": False}
+        (root / "datastore_state.json").write_text(json.dumps(state, indent=2))
+        attrs = {"num_rounds": int(num_rounds), "num_tiles": int(num_tiles), "num_bits": int(codebook.shape[1] - 1),
+                 "codebook": _jsonable(codebook.to_numpy(dtype=object)), "microscope_type": str(microscope_type),
+                 "voxel_size_zyx_um": [float(v) for v in voxel_size_zyx_um], "channels_in_data": None,
+                 "tile_overlap": None, "binning": 1, "e_per_ADU": None, "na": None, "ri": None, "exp_order": None,
+                 "camera_model": None}
+        attrs.update(_jsonable(calibrations))
+        (root / "calibrations" / "attributes.json").write_text(json.dumps(attrs, indent=2))
+        return cls(root)
+
+    def _refresh(self, attrs=None) -> None:
+        attrs = self._load_calibrations_attributes() if attrs is None else attrs
+        rows = attrs.get("codebook")
+        if rows is None:
+            raise KeyError("Calibration attributes incomplete")
+        ncol = len(rows[0]) if rows else 0
+        self._codebook = pd.DataFrame(rows, columns=["gene_id"] + [f"bit{i:02d}" for i in range(1, ncol)])  # DS:838
+        self._num_tiles_attr = int(attrs.get("num_tiles") or 0)
+        self._tile_ids = [f"tile{i:04d}" for i in range(self._num_tiles_attr)]
+        self._round_ids = [f"round{i + 1:03d}" for i in range(int(attrs.get("num_rounds") or 1))]
+        self._bit_ids = [f"bit{i + 1:03d}" for i in range(int(attrs.get("num_bits") or max(ncol - 1, 0)))]
+        self._voxel_size_zyx_um = np.asarray(attrs["voxel_size_zyx_um"], dtype=float)
+        self._microscope_type = attrs.get("microscope_type", "3D")
+        self._tile_meta = {}
+        self._entity_cache: dict[Path, dict] = {}
+
+    @property
+    def round_ids(self):
+        return list(self._round_ids)
+
+    @property
+    def datastore_state(self):
+        return dict(self._datastore_state)
+
+    # ---- entity metadata (DS:1860-1901)
+    def _load_entity_attributes(self, entity_root: Path, image_names: Sequence[str] | None = None) -> dict[str, Any]:
+        key = (Path(entity_root), tuple(image_names or ()))
+        hit = self._entity_cache.get(key)
+        if hit is not None:
+            return hit
+        merged: dict[str, Any] = {}
+        for name in image_names or self._ENTITY_IMAGES:
+            p = image_store_path(Path(entity_root) / name)
+            if (p / "zarr.json").exists():
+                merged.update(read_extra_attributes(p))
+        side = Path(entity_root) / "attributes.json"
+        if side.exists():
+            d = json.loads(side.read_text())
+            if isinstance(d, dict):
+                merged.update(d)
+        self._entity_cache[key] = merged
+        return merged
+
+    def _save_entity_attributes(self, entity_root: Path, updates: Mapping[str, Any]) -> None:
+        entity_root = Path(entity_root)
+        entity_root.mkdir(parents=True, exist_ok=True)
+        side = entity_root / "attributes.json"
+        d = json.loads(side.read_text()) if side.exists() else {}
+        d.update(_jsonable(dict(updates)))
+        side.write_text(json.dumps(d, indent=2))
+        self._entity_cache.clear()
+
+    def _round_id(self, round) -> str | None:
+        if isinstance(round, (int, np.integer)):
+            return self._round_ids[int(round)] if 0 <= round < len(self._round_ids) else None
+        return round if round in self._round_ids else None
+
+    # ---- images
+    def _open_image(self, entity_root: Path, name: str, return_future):
+        p = image_store_path(entity_root / name)
+        if not (p / "zarr.json").exists():
+            return None
+        img = ZarrImage(p)
+        if return_future is None or return_future:
+            return img  # lazy handle: `.result()` / np.asarray materialise it
+        return img
+
+    def load_local_readout_image(self, tile, bit, return_future: bool | None = True):
+        """DS:4709-4745: ``decon_data`` when present, else ``corrected_data``; native frame."""
+        tile_id, bit_id = self._tile_id(tile), self._bit_id(bit)
+        if tile_id is None or bit_id is None:
+            return None
+        root = self._readouts_root_path / tile_id / bit_id
+        for name in ("decon_data", "corrected_data"):
+            img = self._open_image(root, name, return_future)
+            if img is not None:
+                return img
+        print("Readout image not found.")
+        return None
+
+    def load_local_feature_predictor_image(self, tile, bit, return_future: bool | None = True):
+        """DS:4838-4916; a bit without a stored predictor gets unit weights (multiply skipped downstream)."""
+        tile_id, bit_id = self._tile_id(tile), self._bit_id(bit)
+        if tile_id is None or bit_id is None:
+            return None
+        img = self._open_image(self._readouts_root_path / tile_id / bit_id, "feature_predictor_data", return_future)
+        if img is None:
+            ro = self.load_local_readout_image(tile_id, bit_id, return_future=None)
+            return None if ro is None else UnitPredictor(ro.shape)
+        return img
+
+    def save_local_corrected_image(self, image, tile, bit, **attributes) -> None:
+        root = self._readouts_root_path / self._tile_id(tile) / self._bit_id(bit)
+        write_ome_image(root / "corrected_data", np.asarray(image), extra_attributes=attributes,
+                        scale=self._voxel_size_zyx_um)
+        self._entity_cache.clear()
+
+    def save_local_feature_predictor_image(self, image, tile, bit) -> None:
+        root = self._readouts_root_path / self._tile_id(tile) / self._bit_id(bit)
+        write_ome_image(root / "feature_predictor_data", np.asarray(image, dtype=np.float32),
+                        scale=self._voxel_size_zyx_um)
+        self._entity_cache.clear()
+
+    # ---- per-entity scalars / transforms
+    def load_local_wavelengths_um(self, tile, bit=None, round=None):
+        """DS:3352-3436."""
+        tile_id = self._tile_id(tile)
+        if tile_id is None:
+            return None
+        root = (self._readouts_root_path / tile_id / self._bit_id(bit) if bit is not None
+                else self._fiducial_root_path / tile_id / self._round_id(round))
+        a = self._load_entity_attributes(root)
+        try:
+            return (a["excitation_um"], a["emission_um"])
+        except KeyError:
+            print("Wavelength attributes not found.")
+            return None
+
+    def load_local_round_linker(self, tile, bit):
+        """DS:3083-3146."""
+        a = self._load_entity_attributes(self._readouts_root_path / self._tile_id(tile) / self._bit_id(bit))
+        rl = a.get("round_linker")
+        if rl is None:
+            print("Round linker attribute not found.")
+            return None
+        return int(rl)
+
+    def load_local_stage_position_zyx_um(self, tile, round=0):
+        """DS:3209-3277."""
+        a = self._load_entity_attributes(self._fiducial_root_path / self._tile_id(tile) / self._round_id(round))
+        if a.get("stage_zyx_um") is None or a.get("affine_zyx_px") is None:
+            print("Stage position attribute not found.")
+            return None
+        return np.asarray(a["stage_zyx_um"], dtype=np.float32), np.asarray(a["affine_zyx_px"], dtype=np.float32)
+
+    def load_local_round_transform_zyx_um(self, tile, round):
+        """DS:3901-3960."""
+        a = self._load_entity_attributes(self._fiducial_root_path / self._tile_id(tile) / self._round_id(round))
+        xf = a.get("local_round_transform_zyx_um")
+        if xf is None:
+            print("Local round transform mapping back to first round not found.")
+            return None
+        return np.asarray(xf, dtype=np.float32)
+
+    def load_global_coord_xforms_um(self, tile):
+        """DS:5131-5185: stored on the first round's fiducial entity."""
+        a = self._load_entity_attributes(self._fiducial_root_path / self._tile_id(tile) / self._round_ids[0])
+        try:
+            return (np.asarray(a["affine_zyx_um"], dtype=np.float32), np.asarray(a["origin_zyx_um"], dtype=np.float32),
+                    np.asarray(a["spacing_zyx_um"], dtype=np.float32))
+        except KeyError:
+            return None, None, None
+
+    def load_chromatic_affine_transform_zyx_um(self, channel_name=None, channel_index=None, wavelength_um=None):
+        """DS:213-268: identity unless the calibration holds a matching channel."""
+        cal = self._load_calibrations_attributes().get("chromatic_affine_transforms_zyx_um", {})
+        channels = cal.get("channels", {}) if isinstance(cal, Mapping) else {}
+        if not isinstance(channels, Mapping):
+            return np.eye(4, dtype=np.float32)
+        cands = []
+        if channel_name is not None and isinstance(channels.get(str(channel_name)), Mapping):
+            cands.append(channels[str(channel_name)])
+        for ch in channels.values():
+            if not isinstance(ch, Mapping):
+                continue
+            if channel_index is not None and int(ch.get("channel_index", -1)) == int(channel_index):
+                cands.append(ch)
+        if wavelength_um is not None:
+            for ch in channels.values():
+                if isinstance(ch, Mapping) and ch.get("wavelength_um") is not None and np.isclose(
+                        float(ch["wavelength_um"]), float(wavelength_um)):
+                    cands.append(ch)
+        for ch in cands:
+            if ch.get("affine_zyx_um") is not None:
+                return np.asarray(ch["affine_zyx_um"], dtype=np.float32)
+        return np.eye(4, dtype=np.float32)
+
+    def load_local_sofima_flow_field(self, tile, round, return_future: bool | None = True):
+        """DS:4203-4280: (flow (3, fz, fy, fx) float32, attributes) or None."""
+        tile_id, round_id = self._tile_id(tile), self._round_id(round)
+        if tile_id is None or round_id is None:
+            return None
+        root = self._fiducial_root_path / tile_id / round_id
+        p = image_store_path(root / "local_sofima_flow_field")
+        if not (p / "zarr.json").exists():
+            return None
+        field = np.asarray(ZarrImage(p))  # small (block grid): decoded on the host, uploaded with the tile
+        return field, self._load_entity_attributes(root, image_names=("local_sofima_flow_field",))
+
+    @property
+    def has_identity_decode_transforms(self) -> bool:
+        for tile_id in self._tile_ids:
+            for bit_id in self._bit_ids:
+                if (self.load_local_round_linker(tile_id, bit_id) or 1) != 1:
+                    return False
+        for tile_id in self._tile_ids:
+            for rid in self._round_ids:
+                if (image_store_path(self._fiducial_root_path / tile_id / rid / "local_sofima_flow_field")).exists():
+                    return False
+        cal = self._load_calibrations_attributes().get("chromatic_affine_transforms_zyx_um")
+        return not cal
+
+    # ---- writing a tile in the reference's conventions (fixtures, synthetic stores, upstream stages)
+    def add_tile(self, readouts, predictors=None, tile_id: str | None = None, stage_origin_zyx_um=None,
+                 camera_to_stage_affine=None, global_xform=None, wavelengths_um=None, persist: bool = True,
+                 bit_round=None, round_transforms_zyx_um=None, sofima_flow_fields=None,
+                 compression: str = "blosc-zstd", chunks=None, shards=None) -> str:
+        readouts = np.asarray(readouts)
+        if readouts.ndim != 4:
+            raise ValueError("readouts must be (bits, z, y, x)")
+        cal = self._load_calibrations_attributes()
+        if tile_id is None:
+            tile_id = f"tile{int(cal.get('num_tiles') or 0):04d}"
+        idx = int(tile_id[4:])
+        n_bits = readouts.shape[0]
+        bit_round = [1] * n_bits if bit_round is None else [int(r) for r in bit_round]
+        cal["num_tiles"] = max(int(cal.get("num_tiles") or 0), idx + 1)
+        cal["num_rounds"] = max(int(cal.get("num_rounds") or 1), max(bit_round))
+        cal["num_bits"] = max(int(cal.get("num_bits") or 0), n_bits)
+        self._save_calibrations_attributes(cal)
+        self._refresh(cal)
+        for b in range(n_bits):
+            root = self._readouts_root_path / tile_id / self._bit_ids[b]
+            ex, em = (0.561, 0.580) if wavelengths_um is None else wavelengths_um[b]
+            extra = {"round_linker": bit_round[b], "excitation_um": float(ex), "emission_um": float(em)}
+            src = readouts[b]
+            src = src.astype(np.float32) if src.dtype.kind == "f" else src.astype(np.uint16)
+            write_ome_image(root / "corrected_data", src, chunks=chunks, compression=compression, shards=shards,
+                            extra_attributes=extra, scale=self._voxel_size_zyx_um)
+            if predictors is not None:
+                write_ome_image(root / "feature_predictor_data", np.asarray(predictors[b], dtype=np.float32),
+                                chunks=chunks, compression=compression, shards=shards, scale=self._voxel_size_zyx_um)
+        for r, rid in enumerate(self._round_ids, start=1):
+            meta = {"bit_linker": [b + 1 for b in range(n_bits) if bit_round[b] == r], "psf_idx": 0,
+                    "excitation_um": 0.488, "emission_um": 0.520}
+            if stage_origin_zyx_um is not None:
+                meta["stage_zyx_um"] = [float(v) for v in stage_origin_zyx_um]
+                meta["affine_zyx_px"] = np.asarray(
+                    np.eye(4) if camera_to_stage_affine is None else camera_to_stage_affine, dtype=float)
+            xf = (round_transforms_zyx_um or {}).get(r)
+            meta["local_round_transform_zyx_um"] = np.eye(4) if xf is None else np.asarray(xf, dtype=float)
+            if r == 1 and global_xform is not None:
+                aff, org, spc = global_xform
+                meta.update(affine_zyx_um=np.asarray(aff, dtype=float), origin_zyx_um=np.asarray(org, dtype=float),
+                            spacing_zyx_um=np.asarray(spc, dtype=float))
+            root = self._fiducial_root_path / tile_id / rid
+            self._save_entity_attributes(root, meta)
+            if sofima_flow_fields and r in sofima_flow_fields:
+                field, fattrs = sofima_flow_fields[r]
+                write_ome_image(root / "local_sofima_flow_field", np.asarray(field, dtype=np.float32),
+                                compression=compression, extra_attributes=dict(fattrs))
+        self._entity_cache.clear()
+        return tile_id

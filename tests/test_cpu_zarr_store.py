@@ -1,0 +1,239 @@
+"""Image store without a GPU: the C library's Blosc / Zarr v3 host decoder and encoder against the
+NumPy + pyarrow oracle (an independent implementation: different shuffle code, different zstd / lz4 builds),
+the datastore's metadata conventions, and malformed input."""
+
+import json
+import struct
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from merfish3d_analysis_b200 import _capi, zarr_store as zs
+from oracle import zarr_oracle as zo
+
+
+def _image(rng, shape, dtype):
+    if np.dtype(dtype).kind == "f":
+        return (rng.gamma(2.0, 50.0, shape) * (rng.random(shape) > 0.3)).astype(dtype)
+    return rng.poisson(180, shape).astype(dtype)
+
+
+@pytest.mark.parametrize("typesize", [1, 2, 4, 8])
+def test_blosc_frames_both_ways(typesize):
+    rng = np.random.default_rng(typesize)
+    for n in (0, 5, 127, 128, 1000, 33000):
+        data = rng.integers(0, 30, n * typesize, dtype=np.uint8).tobytes()
+        for cname in ("zstd", "lz4"):
+            for shuffle in ("noshuffle", "shuffle", "bitshuffle"):
+                for blocksize in (0, 2048 * typesize, 1000 * typesize):
+                    for split in (None, True, False):  # lz4 frames are split into `typesize` streams by c-blosc
+                        frame = zo.blosc_compress(data, typesize, cname=cname, shuffle=shuffle, blocksize=blocksize,
+                                                  split=split)
+                        assert _capi.blosc_decode_host(frame) == data, (n, cname, shuffle, blocksize, split)
+                    mine = _capi.blosc_encode_host(data, typesize, cname, 5, shuffle, blocksize)
+                    assert zo.blosc_decompress(mine) == data, (n, cname, shuffle, blocksize)
+                    info = _capi.blosc_info(mine)
+                    assert info["nbytes"] == len(data) and info["typesize"] == typesize and info["cbytes"] == len(mine)
+
+
+def test_bitshuffle_layout_known_answer():
+    # element j of 8 uint16 carries bit j in its low byte and bit (7 - j) in its high byte: row (byte b, bit i) of the
+    # bit-shuffled block is one byte whose bit j says whether element j has bit i of byte b set
+    elems = np.array([(1 << j) | (1 << (15 - j)) for j in range(8)], dtype="<u2")
+    rows = np.frombuffer(zo.bit_shuffle(elems.tobytes(), 2), dtype=np.uint8)
+    assert rows.tolist() == [1 << i for i in range(8)] + [1 << (7 - i) for i in range(8)]
+    frame = zo.blosc_compress(np.tile(elems, 64).tobytes(), 2)
+    assert _capi.blosc_decode_host(frame) == np.tile(elems, 64).tobytes()
+    assert zo.crc32c(b"123456789") == 0xE3069283 == zs.crc32c(b"123456789")
+
+
+def test_zstd_codec_both_ways():
+    data = np.random.default_rng(0).poisson(3, 50000).astype(np.uint8).tobytes()
+    assert zo._decompress(4, _capi.zstd_host(data, True), len(data)) == data
+    assert _capi.zstd_host(zo._compress("zstd", data, 3), False, len(data)) == data
+
+
+CASES = [
+    ((37, 150, 140), np.uint16, (16, 64, 64), "blosc-zstd", None),
+    ((37, 150, 140), np.uint16, (16, 64, 64), "blosc-lz4", None),
+    ((20, 70, 90), np.float32, (8, 32, 48), "blosc-zstd", None),
+    ((20, 70, 90), np.float32, (8, 32, 48), "zstd", None),
+    ((9, 33, 31), np.uint16, (4, 16, 16), "none", None),
+    ((37, 150, 140), np.uint16, (8, 32, 32), "blosc-zstd", (16, 64, 64)),
+    ((5, 40, 40), np.uint16, None, "blosc-zstd", None),  # reference default chunks, clipped to the image
+    ((3, 6, 40, 44), np.float32, (1, 4, 16, 16), "blosc-zstd", None),  # SOFIMA flow field layout
+    ((50, 60), np.uint16, (32, 32), "blosc-zstd", None),
+    ((17, 19, 23), np.uint8, (8, 8, 8), "blosc-zstd", None),
+]
+
+
+@pytest.mark.parametrize("shape,dtype,chunks,compression,shards", CASES)
+def test_reader_matches_oracle_written_images(tmp_path, shape, dtype, chunks, compression, shards):
+    rng = np.random.default_rng(len(shape) * 7 + shape[-1])
+    a = _image(rng, shape, dtype)
+    zo.write_ome_image(tmp_path / "img.ome.zarr", a, chunks=chunks, compression=compression, shards=shards,
+                       extra_attributes={"round_linker": 2, "emission_um": 0.67})
+    img = zs.ZarrImage(tmp_path / "img.ome.zarr")
+    assert img.shape == a.shape and img.dtype == a.dtype
+    np.testing.assert_array_equal(np.asarray(img), a)
+    assert img.extra_attributes == {"round_linker": 2, "emission_um": 0.67}
+    if a.ndim == 3:  # z windows touch only their chunks and crop them
+        for z0, z1 in ((0, 1), (3, min(11, shape[0])), (shape[0] - 2, shape[0]), (4, 4)):
+            np.testing.assert_array_equal(img.read(z0, z1), a[z0:z1])
+            np.testing.assert_array_equal(img[z0:z1], a[z0:z1])
+        np.testing.assert_array_equal(img[2], a[2])
+
+
+@pytest.mark.parametrize("shape,dtype,chunks,compression,shards", CASES)
+def test_writer_is_read_by_the_oracle(tmp_path, shape, dtype, chunks, compression, shards):
+    rng = np.random.default_rng(11)
+    a = _image(rng, shape, dtype)
+    zs.write_ome_image(tmp_path / "img", a, chunks=chunks, compression=compression, shards=shards,
+                       extra_attributes={"psf_idx": 1})
+    b, attrs = zo.read_ome_image(tmp_path / "img.ome.zarr")
+    np.testing.assert_array_equal(b, a)
+    assert attrs == {"psf_idx": 1}
+    np.testing.assert_array_equal(np.asarray(zs.ZarrImage(tmp_path / "img.ome.zarr")), a)
+    meta = json.loads((tmp_path / "img.ome.zarr" / "zarr.json").read_text())
+    assert meta["attributes"]["ome"]["version"] == "0.5"
+    assert meta["attributes"]["ome"]["multiscales"][0]["datasets"][0]["path"] == "0"
+
+
+def test_unwritten_chunks_are_fill_value(tmp_path):
+    a = np.zeros((20, 64, 64), dtype=np.uint16)
+    a[:8, :32, :32] = 7
+    for shards in (None, (16, 64, 64)):
+        p = tmp_path / f"s{shards is not None}"
+        zo.write_zarr3_array(p / "0", a, (8, 32, 32), shards=shards, skip_fill_chunks=True)
+        (p / "zarr.json").write_text(json.dumps({"zarr_format": 3, "node_type": "group", "attributes": {}}))
+        np.testing.assert_array_equal(np.asarray(zs.ZarrImage(p)), a)
+    # a whole shard file missing
+    (tmp_path / "sTrue" / "0" / "c" / "1" / "0" / "0").unlink()
+    np.testing.assert_array_equal(np.asarray(zs.ZarrImage(tmp_path / "sTrue"))[16:], 0)
+
+
+def test_malformed_input_raises(tmp_path):
+    a = np.random.default_rng(0).poisson(100, (16, 64, 64)).astype(np.uint16)
+    zo.write_ome_image(tmp_path / "img.ome.zarr", a, chunks=(16, 32, 32))
+    f = tmp_path / "img.ome.zarr" / "0" / "c" / "0" / "1" / "0"
+    good = f.read_bytes()
+    for bad in (good[: len(good) // 2], good[:10], b"", good[:16] + bytes(len(good) - 16),
+                struct.pack("<BBBBIII", 2, 1, 0x94, 2, 32768, 4096, len(good)) + good[16:]):
+        f.write_bytes(bad)
+        with pytest.raises(_capi.M3dError):
+            np.asarray(zs.ZarrImage(tmp_path / "img.ome.zarr"))
+    f.write_bytes(good)
+    np.testing.assert_array_equal(np.asarray(zs.ZarrImage(tmp_path / "img.ome.zarr")), a)
+    # what the reader does not handle is refused when the metadata is read, not guessed at
+    mp = tmp_path / "img.ome.zarr" / "0" / "zarr.json"
+    meta = json.loads(mp.read_text())
+    for key, val in (("codecs", [{"name": "bytes", "configuration": {"endian": "big"}}]),
+                     ("codecs", [{"name": "transpose", "configuration": {"order": [2, 1, 0]}}, {"name": "bytes"}]),
+                     ("codecs", [{"name": "bytes"}, {"name": "gzip", "configuration": {"level": 5}}]),
+                     ("chunk_grid", {"name": "rectilinear", "configuration": {}}),
+                     ("data_type", "complex64")):
+        mp.write_text(json.dumps(dict(meta, **{key: val})))
+        with pytest.raises(ValueError):
+            zs.ZarrImage(tmp_path / "img.ome.zarr")
+    with pytest.raises(FileNotFoundError):
+        zs.ZarrImage(tmp_path / "nothing.ome.zarr")
+
+
+def _codebook(n_bits=8):
+    rows = [["gene%d" % i] + [int((i >> b) & 1) for b in range(n_bits)] for i in range(1, 6)]
+    return pd.DataFrame(rows, columns=["gene_id"] + [f"bit{i:02d}" for i in range(1, n_bits + 1)])
+
+
+def test_datastore_reference_layout_round_trip(tmp_path):
+    rng = np.random.default_rng(5)
+    cb = _codebook()
+    ds = zs.Qi2labZarrDataStore.create(tmp_path / "qi2labdatastore", cb, voxel_size_zyx_um=(0.3, 0.1, 0.1))
+    ro = rng.poisson(150, (8, 6, 40, 48)).astype(np.uint16)
+    pr = rng.random((8, 6, 40, 48)).astype(np.float32)
+    xf = np.eye(4)
+    xf[:3, 3] = (0.1, -0.2, 0.3)
+    flow = rng.normal(0, 0.2, (3, 2, 5, 6)).astype(np.float32)
+    ds.add_tile(ro, pr, stage_origin_zyx_um=(1.0, 2.0, 3.0), global_xform=(np.eye(4), (4, 5, 6), (0.3, 0.1, 0.1)),
+                wavelengths_um=[(0.561, 0.58)] * 4 + [(0.638, 0.67)] * 4, bit_round=[1, 1, 2, 2, 1, 1, 2, 2],
+                round_transforms_zyx_um={2: xf}, chunks=(4, 16, 16),
+                sofima_flow_fields={2: (flow, {"block_size": [8, 8, 8], "block_stride": [4, 4, 4]})})
+    ds.add_tile(ro[:, ::-1].copy(), None, chunks=(4, 16, 16), bit_round=[1, 1, 2, 2, 1, 1, 2, 2])
+
+    again = zs.Qi2labZarrDataStore(tmp_path / "qi2labdatastore", validate=True)
+    assert again.tile_ids == ["tile0000", "tile0001"] and len(again.bit_ids) == 8
+    assert again.round_ids == ["round001", "round002"]
+    pd.testing.assert_frame_equal(again.codebook, cb, check_dtype=False)
+    np.testing.assert_allclose(again.voxel_size_zyx_um, (0.3, 0.1, 0.1))
+    # layout of docs/datastore.md:211-300
+    root = tmp_path / "qi2labdatastore"
+    assert (root / "readouts/tile0000/bit003/corrected_data.ome.zarr/0/zarr.json").exists()
+    assert (root / "readouts/tile0000/bit003/feature_predictor_data.ome.zarr/zarr.json").exists()
+    assert (root / "fiducial/tile0000/round002/local_sofima_flow_field.ome.zarr/0/zarr.json").exists()
+    assert (root / "fiducial/tile0000/round001/attributes.json").exists()
+    for b in range(8):
+        img = again.load_local_readout_image("tile0000", b)
+        np.testing.assert_array_equal(np.asarray(img.result()), ro[b])
+        np.testing.assert_array_equal(np.asarray(again.load_local_feature_predictor_image(0, b, return_future=False)),
+                                      pr[b])
+    assert type(again.load_local_feature_predictor_image("tile0001", 0)).__name__ == "UnitPredictor"
+    assert again.load_local_round_linker("tile0000", "bit003") == 2
+    assert again.load_local_wavelengths_um("tile0000", bit="bit005") == (0.638, 0.67)
+    stage, cam = again.load_local_stage_position_zyx_um("tile0000", round=0)
+    np.testing.assert_allclose(stage, (1, 2, 3))
+    np.testing.assert_allclose(cam, np.eye(4))
+    np.testing.assert_allclose(again.load_local_round_transform_zyx_um("tile0000", "round002"), xf, rtol=1e-6)
+    aff, org, spc = again.load_global_coord_xforms_um("tile0000")
+    np.testing.assert_allclose(org, (4, 5, 6))
+    assert again.load_global_coord_xforms_um("tile0001") == (None, None, None)
+    f2, fattrs = again.load_local_sofima_flow_field("tile0000", "round002")
+    np.testing.assert_array_equal(f2, flow)
+    assert fattrs["block_size"] == [8, 8, 8]
+    assert again.load_local_sofima_flow_field("tile0000", "round001") is None
+    assert not again.has_identity_decode_transforms
+    np.testing.assert_array_equal(again.load_chromatic_affine_transform_zyx_um(wavelength_um=0.67), np.eye(4))
+    # decon_data wins over corrected_data (DS:4709-4745)
+    zo.write_ome_image(root / "readouts/tile0001/bit001/decon_data.ome.zarr", ro[0] + 1, chunks=(4, 16, 16))
+    np.testing.assert_array_equal(np.asarray(again.load_local_readout_image("tile0001", "bit001")), ro[0] + 1)
+    # decode-stage outputs keep working on this store (inherited, same files as the reference)
+    again.save_decode_normalization_vectors(None, "global", np.ones(8), np.zeros(8))
+    nv, bv = zs.Qi2labZarrDataStore(root).load_decode_normalization_vectors(None, "global")
+    np.testing.assert_array_equal(nv, np.ones(8, dtype=np.float32))
+
+
+def test_store_written_in_reference_conventions_by_hand(tmp_path):
+    """A store assembled file by file the way the reference's conversion stage leaves it (metadata split between image
+    extra attributes and sidecars, DS:1860-1901) opens without this package's writer."""
+    root = tmp_path / "qi2labdatastore"
+    cb = _codebook(4)
+    (root / "calibrations").mkdir(parents=True)
+    (root / "datastore_state.json").write_text(json.dumps({"Version": 0.6, "Initialized": True, "Calibrations": True,
+                                                           "Corrected": True}))
+    (root / "calibrations" / "attributes.json").write_text(json.dumps({
+        "num_rounds": 2, "num_tiles": 1, "num_bits": 4, "codebook": cb.to_numpy(dtype=object).tolist(),
+        "voxel_size_zyx_um": [0.315, 0.098, 0.098], "microscope_type": "3D",
+        "chromatic_affine_transforms_zyx_um": {"channels": {"far_red": {
+            "channel_index": 2, "wavelength_um": 0.67, "affine_zyx_um": (np.eye(4) * 1.001).tolist()}}}}))
+    rng = np.random.default_rng(2)
+    vols = rng.poisson(90, (4, 18, 40, 36)).astype(np.uint16)
+    for b in range(4):
+        d = root / "readouts" / "tile0000" / f"bit{b + 1:03d}"
+        zo.write_ome_image(d / "corrected_data.ome.zarr", vols[b], extra_attributes={
+            "round_linker": 1 + b // 2, "excitation_um": 0.638, "psf_idx": 2})
+        (d / "attributes.json").write_text(json.dumps({"emission_um": 0.67}))  # the sidecar completes / overrides
+    for r in (1, 2):
+        d = root / "fiducial" / "tile0000" / f"round{r:03d}"
+        d.mkdir(parents=True)
+        (d / "attributes.json").write_text(json.dumps({
+            "stage_zyx_um": [0, 10, 20], "affine_zyx_px": np.eye(4).tolist(),
+            "local_round_transform_zyx_um": np.eye(4).tolist(), "bit_linker": [2 * r - 1, 2 * r]}))
+    ds = zs.Qi2labZarrDataStore(root, validate=True)
+    assert ds.bit_ids == ["bit001", "bit002", "bit003", "bit004"]
+    assert ds.load_local_wavelengths_um(0, bit=3) == (0.638, 0.67)
+    assert ds.load_local_round_linker(0, 3) == 2
+    np.testing.assert_array_equal(np.asarray(ds.load_local_readout_image(0, 2)), vols[2])
+    np.testing.assert_allclose(ds.load_chromatic_affine_transform_zyx_um(wavelength_um=0.67), np.eye(4) * 1.001)
+    np.testing.assert_array_equal(ds.load_chromatic_affine_transform_zyx_um(wavelength_um=0.52), np.eye(4))
+    assert not ds.has_identity_decode_transforms
+    with pytest.raises(FileNotFoundError):
+        zs.Qi2labZarrDataStore(tmp_path / "elsewhere")
