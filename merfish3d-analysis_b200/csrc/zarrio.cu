@@ -282,10 +282,120 @@ inline int64_t group_count(const ChunkGeom& g, int ts) {
     return nblocks * ((nb + 7) >> 3);
 }
 
+// Host path (NumPy destinations).  Two passes per chunk: un-shuffle block by block into a linear copy of the chunk
+// (bit shuffle: 64 elements at a time -- an 8 x 8 byte transpose gathers, for each of 8 groups, its byte from the 8
+// bit rows, then the 8 x 8 bit transpose), then copy the chunk's x-runs into the destination, clipped.
+inline void transpose_bytes8x8(uint64_t r[8]) {
+    uint64_t t;
+    for (int i = 0; i < 8; i += 2) {
+        t = ((r[i] >> 8) ^ r[i + 1]) & 0x00FF00FF00FF00FFull;
+        r[i + 1] ^= t;
+        r[i] ^= t << 8;
+    }
+    for (int i = 0; i < 8; i += 4)
+        for (int k = 0; k < 2; ++k) {
+            t = ((r[i + k] >> 16) ^ r[i + k + 2]) & 0x0000FFFF0000FFFFull;
+            r[i + k + 2] ^= t;
+            r[i + k] ^= t << 16;
+        }
+    for (int i = 0; i < 4; ++i) {
+        t = ((r[i] >> 32) ^ r[i + 4]) & 0x00000000FFFFFFFFull;
+        r[i + 4] ^= t;
+        r[i] ^= t << 32;
+    }
+}
+
+// bytes of a and b alternating (a0 b0 a1 b1 ...): w[0] from their low halves, w[1] from their high halves
+inline uint64_t spread_bytes(uint64_t x) {
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+    return (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+}
+inline void interleave_bytes(uint64_t a, uint64_t b, uint64_t w[2]) {
+    w[0] = spread_bytes(a & 0xFFFFFFFFull) | (spread_bytes(b & 0xFFFFFFFFull) << 8);
+    w[1] = spread_bytes(a >> 32) | (spread_bytes(b >> 32) << 8);
+}
+
+template <int TS>
+void unshuffle_block_host(const uint8_t* blk, int64_t n_elem, int mode, uint8_t* lin) {
+    if (mode == SH_NONE) {
+        memcpy(lin, blk, (size_t)(n_elem * TS));
+        return;
+    }
+    if (mode == SH_BYTE) {
+        for (int b = 0; b < TS; ++b) {
+            const uint8_t* plane = blk + (int64_t)b * n_elem;
+            for (int64_t e = 0; e < n_elem; ++e) lin[e * TS + b] = plane[e];
+        }
+        return;
+    }
+    const int64_t n8 = n_elem & ~(int64_t)7, row = n8 >> 3;
+    int64_t k = 0;
+    for (; k + 8 <= row; k += 8) {  // groups k .. k+7 = elements 8k .. 8k+63
+        uint64_t y[TS][8];
+        for (int b = 0; b < TS; ++b) {
+            uint64_t r[8];
+            for (int i = 0; i < 8; ++i) memcpy(&r[i], blk + (int64_t)(b * 8 + i) * row + k, 8);
+            transpose_bytes8x8(r);  // r[g]: byte i = bit row i of group k+g
+            for (int g = 0; g < 8; ++g) y[b][g] = transpose8x8(r[g]);  // byte j = byte b of element 8(k+g)+j
+        }
+        uint8_t* o = lin + 8 * k * TS;
+        for (int g = 0; g < 8; ++g) {  // element j of the group = bytes j of y[0..TS-1][g], interleaved
+            if (TS == 1) {
+                memcpy(o + g * 8, &y[0][g], 8);
+            } else if (TS == 2) {
+                uint64_t w[2];
+                interleave_bytes(y[0][g], y[1 % TS][g], w);
+                memcpy(o + g * 16, w, 16);
+            } else if (TS == 4) {
+                uint64_t a[2], c[2], w[4];
+                interleave_bytes(y[0][g], y[2 % TS][g], a);  // (b0, b2) pairs
+                interleave_bytes(y[1 % TS][g], y[3 % TS][g], c);  // (b1, b3) pairs
+                interleave_bytes(a[0], c[0], w);
+                interleave_bytes(a[1], c[1], w + 2);
+                memcpy(o + g * 32, w, 32);
+            } else {
+                for (int j = 0; j < 8; ++j)
+                    for (int b = 0; b < TS; ++b) o[(g * 8 + j) * TS + b] = (uint8_t)(y[b][g] >> (8 * j));
+            }
+        }
+    }
+    for (; 8 * k < n_elem; ++k) {  // the last groups of the rows and the elements past n8 (stored plain)
+        uint8_t v[8][TS];
+        fetch_group<TS>(blk, n_elem, mode, k, v);
+        const int64_t left = n_elem - 8 * k;
+        for (int j = 0; j < (left < 8 ? (int)left : 8); ++j)
+            for (int b = 0; b < TS; ++b) lin[(8 * k + j) * TS + b] = v[j][b];
+    }
+}
+
 template <int TS>
 void unshuffle_place_host(const uint8_t* staged, const ChunkGeom& g, uint8_t* dst) {
-    const int64_t n = group_count(g, TS);
-    for (int64_t t = 0; t < n; ++t) unshuffle_place_group<TS>(staged, g, t, dst);
+    const int64_t total = g.nbytes / TS;
+    const int64_t nb = g.blocksize / TS;
+    const uint8_t* lin = staged;
+    std::vector<uint8_t> tmp;
+    if (g.mode != SH_NONE) {
+        tmp.resize((size_t)g.nbytes);
+        for (int64_t first = 0, j = 0; first < total; first += nb, ++j)
+            unshuffle_block_host<TS>(staged + j * g.blocksize, total - first < nb ? total - first : nb, g.mode,
+                                     tmp.data() + first * TS);
+        lin = tmp.data();
+    }
+    // x-runs of the chunk that fall inside the destination
+    const int64_t x0 = g.origin[2] < 0 ? -g.origin[2] : 0;
+    int64_t x1 = g.cshape[2];
+    if (g.origin[2] + x1 > g.dshape[2]) x1 = g.dshape[2] - g.origin[2];
+    if (x1 <= x0) return;
+    for (int64_t cz = 0; cz < g.cshape[0]; ++cz) {
+        const int64_t z = g.origin[0] + cz;
+        if (z < 0 || z >= g.dshape[0]) continue;
+        for (int64_t cy = 0; cy < g.cshape[1]; ++cy) {
+            const int64_t y = g.origin[1] + cy;
+            if (y < 0 || y >= g.dshape[1]) continue;
+            memcpy(dst + ((z * g.dshape[1] + y) * g.dshape[2] + g.origin[2] + x0) * TS,
+                   lin + ((cz * g.cshape[1] + cy) * g.cshape[2] + x0) * TS, (size_t)((x1 - x0) * TS));
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------ chunk sources
