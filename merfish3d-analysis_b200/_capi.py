@@ -169,28 +169,69 @@ class ZarrChunk(C.Structure):
     ]
 
 
-def zarr_chunk_array(chunks):
-    """ctypes array of ``m3d_zarr_chunk`` from dicts with the struct's field names."""
-    arr = (ZarrChunk * len(chunks))()
-    for rec, c in zip(arr, chunks):
-        rec.path = c["path"].encode() if isinstance(c["path"], str) else c["path"]
-        rec.offset, rec.length = int(c.get("offset", 0)), int(c.get("length", -1))
-        rec.codec, rec.elem_size = int(c["codec"]), int(c["elem_size"])
-        rec.chunk_shape = _c_i64_3(*[int(v) for v in c["chunk_shape"]])
-        rec.origin = _c_i64_3(*[int(v) for v in c["origin"]])
-        rec.dst = int(c["dst"])
-        rec.dst_shape = _c_i64_3(*[int(v) for v in c["dst_shape"]])
-        rec.fill_bits = int(c.get("fill_bits", 0))
-        rec.piece = int(c.get("piece", 0))
-    return arr
+# the same record as a NumPy structured dtype: chunk tables of whole tiles are built with array arithmetic
+ZARR_CHUNK_DTYPE = np.dtype({
+    "names": ["path", "offset", "length", "codec", "elem_size", "chunk_shape", "origin", "dst", "dst_shape",
+              "fill_bits", "piece", "reserved"],
+    "formats": ["<u8", "<i8", "<i8", "<i4", "<i4", ("<i8", 3), ("<i8", 3), "<u8", ("<i8", 3), "<u8", "<i4", "<i4"],
+    "offsets": [0, 8, 16, 24, 28, 32, 56, 80, 88, 112, 120, 124],
+    "itemsize": 128,
+})
+assert C.sizeof(ZarrChunk) == ZARR_CHUNK_DTYPE.itemsize
+
+
+class ChunkTable:
+    """``m3d_zarr_chunk[n]`` as a structured array + the NUL-terminated path strings its pointers refer to."""
+
+    def __init__(self, records: np.ndarray, path_blobs: list):
+        self.records = records
+        self.path_blobs = path_blobs  # keep-alive
+
+    def __len__(self):
+        return int(self.records.shape[0])
+
+    @staticmethod
+    def from_paths(paths: list[str], n: int) -> "ChunkTable":
+        """n zeroed records whose ``path`` fields point at ``paths`` (len n)."""
+        enc = [p.encode() for p in paths]
+        blob = np.frombuffer(b"\0".join(enc) + b"\0", dtype=np.uint8)
+        starts = np.zeros(n, dtype=np.uint64)
+        if n > 1:
+            starts[1:] = np.cumsum([len(e) + 1 for e in enc[:-1]], dtype=np.uint64)
+        rec = np.zeros(n, dtype=ZARR_CHUNK_DTYPE)
+        rec["path"] = np.uint64(blob.ctypes.data) + starts
+        return ChunkTable(rec, [blob])
+
+    @staticmethod
+    def from_dicts(chunks) -> "ChunkTable":
+        t = ChunkTable.from_paths([c["path"] for c in chunks], len(chunks))
+        r = t.records
+        for k in ("offset", "length", "codec", "elem_size", "dst", "fill_bits", "piece"):
+            default = {"offset": 0, "length": -1, "fill_bits": 0, "piece": 0}.get(k)
+            r[k] = [c.get(k, default) for c in chunks]
+        for k in ("chunk_shape", "origin", "dst_shape"):
+            r[k] = np.asarray([c[k] for c in chunks], dtype=np.int64).reshape(len(chunks), 3)
+        return t
+
+    @staticmethod
+    def concatenate(tables) -> "ChunkTable":
+        tables = [t for t in tables if len(t)]
+        if not tables:
+            return ChunkTable(np.zeros(0, dtype=ZARR_CHUNK_DTYPE), [])
+        return ChunkTable(np.ascontiguousarray(np.concatenate([t.records for t in tables])),
+                          [b for t in tables for b in t.path_blobs])
+
+
+def _as_chunk_table(chunks) -> ChunkTable:
+    return chunks if isinstance(chunks, ChunkTable) else ChunkTable.from_dicts(list(chunks))
 
 
 def zarr_read_chunks_host(chunks) -> None:
     """Decode chunks into HOST destinations (``dst`` = host addresses); needs no GPU."""
-    if not chunks:
-        return
-    arr = zarr_chunk_array(chunks)
-    _check(load_library().m3d_zarr_read_chunks_host(len(chunks), C.cast(arr, C.c_void_p)), "m3d_zarr_read_chunks_host")
+    t = _as_chunk_table(chunks)
+    if len(t):
+        _check(load_library().m3d_zarr_read_chunks_host(len(t), C.c_void_p(t.records.ctypes.data)),
+               "m3d_zarr_read_chunks_host")
 
 
 def blosc_info(frame: bytes) -> dict:
@@ -400,9 +441,9 @@ class DecodeContext:
     def zarr_read(self, chunks, on_piece=None):
         """``m3d_zarr_read_chunks``: decode the listed chunks (dicts with the ``m3d_zarr_chunk`` fields, ``dst`` a
         device address) into their device volumes on the current stream.  ``on_piece(i)`` as in :meth:`upload`."""
-        if not chunks:
+        t = _as_chunk_table(chunks)
+        if not len(t):
             return
-        arr = zarr_chunk_array(chunks)
         failure = []
 
         def trampoline(piece, _user):
@@ -414,7 +455,7 @@ class DecodeContext:
                 failure.append(e)
 
         cb = _PIECE_CB(trampoline)
-        rc = self._lib.m3d_zarr_read_chunks(self._h, len(chunks), C.cast(arr, C.c_void_p), _stream(self.device),
+        rc = self._lib.m3d_zarr_read_chunks(self._h, len(t), C.c_void_p(t.records.ctypes.data), _stream(self.device),
                                             C.cast(cb, C.c_void_p), None)
         if failure:
             raise failure[0]

@@ -225,6 +225,44 @@ class ZarrArray:
                                     out.append(rec)
         return out
 
+    def chunk_table(self, dst_addr: int, z0: int = 0, z1: int | None = None, piece: int = 0) -> "_capi.ChunkTable":
+        """:meth:`chunk_records` as a ``ChunkTable``; un-sharded arrays (the reference's default) are listed with
+        array arithmetic, one Python string per chunk file being the only per-chunk work."""
+        if self.sharded:
+            return _capi.ChunkTable.from_dicts(self.chunk_records(dst_addr, z0, z1, piece))
+        vz, vy, vx = self.volume_shape
+        z1 = vz if z1 is None else int(z1)
+        z0 = int(z0)
+        if not 0 <= z0 <= z1 <= vz:
+            raise ValueError(f"z window [{z0}, {z1}) outside 0..{vz}")
+        if z1 == z0:
+            return _capi.ChunkTable.from_dicts([])
+        nd3 = min(self.ndim, 3)
+        cz, cy, cx = (1,) * (3 - nd3) + tuple(self.chunks[-nd3:])
+        iz = np.arange(z0 // cz, (z1 - 1) // cz + 1)
+        iy, ix = np.arange(-(-vy // cy)), np.arange(-(-vx // cx))
+        leads = list(np.ndindex(*self.lead_shape))
+        n3 = iz.size * iy.size * ix.size
+        gz, gy, gx = (g.reshape(-1) for g in np.meshgrid(iz, iy, ix, indexing="ij"))
+        base = str(self.path) + "/" if self._prefix is None else f"{self.path}/{self._prefix}{self._sep}"
+        sep = self._sep
+        keep = (slice(None), slice(1, None), slice(2, None))[3 - nd3]
+        paths = []
+        for lead in leads:
+            head = base + "".join(f"{i}{sep}" for i in lead)
+            cols = [gz.tolist(), gy.tolist(), gx.tolist()][keep]
+            paths += [head + sep.join(map(str, idx)) for idx in zip(*cols)]
+        t = _capi.ChunkTable.from_paths(paths, n3 * len(leads))
+        r = t.records
+        dst_shape = (z1 - z0, vy, vx)
+        vol_bytes = int(np.prod(dst_shape)) * self.dtype.itemsize
+        r["length"], r["codec"], r["elem_size"] = -1, self.codec, self.dtype.itemsize
+        r["chunk_shape"], r["dst_shape"] = (cz, cy, cx), dst_shape
+        r["fill_bits"], r["piece"] = self.fill_bits, piece
+        r["origin"] = np.tile(np.stack([gz * cz - z0, gy * cy, gx * cx], axis=1), (len(leads), 1))
+        r["dst"] = np.uint64(dst_addr) + np.repeat(np.arange(len(leads), dtype=np.uint64) * np.uint64(vol_bytes), n3)
+        return t
+
     def read(self, z0: int = 0, z1: int | None = None) -> np.ndarray:
         """Host array of planes [z0, z1) (all leading indices), decoded by the C library on host threads."""
         vz = self.volume_shape[0]
@@ -233,7 +271,7 @@ class ZarrArray:
         shape = self.lead_shape + ((z1 - z0,) + self.volume_shape[1:])[3 - nd3 :]
         out = np.empty(shape, dtype=self.dtype)
         if out.size:
-            _capi.zarr_read_chunks_host(self.chunk_records(out.ctypes.data, z0, z1))
+            _capi.zarr_read_chunks_host(self.chunk_table(out.ctypes.data, z0, z1))
         return out
 
 
@@ -317,7 +355,7 @@ def transfer(ctx, pieces, on_piece=None) -> None:
         if not lazy:
             ctx.upload(run, on_piece=cb)
         else:
-            records = []
+            tables = []
             empty = []
             for k, (src, dst) in enumerate(run):
                 if isinstance(src, ZarrImage):
@@ -326,12 +364,12 @@ def transfer(ctx, pieces, on_piece=None) -> None:
                 if not dst.is_cuda or not dst.is_contiguous() or dst.numel() * dst.element_size() != nbytes:
                     raise _capi.M3dError("transfer(): destination must be a contiguous device tensor of the source's size")
                 if isinstance(src, ZarrWindow):
-                    recs = src.image.array.chunk_records(dst.data_ptr(), src.z0, src.z1, piece=k)
+                    recs = src.image.array.chunk_table(dst.data_ptr(), src.z0, src.z1, piece=k)
                 else:
-                    recs = src.array.chunk_records(dst.data_ptr(), piece=k)
-                if not recs:
+                    recs = src.array.chunk_table(dst.data_ptr(), piece=k)
+                if not len(recs):
                     empty.append(k)
-                records.extend(recs)
+                tables.append(recs)
             done = set()
 
             def note(k, cb=cb, done=done):
@@ -339,7 +377,7 @@ def transfer(ctx, pieces, on_piece=None) -> None:
                 if cb is not None:
                     cb(k)
 
-            ctx.zarr_read(records, on_piece=note)
+            ctx.zarr_read(_capi.ChunkTable.concatenate(tables), on_piece=note)
             for k in empty:  # zero-sized windows have no chunk to wait for
                 if k not in done and cb is not None:
                     cb(k)

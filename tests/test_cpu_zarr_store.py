@@ -237,3 +237,24 @@ def test_store_written_in_reference_conventions_by_hand(tmp_path):
     assert not ds.has_identity_decode_transforms
     with pytest.raises(FileNotFoundError):
         zs.Qi2labZarrDataStore(tmp_path / "elsewhere")
+
+
+@pytest.mark.parametrize("shape,chunks", [((37, 150, 140), (16, 64, 64)), ((3, 6, 40, 44), (1, 4, 16, 16)),
+                                          ((50, 60), (32, 32)), ((2, 3, 9, 20, 20), (1, 1, 4, 8, 8))])
+def test_vectorised_chunk_table_equals_the_record_list(tmp_path, shape, chunks):
+    import ctypes
+
+    zo.write_ome_image(tmp_path / "img.ome.zarr", np.zeros(shape, dtype=np.float32), chunks=chunks)
+    arr = zs.ZarrImage(tmp_path / "img.ome.zarr").array
+    vz = arr.volume_shape[0]
+    for z0, z1 in ((0, vz), (1, vz - 1), (vz // 2, vz // 2 + 1)):
+        if not 0 <= z0 < z1 <= vz:
+            continue
+        fast = arr.chunk_table(0x10000, z0, z1, piece=3)
+        slow = _capi.ChunkTable.from_dicts(arr.chunk_records(0x10000, z0, z1, piece=3))
+        assert len(fast) == len(slow) > 0
+        for name in _capi.ZARR_CHUNK_DTYPE.names:
+            if name != "path":
+                np.testing.assert_array_equal(fast.records[name], slow.records[name], err_msg=name)
+        paths = [[ctypes.string_at(int(p)).decode() for p in t.records["path"]] for t in (fast, slow)]
+        assert paths[0] == paths[1]
