@@ -60,6 +60,7 @@ enum M3dKernel {
     KF_RESET_FG,
     KF_ZARR_UNSHUFFLE,
     KF_ZARR_FILL,
+    KF_ZARR_LZ4,
     KF_COUNT
 };
 

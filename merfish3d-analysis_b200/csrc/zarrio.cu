@@ -90,6 +90,123 @@ bool parse_blosc_header(const uint8_t* p, size_t n, BloscHeader& h) {
     return h.typesize >= 1 && (h.nbytes == 0 || h.blocksize >= 1) && (size_t)h.cbytes <= n;
 }
 
+// ------------------------------------------------------------------------------------------ LZ4 blocks
+// One LZ4 block (the raw block format Blosc stores: token, literal run, 2-byte match offset, match run) decoded
+// by a team of lanes.  The parse is sequential and identical on every lane (all lanes read the same bytes);
+// the two copies are what the team shares.  A match may overlap its own output (offset < length): byte i of it
+// is byte (i mod offset) of the `offset` bytes before the match, which are all written before it starts, so the
+// lanes never wait for each other inside a copy.  HostLanes (one lane) runs the same parse on the CPU -- it is the
+// library's only LZ4 decoder, so the CPU tests exercise the code the GPU runs.  Every length is checked against
+// both buffers: the input is a file from disk.
+struct HostLanes {
+    static inline void copy(uint8_t* d, const uint8_t* s, int64_t n) { memcpy(d, s, (size_t)n); }
+    static inline void match(uint8_t* d, int64_t off, int64_t n) {
+        if (off >= n) memcpy(d, d - off, (size_t)n);
+        else for (int64_t i = 0; i < n; ++i) d[i] = d[i - off];
+    }
+    static inline void sync() {}
+};
+
+struct WarpLanes {
+    static __device__ inline void copy(uint8_t* d, const uint8_t* s, int64_t n) {
+        for (int64_t i = threadIdx.x & 31; i < n; i += 32) d[i] = s[i];
+    }
+    static __device__ inline void match(uint8_t* d, int64_t off, int64_t n) {
+        const uint8_t* src = d - off;
+        if (off >= n) {
+            for (int64_t i = threadIdx.x & 31; i < n; i += 32) d[i] = src[i];
+        } else {
+            const uint32_t o = (uint32_t)off;  // off < 65536
+            for (uint32_t i = threadIdx.x & 31; i < (uint32_t)n; i += 32) d[i] = src[i % o];  // n < 2^31
+        }
+    }
+    static __device__ inline void sync() { __syncwarp(); }
+};
+
+template <class L>
+__host__ __device__ inline bool lz4_decode_block(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t out_len) {
+    int64_t ip = 0, op = 0;
+    while (true) {
+        if (ip >= in_len) return false;  // a block ends with a literals-only sequence
+        const unsigned token = in[ip++];
+        int64_t lit = token >> 4;
+        if (lit == 15) {
+            unsigned b;
+            do {
+                if (ip >= in_len) return false;
+                b = in[ip++];
+                lit += b;
+            } while (b == 255);
+        }
+        if (lit > in_len - ip || lit > out_len - op) return false;
+        L::copy(out + op, in + ip, lit);
+        ip += lit;
+        op += lit;
+        if (ip == in_len) break;
+        if (in_len - ip < 2) return false;
+        const int64_t off = (int64_t)in[ip] | ((int64_t)in[ip + 1] << 8);
+        ip += 2;
+        if (off == 0 || off > op) return false;
+        int64_t ml = token & 15;
+        if (ml == 15) {
+            unsigned b;
+            do {
+                if (ip >= in_len) return false;
+                b = in[ip++];
+                ml += b;
+            } while (b == 255);
+        }
+        ml += 4;
+        if (ml > out_len - op) return false;
+        L::sync();  // the literals above and the previous match are visible to every lane
+        L::match(out + op, off, ml);
+        op += ml;
+    }
+    return op == out_len;
+}
+
+__host__ __device__ inline uint32_t le32_hd(const uint8_t* p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+// A Blosc-1 frame of LZ4 streams, decoded on the device: one warp per stream (block j, split s).  `frame` is the
+// chunk file as it sits on disk (the host only checked its 16-byte header); the warp finds its stream by
+// walking the block's length prefixes, then decodes -- or copies a stored stream -- into its place of the
+// still-shuffled chunk image `out`.  Anything inconsistent sets *error and the warp leaves.
+__global__ void __launch_bounds__(128) blosc_lz4_decode_kernel(const uint8_t* frame, int64_t frame_len, uint8_t* out,
+                                                                int splits_per_block, int* __restrict__ error) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int typesize = frame[3], flags = frame[2];
+    const int64_t nbytes = le32_hd(frame + 4), blocksize = le32_hd(frame + 8);
+    const int64_t nblocks = (nbytes + blocksize - 1) / blocksize, leftover = nbytes % blocksize;
+    const int64_t j = warp / splits_per_block;
+    const int s = (int)(warp - j * splits_per_block);
+    if (j >= nblocks) return;
+    const bool is_left = (j == nblocks - 1) && leftover > 0;
+    const int64_t bsize = is_left ? leftover : blocksize;
+    const int nsplits = (!(flags & FLAG_DONT_SPLIT) && typesize <= MAX_SPLITS && bsize / typesize >= MIN_BUFFERSIZE &&
+                         !is_left) ? typesize : 1;
+    if (s >= nsplits) return;
+    const int64_t neblock = bsize / nsplits;
+    bool ok = BLOSC_HEADER + 4 * nblocks <= frame_len;
+    int64_t pos = ok ? le32_hd(frame + BLOSC_HEADER + 4 * j) : 0;
+    int64_t cb = 0;
+    for (int t = 0; ok && t <= s; ++t) {  // length prefixes of the streams before ours, then ours
+        ok = pos >= BLOSC_HEADER && pos + 4 <= frame_len;
+        if (!ok) break;
+        cb = (int32_t)le32_hd(frame + pos);
+        pos += 4;
+        ok = cb >= 0 && pos + cb <= frame_len;
+        if (ok && t < s) pos += cb;
+    }
+    uint8_t* dst = out + j * blocksize + (int64_t)s * neblock;
+    if (ok) {
+        if (cb == neblock) WarpLanes::copy(dst, frame + pos, cb);
+        else ok = lz4_decode_block<WarpLanes>(frame + pos, cb, dst, neblock);
+    }
+    if (!ok && (threadIdx.x & 31) == 0) atomicExch(error, 1);
+}
+
 // how the decoded bytes of a chunk are still arranged when they reach the device
 enum ShuffleMode { SH_NONE = 0, SH_BYTE = 1, SH_BIT = 2 };
 
@@ -108,7 +225,6 @@ const char* blosc_decode_blocks(const uint8_t* frame, size_t n, const BloscHeade
     else if (h.flags & FLAG_BITSHUFFLE) *mode = SH_BIT;
     const HostCodecs& C = codecs();
     if (h.codec == BLOSC_ZSTD && !C.zstd_decompress) return "blosc: libzstd.so.1 is not available";
-    if (h.codec == BLOSC_LZ4 && !C.lz4_decompress) return "blosc: liblz4.so.1 is not available";
     if (h.codec != BLOSC_ZSTD && h.codec != BLOSC_LZ4) return "blosc: unsupported inner codec (zstd and lz4 only)";
     const int64_t nblocks = (h.nbytes + h.blocksize - 1) / h.blocksize;
     const int64_t leftover = h.nbytes % h.blocksize;
@@ -132,9 +248,7 @@ const char* blosc_decode_blocks(const uint8_t* frame, size_t n, const BloscHeade
                 const size_t r = C.zstd_decompress(dst, (size_t)neblock, frame + pos, (size_t)cb);
                 if (C.zstd_is_error(r) || r != (size_t)neblock) return "blosc: zstd stream is corrupt";
             } else {
-                const int r = C.lz4_decompress(reinterpret_cast<const char*>(frame + pos),
-                                               reinterpret_cast<char*>(dst), (int)cb, (int)neblock);
-                if (r != (int)neblock) return "blosc: lz4 stream is corrupt";
+                if (!lz4_decode_block<HostLanes>(frame + pos, cb, dst, neblock)) return "blosc: lz4 stream is corrupt";
             }
             pos += (size_t)cb;
             dst += neblock;
@@ -426,6 +540,17 @@ bool read_range(const char* path, int64_t offset, int64_t length, std::vector<ui
     return got == (size_t)length;
 }
 
+bool read_all(int fd, int64_t offset, int64_t length, std::vector<uint8_t>& buf) {
+    buf.resize((size_t)length);
+    int64_t got = 0;
+    while (got < length) {
+        const ssize_t r = pread(fd, buf.data() + got, (size_t)(length - got), (off_t)(offset + got));
+        if (r <= 0) break;
+        got += r;
+    }
+    return got == length;
+}
+
 struct Decoded {
     int mode = SH_NONE;
     int64_t blocksize = 0;
@@ -487,10 +612,16 @@ ChunkGeom geom_of(const m3d_zarr_chunk& c, const Decoded& d) {
 
 // ------------------------------------------------------------------------------------------ slot ring
 struct ZarrRing {
-    std::vector<void*> pinned, dev;
+    std::vector<void*> pinned;    // host slot: the decoded (still shuffled) chunk, or the chunk file itself (LZ4)
+    std::vector<void*> dev;       // device slot: the still-shuffled chunk image the un-shuffle kernel reads
+    std::vector<void*> dev_comp;  // device slot: the chunk file, for frames the GPU entropy-decodes
     std::vector<cudaEvent_t> drained;
+    std::vector<cudaStream_t> streams;  // one per slot: chunks in different slots overlap their copies and kernels
     std::vector<char> used;
     size_t slot_bytes = 0;
+    cudaEvent_t begin = nullptr;
+    int* d_error = nullptr;
+    int* h_error = nullptr;
 };
 
 std::mutex g_zring_mu;
@@ -505,37 +636,55 @@ ZarrRing* zring_of(m3d_ctx* ctx) {
     return r;
 }
 
-void zring_free(ZarrRing* r) {
+void zring_free_slots(ZarrRing* r) {
     for (size_t s = 0; s < r->pinned.size(); ++s) {
-        if (r->used[s]) cudaEventSynchronize(r->drained[s]);
-        cudaFreeHost(r->pinned[s]);
-        cudaFree(r->dev[s]);
-        cudaEventDestroy(r->drained[s]);
+        if (r->streams[s]) cudaStreamSynchronize(r->streams[s]);
+        if (r->pinned[s]) cudaFreeHost(r->pinned[s]);
+        if (r->dev[s]) cudaFree(r->dev[s]);
+        if (r->dev_comp[s]) cudaFree(r->dev_comp[s]);
+        if (r->drained[s]) cudaEventDestroy(r->drained[s]);
+        if (r->streams[s]) cudaStreamDestroy(r->streams[s]);
     }
     r->pinned.clear();
     r->dev.clear();
+    r->dev_comp.clear();
     r->drained.clear();
+    r->streams.clear();
     r->used.clear();
     r->slot_bytes = 0;
 }
 
+void zring_free(ZarrRing* r) {
+    zring_free_slots(r);
+    if (r->begin) cudaEventDestroy(r->begin);
+    if (r->d_error) cudaFree(r->d_error);
+    if (r->h_error) cudaFreeHost(r->h_error);
+    r->begin = nullptr;
+    r->d_error = r->h_error = nullptr;
+}
+
 int zring_ensure(ZarrRing* r, int n_slots, size_t slot_bytes) {
+    if (!r->begin) {
+        M3D_CUDA(cudaEventCreateWithFlags(&r->begin, cudaEventDisableTiming));
+        M3D_CUDA(cudaMalloc(reinterpret_cast<void**>(&r->d_error), sizeof(int)));
+        M3D_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&r->h_error), sizeof(int), cudaHostAllocDefault));
+    }
     if (r->slot_bytes >= slot_bytes && (int)r->pinned.size() >= n_slots) return M3D_OK;
     if (slot_bytes < r->slot_bytes) slot_bytes = r->slot_bytes;
     if (n_slots < (int)r->pinned.size()) n_slots = (int)r->pinned.size();
-    zring_free(r);
+    zring_free_slots(r);
     for (int s = 0; s < n_slots; ++s) {
-        void *h = nullptr, *d = nullptr;
-        cudaEvent_t ev = nullptr;
-        M3D_CUDA(cudaHostAlloc(&h, slot_bytes, cudaHostAllocDefault));
-        r->pinned.push_back(h);
+        r->pinned.push_back(nullptr);
         r->dev.push_back(nullptr);
+        r->dev_comp.push_back(nullptr);
         r->drained.push_back(nullptr);
+        r->streams.push_back(nullptr);
         r->used.push_back(0);
-        M3D_CUDA(cudaMalloc(&d, slot_bytes));
-        r->dev.back() = d;
-        M3D_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        r->drained.back() = ev;
+        M3D_CUDA(cudaHostAlloc(&r->pinned[s], slot_bytes, cudaHostAllocDefault));
+        M3D_CUDA(cudaMalloc(&r->dev[s], slot_bytes));
+        M3D_CUDA(cudaMalloc(&r->dev_comp[s], slot_bytes));
+        M3D_CUDA(cudaEventCreateWithFlags(&r->drained[s], cudaEventDisableTiming));
+        M3D_CUDA(cudaStreamCreateWithFlags(&r->streams[s], cudaStreamNonBlocking));
     }
     r->slot_bytes = slot_bytes;
     return M3D_OK;
@@ -840,24 +989,34 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
         if (b > slot_bytes) slot_bytes = b;
     }
     if (slot_bytes > ((size_t)1 << 30)) return m3d_fail(M3D_ERR_ARG, "m3d_zarr_read_chunks: chunk larger than 1 GiB");
+    slot_bytes += slot_bytes / 64 + 4096;  // room for a Blosc frame that did not compress (header, index, prefixes)
     int workers = io_threads();
     if (workers > n_chunks) workers = n_chunks;
-    // enough slots that every worker can decode while a few finished slots drain; bounded in bytes
-    int n_slots = workers + 4;
+    // Slots in flight.  A host-decoded chunk holds its slot for the decode (~5 ms) plus a short drain; a chunk the
+    // device decodes holds it for the file read plus ~1 ms of sequence-latency-bound LZ4 kernel, and it is the number
+    // of such kernels running side by side (one stream per slot) that fills the GPU: 3 per worker, bounded in bytes.
+    int n_slots = 3 * workers;
     while (n_slots > 3 && (size_t)n_slots * slot_bytes > ((size_t)768 << 20)) --n_slots;
     ZarrRing* R = zring_of(ctx);
     if (int rc = zring_ensure(R, n_slots, (slot_bytes + 255) & ~(size_t)255)) return rc;
     n_slots = (int)R->pinned.size();
+    const size_t slot_cap = R->slot_bytes;
 
-    // chunk j decodes into slot j % n_slots once chunk j - n_slots has been issued and its slot has drained
-    std::vector<char> staged((size_t)n_chunks, 0), issued((size_t)n_chunks, 0), absent((size_t)n_chunks, 0);
+    // Chunk j uses slot j % n_slots (and that slot's stream) once chunk j - n_slots has been issued and the slot has
+    // drained.  A worker leaves in the pinned slot either the entropy-decoded chunk (HOST: zstd, raw, stored) or the
+    // chunk file itself (GPU_LZ4: the device decodes it, so compressed bytes are what crosses PCIe).
+    enum Kind : char { HOST = 0, GPU_LZ4 = 1, MISSING = 2 };
+    std::vector<char> staged((size_t)n_chunks, 0), issued((size_t)n_chunks, 0), kind((size_t)n_chunks, HOST);
     std::vector<Decoded> info((size_t)n_chunks);
+    std::vector<int64_t> comp_len((size_t)n_chunks, 0);
+    std::vector<int> splits((size_t)n_chunks, 1);
     std::mutex mu;
     std::condition_variable cv;
     std::atomic<int> next{0};
     std::atomic<int> failed{0};
     std::string first_error;
     const int device = ctx->device;
+    const bool gpu_lz4 = getenv("M3D_ZARR_HOST_LZ4") == nullptr;
     auto fail = [&](const std::string& what) {
         {
             std::lock_guard<std::mutex> lk(mu);
@@ -873,35 +1032,102 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
             const int j = next.fetch_add(1);
             if (j >= n_chunks || failed.load()) return;
             const m3d_zarr_chunk& c = chunks[j];
-            bool missing = false;
-            if (c.codec == M3D_ZARR_ABSENT) missing = true;
-            else if (!read_range(c.path, c.offset, c.length, enc, &missing)) return fail(std::string("zarr: cannot read ") + c.path);
-            if (!missing) {
-                const int s = j % n_slots;
+            const int s = j % n_slots;
+            const int64_t expected = c.chunk_shape[0] * c.chunk_shape[1] * c.chunk_shape[2] * c.elem_size;
+            char k = HOST;
+            int fd = -1;
+            int64_t length = c.length;
+            if (c.codec == M3D_ZARR_ABSENT) {
+                k = MISSING;
+            } else {
+                fd = open(c.path, O_RDONLY);
+                if (fd < 0) {
+                    if (errno != ENOENT) return fail(std::string("zarr: cannot open ") + c.path);
+                    k = MISSING;
+                } else if (length < 0) {
+                    struct stat sb;
+                    if (fstat(fd, &sb) != 0) {
+                        close(fd);
+                        return fail(std::string("zarr: cannot stat ") + c.path);
+                    }
+                    length = (int64_t)sb.st_size - c.offset;
+                    if (length < 0) length = 0;
+                }
+            }
+            auto read_into = [&](uint8_t* dst, int64_t from, int64_t n) {
+                int64_t got = 0;
+                while (got < n) {
+                    const ssize_t r = pread(fd, dst + got, (size_t)(n - got), (off_t)(c.offset + from + got));
+                    if (r <= 0) break;
+                    got += r;
+                }
+                return got == n;
+            };
+            uint8_t head[BLOSC_HEADER];
+            BloscHeader h;
+            if (k != MISSING && gpu_lz4 && c.codec == M3D_ZARR_BLOSC && length >= BLOSC_HEADER && (size_t)length <= slot_cap &&
+                read_into(head, 0, BLOSC_HEADER) && parse_blosc_header(head, (size_t)length, h) && h.codec == BLOSC_LZ4 &&
+                !(h.flags & FLAG_MEMCPY) && h.nbytes == expected && h.blocksize % h.typesize == 0 &&
+                (h.typesize == c.elem_size || !(h.flags & (FLAG_SHUFFLE | FLAG_BITSHUFFLE))) &&
+                BLOSC_HEADER + 4 * ((h.nbytes + h.blocksize - 1) / h.blocksize) <= length)
+                k = GPU_LZ4;
+            if (k == HOST && !read_all(fd, c.offset, length, enc)) {
+                close(fd);
+                return fail(std::string("zarr: cannot read ") + c.path);
+            }
+            if (k != MISSING) {  // the slot: its previous chunk must have been issued, and must have left it
                 bool wait_drain = R->used[s];
                 if (j >= n_slots) {
                     std::unique_lock<std::mutex> lk(mu);
                     cv.wait(lk, [&] { return issued[j - n_slots] || failed.load(); });
                     wait_drain = true;
                 }
-                if (failed.load()) return;
-                if (wait_drain && cudaEventSynchronize(R->drained[s]) != cudaSuccess) return fail("zarr: slot event failed");
-                const int64_t expected = c.chunk_shape[0] * c.chunk_shape[1] * c.chunk_shape[2] * c.elem_size;
-                if (const char* err = decode_chunk_bytes(c, enc, expected, reinterpret_cast<uint8_t*>(R->pinned[s]), &info[j]))
+                if (!failed.load() && wait_drain && cudaEventSynchronize(R->drained[s]) != cudaSuccess) {
+                    close(fd);
+                    return fail("zarr: slot event failed");
+                }
+                if (failed.load()) {
+                    close(fd);
+                    return;
+                }
+                uint8_t* slot = reinterpret_cast<uint8_t*>(R->pinned[s]);
+                if (k == GPU_LZ4) {
+                    if (!read_into(slot, 0, length)) {
+                        close(fd);
+                        return fail(std::string("zarr: cannot read ") + c.path);
+                    }
+                    comp_len[j] = length;
+                    splits[j] = ((h.flags & FLAG_DONT_SPLIT) || h.typesize > MAX_SPLITS) ? 1 : h.typesize;
+                    info[j].blocksize = h.blocksize;
+                    info[j].mode = ((h.flags & FLAG_SHUFFLE) && h.typesize > 1) ? SH_BYTE
+                                   : (h.flags & FLAG_BITSHUFFLE) ? SH_BIT : SH_NONE;
+                } else if (const char* err = decode_chunk_bytes(c, enc, expected, slot, &info[j])) {
+                    close(fd);
                     return fail(std::string(err) + " (" + c.path + ")");
+                }
             }
+            if (fd >= 0) close(fd);
             {
                 std::lock_guard<std::mutex> lk(mu);
-                absent[j] = missing ? 1 : 0;
+                kind[j] = k;
                 staged[j] = 1;
             }
             cv.notify_all();
         }
     };
+    // the slot streams start behind whatever `stream` has done so far (the destination's allocation, its readers)
+    M3D_CUDA(cudaMemsetAsync(R->d_error, 0, sizeof(int), st));
+    M3D_CUDA(cudaEventRecord(R->begin, st));
+    std::vector<char> joined((size_t)n_slots, 0);
     std::vector<std::thread> pool;
     pool.reserve(workers);
     for (int w = 0; w < workers; ++w) pool.emplace_back(work);
     int rc = M3D_OK;
+    bool any_gpu = false;
+    auto cuda_ok = [&](cudaError_t e) {
+        if (e != cudaSuccess && rc == M3D_OK) rc = m3d_fail(M3D_ERR_CUDA, "m3d_zarr_read_chunks: %s", cudaGetErrorString(e));
+        return e == cudaSuccess;
+    };
     for (int j = 0; j < n_chunks && rc == M3D_OK; ++j) {
         {
             std::unique_lock<std::mutex> lk(mu);
@@ -910,19 +1136,34 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
         if (failed.load()) break;
         const m3d_zarr_chunk& c = chunks[j];
         const int s = j % n_slots;
-        if (absent[j]) {
-            rc = launch_fill(ctx, c, st);
-            // the slot was not used: keep its event as it is (still valid for the previous user)
-        } else {
+        cudaStream_t q = R->streams[s];
+        if (!joined[s]) {
+            cuda_ok(cudaStreamWaitEvent(q, R->begin, 0));
+            joined[s] = 1;
+        }
+        if (rc == M3D_OK && kind[j] == MISSING) {
+            rc = launch_fill(ctx, c, q);
+        } else if (rc == M3D_OK) {
             const ChunkGeom g = geom_of(c, info[j]);
-            cudaError_t e = cudaMemcpyAsync(R->dev[s], R->pinned[s], (size_t)g.nbytes, cudaMemcpyHostToDevice, st);
-            if (e != cudaSuccess) rc = m3d_fail(M3D_ERR_CUDA, "m3d_zarr_read_chunks: %s", cudaGetErrorString(e));
-            if (rc == M3D_OK) rc = launch_for(ctx, c.elem_size, reinterpret_cast<const uint8_t*>(R->dev[s]), g, c.dst, st);
-            if (rc == M3D_OK) {
-                e = cudaEventRecord(R->drained[s], st);
-                if (e != cudaSuccess) rc = m3d_fail(M3D_ERR_CUDA, "m3d_zarr_read_chunks: %s", cudaGetErrorString(e));
-                R->used[s] = 1;
+            if (kind[j] == GPU_LZ4) {
+                any_gpu = true;
+                const int64_t nblocks = (g.nbytes + g.blocksize - 1) / g.blocksize;
+                const int64_t warps = nblocks * splits[j];
+                if (cuda_ok(cudaMemcpyAsync(R->dev_comp[s], R->pinned[s], (size_t)comp_len[j], cudaMemcpyHostToDevice, q))) {
+                    M3D_LAUNCH(ctx, KF_ZARR_LZ4, q,
+                               blosc_lz4_decode_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, q>>>(
+                                   reinterpret_cast<const uint8_t*>(R->dev_comp[s]), comp_len[j],
+                                   reinterpret_cast<uint8_t*>(R->dev[s]), splits[j], R->d_error));
+                    cuda_ok(cudaGetLastError());
+                }
+            } else {
+                cuda_ok(cudaMemcpyAsync(R->dev[s], R->pinned[s], (size_t)g.nbytes, cudaMemcpyHostToDevice, q));
             }
+            if (rc == M3D_OK) rc = launch_for(ctx, c.elem_size, reinterpret_cast<const uint8_t*>(R->dev[s]), g, c.dst, q);
+        }
+        if (rc == M3D_OK && cuda_ok(cudaEventRecord(R->drained[s], q))) {
+            R->used[s] = 1;
+            cuda_ok(cudaStreamWaitEvent(st, R->drained[s], 0));  // `stream` is ordered behind every chunk
         }
         if (rc != M3D_OK) {
             failed.store(1);
@@ -939,5 +1180,10 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
     for (auto& t : pool) t.join();
     if (rc != M3D_OK) return rc;
     if (failed.load()) return m3d_fail(M3D_ERR_ARG, "%s", first_error.empty() ? "m3d_zarr_read_chunks failed" : first_error.c_str());
+    if (any_gpu) {  // frames decoded on the device report corruption through a flag: collect it before returning
+        M3D_CUDA(cudaMemcpyAsync(R->h_error, R->d_error, sizeof(int), cudaMemcpyDeviceToHost, st));
+        M3D_CUDA(cudaStreamSynchronize(st));
+        if (*R->h_error) return m3d_fail(M3D_ERR_ARG, "blosc: lz4 stream is corrupt (device decode)");
+    }
     return M3D_OK;  // the tail of the copies / kernels is still in flight on `stream`
 }

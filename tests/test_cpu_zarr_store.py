@@ -258,3 +258,24 @@ def test_vectorised_chunk_table_equals_the_record_list(tmp_path, shape, chunks):
                 np.testing.assert_array_equal(fast.records[name], slow.records[name], err_msg=name)
         paths = [[ctypes.string_at(int(p)).decode() for p in t.records["path"]] for t in (fast, slow)]
         assert paths[0] == paths[1]
+
+
+def test_corrupted_lz4_and_zstd_frames_never_escape_their_buffers():
+    """The LZ4 parser is the library's own (shared with the device kernel): flip bytes anywhere in valid frames and
+    the decoder must either report an error or return exactly nbytes bytes -- guard pages around NumPy buffers are not
+    available, so this is a crash / hang test, plus a check that untouched frames still decode."""
+    rng = np.random.default_rng(42)
+    data = (rng.poisson(5, 40000) * (rng.random(40000) > 0.5)).astype(np.uint16).tobytes()
+    for cname in ("lz4", "zstd"):
+        for split in (True, False):
+            frame = bytearray(zo.blosc_compress(data, 2, cname=cname, blocksize=8192, split=split))
+            assert _capi.blosc_decode_host(bytes(frame)) == data
+            for _ in range(300):
+                bad = bytearray(frame)
+                for _k in range(int(rng.integers(1, 4))):
+                    bad[int(rng.integers(16, len(bad)))] = int(rng.integers(0, 256))
+                try:
+                    out = _capi.blosc_decode_host(bytes(bad))
+                    assert len(out) == len(data)
+                except _capi.M3dError:
+                    pass

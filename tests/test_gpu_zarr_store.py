@@ -48,6 +48,14 @@ def test_device_reader_matches_oracle_written_images(tmp_path, ctx, shape, dtype
     np.testing.assert_array_equal(dst.cpu().numpy(), a)
     after = ctx.launches_by_kernel()
     assert after.get("zarr_unshuffle_place_kernel", 0) > before.get("zarr_unshuffle_place_kernel", 0)
+    if compression == "blosc-lz4":  # LZ4 frames are entropy-decoded on the device (split streams, one warp each)
+        assert after.get("blosc_lz4_decode_kernel", 0) > before.get("blosc_lz4_decode_kernel", 0)
+        mine = tmp_path / "mine"  # and the un-split frames this package's writer produces
+        zs.write_ome_image(mine, a, chunks=chunks, compression=compression)
+        dst.fill_(1)
+        zs.transfer(ctx, [(zs.ZarrImage(tmp_path / "mine.ome.zarr"), dst)])
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(dst.cpu().numpy(), a)
     if a.ndim == 3:
         for z0, z1 in ((0, 1), (3, min(11, shape[0])), (shape[0] - 2, shape[0])):
             win = torch.full((z1 - z0,) + a.shape[1:], 9, dtype=tdt, device=ctx.device)
@@ -87,6 +95,30 @@ def test_unwritten_chunks_and_corrupt_chunks_on_the_device(tmp_path, ctx):
     torch.cuda.synchronize()
     f.write_bytes(good)
     zs.transfer(ctx, [(zs.ZarrImage(tmp_path / "img.ome.zarr"), dst)])
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(dst.cpu().numpy(), b)
+    # the same for frames the device decodes: corruption is reported through the kernel's error flag
+    zo.write_ome_image(tmp_path / "lz.ome.zarr", b, chunks=(8, 32, 32), compression="blosc-lz4")
+    f = tmp_path / "lz.ome.zarr" / "0" / "c" / "1" / "1" / "0"
+    good = f.read_bytes()
+    raised = 0
+    for trial in range(6):
+        bad = bytearray(good)
+        bad[len(bad) // 2 + trial] ^= 0xFF
+        bad[-1 - trial] ^= 0x5A
+        f.write_bytes(bytes(bad))
+        try:
+            zs.transfer(ctx, [(zs.ZarrImage(tmp_path / "lz.ome.zarr"), dst)])
+        except M3dError:
+            raised += 1
+        torch.cuda.synchronize()
+    assert raised > 0
+    f.write_bytes(good[: len(good) // 2])
+    with pytest.raises(M3dError):
+        zs.transfer(ctx, [(zs.ZarrImage(tmp_path / "lz.ome.zarr"), dst)])
+    torch.cuda.synchronize()
+    f.write_bytes(good)
+    zs.transfer(ctx, [(zs.ZarrImage(tmp_path / "lz.ome.zarr"), dst)])
     torch.cuda.synchronize()
     np.testing.assert_array_equal(dst.cpu().numpy(), b)
 

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--z", type=int, default=32)
     ap.add_argument("--yx", type=int, default=2048)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--compression", default="blosc-zstd")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
 
@@ -49,7 +50,7 @@ def main():
     del stack_dev
     torch.cuda.empty_cache()
     raw_bytes = stack.nbytes
-    res = {"tile": f"{args.bits} bits x {shape} uint16", "raw_gb": raw_bytes / 1e9, "host_threads": os.cpu_count()}
+    res = {"tile": f"{args.bits} bits x {shape} uint16", "compression": args.compression, "raw_gb": raw_bytes / 1e9, "host_threads": os.cpu_count()}
 
     with tempfile.TemporaryDirectory() as tmp:
         root = Path(tmp) / "qi2labdatastore"
@@ -62,7 +63,7 @@ def main():
 
         def write_bit(b):
             d = root / "readouts" / "tile0000" / f"bit{b + 1:03d}"
-            zs.write_ome_image(d / "corrected_data", stack[b], extra_attributes={
+            zs.write_ome_image(d / "corrected_data", stack[b], compression=args.compression, extra_attributes={
                 "round_linker": 1, "excitation_um": 0.561, "emission_um": 0.58})
 
         with ThreadPoolExecutor(max_workers=min(args.bits, os.cpu_count() or 4)) as ex:
@@ -97,7 +98,9 @@ def main():
         ctx.set_timing(True)
         ctx.reset_counters()
         run_transfer()
-        res["a_store_to_device"]["unshuffle_kernel_ms_total"] = ctx.kernel_times_ms().get("zarr_unshuffle_place_kernel")
+        kt = ctx.kernel_times_ms()
+        res["a_store_to_device"]["unshuffle_kernel_ms_total"] = kt.get("zarr_unshuffle_place_kernel")
+        res["a_store_to_device"]["lz4_kernel_ms_total"] = kt.get("blosc_lz4_decode_kernel")
         ctx.set_timing(False)
 
         def run_host_then_upload():
