@@ -85,9 +85,11 @@ int m3d_upload_batch_cb(m3d_ctx* ctx, int n_pieces, const void* const* src_host,
  * `_load_bit_data` (PD:1861-1881), for the arrays `_create_array_tensorstore_qi2lab` writes (DS:1425-1529: Zarr
  * v3, regular chunks, `bytes` + `blosc` {zstd | lz4, bitshuffle} or `zstd` or no compression, optionally inside
  * `sharding_indexed` shards).  The host side (zarr_store.py) reads `zarr.json` and lists the chunks; the library
- * reads each chunk's bytes, entropy-decodes its blocks on a pool of host threads (system libzstd / liblz4) into
- * page-locked slots, and the device undoes the Blosc bit / byte shuffle and places the chunk into the
- * destination volume (cropped at the array edge and to the requested window).  Unwritten chunks = fill value. */
+ * reads each chunk's bytes into a page-locked slot -- Blosc-LZ4 frames as they are (the device decodes their
+ * streams, one warp each), everything else entropy-decoded by a pool of host threads (system libzstd) -- and the
+ * device undoes the Blosc bit / byte shuffle and places the chunk into the destination volume (cropped at the
+ * array edge and to the requested window).  Unwritten chunks = fill value.  The call returns when everything is
+ * enqueued; when the device decoded any frame it first waits for `stream` to collect the kernels' error flag. */
 #define M3D_ZARR_RAW 0    /* `bytes` only */
 #define M3D_ZARR_BLOSC 1  /* `bytes` + `blosc` */
 #define M3D_ZARR_ZSTD 2   /* `bytes` + `zstd` */
