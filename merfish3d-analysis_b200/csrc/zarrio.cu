@@ -704,6 +704,10 @@ int io_threads() {
     }
     unsigned hw = std::thread::hardware_concurrency();
     int w = hw ? (int)hw : 8;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) {  // torchrun: the node's cores are shared by its ranks
+        const int ranks = atoi(e);
+        if (ranks > 1) w = w / ranks > 4 ? w / ranks : 4;
+    }
     return w > 32 ? 32 : w;
 }
 

@@ -314,9 +314,31 @@ class ZarrImage:
     def window(self, z0: int, z1: int) -> "ZarrWindow":
         return ZarrWindow(self, int(z0), int(z1))
 
+    def __getattr__(self, name):
+        # ndarray methods / attributes a caller of the reference's loaders may use (astype, mean, max, T, ...)
+        if name.startswith("__") or name in ("array", "image_path"):
+            raise AttributeError(name)
+        return getattr(self.read(), name)
+
     @property
     def extra_attributes(self) -> dict[str, Any]:
         return read_extra_attributes(self.image_path)
+
+
+def _forward_operator(name):
+    def op(self, *args):
+        return getattr(self.read(), name)(*args)
+
+    op.__name__ = name
+    return op
+
+
+for _name in ("add", "sub", "mul", "truediv", "floordiv", "mod", "pow", "and", "or", "xor", "lshift", "rshift"):
+    setattr(ZarrImage, f"__{_name}__", _forward_operator(f"__{_name}__"))
+    setattr(ZarrImage, f"__r{_name}__", _forward_operator(f"__r{_name}__"))
+for _name in ("lt", "le", "gt", "ge", "eq", "ne", "neg", "abs", "invert"):
+    setattr(ZarrImage, f"__{_name}__", _forward_operator(f"__{_name}__"))
+ZarrImage.__hash__ = object.__hash__  # __eq__ is element-wise, like ndarray's
 
 
 class ZarrWindow:
@@ -633,13 +655,14 @@ class Qi2labZarrDataStore(ArrayDataStore):
 
     # ---- images
     def _open_image(self, entity_root: Path, name: str, return_future):
+        """The lazy handle for every ``return_future`` value (DS:2263-2266 returns the un-read tensorstore array for
+        ``None``, a read future for ``True``, the array for ``False``): ``.result()``, ``np.asarray``, slicing,
+        arithmetic and ndarray methods all work on it and materialise a host array only then, so the tile loader can
+        send the chunks to the device instead."""
         p = image_store_path(entity_root / name)
         if not (p / "zarr.json").exists():
             return None
-        img = ZarrImage(p)
-        if return_future is None or return_future:
-            return img  # lazy handle: `.result()` / np.asarray materialise it
-        return img
+        return ZarrImage(p)
 
     def load_local_readout_image(self, tile, bit, return_future: bool | None = True):
         """DS:4709-4745: ``decon_data`` when present, else ``corrected_data``; native frame."""

@@ -83,6 +83,12 @@ def test_reader_matches_oracle_written_images(tmp_path, shape, dtype, chunks, co
             np.testing.assert_array_equal(img.read(z0, z1), a[z0:z1])
             np.testing.assert_array_equal(img[z0:z1], a[z0:z1])
         np.testing.assert_array_equal(img[2], a[2])
+    # the handle behaves like the array a reference loader returns
+    np.testing.assert_array_equal(img * 2, a * 2)
+    np.testing.assert_array_equal(1 + img, 1 + a)
+    np.testing.assert_array_equal(img.astype(np.float64), a.astype(np.float64))
+    assert img.max() == a.max() and float(np.mean(img)) == float(np.mean(a)) and len(img) == len(a)
+    np.testing.assert_array_equal(img > a.mean(), a > a.mean())
 
 
 @pytest.mark.parametrize("shape,dtype,chunks,compression,shards", CASES)
