@@ -33,6 +33,9 @@ struct HostCodecs {
     size_t (*zstd_compress)(void*, size_t, const void*, size_t, int) = nullptr;
     size_t (*zstd_bound)(size_t) = nullptr;
     unsigned (*zstd_is_error)(size_t) = nullptr;
+    void* (*zstd_create_dctx)() = nullptr;
+    size_t (*zstd_free_dctx)(void*) = nullptr;
+    size_t (*zstd_decompress_dctx)(void*, void*, size_t, const void*, size_t) = nullptr;
     int (*lz4_decompress)(const char*, char*, int, int) = nullptr;
     int (*lz4_compress)(const char*, char*, int, int) = nullptr;
     int (*lz4_bound)(int) = nullptr;
@@ -47,6 +50,9 @@ const HostCodecs& codecs() {
             c.zstd_compress = reinterpret_cast<decltype(c.zstd_compress)>(dlsym(z, "ZSTD_compress"));
             c.zstd_bound = reinterpret_cast<decltype(c.zstd_bound)>(dlsym(z, "ZSTD_compressBound"));
             c.zstd_is_error = reinterpret_cast<decltype(c.zstd_is_error)>(dlsym(z, "ZSTD_isError"));
+            c.zstd_create_dctx = reinterpret_cast<decltype(c.zstd_create_dctx)>(dlsym(z, "ZSTD_createDCtx"));
+            c.zstd_free_dctx = reinterpret_cast<decltype(c.zstd_free_dctx)>(dlsym(z, "ZSTD_freeDCtx"));
+            c.zstd_decompress_dctx = reinterpret_cast<decltype(c.zstd_decompress_dctx)>(dlsym(z, "ZSTD_decompressDCtx"));
         }
         if (void* l = dlopen("liblz4.so.1", RTLD_NOW | RTLD_LOCAL)) {
             c.lz4_decompress = reinterpret_cast<decltype(c.lz4_decompress)>(dlsym(l, "LZ4_decompress_safe"));
@@ -55,6 +61,24 @@ const HostCodecs& codecs() {
         }
     });
     return c;
+}
+
+// One zstd frame -> dst.  A chunk is 32 frames of 256 KiB: the decompression context (~100 KB of tables) is kept
+// per thread instead of being allocated and freed by every ZSTD_decompress call.
+struct ThreadDCtx {
+    void* ctx = nullptr;
+    ~ThreadDCtx() {
+        if (ctx) codecs().zstd_free_dctx(ctx);
+    }
+};
+
+size_t zstd_decode_frame(const HostCodecs& C, void* dst, size_t cap, const void* src, size_t n) {
+    if (C.zstd_create_dctx && C.zstd_free_dctx && C.zstd_decompress_dctx) {
+        static thread_local ThreadDCtx t;
+        if (!t.ctx) t.ctx = C.zstd_create_dctx();
+        if (t.ctx) return C.zstd_decompress_dctx(t.ctx, dst, cap, src, n);
+    }
+    return C.zstd_decompress(dst, cap, src, n);
 }
 
 // ------------------------------------------------------------------------------------------ Blosc-1 frames
@@ -246,7 +270,7 @@ const char* blosc_decode_blocks(const uint8_t* frame, size_t n, const BloscHeade
             if (cb == neblock) {
                 memcpy(dst, frame + pos, (size_t)cb);
             } else if (h.codec == BLOSC_ZSTD) {
-                const size_t r = C.zstd_decompress(dst, (size_t)neblock, frame + pos, (size_t)cb);
+                const size_t r = zstd_decode_frame(C, dst, (size_t)neblock, frame + pos, (size_t)cb);
                 if (C.zstd_is_error(r) || r != (size_t)neblock) return "blosc: zstd stream is corrupt";
             } else {
                 if (!lz4_decode_block<HostLanes>(frame + pos, cb, dst, neblock)) return "blosc: lz4 stream is corrupt";
@@ -576,7 +600,7 @@ const char* decode_chunk_bytes(const m3d_zarr_chunk& c, const Bytes& enc, int64_
     if (c.codec == M3D_ZARR_ZSTD) {
         const HostCodecs& C = codecs();
         if (!C.zstd_decompress) return "zarr: libzstd.so.1 is not available";
-        const size_t r = C.zstd_decompress(out, (size_t)expected, enc.data(), enc.size());
+        const size_t r = zstd_decode_frame(C, out, (size_t)expected, enc.data(), enc.size());
         if (C.zstd_is_error(r) || r != (size_t)expected) return "zarr: zstd chunk is corrupt";
         return nullptr;
     }
