@@ -65,6 +65,9 @@ CASES = [
     ((3, 6, 40, 44), np.float32, (1, 4, 16, 16), "blosc-zstd", None),  # SOFIMA flow field layout
     ((50, 60), np.uint16, (32, 32), "blosc-zstd", None),
     ((17, 19, 23), np.uint8, (8, 8, 8), "blosc-zstd", None),
+    ((10, 30, 34), np.int32, (4, 16, 16), "blosc-lz4", None),  # label images
+    ((6, 20, 24), np.int64, (4, 8, 8), "blosc-zstd", None),
+    ((5, 7, 3), np.uint16, (4, 4, 2), "blosc-lz4", None),  # chunks smaller than one 8-element shuffle group row
 ]
 
 

@@ -40,7 +40,8 @@ def test_device_reader_matches_oracle_written_images(tmp_path, ctx, shape, dtype
     a = _image(rng, shape, dtype)
     zo.write_ome_image(tmp_path / "img.ome.zarr", a, chunks=chunks, compression=compression, shards=shards)
     img = zs.ZarrImage(tmp_path / "img.ome.zarr")
-    tdt = {np.dtype(np.uint16): torch.uint16, np.dtype(np.float32): torch.float32, np.dtype(np.uint8): torch.uint8}[a.dtype]
+    tdt = {np.dtype(np.uint16): torch.uint16, np.dtype(np.float32): torch.float32, np.dtype(np.uint8): torch.uint8,
+           np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64}[a.dtype]
     dst = torch.full(a.shape, 3, dtype=tdt, device=ctx.device)
     before = ctx.launches_by_kernel()
     zs.transfer(ctx, [(img, dst)])
@@ -62,6 +63,26 @@ def test_device_reader_matches_oracle_written_images(tmp_path, ctx, shape, dtype
             zs.transfer(ctx, [(img.window(z0, z1), win)])
             torch.cuda.synchronize()
             np.testing.assert_array_equal(win.cpu().numpy(), a[z0:z1])
+
+
+@pytest.mark.parametrize("env", [{"M3D_ZARR_HOST_LZ4": "1"}, {"M3D_ZARR_MMAP": "0"}, {"M3D_IO_THREADS": "1"},
+                                 {"M3D_IO_THREADS": "3", "LOCAL_WORLD_SIZE": "8"}])
+def test_alternative_host_paths_give_the_same_volume(tmp_path, ctx, monkeypatch, env):
+    """LZ4 frames decoded by the host threads instead of the device, chunk files read instead of mapped, one worker
+    (every chunk waits for the previous one's slot), few workers and many chunks (slot reuse)."""
+    import torch
+    from merfish3d_analysis_b200 import zarr_store as zs
+
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(8)
+    a = rng.poisson(120, (40, 100, 90)).astype(np.uint16)
+    for comp in ("blosc-lz4", "blosc-zstd"):
+        zo.write_ome_image(tmp_path / f"{comp}.ome.zarr", a, chunks=(4, 16, 16), compression=comp)  # 420 chunks
+        dst = torch.zeros(a.shape, dtype=torch.uint16, device=ctx.device)
+        zs.transfer(ctx, [(zs.ZarrImage(tmp_path / f"{comp}.ome.zarr"), dst)])
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(dst.cpu().numpy(), a)
 
 
 def test_unwritten_chunks_and_corrupt_chunks_on_the_device(tmp_path, ctx):
