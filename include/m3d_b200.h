@@ -128,6 +128,9 @@ int m3d_blosc_encode_host(const void* src, int64_t n_bytes, int typesize, int cn
 /* plain zstd frame (the Zarr v3 `zstd` codec): compress != 0 encodes at `level`, else decodes */
 int m3d_zstd_host(int compress, const void* src, int64_t n_bytes, void* dst, int64_t dst_capacity, int level,
                   int64_t* out_bytes);
+/* One zstd frame decoded by the library's OWN decoder (csrc/zstd_decode.cuh: RFC 8878, allocation-free, written to
+ * run on the device next) instead of libzstd.  Test hook: the product path does not call it yet. */
+int m3d_zstd_decode_builtin(const void* src, int64_t n_bytes, void* dst, int64_t dst_capacity, int64_t* out_bytes);
 
 /* _load_bit_data weighting (PD:1879-1881): out = float32(readout) * float32(predictor). */
 int m3d_weight(m3d_ctx* ctx, const uint16_t* readout_dev, const float* predictor_dev,

@@ -56,6 +56,7 @@ SIGNATURES = {
     "m3d_zstd_host": (
         C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int64)]
     ),
+    "m3d_zstd_decode_builtin": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "m3d_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "m3d_warp_affine": (
         C.c_int,
@@ -261,6 +262,16 @@ def blosc_encode_host(data, typesize: int, cname: str = "zstd", clevel: int = 5,
     _check(lib.m3d_blosc_encode_host(src.ctypes.data, src.size, int(typesize), {"zstd": 4, "lz4": 1}[cname], int(clevel),
                                      {"noshuffle": 0, "shuffle": 1, "bitshuffle": 2}[shuffle], int(blocksize),
                                      out.ctypes.data, cap, C.byref(n)), "m3d_blosc_encode_host")
+    return out[: n.value].tobytes()
+
+
+def zstd_decode_builtin(frame, capacity: int) -> bytes:
+    """One zstd frame through the library's own decoder (``csrc/zstd_decode.cuh``), not libzstd."""
+    src = np.ascontiguousarray(np.frombuffer(frame, dtype=np.uint8))
+    out = np.empty(max(int(capacity), 1), dtype=np.uint8)
+    n = C.c_int64(0)
+    _check(load_library().m3d_zstd_decode_builtin(src.ctypes.data, src.size, out.ctypes.data, int(capacity), C.byref(n)),
+           "m3d_zstd_decode_builtin")
     return out[: n.value].tobytes()
 
 

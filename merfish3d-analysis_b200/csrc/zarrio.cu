@@ -24,6 +24,7 @@
 #include <thread>
 
 #include "common.cuh"
+#include "zstd_decode.cuh"
 
 namespace {
 
@@ -953,6 +954,21 @@ extern "C" int m3d_zstd_host(int compress, const void* src, int64_t n_bytes, voi
                               : C.zstd_decompress(dst, (size_t)dst_capacity, src, (size_t)n_bytes);
     if (C.zstd_is_error(r)) return m3d_fail(M3D_ERR_ARG, "m3d_zstd_host: corrupt frame or destination too small");
     *out_bytes = (int64_t)r;
+    return M3D_OK;
+}
+
+// The library's own zstd frame decoder (zstd_decode.cuh), on the host: the test hook that pins it to libzstd before it
+// is moved behind the PCIe link.  Not used by the product path yet.
+extern "C" int m3d_zstd_decode_builtin(const void* src, int64_t n_bytes, void* dst, int64_t dst_capacity, int64_t* out_bytes) {
+    if (!src || !dst || !out_bytes || n_bytes < 0 || dst_capacity < 0) return m3d_fail(M3D_ERR_ARG, "m3d_zstd_decode_builtin: bad argument");
+    std::vector<uint8_t> lit((size_t)m3d_zstd::MAX_BLOCK);
+    std::vector<uint8_t> ws(sizeof(m3d_zstd::Work));
+    m3d_zstd::Work* w = reinterpret_cast<m3d_zstd::Work*>(ws.data());
+    memset(w, 0, sizeof(*w));
+    w->lit = lit.data();
+    const int64_t r = m3d_zstd::decode_frame(*w, reinterpret_cast<const uint8_t*>(src), n_bytes, reinterpret_cast<uint8_t*>(dst), dst_capacity);
+    if (r < 0) return m3d_fail(M3D_ERR_ARG, "m3d_zstd_decode_builtin: corrupt or unsupported frame");
+    *out_bytes = r;
     return M3D_OK;
 }
 

@@ -288,3 +288,56 @@ def test_corrupted_lz4_and_zstd_frames_never_escape_their_buffers():
                     assert len(out) == len(data)
                 except _capi.M3dError:
                     pass
+
+
+def _zstd_datasets():
+    rng = np.random.default_rng(0)
+    yield "zeros", bytes(100000)
+    yield "one", b"x"
+    yield "short", b"hello world hello world hello"
+    yield "text", b"the quick brown fox jumps over the lazy dog. " * 3000
+    yield "random", rng.integers(0, 256, 200000, dtype=np.uint8).tobytes()
+    yield "low_entropy", rng.integers(0, 4, 300000, dtype=np.uint8).tobytes()
+    yield "poisson_u16", rng.poisson(100, 150000).astype(np.uint16).tobytes()
+    a = (rng.poisson(100, 131072) + 100).astype(np.uint16)
+    a[1000:1200] += 3000
+    yield "bitshuffled_block", zo.bit_shuffle(a.tobytes(), 2)  # what a Blosc block of a readout image holds
+    yield "mixed", b"".join([bytes(5000), rng.integers(0, 256, 5000, dtype=np.uint8).tobytes(), b"abc" * 4000,
+                             rng.integers(0, 16, 70000, dtype=np.uint8).tobytes()])
+    yield "multi_block", rng.poisson(3, 1 << 20).astype(np.uint8).tobytes()  # 8 blocks: repeat tables / offsets
+    words = [bytes(rng.integers(97, 123, int(rng.integers(2, 9)), dtype=np.uint8)) for _ in range(500)]
+    yield "words", b" ".join(words[int(i)] for i in rng.integers(0, 500, 60000))
+
+
+def test_builtin_zstd_decoder_equals_libzstd():
+    """csrc/zstd_decode.cuh (the decoder that is to move onto the device) against frames written by the system
+    libzstd at fast, default, high and negative levels and by pyarrow's bundled zstd: raw / RLE / compressed blocks,
+    Huffman literals in 1 and 4 streams with direct and FSE-coded weights, predefined / RLE / described / repeated
+    sequence tables, repeat offsets."""
+    for name, data in _zstd_datasets():
+        for level in (-5, 1, 3, 5, 9, 15, 19):
+            frame = _capi.zstd_host(data, True, level=level)
+            assert _capi.zstd_decode_builtin(frame, len(data)) == data, (name, level)
+        assert _capi.zstd_decode_builtin(zo._compress("zstd", data, 3), len(data)) == data, name
+    assert _capi.zstd_decode_builtin(_capi.zstd_host(b"", True), 0) == b""
+    with pytest.raises(_capi.M3dError):  # does not fit
+        _capi.zstd_decode_builtin(_capi.zstd_host(bytes(1000), True), 999)
+
+
+def test_builtin_zstd_decoder_survives_corruption():
+    rng = np.random.default_rng(7)
+    data = b"the quick brown fox " * 2000 + rng.integers(0, 8, 30000, dtype=np.uint8).tobytes()
+    frame = bytearray(_capi.zstd_host(data, True, level=5))
+    reported = 0
+    for _ in range(1500):
+        bad = bytearray(frame)
+        for _k in range(int(rng.integers(1, 4))):
+            bad[int(rng.integers(0, len(bad)))] = int(rng.integers(0, 256))
+        try:
+            assert len(_capi.zstd_decode_builtin(bytes(bad), len(data))) <= len(data)
+        except _capi.M3dError:
+            reported += 1
+    assert reported > 500
+    for cut in (0, 3, 5, 9, len(frame) // 2, len(frame) - 1):
+        with pytest.raises(_capi.M3dError):
+            _capi.zstd_decode_builtin(bytes(frame[:cut]), len(data))
