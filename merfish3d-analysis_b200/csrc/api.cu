@@ -24,7 +24,7 @@ static const char* const kKernelNames[KF_COUNT] = {
     "ccl_interface_kernel",   "features_kernel",     "select_hist_kernel",  "replace_above_kernel", "warp_affine_kernel",
     "table_hist3d_kernel", "table_grid_kernels", "table_overlap_kernel", "table_within_kernels",
     "centroid_stats_kernel", "inertia_eigvals_kernel", "assign_cells_kernel", "reset_foreground_kernel",
-    "zarr_unshuffle_place_kernel", "zarr_fill_chunk_kernel", "blosc_lz4_decode_kernel"};
+    "zarr_unshuffle_place_kernel", "zarr_fill_chunk_kernel", "blosc_lz4_decode_kernel", "blosc_zstd_decode_kernel"};
 
 DecodeParams m3d_ctx::params() const {
     DecodeParams P;

@@ -61,6 +61,7 @@ enum M3dKernel {
     KF_ZARR_UNSHUFFLE,
     KF_ZARR_FILL,
     KF_ZARR_LZ4,
+    KF_ZARR_ZSTD,
     KF_COUNT
 };
 

@@ -233,6 +233,56 @@ __global__ void __launch_bounds__(128) blosc_lz4_decode_kernel(const uint8_t* fr
     if (!ok && (threadIdx.x & 31) == 0) atomicExch(error, 1);
 }
 
+// The same for Blosc-zstd frames, first device version (off unless M3D_ZARR_GPU_ZSTD=1): one warp per stream, the
+// stream's zstd frame decoded by lane 0 with m3d_zstd::decode_frame (zstd_decode.cuh; tables in shared memory, the
+// literal buffer in `lit_scratch`), stored streams copied by the whole warp.  Correct by construction -- it is the
+// function the CPU tests pin to libzstd -- but lane-serial: sharing the Huffman streams and the copies among the
+// lanes is the next step.
+__global__ void __launch_bounds__(64) blosc_zstd_decode_kernel(const uint8_t* frame, int64_t frame_len, uint8_t* out,
+                                                               int splits_per_block, uint8_t* lit_scratch,
+                                                               int* __restrict__ error) {
+    __shared__ m3d_zstd::Work work[2];
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int typesize = frame[3], flags = frame[2];
+    const int64_t nbytes = le32_hd(frame + 4), blocksize = le32_hd(frame + 8);
+    const int64_t nblocks = (nbytes + blocksize - 1) / blocksize, leftover = nbytes % blocksize;
+    const int64_t j = warp / splits_per_block;
+    const int s = (int)(warp - j * splits_per_block);
+    if (j >= nblocks) return;
+    const bool is_left = (j == nblocks - 1) && leftover > 0;
+    const int64_t bsize = is_left ? leftover : blocksize;
+    const int nsplits = (!(flags & FLAG_DONT_SPLIT) && typesize <= MAX_SPLITS && bsize / typesize >= MIN_BUFFERSIZE &&
+                         !is_left) ? typesize : 1;
+    if (s >= nsplits) return;
+    const int64_t neblock = bsize / nsplits;
+    bool ok = BLOSC_HEADER + 4 * nblocks <= frame_len;
+    int64_t pos = ok ? le32_hd(frame + BLOSC_HEADER + 4 * j) : 0;
+    int64_t cb = 0;
+    for (int t = 0; ok && t <= s; ++t) {
+        ok = pos >= BLOSC_HEADER && pos + 4 <= frame_len;
+        if (!ok) break;
+        cb = (int32_t)le32_hd(frame + pos);
+        pos += 4;
+        ok = cb >= 0 && pos + cb <= frame_len;
+        if (ok && t < s) pos += cb;
+    }
+    uint8_t* dst = out + j * blocksize + (int64_t)s * neblock;
+    if (ok) {
+        if (cb == neblock) {
+            WarpLanes::copy(dst, frame + pos, cb);
+        } else {
+            int good = 0;
+            if ((threadIdx.x & 31) == 0) {
+                m3d_zstd::Work& w = work[(threadIdx.x >> 5) & 1];
+                w.lit = lit_scratch + warp * (int64_t)m3d_zstd::MAX_BLOCK;
+                good = m3d_zstd::decode_frame(w, frame + pos, cb, dst, neblock) == neblock;
+            }
+            ok = __shfl_sync(0xffffffffu, good, 0) != 0;
+        }
+    }
+    if (!ok && (threadIdx.x & 31) == 0) atomicExch(error, 1);
+}
+
 // how the decoded bytes of a chunk are still arranged when they reach the device
 enum ShuffleMode { SH_NONE = 0, SH_BYTE = 1, SH_BIT = 2 };
 
@@ -647,6 +697,8 @@ struct ZarrRing {
     std::vector<void*> pinned;    // host slot: the decoded (still shuffled) chunk, or the chunk file itself (LZ4)
     std::vector<void*> dev;       // device slot: the still-shuffled chunk image the un-shuffle kernel reads
     std::vector<void*> dev_comp;  // device slot: the chunk file, for frames the GPU entropy-decodes
+    std::vector<void*> dev_lit;   // device slot: zstd literal buffers (128 KiB per stream), allocated on first use
+    std::vector<size_t> dev_lit_bytes;
     std::vector<cudaEvent_t> drained;
     std::vector<cudaStream_t> streams;  // one per slot: chunks in different slots overlap their copies and kernels
     std::vector<char> used;
@@ -674,12 +726,15 @@ void zring_free_slots(ZarrRing* r) {
         if (r->pinned[s]) cudaFreeHost(r->pinned[s]);
         if (r->dev[s]) cudaFree(r->dev[s]);
         if (r->dev_comp[s]) cudaFree(r->dev_comp[s]);
+        if (r->dev_lit[s]) cudaFree(r->dev_lit[s]);
         if (r->drained[s]) cudaEventDestroy(r->drained[s]);
         if (r->streams[s]) cudaStreamDestroy(r->streams[s]);
     }
     r->pinned.clear();
     r->dev.clear();
     r->dev_comp.clear();
+    r->dev_lit.clear();
+    r->dev_lit_bytes.clear();
     r->drained.clear();
     r->streams.clear();
     r->used.clear();
@@ -709,6 +764,8 @@ int zring_ensure(ZarrRing* r, int n_slots, size_t slot_bytes) {
         r->pinned.push_back(nullptr);
         r->dev.push_back(nullptr);
         r->dev_comp.push_back(nullptr);
+        r->dev_lit.push_back(nullptr);
+        r->dev_lit_bytes.push_back(0);
         r->drained.push_back(nullptr);
         r->streams.push_back(nullptr);
         r->used.push_back(0);
@@ -1068,6 +1125,9 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
     std::string first_error;
     const int device = ctx->device;
     const bool gpu_lz4 = getenv("M3D_ZARR_HOST_LZ4") == nullptr;
+    const char* gz = getenv("M3D_ZARR_GPU_ZSTD");
+    const bool gpu_zstd = gz && atoi(gz) != 0;  // first device version of the zstd decoder: opt-in
+    std::vector<char> on_gpu_zstd((size_t)n_chunks, 0);
     const char* mm = getenv("M3D_ZARR_MMAP");
     const bool use_mmap = mm ? atoi(mm) != 0 : true;  // +10 % on the zstd path: one copy of the file less
     auto fail = [&](const std::string& what) {
@@ -1118,8 +1178,9 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
             };
             uint8_t head[BLOSC_HEADER];
             BloscHeader h;
-            if (k != MISSING && gpu_lz4 && c.codec == M3D_ZARR_BLOSC && length >= BLOSC_HEADER && (size_t)length <= slot_cap &&
-                read_into(head, 0, BLOSC_HEADER) && parse_blosc_header(head, (size_t)length, h) && h.codec == BLOSC_LZ4 &&
+            if (k != MISSING && (gpu_lz4 || gpu_zstd) && c.codec == M3D_ZARR_BLOSC && length >= BLOSC_HEADER &&
+                (size_t)length <= slot_cap && read_into(head, 0, BLOSC_HEADER) && parse_blosc_header(head, (size_t)length, h) &&
+                ((gpu_lz4 && h.codec == BLOSC_LZ4) || (gpu_zstd && h.codec == BLOSC_ZSTD)) &&
                 !(h.flags & FLAG_MEMCPY) && h.nbytes == expected && h.blocksize % h.typesize == 0 &&
                 (h.typesize == c.elem_size || !(h.flags & (FLAG_SHUFFLE | FLAG_BITSHUFFLE))) &&
                 BLOSC_HEADER + 4 * ((h.nbytes + h.blocksize - 1) / h.blocksize) <= length)
@@ -1171,6 +1232,7 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
                         return fail(std::string("zarr: cannot read ") + c.path);
                     }
                     comp_len[j] = length;
+                    on_gpu_zstd[j] = h.codec == BLOSC_ZSTD;
                     splits[j] = ((h.flags & FLAG_DONT_SPLIT) || h.typesize > MAX_SPLITS) ? 1 : h.typesize;
                     info[j].blocksize = h.blocksize;
                     info[j].mode = ((h.flags & FLAG_SHUFFLE) && h.typesize > 1) ? SH_BYTE
@@ -1223,7 +1285,25 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
                 any_gpu = true;
                 const int64_t nblocks = (g.nbytes + g.blocksize - 1) / g.blocksize;
                 const int64_t warps = nblocks * splits[j];
-                if (cuda_ok(cudaMemcpyAsync(R->dev_comp[s], R->pinned[s], (size_t)comp_len[j], cudaMemcpyHostToDevice, q))) {
+                if (on_gpu_zstd[j]) {
+                    const size_t need = (size_t)warps * m3d_zstd::MAX_BLOCK;
+                    if (R->dev_lit_bytes[s] < need) {
+                        cuda_ok(cudaStreamSynchronize(q));
+                        if (R->dev_lit[s]) cudaFree(R->dev_lit[s]);
+                        R->dev_lit[s] = nullptr;
+                        R->dev_lit_bytes[s] = 0;
+                        if (cuda_ok(cudaMalloc(&R->dev_lit[s], need))) R->dev_lit_bytes[s] = need;
+                    }
+                    if (rc == M3D_OK &&
+                        cuda_ok(cudaMemcpyAsync(R->dev_comp[s], R->pinned[s], (size_t)comp_len[j], cudaMemcpyHostToDevice, q))) {
+                        M3D_LAUNCH(ctx, KF_ZARR_ZSTD, q,
+                                   blosc_zstd_decode_kernel<<<(unsigned)((warps + 1) / 2), 64, 0, q>>>(
+                                       reinterpret_cast<const uint8_t*>(R->dev_comp[s]), comp_len[j],
+                                       reinterpret_cast<uint8_t*>(R->dev[s]), splits[j],
+                                       reinterpret_cast<uint8_t*>(R->dev_lit[s]), R->d_error));
+                        cuda_ok(cudaGetLastError());
+                    }
+                } else if (cuda_ok(cudaMemcpyAsync(R->dev_comp[s], R->pinned[s], (size_t)comp_len[j], cudaMemcpyHostToDevice, q))) {
                     M3D_LAUNCH(ctx, KF_ZARR_LZ4, q,
                                blosc_lz4_decode_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, q>>>(
                                    reinterpret_cast<const uint8_t*>(R->dev_comp[s]), comp_len[j],
@@ -1257,7 +1337,7 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
     if (any_gpu) {  // frames decoded on the device report corruption through a flag: collect it before returning
         M3D_CUDA(cudaMemcpyAsync(R->h_error, R->d_error, sizeof(int), cudaMemcpyDeviceToHost, st));
         M3D_CUDA(cudaStreamSynchronize(st));
-        if (*R->h_error) return m3d_fail(M3D_ERR_ARG, "blosc: lz4 stream is corrupt (device decode)");
+        if (*R->h_error) return m3d_fail(M3D_ERR_ARG, "blosc: compressed stream is corrupt (device decode)");
     }
     return M3D_OK;  // the tail of the copies / kernels is still in flight on `stream`
 }

@@ -238,3 +238,43 @@ def test_optimizer_and_all_tiles_from_a_reference_layout_store(tmp_path):
     d2 = PixelDecoder(ads, merfish_bits=16, verbose=0)
     d2.decode_one_tile(1, lowpass_sigma=None, minimum_pixels=4, magnitude_threshold=(0.9, 10.0))
     pd.testing.assert_frame_equal(d1.decoded_barcodes, d2.decoded_barcodes)
+
+
+def test_device_zstd_decoder_opt_in(tmp_path, ctx, monkeypatch, capsys):
+    """M3D_ZARR_GPU_ZSTD=1: Blosc-zstd frames cross PCIe compressed and `blosc_zstd_decode_kernel` runs the library's
+    own zstd decoder (csrc/zstd_decode.cuh, pinned to libzstd on the CPU) on the device -- first, lane-serial version."""
+    import time
+
+    import torch
+    from merfish3d_analysis_b200 import zarr_store as zs
+    from merfish3d_analysis_b200._capi import M3dError
+
+    monkeypatch.setenv("M3D_ZARR_GPU_ZSTD", "1")
+    rng = np.random.default_rng(21)
+    for shape, dtype, chunks, tdt in (((24, 64, 64), np.uint16, (8, 32, 32), torch.uint16),
+                                      ((20, 70, 90), np.float32, (8, 32, 48), torch.float32),
+                                      ((16, 512, 512), np.uint16, (16, 512, 512), torch.uint16)):
+        a = _image(rng, shape, dtype)
+        if shape[1] == 512:
+            a[:, 100:110, 200:230] += 4000
+        p = tmp_path / f"z{shape[1]}"
+        zs.write_ome_image(p, a, chunks=chunks, compression="blosc-zstd")
+        img = zs.ZarrImage(tmp_path / f"z{shape[1]}.ome.zarr")
+        dst = torch.full(a.shape, 7, dtype=tdt, device=ctx.device)
+        before = ctx.launches_by_kernel().get("blosc_zstd_decode_kernel", 0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        zs.transfer(ctx, [(img, dst)])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        np.testing.assert_array_equal(dst.cpu().numpy(), a)
+        assert ctx.launches_by_kernel().get("blosc_zstd_decode_kernel", 0) > before
+        with capsys.disabled():
+            print(f"\n[device zstd] {shape} {np.dtype(dtype).name}: {a.nbytes / 1e6:.2f} MB in {dt * 1e3:.1f} ms")
+    f = tmp_path / "z64.ome.zarr" / "0" / "c" / "1" / "1" / "0"
+    good = f.read_bytes()
+    f.write_bytes(good[:40] + bytes(len(good) - 40))
+    dst = torch.zeros((24, 64, 64), dtype=torch.uint16, device=ctx.device)
+    with pytest.raises(M3dError):
+        zs.transfer(ctx, [(zs.ZarrImage(tmp_path / "z64.ome.zarr"), dst)])
+    torch.cuda.synchronize()
