@@ -212,7 +212,9 @@ def within_tile_duplicates(coords_zyx: np.ndarray, tile_idx: np.ndarray, gene_id
 
 
 def assign_cells(points_yx: np.ndarray, polygons_yx: list[np.ndarray]) -> np.ndarray:
-    """PD:4107-4135 restated without rtree / shapely (neither is installed; parity UNPINNED for this function):
+    """PD:4107-4135 restated without rtree / shapely (neither is installed, so this function cannot be pinned to the
+    reference's own output; its containment predicate is cross-checked against OpenCV's pointPolygonTest, an independent
+    implementation, in tests/test_cpu_table_stage.py):
     1 + index of the lowest-numbered polygon whose interior contains the point (even-odd rule, float64), else 0."""
     pts = np.asarray(points_yx, dtype=np.float64)
     out = np.zeros(len(pts), dtype=np.int64)

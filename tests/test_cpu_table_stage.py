@@ -162,3 +162,27 @@ def test_imagej_roi_round_trip_and_grid_index(tmp_path):
         assert want[i] - 1 in cand and np.all(np.diff(cand) > 0)  # reachable, candidates ascending
         hits += 1
     assert hits > 300
+
+
+def test_assign_cells_containment_agrees_with_opencv():
+    """shapely / rtree are not installed, so `assign_cells` (PD:4107-4135) cannot be pinned to them; OpenCV's
+    pointPolygonTest is an independent point-in-polygon implementation that is: for simple polygons (cell outlines)
+    interior membership is the same predicate as shapely's `contains` away from the boundary."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(17)
+    polys = []
+    for _ in range(40):  # star-shaped outlines: simple, non-convex, overlapping each other
+        cy, cx = rng.uniform(100, 900, 2)
+        ang = np.sort(rng.uniform(0, 2 * np.pi, int(rng.integers(5, 40))))
+        rad = rng.uniform(20, 120, ang.size)
+        polys.append(np.stack([cy + rad * np.sin(ang), cx + rad * np.cos(ang)], axis=1))
+    pts = rng.uniform(0, 1000, (20000, 2))
+    contours = [np.ascontiguousarray(p[:, ::-1], dtype=np.float32).reshape(-1, 1, 2) for p in polys]  # (x, y)
+    dist = np.array([[cv2.pointPolygonTest(c, (float(x), float(y)), True) for c in contours] for y, x in pts])
+    clear = np.all(np.abs(dist) > 1e-2, axis=1)  # float32 contours: stay away from the outlines
+    assert clear.sum() > 19000
+    inside = dist > 0
+    expected = np.where(inside.any(axis=1), inside.argmax(axis=1) + 1, 0)  # lowest-numbered containing polygon
+    got = tor.assign_cells(pts, polys)
+    np.testing.assert_array_equal(got[clear], expected[clear])
+    assert (got[clear] > 0).sum() > 2000
