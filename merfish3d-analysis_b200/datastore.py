@@ -1,8 +1,10 @@
 """Duck-typed stand-in for ``qi2labDataStore`` covering the surface ``PixelDecoder`` calls.
 
 The decoder never imports this module: any object with the same attributes/methods works
-(the real ``qi2labDataStore`` included -- SURVEY.md section 8b lists the surface).  This shim
-exists because zarr / tensorstore / yaozarrs are not available in the build image; it keeps
+(the real ``qi2labDataStore`` included -- SURVEY.md section 8b lists the surface).  The store that reads
+the reference's own ``<image>.ome.zarr`` chunk files straight into HBM is ``zarr_store.Qi2labZarrDataStore``
+(it inherits the output side from this class); this array-fed one serves tests, benchmarks and callers that
+already hold the tile in memory.  It keeps
 the reference's directory layout and file names for everything the decode stage WRITES
 (``docs/datastore.md:211-300`` of the reference):
 
