@@ -282,12 +282,24 @@ class ZarrImage:
 
     def __init__(self, image_path: str | Path):
         self.image_path = Path(image_path)
-        self.array = ZarrArray(self.image_path / "0")
+        self.array = ZarrArray(self.image_path / self._level0_path(self.image_path))
         self.shape = self.array.shape
         self.dtype = self.array.dtype
         self.ndim = self.array.ndim
         self.size = int(np.prod(self.shape))
         self.nbytes = self.size * self.dtype.itemsize
+
+    @staticmethod
+    def _level0_path(image_path: Path) -> str:
+        """The full-resolution dataset named by the group's OME metadata; the reference always writes "0" (DS:2343)."""
+        try:
+            meta = json.loads((image_path / "zarr.json").read_text())
+            path = meta["attributes"]["ome"]["multiscales"][0]["datasets"][0]["path"]
+            if isinstance(path, str) and path and (image_path / path / "zarr.json").exists():
+                return path
+        except (OSError, ValueError, KeyError, IndexError, TypeError):
+            pass
+        return "0"
 
     def result(self):
         return self

@@ -109,6 +109,17 @@ def test_writer_is_read_by_the_oracle(tmp_path, shape, dtype, chunks, compressio
     assert meta["attributes"]["ome"]["multiscales"][0]["datasets"][0]["path"] == "0"
 
 
+def test_level_zero_is_taken_from_the_ome_metadata(tmp_path):
+    a = np.arange(4 * 6 * 8, dtype=np.uint16).reshape(4, 6, 8)
+    zo.write_ome_image(tmp_path / "img.ome.zarr", a, chunks=(2, 4, 4))
+    root = tmp_path / "img.ome.zarr"
+    (root / "0").rename(root / "s0")
+    meta = json.loads((root / "zarr.json").read_text())
+    meta["attributes"]["ome"]["multiscales"][0]["datasets"][0]["path"] = "s0"
+    (root / "zarr.json").write_text(json.dumps(meta))
+    np.testing.assert_array_equal(np.asarray(zs.ZarrImage(root)), a)
+
+
 def test_unwritten_chunks_are_fill_value(tmp_path):
     a = np.zeros((20, 64, 64), dtype=np.uint16)
     a[:8, :32, :32] = 7
