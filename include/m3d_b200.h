@@ -131,6 +131,9 @@ int m3d_zstd_host(int compress, const void* src, int64_t n_bytes, void* dst, int
 /* One zstd frame decoded by the library's OWN decoder (csrc/zstd_decode.cuh: RFC 8878, allocation-free, written to
  * run on the device next) instead of libzstd.  Test hook: the product path does not call it yet. */
 int m3d_zstd_decode_builtin(const void* src, int64_t n_bytes, void* dst, int64_t dst_capacity, int64_t* out_bytes);
+/* The same through the team-of-lanes arrangement (csrc/zstd_lanes.cuh: one lane per Huffman stream, shared copies)
+ * with a team of one: the host pin of the code the second device version runs. */
+int m3d_zstd_decode_builtin_lanes(const void* src, int64_t n_bytes, void* dst, int64_t dst_capacity, int64_t* out_bytes);
 
 /* _load_bit_data weighting (PD:1879-1881): out = float32(readout) * float32(predictor). */
 int m3d_weight(m3d_ctx* ctx, const uint16_t* readout_dev, const float* predictor_dev,

@@ -57,6 +57,7 @@ SIGNATURES = {
         C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int64)]
     ),
     "m3d_zstd_decode_builtin": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "m3d_zstd_decode_builtin_lanes": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "m3d_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "m3d_warp_affine": (
         C.c_int,
@@ -265,13 +266,15 @@ def blosc_encode_host(data, typesize: int, cname: str = "zstd", clevel: int = 5,
     return out[: n.value].tobytes()
 
 
-def zstd_decode_builtin(frame, capacity: int) -> bytes:
-    """One zstd frame through the library's own decoder (``csrc/zstd_decode.cuh``), not libzstd."""
+def zstd_decode_builtin(frame, capacity: int, lanes: bool = False) -> bytes:
+    """One zstd frame through the library's own decoder (``csrc/zstd_decode.cuh``), not libzstd; ``lanes=True`` takes
+    the team-of-lanes arrangement (``csrc/zstd_lanes.cuh``) with a team of one."""
     src = np.ascontiguousarray(np.frombuffer(frame, dtype=np.uint8))
     out = np.empty(max(int(capacity), 1), dtype=np.uint8)
     n = C.c_int64(0)
-    _check(load_library().m3d_zstd_decode_builtin(src.ctypes.data, src.size, out.ctypes.data, int(capacity), C.byref(n)),
-           "m3d_zstd_decode_builtin")
+    lib = load_library()
+    fn = lib.m3d_zstd_decode_builtin_lanes if lanes else lib.m3d_zstd_decode_builtin
+    _check(fn(src.ctypes.data, src.size, out.ctypes.data, int(capacity), C.byref(n)), "m3d_zstd_decode_builtin")
     return out[: n.value].tobytes()
 
 

@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "zstd_decode.cuh"
+#include "zstd_lanes.cuh"
 
 namespace {
 
@@ -278,6 +279,51 @@ __global__ void __launch_bounds__(64) blosc_zstd_decode_kernel(const uint8_t* fr
                 good = m3d_zstd::decode_frame(w, frame + pos, cb, dst, neblock) == neblock;
             }
             ok = __shfl_sync(0xffffffffu, good, 0) != 0;
+        }
+    }
+    if (!ok && (threadIdx.x & 31) == 0) atomicExch(error, 1);
+}
+
+// Second device version (M3D_ZARR_GPU_ZSTD=2; zstd_lanes.cuh): the warp works as a team -- one lane per Huffman
+// stream, shared copies.  Pinned on the host through the one-lane policy; NOT yet run on a device.
+__global__ void __launch_bounds__(64) blosc_zstd_decode_kernel_v2(const uint8_t* frame, int64_t frame_len, uint8_t* out,
+                                                                  int splits_per_block, uint8_t* lit_scratch,
+                                                                  int* __restrict__ error) {
+    __shared__ m3d_zstd::Work work[2];
+    __shared__ m3d_zstd::LitPlan plans[2];
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int typesize = frame[3], flags = frame[2];
+    const int64_t nbytes = le32_hd(frame + 4), blocksize = le32_hd(frame + 8);
+    const int64_t nblocks = (nbytes + blocksize - 1) / blocksize, leftover = nbytes % blocksize;
+    const int64_t j = warp / splits_per_block;
+    const int s = (int)(warp - j * splits_per_block);
+    if (j >= nblocks) return;
+    const bool is_left = (j == nblocks - 1) && leftover > 0;
+    const int64_t bsize = is_left ? leftover : blocksize;
+    const int nsplits = (!(flags & FLAG_DONT_SPLIT) && typesize <= MAX_SPLITS && bsize / typesize >= MIN_BUFFERSIZE &&
+                         !is_left) ? typesize : 1;
+    if (s >= nsplits) return;
+    const int64_t neblock = bsize / nsplits;
+    bool ok = BLOSC_HEADER + 4 * nblocks <= frame_len;
+    int64_t pos = ok ? le32_hd(frame + BLOSC_HEADER + 4 * j) : 0;
+    int64_t cb = 0;
+    for (int t = 0; ok && t <= s; ++t) {
+        ok = pos >= BLOSC_HEADER && pos + 4 <= frame_len;
+        if (!ok) break;
+        cb = (int32_t)le32_hd(frame + pos);
+        pos += 4;
+        ok = cb >= 0 && pos + cb <= frame_len;
+        if (ok && t < s) pos += cb;
+    }
+    uint8_t* dst = out + j * blocksize + (int64_t)s * neblock;
+    if (ok) {
+        if (cb == neblock) {
+            WarpLanes::copy(dst, frame + pos, cb);
+        } else {
+            const int wi = (threadIdx.x >> 5) & 1;
+            if ((threadIdx.x & 31) == 0) work[wi].lit = lit_scratch + warp * (int64_t)m3d_zstd::MAX_BLOCK;
+            __syncwarp();
+            ok = m3d_zstd::decode_frame_lanes<m3d_zstd::Warp32>(work[wi], plans[wi], frame + pos, cb, dst, neblock) == neblock;
         }
     }
     if (!ok && (threadIdx.x & 31) == 0) atomicExch(error, 1);
@@ -1029,6 +1075,23 @@ extern "C" int m3d_zstd_decode_builtin(const void* src, int64_t n_bytes, void* d
     return M3D_OK;
 }
 
+// The team-of-lanes arrangement of the same decoder (zstd_lanes.cuh) with a team of one: what pins its logic on the host.
+extern "C" int m3d_zstd_decode_builtin_lanes(const void* src, int64_t n_bytes, void* dst, int64_t dst_capacity, int64_t* out_bytes) {
+    if (!src || !dst || !out_bytes || n_bytes < 0 || dst_capacity < 0) return m3d_fail(M3D_ERR_ARG, "m3d_zstd_decode_builtin_lanes: bad argument");
+    std::vector<uint8_t> lit((size_t)m3d_zstd::MAX_BLOCK);
+    std::vector<uint8_t> ws(sizeof(m3d_zstd::Work));
+    m3d_zstd::Work* w = reinterpret_cast<m3d_zstd::Work*>(ws.data());
+    memset(w, 0, sizeof(*w));
+    w->lit = lit.data();
+    m3d_zstd::LitPlan plan;
+    memset(&plan, 0, sizeof(plan));
+    const int64_t r = m3d_zstd::decode_frame_lanes<m3d_zstd::OneLane>(*w, plan, reinterpret_cast<const uint8_t*>(src), n_bytes,
+                                                                     reinterpret_cast<uint8_t*>(dst), dst_capacity);
+    if (r < 0) return m3d_fail(M3D_ERR_ARG, "m3d_zstd_decode_builtin_lanes: corrupt or unsupported frame");
+    *out_bytes = r;
+    return M3D_OK;
+}
+
 // Host destination: the same chunk decode, the un-shuffle and placement run on the calling threads.  This is the
 // reference's `tensorstore.read().result()` (DS:2235-2267) for callers that want a NumPy array (metadata probes,
 // the normalisation sampler); the decode path proper uses m3d_zarr_read_chunks.
@@ -1126,7 +1189,8 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
     const int device = ctx->device;
     const bool gpu_lz4 = getenv("M3D_ZARR_HOST_LZ4") == nullptr;
     const char* gz = getenv("M3D_ZARR_GPU_ZSTD");
-    const bool gpu_zstd = gz && atoi(gz) != 0;  // first device version of the zstd decoder: opt-in
+    const int gpu_zstd_mode = gz ? atoi(gz) : 0;  // device zstd decoder, opt-in: 1 = lane-serial, 2 = team of lanes
+    const bool gpu_zstd = gpu_zstd_mode != 0;
     std::vector<char> on_gpu_zstd((size_t)n_chunks, 0);
     const char* mm = getenv("M3D_ZARR_MMAP");
     const bool use_mmap = mm ? atoi(mm) != 0 : true;  // +10 % on the zstd path: one copy of the file less
@@ -1296,11 +1360,19 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
                     }
                     if (rc == M3D_OK &&
                         cuda_ok(cudaMemcpyAsync(R->dev_comp[s], R->pinned[s], (size_t)comp_len[j], cudaMemcpyHostToDevice, q))) {
-                        M3D_LAUNCH(ctx, KF_ZARR_ZSTD, q,
-                                   blosc_zstd_decode_kernel<<<(unsigned)((warps + 1) / 2), 64, 0, q>>>(
-                                       reinterpret_cast<const uint8_t*>(R->dev_comp[s]), comp_len[j],
-                                       reinterpret_cast<uint8_t*>(R->dev[s]), splits[j],
-                                       reinterpret_cast<uint8_t*>(R->dev_lit[s]), R->d_error));
+                        if (gpu_zstd_mode == 2) {
+                            M3D_LAUNCH(ctx, KF_ZARR_ZSTD, q,
+                                       blosc_zstd_decode_kernel_v2<<<(unsigned)((warps + 1) / 2), 64, 0, q>>>(
+                                           reinterpret_cast<const uint8_t*>(R->dev_comp[s]), comp_len[j],
+                                           reinterpret_cast<uint8_t*>(R->dev[s]), splits[j],
+                                           reinterpret_cast<uint8_t*>(R->dev_lit[s]), R->d_error));
+                        } else {
+                            M3D_LAUNCH(ctx, KF_ZARR_ZSTD, q,
+                                       blosc_zstd_decode_kernel<<<(unsigned)((warps + 1) / 2), 64, 0, q>>>(
+                                           reinterpret_cast<const uint8_t*>(R->dev_comp[s]), comp_len[j],
+                                           reinterpret_cast<uint8_t*>(R->dev[s]), splits[j],
+                                           reinterpret_cast<uint8_t*>(R->dev_lit[s]), R->d_error));
+                        }
                         cuda_ok(cudaGetLastError());
                     }
                 } else if (cuda_ok(cudaMemcpyAsync(R->dev_comp[s], R->pinned[s], (size_t)comp_len[j], cudaMemcpyHostToDevice, q))) {

@@ -329,7 +329,9 @@ def test_builtin_zstd_decoder_equals_libzstd():
         for level in (-5, 1, 3, 5, 9, 15, 19):
             frame = _capi.zstd_host(data, True, level=level)
             assert _capi.zstd_decode_builtin(frame, len(data)) == data, (name, level)
-        assert _capi.zstd_decode_builtin(zo._compress("zstd", data, 3), len(data)) == data, name
+            assert _capi.zstd_decode_builtin(frame, len(data), lanes=True) == data, (name, level, "lanes")
+        for lanes in (False, True):
+            assert _capi.zstd_decode_builtin(zo._compress("zstd", data, 3), len(data), lanes=lanes) == data, name
     assert _capi.zstd_decode_builtin(_capi.zstd_host(b"", True), 0) == b""
     with pytest.raises(_capi.M3dError):  # does not fit
         _capi.zstd_decode_builtin(_capi.zstd_host(bytes(1000), True), 999)
@@ -344,10 +346,16 @@ def test_builtin_zstd_decoder_survives_corruption():
         bad = bytearray(frame)
         for _k in range(int(rng.integers(1, 4))):
             bad[int(rng.integers(0, len(bad)))] = int(rng.integers(0, 256))
-        try:
-            assert len(_capi.zstd_decode_builtin(bytes(bad), len(data))) <= len(data)
-        except _capi.M3dError:
-            reported += 1
+        outcomes = []
+        for lanes in (False, True):  # the two arrangements of the decoder agree on what is damage
+            try:
+                out = _capi.zstd_decode_builtin(bytes(bad), len(data), lanes=lanes)
+                assert len(out) <= len(data)
+                outcomes.append(out)
+            except _capi.M3dError:
+                outcomes.append(None)
+        assert outcomes[0] == outcomes[1]
+        reported += outcomes[0] is None
     assert reported > 500
     for cut in (0, 3, 5, 9, len(frame) // 2, len(frame) - 1):
         with pytest.raises(_capi.M3dError):
