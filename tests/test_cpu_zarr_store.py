@@ -360,3 +360,23 @@ def test_builtin_zstd_decoder_survives_corruption():
     for cut in (0, 3, 5, 9, len(frame) // 2, len(frame) - 1):
         with pytest.raises(_capi.M3dError):
             _capi.zstd_decode_builtin(bytes(frame[:cut]), len(data))
+
+
+def test_run_scoped_normalization_metadata_round_trips_on_both_stores(tmp_path):
+    """Mirror of the reference's tests/test_optimization_codeword_exclusions.py:275-299 (DS:1179-1271)."""
+    from merfish3d_analysis_b200.datastore import ArrayDataStore
+
+    cb = _codebook(4)
+    stores = [ArrayDataStore(tmp_path / "a" / "qi2labdatastore", codebook=cb),
+              zs.Qi2labZarrDataStore.create(tmp_path / "z" / "qi2labdatastore", cb)]
+    metadata = {"scope": "iterative_optimization", "excluded_gene_ids": ["GeneB"], "codebook_sha256": "abc123"}
+    for ds in stores:
+        ds.save_decode_normalization_vectors("run1", "iterative", np.ones(4, dtype=np.float32),
+                                             np.zeros(4, dtype=np.float32), decode_mode="3d", metadata=metadata)
+        assert ds.load_decode_normalization_metadata("run1", "iterative") == metadata
+        assert ds.load_decode_normalization_metadata(None, "iterative") is None
+        n, b = type(ds)(ds._datastore_path).load_decode_normalization_vectors("run1", "iterative")
+        np.testing.assert_array_equal(n, np.ones(4, dtype=np.float32))
+        np.testing.assert_array_equal(b, np.zeros(4, dtype=np.float32))
+        with pytest.raises(ValueError):
+            ds.save_decode_normalization_vectors("bad/key", "iterative", np.ones(4), np.zeros(4))
