@@ -642,14 +642,17 @@ bool read_range(const char* path, int64_t offset, int64_t length, std::vector<ui
         *missing = (errno == ENOENT);
         return *missing;
     }
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) {
+        close(fd);
+        return false;
+    }
     if (length < 0) {
-        struct stat sb;
-        if (fstat(fd, &sb) != 0) {
-            close(fd);
-            return false;
-        }
         length = (int64_t)sb.st_size - offset;
         if (length < 0) length = 0;
+    } else if (offset < 0 || offset + length > (int64_t)sb.st_size) {  // shard index entry past the end of the file
+        close(fd);
+        return false;
     }
     buf.resize((size_t)length);
     size_t got = 0;
@@ -712,7 +715,9 @@ const char* decode_chunk_bytes(const m3d_zarr_chunk& c, const Bytes& enc, int64_
         if (h.blocksize % h.typesize != 0) return "blosc: block size is not a whole number of elements";
     }
     d->mode = mode;
-    d->blocksize = (h.flags & FLAG_MEMCPY) ? expected : h.blocksize;
+    // un-shuffled data is already linear: placing it block by block would drop the bytes of an element that
+    // straddles a block edge when the block size is not a multiple of the array's element size
+    d->blocksize = ((h.flags & FLAG_MEMCPY) || mode == SH_NONE) ? expected : h.blocksize;
     return nullptr;
 }
 
@@ -1181,6 +1186,7 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
     std::vector<Decoded> info((size_t)n_chunks);
     std::vector<int64_t> comp_len((size_t)n_chunks, 0);
     std::vector<int> splits((size_t)n_chunks, 1);
+    std::vector<int64_t> frame_blocksize((size_t)n_chunks, 0);  // Blosc block size of frames the device decodes
     std::mutex mu;
     std::condition_variable cv;
     std::atomic<int> next{0};
@@ -1189,7 +1195,9 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
     const int device = ctx->device;
     const bool gpu_lz4 = getenv("M3D_ZARR_HOST_LZ4") == nullptr;
     const char* gz = getenv("M3D_ZARR_GPU_ZSTD");
-    const int gpu_zstd_mode = gz ? atoi(gz) : 0;  // device zstd decoder, opt-in: 1 = lane-serial, 2 = team of lanes
+    const int gpu_zstd_mode = (gz && *gz) ? atoi(gz) : 0;  // device zstd decoder, opt-in: 1 = lane-serial, 2 = team of lanes
+    if (gpu_zstd_mode < 0 || gpu_zstd_mode > 2 || (gz && *gz && gpu_zstd_mode == 0 && strcmp(gz, "0") != 0))
+        return m3d_fail(M3D_ERR_ARG, "M3D_ZARR_GPU_ZSTD must be 0, 1 or 2 (got '%s')", gz);
     const bool gpu_zstd = gpu_zstd_mode != 0;
     std::vector<char> on_gpu_zstd((size_t)n_chunks, 0);
     const char* mm = getenv("M3D_ZARR_MMAP");
@@ -1221,14 +1229,21 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
                 if (fd < 0) {
                     if (errno != ENOENT) return fail(std::string("zarr: cannot open ") + c.path);
                     k = MISSING;
-                } else if (length < 0) {
+                } else {
                     struct stat sb;
                     if (fstat(fd, &sb) != 0) {
                         close(fd);
                         return fail(std::string("zarr: cannot stat ") + c.path);
                     }
-                    length = (int64_t)sb.st_size - c.offset;
-                    if (length < 0) length = 0;
+                    if (length < 0) {
+                        length = (int64_t)sb.st_size - c.offset;
+                        if (length < 0) length = 0;
+                    } else if (c.offset < 0 || c.offset + length > (int64_t)sb.st_size) {
+                        // a shard index entry that points past the end of a truncated shard: reading the mapping
+                        // would raise SIGBUS, so it is refused here like the pread paths refuse it
+                        close(fd);
+                        return fail(std::string("zarr: chunk byte range lies outside ") + c.path);
+                    }
                 }
             }
             auto read_into = [&](uint8_t* dst, int64_t from, int64_t n) {
@@ -1247,7 +1262,12 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
                 ((gpu_lz4 && h.codec == BLOSC_LZ4) || (gpu_zstd && h.codec == BLOSC_ZSTD)) &&
                 !(h.flags & FLAG_MEMCPY) && h.nbytes == expected && h.blocksize % h.typesize == 0 &&
                 (h.typesize == c.elem_size || !(h.flags & (FLAG_SHUFFLE | FLAG_BITSHUFFLE))) &&
-                BLOSC_HEADER + 4 * ((h.nbytes + h.blocksize - 1) / h.blocksize) <= length)
+                BLOSC_HEADER + 4 * ((h.nbytes + h.blocksize - 1) / h.blocksize) <= length &&
+                // the device zstd decoder needs 128 KiB of literal scratch per stream: frames cut into so many
+                // blocks that this passes 256 MiB per slot are decoded by the host threads instead
+                (h.codec != BLOSC_ZSTD ||
+                 ((h.nbytes + h.blocksize - 1) / h.blocksize) * (int64_t)(h.typesize <= MAX_SPLITS ? h.typesize : 1) *
+                         (int64_t)m3d_zstd::MAX_BLOCK <= ((int64_t)256 << 20)))
                 k = GPU_LZ4;
             // the encoded chunk: mapped straight from the page cache (no copy; M3D_ZARR_MMAP=0 reads it instead)
             Bytes src;
@@ -1298,9 +1318,10 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
                     comp_len[j] = length;
                     on_gpu_zstd[j] = h.codec == BLOSC_ZSTD;
                     splits[j] = ((h.flags & FLAG_DONT_SPLIT) || h.typesize > MAX_SPLITS) ? 1 : h.typesize;
-                    info[j].blocksize = h.blocksize;
                     info[j].mode = ((h.flags & FLAG_SHUFFLE) && h.typesize > 1) ? SH_BYTE
                                    : (h.flags & FLAG_BITSHUFFLE) ? SH_BIT : SH_NONE;
+                    info[j].blocksize = info[j].mode == SH_NONE ? expected : h.blocksize;  // linear data: one block
+                    frame_blocksize[j] = h.blocksize;
                 } else if (const char* err = decode_chunk_bytes(c, src, expected, slot, &info[j])) {
                     close(fd);
                     return fail(std::string(err) + " (" + c.path + ")");
@@ -1347,7 +1368,7 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
             const ChunkGeom g = geom_of(c, info[j]);
             if (kind[j] == GPU_LZ4) {
                 any_gpu = true;
-                const int64_t nblocks = (g.nbytes + g.blocksize - 1) / g.blocksize;
+                const int64_t nblocks = (g.nbytes + frame_blocksize[j] - 1) / frame_blocksize[j];
                 const int64_t warps = nblocks * splits[j];
                 if (on_gpu_zstd[j]) {
                     const size_t need = (size_t)warps * m3d_zstd::MAX_BLOCK;

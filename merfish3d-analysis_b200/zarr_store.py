@@ -170,9 +170,21 @@ class ZarrArray:
         except FileNotFoundError:
             return None
         body = raw[: n * 16]
+        if len(body) != n * 16:
+            raise ZarrFormatError(f"{f}: shard smaller than its index")
         if self._index_crc and struct.unpack("<I", raw[n * 16 :])[0] != crc32c(body):
             raise ZarrFormatError(f"{f}: shard index checksum mismatch")
-        return np.frombuffer(body, dtype="<u8").reshape(tuple(per) + (2,))
+        index = np.frombuffer(body, dtype="<u8").reshape(tuple(per) + (2,))
+        # every entry must lie inside the shard file (a truncated shard keeps a valid-looking index): the C reader
+        # refuses such ranges too, this reports it when the table is built
+        file_size = f.stat().st_size
+        flat = index.reshape(-1, 2)
+        present = ~((flat[:, 0] == _ABSENT) & (flat[:, 1] == _ABSENT))
+        if present.any():
+            off, nb = flat[present, 0].astype(np.float64), flat[present, 1].astype(np.float64)
+            if ((off + nb) > file_size).any():
+                raise ZarrFormatError(f"{f}: shard index points outside the file ({file_size} bytes)")
+        return index
 
     def chunk_records(self, dst_addr: int, z0: int = 0, z1: int | None = None, piece: int = 0) -> list[dict]:
         """``m3d_zarr_chunk`` records that fill planes [z0, z1) of every (z, y, x) volume of the array into a

@@ -160,6 +160,46 @@ def test_malformed_input_raises(tmp_path):
         zs.ZarrImage(tmp_path / "nothing.ome.zarr")
 
 
+def test_truncated_shard_with_a_valid_index_is_an_error_not_a_fault(tmp_path):
+    """A shard whose index survives (index at the start, or re-appended) but whose chunk bytes are cut off: the
+    byte range of an entry lies past the end of the file.  Refused when the chunk table is built and again by the C
+    reader (which maps the range: touching it would be SIGBUS)."""
+    a = np.random.default_rng(5).poisson(100, (16, 64, 64)).astype(np.uint16)
+    zo.write_ome_image(tmp_path / "img.ome.zarr", a, chunks=(8, 32, 32), shards=(16, 64, 64))
+    shard = next(f for f in (tmp_path / "img.ome.zarr" / "0" / "c").rglob("*") if f.is_file())
+    good = shard.read_bytes()
+    img = zs.ZarrImage(tmp_path / "img.ome.zarr")
+    arr = img.array
+    n_index = 8 * 16 + (4 if arr._index_crc else 0)
+    assert arr._index_at_end
+    cut = good[: (len(good) - n_index) // 2] + good[-n_index:]  # half of the chunk bytes gone, index intact
+    shard.write_bytes(cut)
+    with pytest.raises(ValueError):
+        np.asarray(zs.ZarrImage(tmp_path / "img.ome.zarr"))
+    # the C reader on its own (a table built from the intact file, read after the truncation)
+    shard.write_bytes(good)
+    dst = np.zeros(a.shape, dtype=a.dtype)
+    table = arr.chunk_table(dst.ctypes.data)
+    shard.write_bytes(cut)
+    with pytest.raises(_capi.M3dError):
+        _capi.zarr_read_chunks_host(table)
+    shard.write_bytes(good)
+    _capi.zarr_read_chunks_host(table)
+    np.testing.assert_array_equal(dst, a)
+
+
+def test_unshuffled_typesize_one_frame_with_odd_block_size(tmp_path):
+    """A Blosc frame written with typesize 1 and no shuffle for a uint16 array, block size not a multiple of the
+    element size: the decoded bytes are linear, so elements straddling a block edge must survive placement."""
+    a = np.random.default_rng(6).poisson(300, (8, 32, 32)).astype(np.uint16)
+    zo.write_ome_image(tmp_path / "img.ome.zarr", a, chunks=(8, 32, 32), compression="blosc-zstd")
+    f = tmp_path / "img.ome.zarr" / "0" / "c" / "0" / "0" / "0"
+    f.write_bytes(zo.blosc_compress(a.tobytes(), typesize=1, cname="zstd", shuffle="noshuffle", blocksize=4099))
+    np.testing.assert_array_equal(np.asarray(zs.ZarrImage(tmp_path / "img.ome.zarr")), a)
+    f.write_bytes(zo.blosc_compress(a.tobytes(), typesize=1, cname="lz4", shuffle="noshuffle", blocksize=4099))
+    np.testing.assert_array_equal(np.asarray(zs.ZarrImage(tmp_path / "img.ome.zarr")), a)
+
+
 def _codebook(n_bits=8):
     rows = [["gene%d" % i] + [int((i >> b) & 1) for b in range(n_bits)] for i in range(1, 6)]
     return pd.DataFrame(rows, columns=["gene_id"] + [f"bit{i:02d}" for i in range(1, n_bits + 1)])

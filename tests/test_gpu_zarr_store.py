@@ -240,16 +240,19 @@ def test_optimizer_and_all_tiles_from_a_reference_layout_store(tmp_path):
     pd.testing.assert_frame_equal(d1.decoded_barcodes, d2.decoded_barcodes)
 
 
-def test_device_zstd_decoder_opt_in(tmp_path, ctx, monkeypatch, capsys):
-    """M3D_ZARR_GPU_ZSTD=1: Blosc-zstd frames cross PCIe compressed and `blosc_zstd_decode_kernel` runs the library's
-    own zstd decoder (csrc/zstd_decode.cuh, pinned to libzstd on the CPU) on the device -- first, lane-serial version."""
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_device_zstd_decoder_opt_in(tmp_path, ctx, monkeypatch, capsys, mode):
+    """M3D_ZARR_GPU_ZSTD=1|2: Blosc-zstd frames cross PCIe compressed and the library's own zstd decoder
+    (csrc/zstd_decode.cuh, pinned to libzstd on the CPU) runs on the device -- mode 1 lane-serial
+    (`blosc_zstd_decode_kernel`), mode 2 a warp as a team (`blosc_zstd_decode_kernel_v2`, csrc/zstd_lanes.cuh).
+    Both must reproduce the host decode bit for bit and report a damaged frame."""
     import time
 
     import torch
     from merfish3d_analysis_b200 import zarr_store as zs
     from merfish3d_analysis_b200._capi import M3dError
 
-    monkeypatch.setenv("M3D_ZARR_GPU_ZSTD", "1")
+    monkeypatch.setenv("M3D_ZARR_GPU_ZSTD", mode)
     rng = np.random.default_rng(21)
     for shape, dtype, chunks, tdt in (((24, 64, 64), np.uint16, (8, 32, 32), torch.uint16),
                                       ((20, 70, 90), np.float32, (8, 32, 48), torch.float32),
@@ -270,7 +273,7 @@ def test_device_zstd_decoder_opt_in(tmp_path, ctx, monkeypatch, capsys):
         np.testing.assert_array_equal(dst.cpu().numpy(), a)
         assert ctx.launches_by_kernel().get("blosc_zstd_decode_kernel", 0) > before
         with capsys.disabled():
-            print(f"\n[device zstd] {shape} {np.dtype(dtype).name}: {a.nbytes / 1e6:.2f} MB in {dt * 1e3:.1f} ms")
+            print(f"\n[device zstd mode {mode}] {shape} {np.dtype(dtype).name}: {a.nbytes / 1e6:.2f} MB in {dt * 1e3:.1f} ms")
     f = tmp_path / "z64.ome.zarr" / "0" / "c" / "1" / "1" / "0"
     good = f.read_bytes()
     f.write_bytes(good[:40] + bytes(len(good) - 40))
@@ -278,3 +281,48 @@ def test_device_zstd_decoder_opt_in(tmp_path, ctx, monkeypatch, capsys):
     with pytest.raises(M3dError):
         zs.transfer(ctx, [(zs.ZarrImage(tmp_path / "z64.ome.zarr"), dst)])
     torch.cuda.synchronize()
+
+
+def test_device_zstd_mode_values_are_validated(tmp_path, ctx, monkeypatch):
+    """Only 0, 1 and 2 select a decoder; anything else is refused instead of silently picking one."""
+    import torch
+    from merfish3d_analysis_b200 import zarr_store as zs
+    from merfish3d_analysis_b200._capi import M3dError
+
+    a = _image(np.random.default_rng(3), (8, 32, 32), np.uint16)
+    zs.write_ome_image(tmp_path / "v", a, chunks=(8, 32, 32), compression="blosc-zstd")
+    img = zs.ZarrImage(tmp_path / "v.ome.zarr")
+    dst = torch.zeros(a.shape, dtype=torch.uint16, device=ctx.device)
+    for bad in ("3", "-1", "yes"):
+        monkeypatch.setenv("M3D_ZARR_GPU_ZSTD", bad)
+        with pytest.raises(M3dError):
+            zs.transfer(ctx, [(img, dst)])
+    monkeypatch.setenv("M3D_ZARR_GPU_ZSTD", "0")
+    zs.transfer(ctx, [(img, dst)])
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(dst.cpu().numpy(), a)
+
+
+def test_truncated_shard_is_an_error_on_the_device_path(tmp_path, ctx):
+    """The device reader maps chunk byte ranges from the page cache: a shard index entry past the end of a truncated
+    shard must come back as an error (the mapping would raise SIGBUS)."""
+    import torch
+    from merfish3d_analysis_b200 import zarr_store as zs
+    from merfish3d_analysis_b200._capi import M3dError
+
+    a = _image(np.random.default_rng(4), (16, 64, 64), np.uint16)
+    zs.write_ome_image(tmp_path / "s", a, chunks=(8, 32, 32), shards=(16, 64, 64), compression="blosc-zstd")
+    shard = next(f for f in (tmp_path / "s.ome.zarr" / "0" / "c").rglob("*") if f.is_file())
+    good = shard.read_bytes()
+    arr = zs.ZarrImage(tmp_path / "s.ome.zarr").array
+    dst = torch.zeros(a.shape, dtype=torch.uint16, device=ctx.device)
+    table = arr.chunk_table(dst.data_ptr())
+    n_index = 8 * 16 + (4 if arr._index_crc else 0)
+    shard.write_bytes(good[: (len(good) - n_index) // 2] + good[-n_index:])
+    with pytest.raises(M3dError):
+        ctx.zarr_read(table)
+    torch.cuda.synchronize()
+    shard.write_bytes(good)
+    ctx.zarr_read(table)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(dst.cpu().numpy(), a)
