@@ -15,8 +15,10 @@ What differs from the reference by design
   * multi-GPU work runs on persistent ranks (``torch.distributed``) or, without a
     launcher, on one host thread per device -- never a process spawn per iteration.
 
-Out of scope here: decode-time warping with non-identity transforms,
-transcript filters / de-duplication / cell assignment, chromatic-affine estimation.
+Also built behind this class (SURVEY.md 8f "next" rows): the decode-time warp of unregistered bits (affine and
+SOFIMA flow), the pooled table stage (blank-fraction / LR filter, de-duplication, cell assignment) and the
+optimiser's per-on-bit weighted centroids.  Out of scope: chromatic-affine ESTIMATION, cell-restricted
+normalisation, napari display.
 """
 
 from __future__ import annotations
@@ -145,6 +147,13 @@ class PixelDecoder:
         self._contexts: dict[int, DecodeContext] = {}
         self._context_excluded: dict[int, tuple] = {}
         self._device_state: dict[int, dict] = {}
+        # decode inputs kept in HBM across the optimiser's iterations (None = caching off)
+        self._tile_cache: dict[tuple, tuple] | None = None
+        self._tile_cache_budget = 0
+        self._tile_cache_used = 0
+        self._tile_cache_last_bytes = 0
+        self._tile_cache_stats = {"hits": 0, "misses": 0, "resident_tiles": 0, "resident_bytes": 0, "budget_bytes": 0}
+        self._profile: dict[str, float] | None = None  # host wall-clock split of the per-tile call (bench / probes)
 
     # ================================================================== codebook (PD:756-932)
     def _load_codebook(self) -> None:
@@ -531,12 +540,24 @@ class PixelDecoder:
         import torch
 
         st = self._device_state.setdefault(gpu_id, {})
+        key = self._stage_key(self._tile_idx, gpu_id, z_bounds, lowpass_sigma)
+        cache = self._tile_cache
+        if cache is not None and key in cache:
+            # the optimiser's later iterations: the decode input of this tile is still in HBM
+            # (already weighted / warped / low-passed) -- no datastore read, no PCIe, no filter
+            new_state, meta = cache[key]
+            self._tile_cache_stats["hits"] += 1
+            st.clear()
+            st.update(new_state)
+            self._em_wvl, self._full_z = meta["em_wvl"], meta["full_z"]
+            self._load_coordinate_metadata()
+            return
         staged = self._take_prefetched(self._tile_idx, gpu_id, z_bounds, lowpass_sigma)
         if staged is None:
             st.clear()  # release the previous tile before staging this one
             # same buffer set as the previous tile: this stream's order already protects it
             staged = self._stage_tile(self._tile_idx, gpu_id, z_bounds, lowpass_sigma,
-                                      slot=self._slot.get(gpu_id, 0))
+                                      slot=self._slot.get(gpu_id, 0), fresh_final=self._tile_cache_admit())
         new_state, meta = staged
         ready = meta.get("ready")
         if ready is not None:  # staged on the prefetch stream: order it before this stream's kernels
@@ -545,11 +566,82 @@ class PixelDecoder:
             self._slot[gpu_id] = meta["slot"]
         st.clear()
         st.update(new_state)
+        if cache is not None:
+            self._tile_cache_stats["misses"] += 1
+            if meta.get("fresh_final"):
+                self._tile_cache_insert(key, new_state, meta)
         self._em_wvl, self._full_z = meta["em_wvl"], meta["full_z"]
         self._load_coordinate_metadata()
 
+    # ------------------------------------------------------------------ decode inputs kept in HBM (optimiser)
+    @staticmethod
+    def _stage_key(tile_idx, gpu_id, z_bounds, lowpass_sigma) -> tuple:
+        return (tile_idx, gpu_id, None if z_bounds is None else tuple(z_bounds),
+                None if lowpass_sigma is None else tuple(float(v) for v in lowpass_sigma))
+
+    def _tile_cache_begin(self, gpu_id: int, budget_bytes: int | None = None) -> None:
+        """Start keeping staged decode inputs in HBM.  The optimiser decodes the SAME tiles in every iteration
+        and only the two normalisation vectors change (PD:4689-4751; the reference re-spawns its workers and
+        re-loads every tile per iteration, PD:4702-4729), so after the first pass an iteration is
+        ``set_normalization -> decode + label -> features -> exchange`` with no PCIe traffic and no re-filtering.
+
+        Budget: ``budget_bytes`` / ``$M3D_TILE_CACHE_GB``, else 55 % of the device memory that is free now -- the
+        rest stays for the two staging slots of the tiles that stream through, the labelling scratch and the
+        low-pass temporaries.  Tiles are admitted in the order they are first decoded until the budget is used and
+        are never evicted: the access pattern is cyclic, so keeping a fixed subset resident is what maximises hits
+        (LRU would evict every tile just before its next use).  Tiles beyond the budget keep streaming through the
+        double-buffered upload path."""
+        import os
+
+        import torch
+
+        if budget_bytes is None:
+            env = os.environ.get("M3D_TILE_CACHE_GB")
+            if env is not None:
+                budget_bytes = int(float(env) * 1e9)
+            else:
+                dev = self._ctx(gpu_id).device
+                free, _total = torch.cuda.mem_get_info(dev)
+                reusable = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+                budget_bytes = int(0.55 * (free + max(reusable, 0)))
+        self._tile_cache = {}
+        self._tile_cache_budget = max(int(budget_bytes), 0)
+        self._tile_cache_used = 0
+        self._tile_cache_last_bytes = 0
+        self._tile_cache_stats = {"hits": 0, "misses": 0, "resident_tiles": 0, "resident_bytes": 0,
+                                  "budget_bytes": self._tile_cache_budget}
+
+    def _tile_cache_end(self) -> None:
+        self._tile_cache = None
+        self._tile_cache_used = 0
+
+    def _tile_cache_admit(self) -> bool:
+        """Would one more tile (of the size last seen) fit the budget?  Decided before staging so that the tile's
+        final buffer is allocated outside the recycled staging slots."""
+        if self._tile_cache is None:
+            return False
+        return self._tile_cache_used + self._tile_cache_last_bytes <= self._tile_cache_budget and \
+            self._tile_cache_budget > 0
+
+    def _tile_cache_insert(self, key, state: dict, meta: dict) -> None:
+        nbytes = sum(int(t.numel()) * int(t.element_size()) for t in state.values() if hasattr(t, "element_size"))
+        self._tile_cache_last_bytes = nbytes
+        if self._tile_cache_used + nbytes > self._tile_cache_budget:
+            return  # the size guess was too small: this tile keeps streaming
+        self._tile_cache[key] = (dict(state), {"em_wvl": meta["em_wvl"], "full_z": meta["full_z"]})
+        self._tile_cache_used += nbytes
+        self._tile_cache_stats["resident_tiles"] = len(self._tile_cache)
+        self._tile_cache_stats["resident_bytes"] = self._tile_cache_used
+
+    def _release_staging_buffers(self) -> None:
+        """Drop the two staging slots (kept: the persistent decoded image).  Used once every tile of this rank is
+        resident in the cache."""
+        self._drop_prefetched()
+        for k in [k for k in self._buffers if k[1] != "dec"]:
+            del self._buffers[k]
+
     # ------------------------------------------------------------------ next-tile prefetch
-    def _schedule_prefetch(self, tile_idx, gpu_id: int, z_bounds, lowpass_sigma) -> None:
+    def _schedule_prefetch(self, tile_idx, gpu_id: int, z_bounds, lowpass_sigma, fresh_final: bool = False) -> None:
         """Stage ``tile_idx`` (datastore reads, host -> device copies, per-bit low-pass) on a side stream
         from a helper thread while the current tile is decoded, annotated and saved.  Multi-tile loops
         (``decode_all_tiles``, the optimiser) are transfer-bound: 13.4 GB over PCIe per tile against a few
@@ -575,14 +667,14 @@ class PixelDecoder:
             torch.cuda.set_device(ctx.device)
             with torch.cuda.stream(stream):
                 stream.wait_event(idle)
-                st, meta = self._stage_tile(tile_idx, gpu_id, z_bounds, lowpass_sigma, slot=slot, alloc_stream=main)
+                st, meta = self._stage_tile(tile_idx, gpu_id, z_bounds, lowpass_sigma, slot=slot, alloc_stream=main,
+                                            fresh_final=fresh_final)
                 ev = torch.cuda.Event()
                 ev.record(stream)
                 meta["ready"] = ev
             return st, meta
 
-        key = (tile_idx, gpu_id, None if z_bounds is None else tuple(z_bounds),
-               None if lowpass_sigma is None else tuple(float(v) for v in lowpass_sigma))
+        key = self._stage_key(tile_idx, gpu_id, z_bounds, lowpass_sigma)
         self._prefetched = (key, self._prefetch_pool.submit(job))
 
     def _take_prefetched(self, tile_idx, gpu_id: int, z_bounds, lowpass_sigma):
@@ -590,8 +682,7 @@ class PixelDecoder:
             return None
         key, fut = self._prefetched
         self._prefetched = None
-        want = (tile_idx, gpu_id, None if z_bounds is None else tuple(z_bounds),
-                None if lowpass_sigma is None else tuple(float(v) for v in lowpass_sigma))
+        want = self._stage_key(tile_idx, gpu_id, z_bounds, lowpass_sigma)
         try:
             staged = fut.result()
         except Exception:  # the synchronous path below reports the error with its real traceback
@@ -629,7 +720,7 @@ class PixelDecoder:
         return t
 
     def _stage_tile(self, tile_idx, gpu_id: int = 0, z_bounds: tuple[int, int] | None = None, lowpass_sigma=None,
-                    slot=None, alloc_stream=None):
+                    slot=None, alloc_stream=None, fresh_final: bool = False):
         """PD:1828-1946: gather the tile's bit volumes into one device stack.  Returns
         ``(state dict, {"em_wvl", "full_z"})`` and touches no per-tile attribute of ``self``, so it can
         run ahead on the prefetch thread / stream.
@@ -640,11 +731,16 @@ class PixelDecoder:
         Otherwise the reference's warp (PD:1882-1889) runs on the device per bit --
         ``m3d_warp_affine`` with the predictor multiply fused -- and the state holds the float32
         ``stack`` directly.  ``z_bounds`` (z-slab sharding) selects planes [a, b) of the z-cropped
-        volume; warped bits still read their full input volume."""
+        volume; warped bits still read their full input volume.  ``fresh_final``: the buffer(s) the decode
+        kernels will read are allocated fresh instead of taken from the recycled staging slot, so that the caller
+        can keep them (the optimiser's tile cache); intermediates still use the slot."""
         import torch
 
         ctx = self._ctx(gpu_id)
         bit_ids = list(self._datastore.bit_ids)[0 : self._n_merfish_bits]
+
+        def final_buffer(name, shape_, dtype_):
+            return self._tile_buffer(gpu_id, None if fresh_final else slot, name, shape_, dtype_, ctx.device, alloc_stream)
         loaded = []
         em_wvl = []
         # issue every read first, then collect: a datastore that returns real futures (tensorstore
@@ -689,11 +785,12 @@ class PixelDecoder:
             if any(pa is not None for _r, pa, _w in loaded):
                 rawp = self._tile_buffer(gpu_id, slot, "native_pred", (n_b, *native), torch.float32, ctx.device,
                                          alloc_stream)
-            stack = self._tile_buffer(gpu_id, slot, "warped", (n_b, *shape), torch.float32, ctx.device, alloc_stream)
             lp_out = None
             if lowpass_sigma is not None:
-                lp_out = self._tile_buffer(gpu_id, slot, "lowpassed", (n_b, *shape), torch.float32, ctx.device,
-                                           alloc_stream)
+                stack = self._tile_buffer(gpu_id, slot, "warped", (n_b, *shape), torch.float32, ctx.device, alloc_stream)
+                lp_out = final_buffer("lowpassed", (n_b, *shape), torch.float32)
+            else:
+                stack = final_buffer("warped", (n_b, *shape), torch.float32)
             for _ra, _pa, warp in loaded:  # flow fields go up first: the staging ring is not re-entrant
                 if isinstance(warp, dict) and "flow_dev" not in warp:
                     warp["flow_dev"] = torch.empty(warp["flow"].shape, dtype=torch.float32, device=ctx.device)
@@ -725,16 +822,20 @@ class PixelDecoder:
             st["stack"] = stack if lp_out is None else lp_out
             if lp_out is not None:
                 st["lowpass_done"] = True
-            return st, {"em_wvl": em_wvl, "full_z": full_z, "slot": slot}
+            return st, {"em_wvl": em_wvl, "full_z": full_z, "slot": slot, "fresh_final": fresh_final}
         else:
             dt = torch.float32 if float_input else torch.uint16
             if z_bounds is not None:
                 slot = None  # z-slabs keep several stacks alive at once: fresh tensors
             full = (len(bit_ids), *shape)
-            stack = self._tile_buffer(gpu_id, slot, "stack", full, dt, ctx.device, alloc_stream)
-            pred = None
-            if any(pa is not None for _r, pa, _w in loaded):
-                pred = self._tile_buffer(gpu_id, slot, "pred", full, torch.float32, ctx.device, alloc_stream)
+            has_pred = any(pa is not None for _r, pa, _w in loaded)
+            if lowpass_sigma is None:  # the uploaded volumes ARE the decode input
+                stack = final_buffer("stack", full, dt)
+                pred = final_buffer("pred", full, torch.float32) if has_pred else None
+            else:
+                stack = self._tile_buffer(gpu_id, slot, "stack", full, dt, ctx.device, alloc_stream)
+                pred = self._tile_buffer(gpu_id, slot, "pred", full, torch.float32, ctx.device, alloc_stream) \
+                    if has_pred else None
             pieces, piece_bit = [], []  # per bit: readout, then its predictor weights (if stored)
             for i, (ra, pa, _w) in enumerate(loaded):
                 pieces.append((_zs.host_piece(ra, a, b, npdt), stack[i]))
@@ -750,11 +851,10 @@ class PixelDecoder:
                 st["readout"], st["predictor"] = stack, pred
             else:
                 st["readout"], st["predictor"] = None, None
-                out = self._tile_buffer(gpu_id, slot, "lowpassed", full, torch.float32, ctx.device, alloc_stream)
+                out = final_buffer("lowpassed", full, torch.float32)
                 st["stack"] = self._upload_and_lowpass(ctx, pieces, piece_bit, stack, pred, lowpass_sigma, out)
                 st["lowpass_done"] = True
-            return st, {"em_wvl": em_wvl, "full_z": full_z, "slot": slot}
-        return st, {"em_wvl": em_wvl, "full_z": full_z}
+            return st, {"em_wvl": em_wvl, "full_z": full_z, "slot": slot, "fresh_final": fresh_final}
 
     def _upload_pipelined(self, ctx, pieces, piece_bit, on_bit):
         """Upload ``pieces`` on a copy stream and call ``on_bit(b)`` -- with the compute stream current and already
@@ -1184,15 +1284,26 @@ class PixelDecoder:
             magnitude_threshold = DEFAULT_DECODE_MAGNITUDE_THRESHOLD
         if minimum_pixels is None:
             minimum_pixels = self._default_minimum_pixels()
+        import time as _time
+
+        prof = self._profile
+        t0 = _time.perf_counter()
         self._prepare_normalization_state(normalization_method, use_normalization, gpu_id, lowpass_sigma)
         self._tile_idx = tile_idx
         sigma = self._effective_lowpass_sigma(lowpass_sigma)
         lp_active = self._lowpass_active(sigma)
+        t1 = _time.perf_counter()
         self._load_bit_data(feature_predictor_threshold=feature_predictor_threshold, gpu_id=gpu_id,
                             lowpass_sigma=sigma if lp_active else None)
-        nxt, self._next_tile_hint = self._next_tile_hint, None
-        if nxt is not None and _is_identity_store(self._datastore):
-            self._schedule_prefetch(nxt, gpu_id, None, sigma if lp_active else None)
+        self._prefetch_upcoming(gpu_id, sigma if lp_active else None)
+        if prof is not None:
+            if prof.get("sync"):  # attribute the staged copies / filters to "stage", not to the decode that waits for them
+                import torch
+
+                torch.cuda.synchronize(self._ctx(gpu_id).device)
+            t2 = _time.perf_counter()
+            prof["vectors_s"] = prof.get("vectors_s", 0.0) + (t1 - t0)
+            prof["stage_s"] = prof.get("stage_s", 0.0) + (t2 - t1)
         self._filter_type = "raw"
         if lp_active:
             if self._device_state[gpu_id].get("lowpass_done"):
@@ -1206,6 +1317,9 @@ class PixelDecoder:
         finally:
             self._fuse_label_args = None
         self._extract_barcodes(minimum_pixels=minimum_pixels, gpu_id=gpu_id)
+        if prof is not None:
+            prof["decode_extract_s"] = prof.get("decode_extract_s", 0.0) + (_time.perf_counter() - t2)
+            prof["tiles"] = prof.get("tiles", 0) + 1
         if return_results:
             import torch
 
@@ -1221,6 +1335,32 @@ class PixelDecoder:
                 st["decoded"].cpu().numpy(),
             )
         return None
+
+    def _prefetch_upcoming(self, gpu_id: int, sigma) -> None:
+        """Multi-tile loops: stage the next tile that is not already resident (tile cache) on the side stream while
+        this one is decoded, annotated and saved.  Works for registered and unregistered stores alike: the per-bit
+        warp / low-pass kernels of the staged tile run on the prefetch stream, and the staging ring, the copy stream
+        and the buffers are per thread / per slot."""
+        upcoming = list(getattr(self, "_upcoming_tiles", None) or [])
+        nxt, self._next_tile_hint = self._next_tile_hint, None
+        if nxt is not None and nxt not in upcoming:
+            upcoming.insert(0, nxt)
+        self._upcoming_tiles = None
+        for t in upcoming:
+            key = self._stage_key(t, gpu_id, None, sigma)
+            if self._tile_cache is not None and key in self._tile_cache:
+                continue  # resident: nothing to stage; look further ahead
+            if self._prefetched is not None and self._prefetched[0] == key:
+                return  # already on its way
+            self._schedule_prefetch(t, gpu_id, None, sigma, fresh_final=self._tile_cache_admit_next())
+            return
+
+    def _tile_cache_admit_next(self) -> bool:
+        """Admission for a tile staged AHEAD: the tile being decoded now may not have been counted yet."""
+        if self._tile_cache is None:
+            return False
+        pending = self._tile_cache_last_bytes  # the prefetched tile itself
+        return self._tile_cache_budget > 0 and self._tile_cache_used + pending <= self._tile_cache_budget
 
     # ------------------------------------------------------------------ z-slab sharding of one volume
     def decode_one_tile_sharded(
@@ -1450,32 +1590,47 @@ class PixelDecoder:
             mine = self._contiguous_chunks(list(tiles), world)[rank]
             gpu = self._local_gpu()
             for i, t in enumerate(mine):
-                self._next_tile_hint = mine[i + 1] if i + 1 < len(mine) else None
+                self._upcoming_tiles = mine[i + 1 :]
                 per_tile(self, t, gpu)
-            return
+            return mine
         n = max(1, min(int(self._num_gpus), torch.cuda.device_count() or 1))
         chunks = [c for c in self._contiguous_chunks(list(tiles), n) if c]
         if len(chunks) <= 1:
             only = chunks[0] if chunks else []
             for i, t in enumerate(only):
-                self._next_tile_hint = only[i + 1] if i + 1 < len(only) else None
+                self._upcoming_tiles = only[i + 1 :]
                 per_tile(self, t, 0)
-            return
+            return only
+
+        keep = getattr(self, "_persistent_workers", None)  # the optimiser keeps its per-GPU decoders (tile cache)
 
         def work(args):
             gpu, subset = args
             torch.cuda.set_device(gpu)
-            dec = self._worker_clone(gpu)
+            dec = keep.get(gpu) if keep is not None else None
+            if dec is None:
+                dec = self._worker_clone(gpu)
+                if keep is not None:
+                    keep[gpu] = dec
+                    if self._tile_cache is not None:
+                        dec._tile_cache_begin(gpu, self._tile_cache_budget_request)
             dec._global_normalization_vector = self._global_normalization_vector
             dec._global_background_vector = self._global_background_vector
             dec._global_normalization_loaded = self._global_normalization_loaded
+            dec._iterative_normalization_vector = None  # re-read from the datastore, like a fresh worker
+            dec._iterative_background_vector = None
+            dec._iterative_normalization_loaded = False
             for i, t in enumerate(subset):
-                dec._next_tile_hint = subset[i + 1] if i + 1 < len(subset) else None
+                dec._upcoming_tiles = subset[i + 1 :]
                 per_tile(dec, t, gpu)
-            dec._cleanup()
+            if keep is None:
+                dec._cleanup()
+            else:
+                dec._cleanup(keep_pipeline=True)
 
         with ThreadPoolExecutor(max_workers=len(chunks)) as ex:
             list(ex.map(work, list(enumerate(chunks))))
+        return None
 
     def _barrier(self):
         _r, world, dist = self._dist()
@@ -1586,17 +1741,33 @@ class PixelDecoder:
         self._excluded_gene_ids = self._optimization_excluded_gene_ids
         self._excluded_codeword_indices = excluded_idx
         rank, world, dist = self._dist()
+        import time as _time
+
+        timing = self._optimizer_timing = {"seed_s": 0.0, "iterations": []}
+        made_temp_dir = False
+        temp_dir = None
         try:
+            t_seed = _time.perf_counter()
             if rank == 0:
                 self._load_global_normalization_vectors(gpu_id=self._local_gpu(), recalculate=True,
                                                         tile_indices=tile_indices, lowpass_sigma=lowpass_sigma)
             self._barrier()
             if rank != 0:
                 self._load_global_normalization_vectors(gpu_id=self._local_gpu(), lowpass_sigma=lowpass_sigma)
-            temp_dir = Path(tempfile.mkdtemp()) if self._decode_run_key is None else \
-                self._datastore.decoded_temporary_dir(self._decode_run_key)
-            temp_dir.mkdir(parents=True, exist_ok=True)
+            timing["seed_s"] = _time.perf_counter() - t_seed
+            if self._decode_run_key is None:
+                # tables travel in memory (all_gather); the scratch directory exists only for `_keep_temp_tables`
+                # debugging and is removed by the rank that made it
+                temp_dir = Path(tempfile.mkdtemp())
+                made_temp_dir = True
+            else:
+                temp_dir = self._datastore.decoded_temporary_dir(self._decode_run_key)
+                temp_dir.mkdir(parents=True, exist_ok=True)
             self._temp_dir = temp_dir
+            # decode inputs stay in HBM from the first iteration on (budgeted; see _tile_cache_begin)
+            self._tile_cache_budget_request = getattr(self, "tile_cache_budget_bytes", None)
+            self._tile_cache_begin(self._local_gpu(), self._tile_cache_budget_request)
+            self._persistent_workers = {}
             if tile_indices is not None:
                 random_tiles = list(tile_indices)
             elif len(all_tiles) > n_random_tiles:
@@ -1610,6 +1781,10 @@ class PixelDecoder:
             for iteration in range(n_iterations):
                 use_norm = iteration > 0
                 tables: list[pd.DataFrame] = []
+                t_it = _time.perf_counter()
+                prof_was = self._profile
+                self._profile = {"sync": bool(prof_was and prof_was.get("sync"))} if prof_was is not None else None
+                hits0 = self._tile_cache_stats["hits"]
 
                 def per_tile(dec, tile_idx, gpu, _use=use_norm):
                     dec.decode_one_tile(
@@ -1621,10 +1796,18 @@ class PixelDecoder:
                     dec._save_barcodes()
                     tables.append((tile_idx, dec._df_barcodes))
 
-                self._run_tiles(random_tiles, per_tile)
-                tables.sort(key=lambda t: t[0])
+                mine = self._run_tiles(random_tiles, per_tile)
+                if mine is not None and self._tile_cache is not None and mine and all(
+                        any(k[0] == t for k in self._tile_cache) for t in mine):
+                    self._release_staging_buffers()  # every tile of this rank is resident: the two slots can go
+                t_tiles = _time.perf_counter()
+                # pooled row order = tile order of `random_tiles` on one process and across ranks alike (the 2-D
+                # within-tile de-duplication breaks ties by row)
+                pos = {t: i for i, t in enumerate(random_tiles)}
+                tables.sort(key=lambda t: pos.get(t[0], len(pos)))
                 local = pd.concat([t[1] for t in tables], ignore_index=True) if tables else pd.DataFrame()
                 pooled = self._gather_tables(local)
+                t_gather = _time.perf_counter()
                 if len(pooled) == 0 and "gene_id" not in pooled.columns:
                     pooled = pd.DataFrame({"gene_id": pd.Series(dtype="string")})
                 g = pooled["gene_id"]
@@ -1643,12 +1826,27 @@ class PixelDecoder:
                     self._load_iterative_normalization_vectors(gpu_id=self._local_gpu())
                 self._global_background_vector = None
                 self._global_normalization_vector = None
+                t_end = _time.perf_counter()
+                it = {"iteration": iteration, "total_s": t_end - t_it, "tiles_s": t_tiles - t_it,
+                      "exchange_s": t_gather - t_tiles, "vectors_s": t_end - t_gather,
+                      "tiles_this_rank": len(tables), "cache_hits": self._tile_cache_stats["hits"] - hits0,
+                      "transcripts_pooled": int(len(pooled))}
+                if self._profile is not None:
+                    it.update({k: v for k, v in self._profile.items() if k.endswith("_s")})
+                self._profile = prof_was
+                timing["iterations"].append(it)
+            timing["cache"] = dict(self._tile_cache_stats)
         finally:
             self._excluded_gene_ids, self._excluded_codeword_indices = saved_excluded
+            for w in (getattr(self, "_persistent_workers", None) or {}).values():
+                w._tile_cache_end()
+                w._cleanup()
+            self._persistent_workers = None
+            self._tile_cache_end()
             self._cleanup()
             self._optimize_normalization_weights = False
-        if self._decode_run_key is None and rank == 0:
-            shutil.rmtree(temp_dir, ignore_errors=True)
+            if made_temp_dir and temp_dir is not None:  # every rank removes the directory it made
+                shutil.rmtree(temp_dir, ignore_errors=True)
 
     def _local_gpu(self) -> int:
         import torch
@@ -1788,6 +1986,17 @@ class PixelDecoder:
             )
             dec._save_barcodes()
             dec._cleanup(keep_pipeline=True)
+
+        # Resolve the normalisation vectors ONCE before the tiles are handed out: with
+        # normalization_method="global" and nothing cached, every rank's first tile would otherwise compute its
+        # own vectors from its own unseeded random sample of tiles (PD:1018) and all ranks would write
+        # calibrations/attributes.json at the same time.  Rank 0 computes and saves, the others load.
+        rank0, _w, _d = self._dist()
+        if rank0 == 0:
+            self._prepare_normalization_state(normalization_method, True, self._local_gpu(), lowpass_sigma)
+        self._barrier()
+        if rank0 != 0:
+            self._prepare_normalization_state(normalization_method, True, self._local_gpu(), lowpass_sigma)
 
         self._run_tiles(all_tiles, per_tile)
         self._cleanup()

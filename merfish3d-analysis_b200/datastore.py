@@ -22,7 +22,9 @@ exactly like the reference's workers do (PD:249, PD:354).
 from __future__ import annotations
 
 import json
+import os
 import re
+import uuid
 from collections.abc import Mapping
 from pathlib import Path
 from typing import Any, Sequence
@@ -103,10 +105,15 @@ class ArrayDataStore:
             return v
 
         p = self._calibrations_attributes_path()
-        tmp = p.with_suffix(".json.tmp")
-        with open(tmp, "w") as f:
-            json.dump(clean(dict(attributes)), f)
-        tmp.replace(p)
+        # one temporary file per writer (ranks / worker threads may save at the same time), then an atomic replace
+        tmp = p.with_name(f"{p.name}.{os.getpid()}.{uuid.uuid4().hex}.tmp")
+        try:
+            with open(tmp, "w") as f:
+                json.dump(clean(dict(attributes)), f)
+            tmp.replace(p)
+        finally:
+            if tmp.exists():
+                tmp.unlink()
 
     def _refresh(self, attrs=None) -> None:
         attrs = self._load_calibrations_attributes() if attrs is None else attrs

@@ -68,3 +68,68 @@ def test_cuda_optimizer_equals_reference_golden(tmp_path):
     np.testing.assert_array_equal(g_b, g["global_background"])
     np.testing.assert_array_equal(i_n, g["iterative_normalization"])
     np.testing.assert_array_equal(i_b, g["iterative_background"])
+
+
+@pytest.mark.parametrize("budget,lowpass", [(None, None), (0, None), ("one", None), (None, (3.0, 1.0, 1.0)), ("one", (3.0, 1.0, 1.0))])
+def test_optimizer_tile_cache_does_not_change_the_result(tmp_path, budget, lowpass):
+    """The optimiser keeps its tiles' decode inputs in HBM after the first pass (no re-upload, no re-filtering).
+    Whatever the budget -- everything resident, nothing resident, or room for one tile so that the others keep
+    streaming through the prefetch slots -- the vectors and the last iteration's tables are the same; with the
+    low-pass off they are the reference's golden vectors."""
+    from merfish3d_analysis_b200.datastore import ArrayDataStore
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    g = np.load(GOLDEN / "reference_optimizer.npz")
+    df_cb, _cb = cases.codebook16()
+    ds = ArrayDataStore(tmp_path / "qi2labdatastore", codebook=df_cb)
+    for st in g["stacks"]:
+        ds.add_tile(st)
+    tile_bytes = g["stacks"][0].nbytes * (2 if lowpass else 1)  # low-passed stacks are float32
+    dec = PixelDecoder(ds, merfish_bits=16, verbose=0)
+    if budget is not None:
+        dec.tile_cache_budget_bytes = int(tile_bytes * 1.5) if budget == "one" else int(budget)
+    dec._keep_temp_tables = True
+    kept = {}
+    orig = dec._save_barcodes
+
+    def spy():
+        kept[dec._tile_idx] = dec._df_barcodes.copy()
+        orig()
+
+    dec._save_barcodes = spy
+    dec.optimize_normalization_by_decoding(n_iterations=3, minimum_pixels=4, lowpass_sigma=lowpass,
+                                           magnitude_threshold=(0.9, 10.0), tile_indices=[0, 1, 2])
+    stats = dec._optimizer_timing["cache"]
+    want_resident = {None: 3, 0: 0, "one": 1}[budget]
+    assert stats["resident_tiles"] == want_resident, stats
+    assert stats["hits"] == 2 * want_resident and stats["misses"] == 9 - 2 * want_resident, stats
+    assert [it["cache_hits"] for it in dec._optimizer_timing["iterations"]] == [0, want_resident, want_resident]
+    i_n, i_b = ds.load_decode_normalization_vectors(None, "iterative")
+    if lowpass is None:
+        np.testing.assert_array_equal(i_n, g["iterative_normalization"])
+        np.testing.assert_array_equal(i_b, g["iterative_background"])
+    # against an uncached run of the same thing
+    ds2 = ArrayDataStore(tmp_path / "plain" / "qi2labdatastore", codebook=df_cb)
+    for st in g["stacks"]:
+        ds2.add_tile(st)
+    dec2 = PixelDecoder(ds2, merfish_bits=16, verbose=0)
+    dec2.tile_cache_budget_bytes = 0
+    kept2 = {}
+    orig2 = dec2._save_barcodes
+
+    def spy2():
+        kept2[dec2._tile_idx] = dec2._df_barcodes.copy()
+        orig2()
+
+    dec2._save_barcodes = spy2
+    dec2.optimize_normalization_by_decoding(n_iterations=3, minimum_pixels=4, lowpass_sigma=lowpass,
+                                            magnitude_threshold=(0.9, 10.0), tile_indices=[0, 1, 2])
+    p_n, p_b = ds2.load_decode_normalization_vectors(None, "iterative")
+    np.testing.assert_array_equal(i_n, p_n)
+    np.testing.assert_array_equal(i_b, p_b)
+    import pandas as pd
+
+    assert sorted(kept) == sorted(kept2) == [0, 1, 2]
+    for t in kept:
+        pd.testing.assert_frame_equal(kept[t], kept2[t])
+    assert dec._tile_cache is None and not dec._buffers  # everything released at the end

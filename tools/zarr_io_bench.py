@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--compression", default="blosc-zstd")
     ap.add_argument("--skip-host", action="store_true", help="skip leg b (host decode to arrays, then upload)")
+    ap.add_argument("--only-transfer", action="store_true", help="leg a only (store -> device)")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
 
@@ -102,6 +103,7 @@ def main():
         kt = ctx.kernel_times_ms()
         res["a_store_to_device"]["unshuffle_kernel_ms_total"] = kt.get("zarr_unshuffle_place_kernel")
         res["a_store_to_device"]["lz4_kernel_ms_total"] = kt.get("blosc_lz4_decode_kernel")
+        res["a_store_to_device"]["zstd_kernel_ms_total"] = kt.get("blosc_zstd_decode_kernel")
         ctx.set_timing(False)
 
         def run_host_then_upload():
@@ -123,6 +125,13 @@ def main():
             res["b_host_decode_then_upload"] = {"ms": 1e3 * min(ts), "host_decode_ms": 1e3 * min(th),
                                                 "decoded_gb_s": raw_bytes / min(ts) / 1e9}
 
+        res["M3D_ZARR_GPU_ZSTD"] = os.environ.get("M3D_ZARR_GPU_ZSTD", "0")
+        if args.only_transfer:
+            line = json.dumps(res)
+            print(line)
+            if args.out:
+                Path(args.out).write_text(line + "\n")
+            return
         nrm = np.full(args.bits, 900.0, dtype=np.float32)  # bench.py's vectors / thresholds
         bkg = np.full(args.bits, 200.0, dtype=np.float32)
         ds.save_decode_normalization_vectors(None, "global", nrm, bkg)

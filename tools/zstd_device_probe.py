@@ -1,4 +1,4 @@
-"""Time the opt-in device zstd decoder (M3D_ZARR_GPU_ZSTD=1) on one (16, 512, 512) uint16 chunk, ring warm."""
+"""Time the opt-in device zstd decoders (M3D_ZARR_GPU_ZSTD=1|2, argv[1]) on one (16, 512, 512) uint16 chunk, ring warm."""
 import os
 import sys
 import tempfile
@@ -7,7 +7,7 @@ from pathlib import Path
 
 import numpy as np
 
-os.environ["M3D_ZARR_GPU_ZSTD"] = "1"
+os.environ["M3D_ZARR_GPU_ZSTD"] = sys.argv[1] if len(sys.argv) > 1 else "1"
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import torch  # noqa: E402
 
@@ -34,4 +34,4 @@ with tempfile.TemporaryDirectory() as t:
         zs.transfer(ctx, [(img, dst)])
         torch.cuda.synchronize()
         ts.append((time.perf_counter() - t0) * 1e3)
-    print("wall ms per 8.4 MB chunk:", [round(v, 2) for v in ts], "kernel ms total (3 launches):", ctx.kernel_times_ms())
+    print("mode", os.environ["M3D_ZARR_GPU_ZSTD"], "wall ms per 8.4 MB chunk:", [round(v, 2) for v in ts], "kernel ms total (3 launches):", ctx.kernel_times_ms())
