@@ -50,6 +50,20 @@ GATE_BYTES_PER_VOXEL = N_BITS * 2
 CPU_SAMPLE_SHAPE = (8, 256, 256)
 
 
+def bench_config(n_gpus: int) -> dict:
+    """The `config` object of the JSON line -- the SAME dict in both arms (GPU and `--impl reference`)."""
+    return {
+        "workload": WORKLOAD,
+        "step": "decode (scale, clip, L2-normalise, nearest codeword, gates) + connected components + size filters + "
+                "regionprops of one tile",
+        "lowpass": "off (north_star kernel sequence)",
+        "thresholds": {"magnitude": list(MAG), "minimum_pixels": MIN_PX, "maximum_pixels": 500},
+        "normalization": {"background": BKG, "normalization": NRM},
+        "parallelism": f"tile-sharded x{n_gpus}",
+        "l2": "every step reads a whole tile (13.4 GB on the GPU, fresh sub-tiles on the CPU arm): far beyond any cache",
+    }
+
+
 # ---------------------------------------------------------------------------------- clocks
 class ClockSampler:
     """SM clock / throttle reasons sampled DURING the timed region: NVML polled every ~2 ms from a
@@ -248,7 +262,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "lowpass": "off", "l2": "each step decodes fresh sub-tiles"},
+        "config": bench_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": "Gvoxel/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Gvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -303,6 +317,237 @@ def _zarr_store_extra(sub, df_cb, nrm, bkg, tmp_dir, local, compression="blosc-z
     del dec
     torch.cuda.empty_cache()
     return out
+
+
+OPT_SHAPE = (64, 2048, 2048)   # configs[2]: human-olfactory-bulb-shaped tiles
+OPT_TILES_PER_RANK = 2
+OPT_ITERATIONS = 4
+ZSLAB_PLANES_PER_RANK = 50     # configs[4] = 16 x 400 x 4096 x 4096 is exactly 8 ranks x 50 planes
+ZSLAB_YX = 4096
+
+
+def _host_gb_available():
+    try:
+        import psutil
+
+        return psutil.virtual_memory().available / 1e9
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def _max_over_ranks(dist, world, dev, values):
+    import torch
+
+    t = torch.tensor(list(values), device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t.cpu()]
+
+
+def _optimizer_extra(dist, world, rank, local, dev, matrix, df_cb, shared_root):
+    """configs[2]-shaped run of `optimize_normalization_by_decoding` (PD:4581-4757): OPT_TILES_PER_RANK tiles of
+    16 x 64 x 2048 x 2048 uint16 per rank in pinned host memory, reference-default low-pass (3,1,1), one shared
+    datastore directory.  Iteration 0 uploads, low-passes and decodes (dense-candidate regime: percentile-seeded
+    vectors); iterations 1.. decode the HBM-resident low-passed stacks.  Exchanges: all_reduce of the percentile
+    seed's digit histograms, one padded all_gather of transcript rows per iteration."""
+    import torch
+
+    from merfish3d_analysis_b200 import synthetic
+    from merfish3d_analysis_b200.datastore import ArrayDataStore
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    T = OPT_TILES_PER_RANK
+    n_vox = int(np.prod(OPT_SHAPE))
+    need_gb = 16 * n_vox * 2 * T * world / 1e9
+    avail = _host_gb_available()
+    if avail is not None and need_gb * 1.2 > avail:
+        return {"skipped": f"host memory: needs {need_gb:.0f} GB pinned, {avail:.0f} GB available"}
+    hosts = []
+    for k in range(T):
+        blk = synthetic.make_stack_device(matrix, OPT_SHAPE, 3000 + rank * T + k, device=dev)
+        h = torch.empty(blk.shape, dtype=torch.uint16, pin_memory=True)
+        h.copy_(blk)
+        hosts.append(h)
+        del blk
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    root = Path(shared_root) / "qi2labdatastore_optimizer"
+    if rank == 0:
+        ArrayDataStore(root, codebook=df_cb)
+    if world > 1:
+        dist.barrier()
+    ds = ArrayDataStore(root)
+    for r in range(world):  # tile metadata goes into ONE calibrations/attributes.json: ranks register in turn
+        if r == rank:
+            ds._refresh()
+            for k in range(T):
+                ds.add_tile(hosts[k].numpy(), tile_id=f"tile{r * T + k:04d}")
+        if world > 1:
+            dist.barrier()
+    ds._refresh()
+    dec = PixelDecoder(ds, merfish_bits=16, num_gpus=world, verbose=0)
+    dec._profile = {"sync": True}
+    ctx = dec._ctx(local)
+    ctx.reset_counters()
+    ctx.set_timing(True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dec.optimize_normalization_by_decoding(n_iterations=OPT_ITERATIONS, lowpass_sigma=(3.0, 1.0, 1.0),
+                                           magnitude_threshold=MAG, minimum_pixels=MIN_PX,
+                                           tile_indices=list(range(world * T)))
+    torch.cuda.synchronize()
+    total_s = time.perf_counter() - t0
+    tm = dec._optimizer_timing
+    kt = ctx.kernel_times_ms()
+    keys = ("total_s", "tiles_s", "exchange_s", "vectors_s", "stage_s", "decode_extract_s")
+    its = []
+    for it in tm["iterations"]:
+        vals = _max_over_ranks(dist, world, dev, [it.get(k, 0.0) for k in keys])
+        its.append(dict(zip(keys, vals), cache_hits=it["cache_hits"], transcripts_pooled=it["transcripts_pooled"]))
+    seed_s, total_s = _max_over_ranks(dist, world, dev, [tm["seed_s"], total_s])
+    steady = its[1:]
+    steady_s = float(np.mean([it["total_s"] for it in steady])) if steady else None
+    i_n, i_b = ds.load_decode_normalization_vectors(None, "iterative")
+    out = {
+        "tiles": world * T, "tiles_per_rank": T, "tile": f"16 x {OPT_SHAPE[0]} x {OPT_SHAPE[1]} x {OPT_SHAPE[2]} uint16",
+        "iterations": OPT_ITERATIONS, "lowpass_sigma": [3.0, 1.0, 1.0], "total_s": total_s, "seed_s": seed_s,
+        "iteration0": its[0] if its else None, "steady_iterations": steady,
+        "steady_s_per_iteration": steady_s,
+        "steady_gvoxel_per_s": (world * T * n_vox / steady_s / 1e9) if steady_s else None,
+        "iteration0_gvoxel_per_s": (world * T * n_vox / its[0]["total_s"] / 1e9) if its else None,
+        "cache": tm.get("cache"),
+        "kernel_ms_whole_run_rank0": {k: v for k, v in sorted(kt.items(), key=lambda kv: -kv[1])[:8]},
+        "iterative_normalization_head": [float(v) for v in np.asarray(i_n)[:4]],
+        "exchange": "seed: all_reduce(SUM) of 2048-bin int64 digit histograms (radix select over tiles sharded on "
+                    "ranks); per iteration: sizes + one padded float64 all_gather of transcript rows" if world > 1
+                    else "single process: no collective",
+        "note": "times are max over ranks; stage_s = datastore read + H2D + per-bit low-pass of tiles not yet resident "
+                "(0 once cached), decode_extract_s = decode + label + features + annotation, exchange_s = all_gather of "
+                "the tables, vectors_s = medians + JSON hand-off; all phases separated by stream syncs",
+    }
+    ctx.set_timing(False)
+    dec._cleanup()
+    del dec, hosts
+    torch.cuda.empty_cache()
+    return out
+
+
+def _zslab_extra(dist, world, rank, local, dev, matrix, df_cb, tmp_dir):
+    """configs[4]-shaped z-slab sharding: ONE volume of 16 x (50 N) x 4096 x 4096 uint16 (N = 8 is configs[4]
+    itself), every rank holding only its own 50 planes in pinned host memory, through
+    `decode_one_tile_sharded`: H2D, decode + label per slab, boundary-plane send/recv, all_gather of the
+    cross-slab equivalences, gather of the crossing components' records, assembly on rank 0."""
+    import pandas as pd
+    import torch
+
+    from merfish3d_analysis_b200 import synthetic
+    from merfish3d_analysis_b200.datastore import ArrayDataStore, ZWindowVolume
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    per, yx = ZSLAB_PLANES_PER_RANK, ZSLAB_YX
+    avail = _host_gb_available()
+    note = None
+    while avail is not None and 16 * per * yx * yx * 2 * world * 1.2 / 1e9 > avail and per > 10:
+        per //= 2
+        note = f"planes per rank reduced to {per}: host memory ({avail:.0f} GB available)"
+    Z = per * world
+    nrm = np.full(16, NRM, dtype=np.float32)
+    bkg = np.full(16, BKG, dtype=np.float32)
+    block = torch.empty((16, per, yx, yx), dtype=torch.uint16, pin_memory=True)
+    step = 10
+    for z0 in range(0, per, step):  # generated on the device a few planes at a time (data synthesis only)
+        z1 = min(per, z0 + step)
+        blk = synthetic.make_stack_device(matrix, (z1 - z0, yx, yx), 5005 + rank * 100 + z0, device=dev)
+        block[:, z0:z1].copy_(blk)
+        del blk
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    ds = ArrayDataStore(Path(tmp_dir) / f"qi2labdatastore_zslab_r{rank}", codebook=df_cb)
+    ds.add_tile([ZWindowVolume((Z, yx, yx), rank * per, block[b].numpy()) for b in range(16)])
+    ds.save_decode_normalization_vectors(None, "global", nrm, bkg)
+    dec = PixelDecoder(ds, merfish_bits=16, num_gpus=world, verbose=0)
+    dec._profile = {"sync": True}
+    times, splits = [], []
+    for it in range(3):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dec.decode_one_tile_sharded(0, lowpass_sigma=None, magnitude_threshold=MAG, minimum_pixels=MIN_PX,
+                                    normalization_method="global")
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        times.append(time.perf_counter() - t0)
+        splits.append(dict(dec._zslab_timing))
+    n_tr = len(dec._df_barcodes) if rank == 0 else 0
+    keys = sorted(splits[-1])
+    best = int(np.argmin(times[1:])) + 1
+    split = dict(zip(keys, _max_over_ranks(dist, world, dev, [splits[best].get(k, 0.0) for k in keys])))
+    t_best = _max_over_ranks(dist, world, dev, [times[best]])[0]
+    n_vox = Z * yx * yx
+    dec._cleanup()
+    del dec, block
+    torch.cuda.empty_cache()
+    # identical-to-unsharded check on a volume that fits one GPU (every rank holds all of it)
+    identical = None
+    try:
+        zs_, ys_ = 6 * max(world, 2), 512
+        small = synthetic.make_stack_device(matrix, (zs_, ys_, ys_), 777, device=dev, density=4e-4).cpu().numpy()
+        ds2 = ArrayDataStore(Path(tmp_dir) / f"qi2labdatastore_zcheck_r{rank}", codebook=df_cb)
+        ds2.add_tile(small)
+        ds2.save_decode_normalization_vectors(None, "global", nrm, bkg)
+        d_sh = PixelDecoder(ds2, merfish_bits=16, num_gpus=world, verbose=0)
+        kw = dict(lowpass_sigma=None, magnitude_threshold=MAG, minimum_pixels=MIN_PX, normalization_method="global")
+        if world > 1:
+            d_sh.decode_one_tile_sharded(0, **kw)
+        else:
+            d_sh.decode_one_tile_sharded(0, n_slabs=3, **kw)
+        if rank == 0:
+            d_un = PixelDecoder(ds2, merfish_bits=16, num_gpus=1, verbose=0)
+            d_un.decode_one_tile(0, gpu_id=local, **kw)
+            pd.testing.assert_frame_equal(d_sh.decoded_barcodes, d_un.decoded_barcodes)
+            identical = {"ok": True, "volume": f"16 x {zs_} x {ys_} x {ys_}", "transcripts": int(len(d_un.decoded_barcodes)),
+                         "slabs": world if world > 1 else 3}
+    except AssertionError as e:
+        identical = {"ok": False, "error": str(e)[:300]}
+    return {
+        "volume": f"16 x {Z} x {yx} x {yx} uint16", "planes_per_rank": per, "gb_total": 16 * n_vox * 2 / 1e9,
+        "s_per_volume": t_best, "gvoxel_per_s": n_vox / t_best / 1e9, "runs_s": times, "transcripts": int(n_tr),
+        "split_s_max_over_ranks": split, "identical_to_unsharded": identical,
+        "exchange": "boundary planes: NCCL send/recv of one (2, Y, X) int32 message per interface; equivalences / areas: "
+                    "sizes + padded float64 all_gather; crossing components' records + kept rows: padded float64 gather "
+                    "to rank 0" if world > 1 else "one slab, no exchange",
+        "note": note,
+    }
+
+
+def _h2d_rates(dist, world, dev, host):
+    """Concurrent pinned H2D of every rank's tile: per-rank GB/s (the host fabric's ceiling for `e2e` at N > 1)."""
+    import torch
+
+    dst = torch.empty(host.shape, dtype=host.dtype, device=dev)
+    dst.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    dst.copy_(host, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    gbs = host.numel() * host.element_size() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    t = torch.tensor([gbs], device=dev, dtype=torch.float64)
+    if world > 1:
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        rates = [float(p.item()) for p in parts]
+    else:
+        rates = [gbs]
+    del dst
+    return rates
 
 
 def run_b200(args):
@@ -414,7 +659,12 @@ def run_b200(args):
     # ---- secondary measurements (not the headline): reference-default low-pass on, and the
     # all-foreground worst case where every voxel passes the magnitude gate
     extras = {}
-    if not args.no_extras and world == 1:
+    want = set((args.extras or "all").split(","))
+
+    def wanted(name):
+        return not args.no_extras and ("all" in want or name in want)
+
+    if world == 1 and (wanted("lowpass_on") or wanted("all_foreground")):
         ctx.reset_counters()
         ctx.set_timing(True)
         lp = None
@@ -497,7 +747,7 @@ def run_b200(args):
         }
 
         # the reference-default call (low-pass sigma (3,1,1) on): the per-bit filter runs behind the upload
-        if world == 1 and not args.no_extras:
+        if world == 1 and wanted("e2e_variants"):
             for i in range(3):
                 if i == 1:
                     torch.cuda.synchronize()
@@ -515,7 +765,7 @@ def run_b200(args):
             torch.cuda.empty_cache()
         # unregistered tile (the usual case: only round-1 bits are in the reference frame): 12 of 16 bits carry an
         # affine round transform and are resampled on the device, then the reference-default low-pass
-        if world == 1 and not args.no_extras:
+        if world == 1 and wanted("e2e_variants"):
             rng_x = np.random.default_rng(7)
             xf = {}
             for r in (2, 3, 4):
@@ -545,7 +795,7 @@ def run_b200(args):
             torch.cuda.empty_cache()
         # multi-tile public API: decode_all_tiles over 3 tiles (the same pinned array registered three times),
         # per-tile parquet output + the pooled table stage; tile t+1 is staged while tile t is finished
-        if world == 1 and not args.no_extras:
+        if world == 1 and wanted("e2e_variants"):
             ds3 = ArrayDataStore(Path(tmp.name) / "qi2labdatastore_multi", codebook=df_cb)
             for k in range(3):
                 ds3.add_tile(host.numpy(), stage_origin_zyx_um=(0.0, 0.0, 250.0 * k))
@@ -570,7 +820,7 @@ def run_b200(args):
             torch.cuda.empty_cache()
         # the same call with the stack in PAGEABLE host memory (what a datastore returning plain NumPy
         # arrays gives the loader): staged through the library's pinned ring by m3d_upload_batch
-        if world == 1 and not args.no_extras:
+        if world == 1 and wanted("e2e_variants"):
             pageable = np.empty(tuple(host.shape), dtype=np.uint16)
             np.copyto(pageable, host.numpy())
             ds2 = ArrayDataStore(Path(tmp.name) / "qi2labdatastore_pageable", codebook=df_cb)
@@ -599,7 +849,7 @@ def run_b200(args):
         # the same call with the tile in the reference's on-disk form: `<image>.ome.zarr` Zarr v3 arrays of
         # blosc-zstd bit-shuffled (16, 512, 512) chunks.  32 planes keep the store small; the
         # figure of merit is decoded GB/s.  Guarded: a full disk must not cost the bench line.
-        if world == 1 and not args.no_extras:
+        if world == 1 and wanted("zarr"):
             for key, comp in (("e2e_from_zarr_store", "blosc-zstd"), ("e2e_from_zarr_store_lz4", "blosc-lz4")):
                 try:
                     extras[key] = _zarr_store_extra(host.numpy()[:, :32], df_cb, nrm, bkg, tmp.name, local, comp)
@@ -622,6 +872,44 @@ def run_b200(args):
             except Exception as e:  # noqa: BLE001
                 extras["e2e_32_planes_from_pinned_host"] = {"error": f"{type(e).__name__}: {e}"}
 
+    if e2e is not None:
+        try:
+            rates = _h2d_rates(dist, world, dev, host)
+            e2e["h2d_gb_s_per_rank_concurrent"] = [round(r, 2) for r in rates]
+            e2e["h2d_gb_s_total"] = round(float(sum(rates)), 2)
+        except Exception as ex:  # noqa: BLE001
+            e2e["h2d_gb_s_per_rank_concurrent"] = f"{type(ex).__name__}: {ex}"
+    # free everything the first part of the bench held before the two sharded configurations
+    try:
+        del host
+    except NameError:
+        pass
+    try:
+        del stack, decoded
+    except NameError:
+        pass
+    dec._cleanup()
+    torch.cuda.empty_cache()
+    import gc
+
+    gc.collect()
+    shared = [tmp.name]
+    if world > 1:
+        dist.broadcast_object_list(shared, src=0)  # control plane: the path of the shared datastore directory
+    for name, fn, root in (("optimizer", _optimizer_extra, shared[0]), ("zslab", _zslab_extra, tmp.name)):
+        if not wanted(name):
+            continue
+        try:
+            extras[name] = fn(dist, world, rank, local, dev, matrix, df_cb, root)
+        except Exception as ex:  # noqa: BLE001
+            import traceback
+
+            extras[name] = {"error": f"{type(ex).__name__}: {ex}", "trace": traceback.format_exc()[-600:]}
+            if world > 1:
+                raise  # a rank that left a collective early would hang the others: fail loudly
+        torch.cuda.empty_cache()
+        gc.collect()
+
     line = None
     if rank == 0:
         cpu = None
@@ -633,13 +921,12 @@ def run_b200(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {
-                "workload": WORKLOAD if shape == SHAPE else f"reduced tile 16x{shape[0]}x{shape[1]}x{shape[2]} uint16",
-                "step": "m3d_decode_label (gate + search + CCL) + m3d_features on the HBM-resident stack",
-                "lowpass": "off (north_star kernel sequence)", "parallelism": f"tile-sharded x{world}",
-                "l2": f"input {stack_bytes(shape) / 1e9:.1f} GB per step >> 126 MB L2",
-                "foreground_voxels": n_fg, "features": int(n_feat),
-            },
+            "config": bench_config(world) if shape == SHAPE else dict(
+                bench_config(world), workload=f"reduced tile 16x{shape[0]}x{shape[1]}x{shape[2]} uint16 (debug)"),
+            "workload_stats": {"foreground_voxels": n_fg, "features": int(n_feat),
+                               "input_gb_per_step": stack_bytes(shape) / 1e9,
+                               "device_step": "m3d_decode_label_persistent (gate + search + CCL) + m3d_features on the "
+                                              "HBM-resident stack"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
             "extras": extras,
             "clocks": clocks.summary(),
@@ -666,6 +953,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--extras", default="all", help="comma list of extras to run (default all): lowpass_on,all_foreground,"
+                    "e2e_variants,zarr,optimizer,zslab")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -289,13 +289,17 @@ class PixelDecoder:
 
     def _load_global_normalization_vectors(self, gpu_id: int = 0, recalculate: bool = False,
                                            tile_indices=None,
-                                           lowpass_sigma=DEFAULT_DECODE_LOWPASS_SIGMA) -> None:
+                                           lowpass_sigma=DEFAULT_DECODE_LOWPASS_SIGMA,
+                                           collective: bool = False) -> None:
         """PD:934-979."""
         nv, bv = self._datastore.load_decode_normalization_vectors(self._decode_run_key, "global")
         if not recalculate and nv is not None and bv is not None:
             self._global_normalization_vector = np.asarray(nv, dtype=np.float32)
             self._global_background_vector = np.asarray(bv, dtype=np.float32)
             self._global_normalization_loaded = True
+        elif collective:
+            self._global_normalization_vectors(gpu_id=gpu_id, tile_indices=tile_indices,
+                                               lowpass_sigma=lowpass_sigma, collective=True)
         else:
             self._global_normalization_vectors(gpu_id=gpu_id, tile_indices=tile_indices,
                                                lowpass_sigma=lowpass_sigma)
@@ -304,18 +308,40 @@ class PixelDecoder:
                                       high_percentile_cut: float = 90.0,
                                       hot_pixel_threshold: int = 50000, gpu_id: int = 0,
                                       tile_indices=None,
-                                      lowpass_sigma=DEFAULT_DECODE_LOWPASS_SIGMA) -> None:
+                                      lowpass_sigma=DEFAULT_DECODE_LOWPASS_SIGMA,
+                                      collective: bool = False) -> None:
         """PD:981-1199 on the device: per bit, hot-pixel replace -> z-crop -> low-pass ->
-        percentile-gated medians through a radix select (no sort, no host copy)."""
+        percentile-gated medians through a radix select (no sort, no host copy).
+
+        ``collective`` (every rank of the process group calls this together; the optimiser does): the sampled
+        tiles are sharded over the ranks in contiguous chunks, each rank loads / filters only its own, and the
+        pooled medians come from the radix select with its 2048-bin digit histograms ALL-REDUCED over NCCL --
+        exact, so every rank ends with the vectors a single process computes.  Rank 0 saves them."""
         import torch
 
         sigma = self._effective_lowpass_sigma(lowpass_sigma)
+        rank, world, dist = self._dist()
+        collective = bool(collective and dist is not None and world > 1)
+        all_ids = list(self._datastore.tile_ids)
         if tile_indices is not None:
-            tiles = [self._datastore.tile_ids[t] for t in tile_indices]
-        elif len(self._datastore.tile_ids) > 5:
-            tiles = sample(list(self._datastore.tile_ids), 5)
+            tiles = [all_ids[t] for t in tile_indices]
+        elif len(all_ids) > 5:
+            tiles = sample(all_ids, 5)
+            if collective:  # one sample for the whole group (the reference's is unseeded, PD:1018)
+                idx = torch.tensor([all_ids.index(t) for t in tiles], dtype=torch.int64)
+                dev_c = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else "cpu"
+                idx = idx.to(dev_c)
+                dist.broadcast(idx, src=0)
+                tiles = [all_ids[int(i)] for i in idx.cpu()]
         else:
-            tiles = list(self._datastore.tile_ids)
+            tiles = all_ids
+        reduce = None
+        if collective:
+            tiles = self._contiguous_chunks(tiles, world)[rank]
+
+            def reduce(hist):
+                dist.all_reduce(hist)
+
         ctx = self._ctx(gpu_id)
         dev = ctx.device
         stats = _norm.DeviceOrderStats(ctx)
@@ -341,16 +367,18 @@ class PixelDecoder:
                 vols.append(img)
             per_bit.append(vols)
             # one bit at a time keeps the peak at <= 5 volumes (+ low-pass temporaries)
-            nv1, bv1 = _norm.global_normalization_vectors(ctx, [vols], low_percentile_cut, high_percentile_cut)
+            nv1, bv1 = _norm.global_normalization_vectors(ctx, [vols], low_percentile_cut, high_percentile_cut,
+                                                          reduce=reduce)
             per_bit[-1] = (nv1[0], bv1[0])
             del vols
         torch.cuda.synchronize(dev)
         normalization_vector = np.asarray([p[0] for p in per_bit], dtype=np.float32)
         background_vector = np.asarray([p[1] for p in per_bit], dtype=np.float32)
-        self._datastore.save_decode_normalization_vectors(
-            self._decode_run_key, "global", normalization_vector, background_vector,
-            decode_mode=self._effective_decode_mode,
-        )
+        if not collective or rank == 0:
+            self._datastore.save_decode_normalization_vectors(
+                self._decode_run_key, "global", normalization_vector, background_vector,
+                decode_mode=self._effective_decode_mode,
+            )
         self._global_background_vector = background_vector
         self._global_normalization_vector = normalization_vector
         self._global_normalization_loaded = True
@@ -593,23 +621,29 @@ class PixelDecoder:
         double-buffered upload path."""
         import os
 
-        import torch
-
         if budget_bytes is None:
             env = os.environ.get("M3D_TILE_CACHE_GB")
             if env is not None:
                 budget_bytes = int(float(env) * 1e9)
-            else:
-                dev = self._ctx(gpu_id).device
-                free, _total = torch.cuda.mem_get_info(dev)
-                reusable = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
-                budget_bytes = int(0.55 * (free + max(reusable, 0)))
         self._tile_cache = {}
-        self._tile_cache_budget = max(int(budget_bytes), 0)
+        # None = resolved from the device's free memory when the first tile is about to be staged
+        self._tile_cache_budget = None if budget_bytes is None else max(int(budget_bytes), 0)
+        self._tile_cache_gpu = gpu_id
         self._tile_cache_used = 0
         self._tile_cache_last_bytes = 0
         self._tile_cache_stats = {"hits": 0, "misses": 0, "resident_tiles": 0, "resident_bytes": 0,
                                   "budget_bytes": self._tile_cache_budget}
+
+    def _tile_cache_resolve_budget(self) -> int:
+        if self._tile_cache_budget is None:
+            import torch
+
+            dev = self._ctx(self._tile_cache_gpu).device
+            free, _total = torch.cuda.mem_get_info(dev)
+            reusable = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+            self._tile_cache_budget = int(0.55 * (free + max(reusable, 0)))
+            self._tile_cache_stats["budget_bytes"] = self._tile_cache_budget
+        return self._tile_cache_budget
 
     def _tile_cache_end(self) -> None:
         self._tile_cache = None
@@ -620,13 +654,13 @@ class PixelDecoder:
         final buffer is allocated outside the recycled staging slots."""
         if self._tile_cache is None:
             return False
-        return self._tile_cache_used + self._tile_cache_last_bytes <= self._tile_cache_budget and \
-            self._tile_cache_budget > 0
+        budget = self._tile_cache_resolve_budget()
+        return budget > 0 and self._tile_cache_used + self._tile_cache_last_bytes <= budget
 
     def _tile_cache_insert(self, key, state: dict, meta: dict) -> None:
         nbytes = sum(int(t.numel()) * int(t.element_size()) for t in state.values() if hasattr(t, "element_size"))
         self._tile_cache_last_bytes = nbytes
-        if self._tile_cache_used + nbytes > self._tile_cache_budget:
+        if self._tile_cache_used + nbytes > self._tile_cache_resolve_budget():
             return  # the size guess was too small: this tile keeps streaming
         self._tile_cache[key] = (dict(state), {"em_wvl": meta["em_wvl"], "full_z": meta["full_z"]})
         self._tile_cache_used += nbytes
@@ -1300,7 +1334,8 @@ class PixelDecoder:
             if prof.get("sync"):  # attribute the staged copies / filters to "stage", not to the decode that waits for them
                 import torch
 
-                torch.cuda.synchronize(self._ctx(gpu_id).device)
+                # this stream only (it is ordered behind the tile just staged): the next tile's prefetch keeps running
+                torch.cuda.current_stream(self._ctx(gpu_id).device).synchronize()
             t2 = _time.perf_counter()
             prof["vectors_s"] = prof.get("vectors_s", 0.0) + (t1 - t0)
             prof["stage_s"] = prof.get("stage_s", 0.0) + (t2 - t1)
@@ -1357,10 +1392,7 @@ class PixelDecoder:
 
     def _tile_cache_admit_next(self) -> bool:
         """Admission for a tile staged AHEAD: the tile being decoded now may not have been counted yet."""
-        if self._tile_cache is None:
-            return False
-        pending = self._tile_cache_last_bytes  # the prefetched tile itself
-        return self._tile_cache_budget > 0 and self._tile_cache_used + pending <= self._tile_cache_budget
+        return self._tile_cache_admit()
 
     # ------------------------------------------------------------------ z-slab sharding of one volume
     def decode_one_tile_sharded(
@@ -1438,6 +1470,21 @@ class PixelDecoder:
         else:
             mine = list(range(len(bounds)))
             owner = {r: 0 for r in mine}
+        import time as _time
+
+        timing = self._zslab_timing = {}
+        sync = bool(self._profile and self._profile.get("sync"))
+        t_last = [_time.perf_counter()]
+
+        def mark(name):
+            """host wall-clock split of the call (with ``_profile = {"sync": True}`` the device is drained at
+            every mark so that copies / kernels are attributed to the phase that issued them)"""
+            if sync:
+                torch.cuda.synchronize(ctx.device)
+            now = _time.perf_counter()
+            timing[name] = timing.get(name, 0.0) + (now - t_last[0])
+            t_last[0] = now
+
         results: dict[int, sh.SlabResult] = {}
         kept: dict[int, tuple] = {}  # slab -> (stack, decoded, labels) still on the device
         records: dict[tuple, dict] = {}
@@ -1461,7 +1508,9 @@ class PixelDecoder:
         for r in mine:
             z0, z1 = bounds[r]
             stack = load_slab(z0, z1, full_z)
+            mark("load_h2d_lowpass_s")
             decoded, labels, table = sh.decode_slab(ctx, stack, False, MAXIMUM_PIXELS, optimize)
+            mark("decode_label_features_s")
             res = sh.SlabResult(z0, z1, tuple(stack.shape[2:]), table)
             if distributed:
                 reqs = []
@@ -1475,10 +1524,12 @@ class PixelDecoder:
                     prev_planes = (in_planes[0].to(torch.int16).contiguous(), in_planes[1].contiguous())
                 for q in reqs:
                     q.wait()
+                mark("boundary_send_recv_s")
             if prev_planes is not None:
                 res.pairs, res.poisoned_here, poisoned_prev = sh.interface(ctx, prev_planes, decoded, labels)
             else:
                 poisoned_prev = np.zeros(0, dtype=np.int64)
+            mark("interface_pairs_s")
             res._poisoned_prev = poisoned_prev
             results[r] = res
             kept[r] = (stack, decoded, labels)
@@ -1488,6 +1539,7 @@ class PixelDecoder:
                 retire(r - 1)  # both of its interfaces are known now: at most two slabs stay resident
         if mine and (not distributed or mine[-1] == len(bounds) - 1):
             retire(mine[-1])  # no upper neighbour; otherwise the next rank computes that interface (below)
+        mark("resolve_records_s")
         # ---- resolve (identical on every rank)
         summary = {
             r: dict(z0=s.z0, z1=s.z1, shape_yx=s.shape_yx, areas=s.table[:, _COL_AREA].copy(), pairs=s.pairs,
@@ -1495,9 +1547,10 @@ class PixelDecoder:
             for r, s in results.items()
         }
         if distributed:
-            gathered = [None] * world
-            dist.all_gather_object(gathered, summary)
-            summary = {k: v for g in gathered for k, v in g.items()}
+            # tensor collective (sizes + one padded float64 buffer per rank), not pickled objects
+            gathered = sh.all_gather_vectors(dist, sh.pack_summary(summary))
+            summary = {k: v for g in gathered for k, v in sh.unpack_summary(g).items()}
+        mark("equivalence_gather_s")
         order = sorted(summary)
         areas = [summary[r]["areas"] for r in order]
         pairs = [summary[r]["pairs"] for r in order]
@@ -1517,12 +1570,14 @@ class PixelDecoder:
                 records[(r, cid)] = rec
             decoded_slabs.append(decoded)
         local_tabs = {r: results[r].table[keep_local[order.index(r)]] for r in mine}
+        mark("resolve_records_s")
         if distributed:
-            gathered = [None] * world if rank == 0 else None
-            dist.gather_object((records, local_tabs), gathered, dst=0)
+            gathered = sh.gather_vectors(dist, sh.pack_records(records, local_tabs, nb), dst=0)
             if rank == 0:
-                records = {k: v for g in gathered for k, v in g[0].items()}
-                local_tabs = {k: v for g in gathered for k, v in g[1].items()}
+                unpacked = [sh.unpack_records(g) for g in gathered]
+                records = {k: v for u in unpacked for k, v in u[0].items()}
+                local_tabs = {k: v for u in unpacked for k, v in u[1].items()}
+        mark("record_gather_s")
         # ---- assemble on rank 0 (or the only process)
         st = self._device_state.setdefault(gpu_id, {})
         st.clear()
@@ -1532,6 +1587,7 @@ class PixelDecoder:
         self._slab_bounds = [bounds[r] for r in mine]
         if distributed and rank != 0:
             self._df_barcodes = pd.DataFrame({c: [] for c in self._table_columns()})
+            mark("assemble_annotate_s")
             return None
         self._load_coordinate_metadata()
         merged = []
@@ -1541,6 +1597,7 @@ class PixelDecoder:
         slabs = [sh.SlabResult(summary[r]["z0"], summary[r]["z1"], summary[r]["shape_yx"], local_tabs[r]) for r in order]
         tab = sh.assemble(slabs, [np.ones(len(local_tabs[r]), dtype=bool) for r in order], merged, nb)
         self._df_barcodes = self._annotate_table(tab)
+        mark("assemble_annotate_s")
         return None
 
     # ------------------------------------------------------------------ multi-GPU plumbing
@@ -1748,12 +1805,12 @@ class PixelDecoder:
         temp_dir = None
         try:
             t_seed = _time.perf_counter()
-            if rank == 0:
-                self._load_global_normalization_vectors(gpu_id=self._local_gpu(), recalculate=True,
-                                                        tile_indices=tile_indices, lowpass_sigma=lowpass_sigma)
-            self._barrier()
-            if rank != 0:
-                self._load_global_normalization_vectors(gpu_id=self._local_gpu(), lowpass_sigma=lowpass_sigma)
+            # the percentile seed (PD:4662-4667 computes it in the parent process): under a process group its
+            # tiles are sharded over the ranks and the pooled medians are all-reduced (see the method)
+            self._load_global_normalization_vectors(gpu_id=self._local_gpu(), recalculate=True,
+                                                    tile_indices=tile_indices, lowpass_sigma=lowpass_sigma,
+                                                    collective=True)
+            self._barrier()  # rank 0 has written calibrations/attributes.json
             timing["seed_s"] = _time.perf_counter() - t_seed
             if self._decode_run_key is None:
                 # tables travel in memory (all_gather); the scratch directory exists only for `_keep_temp_tables`

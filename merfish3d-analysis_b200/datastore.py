@@ -43,6 +43,37 @@ class _Ready:
         return self._value
 
 
+class ZWindowVolume:
+    """A (z, y, x) image of which this process holds only planes [z0, z0 + len(block)): what a rank of a z-slab
+    sharded decode needs of a volume too large for one host / one GPU (configs[4]: 16 x 400 x 4096 x 4096).
+    Quacks like the array a loader returns (``shape``, ``dtype``, ``ndim``, ``[a:b]``); slicing outside the held
+    window raises."""
+
+    def __init__(self, full_shape, z0: int, block: np.ndarray):
+        self.shape = tuple(int(v) for v in full_shape)
+        self.dtype = block.dtype
+        self.ndim = 3
+        self._z0 = int(z0)
+        self._block = block
+        if block.shape[1:] != self.shape[1:] or self._z0 < 0 or self._z0 + block.shape[0] > self.shape[0]:
+            raise ValueError("block does not fit the volume")
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, key):
+        if not isinstance(key, slice):
+            raise TypeError("ZWindowVolume supports z slices only")
+        a, b, step = key.indices(self.shape[0])
+        if step != 1:
+            raise ValueError("ZWindowVolume supports unit-step z slices only")
+        if b <= a:
+            return self._block[0:0]
+        if a < self._z0 or b > self._z0 + self._block.shape[0]:
+            raise IndexError(f"planes [{a}, {b}) are not held by this process (window starts at {self._z0})")
+        return self._block[a - self._z0 : b - self._z0]
+
+
 class ArrayDataStore:
     """In-memory / ``.npy``-backed datastore with the qi2labDataStore decode-stage surface."""
 
@@ -217,14 +248,23 @@ class ArrayDataStore:
         round_transforms_zyx_um: Mapping[int, np.ndarray] | None = None,
         sofima_flow_fields: Mapping[int, tuple] | None = None,
     ) -> str:
-        """Register one tile: ``readouts`` (bits, z, y, x) uint16, ``predictors`` float32/None."""
-        readouts = np.asarray(readouts)
-        if readouts.ndim != 4:
-            raise ValueError("readouts must be (bits, z, y, x)")
+        """Register one tile: ``readouts`` (bits, z, y, x) uint16, ``predictors`` float32/None.  ``readouts`` may
+        also be a list of per-bit array-likes (``shape``, ``dtype``, z slicing) that are kept as they are -- e.g.
+        :class:`ZWindowVolume` for a volume of which this process holds only some planes."""
+        lazy = isinstance(readouts, (list, tuple)) and all(
+            not isinstance(r, np.ndarray) and len(getattr(r, "shape", ())) == 3 for r in readouts)
+        if lazy:
+            if predictors is not None or persist:
+                raise ValueError("lazy per-bit images take no predictors and cannot be persisted")
+            readouts = list(readouts)
+        else:
+            readouts = np.asarray(readouts)
+            if readouts.ndim != 4:
+                raise ValueError("readouts must be (bits, z, y, x)")
         if tile_id is None:
             tile_id = f"tile{len(self._tile_ids):04d}"
         attrs = self._load_calibrations_attributes()
-        n_bits = readouts.shape[0]
+        n_bits = len(readouts)
         if len(attrs.get("bit_ids", [])) < n_bits:
             attrs["bit_ids"] = [f"bit{i:03d}" for i in range(1, n_bits + 1)]
         if tile_id not in attrs["tile_ids"]:
@@ -264,7 +304,7 @@ class ArrayDataStore:
         self._refresh(attrs)
         for b in range(n_bits):
             bit_id = self._bit_ids[b]
-            r = np.ascontiguousarray(readouts[b], dtype=np.uint16)
+            r = readouts[b] if lazy else np.ascontiguousarray(readouts[b], dtype=np.uint16)
             p = None if predictors is None else np.ascontiguousarray(predictors[b], dtype=np.float32)
             if persist:
                 d = self._readouts_root_path / tile_id / bit_id

@@ -41,12 +41,18 @@ def _key_to_f32(key: int) -> np.float32:
 class DeviceOrderStats:
     """Rank selection over ``v = clip0 ? max(x - sub, 0) : x - sub`` of several volumes."""
 
-    def __init__(self, ctx):
+    def __init__(self, ctx, reduce=None):
+        """``reduce(hist)``: optional in-place sum of the 2048-bin int64 device histogram over the ranks of a
+        process group (``dist.all_reduce``).  With it the pooled multiset is the union of every rank's volumes:
+        all ranks walk the same digits and end with the same exact order statistics, so the tiles behind a
+        pooled median can be sharded over GPUs.  Every rank must issue the same sequence of queries (ranks
+        holding no volume pass an empty list)."""
         import torch
 
         self._ctx = ctx
         self._torch = torch
         self._hist = torch.zeros(2048, dtype=torch.int64, device=ctx.device)
+        self._reduce = reduce
 
     def _pass(self, volumes, sub, clip0, pred, cutoffs, prefix_mask, prefix_value, shift):
         self._hist.zero_()
@@ -55,6 +61,8 @@ class DeviceOrderStats:
                 vol, self._hist, sub=sub, clip0=clip0, pred=pred, cutoff=cut,
                 prefix_mask=prefix_mask, prefix_value=prefix_value, shift=shift,
             )
+        if self._reduce is not None:
+            self._reduce(self._hist)
         return self._hist.cpu().numpy()
 
     def count(self, volumes, sub=0.0, clip0=False, pred=PRED_ALL, cutoffs=None) -> int:
@@ -128,24 +136,30 @@ class DeviceOrderStats:
 
 
 def global_normalization_vectors(ctx, bit_volume_lists, low_percentile_cut=10.0,
-                                 high_percentile_cut=90.0):
+                                 high_percentile_cut=90.0, reduce=None):
     """PD:1113-1183 -- per bit: bkg = median(pooled pixels < P10_t), nrm = median(pooled
     clip(img - bkg, 0) > P90_t).  ``bit_volume_lists[b]`` = list of float32 device volumes (one
-    per sampled tile), already hot-pixel-corrected, z-cropped and low-passed."""
-    stats = DeviceOrderStats(ctx)
+    per sampled tile), already hot-pixel-corrected, z-cropped and low-passed.
+
+    ``reduce`` (see :class:`DeviceOrderStats`): the sampled tiles are sharded over ranks.  The percentile
+    cut-offs are per tile (local); the two medians are over the pool of all ranks' selected pixels, found by
+    the same radix select with the digit histograms summed across ranks -- exact, so the vectors equal the
+    single-process ones bit for bit.  A rank without tiles passes empty lists and still takes part."""
+    local = DeviceOrderStats(ctx)
+    pooled = local if reduce is None else DeviceOrderStats(ctx, reduce=reduce)
     n_bits = len(bit_volume_lists)
     nrm = np.ones(n_bits, dtype=np.float32)
     bkg = np.zeros(n_bits, dtype=np.float32)
     for b, vols in enumerate(bit_volume_lists):
         vols = [v for v in vols if v.numel() > 0]
-        if not vols:
+        if not vols and reduce is None:
             continue
-        cuts = [float(stats.percentile(v, low_percentile_cut)) for v in vols]  # float32 cut-offs, like NumPy
-        m = stats.median(vols, pred=PRED_LT, cutoffs=cuts)
+        cuts = [float(local.percentile(v, low_percentile_cut)) for v in vols]  # float32 cut-offs, like NumPy
+        m = pooled.median(vols, pred=PRED_LT, cutoffs=cuts)
         bkg[b] = 0 if m is None else m
         sub = float(bkg[b])
-        cuts = [float(stats.percentile(v, high_percentile_cut, sub=sub, clip0=True)) for v in vols]
-        m = stats.median(vols, sub=sub, clip0=True, pred=PRED_GT, cutoffs=cuts)
+        cuts = [float(local.percentile(v, high_percentile_cut, sub=sub, clip0=True)) for v in vols]
+        m = pooled.median(vols, sub=sub, clip0=True, pred=PRED_GT, cutoffs=cuts)
         nrm[b] = 1 if m is None else m
     return nrm, bkg
 

@@ -225,3 +225,134 @@ def assemble(slabs: list[SlabResult], keep_local, merged_rows, n_bits: int) -> n
         return np.zeros((0, M3D_TABLE_FIXED_COLS + n_bits), dtype=np.float64)
     tab = np.concatenate(parts, axis=0)
     return tab[np.argsort(tab[:, 0], kind="stable")]
+
+
+# ---------------------------------------------------------------------------------------------- exchange
+# What the ranks exchange travels as flat float64 vectors through tensor collectives (counts first, then one
+# padded buffer per rank -- the same scheme as PixelDecoder._gather_tables), never as pickled Python objects:
+# every number below is an integer < 2^53, a float16 / float32 value or a float64 table entry, so the float64
+# container is exact.
+
+def pack_summary(summary: dict) -> np.ndarray:
+    """``{slab: dict(z0, z1, shape_yx, areas, pairs, poisoned_here, poisoned_prev)}`` -> float64 vector."""
+    parts = [np.asarray([len(summary)], dtype=np.float64)]
+    for r in sorted(summary):
+        s_ = summary[r]
+        areas = np.asarray(s_["areas"], dtype=np.float64).reshape(-1)
+        pairs = np.asarray(s_["pairs"], dtype=np.float64).reshape(-1)
+        ph = np.asarray(s_["poisoned_here"], dtype=np.float64).reshape(-1)
+        pp = np.asarray(s_["poisoned_prev"], dtype=np.float64).reshape(-1)
+        head = [r, s_["z0"], s_["z1"], s_["shape_yx"][0], s_["shape_yx"][1], areas.size, pairs.size // 2, ph.size, pp.size]
+        parts += [np.asarray(head, dtype=np.float64), areas, pairs, ph, pp]
+    return np.concatenate(parts)
+
+
+def unpack_summary(vec: np.ndarray) -> dict:
+    vec = np.asarray(vec, dtype=np.float64)
+    out, at = {}, 1
+    for _ in range(int(vec[0])):
+        r, z0, z1, sy, sx, na, npair, nph, npp = (int(v) for v in vec[at : at + 9])
+        at += 9
+        areas = vec[at : at + na].copy()
+        at += na
+        pairs = vec[at : at + 2 * npair].astype(np.int64).reshape(-1, 2)
+        at += 2 * npair
+        ph = vec[at : at + nph].astype(np.int64)
+        at += nph
+        pp = vec[at : at + npp].astype(np.int64)
+        at += npp
+        out[r] = dict(z0=z0, z1=z1, shape_yx=(sy, sx), areas=areas, pairs=pairs, poisoned_here=ph, poisoned_prev=pp)
+    return out
+
+
+def pack_records(records: dict, local_tabs: dict, n_bits: int) -> np.ndarray:
+    """Per-voxel records of crossing components ``{(slab, id): dict(lin, vals, mag, dist, dec)}`` and the kept
+    slab-local feature rows ``{slab: (n, 14 + bits) float64}`` -> float64 vector."""
+    parts = [np.asarray([len(records), len(local_tabs), n_bits], dtype=np.float64)]
+    for (r, cid) in sorted(records):
+        rec = records[(r, cid)]
+        n = int(rec["lin"].size)
+        kind = 1 if np.asarray(rec["vals"]).dtype == np.float32 else 0  # 0: float16 scaled image, 1: float32 raw
+        parts += [np.asarray([r, cid, n, rec["dec"], kind], dtype=np.float64),
+                  np.asarray(rec["lin"], dtype=np.float64).reshape(-1),
+                  np.asarray(rec["mag"], dtype=np.float64).reshape(-1),
+                  np.asarray(rec["dist"], dtype=np.float64).reshape(-1),
+                  np.asarray(rec["vals"], dtype=np.float64).reshape(-1)]
+    for r in sorted(local_tabs):
+        t = np.ascontiguousarray(local_tabs[r], dtype=np.float64)
+        parts += [np.asarray([r, t.shape[0]], dtype=np.float64), t.reshape(-1)]
+    return np.concatenate(parts)
+
+
+def unpack_records(vec: np.ndarray):
+    vec = np.asarray(vec, dtype=np.float64)
+    n_rec, n_tab, n_bits = (int(v) for v in vec[:3])
+    at = 3
+    records, tabs = {}, {}
+    for _ in range(n_rec):
+        r, cid, n, dec, kind = (int(v) for v in vec[at : at + 5])
+        at += 5
+        lin = vec[at : at + n].astype(np.int64)
+        at += n
+        mag = vec[at : at + n].astype(np.float16)
+        at += n
+        dist = vec[at : at + n].astype(np.float16)
+        at += n
+        vals = vec[at : at + n * n_bits].astype(np.float32 if kind else np.float16).reshape(n, n_bits)
+        at += n * n_bits
+        records[(r, cid)] = dict(lin=lin, vals=vals, mag=mag, dist=dist, dec=dec)
+    width = M3D_TABLE_FIXED_COLS + n_bits
+    for _ in range(n_tab):
+        r, n = int(vec[at]), int(vec[at + 1])
+        at += 2
+        tabs[r] = vec[at : at + n * width].reshape(n, width).copy()
+        at += n * width
+    return records, tabs
+
+
+def _collective_device(dist):
+    import torch
+
+    if dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def all_gather_vectors(dist, vec: np.ndarray) -> list[np.ndarray]:
+    """Variable-length float64 vectors of every rank, on every rank: sizes first, then one padded all_gather."""
+    import torch
+
+    dev = _collective_device(dist)
+    world = dist.get_world_size()
+    n = torch.tensor([int(vec.size)], dtype=torch.int64, device=dev)
+    sizes = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(t.item()) for t in sizes]
+    n_max = max(max(sizes), 1)
+    send = torch.zeros(n_max, dtype=torch.float64, device=dev)
+    if vec.size:
+        send[: vec.size] = torch.from_numpy(np.ascontiguousarray(vec, dtype=np.float64)).to(dev)
+    parts = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(parts, send)
+    return [p[:c].cpu().numpy() for p, c in zip(parts, sizes)]
+
+
+def gather_vectors(dist, vec: np.ndarray, dst: int = 0):
+    """Variable-length float64 vectors of every rank on rank ``dst`` (None elsewhere)."""
+    import torch
+
+    dev = _collective_device(dist)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = torch.tensor([int(vec.size)], dtype=torch.int64, device=dev)
+    sizes = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(t.item()) for t in sizes]
+    n_max = max(max(sizes), 1)
+    send = torch.zeros(n_max, dtype=torch.float64, device=dev)
+    if vec.size:
+        send[: vec.size] = torch.from_numpy(np.ascontiguousarray(vec, dtype=np.float64)).to(dev)
+    parts = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, parts, dst=dst)
+    if rank != dst:
+        return None
+    return [p[:c].cpu().numpy() for p, c in zip(parts, sizes)]

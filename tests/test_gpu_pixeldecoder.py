@@ -280,6 +280,60 @@ def test_multi_tile_pipeline_equals_tile_by_tile(tmp_path, lowpass):
                                           check_dtype=False)
 
 
+@pytest.mark.parametrize("lowpass", [None, (3.0, 1.0, 1.0)])
+def test_multi_tile_pipeline_on_an_unregistered_store(tmp_path, lowpass):
+    """Tiles whose later-round bits need the decode-time warp (the usual case) are prefetched too: tile t+1 is
+    uploaded, warped and low-passed on the side stream while tile t is finished.  Per-tile tables must equal plain
+    decode_one_tile calls; the optimiser (tile cache on and off) must give the same vectors either way."""
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    df_cb, cb = cases.codebook16()
+    rng = np.random.default_rng(17)
+    bit_round = [1 + (b // 2) % 4 for b in range(16)]
+    xfs = {}
+    for r in (2, 3, 4):
+        xf = np.eye(4, dtype=np.float32)
+        xf[:3, :3] += rng.normal(0, 0.002, (3, 3)).astype(np.float32)
+        xf[:3, 3] = (rng.uniform(-1.0, 1.0, 3) * np.array([0.315, 0.098, 0.098])).astype(np.float32)
+        xfs[r] = xf
+    stacks = [cases.small_stack(cb["matrix"], shape=(12, 40, 56), seed=600 + i, density=5e-3) for i in range(4)]
+    preds = [None, rng.uniform(0.8, 1.0, stacks[1].shape).astype(np.float32), None, None]
+    ds = _store(tmp_path, df_cb, stacks, preds, bit_round=bit_round, round_transforms_zyx_um=xfs)
+    bkg, nrm = cases.simple_vectors(16, nrm=300.0 if lowpass else 800.0)
+    ds.save_decode_normalization_vectors(None, "global", nrm, bkg)
+    kw = dict(lowpass_sigma=lowpass, minimum_pixels=4, normalization_method="global")
+    single = []
+    for t in range(4):
+        one = PixelDecoder(ds, merfish_bits=16, verbose=0)
+        one.decode_one_tile(t, **kw)
+        single.append(one.decoded_barcodes)
+    assert sum(len(s) for s in single) > 20
+    dec = PixelDecoder(ds, merfish_bits=16, verbose=0)
+    scheduled = []
+    orig = dec._schedule_prefetch
+
+    def spy(tile_idx, *a, **k):
+        scheduled.append(tile_idx)
+        return orig(tile_idx, *a, **k)
+
+    dec._schedule_prefetch = spy
+    dec.decode_all_tiles(assign_to_cells=False, **kw)
+    assert scheduled == [1, 2, 3]  # every following tile was staged ahead
+    for t in range(4):
+        got = ds.load_local_decoded_spots(t)
+        pd.testing.assert_frame_equal(got.reset_index(drop=True), single[t].reset_index(drop=True), check_dtype=False)
+    vectors = []
+    for budget in (None, 0):
+        d = PixelDecoder(ds, merfish_bits=16, verbose=0)
+        d.tile_cache_budget_bytes = budget
+        d.optimize_normalization_by_decoding(n_iterations=3, minimum_pixels=4, lowpass_sigma=lowpass,
+                                             magnitude_threshold=(0.9, 10.0), tile_indices=[0, 1, 2, 3])
+        vectors.append(ds.load_decode_normalization_vectors(None, "iterative"))
+        assert d._optimizer_timing["cache"]["resident_tiles"] == (4 if budget is None else 0)
+    np.testing.assert_array_equal(vectors[0][0], vectors[1][0])
+    np.testing.assert_array_equal(vectors[0][1], vectors[1][1])
+
+
 def test_multi_tile_pipeline_with_staged_pageable_uploads(tmp_path):
     """Same, with bit volumes large enough (10 MB each, pageable NumPy memory) to go through the pinned
     staging ring: tile t+1 is staged by the prefetch thread's upload workers while tile t runs on the main
