@@ -1059,7 +1059,17 @@ class PixelDecoder:
         centroid_stats = None
         if chroma and n > 0:
             centroid_stats = self._chromatic_centroid_statistics(ctx, st["stack"], labels, table)
-        eigvals = ctx.inertia_eigvals(table).cpu().numpy() if n > 0 else None
+        # the transcript gate (PD:3176: distance_min <= threshold, float64 compare) is applied on the device, so rows
+        # that will be dropped never cross PCIe and the host annotation only touches surviving rows (the optimiser's
+        # first iteration has several 1e5 rows per tile)
+        if n > 0:
+            keep = table[:, _COL_DMIN] <= float(self._transcript_distance_threshold)
+            if not bool(keep.all()):
+                if centroid_stats is not None:
+                    kh = keep.cpu().numpy()
+                    centroid_stats = tuple(a[kh] for a in centroid_stats)
+                table = table[keep]
+        eigvals = ctx.inertia_eigvals(table).cpu().numpy() if table.shape[0] > 0 else None
         # column-major on the host: the annotation works column by column (transposed on the device, a view here)
         tab = table.t().contiguous().cpu().numpy().T
         self._df_barcodes = self._annotate_table(tab, centroid_stats, eigvals)

@@ -131,11 +131,88 @@ def run_optimizer_scenario(RefPD):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def run_simcfg0_scenario(RefPD):
+    """configs[0]: the call sequence and parameters of the reference's simulation CLI
+    (cli/statphysbio_simulation/pixeldecode.py:259-292) on one tile: optimize_normalization_by_decoding(
+    n_random_tiles=1, n_iterations=3, magnitude (0.9, 10), minimum 28 px, default low-pass) followed by
+    decode_all_tiles(assign_to_cells=False, ...) with the blank-fraction filter.  Workers run in-process as in
+    ``run_optimizer_scenario``."""
+    import torch
+
+    import merfish3danalysis.PixelDecoder as refmod
+    from scenarios import SIM_CFG0, simcfg0_stack
+
+    df_cb, _cb, stack = simcfg0_stack()
+    tmp = Path(tempfile.mkdtemp())
+    try:
+        ds = ArrayDataStore(tmp / "qi2labdatastore", codebook=df_cb)
+        ds.add_tile(stack, persist=True)
+
+        class _Done:
+            exitcode = 0
+            pid = 0
+
+            def join(self):
+                return None
+
+        def run_inline(*, target, args, physical_gpu_id):
+            with rs.pandas2_semantics():
+                target(*args)
+            return _Done()
+
+        saved = (refmod._start_gpu_worker_process, refmod.qi2labDataStore, torch.cuda.set_device)
+        refmod._start_gpu_worker_process = run_inline
+        refmod.qi2labDataStore = lambda path, validate=False: ArrayDataStore(path)
+        torch.cuda.set_device = lambda *_a, **_k: None
+        try:
+            dec = RefPD(datastore=ds, use_mask=False, merfish_bits=16, verbose=0)
+            with rs.pandas2_semantics():
+                dec.optimize_normalization_by_decoding(
+                    n_random_tiles=1, n_iterations=SIM_CFG0["iterations"], lowpass_sigma=SIM_CFG0["lowpass"],
+                    magnitude_threshold=SIM_CFG0["magnitude"], minimum_pixels=SIM_CFG0["min_px"],
+                    feature_predictor_threshold=0.5, estimate_chromatic_affines=False,
+                )
+                dec.decode_all_tiles(
+                    assign_to_cells=False, lowpass_sigma=SIM_CFG0["lowpass"], magnitude_threshold=SIM_CFG0["magnitude"],
+                    minimum_pixels=SIM_CFG0["min_px"], feature_predictor_threshold=0.5, duplicate_radius_xy=None,
+                    duplicate_radius_z=None, filter_method="blank_fraction", target_gross_misid_rate=0.05,
+                    lr_fdr_target=0.05,
+                )
+        finally:
+            refmod._start_gpu_worker_process, refmod.qi2labDataStore, torch.cuda.set_device = saved
+        ds2 = ArrayDataStore(tmp / "qi2labdatastore")
+        g = ds2.load_decode_normalization_vectors(None, "global")
+        it = ds2.load_decode_normalization_vectors(None, "iterative")
+        tile = ds2.load_local_decoded_spots(0)
+        filt = ds2.load_global_filtered_decoded_spots()
+        t_arr = table_arrays(tile)
+        f_arr = table_arrays(filt)
+        np.savez_compressed(
+            OUT / "reference_simcfg0.npz", stack=stack,
+            global_normalization=np.asarray(g[0], dtype=np.float32), global_background=np.asarray(g[1], dtype=np.float32),
+            iterative_normalization=np.asarray(it[0], dtype=np.float32),
+            iterative_background=np.asarray(it[1], dtype=np.float32),
+            tile_table_columns=t_arr["table_columns"], tile_table=t_arr["table"], tile_gene_id=t_arr["gene_id"],
+            filtered_table_columns=f_arr["table_columns"], filtered_table=f_arr["table"], filtered_gene_id=f_arr["gene_id"],
+        )
+        print(f"simcfg0: iterative {np.asarray(it[0])[:4]} {np.asarray(it[1])[:4]}; {len(tile)} transcripts decoded, "
+              f"{len(filt)} after the blank-fraction filter; area min {tile['area'].min() if len(tile) else None}")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
+    """``python make_reference_golden.py [name ...]``: all fixtures, or only the named ones
+    (scenario names, ``optimizer``, ``simcfg0``)."""
+    only = set(sys.argv[1:])
     RefPD = rs.load_reference_pixeldecoder()
     for name, sc in SCENARIOS.items():
-        run_tile_scenario(name, sc, RefPD)
-    run_optimizer_scenario(RefPD)
+        if not only or name in only:
+            run_tile_scenario(name, sc, RefPD)
+    if not only or "optimizer" in only:
+        run_optimizer_scenario(RefPD)
+    if not only or "simcfg0" in only:
+        run_simcfg0_scenario(RefPD)
 
 
 if __name__ == "__main__":

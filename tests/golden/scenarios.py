@@ -23,6 +23,22 @@ SCENARIOS = {
     # configs[3] flavour: 22 bits, 300 random weight-4 codewords, 2-D decode mode
     "bits22": dict(shape=(4, 40, 48), seed=16, density=8e-3, lowpass=None, norm="global", min_px=4, bits=22,
                    microscope="2D"),
+    # configs[3] at the sizes BASELINE.json / SURVEY 8d name: K = 385 (the most a 22-bit weight-4 distance-4 code can
+    # hold) and K ~ 1000 weight-4 words -- sparse candidates (production vectors) and dense candidates (noise-level
+    # vectors: every voxel passes the magnitude gate, exact ties among codewords are common).  K > 256 takes the
+    # wide candidate sets / larger hash of the search kernel.
+    "bits22_k385": dict(shape=(4, 40, 48), seed=18, density=8e-3, lowpass=None, norm="global", min_px=4, bits=22,
+                        words=385, microscope="2D"),
+    "bits22_k1000": dict(shape=(4, 40, 48), seed=19, density=8e-3, lowpass=None, norm="global", min_px=4, bits=22,
+                         words=1000, microscope="2D"),
+    "bits22_k385_dense": dict(shape=(3, 40, 48), seed=20, density=1.5e-3, lowpass=None, norm="global", min_px=3, bits=22,
+                              words=385, microscope="2D", bkg=195.0, nrm=30.0, nrm_jitter=3.0, mag=(0.05, 10.0)),
+    "bits22_k1000_dense": dict(shape=(3, 40, 48), seed=21, density=1.5e-3, lowpass=None, norm="global", min_px=3, bits=22,
+                               words=1000, microscope="2D", bkg=195.0, nrm=30.0, nrm_jitter=3.0, mag=(0.05, 10.0)),
+    # dense candidates with the 16-bit MHD4 code in 3-D (the optimiser's first iteration looks like this: several
+    # bits of every trace clip to exactly 0 or 1, so exact distance ties between codewords are the rule)
+    "dense16": dict(shape=(6, 40, 48), seed=22, density=1.5e-3, lowpass=None, norm="global", min_px=4,
+                    bkg=195.0, nrm=30.0, nrm_jitter=3.0, mag=(0.05, 10.0)),
     # decode-time warp: bits imaged in later rounds carry an affine round transform; rounds 2 and 3 also a SOFIMA
     # flow field (round 4's is an identity fallback -> affine only); z crop on top
     "warp": dict(shape=(8, 40, 48), seed=17, density=6e-3, lowpass=None, norm="global", min_px=4, warp=True,
@@ -37,13 +53,16 @@ SCENARIOS = {
 def scenario_inputs(sc):
     """(codebook df, oracle codebook dict, stack uint16, predictor | None, bkg, nrm, excluded gene ids | None)."""
     n_bits = int(sc.get("bits", 16))
-    df_cb, cb = cases.codebook16() if n_bits == 16 else cases.codebook22(n_words=300)
+    df_cb, cb = cases.codebook16() if n_bits == 16 else cases.codebook22(n_words=int(sc.get("words", 300)))
     stack = cases.small_stack(cb["matrix"], shape=sc["shape"], seed=sc["seed"], density=sc["density"])
     rng = np.random.default_rng(sc["seed"] + 1000)
     pred = None
     if sc.get("predictor"):
         pred = rng.uniform(0.0, 1.0, size=stack.shape).astype(np.float32)
     bkg, nrm = cases.simple_vectors(n_bits, bkg=sc.get("bkg", 200.0), nrm=sc.get("nrm", 900.0), seed=sc["seed"])
+    if "nrm_jitter" in sc:  # noise-level vectors: a +-50 jitter would make them negative
+        j = float(sc["nrm_jitter"])
+        nrm = (np.float32(sc["nrm"]) + np.random.default_rng(sc["seed"]).uniform(-j, j, n_bits)).astype(np.float32)
     excluded = None
     if sc.get("exclude"):
         genes = [g for g in df_cb["gene_id"] if not str(g).lower().startswith("blank")]
@@ -130,3 +149,21 @@ def warp_tile_kwargs(sc):
     bit_xf = [np.eye(4, dtype=np.float32) if r == 1 else np.asarray(xf[r], dtype=np.float32) for r in bit_round]
     bit_flows = [None if r in (1, 4) else (flows[r][0], stride, box_start_xyz) for r in bit_round]
     return kwargs, bit_xf, bit_flows
+
+
+# configs[0] (BASELINE.json: "simulation-example dataset: one 3D tile, 16-bit MHD4 codebook"): the parameter set of the
+# reference's simulation CLI (cli/statphysbio_simulation/pixeldecode.py:18,259,273-276): magnitude (0.9, 10), minimum
+# 28 px, reference-default low-pass, ONE tile x THREE optimiser iterations, then decode_all_tiles with the blank-fraction
+# filter and no cell assignment.  The simulation volume is 16 x 48 x 512 x 512; the fixture keeps the call sequence and
+# the parameters on a volume small enough to commit.
+SIM_CFG0 = dict(shape=(14, 72, 80), seed=23, density=2.5e-3, magnitude=(0.9, 10.0), min_px=28, iterations=3,
+                lowpass=(3.0, 1.0, 1.0), amplitude=2600.0)
+
+
+def simcfg0_stack():
+    df_cb, cb = cases.codebook16()
+    from merfish3d_analysis_b200 import synthetic
+
+    stack = synthetic.make_stack(cb["matrix"], SIM_CFG0["shape"], SIM_CFG0["seed"], density=SIM_CFG0["density"],
+                                 amplitude=SIM_CFG0["amplitude"])
+    return df_cb, cb, stack

@@ -102,6 +102,43 @@ def test_oracle_optimizer_equals_reference_golden():
     np.testing.assert_array_equal(res["iterative"][1], g["iterative_background"])
 
 
+def simcfg0_tables(g):
+    tile = pd.DataFrame(g["tile_table"], columns=[str(c) for c in g["tile_table_columns"]])
+    tile["gene_id"] = [str(x) for x in g["tile_gene_id"]]
+    filt = pd.DataFrame(g["filtered_table"], columns=[str(c) for c in g["filtered_table_columns"]])
+    filt["gene_id"] = [str(x) for x in g["filtered_gene_id"]]
+    return tile, filt
+
+
+def test_oracle_equals_reference_on_the_simulation_cli_sequence():
+    """configs[0]: optimiser (1 tile x 3 iterations, magnitude (0.9, 10), minimum 28 px, default low-pass) then
+    decode_all_tiles with the blank-fraction filter, as cli/statphysbio_simulation/pixeldecode.py:259-292 calls them
+    (fixture: the reference's own run, ``make_reference_golden.py simcfg0``)."""
+    from oracle import table_oracle as tor
+    from scenarios import SIM_CFG0, simcfg0_stack
+
+    g = np.load(GOLDEN / "reference_simcfg0.npz")
+    _df_cb, cb, stack = simcfg0_stack()
+    np.testing.assert_array_equal(stack, g["stack"])
+    res = orc.optimize_normalization([(stack, None)], cb, SIM_CFG0["iterations"], True, SIM_CFG0["lowpass"],
+                                     SIM_CFG0["magnitude"], SIM_CFG0["min_px"])
+    np.testing.assert_array_equal(res["global_"][0], g["global_normalization"])
+    np.testing.assert_array_equal(res["global_"][1], g["global_background"])
+    np.testing.assert_array_equal(res["iterative"][0], g["iterative_normalization"])
+    np.testing.assert_array_equal(res["iterative"][1], g["iterative_background"])
+    df, _imgs = orc.decode_tile(stack, None, cb, res["iterative"][1], res["iterative"][0], True, SIM_CFG0["lowpass"],
+                                SIM_CFG0["magnitude"], SIM_CFG0["min_px"], spacing=(0.315, 0.098, 0.098))
+    tile, filt = simcfg0_tables(g)
+    assert len(tile) > 100 and tile["area"].min() >= SIM_CFG0["min_px"]
+    compare_with_reference_table(df, tile)
+    n_blank = sum(str(x).lower().startswith("blank") for x in cb["gene_ids"])
+    keep, _diag = tor.blank_fraction_filter(df, n_blank, len(cb["gene_ids"]), 0.05)
+    assert 0 < int(keep.sum()) < len(df)
+    # the reference's filter adds its own annotation columns (voxel_intensity ... cell_id): compare what the decode made
+    compare_with_reference_table(df[keep].reset_index(drop=True), filt[[c for c in filt.columns if c in tile.columns]])
+    assert (filt["cell_id"] == -1).all() and filt["blank_fraction_keep"].all()
+
+
 def test_reference_live_fresh_seed(tmp_path):
     """Build container only: run the reference itself on a seed no fixture holds."""
     import reference_shims as rs

@@ -150,3 +150,73 @@ def test_fullsize_dense_candidate_regime_matches_oracle_on_sample(big):
         assert (got >= 0).sum() > 1000
     finally:
         ctx.set_normalization(np.full(16, 200.0, np.float32), np.full(16, 900.0, np.float32))
+
+
+@pytest.mark.parametrize("origin", [(0, 0, 0), (37, 700, 1201), (84, 1792, 1792)])
+def test_fullsize_production_path_matches_oracle_on_crops(big, origin):
+    """The PRODUCTION path (gate + search + fused labelling + regionprops kernel) on the whole configs[1] tile against
+    the CPU oracle on a 16 x 256 x 256 crop of the same tile: the decoded image of the crop voxel by voxel, and the
+    feature-table row of every component the crop holds completely (components touching a crop face are cut by the
+    crop, not by the decoder) -- first voxel, area, codeword, centroid, per-bit means, distance_min, magnitude_mean
+    and inertia eigenvalues."""
+    import torch
+
+    import cases
+    from oracle import decode_oracle as orc
+
+    ctx, stack, _m = big
+    _df_cb, cb = cases.codebook16()
+    bkg, nrm = np.full(16, 200.0, np.float32), np.full(16, 900.0, np.float32)
+    ctx.set_normalization(bkg, nrm)
+    decoded = torch.empty(SHAPE, dtype=torch.int16, device="cuda")
+    n = ctx.decode_label(stack, decoded, False, 16.0, 500)
+    table = ctx.features(stack, decoded, False, n)
+    eig = ctx.inertia_eigvals(table).cpu().numpy()
+    table = table.cpu().numpy()
+    z0, y0, x0 = origin
+    cz, cy, cx = 16, 256, 256
+    crop = stack[:, z0:z0 + cz, y0:y0 + cy, x0:x0 + cx].cpu().numpy()
+    w = orc.weight_readout(crop, None)
+    unit = orc.normalize_codebook(cb["matrix"][:, :16])
+    out = orc.decode_pixels(w, unit, bkg, nrm, cb["pixel_assignment_threshold"], (1.5, 10.0), ())
+    np.testing.assert_array_equal(decoded[z0:z0 + cz, y0:y0 + cy, x0:x0 + cx].cpu().numpy(), out["decoded"])
+    raw = orc.label_decoded(out["decoded"], True)
+    # crop faces that are not the tile's own border cut components: those labels are left out of the comparison
+    cutting = [f for f in (
+        raw[0].ravel() if z0 > 0 else None, raw[-1].ravel() if z0 + cz < SHAPE[0] else None,
+        raw[:, 0].ravel() if y0 > 0 else None, raw[:, -1].ravel() if y0 + cy < SHAPE[1] else None,
+        raw[:, :, 0].ravel() if x0 > 0 else None, raw[:, :, -1].ravel() if x0 + cx < SHAPE[2] else None) if f is not None]
+    touching_raw = np.unique(np.concatenate(cutting))
+    touching_raw = touching_raw[touching_raw > 0]
+    labels = orc.filter_label_sizes(raw.copy(), 16.0)  # labels are not renumbered (PD:2987)
+    labels[np.isin(labels, touching_raw)] = 0
+    tab = orc.region_table(labels, out["distance"], out["magnitude"], out["scaled"])
+    assert len(tab) >= 20
+    zz, rem = np.divmod(tab["first_voxel"].to_numpy(np.int64), cy * cx)
+    yy, xx = np.divmod(rem, cx)
+    first_global = ((zz + z0) * SHAPE[1] + (yy + y0)) * SHAPE[2] + (xx + x0)
+    pos = np.searchsorted(table[:, 0], first_global.astype(np.float64))
+    assert (pos < len(table)).all() and np.array_equal(table[pos, 0], first_global.astype(np.float64)), \
+        "a complete component of the crop is missing from the production table"
+    got = table[pos]
+    np.testing.assert_array_equal(got[:, 1], tab["area"].to_numpy())
+    flat_dec = out["decoded"].ravel()
+    np.testing.assert_array_equal(got[:, 2], flat_dec[tab["first_voxel"].to_numpy(np.int64)].astype(np.float64))
+    np.testing.assert_allclose(got[:, 3], tab["z"].to_numpy() + z0, rtol=1e-12)
+    np.testing.assert_allclose(got[:, 4], tab["y"].to_numpy() + y0, rtol=1e-12)
+    np.testing.assert_allclose(got[:, 5], tab["x"].to_numpy() + x0, rtol=1e-12)
+    np.testing.assert_array_equal(got[:, 12], tab["distance_min"].to_numpy(np.float64))
+    np.testing.assert_array_equal(got[:, 13], tab["magnitude_mean"].to_numpy(np.float64))
+    means = np.stack([tab[f"intensity_mean-{b}"].to_numpy(np.float64) for b in range(16)], axis=1)
+    np.testing.assert_array_equal(got[:, 14:30], means)
+    ev = np.stack([tab[f"inertia_tensor_eigvals-{k}"].to_numpy(np.float64) for k in range(3)], axis=1)
+    np.testing.assert_allclose(eig[pos], ev, rtol=1e-9, atol=1e-9)
+    # and nothing else: every production component whose first voxel lies strictly inside the crop (one voxel away
+    # from the cutting faces) and that the crop holds completely is one of the oracle's rows
+    fz, frem = np.divmod(table[:, 0].astype(np.int64), SHAPE[1] * SHAPE[2])
+    fy, fx = np.divmod(frem, SHAPE[2])
+    inside = (fz >= z0) & (fz < z0 + cz) & (fy >= y0) & (fy < y0 + cy) & (fx >= x0) & (fx < x0 + cx)
+    prod_first_local = ((fz[inside] - z0) * cy + (fy[inside] - y0)) * cx + (fx[inside] - x0)
+    raw_at = raw.ravel()[prod_first_local]
+    complete = ~np.isin(raw_at, touching_raw)
+    assert set(prod_first_local[complete]) == set(tab["first_voxel"].to_numpy(np.int64))

@@ -133,3 +133,38 @@ def test_optimizer_tile_cache_does_not_change_the_result(tmp_path, budget, lowpa
     for t in kept:
         pd.testing.assert_frame_equal(kept[t], kept2[t])
     assert dec._tile_cache is None and not dec._buffers  # everything released at the end
+
+
+def test_cuda_path_on_the_simulation_cli_sequence(tmp_path):
+    """configs[0] through the public API exactly as the reference's simulation CLI drives it
+    (cli/statphysbio_simulation/pixeldecode.py:259-292): optimize_normalization_by_decoding(n_random_tiles=1,
+    n_iterations=3, magnitude (0.9, 10), minimum 28 px) then decode_all_tiles(assign_to_cells=False, blank-fraction
+    filter).  Vectors, the per-tile table and the filtered table equal the reference's own run."""
+    from merfish3d_analysis_b200.datastore import ArrayDataStore
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+    from scenarios import SIM_CFG0, simcfg0_stack
+    from test_cpu_reference_golden import simcfg0_tables
+
+    g = np.load(GOLDEN / "reference_simcfg0.npz")
+    df_cb, _cb, stack = simcfg0_stack()
+    ds = ArrayDataStore(tmp_path / "qi2labdatastore", codebook=df_cb)
+    ds.add_tile(stack)
+    dec = PixelDecoder(datastore=ds, use_mask=False, merfish_bits=16, verbose=0)
+    dec.optimize_normalization_by_decoding(
+        n_random_tiles=1, n_iterations=SIM_CFG0["iterations"], lowpass_sigma=SIM_CFG0["lowpass"],
+        magnitude_threshold=SIM_CFG0["magnitude"], minimum_pixels=SIM_CFG0["min_px"], feature_predictor_threshold=0.5,
+        estimate_chromatic_affines=False)
+    g_n, g_b = ds.load_decode_normalization_vectors(None, "global")
+    i_n, i_b = ds.load_decode_normalization_vectors(None, "iterative")
+    np.testing.assert_array_equal(g_n, g["global_normalization"])
+    np.testing.assert_array_equal(g_b, g["global_background"])
+    np.testing.assert_array_equal(i_n, g["iterative_normalization"])
+    np.testing.assert_array_equal(i_b, g["iterative_background"])
+    dec.decode_all_tiles(
+        assign_to_cells=False, lowpass_sigma=SIM_CFG0["lowpass"], magnitude_threshold=SIM_CFG0["magnitude"],
+        minimum_pixels=SIM_CFG0["min_px"], feature_predictor_threshold=0.5, duplicate_radius_xy=None,
+        duplicate_radius_z=None, filter_method="blank_fraction", target_gross_misid_rate=0.05, lr_fdr_target=0.05)
+    tile, filt = simcfg0_tables(g)
+    compare_with_reference_table(ds.load_local_decoded_spots(0), tile, rel=REL)
+    got = ds.load_global_filtered_decoded_spots()
+    compare_with_reference_table(got[[c for c in filt.columns]], filt, rel=REL)
