@@ -401,7 +401,7 @@ def _optimizer_extra(dist, world, rank, local, dev, matrix, df_cb, shared_root):
     total_s = time.perf_counter() - t0
     tm = dec._optimizer_timing
     kt = ctx.kernel_times_ms()
-    keys = ("total_s", "tiles_s", "exchange_s", "vectors_s", "stage_s", "decode_extract_s")
+    keys = ("total_s", "tiles_s", "local_table_s", "exchange_s", "vectors_s", "stage_s", "decode_extract_s")
     its = []
     for it in tm["iterations"]:
         vals = _max_over_ranks(dist, world, dev, [it.get(k, 0.0) for k in keys])
@@ -421,11 +421,11 @@ def _optimizer_extra(dist, world, rank, local, dev, matrix, df_cb, shared_root):
         "kernel_ms_whole_run_rank0": {k: v for k, v in sorted(kt.items(), key=lambda kv: -kv[1])[:8]},
         "iterative_normalization_head": [float(v) for v in np.asarray(i_n)[:4]],
         "exchange": "seed: all_reduce(SUM) of 2048-bin int64 digit histograms (radix select over tiles sharded on "
-                    "ranks); per iteration: sizes + one padded float64 all_gather of transcript rows" if world > 1
-                    else "single process: no collective",
+                    "ranks); per iteration: 3 all_reduce(SUM) of a (<= 64, 2048) int64 histogram tensor (pooled per-bit "
+                    "medians by radix select; no table leaves its rank)" if world > 1 else "single process: no collective",
         "note": "times are max over ranks; stage_s = datastore read + H2D + per-bit low-pass of tiles not yet resident "
-                "(0 once cached), decode_extract_s = decode + label + features + annotation, exchange_s = all_gather of "
-                "the tables, vectors_s = medians + JSON hand-off; all phases separated by stream syncs",
+                "(0 once cached), decode_extract_s = decode + label + features + annotation, local_table_s = concatenating this rank's tables, exchange_s = pooled "
+                "medians (histogram all_reduce), vectors_s = JSON hand-off; all phases separated by stream syncs",
     }
     ctx.set_timing(False)
     dec._cleanup()

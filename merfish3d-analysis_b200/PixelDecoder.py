@@ -64,6 +64,9 @@ _COL_MU = 6  # zz, yy, xx, zy, zx, yx
 _COL_DMIN, _COL_MAGMEAN = 12, 13
 
 
+_UNSET = object()
+
+
 def _is_identity_store(datastore) -> bool:
     return bool(getattr(datastore, "has_identity_decode_transforms", False))
 
@@ -403,8 +406,10 @@ class PixelDecoder:
         else:
             self._iterative_normalization_vectors(gpu_id=gpu_id)
 
-    def _iterative_normalization_vectors(self, gpu_id: int = 0) -> None:
-        """PD:1250-1421: per-bit medians over the pooled transcript table."""
+    def _iterative_normalization_vectors(self, gpu_id: int = 0, precomputed=_UNSET) -> None:
+        """PD:1250-1421: per-bit medians over the pooled transcript table.  ``precomputed``: the
+        ``(normalization, background)`` pair (or None = keep the previous vectors) already found by
+        ``_pooled_iterative_vectors`` over every rank's rows."""
         if not hasattr(self, "_df_barcodes_loaded"):
             raise ValueError("No decoded transcripts loaded: run optimize_normalization_by_decoding first.")
         if self._iterative_background_vector is None and self._iterative_normalization_vector is None:
@@ -413,7 +418,10 @@ class PixelDecoder:
         else:
             old_b = np.asarray(self._iterative_background_vector)
             old_n = np.asarray(self._iterative_normalization_vector)
-        res = _norm.iterative_normalization_vectors(self._df_barcodes_loaded, self._n_merfish_bits)
+        if precomputed is _UNSET:
+            res = _norm.iterative_normalization_vectors(self._df_barcodes_loaded, self._n_merfish_bits)
+        else:
+            res = precomputed
         if res is None:
             self._datastore.save_decode_normalization_vectors(
                 self._decode_run_key, "iterative", old_n.astype(np.float32), old_b.astype(np.float32),
@@ -1705,7 +1713,8 @@ class PixelDecoder:
             dist.barrier()
 
     def _gather_tables(self, local: pd.DataFrame) -> pd.DataFrame:
-        """The optimiser's one exchange per iteration: all-gather of every rank's
+        """FALLBACK exchange of the optimiser (tables holding values that are not float32 numbers, which this build
+        never writes; the regular exchange is ``_pooled_iterative_vectors``): all-gather of every rank's
         transcript rows so that all ranks compute identical per-bit MEDIANS (a sum all-reduce would
         change the result).  Only what the pooled statistics read travels -- per-bit mean intensities,
         on-bits, gene code, tile, distance_min, global coordinates -- as one float64 matrix per rank:
@@ -1760,6 +1769,60 @@ class PixelDecoder:
             if len(present) and bool(present[:, i].all()):
                 out[c] = pooled[:, nb + 5 + i].astype(np.int64) if c == "tile_idx" else pooled[:, nb + 5 + i]
         return out
+
+    def _pooled_iterative_vectors(self, local: pd.DataFrame):
+        """The optimiser's statistic (PD:1290-1368) over EVERY rank's transcripts without gathering them: each rank
+        keeps its rows; the 2 x bits medians (on-bit / off-bit mean intensities of non-blank transcripts) come from
+        a radix select whose digit histograms are summed with ``all_reduce`` -- three collectives of a
+        (<= 4 x bits, 2048) int64 tensor per iteration, whatever the number of transcripts.  A median is not a sum:
+        this is exact (same values as ``np.median`` over the pooled table), so every rank ends with the vectors a
+        single process computes.  Collective: every rank calls it once per iteration.
+
+        Returns ``(result, n_pooled)``; result = ``(normalization, background)`` float32 vectors, or None when
+        there is no non-blank transcript anywhere (the reference then keeps its previous vectors, PD:1272-1287)."""
+        import torch
+
+        rank, world, dist = self._dist()
+        nb = self._n_merfish_bits
+        multi = dist is not None and world > 1
+        backend = getattr(self, "_order_stats_backend", None)  # tests: a host restatement of the histogram kernel
+        if backend is None:
+            ctx = self._ctx(self._local_gpu())
+            device = ctx.device
+
+            def hist_fn(data, row, pm, pv, sh):
+                ctx.select_hist(data, row, prefix_mask=pm, prefix_value=pv, shift=sh)
+        else:
+            device, hist_fn = torch.device("cpu"), backend
+        has_cols = len(local.columns) > 0 and "gene_id" in local.columns and any(
+            c.startswith("bit") and c.endswith("_mean_intensity") for c in local.columns)
+        queries, kept, foreign = None, 0, 0
+        if has_cols:
+            queries, kept = _norm.iterative_vector_queries(local, nb, device)
+            foreign = int(queries is None)
+        if queries is None or len(queries) != 2 * nb:
+            foreign = max(foreign, int(queries is not None))  # a table with other bit columns: host path
+            queries = [torch.zeros(0, dtype=torch.float32, device=device) for _ in range(2 * nb)]
+        flags = torch.tensor([len(local), kept, foreign], dtype=torch.int64, device=device)
+        if multi:
+            dist.all_reduce(flags)
+        n_pooled, n_kept, any_foreign = (int(v) for v in flags.cpu())
+        if any_foreign:
+            # values that are not float32 numbers (tables this build did not write): gather and take the host median
+            pooled = self._gather_tables(local)
+            if len(pooled) == 0 and "gene_id" not in pooled.columns:
+                return None, n_pooled
+            return _norm.iterative_normalization_vectors(pooled, nb), n_pooled
+        if n_kept == 0:
+            return None, n_pooled
+
+        def reduce(hist):
+            dist.all_reduce(hist)
+
+        med = _norm.pooled_medians(queries, hist_fn,
+                                   lambda rows: torch.zeros((rows, 2048), dtype=torch.int64, device=device),
+                                   reduce if multi else None)
+        return _norm.finish_iterative_vectors(med[:nb], med[nb:]), n_pooled
 
     def optimize_normalization_by_decoding(
         self,
@@ -1873,20 +1936,26 @@ class PixelDecoder:
                 pos = {t: i for i, t in enumerate(random_tiles)}
                 tables.sort(key=lambda t: pos.get(t[0], len(pos)))
                 local = pd.concat([t[1] for t in tables], ignore_index=True) if tables else pd.DataFrame()
-                pooled = self._gather_tables(local)
-                t_gather = _time.perf_counter()
-                if len(pooled) == 0 and "gene_id" not in pooled.columns:
-                    pooled = pd.DataFrame({"gene_id": pd.Series(dtype="string")})
-                g = pooled["gene_id"]
-                self._df_barcodes_loaded = pooled[g.notna() & g.astype(str).str.strip().ne("")]
+                # every rank keeps ITS rows (the reference pools all tiles in the parent process, PD:4731-4733): the
+                # 2-D within-tile collapse only ever joins rows of one tile, and the medians are pooled by
+                # all-reduced histograms (_pooled_iterative_vectors) -- no table travels between ranks
+                if len(local) == 0 and "gene_id" not in local.columns:
+                    local = pd.DataFrame({"gene_id": pd.Series(dtype="string")})
+                g = local["gene_id"]
+                keep_rows = g.notna() & g.astype(str).str.strip().ne("")
+                self._df_barcodes_loaded = local if bool(keep_rows.all()) else local[keep_rows]
                 if not self._is_3D:
                     self._remove_duplicates_within_tile(
                         radius_xy=self._datastore.voxel_size_zyx_um[-1],
                         radius_z=self._datastore.voxel_size_zyx_um[0],
                     )
+                t_local = _time.perf_counter()
+                vectors, n_pooled = self._pooled_iterative_vectors(self._df_barcodes_loaded)
+                t_gather = _time.perf_counter()
+                pooled = range(n_pooled)  # only its length is reported below
                 self._load_global_normalization_vectors(gpu_id=self._local_gpu(), lowpass_sigma=lowpass_sigma)
                 if rank == 0:
-                    self._iterative_normalization_vectors(gpu_id=self._local_gpu())
+                    self._iterative_normalization_vectors(gpu_id=self._local_gpu(), precomputed=vectors)
                 self._barrier()
                 if rank != 0:
                     self._iterative_normalization_vector = None
@@ -1895,7 +1964,7 @@ class PixelDecoder:
                 self._global_normalization_vector = None
                 t_end = _time.perf_counter()
                 it = {"iteration": iteration, "total_s": t_end - t_it, "tiles_s": t_tiles - t_it,
-                      "exchange_s": t_gather - t_tiles, "vectors_s": t_end - t_gather,
+                      "local_table_s": t_local - t_tiles, "exchange_s": t_gather - t_local, "vectors_s": t_end - t_gather,
                       "tiles_this_rank": len(tables), "cache_hits": self._tile_cache_stats["hits"] - hits0,
                       "transcripts_pooled": int(len(pooled))}
                 if self._profile is not None:

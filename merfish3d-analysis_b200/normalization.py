@@ -70,32 +70,28 @@ class DeviceOrderStats:
         return int(self._pass(volumes, sub, clip0, pred, cutoffs, 0, 0, _SHIFTS[0]).sum())
 
     def select(self, volumes, ranks, sub=0.0, clip0=False, pred=PRED_ALL, cutoffs=None):
-        """Values at the given 0-based ranks of the pooled, predicate-filtered multiset."""
+        """Values at the given 0-based ranks of the pooled, predicate-filtered multiset.  The ranks are walked
+        digit by digit TOGETHER: ranks that still share a key prefix (the two middle ranks of a median, the two
+        neighbours of a percentile) share that level's histogram pass over the volumes."""
         cutoffs = [0.0] * len(volumes) if cutoffs is None else cutoffs
-        out = []
-        cache = {}
-        for rank in ranks:
-            rank = int(rank)
-            if rank in cache:
-                out.append(cache[rank])
-                continue
-            prefix_mask = 0
-            prefix_value = 0
-            remaining = rank
-            for shift, width in zip(_SHIFTS, _WIDTHS):
-                h = self._pass(volumes, sub, clip0, pred, cutoffs, prefix_mask, prefix_value, shift)
+        state = {int(r): [0, 0, int(r)] for r in ranks}  # rank -> [prefix_mask, prefix_value, remaining]
+        for shift, width in zip(_SHIFTS, _WIDTHS):
+            hists = {}
+            for st in state.values():
+                key = (st[0], st[1])
+                if key not in hists:
+                    hists[key] = self._pass(volumes, sub, clip0, pred, cutoffs, st[0], st[1], shift)
+                h = hists[key]
                 # the last digit (10 bits) is histogrammed with the kernel's fixed 11-bit mask: its
                 # top bit repeats the previous digit's lowest bit, already pinned by the prefix
                 cum = np.cumsum(h)
-                b = int(np.searchsorted(cum, remaining, side="right"))
+                b = int(np.searchsorted(cum, st[2], side="right"))
                 if b >= h.size:
                     raise ValueError("rank beyond the population")
-                remaining -= int(cum[b - 1]) if b > 0 else 0
-                prefix_value |= b << shift
-                prefix_mask |= (((1 << width) - 1) << shift) & 0xFFFFFFFF
-            cache[rank] = _key_to_f32(prefix_value)
-            out.append(cache[rank])
-        return out
+                st[2] -= int(cum[b - 1]) if b > 0 else 0
+                st[1] |= b << shift
+                st[0] |= (((1 << width) - 1) << shift) & 0xFFFFFFFF
+        return [_key_to_f32(state[int(r)][1]) for r in ranks]
 
     # ------------------------------------------------------------------ NumPy-exact wrappers
     def percentile(self, volume, q: float, sub=0.0, clip0=False):
@@ -202,3 +198,140 @@ def iterative_normalization_vectors(df, n_bits: int):
     nv = np.where(nv == 0.0, 1.0, nv)
     bv = np.nan_to_num(bv, 0.0)
     return nv.astype(np.float32), bv.astype(np.float32)
+
+
+def _numpy_hist_backend(data, hist_row, prefix_mask, prefix_value, shift):
+    """Host restatement of ``select_hist_kernel`` (csrc/api.cu) for tensors that live on the CPU: the digit
+    histogram of the order-preserving uint32 keys.  Used by the CPU tests of the multi-rank host logic."""
+    u = data.detach().cpu().numpy().astype(np.float32).view(np.uint32)
+    key = np.where(u & np.uint32(0x80000000), ~u, u | np.uint32(0x80000000)).astype(np.uint32)
+    sel = (key & np.uint32(prefix_mask)) == np.uint32(prefix_value)
+    digits = (key[sel] >> np.uint32(shift)) & np.uint32(2047)
+    h = np.bincount(digits.astype(np.int64), minlength=2048).astype(np.int64)
+    import torch
+
+    hist_row += torch.from_numpy(h)
+
+
+def pooled_medians(queries, hist_fn, new_hist, reduce=None):
+    """``np.median`` of each query's values pooled over all ranks, without gathering them.
+
+    ``queries``: list of 1-D float32 tensors (this rank's part of every multiset; may be empty).
+    ``hist_fn(data, hist_row, prefix_mask, prefix_value, shift)`` adds the 2048-bin digit histogram of ``data``'s
+    keys into ``hist_row`` (``DecodeContext.select_hist`` on the device); ``new_hist(rows)`` allocates a zeroed
+    ``(rows, 2048)`` int64 tensor; ``reduce(hist)`` sums it in place over the process group (``all_reduce``).
+
+    Three rounds, each ONE collective and ONE device-to-host copy for all queries together: the first digit's
+    histograms (which also give the pooled counts), then the second and third digit of the one or two middle
+    ranks of every query.  Exact: the result is the float64 mean of the two middle float32 values, like
+    ``np.median`` of the float64 column the reference builds (PD:1345-1356).  Returns a list of float (NaN where
+    the pooled multiset is empty) -- identical on every rank."""
+    nq = len(queries)
+    out = [float("nan")] * nq
+    if nq == 0:
+        return out
+
+    def run(rows):
+        """rows: list of (query index, prefix_mask, prefix_value, shift) -> (len(rows), 2048) host histograms"""
+        hist = new_hist(len(rows))
+        for r, (q, pm, pv, sh) in enumerate(rows):
+            if queries[q].numel():
+                hist_fn(queries[q], hist[r], pm, pv, sh)
+        if reduce is not None:
+            reduce(hist)
+        return hist.cpu().numpy()
+
+    first = run([(q, 0, 0, _SHIFTS[0]) for q in range(nq)])
+    counts = first.sum(axis=1)
+    # targets: (query, rank) with per-target walking state [prefix_mask, prefix_value, remaining]
+    targets = {}
+    for q in range(nq):
+        n = int(counts[q])
+        if n == 0:
+            continue
+        for r in sorted({(n - 1) // 2, n // 2}):
+            targets[(q, r)] = [0, 0, r]
+    for level, (shift, width) in enumerate(zip(_SHIFTS, _WIDTHS)):
+        if level == 0:
+            hist_of = {(q, 0, 0): first[q] for q in range(nq)}
+        else:
+            keys = sorted({(q, st[0], st[1]) for (q, _r), st in targets.items()})
+            hs = run([(q, pm, pv, shift) for q, pm, pv in keys]) if keys else np.zeros((0, 2048), dtype=np.int64)
+            hist_of = {k: hs[i] for i, k in enumerate(keys)}
+        for (q, _r), st in targets.items():
+            h = hist_of[(q, st[0], st[1])]
+            cum = np.cumsum(h)
+            b = int(np.searchsorted(cum, st[2], side="right"))
+            if b >= h.size:
+                raise ValueError("rank beyond the population")
+            st[2] -= int(cum[b - 1]) if b > 0 else 0
+            st[1] |= b << shift
+            st[0] |= (((1 << width) - 1) << shift) & 0xFFFFFFFF
+    for q in range(nq):
+        n = int(counts[q])
+        if n == 0:
+            continue
+        a = np.float64(_key_to_f32(targets[(q, (n - 1) // 2)][1]))
+        b = np.float64(_key_to_f32(targets[(q, n // 2)][1]))
+        out[q] = float((a + b) / 2.0) if (n % 2 == 0) else float(a)
+    return out
+
+
+def finish_iterative_vectors(med_on, med_off):
+    """PD:1358-1368: float32, round to 0.1, NaN -> 1 / 0, normalisation 0 -> 1."""
+    nv = np.round(np.asarray(med_on, dtype=np.float64).astype(np.float32), 1)
+    bv = np.round(np.asarray(med_off, dtype=np.float64).astype(np.float32), 1)
+    nv = np.nan_to_num(nv, 1.0)
+    nv = np.where(nv == 0.0, 1.0, nv)
+    bv = np.nan_to_num(bv, 0.0)
+    return nv.astype(np.float32), bv.astype(np.float32)
+
+
+def non_blank_rows(df) -> np.ndarray:
+    """Boolean mask of the rows whose gene id does not start with 'blank' (case-insensitive; missing ids are kept,
+    PD:1263-1270) -- evaluated once per distinct id instead of once per row."""
+    import pandas as pd
+
+    codes, uniques = pd.factorize(df["gene_id"], use_na_sentinel=True)
+    blank_u = np.array([str(u).lower().startswith("blank") for u in uniques], dtype=bool)
+    if blank_u.size == 0:
+        return np.ones(len(df), dtype=bool)
+    return np.where(codes >= 0, ~blank_u[np.maximum(codes, 0)], True)
+
+
+def iterative_vector_queries(df, n_bits: int, device):
+    """The 2 x bits multisets behind the iterative vectors (PD:1290-1356) as float32 tensors on ``device``:
+    for every bit column (sorted by name like the reference) the mean intensities of the non-blank rows that have
+    the bit ON, then those that have it OFF.  Returns ``(queries, n_rows_kept)`` or ``(None, 0)`` when the table has
+    no bit columns; values that are not exactly float32-representable or not finite make it return ``None`` too
+    (foreign tables: the caller falls back to the host median)."""
+    import torch
+
+    bit_cols = sorted(c for c in df.columns if c.startswith("bit") and c.endswith("_mean_intensity"))
+    if not bit_cols:
+        return None, 0
+    keep = non_blank_rows(df) if len(df) else np.zeros(0, dtype=bool)
+    vals = df[bit_cols].to_numpy(dtype=np.float64)[keep]
+    on = df[[f"on_bit_{k}" for k in range(1, 5)]].to_numpy(dtype=np.int64)[keep]
+    v64 = torch.from_numpy(np.ascontiguousarray(vals)).to(device)
+    v32 = v64.to(torch.float32)
+    if v64.numel() and not bool(((v32.to(torch.float64) == v64) | torch.isnan(v64)).all()):
+        return None, int(keep.sum())
+    col_bit = [int(c[3:5]) for c in bit_cols]
+    col_of_bit = torch.full((max(col_bit + [int(on.max()) if on.size else 0]) + 2,), len(bit_cols), dtype=torch.int64,
+                            device=device)
+    col_of_bit[torch.tensor(col_bit, dtype=torch.int64, device=device)] = torch.arange(len(bit_cols), device=device)
+    is_on = torch.zeros((v32.shape[0], len(bit_cols) + 1), dtype=torch.bool, device=device)
+    if on.size:
+        on_d = torch.from_numpy(np.ascontiguousarray(on)).to(device).clamp_(min=0)
+        is_on.scatter_(1, col_of_bit[on_d], True)
+    is_on = is_on[:, : len(bit_cols)]
+    finite = ~torch.isnan(v32)
+    queries = []
+    for j in range(len(bit_cols)):
+        col = v32[:, j]
+        queries.append(col[is_on[:, j] & finite[:, j]].contiguous())
+    for j in range(len(bit_cols)):
+        col = v32[:, j]
+        queries.append(col[~is_on[:, j] & finite[:, j]].contiguous())
+    return queries, int(keep.sum())

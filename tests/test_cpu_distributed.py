@@ -57,6 +57,10 @@ def _patch(decoder, log):
 
     decoder._global_normalization_vectors = types.MethodType(fake_global, decoder)
     decoder.decode_one_tile = types.MethodType(fake_decode, decoder)
+    # the digit histograms of the pooled medians: host restatement of select_hist_kernel, reduced over gloo
+    from merfish3d_analysis_b200 import normalization as _norm
+
+    decoder._order_stats_backend = _norm._numpy_hist_backend
 
 
 def _make_store(path, n_tiles):
@@ -122,8 +126,10 @@ def test_two_rank_optimiser_matches_single_process(tmp_path):
     (r0, log_a, nv_a, bv_a, mem_a), (r1, log_b, nv_b, bv_b, mem_b) = results
     # contiguous chunks like PD:4811-4818: ceil(5/2) = 3 -> rank 0: tiles 0-2, rank 1: tiles 3-4
     assert sorted({t for t, _ in log_a}) == [0, 1, 2] and sorted({t for t, _ in log_b}) == [3, 4]
-    # every rank ends with the same vectors, equal to the single-process result (median of the
-    # pooled table, not a sum all-reduce)
+    # every rank ends with the same vectors, equal to the single-process result and to the host median of the pooled
+    # table (the exchange is an all-reduce of digit histograms -- an exact order statistic, not a sum of means)
+    from merfish3d_analysis_b200 import normalization as _norm
+
     np.testing.assert_array_equal(np.float32(nv_a), nv1)
     np.testing.assert_array_equal(np.float32(bv_a), bv1)
     assert nv_a == nv_b and bv_a == bv_b and mem_a == mem_b == nv_a

@@ -1,3 +1,4 @@
 set -x
-python tools/multi_tile_profile.py 2>&1 | tail -60
-python tools/opt_it0_profile.py 2>&1 | tail -50
+python -m pytest tests/test_gpu_reference_golden.py tests/test_gpu_zarr_store.py -x -q -k "golden or simulation" 2>&1 | tail -15
+python -m pytest tests/test_gpu_fullsize.py -x -q 2>&1 | tail -15
+python tools/opt_it0_profile.py 2>&1 | tail -75
