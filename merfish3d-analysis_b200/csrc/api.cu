@@ -33,7 +33,20 @@ DecodeParams m3d_ctx::params() const {
         const bool live = use_norm && b < n_bits;
         P.bkg[b] = live ? bkg[b] : 0.f;
         P.nrm[b] = live ? nrm[b] : 1.f;
+        // reciprocal form of (s - bkg) / nrm (voxel_math.cuh, div_by_rcp): only for ordinary vectors -- |nrm| in
+        // [2^-40, 2^40] with a significand that is not all ones, bkg = 0 or |bkg| in [2^-20, 2^30] (so that an integer
+        // sample minus bkg is 0 or at least 2^-24 in magnitude); anything else keeps the IEEE division (rcp = 0)
+        const float nm = P.nrm[b], bg = P.bkg[b];
+        uint32_t nbits;
+        memcpy(&nbits, &nm, 4);
+        const float an = fabsf(nm), ab = fabsf(bg);
+        const bool ok = an >= 9.0949470177e-13f && an <= 1.0995116278e+12f && (nbits & 0x7FFFFFu) != 0x7FFFFFu &&
+                        (bg == 0.f || (ab >= 9.5367431640625e-07f && ab <= 1073741824.0f));
+        P.rcp[b] = ok ? 1.0f / nm : 0.f;  // float division on the host: correctly rounded
     }
+    P.rcp_all = 1;
+    for (int b = 0; b < n_bits; ++b)
+        if (P.rcp[b] == 0.f) P.rcp_all = 0;
     P.pix_thr = pix_thr;
     P.mag_lo = mag_lo;
     P.mag_hi = mag_hi;

@@ -96,6 +96,8 @@ struct Scratch {
 struct DecodeParams {
     float bkg[M3D_MAX_BITS];
     float nrm[M3D_MAX_BITS];
+    float rcp[M3D_MAX_BITS];  // RN(1 / nrm) when the reciprocal form of the division is proven exact, else 0 (voxel_math.cuh)
+    int rcp_all;              // every live bit has rcp != 0
     float pix_thr, mag_lo, mag_hi;
     int n_bits;
     int K;

@@ -158,7 +158,7 @@ struct SearchSmem {
     uint32_t* hkeys;     // [1 << hash_bits] (mode 2)
     uint32_t* masks;     // [round_up(K, 8)] on-bit masks, 0 beyond K (mode 2, tensor-core on-bit sums)
     uint32_t* cand_bits; // [SEARCH_THREADS][ceil(K/32)] per-voxel candidate sets marked by the tensor-core pass (mode 2)
-    uint2* blut;         // [16] B-fragment registers by 4-bit on/off pattern (bits 2t, 2t+1, 2t+8, 2t+9 of a codeword)
+    uint4* afrag;        // [ceil(K/16)][KS][32] A fragments (codeword rows x bit columns, bf16 0/1) of the on-bit matrix
     int16_t* hvals;      // [1 << hash_bits]
     uint8_t* on;         // [K][max_on]
 };
@@ -166,7 +166,9 @@ struct SearchSmem {
 static size_t search_smem_bytes(int nb, const DecodeParams& P) {
     size_t n = (size_t)(nb + 1) * XS_STRIDE * 4;
     if (P.mode >= 1) n += (size_t)P.K * 8 + (size_t)P.K * P.max_on;
-    if (P.mode == 2) n += ((size_t)1 << P.hash_bits) * 6 + (size_t)((P.K + 7) & ~7) * 4 + (size_t)SEARCH_THREADS * ((P.K + 31) / 32) * 4 + 16 * 8 + 8;
+    if (P.mode == 2)
+        n += ((size_t)1 << P.hash_bits) * 6 + (size_t)((P.K + 7) & ~7) * 4 + (size_t)SEARCH_THREADS * ((P.K + 31) / 32) * 4 +
+             (size_t)((P.K + 15) / 16) * ((nb + 15) / 16) * 32 * 16 + 16;
     return n + 16;
 }
 
@@ -179,7 +181,7 @@ __device__ __forceinline__ SearchSmem stage_codebook(unsigned char* smem, const 
     s.hkeys = nullptr;
     s.masks = nullptr;
     s.cand_bits = nullptr;
-    s.blut = nullptr;
+    s.afrag = nullptr;
     s.hvals = nullptr;
     s.on = nullptr;
     if (P.mode >= 1) {
@@ -198,14 +200,25 @@ __device__ __forceinline__ SearchSmem stage_codebook(unsigned char* smem, const 
         s.masks = s.hkeys + hs;
         s.cand_bits = s.masks + kpad;
         uint32_t* after_bits = s.cand_bits + SEARCH_THREADS * ((P.K + 31) / 32);
-        after_bits += (reinterpret_cast<uintptr_t>(after_bits) & 7u) ? 1 : 0;  // 8-byte alignment for the uint2 table
-        s.blut = reinterpret_cast<uint2*>(after_bits);
-        if (threadIdx.x < 16) {
-            const uint32_t i = threadIdx.x;  // bit0: k row 2t, bit1: 2t+1, bit2: 2t+8, bit3: 2t+9; 0x3F80 = bf16(1.0)
-            s.blut[i] = make_uint2(((i & 1u) ? 0x3F80u : 0u) | ((i & 2u) ? 0x3F800000u : 0u),
-                                   ((i & 4u) ? 0x3F80u : 0u) | ((i & 8u) ? 0x3F800000u : 0u));
+        while (reinterpret_cast<uintptr_t>(after_bits) & 15u) ++after_bits;  // 16-byte alignment for the fragment table
+        s.afrag = reinterpret_cast<uint4*>(after_bits);
+        constexpr int KS = (NB + 15) / 16;
+        const int n_mt = (P.K + 15) >> 4;
+        // A fragment of mma.m16n8k16 (row-major 16 x 16, bf16): lane (g = lane / 4, t = lane % 4) holds
+        // a0 = (row g, cols 2t, 2t+1), a1 = (row g+8, same cols), a2 = (row g, cols 2t+8, 2t+9), a3 = (row g+8, ...);
+        // rows = codewords 16 i + ..., columns = bits 16 ks + ...; 0x3F80 = bf16(1.0); rows >= K are zero
+        for (int e = threadIdx.x; e < n_mt * KS * 32; e += SEARCH_THREADS) {
+            const int lane = e & 31, ks = (e >> 5) % KS, i = (e >> 5) / KS;
+            const int g = lane >> 2, t = lane & 3;
+            const int k0 = 16 * i + g, k1 = k0 + 8;
+            const uint32_t m0 = (k0 < P.K) ? P.cw_mask[k0] : 0u, m1 = (k1 < P.K) ? P.cw_mask[k1] : 0u;
+            const int c = 16 * ks + 2 * t;
+            auto pack = [](uint32_t m, int col) -> uint32_t {
+                return (((m >> col) & 1u) ? 0x3F80u : 0u) | (((m >> (col + 1)) & 1u) ? 0x3F800000u : 0u);
+            };
+            s.afrag[e] = make_uint4(pack(m0, c), pack(m1, c), pack(m0, c + 8), pack(m1, c + 8));
         }
-        s.hvals = reinterpret_cast<int16_t*>(s.blut + 16);
+        s.hvals = reinterpret_cast<int16_t*>(s.afrag + n_mt * KS * 32);
         for (int i = threadIdx.x; i < hs; i += SEARCH_THREADS) {
             s.hkeys[i] = P.hash_keys[i];
             s.hvals[i] = P.hash_vals[i];
@@ -234,13 +247,14 @@ __device__ __forceinline__ void load_stack_trace(const T* __restrict__ stack, si
     }
 }
 
-template <int NB>
+template <int NB, bool INT_IN>
 __device__ __forceinline__ void finish_trace(const float (&s)[NB], const DecodeParams& P, float (&x)[NB],
                                              float (&xh)[NB], float& mag) {
 #pragma unroll
-    for (int b = 0; b < NB; ++b) x[b] = (b < P.n_bits) ? scale_clip(s[b], P.bkg[b], P.nrm[b]) : 0.f;
+    for (int b = 0; b < NB; ++b)
+        x[b] = (b < P.n_bits) ? scale_clip<INT_IN>(s[b], P.bkg[b], P.nrm[b], P.rcp[b]) : 0.f;
     const float n = l2_norm<NB>(x);
-    mag = unit_vector<NB>(x, n, xh);
+    mag = unit_vector<NB>(x, n, xh, INT_IN && P.rcp_all);
 }
 
 template <typename T, int NB>
@@ -248,7 +262,7 @@ __device__ __forceinline__ void exact_trace(const T* __restrict__ stack, size_t 
                                             const DecodeParams& P, float (&x)[NB], float (&xh)[NB], float& mag) {
     float s[NB];
     load_stack_trace<T, NB>(stack, n_vox, v, P, s);
-    finish_trace<NB>(s, P, x, xh, mag);
+    finish_trace<NB, sizeof(T) == 2>(s, P, x, xh, mag);  // 2-byte samples = uint16: integers in [0, 65535]
 }
 
 // ------------------------------------------------------------------ lane-parallel scans (modes 0, 1, 2)
@@ -408,88 +422,109 @@ __device__ __forceinline__ void mma_bf16_m16n8k16(float (&d)[4], const uint32_t 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// on-bit sums of one n tile (8 codewords) for the 16 voxels of an m tile; accumulator layout: d0,d1 = row g,
-// codewords 8j+2t, 8j+2t+1; d2,d3 = row g+8
-template <int KS>
-__device__ __forceinline__ void onbit_sums_tile(const uint32_t (&ahi)[KS][4], const uint32_t (&alo)[KS][4], uint32_t m,
-                                                int t, const uint2* __restrict__ blut, float (&d)[4]) {
-    d[0] = d[1] = d[2] = d[3] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-        const uint32_t mm = m >> (ks * 16 + 2 * t);  // B fragment: bits 2t, 2t+1, 2t+8, 2t+9 of this lane's codeword
-        const uint2 b = blut[(mm & 3u) | ((mm >> 6) & 12u)];
-        mma_bf16_m16n8k16(d, ahi[ks], b.x, b.y);
-        mma_bf16_m16n8k16(d, alo[ks], b.x, b.y);
-    }
-}
-
-// For the 32 voxels whose unit traces sit in this warp's xs columns: mark in S.cand_bits every codeword that can be
-// the exact arg-min (nothing is marked for NaN traces).  All lanes must call; the bit sets must be zero on entry.
+// For the 32 voxels whose unit traces sit in this warp's xs columns: write into S.cand_bits the set of codewords that
+// can be the exact arg-min (empty for NaN traces).  All lanes must call.
+//
+// Roles in D = A . B (m16n8k16): A = 16 codewords x 16 bits of the on-bit matrix (exact in bf16; the fragments are
+// precomputed once per block, S.afrag: one 128-bit shared-memory load per tile), B = 16 bits x 8 voxels (the traces,
+// bf16 hi + lo, built once per 32 voxels and kept in registers), D = on-bit sums of 16 codewords x 8 voxels.  Lane
+// (g, t) then holds codewords 16 i + g, 16 i + g + 8 for voxels 8 j + 2t, 8 j + 2t + 1.
 template <int NB>
 __device__ __forceinline__ void mma_mark_candidates_warp(const DecodeParams& P, const SearchSmem& S, int warp_col0) {
     constexpr int KS = (NB + 15) / 16;
     const unsigned lane = threadIdx.x & 31u;
     const int g = (int)(lane >> 2), t = (int)(lane & 3u);
-    const int n_tiles = (P.K + 7) >> 3;
+    const int n_mt = (P.K + 15) >> 4;
     const int n_words = (P.K + 31) >> 5;
     const float window = M3D_SUM_MARGIN + 2.f * ((float)P.max_on * 1.5259e-5f + 4.0e-6f);
-    const float inf = __int_as_float(0x7f800000);
-#pragma unroll 1
-    for (int mt = 0; mt < 2; ++mt) {
-        // A fragments (row = voxel, column = bit): rows g and g+8, bit columns 2t, 2t+1, 2t+8, 2t+9 per k step
-        uint32_t ahi[KS][4], alo[KS][4];
-        const float* c0 = S.xs + warp_col0 + mt * 16 + g;
-        const float* c1 = c0 + 8;
+    // B fragments (rows = bits 2t, 2t+1 | 2t+8, 2t+9 of the k step, column = voxel 8 j + g)
+    uint32_t bhi[4][KS][2], blo[4][KS][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float* col = S.xs + warp_col0 + 8 * j + g;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int b = ks * 16 + h * 8 + 2 * t;
                 const int r0 = (b < NB ? b : NB) * XS_STRIDE, r1 = (b + 1 < NB ? b + 1 : NB) * XS_STRIDE;  // NB = zero row
-                split_bf16x2(c0[r0], c0[r1], ahi[ks][2 * h], alo[ks][2 * h]);
-                split_bf16x2(c1[r0], c1[r1], ahi[ks][2 * h + 1], alo[ks][2 * h + 1]);
+                split_bf16x2(col[r0], col[r1], bhi[j][ks][h], blo[j][ks][h]);
             }
         }
-        // pass 1: largest on-bit sum per voxel row
-        float rmax[2] = {-inf, -inf};
-        for (int j = 0; j < n_tiles; ++j) {
-            float d[4];
-            onbit_sums_tile<KS>(ahi, alo, S.masks[8 * j + g], t, S.blut, d);
-            const int k0 = 8 * j + 2 * t;
-            if (k0 < P.K) {
-                rmax[0] = fmaxf(rmax[0], d[0]);
-                rmax[1] = fmaxf(rmax[1], d[2]);
-            }
-            if (k0 + 1 < P.K) {
-                rmax[0] = fmaxf(rmax[0], d[1]);
-                rmax[1] = fmaxf(rmax[1], d[3]);
-            }
-        }
+    }
+    auto sums = [&](const uint4 (&a)[KS], int j, float (&d)[4]) {
+        d[0] = d[1] = d[2] = d[3] = 0.f;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            rmax[r] = fmaxf(rmax[r], __shfl_xor_sync(0xffffffffu, rmax[r], 1));
-            rmax[r] = fmaxf(rmax[r], __shfl_xor_sync(0xffffffffu, rmax[r], 2));
+        for (int ks = 0; ks < KS; ++ks) {
+            const uint32_t af[4] = {a[ks].x, a[ks].y, a[ks].z, a[ks].w};
+            mma_bf16_m16n8k16(d, af, bhi[j][ks][0], bhi[j][ks][1]);
+            mma_bf16_m16n8k16(d, af, blo[j][ks][0], blo[j][ks][1]);
         }
-        // pass 2: mark every codeword inside the window
-        const float cut[2] = {rmax[0] - window, rmax[1] - window};
-        uint32_t* bits0 = S.cand_bits + (size_t)(warp_col0 + mt * 16 + g) * n_words;
-        uint32_t* bits1 = bits0 + 8 * n_words;
-        for (int j = 0; j < n_tiles; ++j) {
+    };
+    // pass 1: largest on-bit sum of every voxel (sums are >= 0, padding rows give 0: no bound checks needed)
+    float vmax[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) vmax[j][0] = vmax[j][1] = 0.f;
+    const uint4* af = S.afrag + lane;
+    for (int i = 0; i < n_mt; ++i) {
+        uint4 a[KS];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) a[ks] = af[(i * KS + ks) * 32];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
             float d[4];
-            onbit_sums_tile<KS>(ahi, alo, S.masks[8 * j + g], t, S.blut, d);
-            const int k0 = 8 * j + 2 * t;  // k0 and k0+1 share a word (k0 is even)
-            uint32_t m0 = 0u, m1 = 0u;
-            if (k0 < P.K) {
-                m0 |= (d[0] >= cut[0]) ? 1u : 0u;
-                m1 |= (d[2] >= cut[1]) ? 1u : 0u;
-            }
-            if (k0 + 1 < P.K) {
-                m0 |= (d[1] >= cut[0]) ? 2u : 0u;
-                m1 |= (d[3] >= cut[1]) ? 2u : 0u;
-            }
-            if (m0) atomicOr(bits0 + (k0 >> 5), m0 << (k0 & 31));
-            if (m1) atomicOr(bits1 + (k0 >> 5), m1 << (k0 & 31));
+            sums(a, j, d);
+            vmax[j][0] = fmaxf(vmax[j][0], fmaxf(d[0], d[2]));
+            vmax[j][1] = fmaxf(vmax[j][1], fmaxf(d[1], d[3]));
         }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            float v = vmax[j][c];  // the other codeword rows of this voxel live in the lanes with the same t
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+            vmax[j][c] = v - window;  // from here on: the cut
+        }
+    // pass 2: the candidate sets, one 32-bit word (= two tiles of 16 codewords) at a time.  Every lane builds the bits
+    // of its own two codeword rows for its eight voxels in registers; the eight lanes that share t (they hold the other
+    // rows of the same voxels) OR them with three shuffles, and the g == 0 lane stores the finished word: no atomics,
+    // no divergent branches, and the sets need no clearing beforehand.  NaN sums compare false: nothing is marked.
+    for (int w = 0; w < n_words; ++w) {
+        uint32_t mk[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mk[j][0] = mk[j][1] = 0u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = 2 * w + h;
+            if (i < n_mt) {  // uniform
+                uint4 a[KS];
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) a[ks] = af[(i * KS + ks) * 32];
+                const uint32_t bit0 = 1u << (16 * h + g), bit1 = bit0 << 8;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float d[4];
+                    sums(a, j, d);
+                    mk[j][0] |= (d[0] >= vmax[j][0] ? bit0 : 0u) | (d[2] >= vmax[j][0] ? bit1 : 0u);
+                    mk[j][1] |= (d[1] >= vmax[j][1] ? bit0 : 0u) | (d[3] >= vmax[j][1] ? bit1 : 0u);
+                }
+            }
+        }
+        // padding rows (k >= K) have a zero sum, which passes when the cut is <= 0: drop them
+        const uint32_t valid = (w == n_words - 1 && (P.K & 31)) ? ((1u << (P.K & 31)) - 1u) : 0xFFFFFFFFu;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t word = mk[j][c];  // OR over the eight lanes that share t (redux.sync is only fast for full masks)
+                word |= __shfl_xor_sync(0xffffffffu, word, 4);
+                word |= __shfl_xor_sync(0xffffffffu, word, 8);
+                word |= __shfl_xor_sync(0xffffffffu, word, 16);
+                if (g == 0) S.cand_bits[(size_t)(warp_col0 + 8 * j + 2 * t + c) * n_words + w] = word & valid;
+            }
     }
     __syncwarp();
 }
@@ -511,23 +546,54 @@ __device__ __forceinline__ void nearest_codeword_warp(bool want, const float (&x
         if (__popc(pending) > COOP_SWITCH) {
             // dense regime: on-bit sums of all 32 voxels on the tensor cores, exact distance for the settled ones
             const int n_words = (P.K + 31) >> 5;
-            uint32_t* my_bits = S.cand_bits + (size_t)threadIdx.x * n_words;
-            for (int w = 0; w < n_words; ++w) my_bits[w] = 0u;
-            __syncwarp();
+            const uint32_t* my_bits = S.cand_bits + (size_t)threadIdx.x * n_words;
             mma_mark_candidates_warp<NB>(P, S, warp_col0);
             if (!done) {
-                float best_d = __int_as_float(0x7f800000);
+                // exact direct form over the marked set.  Per bit the term is (xh_b - c)^2 when the codeword has the
+                // bit and xh_b^2 otherwise -- both computed once per voxel with the direct form's own operations
+                // (direct_distance_binary), so a candidate costs a select and an add per bit.  The square root is
+                // monotone: a candidate can only beat the running best if its SUM is smaller, and only then are the
+                // two distances compared (equal distance from a smaller sum must not replace the earlier index).
+                float t_on[NB], t_off[NB];
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const float tt = __fsub_rn(xh[b], P.cval);
+                    t_on[b] = __fmul_rn(tt, tt);
+                    t_off[b] = __fmul_rn(xh[b], xh[b]);
+                }
+                const uint32_t* masks_sh = S.masks;
+                float best_acc = __int_as_float(0x7f800000), best_d = __int_as_float(0x7f800000);
                 int best_k = -1;
-                for (int w = 0; w < n_words; ++w) {
-                    uint32_t bits = my_bits[w];
-                    while (bits) {  // ascending k: a later equal distance never replaces an earlier one
-                        const int kk = w * 32 + __ffs(bits) - 1;
-                        bits &= bits - 1u;
-                        const float dd = direct_distance_binary<NB>(xh, S.masks[kk], P.cval);
+                auto consider = [&](int kk, float acc) {
+                    if (acc < best_acc) {
+                        const float dd = __fsqrt_rn(acc);
                         if (dd < best_d) {
                             best_d = dd;
                             best_k = kk;
                         }
+                        // keep the smallest sum seen among candidates that did not lose: a later candidate with a sum
+                        // in [acc, best_acc) has distance >= dd >= best_d and cannot win either
+                        best_acc = acc;
+                    }
+                };
+                for (int w = 0; w < n_words; ++w) {
+                    uint32_t bits = my_bits[w];
+                    while (bits) {  // ascending k: a later equal distance never replaces an earlier one
+                        // two candidates per round: each sum is one dependent chain of adds, two chains interleave
+                        const int ka = w * 32 + __ffs(bits) - 1;
+                        bits &= bits - 1u;
+                        const int kb = bits ? (w * 32 + __ffs(bits) - 1) : ka;  // odd count: the same one again (harmless)
+                        bits &= bits - 1u;
+                        const uint32_t ma = masks_sh[ka], mb = masks_sh[kb];
+                        float acc_a = (ma & 1u) ? t_on[0] : t_off[0];
+                        float acc_b = (mb & 1u) ? t_on[0] : t_off[0];
+#pragma unroll
+                        for (int b = 1; b < NB; ++b) {
+                            acc_a = __fadd_rn(acc_a, ((ma >> b) & 1u) ? t_on[b] : t_off[b]);
+                            acc_b = __fadd_rn(acc_b, ((mb >> b) & 1u) ? t_on[b] : t_off[b]);
+                        }
+                        consider(ka, acc_a);
+                        consider(kb, acc_b);
                     }
                 }
                 if (best_k >= 0) {

@@ -377,12 +377,12 @@ features_kernel(const T* __restrict__ stack, size_t n_vox, int Y, int X, DecodeP
                     }
 #pragma unroll
                     for (int b = 0; b < NB; ++b) {
-                        x[b] = (b < P.n_bits) ? scale_clip(raw[b], P.bkg[b], P.nrm[b]) : 0.f;
+                        x[b] = (b < P.n_bits) ? scale_clip<sizeof(T) == 2>(raw[b], P.bkg[b], P.nrm[b], P.rcp[b]) : 0.f;
                         const float val = optimize_mode ? raw[b] : __half2float(round5_f16(x[b]));
                         tile[lane * FEAT_TILE_STRIDE + b] = (b < P.n_bits) ? val : 0.f;
                     }
                     const float nrm2 = l2_norm<NB>(x);
-                    const float mag = unit_vector<NB>(x, nrm2, xh);
+                    const float mag = unit_vector<NB>(x, nrm2, xh, sizeof(T) == 2 && P.rcp_all);
                     mag16 = __half2float(round5_f16(mag));
                     d16 = __half2float(round5_f16(direct_distance<NB>(xh, crow)));
                 }

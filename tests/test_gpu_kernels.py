@@ -119,6 +119,69 @@ def test_decode_degenerate_vectors_use_safe_division(torch):
         _same_f16(got[k], ref[k], k)
 
 
+@pytest.mark.parametrize("dense", [True, False])
+def test_decode_division_guards_f32(torch, dense):
+    """The scale and unit-vector divisions run as a multiply by a correctly rounded reciprocal plus one FMA correction
+    (voxel_math.cuh, div_by_rcp) when every operand is of ordinary size, and as the IEEE division otherwise.  A float32
+    stack with values on both sides of every guard -- exact background hits (zero numerators), differences around
+    2^-40, denormals, huge values, a norm with an all-ones significand, values that make the whole trace tiny -- must
+    still reproduce NumPy's correctly rounded divisions bit for bit."""
+    _df, cb = cases.codebook16()
+    rng = np.random.default_rng(77)
+    stack = cases.small_stack(cb["matrix"], shape=(6, 32, 48), seed=31).astype(np.float32)
+    stack += rng.normal(0, 0.21, stack.shape).astype(np.float32)
+    bkg, nrm = cases.simple_vectors(16, seed=8)
+    flat = stack.reshape(16, -1)
+    n = flat.shape[1]
+    for b in range(16):
+        idx = rng.choice(n, 400, replace=False)
+        flat[b, idx[:50]] = bkg[b]                                        # zero numerator
+        flat[b, idx[50:100]] = np.nextafter(bkg[b], np.float32(np.inf))   # one ulp above the background
+        flat[b, idx[100:150]] = bkg[b] + np.float32(2.0 ** -41)           # rounds to the background or just above it
+        flat[b, idx[150:200]] = np.float32(1e-42)                         # denormal sample
+        flat[b, idx[200:250]] = np.float32(3e38)                          # huge
+        flat[b, idx[250:300]] = bkg[b] + nrm[b] * np.float32(1e-13)       # quotient below 2^-40
+        flat[b, idx[300:350]] = bkg[b] + nrm[b]                           # quotient exactly 1
+        flat[b, idx[350:400]] = bkg[b] + nrm[b] * np.float32(0.99999994)  # quotient just below 1
+    # whole traces that are tiny (norm below 2^-40) or have a norm with an all-ones significand
+    tiny_vox = rng.choice(n, 64, replace=False)
+    flat[:, tiny_vox] = (bkg + nrm * np.float32(3e-14))[:, None]
+    ones_vox = rng.choice(n, 64, replace=False)
+    flat[:, ones_vox] = bkg[:, None]
+    flat[0, ones_vox] = bkg[0] + nrm[0] * np.float32(np.float32(0.99999994))  # single non-zero entry -> norm = that entry
+    with np.errstate(all="ignore"):
+        _c, _s, _d, got, ref = _decode_both(torch, cb, stack, bkg, nrm, mag=(0.05, 10.0), dense=dense)
+    np.testing.assert_array_equal(got["decoded"], ref["decoded"])
+    if dense:
+        for k in ("magnitude", "distance", "scaled"):
+            _same_f16(got[k], ref[k], k)
+
+
+def test_decode_division_guards_vectors(torch):
+    """Vectors on both sides of the host's reciprocal-division conditions (|nrm| in [2^-40, 2^40], significand not all
+    ones, |bkg| in {0} or [2^-20, 2^30]); uint16 input, every result image against the oracle."""
+    _df, cb = cases.codebook16()
+    stack = cases.small_stack(cb["matrix"], shape=(4, 32, 32), seed=19)
+    bkg, nrm = cases.simple_vectors(16, seed=5)
+    nrm[0] = np.float32(2.0 ** 41)
+    nrm[1] = np.float32(2.0 ** -41)
+    nrm[2] = np.float32(np.nextafter(np.float32(1024.0), np.float32(0)))  # all-ones significand
+    nrm[3] = np.float32(-700.0)
+    bkg[4] = np.float32(1e-9)
+    bkg[5] = np.float32(0.0)
+    bkg[6] = np.float32(3e9)
+    bkg[7] = np.float32(187.0)  # integer background: exact zero numerators
+    nrm[8] = np.float32(2.0 ** 40)
+    nrm[9] = np.float32(2.0 ** -40)
+    with np.errstate(all="ignore"):
+        for dense in (True, False):
+            _c, _s, _d, got, ref = _decode_both(torch, cb, stack, bkg, nrm, mag=(0.05, 10.0), dense=dense)
+            np.testing.assert_array_equal(got["decoded"], ref["decoded"])
+            if dense:
+                for k in ("magnitude", "distance", "scaled"):
+                    _same_f16(got[k], ref[k], k)
+
+
 def test_decode_all_foreground_worst_case(torch):
     """every voxel passes the magnitude gate: the search cannot hide behind sparsity."""
     _df, cb = cases.codebook16()
