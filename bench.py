@@ -801,14 +801,14 @@ def run_b200(args):
                 ds3.add_tile(host.numpy(), stage_origin_zyx_um=(0.0, 0.0, 250.0 * k))
             ds3.save_decode_normalization_vectors(None, "global", nrm, bkg)
             dec3 = PixelDecoder(ds3, merfish_bits=16, verbose=0)
-            dec3.decode_one_tile(0, gpu_id=local, lowpass_sigma=None, magnitude_threshold=MAG, minimum_pixels=MIN_PX,
-                                 normalization_method="global")  # warm-up (allocations)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            dec3.decode_all_tiles(assign_to_cells=False, lowpass_sigma=None, magnitude_threshold=MAG,
-                                  minimum_pixels=MIN_PX, normalization_method="global")
-            torch.cuda.synchronize()
-            all_s = time.perf_counter() - t0
+            all_s = None
+            for _rep in range(2):  # the first pass allocates both staging slots; the second is the steady state
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                dec3.decode_all_tiles(assign_to_cells=False, lowpass_sigma=None, magnitude_threshold=MAG,
+                                      minimum_pixels=MIN_PX, normalization_method="global")
+                torch.cuda.synchronize()
+                all_s = time.perf_counter() - t0
             extras["decode_all_tiles_3"] = {
                 "s_total": all_s, "ms_per_tile": all_s / 3 * 1e3, "gvoxel_per_s": 3 * n_vox / all_s / 1e9,
                 "filtered_transcripts": int(len(dec3._df_filtered_barcodes)),

@@ -1077,6 +1077,19 @@ class PixelDecoder:
                     kh = keep.cpu().numpy()
                     centroid_stats = tuple(a[kh] for a in centroid_stats)
                 table = table[keep]
+        if getattr(self, "_defer_annotation", False) and centroid_stats is None:
+            # inside the optimiser (3-D, nothing written to disk): the loop's statistic only reads the per-bit means and
+            # the codeword of every surviving row, and it reads them ON THE DEVICE (_pooled_iterative_vectors) -- the
+            # table is not copied to the host and no data frame is built (several 1e5 rows per tile in iteration 0)
+            import torch
+
+            nb = self._n_merfish_bits
+            self._opt_rows = (table[:, M3D_TABLE_FIXED_COLS : M3D_TABLE_FIXED_COLS + nb].to(torch.float32).contiguous(),
+                              table[:, _COL_DEC].to(torch.int64))
+            if hasattr(self, "_df_barcodes"):
+                del self._df_barcodes
+            return
+        self._opt_rows = None
         eigvals = ctx.inertia_eigvals(table).cpu().numpy() if table.shape[0] > 0 else None
         # column-major on the host: the annotation works column by column (transposed on the device, a view here)
         tab = table.t().contiguous().cpu().numpy().T
@@ -1770,7 +1783,35 @@ class PixelDecoder:
                 out[c] = pooled[:, nb + 5 + i].astype(np.int64) if c == "tile_idx" else pooled[:, nb + 5 + i]
         return out
 
-    def _pooled_iterative_vectors(self, local: pd.DataFrame):
+    def _device_row_queries(self, rows, device):
+        """The 2 x bits multisets of ``_norm.iterative_vector_queries`` built from the feature tables as they sit on the
+        device: ``rows`` = [(per-bit means float32 (n, bits), codeword index int64 (n,)), ...] of this rank's tiles.
+        Blank-ness and the four 'on' bits are properties of the codeword (PD:3101: ``argsort(~codebook)[:, :4]``)."""
+        import torch
+
+        nb = self._n_merfish_bits
+        rows = [r for r in rows if r is not None and r[0].shape[0] > 0]
+        if rows:
+            vals = torch.cat([r[0] for r in rows]).to(device)
+            dec = torch.cat([r[1] for r in rows]).to(device)
+        else:
+            vals = torch.zeros((0, nb), dtype=torch.float32, device=device)
+            dec = torch.zeros((0,), dtype=torch.int64, device=device)
+        n_rows = int(vals.shape[0])
+        blank = torch.tensor([str(g).lower().startswith("blank") for g in self._gene_ids], dtype=torch.bool, device=device)
+        on0 = np.argsort(~self._codebook_matrix.astype(bool, copy=False), axis=1)[:, :4]
+        on_mask = np.zeros((len(self._gene_ids), nb + 1), dtype=bool)
+        np.put_along_axis(on_mask, np.minimum(on0, nb), True, axis=1)  # an 'on' index beyond the bit columns counts nowhere
+        on_mask = torch.from_numpy(on_mask[:, :nb]).to(device)
+        keep = ~blank[dec]
+        vals, dec = vals[keep], dec[keep]
+        on = on_mask[dec]
+        finite = ~torch.isnan(vals)
+        queries = [vals[:, j][on[:, j] & finite[:, j]].contiguous() for j in range(nb)]
+        queries += [vals[:, j][~on[:, j] & finite[:, j]].contiguous() for j in range(nb)]
+        return queries, int(vals.shape[0]), n_rows
+
+    def _pooled_iterative_vectors(self, local: pd.DataFrame | None, device_rows=None):
         """The optimiser's statistic (PD:1290-1368) over EVERY rank's transcripts without gathering them: each rank
         keeps its rows; the 2 x bits medians (on-bit / off-bit mean intensities of non-blank transcripts) come from
         a radix select whose digit histograms are summed with ``all_reduce`` -- three collectives of a
@@ -1794,22 +1835,26 @@ class PixelDecoder:
                 ctx.select_hist(data, row, prefix_mask=pm, prefix_value=pv, shift=sh)
         else:
             device, hist_fn = torch.device("cpu"), backend
-        has_cols = len(local.columns) > 0 and "gene_id" in local.columns and any(
-            c.startswith("bit") and c.endswith("_mean_intensity") for c in local.columns)
         queries, kept, foreign = None, 0, 0
-        if has_cols:
-            queries, kept = _norm.iterative_vector_queries(local, nb, device)
-            foreign = int(queries is None)
-        if queries is None or len(queries) != 2 * nb:
-            foreign = max(foreign, int(queries is not None))  # a table with other bit columns: host path
-            queries = [torch.zeros(0, dtype=torch.float32, device=device) for _ in range(2 * nb)]
-        flags = torch.tensor([len(local), kept, foreign], dtype=torch.int64, device=device)
+        if device_rows is not None:  # the tables never left the device (3-D optimiser iterations)
+            queries, kept, n_local = self._device_row_queries(device_rows, device)
+        else:
+            n_local = len(local)
+            has_cols = len(local.columns) > 0 and "gene_id" in local.columns and any(
+                c.startswith("bit") and c.endswith("_mean_intensity") for c in local.columns)
+            if has_cols:
+                queries, kept = _norm.iterative_vector_queries(local, nb, device)
+                foreign = int(queries is None)
+            if queries is None or len(queries) != 2 * nb:
+                foreign = max(foreign, int(queries is not None))  # a table with other bit columns: host path
+                queries = [torch.zeros(0, dtype=torch.float32, device=device) for _ in range(2 * nb)]
+        flags = torch.tensor([n_local, kept, foreign], dtype=torch.int64, device=device)
         if multi:
             dist.all_reduce(flags)
         n_pooled, n_kept, any_foreign = (int(v) for v in flags.cpu())
         if any_foreign:
             # values that are not float32 numbers (tables this build did not write): gather and take the host median
-            pooled = self._gather_tables(local)
+            pooled = self._gather_tables(local if local is not None else pd.DataFrame())
             if len(pooled) == 0 and "gene_id" not in pooled.columns:
                 return None, n_pooled
             return _norm.iterative_normalization_vectors(pooled, nb), n_pooled
@@ -1916,15 +1961,29 @@ class PixelDecoder:
                 self._profile = {"sync": bool(prof_was and prof_was.get("sync"))} if prof_was is not None else None
                 hits0 = self._tile_cache_stats["hits"]
 
-                def per_tile(dec, tile_idx, gpu, _use=use_norm):
-                    dec.decode_one_tile(
-                        tile_idx=tile_idx, gpu_id=gpu, lowpass_sigma=lowpass_sigma,
-                        magnitude_threshold=magnitude_threshold, minimum_pixels=minimum_pixels,
-                        feature_predictor_threshold=feature_predictor_threshold,
-                        normalization_method="iterative" if _use else "global",
-                    )
-                    dec._save_barcodes()
-                    tables.append((tile_idx, dec._df_barcodes))
+                # 3-D runs that write no per-iteration files keep the feature tables on the device (see _extract_barcodes)
+                defer = bool(self._is_3D and self._decode_run_key is None and not getattr(self, "_keep_temp_tables", False)
+                             and not self._wants_chromatic_centroids()
+                             and getattr(self, "_order_stats_backend", None) is None)
+                dev_rows: list = []
+
+                def per_tile(dec, tile_idx, gpu, _use=use_norm, _defer=defer):
+                    dec._defer_annotation = _defer
+                    try:
+                        dec.decode_one_tile(
+                            tile_idx=tile_idx, gpu_id=gpu, lowpass_sigma=lowpass_sigma,
+                            magnitude_threshold=magnitude_threshold, minimum_pixels=minimum_pixels,
+                            feature_predictor_threshold=feature_predictor_threshold,
+                            normalization_method="iterative" if _use else "global",
+                        )
+                    finally:
+                        dec._defer_annotation = False
+                    if _defer and getattr(dec, "_opt_rows", None) is not None:
+                        dev_rows.append((tile_idx, dec._opt_rows))
+                        tables.append((tile_idx, None))
+                    else:
+                        dec._save_barcodes()
+                        tables.append((tile_idx, dec._df_barcodes))
 
                 mine = self._run_tiles(random_tiles, per_tile)
                 if mine is not None and self._tile_cache is not None and mine and all(
@@ -1935,7 +1994,9 @@ class PixelDecoder:
                 # within-tile de-duplication breaks ties by row)
                 pos = {t: i for i, t in enumerate(random_tiles)}
                 tables.sort(key=lambda t: pos.get(t[0], len(pos)))
-                local = pd.concat([t[1] for t in tables], ignore_index=True) if tables else pd.DataFrame()
+                dev_rows.sort(key=lambda t: pos.get(t[0], len(pos)))
+                frames = [t[1] for t in tables if t[1] is not None]
+                local = pd.concat(frames, ignore_index=True) if frames else pd.DataFrame()
                 # every rank keeps ITS rows (the reference pools all tiles in the parent process, PD:4731-4733): the
                 # 2-D within-tile collapse only ever joins rows of one tile, and the medians are pooled by
                 # all-reduced histograms (_pooled_iterative_vectors) -- no table travels between ranks
@@ -1950,7 +2011,10 @@ class PixelDecoder:
                         radius_z=self._datastore.voxel_size_zyx_um[0],
                     )
                 t_local = _time.perf_counter()
-                vectors, n_pooled = self._pooled_iterative_vectors(self._df_barcodes_loaded)
+                use_dev = defer and len(frames) == 0  # local multi-GPU threads or mixed paths: data frames
+                vectors, n_pooled = self._pooled_iterative_vectors(
+                    None if use_dev else self._df_barcodes_loaded,
+                    device_rows=[r[1] for r in dev_rows] if use_dev else None)
                 t_gather = _time.perf_counter()
                 pooled = range(n_pooled)  # only its length is reported below
                 self._load_global_normalization_vectors(gpu_id=self._local_gpu(), lowpass_sigma=lowpass_sigma)

@@ -114,6 +114,7 @@ def test_optimizer_tile_cache_does_not_change_the_result(tmp_path, budget, lowpa
         ds2.add_tile(st)
     dec2 = PixelDecoder(ds2, merfish_bits=16, verbose=0)
     dec2.tile_cache_budget_bytes = 0
+    dec2._keep_temp_tables = True  # data frames per tile (the default 3-D path keeps the tables on the device)
     kept2 = {}
     orig2 = dec2._save_barcodes
 
@@ -133,6 +134,20 @@ def test_optimizer_tile_cache_does_not_change_the_result(tmp_path, budget, lowpa
     for t in kept:
         pd.testing.assert_frame_equal(kept[t], kept2[t])
     assert dec._tile_cache is None and not dec._buffers  # everything released at the end
+    # the default path: feature tables stay on the device, the medians are taken from them there
+    ds3 = ArrayDataStore(tmp_path / "device" / "qi2labdatastore", codebook=df_cb)
+    for st in g["stacks"]:
+        ds3.add_tile(st)
+    dec3 = PixelDecoder(ds3, merfish_bits=16, verbose=0)
+    if budget is not None:
+        dec3.tile_cache_budget_bytes = dec.tile_cache_budget_bytes
+    dec3.optimize_normalization_by_decoding(n_iterations=3, minimum_pixels=4, lowpass_sigma=lowpass,
+                                            magnitude_threshold=(0.9, 10.0), tile_indices=[0, 1, 2])
+    d_n, d_b = ds3.load_decode_normalization_vectors(None, "iterative")
+    np.testing.assert_array_equal(d_n, i_n)
+    np.testing.assert_array_equal(d_b, i_b)
+    assert [it["transcripts_pooled"] for it in dec3._optimizer_timing["iterations"]] == \
+        [it["transcripts_pooled"] for it in dec._optimizer_timing["iterations"]]
 
 
 def test_cuda_path_on_the_simulation_cli_sequence(tmp_path):

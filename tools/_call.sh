@@ -1,8 +1,8 @@
 set -x
-python -m pytest tests/test_gpu_kernels.py tests/test_gpu_reference_golden.py -x -q 2>&1 | tail -3
-python tools/dense_regime.py > gpurun_out/dense_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:decode_search -s 1 -c 1 -o gpurun_out/r2_dense_search_v4 python tools/dense_regime.py > gpurun_out/dense_ncu.log 2>&1
-tail -2 gpurun_out/dense_plain.log
-python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e --extras all_foreground 2>&1 | tail -1 | python -c "
+python -m pytest tests/test_gpu_reference_golden.py tests/test_gpu_pixeldecoder.py tests/test_gpu_zarr_store.py -x -q -k "optimizer or simulation or unregistered or without_any or multi_gpu" 2>&1 | tail -4
+python bench.py --steps 10 --warmup 3 --no-cpu --extras optimizer,e2e_variants 2>&1 | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('value', d['value'], 'ms', d['ms_per_step']); print(d['extras']['all_foreground'])"
+print('value', d['value'], 'e2e', d['e2e']['value']); o=d['extras']['optimizer']
+print({k:o[k] for k in ('total_s','seed_s','steady_s_per_iteration','steady_gvoxel_per_s','iteration0_gvoxel_per_s')}); print(o['iteration0']); print(o['steady_iterations']); print(o['iterative_normalization_head'])
+print(d['extras']['decode_all_tiles_3'])"
