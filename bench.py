@@ -311,6 +311,9 @@ def _zarr_store_extra(sub, df_cb, nrm, bkg, tmp_dir, local, compression="blosc-z
                 "bitshuffle, (16,512,512) chunks, page-cache warm) through m3d_zarr_read_chunks; " + (
                     "the chunk files cross PCIe compressed and the GPU decodes the LZ4 streams (one warp each), "
                     "un-shuffles and places them" if compression == "blosc-lz4" else
+                    "the chunk files cross PCIe compressed and the GPU decodes the zstd frames (a warp per Blosc block: one "
+                    "lane per Huffman stream, shared copies), un-shuffles and places them"
+                    if os.environ.get("M3D_ZARR_GPU_ZSTD", "2") != "0" else
                     "host threads zstd-decode into pinned slots, the GPU un-shuffles and places the chunks"),
     }
     shutil.rmtree(root.parent, ignore_errors=True)
@@ -850,11 +853,21 @@ def run_b200(args):
         # blosc-zstd bit-shuffled (16, 512, 512) chunks.  32 planes keep the store small; the
         # figure of merit is decoded GB/s.  Guarded: a full disk must not cost the bench line.
         if world == 1 and wanted("zarr"):
-            for key, comp in (("e2e_from_zarr_store", "blosc-zstd"), ("e2e_from_zarr_store_lz4", "blosc-lz4")):
+            for key, comp, env in (("e2e_from_zarr_store", "blosc-zstd", None),
+                                   ("e2e_from_zarr_store_host_zstd", "blosc-zstd", "0"),
+                                   ("e2e_from_zarr_store_lz4", "blosc-lz4", None)):
+                saved_env = os.environ.get("M3D_ZARR_GPU_ZSTD")
                 try:
+                    if env is not None:
+                        os.environ["M3D_ZARR_GPU_ZSTD"] = env
                     extras[key] = _zarr_store_extra(host.numpy()[:, :32], df_cb, nrm, bkg, tmp.name, local, comp)
                 except Exception as e:  # noqa: BLE001
                     extras[key] = {"error": f"{type(e).__name__}: {e}"}
+                finally:
+                    if saved_env is None:
+                        os.environ.pop("M3D_ZARR_GPU_ZSTD", None)
+                    else:
+                        os.environ["M3D_ZARR_GPU_ZSTD"] = saved_env
             # the same 32 planes from pinned host memory, for scale
             try:
                 ds3 = ArrayDataStore(Path(tmp.name) / "qi2labdatastore_32", codebook=df_cb)

@@ -40,8 +40,7 @@ struct FseTable {
 };
 
 struct Work {
-    uint8_t huf_sym[1 << HUF_MAX_BITS];
-    uint8_t huf_nb[1 << HUF_MAX_BITS];
+    uint16_t huf_tab[1 << HUF_MAX_BITS];  // symbol | bits consumed << 8, indexed by the next huf_bits bits
     int huf_bits;
     int huf_valid;
     FseTable ll, of, ml, wt;
@@ -220,8 +219,7 @@ M3D_HD inline bool huf_build(Work& w, int n) {
         const uint32_t len = 1u << (wt - 1);
         const uint32_t at = w.rank_pos[wt];
         for (uint32_t k = 0; k < len; ++k) {
-            w.huf_sym[at + k] = (uint8_t)i;
-            w.huf_nb[at + k] = (uint8_t)(max_bits + 1 - wt);
+            w.huf_tab[at + k] = (uint16_t)((uint32_t)i | ((uint32_t)(max_bits + 1 - wt) << 8));
         }
         w.rank_pos[wt] = (uint16_t)(at + len);
     }
@@ -278,19 +276,149 @@ M3D_HD inline int64_t huf_read_tree(Work& w, const uint8_t* p, int64_t n) {
     return used;
 }
 
+// Window over a backward bitstream made of 32-bit words: word i covers stream bytes [4 i - off, 4 i - off + 4), bytes
+// outside [0, n) read as zero.  On the device `off` aligns the words with the buffer (one aligned 32-bit load per 32
+// consumed bits instead of eight byte loads per field); the host assembles the same words from bytes, so the logic the
+// CPU tests pin is the logic the GPU runs.  The caller guarantees that the 8 bytes after the stream may be READ (they
+// belong to the same frame / staging slot); their bits are never used.
+struct BackWin {
+    const uint8_t* p;
+    int32_t n;
+    int32_t off;   // 0..3: p - (p rounded down to 4 bytes); 0 on the host
+    int32_t idx;   // lo = word(idx), hi = word(idx + 1)
+    uint32_t lo, hi;
+};
+
+M3D_HD inline uint32_t backwin_word(const BackWin& b, int32_t i) {
+    if (i < 0) return 0u;
+#ifdef __CUDA_ARCH__
+    uint32_t v = reinterpret_cast<const uint32_t*>(b.p - b.off)[i];
+    if (i == 0) v &= 0xFFFFFFFFu << (8 * b.off);  // bytes before the stream
+    return v;
+#else
+    uint32_t v = 0;
+    for (int k = 0; k < 4; ++k) {
+        const int64_t at = (int64_t)4 * i - b.off + k;
+        if (at >= 0 && at < b.n) v |= (uint32_t)b.p[at] << (8 * k);
+    }
+    return v;
+#endif
+}
+
+// the k (<= 25) bits [pos, pos + k) of the stream, pos possibly negative (bits below 0 read as zero)
+M3D_HD inline uint32_t backwin_peek(BackWin& b, int32_t pos, int k) {
+    const int32_t q = pos + 8 * b.off;
+    const int32_t wi = q >> 5;  // floor
+    if (wi != b.idx) {
+        if (wi == b.idx - 1) {
+            b.hi = b.lo;
+            b.lo = backwin_word(b, wi);
+        } else {
+            b.lo = backwin_word(b, wi);
+            b.hi = backwin_word(b, wi + 1);
+        }
+        b.idx = wi;
+    }
+    const int sh = q & 31;
+#ifdef __CUDA_ARCH__
+    const uint32_t v = __funnelshift_r(b.lo, b.hi, sh);
+#else
+    const uint32_t v = (uint32_t)((((uint64_t)b.hi << 32) | b.lo) >> sh);
+#endif
+    return v & ((1u << k) - 1u);
+}
+
+// One Huffman stream (RFC 8878 4.2.2): the state is the next `huf_bits` bits; each symbol consumes huf_nb[state] of them.
+// Same results as the field-by-field reader it replaces (pinned against libzstd by the CPU tests), with one aligned word
+// load per 32 bits and four symbols per 32-bit store where the destination allows.
 M3D_HD inline bool huf_decode_stream(const Work& w, const uint8_t* p, int64_t n, uint8_t* out, int64_t n_out) {
-    BackBits b = back_open(p, n);
-    if (!b.ok) return false;
+    if (n < 1 || n > (1 << 26) || p[n - 1] == 0) return false;
     const int mb = w.huf_bits;
     const uint32_t mask = (1u << mb) - 1;
-    uint32_t state = (uint32_t)back_read(b, mb);
-    for (int64_t i = 0; i < n_out; ++i) {
-        if (b.pos <= -mb) return false;  // ran dry before the last symbol
-        const int nb = w.huf_nb[state];
-        out[i] = w.huf_sym[state];
-        state = ((state << nb) & mask) | (uint32_t)back_read(b, nb);
+    BackWin b;
+    b.p = p;
+    b.n = (int32_t)n;
+#ifdef __CUDA_ARCH__
+    b.off = (int32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+#else
+    b.off = 0;
+#endif
+    b.idx = INT32_MIN / 2;
+    b.lo = b.hi = 0;
+    int32_t pos = (int32_t)(n - 1) * 8 + highbit32(p[n - 1]);  // bits still unread (may go negative)
+    pos -= mb;
+    uint32_t state = (pos >= 0) ? backwin_peek(b, pos, mb)
+                                : (pos + mb > 0 ? (backwin_peek(b, 0, pos + mb) << (-pos)) : 0u);
+    int64_t i = 0;
+    // ---- main loop: four symbols per round while at least 4 x 11 payload bits remain.  Nothing in the body depends on
+    // the data except through predicated moves, so the lanes of a warp that decode different streams stay in lockstep
+    // (an earlier version with early exits and a refill branch ran the four streams of a block one after the other).
+    // While pos >= 0 every field lies inside the stream: no zero-fill, no dry-run check.
+    while (i < n_out && (reinterpret_cast<uintptr_t>(out + i) & 3u) && pos >= HUF_MAX_BITS) {
+        const uint32_t e = w.huf_tab[state];
+        const int nb = (int)(e >> 8);
+        out[i++] = (uint8_t)e;
+        pos -= nb;
+        state = ((state << nb) & mask) | (nb ? backwin_peek(b, pos, nb) : 0u);
     }
-    return b.pos == -mb;  // every payload bit used, nothing more
+    {
+        const int32_t base = 8 * b.off;
+        int32_t q0 = pos + base;
+        int32_t idx = q0 >> 5;
+        uint32_t lo = backwin_word(b, idx), hi = backwin_word(b, idx + 1);
+        while (i + 4 <= n_out && pos >= 4 * HUF_MAX_BITS) {
+            uint32_t packed = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t e = w.huf_tab[state];
+                const int nb = (int)(e >> 8);
+                packed |= (e & 0xFFu) << (8 * u);
+                pos -= nb;
+                const int32_t q = pos + base;
+                const int32_t wi = q >> 5;
+                if (wi != idx) {  // at most one word further down (nb <= 11): predicated, not a branch
+                    hi = lo;
+#ifdef __CUDA_ARCH__
+                    lo = reinterpret_cast<const uint32_t*>(b.p - b.off)[wi];
+#else
+                    lo = backwin_word(b, wi);
+#endif
+                    idx = wi;
+                }
+#ifdef __CUDA_ARCH__
+                const uint32_t v = __funnelshift_r(lo, hi, q & 31);
+#else
+                const uint32_t v = (uint32_t)((((uint64_t)hi << 32) | lo) >> (q & 31));
+#endif
+                state = ((state << nb) & mask) | (v & ((1u << nb) - 1u));
+            }
+#ifdef __CUDA_ARCH__
+            *reinterpret_cast<uint32_t*>(out + i) = packed;
+#else
+            memcpy(out + i, &packed, 4);
+#endif
+            i += 4;
+        }
+        b.idx = INT32_MIN / 2;  // the tail reloads its window
+    }
+    // ---- tail (the last few symbols, and streams shorter than the main loop's margin): checked field by field; fields
+    // that reach below bit 0 read zeros in the missing low positions
+    int bad = 0;
+    for (; i < n_out; ++i) {
+        bad |= (pos <= -mb);  // ran dry before the last symbol
+        const uint32_t e = w.huf_tab[state];
+        const int nb = (int)(e >> 8);
+        out[i] = (uint8_t)e;
+        uint32_t fresh = 0;
+        if (nb) {
+            pos -= nb;
+            if (pos >= 0) fresh = backwin_peek(b, pos, nb);
+            else if (pos + nb > 0) fresh = backwin_peek(b, 0, pos + nb) << (-pos);
+        }
+        state = ((state << nb) & mask) | fresh;
+    }
+    if (bad) return false;
+    return pos == -mb;  // every payload bit used, nothing more
 }
 
 // ---------------------------------------------------------------------------------------------- literals

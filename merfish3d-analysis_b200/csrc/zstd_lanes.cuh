@@ -6,10 +6,10 @@
 // sequence chain redundantly -- it is uniform, all lanes read the same bytes -- and the literal and match copies are
 // shared by the team exactly as the LZ4 decoder shares them.
 //
-// STATUS: pinned on the HOST through the one-lane policy (`m3d_zstd_decode_builtin_lanes`,
-// tests/test_cpu_zarr_store.py: same frames as the serial decoder).  The warp policy and
-// `blosc_zstd_decode_kernel_v2` (M3D_ZARR_GPU_ZSTD=2) were written after the round's GPU budget was spent and have
-// NOT run on a device yet; nothing selects them by default.
+// STATUS: the logic is pinned on the HOST through the one-lane policy (`m3d_zstd_decode_builtin_lanes`,
+// tests/test_cpu_zarr_store.py: same frames as the serial decoder); the warp policy / `blosc_zstd_decode_kernel_v2`
+// (M3D_ZARR_GPU_ZSTD=2) is bit-exact on the B200 against the host decode (tests/test_gpu_zarr_store.py, both modes, plus a
+// damaged frame).  Measurements: profiles/r2_zstd_device.txt.
 #pragma once
 #include "zstd_decode.cuh"
 
@@ -41,18 +41,74 @@ struct Warp32 {
         return (int64_t)(((uint64_t)hi << 32) | lo);
     }
     static __device__ inline void copy(uint8_t* d, const uint8_t* s, int64_t n) {
-        for (int64_t i = threadIdx.x & 31; i < n; i += 32) d[i] = s[i];
+        const int lane = threadIdx.x & 31;
+        if ((((uintptr_t)d ^ (uintptr_t)s) & 3u) == 0 && n >= 64) {  // same alignment: 32-bit words
+            int64_t head = (4 - (int64_t)((uintptr_t)d & 3u)) & 3;
+            if (lane < head) d[lane] = s[lane];
+            const int64_t nw = (n - head) >> 2;
+            const uint32_t* sw = reinterpret_cast<const uint32_t*>(s + head);
+            uint32_t* dw = reinterpret_cast<uint32_t*>(d + head);
+            int64_t i = lane;
+            for (; i + 96 < nw; i += 128) {  // four independent loads in flight per lane
+                const uint32_t a = sw[i], b = sw[i + 32], c = sw[i + 64], e = sw[i + 96];
+                dw[i] = a;
+                dw[i + 32] = b;
+                dw[i + 64] = c;
+                dw[i + 96] = e;
+            }
+            for (; i < nw; i += 32) dw[i] = sw[i];
+            const int64_t done = head + (nw << 2);
+            if (lane < n - done) d[done + lane] = s[done + lane];
+            return;
+        }
+        int64_t i = lane;
+        for (; i + 96 < n; i += 128) {
+            const uint8_t a = s[i], b = s[i + 32], c = s[i + 64], e = s[i + 96];
+            d[i] = a;
+            d[i + 32] = b;
+            d[i + 64] = c;
+            d[i + 96] = e;
+        }
+        for (; i < n; i += 32) d[i] = s[i];
     }
     static __device__ inline void fill(uint8_t* d, int v, int64_t n) {
-        for (int64_t i = threadIdx.x & 31; i < n; i += 32) d[i] = (uint8_t)v;
+        const int lane = threadIdx.x & 31;
+        if (n >= 64) {
+            int64_t head = (4 - (int64_t)((uintptr_t)d & 3u)) & 3;
+            if (lane < head) d[lane] = (uint8_t)v;
+            const int64_t nw = (n - head) >> 2;
+            uint32_t* dw = reinterpret_cast<uint32_t*>(d + head);
+            const uint32_t vv = (uint32_t)(uint8_t)v * 0x01010101u;
+            for (int64_t i = lane; i < nw; i += 32) dw[i] = vv;
+            const int64_t done = head + (nw << 2);
+            if (lane < n - done) d[done + lane] = (uint8_t)v;
+            return;
+        }
+        for (int64_t i = lane; i < n; i += 32) d[i] = (uint8_t)v;
     }
     static __device__ inline void match(uint8_t* d, int64_t off, int64_t n) {
         const uint8_t* src = d - off;
+        const int lane = threadIdx.x & 31;
         if (off >= n) {
-            for (int64_t i = threadIdx.x & 31; i < n; i += 32) d[i] = src[i];
-        } else {  // overlapping: byte i is byte (i mod offset) of the bytes before the match
-            const uint64_t o = (uint64_t)off;
-            for (int64_t i = threadIdx.x & 31; i < n; i += 32) d[i] = src[(uint64_t)i % o];
+            copy(d, src, n);
+        } else if (off == 1) {  // a run of one byte (all-zero bit rows of the shuffled high bytes)
+            fill(d, src[0], n);
+        } else if (off >= 32) {
+            // overlapping, long period: waves of `off` bytes; a wave only reads what earlier waves (or the bytes
+            // before the match) wrote
+            for (int64_t base = 0; base < n; base += off) {
+                const int64_t len = off < n - base ? off : n - base;
+                for (int64_t i = lane; i < len; i += 32) d[base + i] = d[base + i - off];
+                __syncwarp();
+            }
+        } else {  // short period: byte i is byte (i mod offset) of the bytes before the match
+            const uint32_t o = (uint32_t)off, step = 32u % o;
+            uint32_t phase = (uint32_t)lane % o;
+            for (int64_t i = lane; i < n; i += 32) {
+                d[i] = src[phase];
+                phase += step;
+                if (phase >= o) phase -= o;
+            }
         }
     }
 };

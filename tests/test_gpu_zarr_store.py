@@ -31,10 +31,17 @@ def ctx():
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("zstd_on", ["device", "host"])
 @pytest.mark.parametrize("shape,dtype,chunks,compression,shards", CASES)
-def test_device_reader_matches_oracle_written_images(tmp_path, ctx, shape, dtype, chunks, compression, shards):
+def test_device_reader_matches_oracle_written_images(tmp_path, ctx, shape, dtype, chunks, compression, shards, zstd_on,
+                                                     monkeypatch):
     import torch
     from merfish3d_analysis_b200 import zarr_store as zs
+
+    if zstd_on == "host":
+        if compression != "blosc-zstd":
+            pytest.skip("only Blosc-zstd frames have two decoders")
+        monkeypatch.setenv("M3D_ZARR_GPU_ZSTD", "0")  # entropy stage on host threads (libzstd)
 
     rng = np.random.default_rng(shape[-1])
     a = _image(rng, shape, dtype)
@@ -241,8 +248,8 @@ def test_optimizer_and_all_tiles_from_a_reference_layout_store(tmp_path):
 
 
 @pytest.mark.parametrize("mode", ["1", "2"])
-def test_device_zstd_decoder_opt_in(tmp_path, ctx, monkeypatch, capsys, mode):
-    """M3D_ZARR_GPU_ZSTD=1|2: Blosc-zstd frames cross PCIe compressed and the library's own zstd decoder
+def test_device_zstd_decoder_modes(tmp_path, ctx, monkeypatch, capsys, mode):
+    """M3D_ZARR_GPU_ZSTD=1|2 (2 is the default): Blosc-zstd frames cross PCIe compressed and the library's own zstd decoder
     (csrc/zstd_decode.cuh, pinned to libzstd on the CPU) runs on the device -- mode 1 lane-serial
     (`blosc_zstd_decode_kernel`), mode 2 a warp as a team (`blosc_zstd_decode_kernel_v2`, csrc/zstd_lanes.cuh).
     Both must reproduce the host decode bit for bit and report a damaged frame."""

@@ -1,8 +1,4 @@
 set -x
-python -m pytest tests/test_gpu_reference_golden.py tests/test_gpu_pixeldecoder.py tests/test_gpu_zarr_store.py -x -q -k "optimizer or simulation or unregistered or without_any or multi_gpu" 2>&1 | tail -4
-python bench.py --steps 10 --warmup 3 --no-cpu --extras optimizer,e2e_variants 2>&1 | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('value', d['value'], 'e2e', d['e2e']['value']); o=d['extras']['optimizer']
-print({k:o[k] for k in ('total_s','seed_s','steady_s_per_iteration','steady_gvoxel_per_s','iteration0_gvoxel_per_s')}); print(o['iteration0']); print(o['steady_iterations']); print(o['iterative_normalization_head'])
-print(d['extras']['decode_all_tiles_3'])"
+python -m pytest tests/test_gpu_zarr_store.py -x -q -k "zstd or truncated" 2>&1 | tail -12
+for m in 1 2; do timeout 300 python tools/zstd_device_probe.py $m 2>&1 | tail -1; done
+for m in 2; do M3D_ZARR_GPU_ZSTD=$m timeout 600 python tools/zarr_io_bench.py --z 32 --skip-host --only-transfer 2>&1 | tail -1 | cut -c1-700; done
