@@ -687,6 +687,25 @@ def run_b200(args):
             "note": "m3d_lowpass sigma=(3,1,1) (SciPy-exact fp64 accumulation) + decode_label + features on float32",
             "kernel_ms_per_step": {k: v / 2 for k, v in sorted(kt.items(), key=lambda kv: -kv[1])[:6]},
         }
+        # the opt-in float32 accumulation (CuPy-style arithmetic, not pinned): HBM-bound instead of float64-pipe-bound
+        ctx.set_lowpass_accumulate("float32")
+        for i in range(3):
+            if i == 1:
+                torch.cuda.synchronize()
+                ctx.reset_counters()
+                t0 = time.perf_counter()
+            lp = ctx.lowpass(stack, (3.0, 1.0, 1.0), False, out=lp)
+        torch.cuda.synchronize()
+        lp32_ms = (time.perf_counter() - t0) * 1e3 / 2
+        kt = ctx.kernel_times_ms()
+        ctx.set_lowpass_accumulate("float64")
+        extras["lowpass_float32_mode"] = {
+            "ms_per_tile": lp32_ms, "gb_s_materialised": (2 + 4 + 4 + 4) * N_BITS * n_vox / lp32_ms / 1e6,
+            "kernel_ms_per_tile": {k: v / 2 for k, v in sorted(kt.items(), key=lambda kv: -kv[1])[:2]},
+            "note": "m3d_lowpass alone with m3d_set_lowpass_mode(ctx, 1): float32 weights + FMA accumulation (what cupyx's "
+                    "filter is believed to do; opt-in, results differ from the SciPy-exact default by a few float32 ulps); "
+                    "traffic = uint16 read + float32 temporary write/read + float32 write per voxel-bit",
+        }
         del lp
         torch.cuda.empty_cache()
         # worst case: thresholds that let every voxel through the magnitude gate

@@ -173,6 +173,12 @@ int m3d_lowpass(m3d_ctx* ctx, const void* in_dev, int in_dtype, const float* pre
                 int n_vols, const int64_t dims[3], const double sigma[3], int mode2d,
                 float* out_dev, void* stream);
 
+/* Arithmetic of m3d_lowpass.  0 (default): float64 accumulation with SciPy's symmetric formula -- what the NumPy/SciPy
+ * stand-in behind the reference-generated goldens computes.  1: float32 weights and float32 FMA accumulation, taps in
+ * ascending order -- what cupyx.scipy.ndimage.gaussian_filter (the call at PD:1972-1979) is believed to do for float32
+ * images; NOT pinned (CuPy is not available to the build), opt-in, HBM-bound instead of float64-pipe-bound. */
+int m3d_set_lowpass_mode(m3d_ctx* ctx, int mode);
+
 /* _decode_pixels (PD:2523-2643) fused: scale -> clip -> L2 norm -> nearest codeword ->
  * pixel gate -> magnitude gates -> exclusion.  decoded_dev int16 (z,y,x) is always
  * written.  magnitude/distance (float16 (z,y,x)) and scaled (float16 (bits,z,y,x)) are

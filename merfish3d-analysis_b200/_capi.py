@@ -34,6 +34,7 @@ SIGNATURES = {
     "m3d_destroy": (C.c_int, [C.c_void_p]),
     "m3d_set_normalization": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "m3d_set_thresholds": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float]),
+    "m3d_set_lowpass_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "m3d_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "m3d_upload_batch": (
         C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p]
@@ -370,6 +371,11 @@ class DecodeContext:
         )
         self._h = handle
         self._n_features = -1
+        import os
+
+        accum = os.environ.get("M3D_LOWPASS_ACCUM")
+        if accum:  # "float32": the opt-in CuPy-style low-pass arithmetic (see set_lowpass_accumulate)
+            self.set_lowpass_accumulate(accum)
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -529,6 +535,13 @@ class DecodeContext:
             "m3d_warp_flow",
         )
         return out
+
+    def set_lowpass_accumulate(self, kind: str) -> None:
+        """``"float64"`` (default: SciPy's arithmetic, pinned by the reference-generated goldens) or ``"float32"``
+        (float32 weights + FMA accumulation as CuPy's filter is believed to compute; opt-in, not pinned)."""
+        if kind not in ("float64", "float32"):
+            raise ValueError("lowpass accumulation must be 'float64' or 'float32'")
+        _check(self._lib.m3d_set_lowpass_mode(self._h, 1 if kind == "float32" else 0), "m3d_set_lowpass_mode")
 
     def lowpass(self, stack, sigma, mode2d: bool, predictor=None, out=None):
         """stack: (n_vols, z, y, x) uint16/float32 device tensor -> float32 low-passed."""

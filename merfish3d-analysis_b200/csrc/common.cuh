@@ -179,6 +179,7 @@ struct m3d_ctx {
     size_t prev_n_vox = 0;
     int prev_fg_valid = 0;
     int gate_skip_background = 0;  // set around the gate launch only
+    int lowpass_f32 = 0;           // m3d_set_lowpass_mode: 1 = float32 FMA accumulation (opt-in, lowpass.cu)
     // accounting
     int64_t launches[KF_COUNT];
     // optional per-kernel-family device timing (m3d_set_timing): event pairs recorded on the

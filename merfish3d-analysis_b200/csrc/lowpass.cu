@@ -16,7 +16,16 @@
 //                             intermediate in shared memory -> x pass -> float32 store.
 //   lowpass_axis_generic_kernel: any radius <= 64 / any shape, one thread per output; used
 //                             when no templated radius matches.
+//
+// Opt-in second arithmetic (m3d_set_lowpass_mode(ctx, 1), M3D_LOWPASS_ACCUM=float32): weights cast to float32 and every
+// 1-D pass accumulated in float32 with one FMA per tap, taps in ascending order -- what cupyx.scipy.ndimage's correlate
+// kernel does for float32 images as far as its source is remembered (weights dtype = promote(input, float32), `sum +=
+// value * w` under NVRTC's default FMA contraction; the reference calls it at PD:1972-1979).  CuPy is not installed
+// here and has no vendored source, so this mode is NOT pinned to the reference; the default stays SciPy's float64
+// arithmetic, which the reference-generated goldens pin.  Same kernels, `F32` template flag.
 #include <math.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -28,6 +37,15 @@ struct Weights {
     int r;
     double w[LP_MAX_RADIUS + 1];  // w[i] = weight at offset -(r - i) ... i.e. w[0]=edge, w[r]=centre
 };
+struct Weights32 {  // the float32 mode's full kernel: w[i] = float32(weight at offset i - r), i = 0 .. 2 r
+    float w[2 * LP_MAX_RADIUS + 1];
+};
+static Weights32 make_weights32(const Weights& W) {
+    Weights32 F;
+    memset(&F, 0, sizeof(F));
+    for (int i = 0; i <= 2 * W.r && W.r >= 0; ++i) F.w[i] = (float)W.w[i <= W.r ? i : 2 * W.r - i];
+    return F;
+}
 
 // SciPy _gaussian_kernel1d (order 0), float64; symmetric so only the first r+1 entries are kept.
 static Weights make_weights(double sigma) {
@@ -96,21 +114,22 @@ __device__ __forceinline__ double load_weighted(const T* in, const float* pred, 
 // (loop unrolled by the ring length so every index is static); the sample entering the ring is
 // fetched PF planes ahead, so the float64 pipe never waits on the load of the plane it is about
 // to consume.
-template <typename T, int R, bool PRED>
+template <typename T, int R, bool PRED, bool F32>
 __global__ void __launch_bounds__(128)
 lowpass_z_kernel(const T* __restrict__ in, const float* __restrict__ pred, float* __restrict__ out,
-                 int Z, size_t plane, Weights W) {
+                 int Z, size_t plane, Weights W, Weights32 W32) {
     constexpr int RING = 2 * R + 1;
     constexpr int PF = (RING % 5 == 0) ? 5 : ((RING % 3 == 0) ? 3 : 1);  // divides the unroll length
     const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= plane) return;
-    double ring[RING];
+    using A = typename std::conditional<F32, float, double>::type;
+    A ring[RING];
     T pre[PF];         // prefetched samples stay in their storage type: converting them on arrival
     float pre_w[PF];   // would make the warp wait on the very load the prefetch is meant to hide
     // slot of ext[j] is (j + R) mod RING
 #pragma unroll
     for (int i = 0; i < 2 * R; ++i)
-        ring[i] = load_weighted<T, PRED>(in, pred, (size_t)reflect_index(i - R, Z) * plane + c);
+        ring[i] = (A)load_weighted<T, PRED>(in, pred, (size_t)reflect_index(i - R, Z) * plane + c);
 #pragma unroll
     for (int i = 0; i < PF; ++i) {
         const size_t a = (size_t)reflect_index(R + i, Z) * plane + c;
@@ -125,20 +144,27 @@ lowpass_z_kernel(const T* __restrict__ in, const float* __restrict__ pred, float
                 {
                     float v = (float)pre[u % PF];
                     if (PRED) v = __fmul_rn(v, pre_w[u % PF]);
-                    ring[(u + 2 * R) % RING] = (double)v;
+                    ring[(u + 2 * R) % RING] = (A)v;
                 }
                 {   // the sample for output o + PF (reflect keeps the address valid past the end)
                     const size_t a = (size_t)reflect_high(o + R + PF, Z) * plane + c;
                     pre[u % PF] = __ldg(in + a);
                     if (PRED) pre_w[u % PF] = __ldg(pred + a);
                 }
-                double acc = __dmul_rn(ring[(u + R) % RING], W.w[R]);
+                if constexpr (F32) {
+                    float acc = 0.f;
 #pragma unroll
-                for (int jj = -R; jj < 0; ++jj) {
-                    double pr = __dadd_rn(ring[(u + R + jj + RING) % RING], ring[(u + R - jj) % RING]);
-                    acc = __dadd_rn(acc, __dmul_rn(pr, W.w[jj + R]));
+                    for (int jj = -R; jj <= R; ++jj) acc = __fmaf_rn(ring[(u + R + jj + RING) % RING], W32.w[jj + R], acc);
+                    out[(size_t)o * plane + c] = acc;
+                } else {
+                    double acc = __dmul_rn(ring[(u + R) % RING], W.w[R]);
+#pragma unroll
+                    for (int jj = -R; jj < 0; ++jj) {
+                        double pr = __dadd_rn(ring[(u + R + jj + RING) % RING], ring[(u + R - jj) % RING]);
+                        acc = __dadd_rn(acc, __dmul_rn(pr, W.w[jj + R]));
+                    }
+                    out[(size_t)o * plane + c] = (float)acc;
                 }
-                out[(size_t)o * plane + c] = (float)acc;
             }
         }
     }
@@ -159,10 +185,11 @@ constexpr int YX_STRIDE = YX_W + 9;  // 73 words: odd and coprime with 32
 constexpr int YX_THREADS = 256;
 constexpr int YX_BLK = 8;            // outputs per work item
 
-template <typename T, int RY, int RX, bool PRED>
+template <typename T, int RY, int RX, bool PRED, bool F32>
 __global__ void __launch_bounds__(YX_THREADS)
 lowpass_yx_kernel(const T* __restrict__ in, const float* __restrict__ pred, float* __restrict__ out,
-                  int Y, int X, Weights WY, Weights WX) {
+                  int Y, int X, Weights WY, Weights WX, Weights32 WY32, Weights32 WX32) {
+    using A = typename std::conditional<F32, float, double>::type;
     constexpr int IN_H = YX_TY + 2 * RY;
     constexpr int TX = YX_W - 2 * RX;
     constexpr int XG = (TX + YX_BLK - 1) / YX_BLK;  // column groups (the last may be partial)
@@ -201,33 +228,47 @@ lowpass_yx_kernel(const T* __restrict__ in, const float* __restrict__ pred, floa
     // ---- y pass: YX_W columns x (YX_TY / 8) row groups = 256 items
     for (int it = threadIdx.x; it < YX_W * (YX_TY / YX_BLK); it += YX_THREADS) {
         const int col = it % YX_W, r0 = (it / YX_W) * YX_BLK;
-        double v[YX_BLK + 2 * RY];
+        A v[YX_BLK + 2 * RY];
 #pragma unroll
-        for (int k = 0; k < YX_BLK + 2 * RY; ++k) v[k] = (double)s_in[r0 + k][col];
+        for (int k = 0; k < YX_BLK + 2 * RY; ++k) v[k] = (A)s_in[r0 + k][col];
 #pragma unroll
         for (int o = 0; o < YX_BLK; ++o) {
-            double acc = __dmul_rn(v[o + RY], WY.w[RY]);
+            if constexpr (F32) {
+                float acc = 0.f;
 #pragma unroll
-            for (int jj = -RY; jj < 0; ++jj)
-                acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v[o + RY + jj], v[o + RY - jj]), WY.w[jj + RY]));
-            s_mid[r0 + o][col] = (float)acc;
+                for (int jj = -RY; jj <= RY; ++jj) acc = __fmaf_rn(v[o + RY + jj], WY32.w[jj + RY], acc);
+                s_mid[r0 + o][col] = acc;
+            } else {
+                double acc = __dmul_rn(v[o + RY], WY.w[RY]);
+#pragma unroll
+                for (int jj = -RY; jj < 0; ++jj)
+                    acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v[o + RY + jj], v[o + RY - jj]), WY.w[jj + RY]));
+                s_mid[r0 + o][col] = (float)acc;
+            }
         }
     }
     __syncthreads();
     // ---- x pass: YX_TY rows x (TX / 8) column groups; lanes = rows
     for (int it = threadIdx.x; it < YX_TY * XG; it += YX_THREADS) {
         const int row = it % YX_TY, c0 = (it / YX_TY) * YX_BLK;
-        double v[YX_BLK + 2 * RX];
+        A v[YX_BLK + 2 * RX];
 #pragma unroll
-        for (int k = 0; k < YX_BLK + 2 * RX; ++k) v[k] = (c0 + k < YX_W) ? (double)s_mid[row][c0 + k] : 0.0;
+        for (int k = 0; k < YX_BLK + 2 * RX; ++k) v[k] = (c0 + k < YX_W) ? (A)s_mid[row][c0 + k] : (A)0;
 #pragma unroll
         for (int o = 0; o < YX_BLK; ++o) {
             if (c0 + o >= TX) break;
-            double acc = __dmul_rn(v[o + RX], WX.w[RX]);
+            if constexpr (F32) {
+                float acc = 0.f;
 #pragma unroll
-            for (int jj = -RX; jj < 0; ++jj)
-                acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v[o + RX + jj], v[o + RX - jj]), WX.w[jj + RX]));
-            s_in[row][c0 + o] = (float)acc;  // the input tile is dead: reuse it as the output stage
+                for (int jj = -RX; jj <= RX; ++jj) acc = __fmaf_rn(v[o + RX + jj], WX32.w[jj + RX], acc);
+                s_in[row][c0 + o] = acc;  // the input tile is dead: reuse it as the output stage
+            } else {
+                double acc = __dmul_rn(v[o + RX], WX.w[RX]);
+#pragma unroll
+                for (int jj = -RX; jj < 0; ++jj)
+                    acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v[o + RX + jj], v[o + RX - jj]), WX.w[jj + RX]));
+                s_in[row][c0 + o] = (float)acc;  // the input tile is dead: reuse it as the output stage
+            }
         }
     }
     __syncthreads();
@@ -242,12 +283,22 @@ lowpass_yx_kernel(const T* __restrict__ in, const float* __restrict__ pred, floa
 template <typename T, bool PRED>
 __global__ void __launch_bounds__(256)
 lowpass_axis_generic_kernel(const T* __restrict__ in, const float* __restrict__ pred,
-                            float* __restrict__ out, size_t total, int len, size_t stride, Weights W) {
+                            float* __restrict__ out, size_t total, int len, size_t stride, Weights W, int f32,
+                            Weights32 W32) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int pos = (int)((i / stride) % (size_t)len);
     const size_t base = i - (size_t)pos * stride;
     const int r = W.r;
+    if (f32) {
+        float acc32 = 0.f;
+        for (int jj = -r; jj <= r; ++jj) {
+            const float a = (float)load_weighted<T, PRED>(in, pred, base + (size_t)reflect_index(pos + jj, len) * stride);
+            acc32 = __fmaf_rn(a, W32.w[jj + r], acc32);
+        }
+        out[i] = acc32;
+        return;
+    }
     double acc = __dmul_rn(load_weighted<T, PRED>(in, pred, i), W.w[r]);
     for (int jj = -r; jj < 0; ++jj) {
         double a = load_weighted<T, PRED>(in, pred, base + (size_t)reflect_index(pos + jj, len) * stride);
@@ -261,8 +312,10 @@ template <typename T, bool PRED>
 int run_generic_axis(m3d_ctx* ctx, const T* in, const float* pred, float* out, size_t total, int len,
                      size_t stride, const Weights& W, cudaStream_t st) {
     int blocks = (int)((total + 255) / 256);
+    const Weights32 W32 = make_weights32(W);
     M3D_LAUNCH(ctx, KF_LOWPASS_GENERIC, st,
-               lowpass_axis_generic_kernel<T, PRED><<<blocks, 256, 0, st>>>(in, pred, out, total, len, stride, W));
+               lowpass_axis_generic_kernel<T, PRED><<<blocks, 256, 0, st>>>(in, pred, out, total, len, stride, W,
+                                                                            ctx->lowpass_f32, W32));
     M3D_CHECK_LAUNCH();
     return M3D_OK;
 }
@@ -275,13 +328,20 @@ int run_z(m3d_ctx* ctx, const T* in, const float* pred, float* out, int Z, int Y
     if (W.r != 12 && W.r != 8 && W.r != 6 && W.r != 4 && W.r != 2)
         return run_generic_axis<T, PRED>(ctx, in, pred, out, (size_t)Z * plane, Z, plane, W, st);
     KernelScope ks(ctx, KF_LOWPASS_Z, st);
+    const Weights32 W32 = make_weights32(W);
+#define M3D_Z_CASE(R_)                                                                                          \
+    case R_:                                                                                                    \
+        if (ctx->lowpass_f32) lowpass_z_kernel<T, R_, PRED, true><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W, W32); \
+        else lowpass_z_kernel<T, R_, PRED, false><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W, W32);      \
+        break;
     switch (W.r) {
-        case 12: lowpass_z_kernel<T, 12, PRED><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W); break;
-        case 8: lowpass_z_kernel<T, 8, PRED><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W); break;
-        case 6: lowpass_z_kernel<T, 6, PRED><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W); break;
-        case 4: lowpass_z_kernel<T, 4, PRED><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W); break;
-        case 2: lowpass_z_kernel<T, 2, PRED><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W); break;
+        M3D_Z_CASE(12)
+        M3D_Z_CASE(8)
+        M3D_Z_CASE(6)
+        M3D_Z_CASE(4)
+        M3D_Z_CASE(2)
     }
+#undef M3D_Z_CASE
     M3D_CHECK_LAUNCH();
     return M3D_OK;
 }
@@ -295,12 +355,18 @@ int run_yx_fast(m3d_ctx* ctx, const T* in, const float* pred, float* out, int n_
     if (grid.y > 65535 || grid.z > 65535) return 1;
     if (!((WY.r == 4 && WX.r == 4) || (WY.r == 2 && WX.r == 2) || (WY.r == 6 && WX.r == 6))) return 1;
     KernelScope ks(ctx, KF_LOWPASS_YX, st);
-    if (WY.r == 4 && WX.r == 4)
-        lowpass_yx_kernel<T, 4, 4, PRED><<<grid, YX_THREADS, 0, st>>>(in, pred, out, Y, X, WY, WX);
-    else if (WY.r == 2 && WX.r == 2)
-        lowpass_yx_kernel<T, 2, 2, PRED><<<grid, YX_THREADS, 0, st>>>(in, pred, out, Y, X, WY, WX);
-    else if (WY.r == 6 && WX.r == 6)
-        lowpass_yx_kernel<T, 6, 6, PRED><<<grid, YX_THREADS, 0, st>>>(in, pred, out, Y, X, WY, WX);
+    const Weights32 WY32 = make_weights32(WY), WX32 = make_weights32(WX);
+#define M3D_YX_CASE(R_)                                                                                                   \
+    if (WY.r == R_ && WX.r == R_) {                                                                                       \
+        if (ctx->lowpass_f32)                                                                                             \
+            lowpass_yx_kernel<T, R_, R_, PRED, true><<<grid, YX_THREADS, 0, st>>>(in, pred, out, Y, X, WY, WX, WY32, WX32); \
+        else                                                                                                              \
+            lowpass_yx_kernel<T, R_, R_, PRED, false><<<grid, YX_THREADS, 0, st>>>(in, pred, out, Y, X, WY, WX, WY32, WX32); \
+    }
+    M3D_YX_CASE(4)
+    M3D_YX_CASE(2)
+    M3D_YX_CASE(6)
+#undef M3D_YX_CASE
     M3D_CHECK_LAUNCH();
     return M3D_OK;
 }
@@ -618,6 +684,13 @@ extern "C" int m3d_lowpass(m3d_ctx* ctx, const void* in_dev, int in_dtype, const
         return lowpass_all<float>(ctx, reinterpret_cast<const float*>(in_dev), predictor_dev, n_vols, Z, Y, X, sigma,
                                   mode2d, out_dev, st);
     return m3d_fail(M3D_ERR_ARG, "m3d_lowpass: dtype %d", in_dtype);
+}
+
+extern "C" int m3d_set_lowpass_mode(m3d_ctx* ctx, int mode) {
+    if (!ctx) return m3d_fail(M3D_ERR_ARG, "m3d_set_lowpass_mode: null ctx");
+    if (mode != 0 && mode != 1) return m3d_fail(M3D_ERR_ARG, "m3d_set_lowpass_mode: mode must be 0 (float64) or 1 (float32)");
+    ctx->lowpass_f32 = mode;
+    return M3D_OK;
 }
 
 extern "C" int m3d_weight(m3d_ctx* ctx, const uint16_t* readout_dev, const float* predictor_dev, int64_t n,

@@ -202,6 +202,36 @@ def lowpass_stack(stack: np.ndarray, sigma, is_3d: bool) -> np.ndarray:
     return out
 
 
+def lowpass_image_float32_accumulation(image: np.ndarray, sigma, is_3d: bool) -> np.ndarray:
+    """The OPT-IN float32 arithmetic of ``m3d_lowpass`` (``m3d_set_lowpass_mode(ctx, 1)``), restated: per axis (z, y, x;
+    y, x only in 2-D mode) the float64 SciPy weights are cast to float32 and every output is ``acc = fma(x[i + j], w[j],
+    acc)`` over the taps j = -r .. r in ascending order, float32 throughout, reflect boundary.  This is what
+    cupyx.scipy.ndimage's correlate kernel is believed to compute for float32 images (the reference's call: PD:1972-1979);
+    CuPy is not available here, so this restatement pins the KERNEL to its documented arithmetic, not to the reference.
+    The fused multiply-add is emulated in extended precision (exact product, one rounding)."""
+    out = np.asarray(image, dtype=F32)
+    axes = (0, 1, 2) if is_3d else (1, 2)
+    sig = tuple(float(v) for v in sigma)
+    if not is_3d:
+        sig = sig[-2:] if len(sig) == 3 else sig
+    for axis, s in zip(axes, sig if is_3d else sig):
+        w64, r = gaussian_kernel1d(s)
+        w32 = w64.astype(F32)
+        n = out.shape[axis]
+        idx = np.arange(-r, n + r)
+        per = 2 * n
+        m = np.mod(idx, per)
+        src = np.where(m >= n, per - 1 - m, m)  # scipy 'reflect': d c b a | a b c d | d c b a
+        ext = np.take(out, src, axis=axis)
+        acc = np.zeros(out.shape, dtype=F32)
+        for j in range(2 * r + 1):
+            x = np.take(ext, np.arange(j, j + n), axis=axis)
+            prod = x.astype(np.longdouble) * np.longdouble(w32[j])  # exact: 24 x 24 bits
+            acc = (prod + acc.astype(np.longdouble)).astype(F32)   # one rounding (64-bit significand holds the sum)
+        out = acc
+    return out
+
+
 def gaussian_kernel1d(sigma: float, truncate: float = 4.0) -> tuple[np.ndarray, int]:
     """SciPy ``_gaussian_kernel1d`` (order 0): float64 weights, radius int(truncate*sigma+0.5)."""
     sd = float(sigma)

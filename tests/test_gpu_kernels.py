@@ -251,6 +251,32 @@ def test_lowpass_matches_scipy_bit_exact(torch, shape, mode2d):
     np.testing.assert_array_equal(got.view(np.uint32), ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("shape", [(5, 33, 47), (30, 40, 72)])
+@pytest.mark.parametrize("mode2d", [False, True])
+def test_lowpass_float32_accumulation_mode(torch, shape, mode2d):
+    """Opt-in arithmetic (m3d_set_lowpass_mode(ctx, 1)): float32 weights, one float32 FMA per tap in ascending order --
+    bit-exact against its restatement, templated radii (3,1,1) and the generic-radius path, with a predictor; and
+    switching back restores SciPy's float64 arithmetic."""
+    _df, cb = cases.codebook16()
+    ctx, _ = _ctx(cb)
+    rng = np.random.default_rng(45)
+    vols = rng.integers(0, 4000, size=(2, *shape)).astype(np.uint16)
+    pred = rng.uniform(0, 1, size=vols.shape).astype(np.float32)
+    ctx.set_lowpass_accumulate("float32")
+    for sigma in [(3.0, 1.0, 1.0), (1.3, 2.2, 0.8)]:
+        got = ctx.lowpass(_dev(torch, vols), sigma, mode2d, predictor=_dev(torch, pred)).cpu().numpy()
+        w = orc.weight_readout(vols, pred)
+        ref = np.stack([orc.lowpass_image_float32_accumulation(v, sigma, not mode2d) for v in w])
+        np.testing.assert_array_equal(got.view(np.uint32), ref.view(np.uint32), err_msg=str(sigma))
+        f64 = orc.lowpass_stack(w, sigma, not mode2d)
+        assert not np.array_equal(got, f64)  # it IS a different arithmetic ...
+        np.testing.assert_allclose(got, f64, rtol=2e-6, atol=1e-3)  # ... a few float32 ulps away
+    ctx.set_lowpass_accumulate("float64")
+    got = ctx.lowpass(_dev(torch, vols), (3.0, 1.0, 1.0), mode2d).cpu().numpy()
+    ref = orc.lowpass_stack(vols.astype(np.float32), (3.0, 1.0, 1.0), not mode2d)
+    np.testing.assert_array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
 def test_lowpass_f32_with_predictor_and_other_sigmas(torch):
     _df, cb = cases.codebook16()
     ctx, _ = _ctx(cb)
