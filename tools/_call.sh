@@ -1,6 +1,4 @@
 set -x
-python -m pytest tests -x -q -m gpu 2>&1 | tail -6
-python tools/zstd_device_probe.py 2 > gpurun_out/zstd_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:blosc_zstd_decode -s 1 -c 1 -o gpurun_out/r2_zstd_v2_fast python tools/zstd_device_probe.py 2 > gpurun_out/zstd_ncu.log 2>&1
-tail -1 gpurun_out/zstd_plain.log
-(time python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_n1_b.json 2> gpurun_out/r2_bench_n1_b.err) 2>&1 | tail -3
-tail -3 gpurun_out/r2_bench_n1_b.err
+python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-extras > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_cfg2.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-extras > gpurun_out/ncu1.log 2>&1
+python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-extras > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:decode_gate -s 3 -c 2 -o gpurun_out/r2_gate_full python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-extras > gpurun_out/ncu2.log 2>&1
+tail -2 gpurun_out/ncu2.log | cut -c1-300
