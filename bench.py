@@ -644,7 +644,7 @@ def run_b200(args):
     achieved = GATE_BYTES_PER_VOXEL * n_vox / (gate_ms * 1e-3) / 1e9 if gate_ms else 0.0
     # measured DRAM traffic of that kernel from the committed ncu --set full capture (same shape only)
     traffic = None
-    tf = ROOT / "profiles" / "r1_gate_traffic.json"
+    tf = ROOT / "profiles" / "r2_gate_traffic.json"
     if tf.exists():
         tj = json.loads(tf.read_text())
         if tuple(tj.get("shape_zyx", ())) == tuple(shape) and tj.get("n_bits") == N_BITS:

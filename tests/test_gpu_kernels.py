@@ -9,6 +9,8 @@ import pytest
 from scipy import ndimage as ndi
 
 import cases
+
+GOLDEN = __import__("pathlib").Path(__file__).resolve().parent / "golden"
 from oracle import decode_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -180,6 +182,41 @@ def test_decode_division_guards_vectors(torch):
             if dense:
                 for k in ("magnitude", "distance", "scaled"):
                     _same_f16(got[k], ref[k], k)
+
+
+@pytest.mark.parametrize("layout", ["packed", "isolated"])
+def test_equal_distance_from_smaller_sum(torch, layout):
+    """The dense-regime evaluation compares SUMS and takes a square root only when the sum improves.  Two different
+    sums can round to the same float32 distance; NumPy's arg-min then keeps the FIRST index even if the later codeword
+    has the smaller sum.  tests/golden/sqrt_tie_traces.npy holds 200 traces found by search
+    (make_sqrt_tie_traces.py) on which exactly that happens; ``packed`` puts them side by side (whole warps unresolved:
+    tensor-core marking path), ``isolated`` between background voxels (warp-cooperative path)."""
+    _df, cb = cases.codebook16()
+    traces = np.load(GOLDEN / "sqrt_tie_traces.npy")
+    unit = orc.normalize_codebook(cb["matrix"][:, :16]).astype(np.float32)
+    if layout == "packed":
+        stack = np.ascontiguousarray(traces.T.reshape(16, 1, 8, 25))
+    else:
+        stack = np.zeros((16, 1, 40, 200), dtype=np.float32)
+        stack[:, 0, np.arange(200) % 40, np.arange(200)] = traces.T
+    for dense in (True, False):
+        _c, _s, _d, got, ref = _decode_both(torch, cb, stack, None, None, mag=(1e-3, 10.0), dense=dense)
+        np.testing.assert_array_equal(got["decoded"], ref["decoded"])
+        if dense:
+            _same_f16(got["distance"], ref["distance"], "distance")
+    # the fixture really holds the case: the winner (first arg-min of the distance) is not the codeword of least sum
+    xs = orc.scale_traces(traces.T.copy(), np.zeros(16, np.float32), np.ones(16, np.float32))
+    xh, _mag = orc.normalize_traces(np.clip(xs, 0, 1).astype(np.float32))
+    xh = xh.T.astype(np.float32)
+    acc = None
+    for b in range(16):
+        t = (xh[:, b:b + 1] - unit[None, :, b]).astype(np.float32)
+        term = (t * t).astype(np.float32)
+        acc = term if acc is None else (acc + term).astype(np.float32)
+    d = np.sqrt(acc).astype(np.float32)
+    first = d.argmin(1)
+    least = acc.argmin(1)
+    assert ((least > first) & (acc[np.arange(len(first)), first] > acc.min(1))).all()
 
 
 def test_decode_all_foreground_worst_case(torch):
