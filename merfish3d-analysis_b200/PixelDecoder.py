@@ -350,7 +350,18 @@ class PixelDecoder:
         stats = _norm.DeviceOrderStats(ctx)
         bit_ids = list(self._datastore.bit_ids)
         per_bit = []
-        for bit_id in bit_ids:
+        # The seed's filtered volumes ARE the decode inputs of the optimiser's first iteration whenever the hot-pixel
+        # replacement (PD:1072-1074) changes nothing: same weighting, warp, z crop and low-pass.  With the tile cache on
+        # they are written straight into per-tile stacks and handed to the cache, so iteration 0 neither uploads nor
+        # filters those tiles again.  A volume that does hold a value above the threshold disqualifies its tile.
+        nb = self._n_merfish_bits
+        lp_on = self._lowpass_active(sigma)
+        keep: dict = {}
+        threads_mode = not collective and max(1, min(int(self._num_gpus), torch.cuda.device_count() or 1)) > 1
+        same_tiles = tile_indices is not None or len(all_ids) <= 5  # the tiles the iterations will decode on this rank
+        if self._tile_cache is not None and lp_on and same_tiles and not threads_mode:
+            keep = {t: {"stack": None, "em": [], "ok": True} for t in tiles}
+        for bi, bit_id in enumerate(bit_ids):
             vols = []
             for tile_id in tiles:
                 readout = self._datastore.load_local_readout_image(tile=tile_id, bit=bit_id, return_future=False)
@@ -360,13 +371,29 @@ class PixelDecoder:
                 _ex, em = self._datastore.load_local_wavelengths_um(tile=tile_id, bit=bit_id)
                 img = self._weighted_volume_device(readout, predictor, ctx,
                                                    warp=self._bit_warp_px(tile_id, bit_id, em))
+                kp = keep.get(tile_id) if bi < nb else None
+                if kp is not None and kp["ok"] and bool((img > float(hot_pixel_threshold)).any()):
+                    kp["ok"], kp["stack"] = False, None  # the replacement below will change this volume
                 # PD:1072-1074: hot pixels -> median of the middle plane
                 mid = img[img.shape[0] // 2]
                 med = stats.median([mid])
                 ctx.replace_above(img, float(hot_pixel_threshold), float(med))
+                full_z = int(img[self._z_slice].shape[0])
                 img = img[self._z_slice].contiguous()
-                if self._lowpass_active(sigma) and img.numel():
-                    img = ctx.lowpass(img[None], sigma, not self._is_3D)[0]
+                if lp_on and img.numel():
+                    out = None
+                    if kp is not None and kp["ok"]:
+                        if kp["stack"] is None:
+                            need = nb * img.numel() * 4
+                            if self._tile_cache_used + self._seed_reserved(keep) + need <= self._tile_cache_resolve_budget():
+                                kp["stack"] = torch.empty((nb, *img.shape), dtype=torch.float32, device=dev)
+                                kp["full_z"] = full_z
+                            else:
+                                kp["ok"] = False
+                        if kp["ok"]:
+                            out = kp["stack"][bi : bi + 1]
+                            kp["em"].append(em)
+                    img = ctx.lowpass(img[None], sigma, not self._is_3D, out=out)[0]
                 vols.append(img)
             per_bit.append(vols)
             # one bit at a time keeps the peak at <= 5 volumes (+ low-pass temporaries)
@@ -385,6 +412,17 @@ class PixelDecoder:
         self._global_background_vector = background_vector
         self._global_normalization_vector = normalization_vector
         self._global_normalization_loaded = True
+        for tile_id, kp in keep.items():
+            if kp["ok"] and kp["stack"] is not None and len(kp["em"]) == nb:
+                key = self._stage_key(all_ids.index(tile_id), gpu_id, None, sigma)
+                state = {"readout": None, "predictor": None, "stack": kp["stack"], "lowpass_done": True}
+                self._tile_cache_insert(key, state, {"em_wvl": kp["em"], "full_z": kp["full_z"]})
+                self._tile_cache_stats["seeded_tiles"] = self._tile_cache_stats.get("seeded_tiles", 0) + 1
+
+    @staticmethod
+    def _seed_reserved(keep: dict) -> int:
+        """bytes of the per-tile stacks the percentile seed already holds for the tile cache"""
+        return sum(int(k["stack"].numel()) * 4 for k in keep.values() if k.get("stack") is not None)
 
     def _load_iterative_normalization_vectors(self, gpu_id: int = 0) -> None:
         """PD:1201-1248 (stale-codebook fingerprint -> ValueError)."""
@@ -1923,6 +1961,9 @@ class PixelDecoder:
         temp_dir = None
         try:
             t_seed = _time.perf_counter()
+            # decode inputs stay in HBM from the seed / the first iteration on (budgeted; see _tile_cache_begin)
+            self._tile_cache_budget_request = getattr(self, "tile_cache_budget_bytes", None)
+            self._tile_cache_begin(self._local_gpu(), self._tile_cache_budget_request)
             # the percentile seed (PD:4662-4667 computes it in the parent process): under a process group its
             # tiles are sharded over the ranks and the pooled medians are all-reduced (see the method)
             self._load_global_normalization_vectors(gpu_id=self._local_gpu(), recalculate=True,
@@ -1939,9 +1980,6 @@ class PixelDecoder:
                 temp_dir = self._datastore.decoded_temporary_dir(self._decode_run_key)
                 temp_dir.mkdir(parents=True, exist_ok=True)
             self._temp_dir = temp_dir
-            # decode inputs stay in HBM from the first iteration on (budgeted; see _tile_cache_begin)
-            self._tile_cache_budget_request = getattr(self, "tile_cache_budget_bytes", None)
-            self._tile_cache_begin(self._local_gpu(), self._tile_cache_budget_request)
             self._persistent_workers = {}
             if tile_indices is not None:
                 random_tiles = list(tile_indices)

@@ -102,8 +102,12 @@ def test_optimizer_tile_cache_does_not_change_the_result(tmp_path, budget, lowpa
     stats = dec._optimizer_timing["cache"]
     want_resident = {None: 3, 0: 0, "one": 1}[budget]
     assert stats["resident_tiles"] == want_resident, stats
-    assert stats["hits"] == 2 * want_resident and stats["misses"] == 9 - 2 * want_resident, stats
-    assert [it["cache_hits"] for it in dec._optimizer_timing["iterations"]] == [0, want_resident, want_resident]
+    # with the low-pass on, the percentile seed's filtered volumes are the decode inputs (no value above the hot-pixel
+    # threshold here): resident tiles are already there in iteration 0
+    first = want_resident if lowpass is not None else 0
+    assert stats.get("seeded_tiles", 0) == first, stats
+    assert stats["hits"] == first + 2 * want_resident and stats["misses"] == 9 - first - 2 * want_resident, stats
+    assert [it["cache_hits"] for it in dec._optimizer_timing["iterations"]] == [first, want_resident, want_resident]
     i_n, i_b = ds.load_decode_normalization_vectors(None, "iterative")
     if lowpass is None:
         np.testing.assert_array_equal(i_n, g["iterative_normalization"])
@@ -183,3 +187,32 @@ def test_cuda_path_on_the_simulation_cli_sequence(tmp_path):
     compare_with_reference_table(ds.load_local_decoded_spots(0), tile, rel=REL)
     got = ds.load_global_filtered_decoded_spots()
     compare_with_reference_table(got[[c for c in filt.columns]], filt, rel=REL)
+
+
+def test_optimizer_seed_does_not_cache_tiles_with_hot_pixels(tmp_path):
+    """The percentile seed replaces values above 50 000 (PD:1072-1074); the decode does not.  A tile that holds such a
+    value must not take its decode input from the seed's volumes: it is staged by the first iteration instead, and the
+    vectors equal those of a run without any cache."""
+    from merfish3d_analysis_b200.datastore import ArrayDataStore
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    g = np.load(GOLDEN / "reference_optimizer.npz")
+    df_cb, _cb = cases.codebook16()
+    stacks = [st.copy() for st in g["stacks"]]
+    stacks[1][3, 2, 5, 5] = 60000
+    out = []
+    for i, budget in enumerate((None, 0)):
+        ds = ArrayDataStore(tmp_path / f"s{i}" / "qi2labdatastore", codebook=df_cb)
+        for st in stacks:
+            ds.add_tile(st)
+        dec = PixelDecoder(ds, merfish_bits=16, verbose=0)
+        dec.tile_cache_budget_bytes = budget
+        dec.optimize_normalization_by_decoding(n_iterations=3, minimum_pixels=4, lowpass_sigma=(3.0, 1.0, 1.0),
+                                               magnitude_threshold=(0.9, 10.0), tile_indices=[0, 1, 2])
+        out.append((ds.load_decode_normalization_vectors(None, "global"), ds.load_decode_normalization_vectors(None, "iterative"),
+                    dec._optimizer_timing["cache"]))
+    assert out[0][2].get("seeded_tiles", 0) == 2 and out[0][2]["resident_tiles"] == 3
+    assert [out[0][2]["hits"], out[0][2]["misses"]] == [2 + 3 + 3, 1]
+    for a, b in zip(out[0][:2], out[1][:2]):
+        np.testing.assert_array_equal(a[0], b[0])
+        np.testing.assert_array_equal(a[1], b[1])

@@ -1,4 +1,7 @@
 set -x
-python -m pytest tests/test_gpu_kernels.py -x -q 2>&1 | tail -3
-python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-extras > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"decode_|ccl_|features_|reset_foreground|DeviceRadixSort|DeviceScan" -c 400 --csv --log-file gpurun_out/r2_launches_cfg2.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-extras > gpurun_out/ncu1.log 2>&1
-grep -vc "^==" gpurun_out/r2_launches_cfg2.csv
+python -m pytest tests/test_gpu_reference_golden.py tests/test_gpu_pixeldecoder.py tests/test_gpu_zarr_store.py -x -q -k "optimizer or simulation or unregistered or without_any or multi_gpu" 2>&1 | tail -4
+python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e --extras optimizer 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+o=d['extras']['optimizer']
+print({k:o[k] for k in ('total_s','seed_s','steady_s_per_iteration','steady_gvoxel_per_s','iteration0_gvoxel_per_s','cache')}); print(o['iteration0']); print(o['iterative_normalization_head'])"

@@ -44,6 +44,36 @@ ds.save_decode_normalization_vectors(None, "global", np.full(16, 17.0, np.float3
 dec = PixelDecoder(ds, merfish_bits=16, verbose=0)
 dec.decode_one_tile(0, lowpass_sigma=None, minimum_pixels=4, normalization_method="global")
 n += len(dec.decoded_barcodes)
+# round 2: K = 385 / 1000 in the dense regime (two fragment k-steps, wide candidate sets), the optimiser with its tile cache
+# and device-resident tables, and the image store with both device entropy decoders
+for name in ("bits22_k385_dense", "bits22_k1000_dense", "dense16"):
+    sc = SCENARIOS[name]
+    df_cb2, _cb2, stack2, pred2, bkg2, nrm2, _ex = scenario_inputs(sc)
+    ds = ArrayDataStore(tmp / name, codebook=df_cb2, microscope_type=sc.get("microscope", "3D"))
+    ds.add_tile(stack2)
+    ds.save_decode_normalization_vectors(None, "global", nrm2, bkg2)
+    dec = PixelDecoder(ds, merfish_bits=int(sc.get("bits", 16)), verbose=0)
+    kw = dict(lowpass_sigma=None, minimum_pixels=sc["min_px"], magnitude_threshold=sc.get("mag"), normalization_method="global")
+    dec.decode_one_tile(0, return_results=True, **kw)
+    dec.decode_one_tile(0, **kw)
+    n += len(dec.decoded_barcodes)
+    dec._cleanup()
+ds = ArrayDataStore(tmp / "opt", codebook=df_cb)
+for k in range(3):
+    ds.add_tile(cases.small_stack(cb["matrix"], shape=(8, 40, 48), seed=300 + k, density=5e-3))
+dec = PixelDecoder(ds, merfish_bits=16, verbose=0)
+dec.optimize_normalization_by_decoding(n_iterations=3, minimum_pixels=4, lowpass_sigma=(3.0, 1.0, 1.0),
+                                       magnitude_threshold=(0.9, 10.0), tile_indices=[0, 1, 2])
+from merfish3d_analysis_b200 import zarr_store as zs  # noqa: E402
+
+rng = np.random.default_rng(3)
+img = (rng.poisson(100, (16, 96, 80)) + 100).astype(np.uint16)
+for comp in ("blosc-zstd", "blosc-lz4"):
+    zs.write_ome_image(tmp / f"img_{comp}", img, chunks=(8, 32, 32), compression=comp)
+    dst = torch.zeros(img.shape, dtype=torch.uint16, device="cuda")
+    zs.transfer(dec._ctx(0), [(zs.ZarrImage(tmp / f"img_{comp}.ome.zarr"), dst)])
+    torch.cuda.synchronize()
+    assert np.array_equal(dst.cpu().numpy(), img), comp
 # table stage incl. 2-D within-tile clusters
 for mode, micro in (("3d", "3D"), ("2d", "2D")):
     ds = ArrayDataStore(tmp / f"tab{mode}", codebook=df_cb, microscope_type=micro,
