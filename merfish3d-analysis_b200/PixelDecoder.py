@@ -361,16 +361,35 @@ class PixelDecoder:
         same_tiles = tile_indices is not None or len(all_ids) <= 5  # the tiles the iterations will decode on this rank
         if self._tile_cache is not None and lp_on and same_tiles and not threads_mode:
             keep = {t: {"stack": None, "em": [], "ok": True} for t in tiles}
+        import threading
+
+        skey = (dev.index, threading.get_ident(), "seed")
+        copy = self._copy_streams.get(skey)
+        if copy is None:
+            copy = self._copy_streams[skey] = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        order = [(bi, bit_id, tile_id) for bi, bit_id in enumerate(bit_ids) for tile_id in tiles]
+
+        def start(item):
+            _bi, bit_id_, tile_id_ = item
+            readout = self._datastore.load_local_readout_image(tile=tile_id_, bit=bit_id_, return_future=False)
+            predictor = self._datastore.load_local_feature_predictor_image(tile=tile_id_, bit=bit_id_, return_future=False)
+            # measured A/B on one box (2 tiles of 16 x 64 x 2048 x 2048): seed 0.80 s with the copies serialised, 0.58 s ahead
+            return self._upload_volume_ahead(readout, predictor, ctx, copy)
+
+        ahead = start(order[0]) if order else None
+        pos = 0
         for bi, bit_id in enumerate(bit_ids):
             vols = []
             for tile_id in tiles:
-                readout = self._datastore.load_local_readout_image(tile=tile_id, bit=bit_id, return_future=False)
-                predictor = self._datastore.load_local_feature_predictor_image(
-                    tile=tile_id, bit=bit_id, return_future=False
-                )
+                r_dev, p_dev, ev = ahead
+                pos += 1
+                copy.wait_stream(main)  # the next volume's buffers may reuse memory the main stream is still reading
+                ahead = start(order[pos]) if pos < len(order) else None
+                main.wait_event(ev)
                 _ex, em = self._datastore.load_local_wavelengths_um(tile=tile_id, bit=bit_id)
-                img = self._weighted_volume_device(readout, predictor, ctx,
-                                                   warp=self._bit_warp_px(tile_id, bit_id, em))
+                img = self._finish_weighted_volume(ctx, r_dev, p_dev, self._bit_warp_px(tile_id, bit_id, em))
+                del r_dev, p_dev
                 kp = keep.get(tile_id) if bi < nb else None
                 if kp is not None and kp["ok"] and bool((img > float(hot_pixel_threshold)).any()):
                     kp["ok"], kp["stack"] = False, None  # the replacement below will change this volume
@@ -601,11 +620,41 @@ class PixelDecoder:
         is_float = self._image_dtype(readout).kind == "f"
         r = to_dev(readout, np.float32 if is_float else np.uint16)
         p = None if self._is_unit_predictor(predictor) else to_dev(predictor, np.float32)
+        return self._finish_weighted_volume(ctx, r, p, warp)
+
+    def _finish_weighted_volume(self, ctx, r, p, warp):
+        """device readout (uint16 / float32) and predictor (float32 / None) -> float32(readout) * predictor, warped"""
+        import torch
+
         if warp is not None:
             return self._warp_volume(ctx, r, p, warp)
-        if is_float:
+        if r.dtype == torch.float32:
             return r if p is None else r * p
         return ctx.weight(r, p)
+
+    def _upload_volume_ahead(self, readout, predictor, ctx, copy_stream):
+        """Start the host -> device copies of one bit volume on ``copy_stream`` and return ``(readout, predictor | None,
+        event)``: the percentile seed uploads volume i + 1 while volume i is corrected, filtered and ranked."""
+        import torch
+
+        main = torch.cuda.current_stream(ctx.device)
+        is_float = self._image_dtype(readout).kind == "f"
+        out = []
+        with torch.cuda.stream(copy_stream):
+            for arr, dtype in ((readout, np.float32 if is_float else np.uint16),
+                               (None if self._is_unit_predictor(predictor) else predictor, np.float32)):
+                if arr is None:
+                    out.append(None)
+                    continue
+                src = _zs.host_piece(arr, 0, int(arr.shape[0]), dtype)
+                dst = torch.empty(tuple(src.shape), dtype=torch.float32 if dtype == np.float32 else torch.uint16,
+                                  device=ctx.device)
+                dst.record_stream(main)  # consumed on the main stream: the allocator must not recycle it under it
+                _zs.transfer(ctx, [(src, dst)])
+                out.append(dst)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return out[0], out[1], ev
 
     def _load_bit_data(self, feature_predictor_threshold: float | None = 0.1, gpu_id: int = 0,
                        z_bounds: tuple[int, int] | None = None, lowpass_sigma=None) -> None:
