@@ -389,6 +389,10 @@ def _optimizer_extra(dist, world, rank, local, dev, matrix, df_cb, shared_root):
             dist.barrier()
     ds._refresh()
     dec = PixelDecoder(ds, merfish_bits=16, num_gpus=world, verbose=0)
+    # warm-up, like every other measurement of this file: one iteration over ONE tile per rank (first use of the kernels,
+    # the library's labelling scratch, pinned registrations); the timed call starts with an empty tile cache again
+    dec.optimize_normalization_by_decoding(n_iterations=1, lowpass_sigma=(3.0, 1.0, 1.0), magnitude_threshold=MAG,
+                                           minimum_pixels=MIN_PX, tile_indices=[r * T for r in range(world)])
     dec._profile = {"sync": True}
     ctx = dec._ctx(local)
     ctx.reset_counters()
