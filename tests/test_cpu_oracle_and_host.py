@@ -285,3 +285,102 @@ def test_plane_wise_centroid_statistics_upstream_known_answer():
     got = orc.plane_wise_centroid_statistics(labels, intensity, z_support=3, minlength=int(labels.max()) + 1)
     for g, e in zip(got, expected, strict=True):
         np.testing.assert_allclose(g, e)
+
+
+# ---------------------------------------------------------------------------------------------- pooled medians (optimiser exchange)
+def _host_hist_backend():
+    import torch
+
+    from merfish3d_analysis_b200 import normalization as nm
+
+    return nm._numpy_hist_backend, (lambda rows: torch.zeros((rows, 2048), dtype=torch.int64))
+
+
+def test_pooled_medians_equal_numpy_median():
+    """The radix-select walk behind the optimiser's exchange (three rounds of digit histograms for all multisets together)
+    returns exactly np.median of the float64 view of float32 values: odd / even counts, duplicates, negatives, zeros of
+    both signs, a single element, an empty multiset, denormals and infinities."""
+    import torch
+
+    from merfish3d_analysis_b200 import normalization as nm
+
+    hist_fn, new_hist = _host_hist_backend()
+    rng = np.random.default_rng(5)
+    sets = [
+        rng.normal(0, 100, 1001).astype(np.float32),
+        rng.normal(0, 100, 1000).astype(np.float32),
+        np.repeat(np.float32([3.5, 3.5, 7.25]), 40),
+        np.float32([0.0, -0.0, 0.0, -0.0]),
+        np.float32([42.0]),
+        np.float32([]),
+        np.float32([1e-42, 2e-42, np.inf, -np.inf, 5.0, 6.0]),
+        rng.integers(0, 5, 999).astype(np.float32),
+        (rng.gamma(2.0, 300.0, 20001)).astype(np.float32),
+    ]
+    got = nm.pooled_medians([torch.from_numpy(a.copy()) for a in sets], hist_fn, new_hist)
+    for a, g in zip(sets, got):
+        if a.size == 0:
+            assert np.isnan(g)
+        else:
+            want = float(np.median(a.astype(np.float64)))
+            assert g == want or (np.isnan(g) and np.isnan(want)), (a[:5], g, want)
+
+
+def test_pooled_medians_over_ranks_equal_the_pooled_median():
+    """Splitting every multiset over 'ranks' and summing the histograms (what all_reduce does) gives the median of the union."""
+    import torch
+
+    from merfish3d_analysis_b200 import normalization as nm
+
+    hist_fn, new_hist = _host_hist_backend()
+    rng = np.random.default_rng(6)
+    full = [rng.gamma(2.0, 200.0, n).astype(np.float32) for n in (0, 1, 2, 777, 4000)]
+    parts = [[a[r::3] for a in full] for r in range(3)]  # three ranks; some get nothing of the small sets
+
+    # emulate the collective: run the walk once, with a histogram function that sums over all ranks' parts
+    def hist_all(data, row, pm, pv, sh):
+        q = int(data[0].item()) if data.numel() else -1  # the query index is smuggled in as the first element
+        for r in range(3):
+            t = torch.from_numpy(parts[r][q].copy())
+            if t.numel():
+                hist_fn(t, row, pm, pv, sh)
+
+    tags = [torch.tensor([float(i)] + [0.0] * 0, dtype=torch.float32) for i in range(len(full))]
+    got = nm.pooled_medians(tags, hist_all, new_hist)
+    for a, g in zip(full, got):
+        if a.size == 0:
+            assert np.isnan(g)
+        else:
+            assert g == float(np.median(a.astype(np.float64)))
+
+
+def test_iterative_vector_queries_match_the_dataframe_statistic():
+    """queries -> pooled medians -> rounding == the pandas restatement of PD:1263-1368, incl. blank genes in any case,
+    missing gene ids, NaN means, rows with on-bits outside the columns, and bits nobody has on."""
+    import torch
+
+    from merfish3d_analysis_b200 import normalization as nm
+
+    hist_fn, new_hist = _host_hist_backend()
+    rng = np.random.default_rng(7)
+    n = 3000
+    df = pd.DataFrame({f"bit{i:02d}_mean_intensity": rng.gamma(2, 100, n).astype(np.float32).astype(np.float64) for i in range(1, 17)})
+    genes = np.array([f"g{i}" for i in range(30)] + ["Blank-1", "blank2", "BLANK_3"], dtype=object)
+    df["gene_id"] = genes[rng.integers(0, len(genes), n)]
+    df.loc[7, "gene_id"] = None
+    on = np.stack([rng.permutation(15)[:4] + 1 for _ in range(n)])  # bit 16 is never on
+    for k in range(4):
+        df[f"on_bit_{k + 1}"] = on[:, k]
+    df.loc[11, "bit03_mean_intensity"] = np.nan
+    want = nm.iterative_normalization_vectors(df, 16)
+    q, kept = nm.iterative_vector_queries(df, 16, torch.device("cpu"))
+    assert kept == int((~df["gene_id"].astype("string").str.lower().str.startswith("blank", na=False)).sum())
+    med = nm.pooled_medians(q, hist_fn, new_hist)
+    got = nm.finish_iterative_vectors(med[:16], med[16:])
+    np.testing.assert_array_equal(got[0], want[0])
+    np.testing.assert_array_equal(got[1], want[1])
+    assert got[0][15] == 1.0  # no transcript has bit 16 on: NaN -> 1
+    # values that are not float32 numbers are refused (the caller then gathers the tables)
+    df2 = df.copy()
+    df2.loc[0, "bit01_mean_intensity"] = 0.1  # not representable in float32
+    assert nm.iterative_vector_queries(df2, 16, torch.device("cpu"))[0] is None
