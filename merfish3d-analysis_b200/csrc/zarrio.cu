@@ -1167,11 +1167,38 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
     if (slot_bytes > ((size_t)1 << 30)) return m3d_fail(M3D_ERR_ARG, "m3d_zarr_read_chunks: chunk larger than 1 GiB");
     slot_bytes += slot_bytes / 64 + 4096;  // room for a Blosc frame that did not compress (header, index, prefixes)
     int workers = io_threads();
-    if (workers > n_chunks) workers = n_chunks;
     // Slots in flight.  A host-decoded chunk holds its slot for the decode (~5 ms) plus a short drain; a chunk the
-    // device decodes holds it for the file read plus ~1 ms of sequence-latency-bound LZ4 kernel, and it is the number
-    // of such kernels running side by side (one stream per slot) that fills the GPU: 3 per worker, bounded in bytes.
+    // device decodes holds it for the file read plus its decode kernel (LZ4 ~1 ms, zstd ~4 ms with others running),
+    // and it is the number of such kernels running side by side (one stream per slot) that fills the GPU.
     int n_slots = 3 * workers;
+    {
+        // What will decode the frames?  The first chunk's Blosc header tells.  When the device does, the host threads only
+        // copy chunk files from the page cache into pinned slots, and more than ~10 of them slow each other down
+        // (measured, 16 bits x 32 x 2048^2, store -> HBM decoded GB/s: lz4 76 with 16 threads / 48 slots, 97 with 10 / 32;
+        // zstd 47 with 16 / 48, 53 with 6-12 / 48; profiles/r2_zstd_device.txt).
+        const char* gz0 = getenv("M3D_ZARR_GPU_ZSTD");
+        const bool dev_zstd = !(gz0 && *gz0 && atoi(gz0) == 0), dev_lz4 = getenv("M3D_ZARR_HOST_LZ4") == nullptr;
+        int inner = -1;
+        if (chunks[0].codec == M3D_ZARR_BLOSC) {
+            const int fd0 = open(chunks[0].path, O_RDONLY);
+            uint8_t head0[BLOSC_HEADER];
+            BloscHeader h0;
+            if (fd0 >= 0) {
+                if (pread(fd0, head0, BLOSC_HEADER, (off_t)chunks[0].offset) == BLOSC_HEADER &&
+                    parse_blosc_header(head0, (size_t)1 << 40, h0) && !(h0.flags & FLAG_MEMCPY))
+                    inner = h0.codec;
+                close(fd0);
+            }
+        }
+        const bool on_device = (inner == BLOSC_LZ4 && dev_lz4) || (inner == BLOSC_ZSTD && dev_zstd);
+        if (on_device && getenv("M3D_IO_THREADS") == nullptr && workers > 10) workers = 10;
+        if (on_device) n_slots = inner == BLOSC_LZ4 ? 32 : 48;
+    }
+    if (workers > n_chunks) workers = n_chunks;
+    if (const char* e = getenv("M3D_ZARR_SLOTS")) {  // tuning hook: slots (= chunks in flight) independent of the threads
+        const int v = atoi(e);
+        if (v >= 1) n_slots = v > 128 ? 128 : v;
+    }
     while (n_slots > 3 && (size_t)n_slots * slot_bytes > ((size_t)768 << 20)) --n_slots;
     ZarrRing* R = zring_of(ctx);
     if (int rc = zring_ensure(R, n_slots, (slot_bytes + 255) & ~(size_t)255)) return rc;

@@ -1,15 +1,10 @@
 set -x
-python -m pytest tests/test_gpu_kernels.py tests/test_gpu_reference_golden.py -x -q 2>&1 | tail -3
-python -m pytest tests/test_gpu_fullsize.py -x -q 2>&1 | tail -2
-python tools/dense_regime.py 2>&1 | tail -1
-python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e --extras all_foreground 2>&1 | tail -1 | python -c "
+python -m pytest tests/test_gpu_zarr_store.py -x -q 2>&1 | tail -2
+for comp in blosc-zstd blosc-lz4; do timeout 600 python tools/zarr_io_bench.py --z 32 --skip-host --only-transfer --reps 4 --compression $comp 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); a=d['a_store_to_device']
+print('RES $comp default', round(a['decoded_gb_s'],1), 'GB/s')"; done
+python bench.py --steps 5 --warmup 3 --no-cpu --extras zarr 2>&1 | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('A value', d['value'], d['roofline']['kernel_ms_per_step']['decode_search_kernel'], d['extras']['all_foreground']['ms_per_decode'])"
-cp merfish3d-analysis_b200/libm3d_b200.so /tmp/libA.so; cp tools/_libm3d_lb5.so merfish3d-analysis_b200/libm3d_b200.so
-python tools/dense_regime.py 2>&1 | tail -1
-python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e --extras all_foreground 2>&1 | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('B(lb5) value', d['value'], d['roofline']['kernel_ms_per_step']['decode_search_kernel'], d['extras']['all_foreground']['ms_per_decode'])"
-python -m pytest tests/test_gpu_kernels.py -x -q -k "decode" 2>&1 | tail -2
+for k,v in d['extras'].items(): print('RES', k, {a:(round(b,2) if isinstance(b,float) else b) for a,b in v.items() if a!='note'})"
