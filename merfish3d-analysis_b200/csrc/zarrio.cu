@@ -286,12 +286,32 @@ __global__ void __launch_bounds__(64) blosc_zstd_decode_kernel(const uint8_t* fr
 
 // Second device version (M3D_ZARR_GPU_ZSTD=2; zstd_lanes.cuh): the warp works as a team -- one lane per Huffman
 // stream, shared copies.  Pinned on the host through the one-lane policy; NOT yet run on a device.
-__global__ void __launch_bounds__(64) blosc_zstd_decode_kernel_v2(const uint8_t* frame, int64_t frame_len, uint8_t* out,
-                                                                  int splits_per_block, uint8_t* lit_scratch,
+// Up to ZSTD_BATCH_MAX chunks per launch: the frames of several slots decoded by ONE grid.  A chunk is only 64 warps, and
+// the device runs at most 32 streams' kernels side by side (hardware work queues), so one launch per chunk leaves most of
+// the GPU idle however many slots are in flight; a launch over G chunks puts G x 64 latency chains behind each queue.
+constexpr int ZSTD_BATCH_MAX = 8;
+struct ZstdBatch {
+    const uint8_t* frame[ZSTD_BATCH_MAX];
+    int64_t frame_len[ZSTD_BATCH_MAX];
+    uint8_t* out[ZSTD_BATCH_MAX];
+    uint8_t* lit[ZSTD_BATCH_MAX];
+    int splits[ZSTD_BATCH_MAX];
+    int first_block[ZSTD_BATCH_MAX + 1];  // thread blocks (two warps each) of chunk g: [first_block[g], first_block[g + 1])
+    int n;
+};
+
+__global__ void __launch_bounds__(64) blosc_zstd_decode_kernel_v2(const __grid_constant__ ZstdBatch batch,
                                                                   int* __restrict__ error) {
     __shared__ m3d_zstd::Work work[2];
     __shared__ m3d_zstd::LitPlan plans[2];
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int g = 0;
+    while (g + 1 < batch.n && (int)blockIdx.x >= batch.first_block[g + 1]) ++g;
+    const uint8_t* frame = batch.frame[g];
+    const int64_t frame_len = batch.frame_len[g];
+    uint8_t* out = batch.out[g];
+    uint8_t* lit_scratch = batch.lit[g];
+    const int splits_per_block = batch.splits[g];
+    const int64_t warp = ((int64_t)((int)blockIdx.x - batch.first_block[g]) * blockDim.x + threadIdx.x) >> 5;
     const int typesize = frame[3], flags = frame[2];
     const int64_t nbytes = le32_hd(frame + 4), blocksize = le32_hd(frame + 8);
     const int64_t nblocks = (nbytes + blocksize - 1) / blocksize, leftover = nbytes % blocksize;
@@ -1171,6 +1191,7 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
     // device decodes holds it for the file read plus its decode kernel (LZ4 ~1 ms, zstd ~4 ms with others running),
     // and it is the number of such kernels running side by side (one stream per slot) that fills the GPU.
     int n_slots = 3 * workers;
+    bool batch_zstd = false;
     {
         // What will decode the frames?  The first chunk's Blosc header tells.  When the device does, the host threads only
         // copy chunk files from the page cache into pinned slots, and more than ~10 of them slow each other down
@@ -1192,17 +1213,28 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
         }
         const bool on_device = (inner == BLOSC_LZ4 && dev_lz4) || (inner == BLOSC_ZSTD && dev_zstd);
         if (on_device && getenv("M3D_IO_THREADS") == nullptr && workers > 10) workers = 10;
-        if (on_device) n_slots = inner == BLOSC_LZ4 ? 32 : 48;
+        if (on_device) n_slots = inner == BLOSC_LZ4 ? 32 : 96;
+        batch_zstd = on_device && inner == BLOSC_ZSTD;
     }
     if (workers > n_chunks) workers = n_chunks;
     if (const char* e = getenv("M3D_ZARR_SLOTS")) {  // tuning hook: slots (= chunks in flight) independent of the threads
         const int v = atoi(e);
         if (v >= 1) n_slots = v > 128 ? 128 : v;
     }
-    while (n_slots > 3 && (size_t)n_slots * slot_bytes > ((size_t)768 << 20)) --n_slots;
+    int batch = 1;  // chunks per decode launch (device zstd only)
+    if (batch_zstd) {
+        batch = 4;
+        if (const char* e = getenv("M3D_ZARR_BATCH")) {
+            const int v = atoi(e);
+            if (v >= 1) batch = v > ZSTD_BATCH_MAX ? ZSTD_BATCH_MAX : v;
+        }
+    }
+    while (n_slots > 3 && (size_t)n_slots * slot_bytes > ((size_t)1 << 30)) --n_slots;
+    if (n_slots < batch) batch = n_slots;
+    n_slots -= n_slots % batch;  // a group's slots are consecutive
     ZarrRing* R = zring_of(ctx);
     if (int rc = zring_ensure(R, n_slots, (slot_bytes + 255) & ~(size_t)255)) return rc;
-    n_slots = (int)R->pinned.size();
+    if ((int)R->pinned.size() < n_slots) n_slots = (int)R->pinned.size();  // (a ring kept from a wider call has more)
     const size_t slot_cap = R->slot_bytes;
 
     // Chunk j uses slot j % n_slots (and that slot's stream) once chunk j - n_slots has been issued and the slot has
@@ -1380,80 +1412,119 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
         if (e != cudaSuccess && rc == M3D_OK) rc = m3d_fail(M3D_ERR_CUDA, "m3d_zarr_read_chunks: %s", cudaGetErrorString(e));
         return e == cudaSuccess;
     };
-    for (int j = 0; j < n_chunks && rc == M3D_OK; ++j) {
+    // Chunks are issued in aligned groups of `batch` consecutive chunks (= consecutive slots) on the stream of the group's
+    // first slot: the device-zstd frames of a group go through ONE decode launch (ZstdBatch), everything else as before.
+    for (int j0 = 0; j0 < n_chunks && rc == M3D_OK; j0 += batch) {
+        const int j1 = j0 + batch < n_chunks ? j0 + batch : n_chunks;
         {
             std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return staged[j] || failed.load(); });
+            cv.wait(lk, [&] {
+                if (failed.load()) return true;
+                for (int j = j0; j < j1; ++j)
+                    if (!staged[j]) return false;
+                return true;
+            });
         }
         if (failed.load()) break;
-        const m3d_zarr_chunk& c = chunks[j];
-        const int s = j % n_slots;
-        cudaStream_t q = R->streams[s];
-        if (!joined[s]) {
+        const int s0 = j0 % n_slots;
+        cudaStream_t q = R->streams[s0];
+        if (!joined[s0]) {
             cuda_ok(cudaStreamWaitEvent(q, R->begin, 0));
-            joined[s] = 1;
+            joined[s0] = 1;
         }
-        if (rc == M3D_OK && kind[j] == MISSING) {
-            rc = launch_fill(ctx, c, q);
-        } else if (rc == M3D_OK) {
-            const ChunkGeom g = geom_of(c, info[j]);
-            if (kind[j] == GPU_LZ4) {
-                any_gpu = true;
-                const int64_t nblocks = (g.nbytes + frame_blocksize[j] - 1) / frame_blocksize[j];
-                const int64_t warps = nblocks * splits[j];
-                if (on_gpu_zstd[j]) {
-                    const size_t need = (size_t)warps * m3d_zstd::MAX_BLOCK;
-                    if (R->dev_lit_bytes[s] < need) {
-                        cuda_ok(cudaStreamSynchronize(q));
-                        if (R->dev_lit[s]) cudaFree(R->dev_lit[s]);
-                        R->dev_lit[s] = nullptr;
-                        R->dev_lit_bytes[s] = 0;
-                        if (cuda_ok(cudaMalloc(&R->dev_lit[s], need))) R->dev_lit_bytes[s] = need;
-                    }
-                    if (rc == M3D_OK &&
-                        cuda_ok(cudaMemcpyAsync(R->dev_comp[s], R->pinned[s], (size_t)comp_len[j], cudaMemcpyHostToDevice, q))) {
-                        if (gpu_zstd_mode == 2) {
-                            M3D_LAUNCH(ctx, KF_ZARR_ZSTD, q,
-                                       blosc_zstd_decode_kernel_v2<<<(unsigned)((warps + 1) / 2), 64, 0, q>>>(
-                                           reinterpret_cast<const uint8_t*>(R->dev_comp[s]), comp_len[j],
-                                           reinterpret_cast<uint8_t*>(R->dev[s]), splits[j],
-                                           reinterpret_cast<uint8_t*>(R->dev_lit[s]), R->d_error));
-                        } else {
+        ZstdBatch zb;
+        zb.n = 0;
+        zb.first_block[0] = 0;
+        for (int j = j0; j < j1 && rc == M3D_OK; ++j) {  // the group's compressed frames cross PCIe, then one launch
+            if (kind[j] != GPU_LZ4 || !on_gpu_zstd[j] || gpu_zstd_mode != 2) continue;
+            const int s = j % n_slots;
+            const ChunkGeom g = geom_of(chunks[j], info[j]);
+            const int64_t warps = (g.nbytes + frame_blocksize[j] - 1) / frame_blocksize[j] * splits[j];
+            const size_t need = (size_t)warps * m3d_zstd::MAX_BLOCK;
+            if (R->dev_lit_bytes[s] < need) {
+                cuda_ok(cudaStreamSynchronize(q));
+                if (R->dev_lit[s]) cudaFree(R->dev_lit[s]);
+                R->dev_lit[s] = nullptr;
+                R->dev_lit_bytes[s] = 0;
+                if (cuda_ok(cudaMalloc(&R->dev_lit[s], need))) R->dev_lit_bytes[s] = need;
+            }
+            if (rc == M3D_OK &&
+                cuda_ok(cudaMemcpyAsync(R->dev_comp[s], R->pinned[s], (size_t)comp_len[j], cudaMemcpyHostToDevice, q))) {
+                const int i = zb.n++;
+                zb.frame[i] = reinterpret_cast<const uint8_t*>(R->dev_comp[s]);
+                zb.frame_len[i] = comp_len[j];
+                zb.out[i] = reinterpret_cast<uint8_t*>(R->dev[s]);
+                zb.lit[i] = reinterpret_cast<uint8_t*>(R->dev_lit[s]);
+                zb.splits[i] = splits[j];
+                zb.first_block[i + 1] = zb.first_block[i] + (int)((warps + 1) / 2);
+            }
+        }
+        if (rc == M3D_OK && zb.n > 0) {
+            any_gpu = true;
+            M3D_LAUNCH(ctx, KF_ZARR_ZSTD, q,
+                       blosc_zstd_decode_kernel_v2<<<(unsigned)zb.first_block[zb.n], 64, 0, q>>>(zb, R->d_error));
+            cuda_ok(cudaGetLastError());
+        }
+        for (int j = j0; j < j1 && rc == M3D_OK; ++j) {
+            const m3d_zarr_chunk& c = chunks[j];
+            const int s = j % n_slots;
+            if (kind[j] == MISSING) {
+                rc = launch_fill(ctx, c, q);
+            } else {
+                const ChunkGeom g = geom_of(c, info[j]);
+                if (kind[j] == GPU_LZ4 && on_gpu_zstd[j] && gpu_zstd_mode == 2) {
+                    // decoded by the group's launch above
+                } else if (kind[j] == GPU_LZ4) {
+                    any_gpu = true;
+                    const int64_t nblocks = (g.nbytes + frame_blocksize[j] - 1) / frame_blocksize[j];
+                    const int64_t warps = nblocks * splits[j];
+                    if (on_gpu_zstd[j]) {  // mode 1: the lane-serial first version, one launch per chunk
+                        const size_t need = (size_t)warps * m3d_zstd::MAX_BLOCK;
+                        if (R->dev_lit_bytes[s] < need) {
+                            cuda_ok(cudaStreamSynchronize(q));
+                            if (R->dev_lit[s]) cudaFree(R->dev_lit[s]);
+                            R->dev_lit[s] = nullptr;
+                            R->dev_lit_bytes[s] = 0;
+                            if (cuda_ok(cudaMalloc(&R->dev_lit[s], need))) R->dev_lit_bytes[s] = need;
+                        }
+                        if (rc == M3D_OK &&
+                            cuda_ok(cudaMemcpyAsync(R->dev_comp[s], R->pinned[s], (size_t)comp_len[j], cudaMemcpyHostToDevice, q))) {
                             M3D_LAUNCH(ctx, KF_ZARR_ZSTD, q,
                                        blosc_zstd_decode_kernel<<<(unsigned)((warps + 1) / 2), 64, 0, q>>>(
                                            reinterpret_cast<const uint8_t*>(R->dev_comp[s]), comp_len[j],
                                            reinterpret_cast<uint8_t*>(R->dev[s]), splits[j],
                                            reinterpret_cast<uint8_t*>(R->dev_lit[s]), R->d_error));
+                            cuda_ok(cudaGetLastError());
                         }
+                    } else if (cuda_ok(cudaMemcpyAsync(R->dev_comp[s], R->pinned[s], (size_t)comp_len[j], cudaMemcpyHostToDevice, q))) {
+                        M3D_LAUNCH(ctx, KF_ZARR_LZ4, q,
+                                   blosc_lz4_decode_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, q>>>(
+                                       reinterpret_cast<const uint8_t*>(R->dev_comp[s]), comp_len[j],
+                                       reinterpret_cast<uint8_t*>(R->dev[s]), splits[j], R->d_error));
                         cuda_ok(cudaGetLastError());
                     }
-                } else if (cuda_ok(cudaMemcpyAsync(R->dev_comp[s], R->pinned[s], (size_t)comp_len[j], cudaMemcpyHostToDevice, q))) {
-                    M3D_LAUNCH(ctx, KF_ZARR_LZ4, q,
-                               blosc_lz4_decode_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, q>>>(
-                                   reinterpret_cast<const uint8_t*>(R->dev_comp[s]), comp_len[j],
-                                   reinterpret_cast<uint8_t*>(R->dev[s]), splits[j], R->d_error));
-                    cuda_ok(cudaGetLastError());
+                } else {
+                    cuda_ok(cudaMemcpyAsync(R->dev[s], R->pinned[s], (size_t)g.nbytes, cudaMemcpyHostToDevice, q));
                 }
-            } else {
-                cuda_ok(cudaMemcpyAsync(R->dev[s], R->pinned[s], (size_t)g.nbytes, cudaMemcpyHostToDevice, q));
+                if (rc == M3D_OK) rc = launch_for(ctx, c.elem_size, reinterpret_cast<const uint8_t*>(R->dev[s]), g, c.dst, q);
             }
-            if (rc == M3D_OK) rc = launch_for(ctx, c.elem_size, reinterpret_cast<const uint8_t*>(R->dev[s]), g, c.dst, q);
-        }
-        if (rc == M3D_OK && cuda_ok(cudaEventRecord(R->drained[s], q))) {
-            R->used[s] = 1;
-            cuda_ok(cudaStreamWaitEvent(st, R->drained[s], 0));  // `stream` is ordered behind every chunk
+            if (rc == M3D_OK && cuda_ok(cudaEventRecord(R->drained[s], q))) {
+                R->used[s] = 1;
+                if (j == j1 - 1) cuda_ok(cudaStreamWaitEvent(st, R->drained[s], 0));  // `stream` is ordered behind every group
+            }
+            if (rc != M3D_OK) break;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                issued[j] = 1;
+            }
+            cv.notify_all();
+            if (on_piece && (j == n_chunks - 1 || chunks[j + 1].piece != c.piece)) on_piece(c.piece, user);
         }
         if (rc != M3D_OK) {
             failed.store(1);
             cv.notify_all();
             break;
         }
-        {
-            std::lock_guard<std::mutex> lk(mu);
-            issued[j] = 1;
-        }
-        cv.notify_all();
-        if (on_piece && (j == n_chunks - 1 || chunks[j + 1].piece != c.piece)) on_piece(c.piece, user);
     }
     for (auto& t : pool) t.join();
     if (rc != M3D_OK) return rc;

@@ -28,13 +28,18 @@ namespace m3d_zstd {
 
 constexpr uint32_t MAGIC = 0xFD2FB528u;
 constexpr int MAX_BLOCK = 128 * 1024;
-constexpr int HUF_MAX_BITS = 12;
+// RFC 8878 4.2.1: "this specification limits its maximum Number_of_Bits to 11" (libzstd's encoder: LitHufLog 11).  The
+// tables below are sized by the format's own maxima (accuracy log 9 for literal / match lengths, 8 for offsets, 6 for
+// Huffman weights): the workspace of one block decoder is ~10 KB, which is what lets 20 of them share an SM's shared memory.
+constexpr int HUF_MAX_BITS = 11;
 constexpr int FSE_MAX_AL = 9;
 
-struct FseTable {
-    uint8_t sym[1 << FSE_MAX_AL];
-    uint8_t nb[1 << FSE_MAX_AL];
-    uint16_t base[1 << FSE_MAX_AL];
+template <int AL>
+struct FseTableT {
+    static constexpr int MAX_AL = AL;
+    uint8_t sym[1 << AL];
+    uint8_t nb[1 << AL];
+    uint16_t base[1 << AL];
     int al;
     int valid;
 };
@@ -43,7 +48,9 @@ struct Work {
     uint16_t huf_tab[1 << HUF_MAX_BITS];  // symbol | bits consumed << 8, indexed by the next huf_bits bits
     int huf_bits;
     int huf_valid;
-    FseTable ll, of, ml, wt;
+    FseTableT<9> ll, ml;
+    FseTableT<8> of;
+    FseTableT<6> wt;
     uint32_t rep[3];
     int16_t freq[256];
     uint8_t weights[256];
@@ -143,8 +150,9 @@ M3D_HD inline int64_t fse_read_counts(const uint8_t* p, int64_t n, int max_al, i
     return (bit + 7) / 8;
 }
 
-M3D_HD inline bool fse_build(FseTable& t, const int16_t* freq, int n_symbols, int al) {
-    if (al > FSE_MAX_AL || n_symbols > 256) return false;
+template <class Table>
+M3D_HD inline bool fse_build(Table& t, const int16_t* freq, int n_symbols, int al) {
+    if (al > Table::MAX_AL || n_symbols > 256) return false;
     const int size = 1 << al;
     uint16_t next[256];
     int high = size;
@@ -180,7 +188,8 @@ M3D_HD inline bool fse_build(FseTable& t, const int16_t* freq, int n_symbols, in
     return true;
 }
 
-M3D_HD inline void fse_rle(FseTable& t, int symbol) {
+template <class Table>
+M3D_HD inline void fse_rle(Table& t, int symbol) {
     t.sym[0] = (uint8_t)symbol;
     t.nb[0] = 0;
     t.base[0] = 0;
@@ -531,7 +540,8 @@ M3D_HD inline void predefined_counts(int which, int16_t* f, int* n, int* al) {
 }
 
 // one of the three code tables of a sequences section; which: 0 LL, 1 OF, 2 ML.  Returns bytes consumed or -1.
-M3D_HD inline int64_t seq_table(Work& w, FseTable& t, int which, int mode, const uint8_t* p, int64_t n) {
+template <class Table>
+M3D_HD inline int64_t seq_table(Work& w, Table& t, int which, int mode, const uint8_t* p, int64_t n) {
     const int max_al[3] = {9, 8, 9}, max_sym[3] = {36, 32, 53};
     if (mode == 0) {
         int ns, al;

@@ -1,10 +1,4 @@
-set -x
-python -m pytest tests/test_gpu_zarr_store.py -x -q 2>&1 | tail -2
-for comp in blosc-zstd blosc-lz4; do timeout 600 python tools/zarr_io_bench.py --z 32 --skip-host --only-transfer --reps 4 --compression $comp 2>&1 | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); a=d['a_store_to_device']
-print('RES $comp default', round(a['decoded_gb_s'],1), 'GB/s')"; done
-python bench.py --steps 5 --warmup 3 --no-cpu --extras zarr 2>&1 | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-for k,v in d['extras'].items(): print('RES', k, {a:(round(b,2) if isinstance(b,float) else b) for a,b in v.items() if a!='note'})"
+cd /root/repo
+timeout 600 python -m pytest tests/test_gpu_zarr_store.py -x -q 2>&1 | tail -3
+timeout 600 python tools/zarr_io_bench.py --sweep "M3D_ZARR_BATCH=4;M3D_ZARR_BATCH=4,M3D_ZARR_SLOTS=120;M3D_ZARR_BATCH=6,M3D_ZARR_SLOTS=120;M3D_ZARR_BATCH=8,M3D_ZARR_SLOTS=120;M3D_ZARR_BATCH=2,M3D_ZARR_SLOTS=64;M3D_ZARR_BATCH=3,M3D_ZARR_SLOTS=96;M3D_ZARR_BATCH=4,M3D_IO_THREADS=14;M3D_ZARR_BATCH=4,M3D_IO_THREADS=8;M3D_ZARR_BATCH=1,M3D_ZARR_SLOTS=48" --z 96 --out gpurun_out/zstd_batch_sweep3.json 2>&1 | grep -v "^{" | tail -20
+timeout 600 python tools/zarr_io_bench.py --sweep "M3D_ZARR_BATCH=4;M3D_ZARR_BATCH=2;M3D_ZARR_BATCH=4,M3D_ZARR_SLOTS=64" --z 32 --out gpurun_out/zstd_batch_sweep4.json 2>&1 | grep -v "^{" | tail -20

@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--skip-host", action="store_true", help="skip leg b (host decode to arrays, then upload)")
     ap.add_argument("--only-transfer", action="store_true", help="leg a only (store -> device)")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--sweep", default=None, help="leg a only, repeated under settings 'K=V,K=V;K=V,...' of the M3D_* "
+                    "environment switches (read by the library on every call), store written once")
     args = ap.parse_args()
 
     import torch
@@ -97,6 +99,35 @@ def main():
         res["a_store_to_device"] = {"ms": 1e3 * min(ts), "decoded_gb_s": raw_bytes / min(ts) / 1e9,
                                     "stored_gb_s": stored / min(ts) / 1e9, "launches": ctx.launches_by_kernel().get(
                                         "zarr_unshuffle_place_kernel", 0)}
+        if args.sweep:
+            res["sweep"] = []
+            for setting in args.sweep.split(";"):
+                pairs = [kv.split("=", 1) for kv in setting.split(",") if kv]
+                saved = {k: os.environ.get(k) for k, _ in pairs}
+                for k, v in pairs:
+                    os.environ[k] = v
+                try:
+                    run_transfer()
+                    ts = []
+                    for _ in range(args.reps):
+                        t0 = time.perf_counter()
+                        run_transfer()
+                        ts.append(time.perf_counter() - t0)
+                    ok = bool(torch.equal(dst.cpu(), torch.from_numpy(stack)))
+                    res["sweep"].append({"setting": setting, "ms": 1e3 * min(ts), "decoded_gb_s": raw_bytes / min(ts) / 1e9,
+                                         "identical": ok})
+                    print("SWEEP", setting, f"{raw_bytes / min(ts) / 1e9:.1f} GB/s", "ok" if ok else "DIFFERENT", flush=True)
+                finally:
+                    for k, v in saved.items():
+                        if v is None:
+                            os.environ.pop(k, None)
+                        else:
+                            os.environ[k] = v
+            line = json.dumps(res)
+            print(line)
+            if args.out:
+                Path(args.out).write_text(line + "\n")
+            return
         ctx.set_timing(True)
         ctx.reset_counters()
         run_transfer()
