@@ -102,6 +102,26 @@ __device__ __forceinline__ float in_as_f32<uint16_t>(const uint16_t* p, size_t i
 template <>
 __device__ __forceinline__ float in_as_f32<float>(const float* p, size_t i) { return __ldg(p + i); }
 
+// A sample that is loaded now and used later stays in a full 32-bit register until then.  (Held as `uint16_t` the
+// compiler packs it into half a register with a PRMT right behind the LDG -- an instruction that waits for the load,
+// which is exactly what a prefetch is meant to avoid: the z kernel spent 10 of 17 cycles per issue in long_scoreboard.)
+template <typename T>
+__device__ __forceinline__ uint32_t ld_raw32(const T* p);
+template <>
+__device__ __forceinline__ uint32_t ld_raw32<uint16_t>(const uint16_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+template <>
+__device__ __forceinline__ uint32_t ld_raw32<float>(const float* p) { return __float_as_uint(__ldg(p)); }
+template <typename T>
+__device__ __forceinline__ float raw32_as_f32(uint32_t v);
+template <>
+__device__ __forceinline__ float raw32_as_f32<uint16_t>(uint32_t v) { return (float)v; }  // < 65536: exact, = (float)(uint16_t)
+template <>
+__device__ __forceinline__ float raw32_as_f32<float>(uint32_t v) { return __uint_as_float(v); }
+
 template <typename T, bool PRED>
 __device__ __forceinline__ double load_weighted(const T* in, const float* pred, size_t i) {
     float v = in_as_f32<T>(in, i);
@@ -110,52 +130,109 @@ __device__ __forceinline__ double load_weighted(const T* in, const float* pred, 
 }
 
 // ------------------------------------------------------------------ z pass, register ring
-// One thread per (y,x) column marching along z.  The 2R+1 float64 samples live in a register ring
-// (loop unrolled by the ring length so every index is static); the sample entering the ring is
-// fetched PF planes ahead, so the float64 pipe never waits on the load of the plane it is about
-// to consume.
-template <typename T, int R, bool PRED, bool F32>
-__global__ void __launch_bounds__(128)
+// One thread per (y,x) column marching along z.  The 2R+1 samples of the window live in a register ring (loop
+// unrolled by the ring length so every index is static).
+//
+// The sample that enters the ring must be requested several planes ahead, and HOW decides everything: with plain
+// loads into registers every prefetch LDG of the unrolled loop gets the same scoreboard, and the first use of the
+// OLDEST sample then waits for the YOUNGEST load too -- the queue is five deep in the source and one deep in the
+// hardware (ncu: 70 % of the stall samples on that conversion, float64 pipe 43 % busy; profiles/r2_lowpass.txt).
+// ASYNC = true stages the samples through shared memory with `cp.async` (LDGSTS): commit groups are COUNTED
+// (`cp.async.wait_group N`), so ZQ planes really are in flight per warp, each warp reads only what its own lanes
+// copied (no block barrier), and the address arithmetic leaves the float64 issue slots.  Needs 4-byte aligned pairs
+// of columns (uint16: even plane size and a 4-byte aligned base); ASYNC = false is the register-queue form for
+// everything else.
+constexpr int ZQ = 8;  // planes in flight per warp (ASYNC)
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <typename T, int R, bool PRED, bool F32, bool ASYNC>
+__global__ void __launch_bounds__(128, 5)
 lowpass_z_kernel(const T* __restrict__ in, const float* __restrict__ pred, float* __restrict__ out,
                  int Z, size_t plane, Weights W, Weights32 W32) {
     constexpr int RING = 2 * R + 1;
-    constexpr int PF = (RING % 5 == 0) ? 5 : ((RING % 3 == 0) ? 3 : 1);  // divides the unroll length
-    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= plane) return;
+    constexpr int PF = ASYNC ? 1 : ((RING % 5 == 0) ? 5 : ((RING % 3 == 0) ? 3 : 1));  // divides the unroll length
+    __shared__ __align__(16) T s_pre[ASYNC ? ZQ : 1][128];
+    __shared__ __align__(16) float s_w[(ASYNC && PRED) ? ZQ : 1][128];
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = c < plane;
+    if (!ASYNC && !active) return;
+    if (ASYNC && !active) c = plane - 2 + (threadIdx.x & 1);  // a valid column: the warp stays whole for its barriers
     using A = typename std::conditional<F32, float, double>::type;
     A ring[RING];
-    T pre[PF];         // prefetched samples stay in their storage type: converting them on arrival
+    uint32_t pre[PF];  // register queue (ASYNC = false): samples stay raw (ld_raw32), converting them on arrival
     float pre_w[PF];   // would make the warp wait on the very load the prefetch is meant to hide
     // slot of ext[j] is (j + R) mod RING
 #pragma unroll
     for (int i = 0; i < 2 * R; ++i)
         ring[i] = (A)load_weighted<T, PRED>(in, pred, (size_t)reflect_index(i - R, Z) * plane + c);
+    // who copies: 4 bytes per cp.async, i.e. one float column or a pair of uint16 columns (the even lane's)
+    const bool copier = sizeof(T) == 4 || (threadIdx.x & 1) == 0;
+    auto stage_plane = [&](int step) {  // ASYNC: request the sample that enters the ring at output `step`
+        if (step < Z) {
+            const size_t a = (size_t)reflect_high(step + R, Z) * plane + c;
+            if (copier) cp_async4(&s_pre[step % ZQ][threadIdx.x], in + a);
+            if (PRED) cp_async4(&s_w[step % ZQ][threadIdx.x], pred + a);
+        }
+        cp_async_commit();  // (an empty group past the end keeps the count in step)
+    };
+    if constexpr (ASYNC) {
 #pragma unroll
-    for (int i = 0; i < PF; ++i) {
-        const size_t a = (size_t)reflect_index(R + i, Z) * plane + c;
-        pre[i] = __ldg(in + a);
-        pre_w[i] = PRED ? __ldg(pred + a) : 1.f;
+        for (int i = 0; i < ZQ; ++i) stage_plane(i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+            const size_t a = (size_t)reflect_index(R + i, Z) * plane + c;
+            pre[i] = ld_raw32<T>(in + a);
+            pre_w[i] = PRED ? __ldg(pred + a) : 1.f;
+        }
     }
+    // marching pointers: the sample entering the prefetch queue and the output plane advance by one plane per step
+    // (the reflected tail past the last plane takes the general address)
+    size_t a_fwd = (size_t)(R + PF) * plane + c;  // address of plane o + R + PF while that plane exists
+    float* po = out + c;
     for (int o0 = 0; o0 < Z; o0 += RING) {
 #pragma unroll
         for (int u = 0; u < RING; ++u) {
             const int o = o0 + u;
             if (o < Z) {
-                {
-                    float v = (float)pre[u % PF];
-                    if (PRED) v = __fmul_rn(v, pre_w[u % PF]);
+                if constexpr (ASYNC) {
+                    cp_async_wait<ZQ - 1>();  // the group of step o has landed (ZQ - 1 younger ones may be pending)
+                    __syncwarp();             // ... for every lane of the warp: pairs share a copy
+                    float v;
+                    if constexpr (sizeof(T) == 4) v = raw32_as_f32<T>(reinterpret_cast<const uint32_t&>(s_pre[o % ZQ][threadIdx.x]));
+                    else v = (float)s_pre[o % ZQ][threadIdx.x];
+                    if (PRED) v = __fmul_rn(v, s_w[o % ZQ][threadIdx.x]);
                     ring[(u + 2 * R) % RING] = (A)v;
-                }
-                {   // the sample for output o + PF (reflect keeps the address valid past the end)
-                    const size_t a = (size_t)reflect_high(o + R + PF, Z) * plane + c;
-                    pre[u % PF] = __ldg(in + a);
-                    if (PRED) pre_w[u % PF] = __ldg(pred + a);
+                    __syncwarp();             // both lanes of a pair have read before the slot is requested again
+                    stage_plane(o + ZQ);
+                } else {
+                    {
+                        float v = raw32_as_f32<T>(pre[u % PF]);
+                        if (PRED) v = __fmul_rn(v, pre_w[u % PF]);
+                        ring[(u + 2 * R) % RING] = (A)v;
+                    }
+                    {   // the sample for output o + PF (reflect keeps the address valid past the end)
+                        const int zi = o + R + PF;
+                        const size_t a = zi < Z ? a_fwd : (size_t)reflect_high(zi, Z) * plane + c;
+                        a_fwd += plane;
+                        pre[u % PF] = ld_raw32<T>(in + a);
+                        if (PRED) pre_w[u % PF] = __ldg(pred + a);
+                    }
                 }
                 if constexpr (F32) {
                     float acc = 0.f;
 #pragma unroll
                     for (int jj = -R; jj <= R; ++jj) acc = __fmaf_rn(ring[(u + R + jj + RING) % RING], W32.w[jj + R], acc);
-                    out[(size_t)o * plane + c] = acc;
+                    if (!ASYNC || active) *po = acc;
                 } else {
                     double acc = __dmul_rn(ring[(u + R) % RING], W.w[R]);
 #pragma unroll
@@ -163,11 +240,13 @@ lowpass_z_kernel(const T* __restrict__ in, const float* __restrict__ pred, float
                         double pr = __dadd_rn(ring[(u + R + jj + RING) % RING], ring[(u + R - jj) % RING]);
                         acc = __dadd_rn(acc, __dmul_rn(pr, W.w[jj + R]));
                     }
-                    out[(size_t)o * plane + c] = (float)acc;
+                    if (!ASYNC || active) *po = (float)acc;
                 }
+                po += plane;
             }
         }
     }
+    if constexpr (ASYNC) cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------ fused y,x pass, shared tile
@@ -206,20 +285,31 @@ lowpass_yx_kernel(const T* __restrict__ in, const float* __restrict__ pred, floa
         constexpr int N_LD = (IN_H + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
         const int lx = threadIdx.x % YX_W, lr = threadIdx.x / YX_W;
         const int gx = reflect_index(x0 + lx - RX, X);
-        T raw[N_LD];
+        uint32_t raw[N_LD];
         float wv[N_LD];
+        if (y0 - RY >= 0 && y0 - RY + N_LD * ROWS_PER_PASS <= Y) {
+            // tile rows (and the rows the last, partly unused pass touches) all exist: one address, then a row stride
+            size_t a = zoff + (size_t)(y0 - RY + lr) * X + gx;
 #pragma unroll
-        for (int k = 0; k < N_LD; ++k) {
-            const int ly = lr + k * ROWS_PER_PASS;
-            const int gy = reflect_index(y0 + (ly < IN_H ? ly : IN_H - 1) - RY, Y);
-            const size_t a = zoff + (size_t)gy * X + gx;
-            raw[k] = __ldg(in + a);
-            wv[k] = PRED ? __ldg(pred + a) : 1.f;
+            for (int k = 0; k < N_LD; ++k) {
+                raw[k] = ld_raw32<T>(in + a);
+                wv[k] = PRED ? __ldg(pred + a) : 1.f;
+                a += (size_t)ROWS_PER_PASS * X;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < N_LD; ++k) {
+                const int ly = lr + k * ROWS_PER_PASS;
+                const int gy = reflect_index(y0 + (ly < IN_H ? ly : IN_H - 1) - RY, Y);
+                const size_t a = zoff + (size_t)gy * X + gx;
+                raw[k] = ld_raw32<T>(in + a);
+                wv[k] = PRED ? __ldg(pred + a) : 1.f;
+            }
         }
 #pragma unroll
         for (int k = 0; k < N_LD; ++k) {
             const int ly = lr + k * ROWS_PER_PASS;
-            float v = (float)raw[k];
+            float v = raw32_as_f32<T>(raw[k]);
             if (PRED) v = __fmul_rn(v, wv[k]);
             if (ly < IN_H) s_in[ly][lx] = v;
         }
@@ -272,10 +362,20 @@ lowpass_yx_kernel(const T* __restrict__ in, const float* __restrict__ pred, floa
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < YX_TY * TX; i += YX_THREADS) {
-        const int ly = i / TX, lx = i - ly * TX;
-        const int gy = y0 + ly, gx = x0 + lx;
-        if (gy < Y && gx < X) out[zoff + (size_t)gy * X + gx] = s_in[ly][lx];
+    {
+        // a warp stores whole rows (lane = column, then column + 32): one row pointer that advances by the warp count
+        constexpr int WARPS = YX_THREADS / 32;
+        const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+        const bool c0_ok = lane < TX && x0 + lane < X, c1_ok = lane + 32 < TX && x0 + lane + 32 < X;
+        float* po = out + zoff + (size_t)(y0 + wrp) * X + x0 + lane;
+#pragma unroll
+        for (int ly = wrp; ly < YX_TY; ly += WARPS) {
+            if (y0 + ly < Y) {
+                if (c0_ok) po[0] = s_in[ly][lane];
+                if (c1_ok) po[32] = s_in[ly][lane + 32];
+            }
+            po += (size_t)WARPS * X;
+        }
     }
 }
 
@@ -329,10 +429,20 @@ int run_z(m3d_ctx* ctx, const T* in, const float* pred, float* out, int Z, int Y
         return run_generic_axis<T, PRED>(ctx, in, pred, out, (size_t)Z * plane, Z, plane, W, st);
     KernelScope ks(ctx, KF_LOWPASS_Z, st);
     const Weights32 W32 = make_weights32(W);
+    // cp.async moves 4 bytes: a float column, or an aligned pair of uint16 columns (see lowpass_z_kernel)
+    const char* no_async = getenv("M3D_LOWPASS_NO_ASYNC");
+    const bool async = !(no_async && atoi(no_async) != 0) && plane >= 2 &&
+                       (sizeof(T) == 4 || (plane % 2 == 0 && reinterpret_cast<uintptr_t>(in) % 4 == 0)) &&
+                       reinterpret_cast<uintptr_t>(in) % sizeof(T) == 0 && (!PRED || reinterpret_cast<uintptr_t>(pred) % 4 == 0);
 #define M3D_Z_CASE(R_)                                                                                          \
     case R_:                                                                                                    \
-        if (ctx->lowpass_f32) lowpass_z_kernel<T, R_, PRED, true><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W, W32); \
-        else lowpass_z_kernel<T, R_, PRED, false><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W, W32);      \
+        if (ctx->lowpass_f32) {                                                                                 \
+            if (async) lowpass_z_kernel<T, R_, PRED, true, true><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W, W32);  \
+            else lowpass_z_kernel<T, R_, PRED, true, false><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W, W32);       \
+        } else {                                                                                                \
+            if (async) lowpass_z_kernel<T, R_, PRED, false, true><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W, W32); \
+            else lowpass_z_kernel<T, R_, PRED, false, false><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W, W32);      \
+        }                                                                                                       \
         break;
     switch (W.r) {
         M3D_Z_CASE(12)

@@ -1,5 +1,6 @@
 cd /root/repo
-python tools/lowpass_probe.py > gpurun_out/lp_plain.log 2>&1 || { tail -5 gpurun_out/lp_plain.log; exit 1; }
-cat gpurun_out/lp_plain.log
-ncu --set full --clock-control none --import-source on -k regex:lowpass --launch-skip 2 -c 2 -o gpurun_out/r2_lowpass -f python tools/lowpass_probe.py > gpurun_out/ncu_lp.log 2>&1
-tail -3 gpurun_out/ncu_lp.log
+timeout 900 python -m pytest tests/test_gpu_kernels.py -x -q -k "lowpass or low_pass" 2>&1 | tail -2
+timeout 120 python tools/lowpass_probe.py 2>&1 | tail -1
+M3D_LOWPASS_NO_ASYNC=1 timeout 120 python tools/lowpass_probe.py 2>&1 | tail -1
+timeout 120 python tools/lowpass_probe.py 100 2048 2048 float32 2>&1 | tail -1
+timeout 120 python tools/lowpass_probe.py 64 2048 2048 2>&1 | tail -1
