@@ -131,122 +131,101 @@ __device__ __forceinline__ double load_weighted(const T* in, const float* pred, 
 
 // ------------------------------------------------------------------ z pass, register ring
 // One thread per (y,x) column marching along z.  The 2R+1 samples of the window live in a register ring (loop
-// unrolled by the ring length so every index is static).
+// unrolled by the ring length so every index is static); the sample that enters the ring is requested PF planes
+// ahead and stays raw until it is needed.
 //
-// The sample that enters the ring must be requested several planes ahead, and HOW decides everything: with plain
-// loads into registers every prefetch LDG of the unrolled loop gets the same scoreboard, and the first use of the
-// OLDEST sample then waits for the YOUNGEST load too -- the queue is five deep in the source and one deep in the
-// hardware (ncu: 70 % of the stall samples on that conversion, float64 pipe 43 % busy; profiles/r2_lowpass.txt).
-// ASYNC = true stages the samples through shared memory with `cp.async` (LDGSTS): commit groups are COUNTED
-// (`cp.async.wait_group N`), so ZQ planes really are in flight per warp, each warp reads only what its own lanes
-// copied (no block barrier), and the address arithmetic leaves the float64 issue slots.  Needs 4-byte aligned pairs
-// of columns (uint16: even plane size and a 4-byte aligned base); ASYNC = false is the register-queue form for
-// everything else.
-constexpr int ZQ = 8;  // planes in flight per warp (ASYNC)
+// What decided the speed of this kernel (profiles/r2_lowpass.txt): the unrolled steps must be BRANCH-FREE.  With a
+// bound check and a reflection branch per step, ptxas gave every prefetch load the same scoreboard, so the first use of
+// the OLDEST sample waited for the YOUNGEST load as well -- a queue five deep in the source and one deep in the
+// hardware (70 % of the stall samples on that conversion, float64 pipe 43 % busy).  Whole chunks of 2R+1 outputs now run
+// without a branch: the plane address marches (forwards, then backwards through the reflected tail: a uniform select),
+// the loads rotate over several scoreboards, and a step is 37 float64 operations plus ~12 others.  The checked form is
+// kept for volumes thinner than the window; a partial last chunk only adds the bound check.  (Staging the samples through shared memory
+// with cp.async commit groups -- counted waits, eight planes in flight -- was measured too: 1.40 ms against 1.22 ms.)
 
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+// f(integral_constant<int, 0>) ... f(integral_constant<int, N - 1>): a loop whose index is a compile-time constant
+template <int N, int I = 0, typename F>
+__device__ __forceinline__ void unroll_steps(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        unroll_steps<N, I + 1>(f);
+    }
 }
 
-template <typename T, int R, bool PRED, bool F32, bool ASYNC>
+template <typename T, int R, bool PRED, bool F32>
 __global__ void __launch_bounds__(128, 5)
 lowpass_z_kernel(const T* __restrict__ in, const float* __restrict__ pred, float* __restrict__ out,
                  int Z, size_t plane, Weights W, Weights32 W32) {
     constexpr int RING = 2 * R + 1;
-    constexpr int PF = ASYNC ? 1 : ((RING % 5 == 0) ? 5 : ((RING % 3 == 0) ? 3 : 1));  // divides the unroll length
-    __shared__ __align__(16) T s_pre[ASYNC ? ZQ : 1][128];
-    __shared__ __align__(16) float s_w[(ASYNC && PRED) ? ZQ : 1][128];
-    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = c < plane;
-    if (!ASYNC && !active) return;
-    if (ASYNC && !active) c = plane - 2 + (threadIdx.x & 1);  // a valid column: the warp stays whole for its barriers
+    constexpr int PF = (RING % 5 == 0) ? 5 : ((RING % 3 == 0) ? 3 : 1);  // divides the unroll length
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= plane) return;
     using A = typename std::conditional<F32, float, double>::type;
     A ring[RING];
-    uint32_t pre[PF];  // register queue (ASYNC = false): samples stay raw (ld_raw32), converting them on arrival
-    float pre_w[PF];   // would make the warp wait on the very load the prefetch is meant to hide
+    uint32_t pre[PF];  // prefetched samples stay raw (ld_raw32): converting them on arrival would make the
+    float pre_w[PF];   // warp wait on the very load the prefetch is meant to hide
     // slot of ext[j] is (j + R) mod RING
 #pragma unroll
     for (int i = 0; i < 2 * R; ++i)
         ring[i] = (A)load_weighted<T, PRED>(in, pred, (size_t)reflect_index(i - R, Z) * plane + c);
-    // who copies: 4 bytes per cp.async, i.e. one float column or a pair of uint16 columns (the even lane's)
-    const bool copier = sizeof(T) == 4 || (threadIdx.x & 1) == 0;
-    auto stage_plane = [&](int step) {  // ASYNC: request the sample that enters the ring at output `step`
-        if (step < Z) {
-            const size_t a = (size_t)reflect_high(step + R, Z) * plane + c;
-            if (copier) cp_async4(&s_pre[step % ZQ][threadIdx.x], in + a);
-            if (PRED) cp_async4(&s_w[step % ZQ][threadIdx.x], pred + a);
-        }
-        cp_async_commit();  // (an empty group past the end keeps the count in step)
-    };
-    if constexpr (ASYNC) {
 #pragma unroll
-        for (int i = 0; i < ZQ; ++i) stage_plane(i);
-    } else {
-#pragma unroll
-        for (int i = 0; i < PF; ++i) {
-            const size_t a = (size_t)reflect_index(R + i, Z) * plane + c;
-            pre[i] = ld_raw32<T>(in + a);
-            pre_w[i] = PRED ? __ldg(pred + a) : 1.f;
-        }
+    for (int i = 0; i < PF; ++i) {
+        const size_t a = (size_t)reflect_index(R + i, Z) * plane + c;
+        pre[i] = ld_raw32<T>(in + a);
+        pre_w[i] = PRED ? __ldg(pred + a) : 1.f;
     }
-    // marching pointers: the sample entering the prefetch queue and the output plane advance by one plane per step
-    // (the reflected tail past the last plane takes the general address)
-    size_t a_fwd = (size_t)(R + PF) * plane + c;  // address of plane o + R + PF while that plane exists
+    // marching address of (reflected) plane o + R + PF: valid while that index stays below 2 Z
+    size_t a_fwd = (size_t)reflect_index(R + PF, Z) * plane + c;
     float* po = out + c;
-    for (int o0 = 0; o0 < Z; o0 += RING) {
-#pragma unroll
-        for (int u = 0; u < RING; ++u) {
-            const int o = o0 + u;
-            if (o < Z) {
-                if constexpr (ASYNC) {
-                    cp_async_wait<ZQ - 1>();  // the group of step o has landed (ZQ - 1 younger ones may be pending)
-                    __syncwarp();             // ... for every lane of the warp: pairs share a copy
-                    float v;
-                    if constexpr (sizeof(T) == 4) v = raw32_as_f32<T>(reinterpret_cast<const uint32_t&>(s_pre[o % ZQ][threadIdx.x]));
-                    else v = (float)s_pre[o % ZQ][threadIdx.x];
-                    if (PRED) v = __fmul_rn(v, s_w[o % ZQ][threadIdx.x]);
-                    ring[(u + 2 * R) % RING] = (A)v;
-                    __syncwarp();             // both lanes of a pair have read before the slot is requested again
-                    stage_plane(o + ZQ);
-                } else {
-                    {
-                        float v = raw32_as_f32<T>(pre[u % PF]);
-                        if (PRED) v = __fmul_rn(v, pre_w[u % PF]);
-                        ring[(u + 2 * R) % RING] = (A)v;
-                    }
-                    {   // the sample for output o + PF (reflect keeps the address valid past the end)
-                        const int zi = o + R + PF;
-                        const size_t a = zi < Z ? a_fwd : (size_t)reflect_high(zi, Z) * plane + c;
-                        a_fwd += plane;
-                        pre[u % PF] = ld_raw32<T>(in + a);
-                        if (PRED) pre_w[u % PF] = __ldg(pred + a);
-                    }
-                }
-                if constexpr (F32) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (int jj = -R; jj <= R; ++jj) acc = __fmaf_rn(ring[(u + R + jj + RING) % RING], W32.w[jj + R], acc);
-                    if (!ASYNC || active) *po = acc;
-                } else {
-                    double acc = __dmul_rn(ring[(u + R) % RING], W.w[R]);
-#pragma unroll
-                    for (int jj = -R; jj < 0; ++jj) {
-                        double pr = __dadd_rn(ring[(u + R + jj + RING) % RING], ring[(u + R - jj) % RING]);
-                        acc = __dadd_rn(acc, __dmul_rn(pr, W.w[jj + R]));
-                    }
-                    if (!ASYNC || active) *po = (float)acc;
-                }
-                po += plane;
-            }
+    // one output step.  CHECK: o may lie past the end (partial last chunk).  MARCH: o + R + PF + 1 < 2 Z holds for every
+    // o < Z, so the address of the reflected plane marches and needs no division.
+    auto step = [&](auto check_tag, auto march_tag, auto u_tag, int o) {
+        constexpr bool CHECK = decltype(check_tag)::value, MARCH = decltype(march_tag)::value;
+        constexpr int u = decltype(u_tag)::value;
+        if (CHECK && o >= Z) return;
+        {
+            float v = raw32_as_f32<T>(pre[u % PF]);
+            if (PRED) v = __fmul_rn(v, pre_w[u % PF]);
+            ring[(u + 2 * R) % RING] = (A)v;
         }
+        {   // the sample for output o + PF
+            const int zi = o + R + PF;
+            size_t a;
+            if (MARCH) {
+                a = a_fwd;  // next: one plane on, the last plane once more (reflection), then back down
+                a_fwd = zi + 1 < Z ? a_fwd + plane : (zi + 1 == Z ? a_fwd : a_fwd - plane);
+            } else {
+                a = (size_t)reflect_high(zi, Z) * plane + c;
+            }
+            pre[u % PF] = ld_raw32<T>(in + a);
+            if (PRED) pre_w[u % PF] = __ldg(pred + a);
+        }
+        if constexpr (F32) {
+            float acc = 0.f;
+#pragma unroll
+            for (int jj = -R; jj <= R; ++jj) acc = __fmaf_rn(ring[(u + R + jj + RING) % RING], W32.w[jj + R], acc);
+            *po = acc;
+        } else {
+            double acc = __dmul_rn(ring[(u + R) % RING], W.w[R]);
+#pragma unroll
+            for (int jj = -R; jj < 0; ++jj) {
+                double pr = __dadd_rn(ring[(u + R + jj + RING) % RING], ring[(u + R - jj) % RING]);
+                acc = __dadd_rn(acc, __dmul_rn(pr, W.w[jj + R]));
+            }
+            *po = (float)acc;
+        }
+        po += plane;
+    };
+    auto chunk = [&](auto check_tag, auto march_tag, int o0) {
+        unroll_steps<RING>([&](auto u_tag) { step(check_tag, march_tag, u_tag, o0 + decltype(u_tag)::value); });
+    };
+    int o0 = 0;
+    if (Z >= R + PF + 1) {
+        for (; o0 + RING <= Z; o0 += RING) chunk(std::false_type{}, std::true_type{}, o0);
+        if (o0 < Z) chunk(std::true_type{}, std::true_type{}, o0);
+    } else {
+        for (; o0 < Z; o0 += RING) chunk(std::true_type{}, std::false_type{}, o0);
     }
-    if constexpr (ASYNC) cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------ fused y,x pass, shared tile
@@ -265,7 +244,7 @@ constexpr int YX_THREADS = 256;
 constexpr int YX_BLK = 8;            // outputs per work item
 
 template <typename T, int RY, int RX, bool PRED, bool F32>
-__global__ void __launch_bounds__(YX_THREADS)
+__global__ void __launch_bounds__(YX_THREADS, F32 ? 4 : 5)
 lowpass_yx_kernel(const T* __restrict__ in, const float* __restrict__ pred, float* __restrict__ out,
                   int Y, int X, Weights WY, Weights WX, Weights32 WY32, Weights32 WX32) {
     using A = typename std::conditional<F32, float, double>::type;
@@ -275,6 +254,7 @@ lowpass_yx_kernel(const T* __restrict__ in, const float* __restrict__ pred, floa
     static_assert(YX_TY % YX_BLK == 0 && TX > 0, "tile must split into 8-output items");
     __shared__ float s_in[IN_H][YX_STRIDE];
     __shared__ float s_mid[YX_TY][YX_STRIDE];
+    float (*s_out)[YX_STRIDE] = s_in;  // output stage (the input tile is dead by then)
     const int x0 = blockIdx.x * TX;
     const int y0 = blockIdx.y * YX_TY;
     const size_t zoff = (size_t)blockIdx.z * (size_t)Y * X;
@@ -351,13 +331,13 @@ lowpass_yx_kernel(const T* __restrict__ in, const float* __restrict__ pred, floa
                 float acc = 0.f;
 #pragma unroll
                 for (int jj = -RX; jj <= RX; ++jj) acc = __fmaf_rn(v[o + RX + jj], WX32.w[jj + RX], acc);
-                s_in[row][c0 + o] = acc;  // the input tile is dead: reuse it as the output stage
+                s_out[row][c0 + o] = acc;  // the input tile is dead: reuse it as the output stage
             } else {
                 double acc = __dmul_rn(v[o + RX], WX.w[RX]);
 #pragma unroll
                 for (int jj = -RX; jj < 0; ++jj)
                     acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v[o + RX + jj], v[o + RX - jj]), WX.w[jj + RX]));
-                s_in[row][c0 + o] = (float)acc;  // the input tile is dead: reuse it as the output stage
+                s_out[row][c0 + o] = (float)acc;  // the input tile is dead: reuse it as the output stage
             }
         }
     }
@@ -371,8 +351,8 @@ lowpass_yx_kernel(const T* __restrict__ in, const float* __restrict__ pred, floa
 #pragma unroll
         for (int ly = wrp; ly < YX_TY; ly += WARPS) {
             if (y0 + ly < Y) {
-                if (c0_ok) po[0] = s_in[ly][lane];
-                if (c1_ok) po[32] = s_in[ly][lane + 32];
+                if (c0_ok) po[0] = s_out[ly][lane];
+                if (c1_ok) po[32] = s_out[ly][lane + 32];
             }
             po += (size_t)WARPS * X;
         }
@@ -429,20 +409,10 @@ int run_z(m3d_ctx* ctx, const T* in, const float* pred, float* out, int Z, int Y
         return run_generic_axis<T, PRED>(ctx, in, pred, out, (size_t)Z * plane, Z, plane, W, st);
     KernelScope ks(ctx, KF_LOWPASS_Z, st);
     const Weights32 W32 = make_weights32(W);
-    // cp.async moves 4 bytes: a float column, or an aligned pair of uint16 columns (see lowpass_z_kernel)
-    const char* no_async = getenv("M3D_LOWPASS_NO_ASYNC");
-    const bool async = !(no_async && atoi(no_async) != 0) && plane >= 2 &&
-                       (sizeof(T) == 4 || (plane % 2 == 0 && reinterpret_cast<uintptr_t>(in) % 4 == 0)) &&
-                       reinterpret_cast<uintptr_t>(in) % sizeof(T) == 0 && (!PRED || reinterpret_cast<uintptr_t>(pred) % 4 == 0);
 #define M3D_Z_CASE(R_)                                                                                          \
     case R_:                                                                                                    \
-        if (ctx->lowpass_f32) {                                                                                 \
-            if (async) lowpass_z_kernel<T, R_, PRED, true, true><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W, W32);  \
-            else lowpass_z_kernel<T, R_, PRED, true, false><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W, W32);       \
-        } else {                                                                                                \
-            if (async) lowpass_z_kernel<T, R_, PRED, false, true><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W, W32); \
-            else lowpass_z_kernel<T, R_, PRED, false, false><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W, W32);      \
-        }                                                                                                       \
+        if (ctx->lowpass_f32) lowpass_z_kernel<T, R_, PRED, true><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W, W32); \
+        else lowpass_z_kernel<T, R_, PRED, false><<<blocks, 128, 0, st>>>(in, pred, out, Z, plane, W, W32);      \
         break;
     switch (W.r) {
         M3D_Z_CASE(12)
