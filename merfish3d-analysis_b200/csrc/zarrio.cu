@@ -196,13 +196,33 @@ __host__ __device__ inline uint32_t le32_hd(const uint8_t* p) {
     return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 }
 
+// Up to FRAME_BATCH_MAX chunks per launch: the frames of several slots decoded by ONE grid.  A chunk is only 64 warps, and
+// the device runs at most 32 streams' kernels side by side (hardware work queues), so one launch per chunk leaves most of
+// the GPU idle however many slots are in flight; a launch over G chunks puts G x 64 latency chains behind each queue.
+constexpr int FRAME_BATCH_MAX = 8;
+struct FrameBatch {
+    const uint8_t* frame[FRAME_BATCH_MAX];
+    int64_t frame_len[FRAME_BATCH_MAX];
+    uint8_t* out[FRAME_BATCH_MAX];
+    uint8_t* lit[FRAME_BATCH_MAX];  // zstd only: literal scratch of the chunk
+    int splits[FRAME_BATCH_MAX];
+    int first_block[FRAME_BATCH_MAX + 1];  // thread blocks of chunk g: [first_block[g], first_block[g + 1])
+    int n;
+};
+
 // A Blosc-1 frame of LZ4 streams, decoded on the device: one warp per stream (block j, split s).  `frame` is the
 // chunk file as it sits on disk (the host only checked its 16-byte header); the warp finds its stream by
 // walking the block's length prefixes, then decodes -- or copies a stored stream -- into its place of the
 // still-shuffled chunk image `out`.  Anything inconsistent sets *error and the warp leaves.
-__global__ void __launch_bounds__(128) blosc_lz4_decode_kernel(const uint8_t* frame, int64_t frame_len, uint8_t* out,
-                                                                int splits_per_block, int* __restrict__ error) {
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+__global__ void __launch_bounds__(128) blosc_lz4_decode_kernel(const __grid_constant__ FrameBatch batch,
+                                                                int* __restrict__ error) {
+    int g = 0;
+    while (g + 1 < batch.n && (int)blockIdx.x >= batch.first_block[g + 1]) ++g;
+    const uint8_t* frame = batch.frame[g];
+    const int64_t frame_len = batch.frame_len[g];
+    uint8_t* out = batch.out[g];
+    const int splits_per_block = batch.splits[g];
+    const int64_t warp = ((int64_t)((int)blockIdx.x - batch.first_block[g]) * blockDim.x + threadIdx.x) >> 5;
     const int typesize = frame[3], flags = frame[2];
     const int64_t nbytes = le32_hd(frame + 4), blocksize = le32_hd(frame + 8);
     const int64_t nblocks = (nbytes + blocksize - 1) / blocksize, leftover = nbytes % blocksize;
@@ -286,21 +306,7 @@ __global__ void __launch_bounds__(64) blosc_zstd_decode_kernel(const uint8_t* fr
 
 // Second device version (M3D_ZARR_GPU_ZSTD=2; zstd_lanes.cuh): the warp works as a team -- one lane per Huffman
 // stream, shared copies.  Pinned on the host through the one-lane policy; NOT yet run on a device.
-// Up to ZSTD_BATCH_MAX chunks per launch: the frames of several slots decoded by ONE grid.  A chunk is only 64 warps, and
-// the device runs at most 32 streams' kernels side by side (hardware work queues), so one launch per chunk leaves most of
-// the GPU idle however many slots are in flight; a launch over G chunks puts G x 64 latency chains behind each queue.
-constexpr int ZSTD_BATCH_MAX = 8;
-struct ZstdBatch {
-    const uint8_t* frame[ZSTD_BATCH_MAX];
-    int64_t frame_len[ZSTD_BATCH_MAX];
-    uint8_t* out[ZSTD_BATCH_MAX];
-    uint8_t* lit[ZSTD_BATCH_MAX];
-    int splits[ZSTD_BATCH_MAX];
-    int first_block[ZSTD_BATCH_MAX + 1];  // thread blocks (two warps each) of chunk g: [first_block[g], first_block[g + 1])
-    int n;
-};
-
-__global__ void __launch_bounds__(64) blosc_zstd_decode_kernel_v2(const __grid_constant__ ZstdBatch batch,
+__global__ void __launch_bounds__(64) blosc_zstd_decode_kernel_v2(const __grid_constant__ FrameBatch batch,
                                                                   int* __restrict__ error) {
     __shared__ m3d_zstd::Work work[2];
     __shared__ m3d_zstd::LitPlan plans[2];
@@ -1192,6 +1198,7 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
     // and it is the number of such kernels running side by side (one stream per slot) that fills the GPU.
     int n_slots = 3 * workers;
     bool batch_zstd = false;
+    int batch_default = 1;
     {
         // What will decode the frames?  The first chunk's Blosc header tells.  When the device does, the host threads only
         // copy chunk files from the page cache into pinned slots, and more than ~10 of them slow each other down
@@ -1214,19 +1221,20 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
         const bool on_device = (inner == BLOSC_LZ4 && dev_lz4) || (inner == BLOSC_ZSTD && dev_zstd);
         if (on_device && getenv("M3D_IO_THREADS") == nullptr && workers > 10) workers = 10;
         if (on_device) n_slots = inner == BLOSC_LZ4 ? 32 : 96;
-        batch_zstd = on_device && inner == BLOSC_ZSTD;
+        batch_zstd = on_device;  // (name kept: chunks per decode launch, both device codecs)
+        batch_default = inner == BLOSC_LZ4 ? 2 : 4;
     }
     if (workers > n_chunks) workers = n_chunks;
     if (const char* e = getenv("M3D_ZARR_SLOTS")) {  // tuning hook: slots (= chunks in flight) independent of the threads
         const int v = atoi(e);
         if (v >= 1) n_slots = v > 128 ? 128 : v;
     }
-    int batch = 1;  // chunks per decode launch (device zstd only)
+    int batch = 1;  // chunks per decode launch (device-decoded frames)
     if (batch_zstd) {
-        batch = 4;
+        batch = batch_default;  // measured: zstd 4 / 96 slots, lz4 2 / 32 slots (profiles/r2_zstd_device.txt)
         if (const char* e = getenv("M3D_ZARR_BATCH")) {
             const int v = atoi(e);
-            if (v >= 1) batch = v > ZSTD_BATCH_MAX ? ZSTD_BATCH_MAX : v;
+            if (v >= 1) batch = v > FRAME_BATCH_MAX ? FRAME_BATCH_MAX : v;
         }
     }
     while (n_slots > 3 && (size_t)n_slots * slot_bytes > ((size_t)1 << 30)) --n_slots;
@@ -1413,7 +1421,7 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
         return e == cudaSuccess;
     };
     // Chunks are issued in aligned groups of `batch` consecutive chunks (= consecutive slots) on the stream of the group's
-    // first slot: the device-zstd frames of a group go through ONE decode launch (ZstdBatch), everything else as before.
+    // first slot: the device-zstd frames of a group go through ONE decode launch (FrameBatch), everything else as before.
     for (int j0 = 0; j0 < n_chunks && rc == M3D_OK; j0 += batch) {
         const int j1 = j0 + batch < n_chunks ? j0 + batch : n_chunks;
         {
@@ -1432,37 +1440,48 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
             cuda_ok(cudaStreamWaitEvent(q, R->begin, 0));
             joined[s0] = 1;
         }
-        ZstdBatch zb;
-        zb.n = 0;
-        zb.first_block[0] = 0;
-        for (int j = j0; j < j1 && rc == M3D_OK; ++j) {  // the group's compressed frames cross PCIe, then one launch
-            if (kind[j] != GPU_LZ4 || !on_gpu_zstd[j] || gpu_zstd_mode != 2) continue;
+        // the group's compressed frames cross PCIe, then one launch per codec decodes them
+        FrameBatch zb, lb;
+        zb.n = lb.n = 0;
+        zb.first_block[0] = lb.first_block[0] = 0;
+        for (int j = j0; j < j1 && rc == M3D_OK; ++j) {
+            if (kind[j] != GPU_LZ4 || (on_gpu_zstd[j] && gpu_zstd_mode != 2)) continue;
             const int s = j % n_slots;
             const ChunkGeom g = geom_of(chunks[j], info[j]);
             const int64_t warps = (g.nbytes + frame_blocksize[j] - 1) / frame_blocksize[j] * splits[j];
-            const size_t need = (size_t)warps * m3d_zstd::MAX_BLOCK;
-            if (R->dev_lit_bytes[s] < need) {
-                cuda_ok(cudaStreamSynchronize(q));
-                if (R->dev_lit[s]) cudaFree(R->dev_lit[s]);
-                R->dev_lit[s] = nullptr;
-                R->dev_lit_bytes[s] = 0;
-                if (cuda_ok(cudaMalloc(&R->dev_lit[s], need))) R->dev_lit_bytes[s] = need;
+            if (on_gpu_zstd[j]) {
+                const size_t need = (size_t)warps * m3d_zstd::MAX_BLOCK;
+                if (R->dev_lit_bytes[s] < need) {
+                    cuda_ok(cudaStreamSynchronize(q));
+                    if (R->dev_lit[s]) cudaFree(R->dev_lit[s]);
+                    R->dev_lit[s] = nullptr;
+                    R->dev_lit_bytes[s] = 0;
+                    if (cuda_ok(cudaMalloc(&R->dev_lit[s], need))) R->dev_lit_bytes[s] = need;
+                }
             }
             if (rc == M3D_OK &&
                 cuda_ok(cudaMemcpyAsync(R->dev_comp[s], R->pinned[s], (size_t)comp_len[j], cudaMemcpyHostToDevice, q))) {
-                const int i = zb.n++;
-                zb.frame[i] = reinterpret_cast<const uint8_t*>(R->dev_comp[s]);
-                zb.frame_len[i] = comp_len[j];
-                zb.out[i] = reinterpret_cast<uint8_t*>(R->dev[s]);
-                zb.lit[i] = reinterpret_cast<uint8_t*>(R->dev_lit[s]);
-                zb.splits[i] = splits[j];
-                zb.first_block[i + 1] = zb.first_block[i] + (int)((warps + 1) / 2);
+                FrameBatch& fb = on_gpu_zstd[j] ? zb : lb;
+                const int i = fb.n++;
+                fb.frame[i] = reinterpret_cast<const uint8_t*>(R->dev_comp[s]);
+                fb.frame_len[i] = comp_len[j];
+                fb.out[i] = reinterpret_cast<uint8_t*>(R->dev[s]);
+                fb.lit[i] = on_gpu_zstd[j] ? reinterpret_cast<uint8_t*>(R->dev_lit[s]) : nullptr;
+                fb.splits[i] = splits[j];
+                // thread blocks: two warps (zstd) / four warps (lz4) each
+                fb.first_block[i + 1] = fb.first_block[i] + (int)(on_gpu_zstd[j] ? (warps + 1) / 2 : (warps + 3) / 4);
             }
         }
         if (rc == M3D_OK && zb.n > 0) {
             any_gpu = true;
             M3D_LAUNCH(ctx, KF_ZARR_ZSTD, q,
                        blosc_zstd_decode_kernel_v2<<<(unsigned)zb.first_block[zb.n], 64, 0, q>>>(zb, R->d_error));
+            cuda_ok(cudaGetLastError());
+        }
+        if (rc == M3D_OK && lb.n > 0) {
+            any_gpu = true;
+            M3D_LAUNCH(ctx, KF_ZARR_LZ4, q,
+                       blosc_lz4_decode_kernel<<<(unsigned)lb.first_block[lb.n], 128, 0, q>>>(lb, R->d_error));
             cuda_ok(cudaGetLastError());
         }
         for (int j = j0; j < j1 && rc == M3D_OK; ++j) {
@@ -1472,35 +1491,27 @@ extern "C" int m3d_zarr_read_chunks(m3d_ctx* ctx, int n_chunks, const m3d_zarr_c
                 rc = launch_fill(ctx, c, q);
             } else {
                 const ChunkGeom g = geom_of(c, info[j]);
-                if (kind[j] == GPU_LZ4 && on_gpu_zstd[j] && gpu_zstd_mode == 2) {
+                if (kind[j] == GPU_LZ4 && !(on_gpu_zstd[j] && gpu_zstd_mode != 2)) {
                     // decoded by the group's launch above
-                } else if (kind[j] == GPU_LZ4) {
+                } else if (kind[j] == GPU_LZ4) {  // zstd mode 1: the lane-serial first version, one launch per chunk
                     any_gpu = true;
                     const int64_t nblocks = (g.nbytes + frame_blocksize[j] - 1) / frame_blocksize[j];
                     const int64_t warps = nblocks * splits[j];
-                    if (on_gpu_zstd[j]) {  // mode 1: the lane-serial first version, one launch per chunk
-                        const size_t need = (size_t)warps * m3d_zstd::MAX_BLOCK;
-                        if (R->dev_lit_bytes[s] < need) {
-                            cuda_ok(cudaStreamSynchronize(q));
-                            if (R->dev_lit[s]) cudaFree(R->dev_lit[s]);
-                            R->dev_lit[s] = nullptr;
-                            R->dev_lit_bytes[s] = 0;
-                            if (cuda_ok(cudaMalloc(&R->dev_lit[s], need))) R->dev_lit_bytes[s] = need;
-                        }
-                        if (rc == M3D_OK &&
-                            cuda_ok(cudaMemcpyAsync(R->dev_comp[s], R->pinned[s], (size_t)comp_len[j], cudaMemcpyHostToDevice, q))) {
-                            M3D_LAUNCH(ctx, KF_ZARR_ZSTD, q,
-                                       blosc_zstd_decode_kernel<<<(unsigned)((warps + 1) / 2), 64, 0, q>>>(
-                                           reinterpret_cast<const uint8_t*>(R->dev_comp[s]), comp_len[j],
-                                           reinterpret_cast<uint8_t*>(R->dev[s]), splits[j],
-                                           reinterpret_cast<uint8_t*>(R->dev_lit[s]), R->d_error));
-                            cuda_ok(cudaGetLastError());
-                        }
-                    } else if (cuda_ok(cudaMemcpyAsync(R->dev_comp[s], R->pinned[s], (size_t)comp_len[j], cudaMemcpyHostToDevice, q))) {
-                        M3D_LAUNCH(ctx, KF_ZARR_LZ4, q,
-                                   blosc_lz4_decode_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, q>>>(
+                    const size_t need = (size_t)warps * m3d_zstd::MAX_BLOCK;
+                    if (R->dev_lit_bytes[s] < need) {
+                        cuda_ok(cudaStreamSynchronize(q));
+                        if (R->dev_lit[s]) cudaFree(R->dev_lit[s]);
+                        R->dev_lit[s] = nullptr;
+                        R->dev_lit_bytes[s] = 0;
+                        if (cuda_ok(cudaMalloc(&R->dev_lit[s], need))) R->dev_lit_bytes[s] = need;
+                    }
+                    if (rc == M3D_OK &&
+                        cuda_ok(cudaMemcpyAsync(R->dev_comp[s], R->pinned[s], (size_t)comp_len[j], cudaMemcpyHostToDevice, q))) {
+                        M3D_LAUNCH(ctx, KF_ZARR_ZSTD, q,
+                                   blosc_zstd_decode_kernel<<<(unsigned)((warps + 1) / 2), 64, 0, q>>>(
                                        reinterpret_cast<const uint8_t*>(R->dev_comp[s]), comp_len[j],
-                                       reinterpret_cast<uint8_t*>(R->dev[s]), splits[j], R->d_error));
+                                       reinterpret_cast<uint8_t*>(R->dev[s]), splits[j],
+                                       reinterpret_cast<uint8_t*>(R->dev_lit[s]), R->d_error));
                         cuda_ok(cudaGetLastError());
                     }
                 } else {
