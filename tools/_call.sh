@@ -1,4 +1,5 @@
 cd /root/repo
-timeout 600 python -m pytest tests/test_gpu_zarr_store.py -x -q 2>&1 | tail -2
-timeout 600 python tools/zarr_io_bench.py --compression blosc-lz4 --sweep "M3D_ZARR_BATCH=1,M3D_ZARR_SLOTS=32;M3D_ZARR_BATCH=2,M3D_ZARR_SLOTS=32;M3D_ZARR_BATCH=4,M3D_ZARR_SLOTS=32;M3D_ZARR_BATCH=2,M3D_ZARR_SLOTS=64;M3D_ZARR_BATCH=4,M3D_ZARR_SLOTS=64;M3D_ZARR_BATCH=4,M3D_ZARR_SLOTS=96;M3D_ZARR_BATCH=8,M3D_ZARR_SLOTS=96;M3D_ZARR_BATCH=2,M3D_ZARR_SLOTS=48;M3D_ZARR_BATCH=4,M3D_ZARR_SLOTS=64,M3D_IO_THREADS=14" --z 96 --out gpurun_out/lz4_batch_sweep.json 2>&1 | grep -v "^{" | tail -12
-timeout 600 python tools/zarr_io_bench.py --compression blosc-lz4 --sweep "M3D_ZARR_BATCH=1,M3D_ZARR_SLOTS=32;M3D_ZARR_BATCH=2,M3D_ZARR_SLOTS=64;M3D_ZARR_BATCH=4,M3D_ZARR_SLOTS=64;M3D_ZARR_BATCH=4,M3D_ZARR_SLOTS=96" --z 32 --out gpurun_out/lz4_batch_sweep2.json 2>&1 | grep -v "^{" | tail -6
+timeout 1500 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -4
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 1200 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_n1_c.json 2> gpurun_out/r2_bench_n1_c.err; echo bench rc=$?
+tail -c 600 gpurun_out/r2_bench_n1_c.err
