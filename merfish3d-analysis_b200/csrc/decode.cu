@@ -639,7 +639,7 @@ struct FgSink {  // optional hand-off to the labelling / regionprops stages (m3d
 };
 
 template <typename T, int NB>
-__global__ void __launch_bounds__(SEARCH_THREADS)
+__global__ void __launch_bounds__(SEARCH_THREADS, 5)  // 96 registers, 20 warps per SM: -4 % in the dense regime, 6 per SM is slower
 decode_search_kernel(const T* __restrict__ stack, size_t n_vox, DecodeParams P, int16_t* __restrict__ decoded,
                      const uint32_t* __restrict__ cand, const unsigned int* __restrict__ cand_count, FgSink sink) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -815,7 +815,7 @@ int launch_decode(m3d_ctx* ctx, const T* stack, size_t n_vox, int16_t* decoded, 
     if (rc) return rc;
     auto kern = decode_search_kernel<T, NB>;
     M3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int blocks = ctx->num_sms * 8;
+    const int blocks = ctx->num_sms * 10;  // two rounds of the 5 resident blocks per SM
     M3D_LAUNCH(ctx, KF_DECODE_SEARCH, st,
                kern<<<blocks, SEARCH_THREADS, smem, st>>>(stack, n_vox, P, decoded, cand, cand_count, sink));
     M3D_CHECK_LAUNCH();

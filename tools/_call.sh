@@ -1,5 +1,11 @@
 cd /root/repo
-timeout 1500 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -4
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 1200 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_n1_c.json 2> gpurun_out/r2_bench_n1_c.err; echo bench rc=$?
-tail -c 600 gpurun_out/r2_bench_n1_c.err
+cp merfish3d-analysis_b200/libm3d_b200.so /tmp/lib_A.so
+for v in A mb5 mb6; do
+  if [ $v != A ]; then cp merfish3d-analysis_b200/build/lib_$v.so merfish3d-analysis_b200/libm3d_b200.so; fi
+  echo "== variant $v"
+  timeout 300 python tools/dense_regime.py 2>&1 | tail -1
+  timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu --extras all_foreground 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('step ms', d['ms_per_step'], d['roofline']['kernel_ms_per_step'].get('decode_search_kernel'), 'all_fg', d['extras']['all_foreground']['ms_per_decode'])"
+done
+cp /tmp/lib_A.so merfish3d-analysis_b200/libm3d_b200.so
