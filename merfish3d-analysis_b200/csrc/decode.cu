@@ -157,8 +157,9 @@ struct SearchSmem {
     float* g;            // [K]
     uint32_t* hkeys;     // [1 << hash_bits] (mode 2)
     uint32_t* masks;     // [round_up(K, 8)] on-bit masks, 0 beyond K (mode 2, tensor-core on-bit sums)
-    uint32_t* cand_bits; // [SEARCH_THREADS][ceil(K/32)] per-voxel candidate sets marked by the tensor-core pass (mode 2)
     uint4* afrag;        // [ceil(K/16)][KS][32] A fragments (codeword rows x bit columns, bf16 0/1) of the on-bit matrix
+    uint32_t* cand_bits; // [warps][ceil(K/16)][4][4] ballot words of the tensor-core marking pass (mode 2)
+    uint16_t* cand_cum;  // [warps][ceil(K/16)][32] per voxel: marked codewords in the tiles before tile i
     int16_t* hvals;      // [1 << hash_bits]
     uint8_t* on;         // [K][max_on]
 };
@@ -167,7 +168,8 @@ static size_t search_smem_bytes(int nb, const DecodeParams& P) {
     size_t n = (size_t)(nb + 1) * XS_STRIDE * 4;
     if (P.mode >= 1) n += (size_t)P.K * 8 + (size_t)P.K * P.max_on;
     if (P.mode == 2)
-        n += ((size_t)1 << P.hash_bits) * 6 + (size_t)((P.K + 7) & ~7) * 4 + (size_t)SEARCH_THREADS * ((P.K + 31) / 32) * 4 +
+        n += ((size_t)1 << P.hash_bits) * 6 + (size_t)((P.K + 7) & ~7) * 4 +
+             (size_t)(SEARCH_THREADS / 32) * ((P.K + 15) / 16) * (64 + 64) +
              (size_t)((P.K + 15) / 16) * ((nb + 15) / 16) * 32 * 16 + 16;
     return n + 16;
 }
@@ -181,6 +183,7 @@ __device__ __forceinline__ SearchSmem stage_codebook(unsigned char* smem, const 
     s.hkeys = nullptr;
     s.masks = nullptr;
     s.cand_bits = nullptr;
+    s.cand_cum = nullptr;
     s.afrag = nullptr;
     s.hvals = nullptr;
     s.on = nullptr;
@@ -196,21 +199,18 @@ __device__ __forceinline__ SearchSmem stage_codebook(unsigned char* smem, const 
     if (P.mode == 2) {
         const int hs = 1 << P.hash_bits;
         const int kpad = (P.K + 7) & ~7;
-        s.hkeys = reinterpret_cast<uint32_t*>(p);
-        s.masks = s.hkeys + hs;
-        s.cand_bits = s.masks + kpad;
-        uint32_t* after_bits = s.cand_bits + SEARCH_THREADS * ((P.K + 31) / 32);
-        while (reinterpret_cast<uintptr_t>(after_bits) & 15u) ++after_bits;  // 16-byte alignment for the fragment table
-        s.afrag = reinterpret_cast<uint4*>(after_bits);
         constexpr int KS = (NB + 15) / 16;
         const int n_mt = (P.K + 15) >> 4;
+        while (reinterpret_cast<uintptr_t>(p) & 15u) ++p;  // 16-byte alignment for the fragment table and the ballot words
+        s.afrag = reinterpret_cast<uint4*>(p);
         // A fragment of mma.m16n8k16 (row-major 16 x 16, bf16): lane (g = lane / 4, t = lane % 4) holds
         // a0 = (row g, cols 2t, 2t+1), a1 = (row g+8, same cols), a2 = (row g, cols 2t+8, 2t+9), a3 = (row g+8, ...);
-        // rows = codewords 16 i + ..., columns = bits 16 ks + ...; 0x3F80 = bf16(1.0); rows >= K are zero
+        // columns = bits 16 ks + ...; 0x3F80 = bf16(1.0); rows >= K are zero.  Row g of tile i is codeword 16 i + 2 g and
+        // row g + 8 is codeword 16 i + 2 g + 1, so that the ballot words of the marking pass interleave into ascending k.
         for (int e = threadIdx.x; e < n_mt * KS * 32; e += SEARCH_THREADS) {
             const int lane = e & 31, ks = (e >> 5) % KS, i = (e >> 5) / KS;
             const int g = lane >> 2, t = lane & 3;
-            const int k0 = 16 * i + g, k1 = k0 + 8;
+            const int k0 = 16 * i + 2 * g, k1 = k0 + 1;
             const uint32_t m0 = (k0 < P.K) ? P.cw_mask[k0] : 0u, m1 = (k1 < P.K) ? P.cw_mask[k1] : 0u;
             const int c = 16 * ks + 2 * t;
             auto pack = [](uint32_t m, int col) -> uint32_t {
@@ -218,7 +218,11 @@ __device__ __forceinline__ SearchSmem stage_codebook(unsigned char* smem, const 
             };
             s.afrag[e] = make_uint4(pack(m0, c), pack(m1, c), pack(m0, c + 8), pack(m1, c + 8));
         }
-        s.hvals = reinterpret_cast<int16_t*>(s.afrag + n_mt * KS * 32);
+        s.cand_bits = reinterpret_cast<uint32_t*>(s.afrag + n_mt * KS * 32);
+        s.cand_cum = reinterpret_cast<uint16_t*>(s.cand_bits + (SEARCH_THREADS / 32) * n_mt * 16);
+        s.hkeys = reinterpret_cast<uint32_t*>(s.cand_cum + (SEARCH_THREADS / 32) * n_mt * 32);
+        s.masks = s.hkeys + hs;
+        s.hvals = reinterpret_cast<int16_t*>(s.masks + kpad);
         for (int i = threadIdx.x; i < hs; i += SEARCH_THREADS) {
             s.hkeys[i] = P.hash_keys[i];
             s.hvals[i] = P.hash_vals[i];
@@ -250,9 +254,16 @@ __device__ __forceinline__ void load_stack_trace(const T* __restrict__ stack, si
 template <int NB, bool INT_IN>
 __device__ __forceinline__ void finish_trace(const float (&s)[NB], const DecodeParams& P, float (&x)[NB],
                                              float (&xh)[NB], float& mag) {
+    if (INT_IN && P.rcp_all) {
+        // every bit has a guarded reciprocal and integer samples need no operand check: straight-line hot path
 #pragma unroll
-    for (int b = 0; b < NB; ++b)
-        x[b] = (b < P.n_bits) ? scale_clip<INT_IN>(s[b], P.bkg[b], P.nrm[b], P.rcp[b]) : 0.f;
+        for (int b = 0; b < NB; ++b)
+            x[b] = (b < P.n_bits) ? clip01_nan(div_by_rcp(__fsub_rn(s[b], P.bkg[b]), P.nrm[b], P.rcp[b])) : 0.f;
+    } else {
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+            x[b] = (b < P.n_bits) ? scale_clip<INT_IN>(s[b], P.bkg[b], P.nrm[b], P.rcp[b]) : 0.f;
+    }
     const float n = l2_norm<NB>(x);
     mag = unit_vector<NB>(x, n, xh, INT_IN && P.rcp_all);
 }
@@ -408,11 +419,12 @@ __device__ __forceinline__ void coop_search(int src, const DecodeParams& P, cons
 // per-voxel IEEE arithmetic and the exact re-evaluations, not by MMA issue; the warp-level form keeps operands
 // and accumulators in registers with no shared-memory descriptors or TMEM round trip.)
 __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(__fsub_rn(x0, __bfloat162float(h0)));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(__fsub_rn(x1, __bfloat162float(h1)));
-    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    // cvt.rn.bf16x2.f32: both values in one full-rate instruction (the scalar conversion is an XU-pipe F2F each)
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);  // .x (low half) = x0
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xFFFF0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(__fsub_rn(x0, h0), __fsub_rn(x1, h1));
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 __device__ __forceinline__ void mma_bf16_m16n8k16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -435,7 +447,6 @@ __device__ __forceinline__ void mma_mark_candidates_warp(const DecodeParams& P, 
     const unsigned lane = threadIdx.x & 31u;
     const int g = (int)(lane >> 2), t = (int)(lane & 3u);
     const int n_mt = (P.K + 15) >> 4;
-    const int n_words = (P.K + 31) >> 5;
     const float window = M3D_SUM_MARGIN + 2.f * ((float)P.max_on * 1.5259e-5f + 4.0e-6f);
     // B fragments (rows = bits 2t, 2t+1 | 2t+8, 2t+9 of the k step, column = voxel 8 j + g)
     uint32_t bhi[4][KS][2], blo[4][KS][2];
@@ -488,45 +499,164 @@ __device__ __forceinline__ void mma_mark_candidates_warp(const DecodeParams& P, 
             v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
             vmax[j][c] = v - window;  // from here on: the cut
         }
-    // pass 2: the candidate sets, one 32-bit word (= two tiles of 16 codewords) at a time.  Every lane builds the bits
-    // of its own two codeword rows for its eight voxels in registers; the eight lanes that share t (they hold the other
-    // rows of the same voxels) OR them with three shuffles, and the g == 0 lane stores the finished word: no atomics,
-    // no divergent branches, and the sets need no clearing beforehand.  NaN sums compare false: nothing is marked.
-    for (int w = 0; w < n_words; ++w) {
-        uint32_t mk[4][2];
+    // pass 2: the candidate sets.  Every comparison `sum >= cut` goes straight into a warp ballot: bit 4 g + t of the word
+    // for accumulator slot q belongs to lane (g, t), i.e. to codeword row g (q = 0, 1) or g + 8 (q = 2, 3) of tile i and
+    // voxel 8 j + 2 t + (q & 1).  Lane 0 stores the four words of (i, j) with one 128-bit store, ordered {q0, q2, q1, q3}
+    // so that the two words a voxel needs are adjacent.  No shuffles, no atomics, no per-lane bit assembly; the sets need
+    // no clearing beforehand.  NaN sums compare false: nothing is marked.  Padding rows (k >= K) are dropped by the reader.
+    uint4* wb = reinterpret_cast<uint4*>(S.cand_bits) + (size_t)(warp_col0 >> 5) * n_mt * 4;
+    for (int i = 0; i < n_mt; ++i) {
+        uint4 a[KS];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) mk[j][0] = mk[j][1] = 0u;
+        for (int ks = 0; ks < KS; ++ks) a[ks] = af[(i * KS + ks) * 32];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int i = 2 * w + h;
-            if (i < n_mt) {  // uniform
-                uint4 a[KS];
-#pragma unroll
-                for (int ks = 0; ks < KS; ++ks) a[ks] = af[(i * KS + ks) * 32];
-                const uint32_t bit0 = 1u << (16 * h + g), bit1 = bit0 << 8;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float d[4];
-                    sums(a, j, d);
-                    mk[j][0] |= (d[0] >= vmax[j][0] ? bit0 : 0u) | (d[2] >= vmax[j][0] ? bit1 : 0u);
-                    mk[j][1] |= (d[1] >= vmax[j][1] ? bit0 : 0u) | (d[3] >= vmax[j][1] ? bit1 : 0u);
-                }
-            }
+        for (int j = 0; j < 4; ++j) {
+            float d[4];
+            sums(a, j, d);
+            const unsigned q0 = __ballot_sync(0xffffffffu, d[0] >= vmax[j][0]);
+            const unsigned q1 = __ballot_sync(0xffffffffu, d[1] >= vmax[j][1]);
+            const unsigned q2 = __ballot_sync(0xffffffffu, d[2] >= vmax[j][0]);
+            const unsigned q3 = __ballot_sync(0xffffffffu, d[3] >= vmax[j][1]);
+            if (lane == 0) wb[i * 4 + j] = make_uint4(q0, q2, q1, q3);
         }
-        // padding rows (k >= K) have a zero sum, which passes when the cut is <= 0: drop them
-        const uint32_t valid = (w == n_words - 1 && (P.K & 31)) ? ((1u << (P.K & 31)) - 1u) : 0xFFFFFFFFu;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t word = mk[j][c];  // OR over the eight lanes that share t (redux.sync is only fast for full masks)
-                word |= __shfl_xor_sync(0xffffffffu, word, 4);
-                word |= __shfl_xor_sync(0xffffffffu, word, 8);
-                word |= __shfl_xor_sync(0xffffffffu, word, 16);
-                if (g == 0) S.cand_bits[(size_t)(warp_col0 + 8 * j + 2 * t + c) * n_words + w] = word & valid;
-            }
     }
     __syncwarp();
+}
+
+// sqrt(sum_b (xh_b - c_b)^2) for one (voxel, codeword) pair, xh read from the voxel's shared-memory column: the direct
+// form's own operations in its own order (x - 0 = x exactly, so the select moves into the subtrahend)
+template <int NB>
+__device__ __forceinline__ float pair_distance(const float* __restrict__ col, int n_bits, uint32_t mask, float c_val) {
+    float acc = 0.f;
+#pragma unroll
+    for (int b0 = 0; b0 < NB; b0 += 8) {
+        if (b0 < n_bits) {  // uniform; rows n_bits .. NB - 1 hold zeros
+#pragma unroll
+            for (int b = b0; b < b0 + 8; ++b) {
+                const float t = __fsub_rn(col[b * XS_STRIDE], ((mask >> b) & 1u) ? c_val : 0.f);
+                const float term = __fmul_rn(t, t);
+                acc = (b == 0) ? term : __fadd_rn(acc, term);
+            }
+        }
+    }
+    return __fsqrt_rn(acc);
+}
+
+// Exact evaluation of the marked candidates of a warp's 32 voxels, shared by the 32 lanes.  The candidate sets are very
+// uneven (mean ~3 codewords per voxel, ~25 for the unluckiest lane of a warp: clipped traces tie exactly), so instead of
+// every lane walking its own set, the (voxel, codeword) pairs are numbered in voxel order / ascending k and lane p of a
+// round evaluates pair 32 r + p from the voxel's shared-memory column.  Nothing is queued: a pair's voxel comes from a
+// shuffle binary search over the inclusive counts, its tile from a binary search over the voxel's per-tile prefix
+// counts (written by the owner lane while counting), its codeword from a rank select inside the tile's word -- all
+// branch-free.  Lanes holding pairs of the same voxel are adjacent: a segmented shuffle scan keeps the lexicographic
+// (distance, k) minimum (= NumPy's first arg-min) and every owner lane pulls the value of its segment's last lane
+// (a later round only brings larger k: strict improvement only).
+// `active`: this lane's voxel takes part.  Returns the owner's result in d / k (k = -1: nothing was marked).
+template <int NB>
+__device__ __forceinline__ void evaluate_marked_pairs_warp(bool active, const DecodeParams& P, const SearchSmem& S,
+                                                           int warp_col0, float& d_out, int& k_out) {
+    const unsigned lane = threadIdx.x & 31u;
+    const int n_mt = (P.K + 15) >> 4;
+    const uint2* words = reinterpret_cast<const uint2*>(S.cand_bits) + (size_t)(warp_col0 >> 5) * n_mt * 8;
+    uint16_t* cum = S.cand_cum + (size_t)(warp_col0 >> 5) * n_mt * 32;
+    const int rem = P.K - 16 * (n_mt - 1);  // codewords in the last tile: 1 .. 16
+    const uint32_t last_valid = (rem >= 16) ? 0x33333333u
+                                            : ((0x33333333u & ((1u << (4 * (rem >> 1))) - 1u)) |
+                                               ((rem & 1) ? (1u << (4 * (rem >> 1))) : 0u));
+    // candidates of voxel (lane) vx in tile i: bit 4 g <-> codeword 16 i + 2 g, bit 4 g + 1 <-> 16 i + 2 g + 1 (ascending k)
+    auto tile_word = [&](unsigned vx, int i) -> uint32_t {
+        const uint2 q = words[i * 8 + (vx >> 3) * 2 + (vx & 1u)];
+        const unsigned tsh = (vx >> 1) & 3u;
+        const uint32_t w = ((q.x >> tsh) & 0x11111111u) | (((q.y >> tsh) & 0x11111111u) << 1);
+        return (i == n_mt - 1) ? (w & last_valid) : w;
+    };
+    unsigned cnt = 0;
+    for (int i = 0; i < n_mt; ++i) {
+        cum[i * 32 + lane] = (uint16_t)cnt;
+        cnt += __popc(tile_word(lane, i));
+    }
+    if (!active) cnt = 0;
+    unsigned incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += n;
+    }
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned excl = incl - cnt;
+    __syncwarp();
+    int top = 1;  // largest power of two below n_mt (binary search stride)
+    while (2 * top < n_mt) top *= 2;
+    const float* cols = S.xs + warp_col0;
+    float best_d = __int_as_float(0x7f800000);
+    int best_k = -1;
+    for (unsigned q0 = 0; q0 < total; q0 += 32) {
+        const unsigned q = q0 + lane;
+        const bool have = q < total;
+        // voxel of pair q = number of lanes whose inclusive count is <= q (31 at most while q < total)
+        unsigned v = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const unsigned t = __shfl_sync(0xffffffffu, incl, (int)(v + step - 1));
+            if (t <= q) v += step;
+        }
+        v &= 31u;
+        unsigned r = q - __shfl_sync(0xffffffffu, excl, (int)v);  // rank of the pair inside the voxel's set
+        float d = __int_as_float(0x7f800000);
+        int k = 0;
+        if (have) {
+            // tile: the last i with cum[i][v] <= r
+            int ti = 0;
+            for (int step = top; step > 0; step >>= 1) {
+                const int j = ti + step;
+                if (j < n_mt && (unsigned)cum[j * 32 + v] <= r) ti = j;
+            }
+            r -= cum[ti * 32 + v];
+            uint32_t w = tile_word(v, ti);
+            // rank select: position of the r-th set bit (each nibble holds at most two, in bits 0 and 1)
+            int pos = 0;
+            unsigned c = __popc(w & 0xFFFFu);
+            if (r >= c) {
+                pos = 16;
+                r -= c;
+            }
+            c = __popc((w >> pos) & 0xFFu);
+            if (r >= c) {
+                pos += 8;
+                r -= c;
+            }
+            c = __popc((w >> pos) & 0xFu);
+            if (r >= c) {
+                pos += 4;
+                r -= c;
+            }
+            pos += (r >= ((w >> pos) & 1u)) ? 1 : 0;
+            k = 16 * ti + ((pos >> 1) | (pos & 1));
+            d = pair_distance<NB>(cols + v, P.n_bits, S.masks[k], P.cval);
+        }
+        const unsigned vtag = have ? v : 0xFFFFu;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {  // lower lanes of a segment hold lower k: they win ties
+            const float od = __shfl_up_sync(0xffffffffu, d, o);
+            const int ok = __shfl_up_sync(0xffffffffu, k, o);
+            const unsigned ov = __shfl_up_sync(0xffffffffu, vtag, o);
+            if (lane >= (unsigned)o && ov == vtag && od <= d) {
+                d = od;
+                k = ok;
+            }
+        }
+        // owner side: the last lane of my voxel's segment in this round, if it has one
+        const bool mine = cnt != 0u && incl > q0 && excl < q0 + 32u;
+        const unsigned tail = min(incl - 1u - q0, 31u);
+        const float od = __shfl_sync(0xffffffffu, d, (int)(tail & 31u));
+        const int ok = __shfl_sync(0xffffffffu, k, (int)(tail & 31u));
+        if (mine && od < best_d) {
+            best_d = od;
+            best_k = ok;
+        }
+    }
+    d_out = best_d;
+    k_out = best_k;
 }
 
 // nearest codeword for the voxels of one warp; `want` = this lane holds a voxel to search.
@@ -545,62 +675,14 @@ __device__ __forceinline__ void nearest_codeword_warp(bool want, const float (&x
         const int warp_col0 = (int)(threadIdx.x & ~31u);
         if (__popc(pending) > COOP_SWITCH) {
             // dense regime: on-bit sums of all 32 voxels on the tensor cores, exact distance for the settled ones
-            const int n_words = (P.K + 31) >> 5;
-            const uint32_t* my_bits = S.cand_bits + (size_t)threadIdx.x * n_words;
             mma_mark_candidates_warp<NB>(P, S, warp_col0);
-            if (!done) {
-                // exact direct form over the marked set.  Per bit the term is (xh_b - c)^2 when the codeword has the
-                // bit and xh_b^2 otherwise -- both computed once per voxel with the direct form's own operations
-                // (direct_distance_binary), so a candidate costs a select and an add per bit.  The square root is
-                // monotone: a candidate can only beat the running best if its SUM is smaller, and only then are the
-                // two distances compared (equal distance from a smaller sum must not replace the earlier index).
-                float t_on[NB], t_off[NB];
-#pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    const float tt = __fsub_rn(xh[b], P.cval);
-                    t_on[b] = __fmul_rn(tt, tt);
-                    t_off[b] = __fmul_rn(xh[b], xh[b]);
-                }
-                const uint32_t* masks_sh = S.masks;
-                float best_acc = __int_as_float(0x7f800000), best_d = __int_as_float(0x7f800000);
-                int best_k = -1;
-                auto consider = [&](int kk, float acc) {
-                    if (acc < best_acc) {
-                        const float dd = __fsqrt_rn(acc);
-                        if (dd < best_d) {
-                            best_d = dd;
-                            best_k = kk;
-                        }
-                        // keep the smallest sum seen among candidates that did not lose: a later candidate with a sum
-                        // in [acc, best_acc) has distance >= dd >= best_d and cannot win either
-                        best_acc = acc;
-                    }
-                };
-                for (int w = 0; w < n_words; ++w) {
-                    uint32_t bits = my_bits[w];
-                    while (bits) {  // ascending k: a later equal distance never replaces an earlier one
-                        // two candidates per round: each sum is one dependent chain of adds, two chains interleave
-                        const int ka = w * 32 + __ffs(bits) - 1;
-                        bits &= bits - 1u;
-                        const int kb = bits ? (w * 32 + __ffs(bits) - 1) : ka;  // odd count: the same one again (harmless)
-                        bits &= bits - 1u;
-                        const uint32_t ma = masks_sh[ka], mb = masks_sh[kb];
-                        float acc_a = (ma & 1u) ? t_on[0] : t_off[0];
-                        float acc_b = (mb & 1u) ? t_on[0] : t_off[0];
-#pragma unroll
-                        for (int b = 1; b < NB; ++b) {
-                            acc_a = __fadd_rn(acc_a, ((ma >> b) & 1u) ? t_on[b] : t_off[b]);
-                            acc_b = __fadd_rn(acc_b, ((mb >> b) & 1u) ? t_on[b] : t_off[b]);
-                        }
-                        consider(ka, acc_a);
-                        consider(kb, acc_b);
-                    }
-                }
-                if (best_k >= 0) {
-                    k = best_k;
-                    d = best_d;
-                    done = true;
-                }
+            float ed;
+            int ek;
+            evaluate_marked_pairs_warp<NB>(!done, P, S, warp_col0, ed, ek);
+            if (!done && ek >= 0) {
+                k = ek;
+                d = ed;
+                done = true;
             }
             pending = __ballot_sync(0xffffffffu, !done);
             if (__popc(pending) > COOP_SWITCH) {

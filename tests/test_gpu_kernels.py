@@ -231,6 +231,35 @@ def test_decode_all_foreground_worst_case(torch):
     assert (ref["magnitude"].astype(np.float32) >= 0.5).mean() > 0.99
 
 
+@pytest.mark.parametrize("code", ["mhd4_16", "hw4_22_k1000"])
+def test_decode_saturated_traces_every_codeword_ties(torch, code):
+    """Traces whose bits all clip to 1 are equidistant (in exact arithmetic) from EVERY codeword: the tensor-core
+    marking pass hands the whole codebook to the exact evaluation for those voxels, so a warp queues 32 x K
+    (voxel, codeword) pairs -- many times the queue's capacity (chunked evaluation, running minimum carried across
+    chunks) -- and the float32 sequential sums decide among K near-equal distances (first arg-min).  Mixed with
+    partly saturated and ordinary voxels so that queue segments of very different length share rounds."""
+    if code == "mhd4_16":
+        _df, cb = cases.codebook16()
+        nb = 16
+    else:
+        _df, cb = cases.codebook22(n_words=1000, seed=4100)
+        nb = 22
+    rng = np.random.default_rng(77)
+    shape = (2, 24, 64)
+    stack = rng.integers(200, 1400, size=(nb,) + shape).astype(np.uint16)
+    sat = rng.random(shape) < 0.4
+    stack[:, sat] = 60000  # every bit clips to 1
+    part = (~sat) & (rng.random(shape) < 0.3)  # a random subset of bits clips: ties among the codewords inside it
+    hot = rng.random((nb,) + shape) < 0.5
+    stack[hot & part[None]] = 60000
+    bkg, nrm = cases.simple_vectors(nb, seed=9)
+    for dense in (True, False):
+        _c, _s, _d, got, ref = _decode_both(torch, cb, stack, bkg, nrm, mag=(0.5, 10.0), dense=dense)
+        np.testing.assert_array_equal(got["decoded"], ref["decoded"])
+        if dense:
+            _same_f16(got["distance"], ref["distance"], "distance")
+
+
 def test_decode_exclusions_do_not_fall_through(torch):
     _df, cb = cases.codebook16()
     stack = cases.small_stack(cb["matrix"], shape=(6, 40, 40), seed=13)
