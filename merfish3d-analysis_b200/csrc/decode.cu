@@ -551,10 +551,11 @@ __device__ __forceinline__ float pair_distance(const float* __restrict__ col, in
 // branch-free.  Lanes holding pairs of the same voxel are adjacent: a segmented shuffle scan keeps the lexicographic
 // (distance, k) minimum (= NumPy's first arg-min) and every owner lane pulls the value of its segment's last lane
 // (a later round only brings larger k: strict improvement only).
-// `active`: this lane's voxel takes part.  Returns the owner's result in d / k (k = -1: nothing was marked).
+// `active`: this lane's voxel takes part.  Returns the owner's result in d / k (k = -1: nothing was marked) and the
+// size of its candidate set.
 template <int NB>
 __device__ __forceinline__ void evaluate_marked_pairs_warp(bool active, const DecodeParams& P, const SearchSmem& S,
-                                                           int warp_col0, float& d_out, int& k_out) {
+                                                           int warp_col0, float& d_out, int& k_out, unsigned& cnt_out) {
     const unsigned lane = threadIdx.x & 31u;
     const int n_mt = (P.K + 15) >> 4;
     const uint2* words = reinterpret_cast<const uint2*>(S.cand_bits) + (size_t)(warp_col0 >> 5) * n_mt * 8;
@@ -657,28 +658,39 @@ __device__ __forceinline__ void evaluate_marked_pairs_warp(bool active, const De
     }
     d_out = best_d;
     k_out = best_k;
+    cnt_out = cnt;
 }
 
 // nearest codeword for the voxels of one warp; `want` = this lane holds a voxel to search.
-// All 32 lanes must call (warp-synchronous).
+// All 32 lanes must call (warp-synchronous).  `dense_mode` is the warp's memory between calls: while the previous
+// batch went through the tensor-core path and few of its voxels had a single candidate, the top-w attempt (which
+// would fail for most lanes) is skipped and every voxel goes straight to marking + pair evaluation.
 template <int NB>
 __device__ __forceinline__ void nearest_codeword_warp(bool want, const float (&xh)[NB], const DecodeParams& P,
-                                                      const SearchSmem& S, float& d, int& k) {
+                                                      const SearchSmem& S, float& d, int& k, bool& dense_mode) {
     float* col = S.xs + threadIdx.x;
 #pragma unroll
     for (int b = 0; b < NB; ++b) col[b * XS_STRIDE] = xh[b];
     __syncwarp();
     if (P.mode == 2) {
         bool done = !want;
-        if (want) done = topw_lookup<NB>(xh, P, S, d, k);
+        const int n_want = __popc(__ballot_sync(0xffffffffu, want));
+        if (!(dense_mode && n_want > COOP_SWITCH)) {
+            if (want) done = topw_lookup<NB>(xh, P, S, d, k);
+        }
         unsigned pending = __ballot_sync(0xffffffffu, !done);
         const int warp_col0 = (int)(threadIdx.x & ~31u);
+        dense_mode = false;
         if (__popc(pending) > COOP_SWITCH) {
             // dense regime: on-bit sums of all 32 voxels on the tensor cores, exact distance for the settled ones
             mma_mark_candidates_warp<NB>(P, S, warp_col0);
             float ed;
             int ek;
-            evaluate_marked_pairs_warp<NB>(!done, P, S, warp_col0, ed, ek);
+            unsigned n_cand;
+            evaluate_marked_pairs_warp<NB>(!done, P, S, warp_col0, ed, ek, n_cand);
+            // voxels with a single candidate are the ones the top-w attempt settles: keep skipping it while they are few
+            const int n_single = __popc(__ballot_sync(0xffffffffu, !done && n_cand == 1u));
+            dense_mode = (__popc(pending) - n_single) > COOP_SWITCH;
             if (!done && ek >= 0) {
                 k = ek;
                 d = ed;
@@ -728,6 +740,7 @@ decode_search_kernel(const T* __restrict__ stack, size_t n_vox, DecodeParams P, 
     SearchSmem S = stage_codebook<NB>(smem, P);
     const unsigned n = *cand_count;
     const unsigned n_round = (n + 31u) & ~31u;
+    bool dense_mode = false;
     for (unsigned i = blockIdx.x * SEARCH_THREADS + threadIdx.x; i < n_round; i += gridDim.x * SEARCH_THREADS) {
         const bool valid = i < n;
         const size_t v = valid ? cand[i] : 0;
@@ -742,7 +755,7 @@ decode_search_kernel(const T* __restrict__ stack, size_t n_vox, DecodeParams P, 
 #pragma unroll
             for (int b = 0; b < NB; ++b) xh[b] = 0.f;
         }
-        nearest_codeword_warp<NB>(want, xh, P, S, d, k);
+        nearest_codeword_warp<NB>(want, xh, P, S, d, k, dense_mode);
         bool fg = false;
         if (want) {
             const int16_t dec = apply_gates(d, k, mag, P);
@@ -793,6 +806,7 @@ decode_dense_kernel(const T* __restrict__ stack, size_t n_vox, DecodeParams P, i
     extern __shared__ __align__(16) unsigned char smem[];
     SearchSmem S = stage_codebook<NB>(smem, P);
     const size_t n_round = (n_vox + 31u) & ~(size_t)31u;
+    bool dense_mode = false;
     for (size_t v = (size_t)blockIdx.x * SEARCH_THREADS + threadIdx.x; v < n_round;
          v += (size_t)gridDim.x * SEARCH_THREADS) {
         const bool valid = v < n_vox;
@@ -810,7 +824,7 @@ decode_dense_kernel(const T* __restrict__ stack, size_t n_vox, DecodeParams P, i
         bool nan_trace = false;
 #pragma unroll
         for (int b = 0; b < NB; ++b) nan_trace |= !(xh[b] == xh[b]);
-        nearest_codeword_warp<NB>(valid && !nan_trace, xh, P, S, d, k);
+        nearest_codeword_warp<NB>(valid && !nan_trace, xh, P, S, d, k, dense_mode);
         if (valid && nan_trace) {
             d = direct_distance<NB>(xh, P.codebook);
             k = 0;
