@@ -733,7 +733,10 @@ struct FgSink {  // optional hand-off to the labelling / regionprops stages (m3d
 };
 
 template <typename T, int NB>
-__global__ void __launch_bounds__(SEARCH_THREADS, 5)  // 96 registers, 20 warps per SM: -4 % in the dense regime, 6 per SM is slower
+#ifndef M3D_SEARCH_MINB
+#define M3D_SEARCH_MINB 5  // 96 registers, 20 warps per SM
+#endif
+__global__ void __launch_bounds__(SEARCH_THREADS, M3D_SEARCH_MINB)
 decode_search_kernel(const T* __restrict__ stack, size_t n_vox, DecodeParams P, int16_t* __restrict__ decoded,
                      const uint32_t* __restrict__ cand, const unsigned int* __restrict__ cand_count, FgSink sink) {
     extern __shared__ __align__(16) unsigned char smem[];
