@@ -25,7 +25,7 @@ sys.path.insert(0, str(ROOT / "tests" / "golden"))
 
 import cases  # noqa: E402
 import reference_shims as rs  # noqa: E402
-from scenarios import SCENARIOS, scenario_inputs, warp_tile_kwargs  # noqa: E402
+from scenarios import SCENARIOS, scenario_inputs, stack_digest, warp_tile_kwargs  # noqa: E402
 from merfish3d_analysis_b200.datastore import ArrayDataStore  # noqa: E402
 
 OUT = ROOT / "tests" / "golden"
@@ -65,6 +65,10 @@ def run_tile_scenario(name, sc, RefPD):
             excluded=np.array([] if excluded is None else excluded, dtype=str),
             **table_arrays(df),
         )
+        if sc.get("slim"):  # medium volumes: inputs by seed + checksum, no float32 copy / scaled images
+            for k in ("stack", "image", "scaled"):
+                del out[k]
+            out["stack_sha256"] = np.array(stack_digest(stack))
         np.savez_compressed(OUT / f"reference_{name}.npz", **out)
         print(f"{name}: {len(df)} transcripts, {int((out['decoded'] >= 0).sum())} decoded voxels")
     finally:

@@ -45,7 +45,21 @@ SCENARIOS = {
                  z_range=(1, 7)),
     "excl_crop": dict(shape=(9, 32, 40), seed=14, density=6e-3, lowpass=None, norm="global", min_px=3,
                       z_range=(2, 8), exclude=3),
+    # medium volumes (40x the voxels of the others, ~2000 transcripts / 330 k searched voxels): more rare events --
+    # near-ties, touching components, size-filter edge cases.  ``slim``: the fixture stores a checksum of the seeded
+    # input instead of the input, and no float32 copy / scaled images (the decoded, magnitude and distance images and
+    # the table are what pins the path).
+    "raw3d_medium": dict(shape=(16, 128, 160), seed=31, density=5e-3, lowpass=None, norm="global", min_px=4,
+                         origin=(-5.0, 120.0, 40.0), slim=True),
+    "dense16_medium": dict(shape=(16, 128, 160), seed=32, density=1.5e-3, lowpass=None, norm="global", min_px=4,
+                           bkg=195.0, nrm=30.0, nrm_jitter=3.0, mag=(0.05, 10.0), slim=True),
 }
+
+
+def stack_digest(stack) -> str:
+    import hashlib
+
+    return hashlib.sha256(np.ascontiguousarray(stack).tobytes()).hexdigest()
 
 
 

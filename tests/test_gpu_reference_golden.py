@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import cases
-from scenarios import SCENARIOS, scenario_inputs, warp_tile_kwargs
+from scenarios import SCENARIOS, scenario_inputs, stack_digest, warp_tile_kwargs
 from test_cpu_reference_golden import compare_with_reference_table, golden_table
 
 pytestmark = pytest.mark.gpu
@@ -25,7 +25,11 @@ def test_cuda_path_equals_reference_golden(tmp_path, name):
     sc = SCENARIOS[name]
     g = np.load(GOLDEN / f"reference_{name}.npz")
     df_cb, _cb, stack, pred, bkg, nrm, excluded = scenario_inputs(sc)
-    np.testing.assert_array_equal(stack, g["stack"])  # the seeded inputs are the fixture's inputs
+    slim = bool(sc.get("slim"))
+    if slim:  # the seeded inputs are the fixture's inputs
+        assert stack_digest(stack) == str(g["stack_sha256"])
+    else:
+        np.testing.assert_array_equal(stack, g["stack"])
     ds = ArrayDataStore(tmp_path / "qi2labdatastore", codebook=df_cb, microscope_type=sc.get("microscope", "3D"))
     extra = warp_tile_kwargs(sc)[0] if sc.get("warp") else {}
     ds.add_tile(stack, predictors=pred, stage_origin_zyx_um=sc.get("origin"), **extra)
@@ -36,11 +40,12 @@ def test_cuda_path_equals_reference_golden(tmp_path, name):
     dec = PixelDecoder(ds, merfish_bits=int(sc.get("bits", 16)), verbose=0, z_range=sc.get("z_range"), excluded_gene_ids=excluded)
     dec._optimize_normalization_weights = dec._collect_chromatic_centroids = bool(sc.get("chroma"))
     image, scaled, magnitude, distance, decoded = dec.decode_one_tile(0, return_results=True, **kw)
-    np.testing.assert_array_equal(image, g["image"])
+    if not slim:
+        np.testing.assert_array_equal(image, g["image"])
+        np.testing.assert_array_equal(scaled, g["scaled"])
     np.testing.assert_array_equal(decoded, g["decoded"])
     np.testing.assert_array_equal(magnitude, g["magnitude"])
     np.testing.assert_array_equal(distance, g["distance"])
-    np.testing.assert_array_equal(scaled, g["scaled"])
     compare_with_reference_table(dec.decoded_barcodes, ref, rel=REL)
     # production path: gate + search + fused labelling, no result images
     dec2 = PixelDecoder(ds, merfish_bits=int(sc.get("bits", 16)), verbose=0, z_range=sc.get("z_range"), excluded_gene_ids=excluded)

@@ -201,9 +201,11 @@ def test_reference_goldens_from_a_reference_layout_store(tmp_path, name):
                        excluded_gene_ids=excluded)
     dec._optimize_normalization_weights = dec._collect_chromatic_centroids = bool(sc.get("chroma"))
     image, scaled, magnitude, distance, decoded = dec.decode_one_tile(0, return_results=True, **kw)
-    np.testing.assert_array_equal(image, g["image"])
+    if not sc.get("slim"):  # medium fixtures hold a checksum of the input instead of the float32 copy / scaled images
+        np.testing.assert_array_equal(image, g["image"])
+        np.testing.assert_array_equal(scaled, g["scaled"])
     np.testing.assert_array_equal(decoded, g["decoded"])
-    np.testing.assert_array_equal(scaled, g["scaled"])
+    np.testing.assert_array_equal(distance, g["distance"])
     compare_with_reference_table(dec.decoded_barcodes, ref, rel=1e-5)
     launches = dec._ctx(0).launches_by_kernel()
     assert launches.get("zarr_unshuffle_place_kernel", 0) >= stack.shape[0]
