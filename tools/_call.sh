@@ -1,6 +1,8 @@
 cd /root/repo
-python tools/dense_regime.py 2>&1 | tail -1
-M3D_PROBE_MODE=allfg python tools/dense_regime.py 2>&1 | tail -1
-ncu --set full --clock-control none --import-source on -k regex:decode_search -s 1 -c 1 -o gpurun_out/r2_dense_search_v7 -f python tools/dense_regime.py > gpurun_out/dense_ncu.log 2>&1
-M3D_PROBE_MODE=allfg ncu --set full --clock-control none --import-source on -k regex:decode_search -s 1 -c 1 -o gpurun_out/r2_dense_search_v7_allfg -f python tools/dense_regime.py > gpurun_out/dense_ncu2.log 2>&1
-tail -2 gpurun_out/dense_ncu2.log | cut -c1-200
+echo "== full gpu suite"
+( time timeout 1500 python -m pytest tests -x -q -m gpu ) 2>&1 | tail -8
+echo "== smoke"
+timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
+echo "== bench N=1 default"
+( time timeout 1500 python bench.py > gpurun_out/r2_bench_n1_d.json 2> gpurun_out/r2_bench_n1_d.err ) 2>&1 | tail -4
+tail -c 600 gpurun_out/r2_bench_n1_d.json
