@@ -338,26 +338,71 @@ __device__ __forceinline__ uint32_t ordered_key(float v) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-__global__ void __launch_bounds__(256)
-select_hist_kernel(const float* __restrict__ data, size_t n, float sub, int clip0, int pred, float cutoff,
-                   uint32_t prefix_mask, uint32_t prefix_value, int shift, unsigned long long* __restrict__ hist) {
+// One digit histogram of the radix select: 4 bytes per element and pass, so the pass should run at HBM speed -- and the
+// optimiser's percentile seed makes ~26 passes over every filtered bit volume.  The first version (scalar loop, runtime
+// predicate / clip / prefix switches, one shared-memory atomic per element) ran at a third of that: it was bound by its
+// ~20 instructions per element, not by atomics (warp-aggregating them with match.any changed nothing: 231 -> 241 ms for
+// 2 tiles).  Now: the switches are template parameters, loads are 128-bit with two in flight per thread, and
+//   * passes WITH a prefix (digits 2 and 3) only test `(key & mask) == value` per element -- the few matching elements
+//     take the atomic in a rare branch;
+//   * passes WITHOUT a prefix (first digit, counts) count every element: image data lands in a handful of bins there, so
+//     each thread run-length-accumulates its consecutive elements and flushes a run with one atomic.
+template <int PRED, bool CLIP, bool PREFIX>
+__global__ void __launch_bounds__(256, 8)
+select_hist_kernel(const float* __restrict__ data, size_t n, float sub, float cutoff, uint32_t prefix_mask,
+                   uint32_t prefix_value, int shift, unsigned long long* __restrict__ hist) {
     __shared__ unsigned int s_hist[2048];
     for (int i = threadIdx.x; i < 2048; i += 256) s_hist[i] = 0u;
     __syncthreads();
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
-        float v = __fsub_rn(__ldcs(data + i), sub);
-        if (clip0 && v < 0.f) v = 0.f;
+    uint32_t run_bin = 0xFFFFFFFFu, run_len = 0u;  // !PREFIX: the current run of equal bins
+    auto add = [&](float raw) {
+        float v = __fsub_rn(raw, sub);
+        if (CLIP && v < 0.f) v = 0.f;
         bool ok = true;
-        if (pred == 1) ok = v < cutoff;
-        else if (pred == 2) ok = v > cutoff;
-        if (ok) {
-            const uint32_t key = ordered_key(v);
-            if ((key & prefix_mask) == prefix_value) atomicAdd(&s_hist[(key >> shift) & 2047u], 1u);
+        if (PRED == 1) ok = v < cutoff;
+        else if (PRED == 2) ok = v > cutoff;
+        const uint32_t key = ordered_key(v);
+        if (PREFIX) {
+            if (ok && (key & prefix_mask) == prefix_value) atomicAdd(&s_hist[(key >> shift) & 2047u], 1u);
+        } else {
+            const uint32_t bin = ok ? ((key >> shift) & 2047u) : 0xFFFFFFFFu;
+            if (bin == run_bin) {
+                ++run_len;
+            } else {
+                if (run_bin != 0xFFFFFFFFu) atomicAdd(&s_hist[run_bin], run_len);
+                run_bin = bin;
+                run_len = 1u;
+            }
         }
+    };
+    const size_t stride = (size_t)gridDim.x * 256;
+    const size_t tid = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const size_t n4 = ((reinterpret_cast<uintptr_t>(data) & 15u) == 0) ? n / 4 : 0;
+    const float4* data4 = reinterpret_cast<const float4*>(data);
+    size_t i = tid;
+    for (; i + stride < n4; i += 2 * stride) {
+        const float4 q0 = __ldcs(data4 + i), q1 = __ldcs(data4 + i + stride);
+        add(q0.x);
+        add(q0.y);
+        add(q0.z);
+        add(q0.w);
+        add(q1.x);
+        add(q1.y);
+        add(q1.z);
+        add(q1.w);
     }
+    if (i < n4) {
+        const float4 q0 = __ldcs(data4 + i);
+        add(q0.x);
+        add(q0.y);
+        add(q0.z);
+        add(q0.w);
+    }
+    for (size_t j = 4 * n4 + tid; j < n; j += stride) add(__ldcs(data + j));  // unaligned volumes, the last n % 4 elements
+    if (!PREFIX && run_bin != 0xFFFFFFFFu) atomicAdd(&s_hist[run_bin], run_len);
     __syncthreads();
-    for (int i = threadIdx.x; i < 2048; i += 256)
-        if (s_hist[i]) atomicAdd(hist + i, (unsigned long long)s_hist[i]);
+    for (int k = threadIdx.x; k < 2048; k += 256)
+        if (s_hist[k]) atomicAdd(hist + k, (unsigned long long)s_hist[k]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -379,9 +424,30 @@ extern "C" int m3d_select_hist(m3d_ctx* ctx, const float* data_dev, int64_t n, f
     size_t want = ((size_t)n + 255) / 256;
     size_t cap = (size_t)ctx->num_sms * 8;
     int blocks = (int)(want < cap ? want : cap);
-    M3D_LAUNCH(ctx, KF_SELECT_HIST, st,
-               select_hist_kernel<<<blocks, 256, 0, st>>>(data_dev, (size_t)n, sub, clip0, pred, cutoff, prefix_mask,
-                                                          prefix_value, shift, hist_dev));
+    const bool prefix = prefix_mask != 0u;
+    const bool clip = clip0 != 0;
+#define M3D_SELECT_CASE(P_, C_, X_)                                                                                  \
+    if (pred == P_ && clip == C_ && prefix == X_) {                                                                  \
+        M3D_LAUNCH(ctx, KF_SELECT_HIST, st,                                                                           \
+                   (select_hist_kernel<P_, C_, X_><<<blocks, 256, 0, st>>>(data_dev, (size_t)n, sub, cutoff, prefix_mask, \
+                                                                          prefix_value, shift, hist_dev)));          \
+        launched = true;                                                                                             \
+    }
+    bool launched = false;
+    M3D_SELECT_CASE(0, false, false)
+    M3D_SELECT_CASE(0, false, true)
+    M3D_SELECT_CASE(0, true, false)
+    M3D_SELECT_CASE(0, true, true)
+    M3D_SELECT_CASE(1, false, false)
+    M3D_SELECT_CASE(1, false, true)
+    M3D_SELECT_CASE(1, true, false)
+    M3D_SELECT_CASE(1, true, true)
+    M3D_SELECT_CASE(2, false, false)
+    M3D_SELECT_CASE(2, false, true)
+    M3D_SELECT_CASE(2, true, false)
+    M3D_SELECT_CASE(2, true, true)
+#undef M3D_SELECT_CASE
+    if (!launched) return m3d_fail(M3D_ERR_ARG, "m3d_select_hist: pred %d", pred);
     M3D_CHECK_LAUNCH();
     return M3D_OK;
 }

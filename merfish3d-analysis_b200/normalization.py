@@ -65,18 +65,24 @@ class DeviceOrderStats:
             self._reduce(self._hist)
         return self._hist.cpu().numpy()
 
-    def count(self, volumes, sub=0.0, clip0=False, pred=PRED_ALL, cutoffs=None) -> int:
+    def first_digit_histogram(self, volumes, sub=0.0, clip0=False, pred=PRED_ALL, cutoffs=None):
+        """Histogram of the first digit over the whole (predicate-filtered) population: its sum is the population
+        size and it is the first level of any ``select`` over the same population."""
         cutoffs = [0.0] * len(volumes) if cutoffs is None else cutoffs
-        return int(self._pass(volumes, sub, clip0, pred, cutoffs, 0, 0, _SHIFTS[0]).sum())
+        return self._pass(volumes, sub, clip0, pred, cutoffs, 0, 0, _SHIFTS[0])
 
-    def select(self, volumes, ranks, sub=0.0, clip0=False, pred=PRED_ALL, cutoffs=None):
+    def count(self, volumes, sub=0.0, clip0=False, pred=PRED_ALL, cutoffs=None) -> int:
+        return int(self.first_digit_histogram(volumes, sub, clip0, pred, cutoffs).sum())
+
+    def select(self, volumes, ranks, sub=0.0, clip0=False, pred=PRED_ALL, cutoffs=None, first_hist=None):
         """Values at the given 0-based ranks of the pooled, predicate-filtered multiset.  The ranks are walked
         digit by digit TOGETHER: ranks that still share a key prefix (the two middle ranks of a median, the two
-        neighbours of a percentile) share that level's histogram pass over the volumes."""
+        neighbours of a percentile) share that level's histogram pass over the volumes.  ``first_hist``: the
+        population's first-digit histogram when the caller already has it (the count behind a median)."""
         cutoffs = [0.0] * len(volumes) if cutoffs is None else cutoffs
         state = {int(r): [0, 0, int(r)] for r in ranks}  # rank -> [prefix_mask, prefix_value, remaining]
         for shift, width in zip(_SHIFTS, _WIDTHS):
-            hists = {}
+            hists = {} if (first_hist is None or shift != _SHIFTS[0]) else {(0, 0): first_hist}
             for st in state.values():
                 key = (st[0], st[1])
                 if key not in hists:
@@ -120,13 +126,14 @@ class DeviceOrderStats:
 
     def median(self, volumes, sub=0.0, clip0=False, pred=PRED_ALL, cutoffs=None):
         """``np.median`` of the pooled selected float32 values; None when empty."""
-        n = self.count(volumes, sub, clip0, pred, cutoffs)
+        h0 = self.first_digit_histogram(volumes, sub, clip0, pred, cutoffs)  # one pass: the count AND the first level
+        n = int(h0.sum())
         if n == 0:
             return None
         if n % 2 == 1:
-            (v,) = self.select(volumes, [n // 2], sub, clip0, pred, cutoffs)
+            (v,) = self.select(volumes, [n // 2], sub, clip0, pred, cutoffs, first_hist=h0)
             return np.float32(v)
-        a, b = self.select(volumes, [n // 2 - 1, n // 2], sub, clip0, pred, cutoffs)
+        a, b = self.select(volumes, [n // 2 - 1, n // 2], sub, clip0, pred, cutoffs, first_hist=h0)
         # np.median -> np.mean of the two middle float32 values (float32 add, then / 2)
         return np.float32(np.float32(a) + np.float32(b)) / np.float32(2.0)
 

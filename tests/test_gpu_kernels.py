@@ -537,6 +537,22 @@ def test_select_hist_order_statistics(torch):
         [a[None], b[None]], 1, True, lowpass_sigma=None, hot_pixel_threshold=1e30
     )
     assert got[0][0] == nrm[0] and got[1][0] == bkg[0]
+    # the histogram kernel's paths: 128-bit body / scalar tail, volumes that do not start on a 16-byte boundary,
+    # sizes below one warp, values that all fall in ONE first-digit bin (warp-aggregated adds), negatives with and
+    # without the clip, a predicate that rejects almost everything
+    flat = torch.from_numpy(np.concatenate([
+        rng.normal(300.0, 0.01, 70001), -rng.gamma(2.0, 50.0, 5003), np.zeros(17)]).astype(np.float32)).cuda()
+    for off, n in ((0, flat.numel()), (1, 4096), (3, 31), (2, 1), (5, 65536 + 7), (0, 8)):
+        v = flat[off:off + n]
+        h = v.cpu().numpy()
+        for q in (0.0, 10.0, 50.0, 100.0):
+            assert float(stats.percentile(v, q)) == float(np.percentile(h, q)), (off, n, q)
+        assert float(stats.percentile(v, 90.0, sub=250.0, clip0=True)) == float(
+            np.percentile(np.clip(h - np.float32(250.0), 0, None), 90.0)), (off, n)
+        sel = h[h < np.float32(-10.0)]
+        m = stats.median([v], pred=nz.PRED_LT, cutoffs=[-10.0])
+        assert (m is None and sel.size == 0) or float(m) == float(np.median(sel)), (off, n)
+        assert stats.count([v], pred=nz.PRED_GT, cutoffs=[299.99]) == int((h > np.float32(299.99)).sum())
 
 
 def test_centroid_statistics_upstream_known_answer_and_random():

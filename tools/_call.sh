@@ -1,8 +1,10 @@
 cd /root/repo
-echo "== full gpu suite"
-( time timeout 1500 python -m pytest tests -x -q -m gpu ) 2>&1 | tail -8
-echo "== smoke"
-timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
-echo "== bench N=1 default"
-( time timeout 1500 python bench.py > gpurun_out/r2_bench_n1_d.json 2> gpurun_out/r2_bench_n1_d.err ) 2>&1 | tail -4
-tail -c 600 gpurun_out/r2_bench_n1_d.json
+cp merfish3d-analysis_b200/libm3d_b200.so /tmp/lib_new.so
+echo "== old kernel"; cp merfish3d-analysis_b200/build/lib_B.so merfish3d-analysis_b200/libm3d_b200.so; timeout 300 python tools/select_hist_probe.py 2>&1 | tail -5
+echo "== new kernel"; cp /tmp/lib_new.so merfish3d-analysis_b200/libm3d_b200.so; timeout 300 python tools/select_hist_probe.py 2>&1 | tail -5
+timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_reference_golden.py tests/test_gpu_pixeldecoder.py -x -q -m gpu -k "select_hist or optimizer or median or normalization or global" 2>&1 | tail -4
+timeout 900 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --extras optimizer 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); o=d['extras']['optimizer']
+print('total', o['total_s'], 'seed', o['seed_s'], 'it0', o['iteration0']['total_s'], 'steady', o['steady_s_per_iteration'])
+print(o['kernel_ms_whole_run_rank0'])"
