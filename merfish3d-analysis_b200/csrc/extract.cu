@@ -78,19 +78,27 @@ ccl_collect_kernel(const int16_t* __restrict__ decoded, size_t n_vox, int vec, u
 }
 
 // ------------------------------------------------------------------ union-find
-__device__ __forceinline__ uint32_t uf_find(const uint32_t* L, uint32_t a) {
-    uint32_t p = __ldcg(L + a);
+// find for the merge phase: a start node that sat more than one hop from its root is pointed at the root afterwards
+// (atomicMin keeps parents moving towards smaller indices whatever else happens to the node meanwhile).  Sparse
+// production foreground never takes the extra atomic (components of a few dozen voxels, chains of one or two hops);
+// smooth data decoded with noise-level vectors -- the optimiser's first iteration on low-passed tiles -- forms
+// components of millions of voxels whose chains otherwise grow with the component.
+__device__ __forceinline__ uint32_t uf_find_shorten(uint32_t* L, uint32_t a0) {
+    uint32_t a = a0, p = __ldcg(L + a);
+    int hops = 0;
     while (p != a) {
         a = p;
         p = __ldcg(L + a);
+        ++hops;
     }
+    if (hops > 1) atomicMin(L + a0, a);
     return a;
 }
 
 // Playne-Hawick style lock-free union; roots always move towards smaller indices.
 __device__ __forceinline__ void uf_union(uint32_t* L, uint32_t a, uint32_t b) {
-    a = uf_find(L, a);
-    b = uf_find(L, b);
+    a = uf_find_shorten(L, a);
+    b = uf_find_shorten(L, b);
     while (a != b) {
         if (a < b) {
             uint32_t t = a;
@@ -166,15 +174,33 @@ ccl_merge_kernel(const int16_t* __restrict__ decoded, const uint32_t* __restrict
     }
 }
 
+// Roots and areas.  The union phase is over, so a voxel may be pointed straight at its root (plain store: every value a
+// concurrent find can read is an ancestor).  Areas are counted per warp first: lanes that share a root (neighbours in
+// the foreground list usually do, and a component of millions of voxels otherwise sends millions of atomics to ONE
+// address) elect their lowest lane, which adds the group's size.
 __global__ void __launch_bounds__(256)
 ccl_compress_kernel(const uint32_t* __restrict__ fg, const unsigned int* __restrict__ fg_count,
                     uint32_t* __restrict__ parent, uint32_t* __restrict__ aux, uint32_t* __restrict__ root_of) {
     const unsigned n = *fg_count;
-    for (unsigned i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-        const uint32_t v = fg[i];
-        const uint32_t r = uf_find(parent, v);
-        root_of[i] = r;
-        atomicAdd(aux + r, 1u);
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned n_round = ((n + 31u) / 32u) * 32u;
+    for (unsigned i = blockIdx.x * 256 + threadIdx.x; i < n_round; i += gridDim.x * 256) {
+        uint32_t r = 0xFFFFFFFFu;
+        if (i < n) {
+            const uint32_t v = fg[i];
+            uint32_t a = v, p = __ldcg(parent + a);
+            int hops = 0;
+            while (p != a) {
+                a = p;
+                p = __ldcg(parent + a);
+                ++hops;
+            }
+            if (hops > 1) parent[v] = a;
+            r = a;
+            root_of[i] = r;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, r);
+        if (i < n && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(aux + r, (unsigned)__popc(peers));
     }
 }
 
