@@ -395,6 +395,12 @@ def test_weight_kernel(torch):
     p = rng.uniform(0, 1, size=r.shape).astype(np.float32)
     got = ctx.weight(_dev(torch, r), _dev(torch, p)).cpu().numpy()
     np.testing.assert_array_equal(got, orc.weight_readout(r, p))
+    # vector body / scalar tail, no predictor, views that do not start on a 16-byte boundary
+    flat_r, flat_p = _dev(torch, r.ravel()), _dev(torch, p.ravel())
+    for off, n in ((0, 969), (0, 968), (0, 7), (0, 1), (1, 64), (8, 801), (3, 9)):
+        rr, pp = flat_r[off:off + n], flat_p[off:off + n]
+        np.testing.assert_array_equal(ctx.weight(rr, pp).cpu().numpy(), orc.weight_readout(rr.cpu().numpy(), pp.cpu().numpy()))
+        np.testing.assert_array_equal(ctx.weight(rr, None).cpu().numpy(), rr.cpu().numpy().astype(np.float32))
 
 
 def _random_decoded(rng, shape, n_codes=6, fill=0.3):
