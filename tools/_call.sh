@@ -1,14 +1,15 @@
 cd /root/repo
-echo "== full gpu suite"
-( time timeout 1500 python -m pytest tests -x -q -m gpu ) 2>&1 | tail -6
-echo "== smoke"
-timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-echo "== bench N=1 default"
-( time timeout 1500 python bench.py > gpurun_out/r2_bench_n1_e.json 2> gpurun_out/r2_bench_n1_e.err ) 2>&1 | tail -4
-python -c "
+echo "== N=2 bench"
+( time timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2_bench_n2_b.json 2> gpurun_out/r2_bench_n2_b.err ) 2>&1 | tail -3
+python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/r2_bench_n1_e.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'])"
-echo "== launch list"
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'decode_|ccl_|features_|reset_foreground|DeviceRadixSort|DeviceScan' -c 400 --csv --log-file gpurun_out/r2_launches_cfg2.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-extras > gpurun_out/ncu1.log 2>&1
-tail -2 gpurun_out/ncu1.log | cut -c1-200
+txt=open('gpurun_out/r2_bench_n2_b.json').read().strip().splitlines()
+d=json.loads([l for l in txt if l.startswith('{')][-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['n_gpus'])
+o=d['extras']['optimizer']; print('opt total', o['total_s'], 'seed', o['seed_s'], 'it0', o['iteration0']['total_s'], 'steady', o['steady_s_per_iteration'], o['exchange'])
+z=d['extras']['zslab']; print('zslab', z['s_per_volume'], z['gvoxel_per_s'], z.get('identical_to_unsharded'))
+PY
+echo "== dist smoke"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/dist_smoke.py 2>&1 | tail -5
+echo "== 2-GPU test"
+timeout 600 python -m pytest tests -x -q -m gpu -k "two_gpu or 2gpu or multi_gpu or devices" 2>&1 | tail -3

@@ -15,9 +15,14 @@ from scenarios import SCENARIOS, scenario_inputs, synthetic_transcript_table, wa
 from merfish3d_analysis_b200.datastore import ArrayDataStore  # noqa: E402
 from merfish3d_analysis_b200.PixelDecoder import PixelDecoder  # noqa: E402
 
+import os
+
+# M3D_SANITIZE_DENSE_ONLY=1: only the dense-candidate scenarios (tensor-core marking + warp-shared pair evaluation), small
+# enough for `compute-sanitizer --tool racecheck`
+DENSE_ONLY = os.environ.get("M3D_SANITIZE_DENSE_ONLY", "0") == "1"
 tmp = Path(tempfile.mkdtemp())
 n = 0
-for name in ("raw3d", "lp3d", "mode2d", "chroma", "bits22", "warp"):
+for name in (() if DENSE_ONLY else ("raw3d", "lp3d", "mode2d", "chroma", "bits22", "warp")):
     sc = SCENARIOS[name]
     df_cb, _cb, stack, pred, bkg, nrm, excluded = scenario_inputs(sc)
     ds = ArrayDataStore(tmp / name, codebook=df_cb, microscope_type=sc.get("microscope", "3D"))
@@ -58,6 +63,9 @@ for name in ("bits22_k385_dense", "bits22_k1000_dense", "dense16"):
     dec.decode_one_tile(0, **kw)
     n += len(dec.decoded_barcodes)
     dec._cleanup()
+if DENSE_ONLY:
+    print("sanitize_small (dense only): transcripts", n)
+    sys.exit(0)
 ds = ArrayDataStore(tmp / "opt", codebook=df_cb)
 for k in range(3):
     ds.add_tile(cases.small_stack(cb["matrix"], shape=(8, 40, 48), seed=300 + k, density=5e-3))
