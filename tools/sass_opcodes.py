@@ -15,7 +15,7 @@ for part in txt.split("Function : ")[1:]:
     name = part.split("\n", 1)[0].strip()
     ops = collections.Counter()
     for line in part.split("\n"):
-        m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
+        m = re.search(r"/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
         if m:
             ops[m.group(1)] += 1
     kernels[name] = ops
