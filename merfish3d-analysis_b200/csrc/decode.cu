@@ -411,10 +411,11 @@ __device__ __forceinline__ void coop_search(int src, const DecodeParams& P, cons
 // into bf16 hi + lo parts (M is exact in bf16), so |S~ - S| <= w * 2^-16 + accumulation noise =: eps.
 // The MMA result never decides: pass 1 finds each voxel's largest S~, pass 2 recomputes the tiles and MARKS
 // every codeword with S~ >= max - (M3D_SUM_MARGIN + 2 eps) -- a superset of the codewords coop_search would
-// re-evaluate -- in a per-voxel bit set in shared memory; each lane then walks the set of its own voxel with
-// the exact float32 direct form on its register copy of the trace, keeping the lexicographic (d, k) minimum
-// = NumPy's first arg-min.  Clipped traces make exact ties among a dozen codewords common (noise-level
-// normalisation saturates many bits at 1), so the candidate set really is a set, not a single winner.
+// re-evaluate -- as warp-ballot words in shared memory; the warp then evaluates the marked (voxel, codeword) pairs
+// with the exact float32 direct form, one pair per lane and round (evaluate_marked_pairs_warp), keeping every
+// voxel's lexicographic (d, k) minimum = NumPy's first arg-min.  Clipped traces make exact ties among a dozen
+// codewords common (noise-level normalisation saturates many bits at 1), so the candidate set really is a set,
+// not a single winner -- and a very uneven one, which is why the pairs are shared out over the lanes.
 // (tcgen05 / TMEM is not warranted here: the contraction is only 16-32 deep and the kernel is bound by the
 // per-voxel IEEE arithmetic and the exact re-evaluations, not by MMA issue; the warp-level form keeps operands
 // and accumulators in registers with no shared-memory descriptors or TMEM round trip.)
@@ -434,13 +435,14 @@ __device__ __forceinline__ void mma_bf16_m16n8k16(float (&d)[4], const uint32_t 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// For the 32 voxels whose unit traces sit in this warp's xs columns: write into S.cand_bits the set of codewords that
-// can be the exact arg-min (empty for NaN traces).  All lanes must call.
+// For the 32 voxels whose unit traces sit in this warp's xs columns: write into S.cand_bits (ballot words, layout at
+// pass 2 below) the set of codewords that can be the exact arg-min (empty for NaN traces).  All lanes must call.
 //
 // Roles in D = A . B (m16n8k16): A = 16 codewords x 16 bits of the on-bit matrix (exact in bf16; the fragments are
 // precomputed once per block, S.afrag: one 128-bit shared-memory load per tile), B = 16 bits x 8 voxels (the traces,
 // bf16 hi + lo, built once per 32 voxels and kept in registers), D = on-bit sums of 16 codewords x 8 voxels.  Lane
-// (g, t) then holds codewords 16 i + g, 16 i + g + 8 for voxels 8 j + 2t, 8 j + 2t + 1.
+// (g, t) then holds codewords 16 i + 2 g, 16 i + 2 g + 1 (fragment rows g, g + 8: see stage_codebook) for voxels
+// 8 j + 2t, 8 j + 2t + 1.
 template <int NB>
 __device__ __forceinline__ void mma_mark_candidates_warp(const DecodeParams& P, const SearchSmem& S, int warp_col0) {
     constexpr int KS = (NB + 15) / 16;
