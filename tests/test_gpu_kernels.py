@@ -305,7 +305,10 @@ def test_decode_non_binary_codebook_generic_path(torch):
     _same_f16(got["distance"], ref["distance"], "distance")
 
 
-@pytest.mark.parametrize("shape", [(5, 33, 47), (30, 40, 72), (2, 8, 8)])
+@pytest.mark.parametrize("shape", [(5, 33, 47), (30, 40, 72), (2, 8, 8),
+                                   # several tile rows / columns: partial last tile column, a single tile reflected on
+                                   # both sides, a last tile row of one line
+                                   (3, 200, 130), (2, 97, 40), (4, 131, 57), (2, 330, 64), (1, 68, 113)])
 @pytest.mark.parametrize("mode2d", [False, True])
 def test_lowpass_matches_scipy_bit_exact(torch, shape, mode2d):
     _df, cb = cases.codebook16()
