@@ -260,6 +260,30 @@ def test_decode_saturated_traces_every_codeword_ties(torch, code):
             _same_f16(got["distance"], ref["distance"], "distance")
 
 
+@pytest.mark.parametrize("n_words", [3, 15, 16, 17, 33, 49])
+def test_decode_dense_regime_small_and_ragged_codebooks(torch, n_words):
+    """Dense-candidate regime with codebooks whose size is not a multiple of the 16-codeword MMA tile (a last tile of one
+    row, exactly one tile, fewer rows than a tile): the padding rows of the fragment table have a zero on-bit sum and
+    must never be handed to the exact evaluation, the per-tile prefix counts / rank select must address the right
+    codeword.  Noise-level vectors: every voxel is a candidate, exact ties are common."""
+    from merfish3d_analysis_b200 import synthetic
+
+    m = synthetic.mhd4_codebook_matrix(16)[:n_words]
+    df = synthetic.codebook_dataframe(m, n_blank=min(2, n_words - 1))
+    cb = orc.load_codebook(df, 16)
+    rng = np.random.default_rng(100 + n_words)
+    stack = rng.integers(150, 260, size=(16, 3, 40, 64)).astype(np.uint16)
+    stack[:, rng.random((3, 40, 64)) < 0.1] = 0  # all-zero traces: zero norm, every on-bit sum 0
+    bkg = (187.0 + rng.uniform(-3, 3, 16)).astype(np.float32)
+    nrm = (17.0 + rng.uniform(-2, 2, 16)).astype(np.float32)
+    for dense in (True, False):
+        _c, _s, _d, got, ref = _decode_both(torch, cb, stack, bkg, nrm, mag=(0.05, 10.0), dense=dense)
+        np.testing.assert_array_equal(got["decoded"], ref["decoded"])
+        if dense:
+            _same_f16(got["distance"], ref["distance"], "distance")
+    assert (ref["decoded"] >= 0).mean() > 0.005
+
+
 def test_decode_exclusions_do_not_fall_through(torch):
     _df, cb = cases.codebook16()
     stack = cases.small_stack(cb["matrix"], shape=(6, 40, 40), seed=13)
