@@ -246,6 +246,16 @@ int m3d_features(m3d_ctx* ctx, const void* stack_dev, int dtype, const int64_t d
 int m3d_select_hist(m3d_ctx* ctx, const float* data_dev, int64_t n, float sub, int clip0,
                     int pred, float cutoff, uint32_t prefix_mask, uint32_t prefix_value,
                     int shift, unsigned long long* hist_dev, void* stream);
+/* Several digit histograms in ONE launch: the optimiser's per-iteration statistic (PD:1290-1356: per-bit medians of
+ * on-bit / off-bit mean intensities) walks 2 x bits small multisets together, one histogram per multiset and level.
+ * Query q adds the histogram of data[q][0 .. n[q]) -- keys with (key & prefix_mask[q]) == prefix_value[q], digit
+ * (key >> shift) & 2047 -- to hist_dev + 2048 * q.  The four arrays are HOST arrays of n_queries entries; entries with
+ * n == 0 are skipped (data may be NULL).  No predicate, no subtraction; NaN values are "no entry" and are not counted
+ * (pandas' median(skipna=True) of the reference's sparse frames), so a multiset may be handed over as a dense column
+ * with NaN in the rows that do not belong to it. */
+int m3d_select_hist_batch(m3d_ctx* ctx, int n_queries, const float* const* data_dev, const int64_t* n,
+                          const uint32_t* prefix_mask, const uint32_t* prefix_value, int shift,
+                          unsigned long long* hist_dev, void* stream);
 /* hot-pixel replacement (PD:1072-1074): data[data > threshold] = value, in place. */
 int m3d_replace_above(m3d_ctx* ctx, float* data_dev, int64_t n, float threshold, float value,
                       void* stream);

@@ -1870,10 +1870,12 @@ class PixelDecoder:
                 out[c] = pooled[:, nb + 5 + i].astype(np.int64) if c == "tile_idx" else pooled[:, nb + 5 + i]
         return out
 
-    def _device_row_queries(self, rows, device):
+    def _device_row_queries(self, rows, device, nan_padded: bool = False):
         """The 2 x bits multisets of ``_norm.iterative_vector_queries`` built from the feature tables as they sit on the
         device: ``rows`` = [(per-bit means float32 (n, bits), codeword index int64 (n,)), ...] of this rank's tiles.
-        Blank-ness and the four 'on' bits are properties of the codeword (PD:3101: ``argsort(~codebook)[:, :4]``)."""
+        Blank-ness and the four 'on' bits are properties of the codeword (PD:3101: ``argsort(~codebook)[:, :4]``).
+        ``nan_padded``: every multiset is a dense (n_rows,) column with NaN where the row does not belong to it (what
+        ``m3d_select_hist_batch`` skips) -- two ``where`` instead of 2 x bits boolean selections with a host sync each."""
         import torch
 
         nb = self._n_merfish_bits
@@ -1893,6 +1895,11 @@ class PixelDecoder:
         keep = ~blank[dec]
         vals, dec = vals[keep], dec[keep]
         on = on_mask[dec]
+        if nan_padded:
+            nanv = torch.full_like(vals, float("nan"))
+            q_on = torch.where(on, vals, nanv).t().contiguous()
+            q_off = torch.where(~on, vals, nanv).t().contiguous()
+            return [q_on[j] for j in range(nb)] + [q_off[j] for j in range(nb)], int(vals.shape[0]), n_rows
         finite = ~torch.isnan(vals)
         queries = [vals[:, j][on[:, j] & finite[:, j]].contiguous() for j in range(nb)]
         queries += [vals[:, j][~on[:, j] & finite[:, j]].contiguous() for j in range(nb)]
@@ -1920,11 +1927,13 @@ class PixelDecoder:
 
             def hist_fn(data, row, pm, pv, sh):
                 ctx.select_hist(data, row, prefix_mask=pm, prefix_value=pv, shift=sh)
+
+            hist_batch_fn = ctx.select_hist_batch  # a whole level of the 2 x bits medians in one launch
         else:
-            device, hist_fn = torch.device("cpu"), backend
+            device, hist_fn, hist_batch_fn = torch.device("cpu"), backend, None
         queries, kept, foreign = None, 0, 0
         if device_rows is not None:  # the tables never left the device (3-D optimiser iterations)
-            queries, kept, n_local = self._device_row_queries(device_rows, device)
+            queries, kept, n_local = self._device_row_queries(device_rows, device, nan_padded=hist_batch_fn is not None)
         else:
             n_local = len(local)
             has_cols = len(local.columns) > 0 and "gene_id" in local.columns and any(
@@ -1953,7 +1962,7 @@ class PixelDecoder:
 
         med = _norm.pooled_medians(queries, hist_fn,
                                    lambda rows: torch.zeros((rows, 2048), dtype=torch.int64, device=device),
-                                   reduce if multi else None)
+                                   reduce if multi else None, hist_batch_fn=hist_batch_fn)
         return _norm.finish_iterative_vectors(med[:nb], med[nb:]), n_pooled
 
     def optimize_normalization_by_decoding(

@@ -111,6 +111,11 @@ SIGNATURES = {
         [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_int, C.c_int, C.c_float,
          C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p],
     ),
+    "m3d_select_hist_batch": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_uint32),
+         C.POINTER(C.c_uint32), C.c_int, C.c_void_p, C.c_void_p],
+    ),
     "m3d_replace_above": (
         C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p]
     ),
@@ -663,6 +668,23 @@ class DecodeContext:
                 _stream(self.device),
             ),
             "m3d_select_hist",
+        )
+
+    def select_hist_batch(self, rows, hist, shift: int):
+        """One launch for a whole level of a multi-query radix select: ``rows`` = list of
+        ``(data tensor, prefix_mask, prefix_value)``; row r's digit histogram is added to ``hist[r]``
+        (``hist``: zeroed (len(rows), 2048) int64 device tensor).  NaN values are not counted."""
+        n = len(rows)
+        if n == 0:
+            return
+        ptrs = (C.c_void_p * n)(*[(_ptr(d) if d.numel() else None) for d, _pm, _pv in rows])
+        sizes = (C.c_int64 * n)(*[int(d.numel()) for d, _pm, _pv in rows])
+        pms = (C.c_uint32 * n)(*[int(pm) & 0xFFFFFFFF for _d, pm, _pv in rows])
+        pvs = (C.c_uint32 * n)(*[int(pv) & 0xFFFFFFFF for _d, _pm, pv in rows])
+        _check(
+            self._lib.m3d_select_hist_batch(self._h, n, ptrs, sizes, pms, pvs, int(shift), _ptr(hist),
+                                            _stream(self.device)),
+            "m3d_select_hist_batch",
         )
 
     def replace_above(self, data, threshold: float, value: float):

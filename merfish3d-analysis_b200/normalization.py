@@ -220,13 +220,15 @@ def _numpy_hist_backend(data, hist_row, prefix_mask, prefix_value, shift):
     hist_row += torch.from_numpy(h)
 
 
-def pooled_medians(queries, hist_fn, new_hist, reduce=None):
+def pooled_medians(queries, hist_fn, new_hist, reduce=None, hist_batch_fn=None):
     """``np.median`` of each query's values pooled over all ranks, without gathering them.
 
     ``queries``: list of 1-D float32 tensors (this rank's part of every multiset; may be empty).
     ``hist_fn(data, hist_row, prefix_mask, prefix_value, shift)`` adds the 2048-bin digit histogram of ``data``'s
     keys into ``hist_row`` (``DecodeContext.select_hist`` on the device); ``new_hist(rows)`` allocates a zeroed
     ``(rows, 2048)`` int64 tensor; ``reduce(hist)`` sums it in place over the process group (``all_reduce``).
+    ``hist_batch_fn(rows, hist, shift)`` (optional; ``DecodeContext.select_hist_batch``) fills all rows of one round with
+    ONE launch -- ``rows`` = list of ``(data, prefix_mask, prefix_value)`` -- instead of one ``hist_fn`` call per row.
 
     Three rounds, each ONE collective and ONE device-to-host copy for all queries together: the first digit's
     histograms (which also give the pooled counts), then the second and third digit of the one or two middle
@@ -241,9 +243,12 @@ def pooled_medians(queries, hist_fn, new_hist, reduce=None):
     def run(rows):
         """rows: list of (query index, prefix_mask, prefix_value, shift) -> (len(rows), 2048) host histograms"""
         hist = new_hist(len(rows))
-        for r, (q, pm, pv, sh) in enumerate(rows):
-            if queries[q].numel():
-                hist_fn(queries[q], hist[r], pm, pv, sh)
+        if hist_batch_fn is not None and rows:
+            hist_batch_fn([(queries[q], pm, pv) for q, pm, pv, _sh in rows], hist, rows[0][3])  # one shift per round
+        else:
+            for r, (q, pm, pv, sh) in enumerate(rows):
+                if queries[q].numel():
+                    hist_fn(queries[q], hist[r], pm, pv, sh)
         if reduce is not None:
             reduce(hist)
         return hist.cpu().numpy()

@@ -324,6 +324,18 @@ def test_pooled_medians_equal_numpy_median():
         else:
             want = float(np.median(a.astype(np.float64)))
             assert g == want or (np.isnan(g) and np.isnan(want)), (a[:5], g, want)
+    # the batched backend (one call per round: DecodeContext.select_hist_batch on the device) walks the same digits
+    calls = []
+
+    def batch_fn(rows, hist, shift):
+        calls.append(len(rows))
+        for r, (data, pm, pv) in enumerate(rows):
+            if data.numel():
+                hist_fn(data, hist[r], pm, pv, shift)
+
+    got_b = nm.pooled_medians([torch.from_numpy(a.copy()) for a in sets], None, new_hist, hist_batch_fn=batch_fn)
+    assert len(calls) == 3 and calls[0] == len(sets)
+    assert all((g == h) or (np.isnan(g) and np.isnan(h)) for g, h in zip(got, got_b))
 
 
 def test_pooled_medians_over_ranks_equal_the_pooled_median():

@@ -588,6 +588,55 @@ def test_select_hist_order_statistics(torch):
         assert stats.count([v], pred=nz.PRED_GT, cutoffs=[299.99]) == int((h > np.float32(299.99)).sum())
 
 
+def test_select_hist_batch_equals_single_launches(torch):
+    """m3d_select_hist_batch (a whole level of the optimiser's 2 x bits medians in one launch) fills the same rows as one
+    m3d_select_hist launch per multiset -- empty multisets, more rows than one parameter block holds, every level's prefix
+    -- and the medians built on it are np.median's."""
+    from merfish3d_analysis_b200 import normalization as nm
+
+    _df, cb = cases.codebook16()
+    ctx, _ = _ctx(cb)
+    rng = np.random.default_rng(88)
+    sets = [rng.gamma(2.0, 200.0, int(n)).astype(np.float32) for n in rng.integers(0, 5000, 150)]
+    sets[3] = np.float32([])
+    sets[5] = np.float32([7.5])
+    sets[9] = -sets[9]
+    dev = [_dev(torch, a) for a in sets]
+    for shift, mask_bits in ((21, 0), (10, 11), (0, 22)):
+        rows = []
+        for a, d in zip(sets, dev):
+            pm = (0xFFFFFFFF << (32 - mask_bits)) & 0xFFFFFFFF if mask_bits else 0
+            key = 0
+            if a.size and mask_bits:
+                u = np.array([a[a.size // 2]], np.float32).view(np.uint32)[0]
+                key = int(~u & 0xFFFFFFFF) if (u & 0x80000000) else int(u | 0x80000000)
+            rows.append((d, pm, key & pm))
+        hb = torch.zeros((len(rows), 2048), dtype=torch.int64, device="cuda")
+        ctx.select_hist_batch(rows, hb, shift)
+        hs = torch.zeros((len(rows), 2048), dtype=torch.int64, device="cuda")
+        for r, (d, pm, pv) in enumerate(rows):
+            if d.numel():
+                ctx.select_hist(d, hs[r], prefix_mask=pm, prefix_value=pv, shift=shift)
+        torch.cuda.synchronize()
+        assert torch.equal(hb, hs), shift
+        if mask_bits == 0:
+            assert hb.sum(1).cpu().tolist() == [a.size for a in sets]
+    got = nm.pooled_medians(dev, None, lambda n: torch.zeros((n, 2048), dtype=torch.int64, device="cuda"),
+                            hist_batch_fn=ctx.select_hist_batch)
+    for a, g in zip(sets, got):
+        assert (np.isnan(g) and a.size == 0) or g == float(np.median(a.astype(np.float64)))
+    # NaN = "no entry": a multiset handed over as a dense column with NaN in the rows that do not belong to it
+    padded = []
+    for a in sets[:40]:
+        col = np.full(a.size + 37, np.nan, dtype=np.float32)
+        col[rng.permutation(col.size)[: a.size]] = a
+        padded.append(_dev(torch, col))
+    got = nm.pooled_medians(padded, None, lambda n: torch.zeros((n, 2048), dtype=torch.int64, device="cuda"),
+                            hist_batch_fn=ctx.select_hist_batch)
+    for a, g in zip(sets[:40], got):
+        assert (np.isnan(g) and a.size == 0) or g == float(np.median(a.astype(np.float64)))
+
+
 def test_centroid_statistics_upstream_known_answer_and_random():
     """m3d_centroid_statistics against the reference's own known-answer case
     (tests/test_optimization_codeword_exclusions.py:153-205) and the oracle on a random volume."""
