@@ -396,3 +396,56 @@ def test_iterative_vector_queries_match_the_dataframe_statistic():
     df2 = df.copy()
     df2.loc[0, "bit01_mean_intensity"] = 0.1  # not representable in float32
     assert nm.iterative_vector_queries(df2, 16, torch.device("cpu"))[0] is None
+
+
+def test_device_row_queries_nan_padded_equal_the_compacted_multisets(tmp_path):
+    """The optimiser's per-iteration multisets built from the device tables (per-bit means + codeword index): the dense
+    NaN-padded columns handed to m3d_select_hist_batch hold exactly the values of the compacted selections, and the
+    medians taken from them (NaN = no entry) are the pandas statistic of the reference's loop (PD:1290-1368)."""
+    import torch
+
+    import cases
+    from merfish3d_analysis_b200 import normalization as nm
+    from merfish3d_analysis_b200.datastore import ArrayDataStore
+    from merfish3d_analysis_b200.PixelDecoder import PixelDecoder
+
+    df_cb, cb = cases.codebook16()
+    ds = ArrayDataStore(tmp_path / "qi2labdatastore", codebook=df_cb)
+    ds.add_tile(np.zeros((16, 2, 8, 8), dtype=np.uint16))
+    dec = PixelDecoder(ds, merfish_bits=16, verbose=0)
+    rng = np.random.default_rng(17)
+    rows = []
+    for n in (700, 0, 1300):
+        vals = rng.gamma(2.0, 120.0, (n, 16)).astype(np.float32)
+        if n:
+            vals[rng.integers(0, n, 9), rng.integers(0, 16, 9)] = np.nan  # a mean that is not a number: no entry
+        rows.append((torch.from_numpy(vals), torch.from_numpy(rng.integers(0, len(dec._gene_ids), n).astype(np.int64))))
+    rows.append(None)
+    cpu = torch.device("cpu")
+    q_c, kept_c, n_c = dec._device_row_queries(rows, cpu)
+    q_p, kept_p, n_p = dec._device_row_queries(rows, cpu, nan_padded=True)
+    assert (kept_c, n_c) == (kept_p, n_p) and len(q_c) == len(q_p) == 32 and n_c == 2000
+    for a, b in zip(q_c, q_p):
+        assert b.is_contiguous() and b.numel() == kept_p
+        np.testing.assert_array_equal(np.sort(a.numpy()), np.sort(b.numpy()[~np.isnan(b.numpy())]))
+    # medians: batch restatement that skips NaN like the kernel, against the DataFrame statistic
+    hist_fn, new_hist = _host_hist_backend()
+
+    def batch_fn(items, hist, shift):
+        for r, (data, pm, pv) in enumerate(items):
+            d = data[~torch.isnan(data)]
+            if d.numel():
+                hist_fn(d, hist[r], pm, pv, shift)
+
+    med = nm.pooled_medians(q_p, None, new_hist, hist_batch_fn=batch_fn)
+    got = nm.finish_iterative_vectors(med[:16], med[16:])
+    vals = torch.cat([r[0] for r in rows if r is not None]).numpy()
+    words = torch.cat([r[1] for r in rows if r is not None]).numpy()
+    on = np.argsort(~dec._codebook_matrix.astype(bool), axis=1)[:, :4] + 1
+    df = pd.DataFrame({f"bit{i + 1:02d}_mean_intensity": vals[:, i].astype(np.float64) for i in range(16)})
+    df["gene_id"] = [dec._gene_ids[w] for w in words]
+    for k in range(4):
+        df[f"on_bit_{k + 1}"] = on[words, k]
+    want = nm.iterative_normalization_vectors(df, 16)
+    np.testing.assert_array_equal(got[0], want[0])
+    np.testing.assert_array_equal(got[1], want[1])
